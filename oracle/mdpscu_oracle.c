@@ -1,0 +1,1042 @@
+/*
+ * mdpscu_oracle.c -- CPU restatement of the MDPSCU tabulated EAM/FS hot path.
+ * TEST INFRASTRUCTURE ONLY (see mdpscu_oracle.h).  Compile with -ffp-contract=off:
+ * the restatement is defined as un-fused arithmetic in the reference's source order.
+ *
+ * Reference paths are relative to the reference root (MDLIB/sor/... is abbreviated
+ * to its last two components where unambiguous).
+ */
+#include "mdpscu_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int orc_get_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* =====================================================================================
+ * Potentials
+ * ===================================================================================== */
+
+/* Cubic-knot sum  sum_k a_k (r_k - r)^3 H(r_k - r)  and  sum_k a_k (r_k - r)^2 H(r_k - r).
+ * Common/MD_Pot_EAM_Utilities.F90:35-44 (H: x>=0 -> 1), :72-79 / :280-287 (the loop,
+ * products in source order a*(d)*(d)*(d)). r and knots in Angstrom. */
+static void knot_sum(double r, const double *a, const double *rk, int n, double *s3, double *s2)
+{
+    double p = 0.0, f = 0.0;
+    for (int i = 0; i < n; i++) {
+        double d = rk[i] - r;
+        double stp = (d >= 0.0) ? 1.0 : 0.0;
+        p = p + a[i] * d * d * d * stp;
+        f = f + a[i] * d * d * stp;
+    }
+    *s3 = p;
+    *s2 = f;
+}
+
+/* NN_FuncPoly3, Common/MD_Pot_EAM_Utilities.F90:48-85: returns 0.5*V [erg], -dV/dr [erg/cm] */
+static void nn_poly3(double r_ang, const double *a, const double *rk, int n, double *potr, double *fpotr)
+{
+    double p, f;
+    knot_sum(r_ang, a, rk, n, &p, &f);
+    *potr = 0.5 * p * ORC_EVERG;
+    *fpotr = 3.0 * f * ORC_EVERG / ORC_A2CM;
+}
+
+/* RHO_FuncPoly3, :259-290: rho (dimensionless), -drho/dr [1/cm] */
+static void rho_poly3(double r_ang, const double *a, const double *rk, int n, double *potb, double *fpotb)
+{
+    double p, f;
+    knot_sum(r_ang, a, rk, n, &p, &f);
+    *potb = p;
+    *fpotb = 3.0 * f / ORC_A2CM;
+}
+
+/* EMBED_FS_PLOY_Func, :332-368: F = A1 sqrt(rho) + A2 rho^2 + ... [erg] */
+static void embed_fs_poly(double rho, const double *a, int n, double *frho, double *dfrho)
+{
+    double fr, dfr;
+    if (rho <= 0.0) {
+        fr = 0.0;
+        dfr = 0.0;
+    } else {
+        double trho = rho;
+        fr = a[0] * sqrt(trho);
+        dfr = 0.5 * a[0] / sqrt(trho);
+        for (int i = 2; i <= n; i++) {
+            fr = fr + a[i - 1] * rho * trho;
+            dfr = dfr + (double)i * a[i - 1] * trho;
+            trho = rho * trho;
+        }
+    }
+    *frho = fr * ORC_EVERG;
+    *dfrho = dfr * ORC_EVERG;
+}
+
+/* ---- Marinica EAM2 W-W. Potentials/EAM_WW_Marinica_JPCM25_2013/EAM2_WW_Marinica_JPCM25_2013.F90:17-116.
+ * Coefficients are D-exponent (double) literals; KNOTS are default-REAL literals in the
+ * Fortran source (:42-56, :80-83) i.e. rounded to float32 then widened -- hence the f suffixes. */
+static const double MAR2_A[15] = {
+    0.960851701343041e2, -0.184410923895214e3, 0.935784079613550e2, -0.798358265041677e1,
+    0.747034092936229e1, -0.152756043708453e1, 0.125205932634393e1, 0.163082162159425e1,
+    -0.141854775352260e1, -0.819936046256149e0, 0.198013514305908e1, -0.696430179520267e0,
+    0.304546909722160e-1, -0.163131143161660e1, 0.138409896486177e1};
+static const double MAR2_R[15] = {
+    2.564897500000000f, 2.629795000000000f, 2.694692500000000f, 2.866317500000000f,
+    2.973045000000000f, 3.079772500000000f, 3.516472500000000f, 3.846445000000000f,
+    4.176417500000000f, 4.700845000000000f, 4.895300000000000f, 5.089755000000000f,
+    5.342952500000000f, 5.401695000000000f, 5.460437500000000f};
+static const double MAR2_B[4] = {-0.420429107805055e1, 0.518217702261442e0, 0.562720834534370e-1,
+                                 0.344164178842340e-1};
+static const double MAR2_BR[4] = {2.500000000000000f, 3.100000000000000f, 3.500000000000000f,
+                                  4.900000000000000f};
+static const double MAR2_AF[2] = {-5.946454472402710e0, -0.049477376935239e0};
+
+static void mar2_nn(double r, double *potr, double *fpotr)
+{
+    nn_poly3(r * ORC_CM2A, MAR2_A, MAR2_R, 15, potr, fpotr);
+}
+static void mar2_rho(double r, double *potb, double *fpotb)
+{
+    const double rc = 2.002970124727e0 * ORC_A2CM; /* :85 */
+    if (r <= rc) {
+        rho_poly3(rc * ORC_CM2A, MAR2_B, MAR2_BR, 4, potb, fpotb);
+        *fpotb = 0.0;
+    } else {
+        rho_poly3(r * ORC_CM2A, MAR2_B, MAR2_BR, 4, potb, fpotb);
+    }
+}
+static void mar2_embd(double rho, double *f, double *df) { embed_fs_poly(rho, MAR2_AF, 2, f, df); }
+
+/* ---- Bonny EAM1 W-H-He. Potentials/EAM_WHeH_Bonny_JPCM26_2014/EAM1_WHeH_Bonny_JPCM26_2014.F90.
+ * W-W is Marinica EAM2 under a gauge transform (:15-103). */
+static void bon_ww_nn(double r, double *potr, double *fpotr)
+{
+    const double c = 1.848055990e0 * ORC_EVERG; /* :27 */
+    double rho, frho;
+    mar2_nn(r, potr, fpotr);
+    mar2_rho(r, &rho, &frho);
+    *potr = *potr - c * rho;           /* :35 (POTR is already 0.5 V) */
+    *fpotr = *fpotr - 2.0 * c * frho;  /* :36 */
+}
+static void bon_ww_rho(double r, double *potb, double *fpotb)
+{
+    const double s = 2.232322602e-1; /* :53 */
+    mar2_rho(r, potb, fpotb);
+    *potb = *potb * s;
+    *fpotb = *fpotb * s;
+}
+static void bon_ww_embd(double rho, double *frho, double *dfrho)
+{
+    /* :69-100 */
+    const double s = 2.232322602e-01;
+    const double is = 1.0e+00 / s;
+    const double c = 1.848055990e+00 * ORC_EVERG;
+    const double cos_ = c * is;
+    const double rhoi = 1.359141225e0;
+    const double a0 = -5.524855802e+00, a1 = 2.317313103e-01, a2 = -3.665345949e-02, a3 = 8.989367404e-03;
+    if (rho <= rhoi) {
+        double trho = rho * is, tf, tdf;
+        mar2_embd(trho, &tf, &tdf);
+        *frho = tf + c * trho;
+        *dfrho = tdf * is + cos_;
+    } else {
+        double trho = rho;
+        *frho = (a0 + trho * (a1 + trho * (a2 + trho * a3))) * ORC_EVERG;
+        *dfrho = (a1 + trho * (2.0 * a2 + 3.0 * a3 * trho)) * ORC_EVERG;
+    }
+}
+/* pair-only members of EAM1 (:107-330); knots here are D-exponent literals (true doubles) */
+static const double BON_HEHE_R[2] = {2.0, 3.0}, BON_HEHE_A[2] = {2.106615791e+00, -2.217639348e-01};
+static const double BON_HH_R[2] = {2.0, 3.0}, BON_HH_A[2] = {4.862785907e-01, 1.018797872e-01};
+static const double BON_HHE_R[3] = {1.8, 2.0, 3.0}, BON_HHE_A[3] = {1.5e+01, 2.563700119e-01, -4.489510592e-02};
+static const double BON_WHE_R[3] = {1.9, 2.2, 3.5}, BON_WHE_A[3] = {2.1e+01, 8.565323293e-01, 2.750099819e-01};
+static const double BON_WH_R[2] = {2.0, 3.0}, BON_WH_A[2] = {1.375733214e+01, 1.296071475e-01};
+
+/* registration order in EAM_ForceTable_Bonny_JPCM26_2014.F90:57-77 gives the numeric ids:
+ * 1 W<-W, 2 W<-H, 3 W<-He, 4 H<-W, 5 H<-H, 6 H<-He, 7 He<-W, 8 He<-H, 9 He<-He */
+static int bon1_nn(int id, double r, double *p, double *f)
+{
+    double ra = r * ORC_CM2A;
+    switch (id) {
+    case 1: bon_ww_nn(r, p, f); return 1;
+    case 2: case 4: nn_poly3(ra, BON_WH_A, BON_WH_R, 2, p, f); return 1;
+    case 3: case 7: nn_poly3(ra, BON_WHE_A, BON_WHE_R, 3, p, f); return 1;
+    case 5: nn_poly3(ra, BON_HH_A, BON_HH_R, 2, p, f); return 1;
+    case 6: case 8: nn_poly3(ra, BON_HHE_A, BON_HHE_R, 3, p, f); return 1;
+    case 9: nn_poly3(ra, BON_HEHE_A, BON_HEHE_R, 2, p, f); return 1;
+    }
+    return 0;
+}
+
+int orc_pot_nn(int lib, int id, double r, double *p, double *f)
+{
+    *p = 0.0; *f = 0.0;
+    if (lib == ORC_LIB_MARINICA_EAM2 && id == 1) { mar2_nn(r, p, f); return 1; }
+    if (lib == ORC_LIB_BONNY_EAM1) return bon1_nn(id, r, p, f);
+    return 0;
+}
+int orc_pot_rho(int lib, int id, double r, double *p, double *f)
+{
+    *p = 0.0; *f = 0.0;
+    if (lib == ORC_LIB_MARINICA_EAM2 && id == 1) { mar2_rho(r, p, f); return 1; }
+    if (lib == ORC_LIB_BONNY_EAM1 && id == 1) { bon_ww_rho(r, p, f); return 1; }
+    return 0;
+}
+int orc_pot_embd(int lib, int id, double rho, double *p, double *f)
+{
+    *p = 0.0; *f = 0.0;
+    if (lib == ORC_LIB_MARINICA_EAM2 && id == 1) { mar2_embd(rho, p, f); return 1; }
+    if (lib == ORC_LIB_BONNY_EAM1 && id == 1) { bon_ww_embd(rho, p, f); return 1; }
+    return 0;
+}
+
+/* =====================================================================================
+ * Table generation
+ * ===================================================================================== */
+int orc_ftable_build(int lib, int ng, const int *ptype, int ntab, int nembd, double rhoscal, double rmax,
+                     int *nkind_out, int *nkind1_out, int *kpair, int *kembd,
+                     double *potr, double *fpotr, double *potb, double *fpotb,
+                     double *fembd, double *dfembd, double *csi_out, double *rhod_out)
+{
+    int fpair[ORC_MXGROUP * ORC_MXGROUP], fpair1[ORC_MXGROUP];
+    int nkind = 0, nkind1 = 0;
+    if (ng > ORC_MXGROUP) return -1;
+    /* New_ForceTable, MD_TypeDef_ForceTable.F90:559-574: unique ids, I outer, J inner */
+    for (int i = 0; i < ng; i++)
+        for (int j = 0; j < ng; j++) {
+            int id = ptype[i + ng * j], k;
+            for (k = 0; k < nkind; k++)
+                if (fpair[k] == id) break;
+            if (k == nkind) fpair[nkind++] = id;
+        }
+    /* :600-611 */
+    for (int i = 0; i < ng; i++) {
+        int id = ptype[i + ng * i], k;
+        for (k = 0; k < nkind1; k++)
+            if (fpair1[k] == id) break;
+        if (k == nkind1) fpair1[nkind1++] = id;
+    }
+    /* :591-594 */
+    double rmaxsqrt = sqrt(rmax);
+    double csi = (double)ntab / rmaxsqrt;
+    double csiv = 1.0 / csi;
+    double rhomx = 0.0, rhod = 0.0;
+
+    /* Create_Interaction_ForceTable :1192-1205 -> Create_Pairwise_ForceTable :949-976 */
+    for (int k = 0; k < nkind; k++) {
+        int id = fpair[k];
+        double p, f;
+        if (!orc_pot_nn(lib, id, 1.0e-8, &p, &f)) return -2; /* unregistered id: reference stops (:930-940) */
+        for (int i = 1; i <= ntab; i++) {
+            double t = (double)i * csiv;
+            double r = t * t;
+            orc_pot_nn(lib, id, r, &p, &f);
+            potr[(size_t)(i - 1) * nkind + k] = p * r;
+            fpotr[(size_t)(i - 1) * nkind + k] = f * r;
+        }
+        if (orc_pot_rho(lib, id, 1.0e-8, &p, &f)) {
+            for (int i = 1; i <= ntab; i++) {
+                double t = (double)i * csiv;
+                double r = t * t;
+                orc_pot_rho(lib, id, r, &p, &f);
+                potb[(size_t)(i - 1) * nkind + k] = p;
+                fpotb[(size_t)(i - 1) * nkind + k] = f;
+                if (rhomx < p * rhoscal) rhomx = p * rhoscal; /* :965 */
+            }
+        } else {
+            for (int i = 1; i <= ntab; i++) {
+                potb[(size_t)(i - 1) * nkind + k] = 0.0;
+                fpotb[(size_t)(i - 1) * nkind + k] = 0.0;
+            }
+        }
+        rhod = rhomx / (double)nembd; /* :976 */
+    }
+    /* NOTE: the reference creates pair tables in (I,J) loop order, which visits ids in the
+     * same first-appearance order as fpair[]; RHOMX is a running max so the order is immaterial. */
+    for (int i = 0; i < ng; i++)
+        for (int j = 0; j < ng; j++) {
+            kpair[i + ng * j] = -1;
+            for (int k = 0; k < nkind; k++)
+                if (fpair[k] == ptype[i + ng * j]) { kpair[i + ng * j] = k + 1; break; }
+        }
+    /* :1207-1224 -> Create_EMBDFUNTable :1043-1052 */
+    for (int k = 0; k < nkind1; k++) {
+        int id = fpair1[k];
+        double p, f;
+        int has = orc_pot_embd(lib, id, 1.0, &p, &f);
+        for (int i = 1; i <= nembd; i++) {
+            double r = (double)(i - 1) * rhod;
+            if (has) orc_pot_embd(lib, id, r, &p, &f);
+            else { p = 0.0; f = 0.0; }
+            fembd[(size_t)(i - 1) * nkind1 + k] = p;
+            dfembd[(size_t)(i - 1) * nkind1 + k] = f;
+        }
+    }
+    for (int i = 0; i < ng; i++) {
+        kembd[i] = -1;
+        for (int k = 0; k < nkind1; k++)
+            if (fpair1[k] == ptype[i + ng * i]) { kembd[i] = k + 1; break; }
+    }
+    if (rhod <= 1.0e-64) rhod = 1.0; /* :1223 */
+    *nkind_out = nkind;
+    *nkind1_out = nkind1;
+    *csi_out = csi;
+    *rhod_out = rhod;
+    return 0;
+}
+
+/* =====================================================================================
+ * Cells and neighbour lists
+ * ===================================================================================== */
+static const double CELL_EPS = (double)0.0001f; /* real(KINDDF),parameter::EPS=0.0001 : a REAL literal */
+
+/* scan order of the 27 cells, MD_NeighborsList_GPU.F90:218-220 (same in Common/MD_NeighborsList.F90:427-429) */
+static const int NIX[27] = {0, -1, -1, -1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1, 1, 1, 1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1};
+static const int NIY[27] = {0, 0, -1, 1, 1, 0, 0, 0, -1, -1, -1, 1, 1, 1, 0, 1, -1, -1, 0, 0, 0, -1, -1, -1, 1, 1, 1};
+static const int NIZ[27] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+
+void orc_ncell(const double zl[3], double nb_rm_max, int ncell[3])
+{
+    /* MD_NeighborsList_GPU.F90:289-298 */
+    for (int k = 0; k < 3; k++) {
+        ncell[k] = (int)(zl[k] / (1.0 * nb_rm_max) - CELL_EPS);
+        if (ncell[k] < 3) ncell[k] = 3;
+    }
+}
+
+int orc_nlist_build_dev(int nbox, int napb, const double *xp, const int *ityp, int *statu,
+                        const double boxlow[3], const double zl[3], const int ifpd[3],
+                        const double boxshape[9], int ng, const double *nb_rm, int mxkvois,
+                        int ncell[3], int *inc, int *gid, int *nac, int *naac, int *ia1th,
+                        int *kvois, int *indi, int *nn_max)
+{
+    const int n = nbox * napb;
+    double rmmax = 0.0;
+    for (int i = 0; i < ng * ng; i++)
+        if (nb_rm[i] > rmmax) rmmax = nb_rm[i];
+    orc_ncell(zl, rmmax, ncell);
+    const int ncx = ncell[0], ncy = ncell[1], ncz = ncell[2];
+    const int nc0 = ncx * ncy * ncz, nc = nc0 * nbox;
+
+    /* NeighboreList_IC_KERNEL :798-815 (first partition: GID = identity, :1455-1457) */
+    for (int i = 0; i < n; i++) {
+        int ib = i / napb;
+        if ((statu[i] & ORC_STATU_OUTOFBOX) != ORC_STATU_OUTOFBOX) {
+            int ix = (int)((xp[i] - boxlow[0]) / zl[0] * (double)ncx - CELL_EPS);
+            int iy = (int)((xp[i + n] - boxlow[1]) / zl[1] * (double)ncy - CELL_EPS);
+            int iz = (int)((xp[i + 2 * n] - boxlow[2]) / zl[2] * (double)ncz - CELL_EPS);
+            if (ix < 0 || ix >= ncx || iy < 0 || iy >= ncy || iz < 0 || iz >= ncz)
+                inc[i] = -2;
+            else
+                inc[i] = 1 + (ix + ncx * (iy + ncy * iz)) + ib * nc0;
+        } else {
+            inc[i] = -1;
+        }
+    }
+    /* host linked-cell build :1490-1528 */
+    int *head = (int *)calloc((size_t)nc + 1, sizeof(int));
+    int *link = (int *)calloc((size_t)n + 1, sizeof(int));
+    memset(nac, 0, sizeof(int) * (size_t)nc);
+    memset(naac, 0, sizeof(int) * (size_t)nc);
+    int numout = 0;
+    for (int i = 1; i <= n; i++) {
+        int ic = inc[i - 1];
+        if (ic > 0) {
+            link[i] = head[ic];
+            head[ic] = i;
+            nac[ic - 1]++;
+            if ((statu[i - 1] & ORC_STATU_ACTIVE) == ORC_STATU_ACTIVE) naac[ic - 1]++;
+        } else {
+            /* the reference prompts on stdin here (:1506-1523); the 'C'ontinue branch: */
+            if (ic < -1) statu[i - 1] = ORC_STATU_OUTOFBOX;
+            numout++;
+        }
+    }
+    /* cell-ordered gather :1541-1570 : cells ascending, chain order = descending original id */
+    int ip = 0;
+    for (int ic = 1; ic <= nc; ic++) {
+        ia1th[ic - 1] = (ic > 1) ? ia1th[ic - 2] + nac[ic - 2] : 1;
+        for (int id = head[ic]; id > 0; id = link[id]) gid[ip++] = id;
+    }
+    /* out-of-box atoms go to the end, backward :1627-1637 */
+    if (numout > 0) {
+        ip = n;
+        for (int i = 1; i <= n; i++)
+            if (inc[i - 1] < 0) gid[--ip] = i;
+    }
+    free(head);
+    free(link);
+
+    /* sorted copies used by the list kernel (hm_XP, hm_ITYP) */
+    float *px = (float *)malloc(sizeof(float) * (size_t)n * 3); /* (float)XP of the sorted atoms  */
+    double *sx = (double *)malloc(sizeof(double) * (size_t)n * 3);
+    int *sty = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int s = 0; s < n; s++) {
+        int o = gid[s] - 1;
+        for (int d = 0; d < 3; d++) {
+            sx[s + d * n] = xp[o + d * n];
+            px[s + d * n] = (float)xp[o + d * n];
+        }
+        sty[s] = ityp[o];
+    }
+    /* fp32 constants :1376-1377,1393-1394,1414-1415 */
+    float bs[9], rm2[ORC_MXGROUP * ORC_MXGROUP];
+    for (int i = 0; i < 9; i++) bs[i] = (float)boxshape[i];
+    for (int i = 0; i < ng * ng; i++) rm2[i] = (float)(nb_rm[i] * nb_rm[i]);
+    const float fbs[3] = {(float)zl[0], (float)zl[1], (float)zl[2]}; /* CXYZ is real(KINDSF) :955,1034 */
+
+    memset(kvois, 0, sizeof(int) * (size_t)n); /* DevSet(KVOIS,0) at init :285 */
+    int nnmx = 0;
+    /* Cal_NeighboreList_Kernel2C :963-1196, one "block" per cell */
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : nnmx)
+    for (int ic0 = 0; ic0 < nc; ic0++) {
+        if (naac[ic0] <= 0) continue; /* :982 */
+        if (nac[ic0] <= 0) continue;  /* :1018 */
+        int is0 = ic0 / nc0, icl = ic0 - is0 * nc0;
+        int iz0 = icl / (ncx * ncy), iy0 = (icl - iz0 * ncx * ncy) / ncx, ix0 = icl - iz0 * ncx * ncy - iy0 * ncx;
+        int cid[27];
+        float cxyz[27][3];
+        for (int k = 0; k < 27; k++) {
+            int c[3] = {ix0 + NIX[k], iy0 + NIY[k], iz0 + NIZ[k]};
+            const int ncs[3] = {ncx, ncy, ncz};
+            int out = 0;
+            for (int d = 0; d < 3; d++) {
+                cxyz[k][d] = 0.0f;
+                if (ifpd[d] && k > 0) { /* :1031-1059 */
+                    if (c[d] >= ncs[d]) { c[d] = 0; cxyz[k][d] = fbs[d]; }
+                    else if (c[d] < 0) { c[d] = ncs[d] - 1; cxyz[k][d] = -fbs[d]; }
+                }
+                if (c[d] >= ncs[d] || c[d] < 0) out = 1;
+            }
+            cid[k] = out ? -1 : (ncx * ncy * c[2] + ncx * c[1] + c[0] + is0 * nc0);
+        }
+        int a0 = ia1th[ic0] - 1, na = nac[ic0];
+        for (int ia = a0; ia < a0 + na; ia++) {
+            float p1 = px[ia], p2 = px[ia + n], p3 = px[ia + 2 * n];
+            int ity = sty[ia], nn = 0;
+            for (int k = 0; k < 27; k++) {
+                if (cid[k] < 0) continue;
+                int j0 = ia1th[cid[k]] - 1, nj = nac[cid[k]];
+                for (int ja = j0; ja < j0 + nj; ja++) {
+                    /* SPOS = XP + CXYZ : double + float -> double, stored to float :1100-1102 */
+                    float s1 = (float)(sx[ja] + (double)cxyz[k][0]);
+                    float s2 = (float)(sx[ja + n] + (double)cxyz[k][1]);
+                    float s3 = (float)(sx[ja + 2 * n] + (double)cxyz[k][2]);
+                    float e1 = p1 - s1, e2 = p2 - s2, e3 = p3 - s3;
+                    float d1 = bs[0] * e1 + bs[3] * e2 + bs[6] * e3; /* BOXSHAPE(1,1:3), column-major */
+                    float d2 = bs[1] * e1 + bs[4] * e2 + bs[7] * e3;
+                    float d3 = bs[2] * e1 + bs[5] * e2 + bs[8] * e3;
+                    if (d1 * d1 + d2 * d2 + d3 * d3 <= rm2[(ity - 1) + ng * (sty[ja] - 1)]) { /* :1123 */
+                        if (k == 0 && ja == ia) continue; /* :1124 */
+                        nn++;
+                        if (nn <= mxkvois) indi[ia + (size_t)(nn - 1) * n] = ja + 1;
+                    }
+                }
+            }
+            kvois[ia] = nn < mxkvois ? nn : mxkvois; /* :1195 */
+            if (nn > nnmx) nnmx = nn;
+        }
+    }
+    if (nn_max) *nn_max = nnmx;
+    free(px);
+    free(sx);
+    free(sty);
+    return numout;
+}
+
+int orc_nlist_build_cpu(int n, const double *xp, const int *ityp, const int *statu,
+                        const double boxlow[3], const double zl[3], const int ifpd[3],
+                        const double boxshape[9], int ng, const double *nb_rm, int mxkvois,
+                        int *kvois, int *indi)
+{
+    /* Common/MD_NeighborsList.F90:432-633 */
+    double rmmax = 0.0, rcut2[ORC_MXGROUP * ORC_MXGROUP];
+    for (int i = 0; i < ng * ng; i++) {
+        if (nb_rm[i] > rmmax) rmmax = nb_rm[i];
+        rcut2[i] = nb_rm[i] * nb_rm[i];
+    }
+    int ncell[3];
+    for (int k = 0; k < 3; k++) { /* :474-483 */
+        ncell[k] = (int)(zl[k] / (1.0 * rmmax) - CELL_EPS);
+        if (ncell[k] < 3) ncell[k] = 3;
+    }
+    const int ncx = ncell[0], ncy = ncell[1], ncz = ncell[2], nc = ncx * ncy * ncz;
+    int *head = (int *)calloc((size_t)nc + 1, sizeof(int));
+    int *link = (int *)calloc((size_t)n + 1, sizeof(int));
+    int err = 0;
+    for (int i = 1; i <= n; i++) { /* :495-526 */
+        if ((statu[i - 1] & ORC_STATU_OUTOFBOX) != ORC_STATU_OUTOFBOX) {
+            int c[3];
+            for (int k = 0; k < 3; k++)
+                c[k] = (int)((xp[(i - 1) + k * n] - boxlow[k]) / zl[k] * (double)ncell[k] - CELL_EPS);
+            if (c[0] < 0 || c[0] > ncx || c[1] < 0 || c[1] > ncy || c[2] < 0 || c[2] > ncz) { err = -2; break; }
+            if (c[0] >= ncx || c[1] >= ncy || c[2] >= ncz) { err = -2; break; } /* would index past HEAD */
+            int ic = 1 + (c[0] + ncx * (c[1] + ncy * c[2]));
+            link[i] = head[ic];
+            head[ic] = i;
+        } else {
+            kvois[i - 1] = 0;
+        }
+    }
+    if (err) { free(head); free(link); return err; }
+
+#pragma omp parallel
+    {
+        int cap = 1024;
+        int *ident = (int *)malloc(sizeof(int) * cap);
+        int *typ = (int *)malloc(sizeof(int) * cap);
+        double *xpt = (double *)malloc(sizeof(double) * 3 * cap);
+#pragma omp for schedule(dynamic, 16)
+        for (int ic0 = 1; ic0 <= nc; ic0++) {
+            if (head[ic0] == 0 || err) continue;
+            int iz = (ic0 - 1) / (ncx * ncy) + 1, iy = ((ic0 - 1) - (iz - 1) * ncx * ncy) / ncx + 1,
+                ix = (ic0 - 1) - (iz - 1) * ncx * ncy - (iy - 1) * ncx + 1;
+            int nloc = 0, n0;
+#define PUSH(ID, CX, CY, CZ)                                                            \
+    do {                                                                                \
+        if (nloc == cap) {                                                              \
+            cap *= 2;                                                                   \
+            ident = (int *)realloc(ident, sizeof(int) * cap);                           \
+            typ = (int *)realloc(typ, sizeof(int) * cap);                               \
+            xpt = (double *)realloc(xpt, sizeof(double) * 3 * cap);                     \
+        }                                                                               \
+        ident[nloc] = (ID);                                                             \
+        xpt[3 * nloc] = xp[(ID)-1] + (CX);                                              \
+        xpt[3 * nloc + 1] = xp[(ID)-1 + n] + (CY);                                      \
+        xpt[3 * nloc + 2] = xp[(ID)-1 + 2 * n] + (CZ);                                  \
+        typ[nloc] = ityp[(ID)-1];                                                       \
+        nloc++;                                                                         \
+    } while (0)
+            for (int id = head[ic0]; id > 0; id = link[id]) PUSH(id, 0.0, 0.0, 0.0);
+            n0 = nloc;
+            for (int k = 1; k < 27; k++) { /* :555-588 */
+                int j[3] = {ix + NIX[k], iy + NIY[k], iz + NIZ[k]};
+                double cx[3] = {0.0, 0.0, 0.0};
+                int out = 0;
+                for (int d = 0; d < 3; d++) {
+                    if (ifpd[d]) {
+                        if (j[d] > ncell[d]) { j[d] = 1; cx[d] = zl[d]; }
+                        else if (j[d] < 1) { j[d] = ncell[d]; cx[d] = -zl[d]; }
+                    }
+                    if (j[d] > ncell[d] || j[d] < 1) out = 1;
+                }
+                if (out) continue;
+                for (int id = head[j[0] + ncx * ((j[1] - 1) + ncy * (j[2] - 1))]; id > 0; id = link[id])
+                    PUSH(id, cx[0], cx[1], cx[2]);
+            }
+#undef PUSH
+            for (int i = 0; i < n0; i++) { /* :594-621 */
+                int id = ident[i], itp = typ[i], nn = 0;
+                for (int jj = 0; jj < nloc; jj++) {
+                    if (jj == i) continue;
+                    double c1 = xpt[3 * i] - xpt[3 * jj], c2 = xpt[3 * i + 1] - xpt[3 * jj + 1],
+                           c3 = xpt[3 * i + 2] - xpt[3 * jj + 2];
+                    double d1 = boxshape[0] * c1 + boxshape[3] * c2 + boxshape[6] * c3;
+                    double d2 = boxshape[1] * c1 + boxshape[4] * c2 + boxshape[7] * c3;
+                    double d3 = boxshape[2] * c1 + boxshape[5] * c2 + boxshape[8] * c3;
+                    if (d1 * d1 + d2 * d2 + d3 * d3 < rcut2[(itp - 1) + ng * (typ[jj] - 1)]) { /* :605 */
+                        nn++;
+                        if (nn > mxkvois) { err = -1; break; } /* reference stops :608-612 */
+                        indi[(id - 1) + (size_t)(nn - 1) * n] = ident[jj];
+                    }
+                }
+                if (err) break;
+                kvois[id - 1] = nn;
+            }
+        }
+        free(ident);
+        free(typ);
+        free(xpt);
+    }
+    free(head);
+    free(link);
+    return err;
+}
+
+/* =====================================================================================
+ * Forces
+ * ===================================================================================== */
+/* T(k,KK) in Fortran layout; KK outside 1..nt is out of bounds in the reference
+ * (r == Rmax reads KK+1 = NTAB+1, MD_EAM_ForceTable_GPU.F90:522-530); defined as 0 here. */
+static inline double tab(const double *t, int nk, int nt, int k, int kk)
+{
+    if (kk < 1 || kk > nt) return 0.0;
+    return t[(size_t)(kk - 1) * nk + (k - 1)];
+}
+
+/* separation with the pairwise minimum image, :497-510 */
+static inline void min_image(double *s, const double zl[3], const int ifpd[3])
+{
+    for (int d = 0; d < 3; d++)
+        if (ifpd[d] > 0 && fabs(s[d]) > zl[d] * 0.5) s[d] = s[d] - copysign(zl[d], s[d]);
+}
+
+void orc_force_pass1(int n, int ia0, int npart, const double *xp, const int *ityp, const int *statu,
+                     const int *kvois, const int *indi, int ldindi, const double zl[3], const int ifpd[3],
+                     const double bs[9], const orc_tables *t, double *den)
+{
+#pragma omp parallel for schedule(static)
+    for (int ic = 1; ic <= npart; ic++) {
+        double den0 = 0.0;
+        if ((statu[ic - 1] & ORC_STATU_ACTIVE) == ORC_STATU_ACTIVE) {
+            int gi = ic + ia0 - 1;
+            double px = xp[gi], py = xp[gi + n], pz = xp[gi + 2 * n];
+            int ti = ityp[gi], iiw = kvois[ic - 1];
+            for (int iw = 0; iw < iiw; iw++) {
+                int j = indi[(ic - 1) + (size_t)iw * ldindi] - 1;
+                double s[3] = {px - xp[j], py - xp[j + n], pz - xp[j + 2 * n]};
+                min_image(s, zl, ifpd);
+                double dx = bs[0] * s[0] + bs[3] * s[1] + bs[6] * s[2]; /* :515-517 */
+                double dy = bs[1] * s[0] + bs[4] * s[1] + bs[7] * s[2];
+                double dz = bs[2] * s[0] + bs[5] * s[1] + bs[8] * s[2];
+                double r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 <= t->ru2max) { /* :522 */
+                    int ktab = t->kpair[(ti - 1) + t->ng * (ityp[j] - 1)];
+                    double r = sqrt(r2);
+                    double sk = sqrt(r) * t->csi;
+                    int kk = (int)sk;
+                    double a = tab(t->potb, t->nkind, t->ntab, ktab, kk);
+                    den0 = den0 + (a + (sk - (double)kk) * (tab(t->potb, t->nkind, t->ntab, ktab, kk + 1) - a)); /* :530 */
+                }
+            }
+            if (t->pot_type == ORC_POT_FS) {
+                /* MD_FS_ForceTable_GPU.F90:497-507: DEN = -0.5/sqrt(rho), guarded rho>0 */
+                if (den0 > 0.0) den0 = -0.5 / sqrt(den0);
+            } else if (den0 > 0.0) { /* :535-541 */
+                int ktab = t->kembd[ti - 1];
+                double sk = den0 / t->rhod + 1.0;
+                int kk = (int)(sk + 0.000001);
+                double a = tab(t->dfembd, t->nkind1, t->nembd, ktab, kk);
+                den0 = a + (sk - (double)kk) * (tab(t->dfembd, t->nkind1, t->nembd, ktab, kk + 1) - a);
+            }
+        }
+        den[ic + ia0 - 1] = den0; /* :544 */
+    }
+}
+
+void orc_force_pass2(int n, int ia0, int npart, const double *xp, const int *ityp, const int *statu,
+                     const int *kvois, const int *indi, int ldindi, const double zl[3], const int ifpd[3],
+                     const double bs[9], const orc_tables *t, const double *den, double *fp, int ldfp,
+                     double *vtensor)
+{
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma omp parallel for schedule(static) reduction(+ : v[:9])
+    for (int ic = 1; ic <= npart; ic++) {
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        if ((statu[ic - 1] & ORC_STATU_ACTIVE) == ORC_STATU_ACTIVE) {
+            int gi = ic + ia0 - 1;
+            double px = xp[gi], py = xp[gi + n], pz = xp[gi + 2 * n];
+            int ti = ityp[gi], iiw = kvois[ic - 1];
+            double denki = den[gi];
+            for (int iw = 0; iw < iiw; iw++) {
+                int j = indi[(ic - 1) + (size_t)iw * ldindi] - 1;
+                double s[3] = {px - xp[j], py - xp[j + n], pz - xp[j + 2 * n]};
+                min_image(s, zl, ifpd);
+                double dx, dy, dz, r2;
+                if (vtensor) { /* CALPTENSOR_KERNEL :1171-1174 applies BOXSHAPE */
+                    dx = bs[0] * s[0] + bs[3] * s[1] + bs[6] * s[2];
+                    dy = bs[1] * s[0] + bs[4] * s[1] + bs[7] * s[2];
+                    dz = bs[2] * s[0] + bs[5] * s[1] + bs[8] * s[2];
+                    r2 = dx * dx + dy * dy + dz * dz;
+                } else { /* CALFORCE_KERNEL :775 does not */
+                    dx = s[0]; dy = s[1]; dz = s[2];
+                    r2 = s[0] * s[0] + s[1] * s[1] + s[2] * s[2];
+                }
+                if (r2 <= t->ru2max) {
+                    int tj = ityp[j];
+                    int k0 = t->kpair[(ti - 1) + t->ng * (tj - 1)];
+                    int k1 = t->kpair[(tj - 1) + t->ng * (ti - 1)];
+                    double r = sqrt(r2);
+                    double sk = sqrt(r) * t->csi;
+                    int kk = (int)sk;
+                    double dk = sk - (double)kk;
+                    double denkj = den[j];
+                    double a = tab(t->fpotr, t->nkind, t->ntab, k0, kk);
+                    double b = tab(t->fpotb, t->nkind, t->ntab, k0, kk);
+                    double c = tab(t->fpotb, t->nkind, t->ntab, k1, kk);
+                    /* :811-813 */
+                    double fortot = (a + dk * (tab(t->fpotr, t->nkind, t->ntab, k0, kk + 1) - a)) / r2 +
+                                    ((b + dk * (tab(t->fpotb, t->nkind, t->ntab, k0, kk + 1) - b)) * denki +
+                                     (c + dk * (tab(t->fpotb, t->nkind, t->ntab, k1, kk + 1) - c)) * denkj) / r;
+                    fx = fx + fortot * s[0];
+                    fy = fy + fortot * s[1];
+                    fz = fz + fortot * s[2];
+                    if (vtensor) { /* :1222-1232 ; P(a,b) stored column-major v[a+3b] */
+                        fortot = fortot * 0.5;
+                        v[0] += dx * dx * fortot; v[3] += dx * dy * fortot; v[6] += dx * dz * fortot;
+                        v[1] += dy * dx * fortot; v[4] += dy * dy * fortot; v[7] += dy * dz * fortot;
+                        v[2] += dz * dx * fortot; v[5] += dz * dy * fortot; v[8] += dz * dz * fortot;
+                    }
+                }
+            }
+        }
+        fp[ic - 1] = fx;
+        fp[ic - 1 + ldfp] = fy;
+        fp[ic - 1 + 2 * ldfp] = fz;
+    }
+    if (vtensor)
+        for (int i = 0; i < 9; i++) vtensor[i] = v[i];
+}
+
+void orc_force_epot(int n, int ia0, int npart, const double *xp, const int *ityp, const int *statu,
+                    const int *kvois, const int *indi, int ldindi, const double zl[3], const int ifpd[3],
+                    const double bs[9], const orc_tables *t, double *epot)
+{
+#pragma omp parallel for schedule(static)
+    for (int ic = 1; ic <= npart; ic++) {
+        double er0 = 0.0, den0 = 0.0;
+        if ((statu[ic - 1] & ORC_STATU_ACTIVE) == ORC_STATU_ACTIVE) {
+            int gi = ic + ia0 - 1;
+            double px = xp[gi], py = xp[gi + n], pz = xp[gi + 2 * n];
+            int ti = ityp[gi], iiw = kvois[ic - 1];
+            for (int iw = 0; iw < iiw; iw++) {
+                int j = indi[(ic - 1) + (size_t)iw * ldindi] - 1;
+                double s[3] = {px - xp[j], py - xp[j + n], pz - xp[j + 2 * n]};
+                min_image(s, zl, ifpd);
+                double dx = bs[0] * s[0] + bs[3] * s[1] + bs[6] * s[2];
+                double dy = bs[1] * s[0] + bs[4] * s[1] + bs[7] * s[2];
+                double dz = bs[2] * s[0] + bs[5] * s[1] + bs[8] * s[2];
+                double r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 <= t->ru2max) {
+                    int ktab = t->kpair[(ti - 1) + t->ng * (ityp[j] - 1)];
+                    double r = sqrt(r2);
+                    double sk = sqrt(r) * t->csi;
+                    int kk = (int)sk;
+                    double dk = sk - (double)kk;
+                    double a = tab(t->potr, t->nkind, t->ntab, ktab, kk);
+                    double b = tab(t->potb, t->nkind, t->ntab, ktab, kk);
+                    er0 = er0 + (a + dk * (tab(t->potr, t->nkind, t->ntab, ktab, kk + 1) - a)) / r; /* :1622 */
+                    den0 = den0 + (b + dk * (tab(t->potb, t->nkind, t->ntab, ktab, kk + 1) - b));  /* :1623 */
+                }
+            }
+            if (t->pot_type == ORC_POT_FS) {
+                /* MD_FS_ForceTable_GPU.F90:1606 : E = sum 0.5V - sqrt(rho) */
+                den0 = -sqrt(den0);
+            } else { /* :1628-1631, no rho>0 guard here */
+                int ktab = t->kembd[ti - 1];
+                double sk = den0 / t->rhod + 1.0;
+                int kk = (int)(sk + 0.000001);
+                double a = tab(t->fembd, t->nkind1, t->nembd, ktab, kk);
+                den0 = a + (sk - (double)kk) * (tab(t->fembd, t->nkind1, t->nembd, ktab, kk + 1) - a);
+            }
+        }
+        epot[ic - 1] = er0 + den0; /* :1633 */
+    }
+}
+
+/* =====================================================================================
+ * Integrator, EPC
+ * ===================================================================================== */
+void orc_predictor(int n, double *xp, double *xp1, const double *fp, double *dis, int *statu,
+                   const int *ityp, const double *cm, double h, const double lb[3], const double ub[3],
+                   const double zl[3], const int ifpd[3])
+{
+    /* Predictor_DEV, MD_DiffScheme_GPU.F90:660-662: TH = H, HS2 = H/2, H2S2 = H*H/2 */
+    const double th = h, hs2 = th * 0.5, h2s2 = th * th * 0.5;
+    static const int FIXP[3] = {ORC_STATU_FIXPOSX, ORC_STATU_FIXPOSY, ORC_STATU_FIXPOSZ};
+    static const int FIXV[3] = {ORC_STATU_FIXVELX, ORC_STATU_FIXVELY, ORC_STATU_FIXVELZ};
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        int stat = statu[i];
+        if ((stat & ORC_STATU_ACTIVE) != ORC_STATU_ACTIVE) continue;
+        double cm0 = cm[ityp[i] - 1];
+        double x[3], f[3];
+        for (int d = 0; d < 3; d++) {
+            f[d] = fp[i + d * n] / cm0;                                /* :309-311 */
+            double dd = th * xp1[i + d * n] + h2s2 * f[d];             /* :314 */
+            if ((stat & FIXP[d]) == FIXP[d]) dd = 0.0;
+            x[d] = xp[i + d * n] + dd;
+            if (ifpd[d]) {                                             /* :317-325 */
+                if (x[d] > ub[d]) x[d] = x[d] - zl[d];
+                else if (x[d] < lb[d]) x[d] = x[d] + zl[d];
+            }
+            dis[i + d * n] = dis[i + d * n] + dd;                      /* :371-373 */
+        }
+        for (int d = 0; d < 3; d++) {
+            if ((stat & FIXV[d]) == 0 && (stat & FIXP[d]) == 0)       /* :353-361 */
+                xp1[i + d * n] = xp1[i + d * n] + hs2 * f[d];
+            xp[i + d * n] = x[d];
+        }
+        /* :375-379 ; the PASSBOUND bit set at :320 is never stored */
+        if (x[0] > ub[0] || x[1] > ub[1] || x[2] > ub[2]) statu[i] = ORC_STATU_OUTOFBOX | ORC_STATU_REFLECT;
+        else if (x[0] < lb[0] || x[1] < lb[1] || x[2] < lb[2]) statu[i] = ORC_STATU_OUTOFBOX | ORC_STATU_TRANSMIT;
+    }
+}
+
+void orc_corrector(int n, double *xp1, const double *fp, const int *statu, const int *ityp, const double *cm,
+                   double h)
+{
+    const double hs2 = h * 0.5;
+    static const int FIXP[3] = {ORC_STATU_FIXPOSX, ORC_STATU_FIXPOSY, ORC_STATU_FIXPOSZ};
+    static const int FIXV[3] = {ORC_STATU_FIXVELX, ORC_STATU_FIXVELY, ORC_STATU_FIXVELZ};
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        int stat = statu[i];
+        if ((stat & ORC_STATU_ACTIVE) != ORC_STATU_ACTIVE) continue;
+        double cm0 = cm[ityp[i] - 1];
+        for (int d = 0; d < 3; d++) {
+            double f = fp[i + d * n] / cm0; /* :735-737 */
+            if ((stat & FIXV[d]) == 0 && (stat & FIXP[d]) == 0) xp1[i + d * n] = xp1[i + d * n] + hs2 * f;
+        }
+    }
+}
+
+void orc_ekin(int n, const double *xp1, const int *statu, const int *ityp, const double *cm, double *ekin)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        double ek = -1.0e32; /* :886 */
+        if ((statu[i] & ORC_STATU_ACTIVE) == ORC_STATU_ACTIVE && (statu[i] & ORC_STATU_FIXPOS) == 0) {
+            double cm0 = cm[ityp[i] - 1];
+            double vx = xp1[i], vy = xp1[i + n], vz = xp1[i + 2 * n];
+            ek = 0.5 * cm0 * (vx * vx + vy * vy + vz * vz); /* :896 */
+        }
+        ekin[i] = ek;
+    }
+}
+
+void orc_epc(int n, const double *xp1, double *fp, const int *statu, const int *ityp, int ng, const int *enable,
+             const double *cm, const double *te, const double *alpha, const double *cut, const double *he)
+{
+    double v2ti[ORC_MXGROUP], epa[ORC_MXGROUP], tcut[ORC_MXGROUP], eup[ORC_MXGROUP];
+    for (int g = 0; g < ng; g++) { /* Reset_EPCMOD_DEV, MD_EP_Coupling_GPU.F90:387-394 */
+        v2ti[g] = cm[g] * (1.0 / 3.0) / ORC_KB;
+        epa[g] = cm[g] / alpha[g];
+        tcut[g] = te[g] * cut[g];
+        eup[g] = 2.0 * he[g] / cm[g];
+    }
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) { /* EPC_MOD_KERNEL :471-491 */
+        int kk = ityp[i] - 1;
+        if (enable[kk] <= 0) continue;
+        if ((statu[i] & ORC_STATU_ACTIVE) != ORC_STATU_ACTIVE) continue;
+        double vx = xp1[i], vy = xp1[i + n], vz = xp1[i + 2 * n];
+        double v2 = vx * vx + vy * vy + vz * vz;
+        if (v2 <= eup[kk]) {
+            double tm = v2 * v2ti[kk];
+            double mu = epa[kk] * (tm - te[kk]) / (tm > tcut[kk] ? tm : tcut[kk]);
+            fp[i] = fp[i] - mu * vx;
+            fp[i + n] = fp[i + n] - mu * vy;
+            fp[i + 2 * n] = fp[i + 2 * n] - mu * vz;
+        }
+    }
+}
+
+/* =====================================================================================
+ * Whole-step driver in cell-sorted order
+ * ===================================================================================== */
+struct orc_md {
+    int nbox, napb, n, ng, mxkvois, haspart;
+    double boxlow[3], boxup[3], zl[3], bs[9], cm[ORC_MXGROUP], nb_rm[ORC_MXGROUP * ORC_MXGROUP];
+    int ifpd[3], ncell[3];
+    orc_tables t;
+    /* sorted-order state */
+    double *xp, *xp1, *fp, *dis, *den, *epot, *ekin;
+    int *ityp, *statu, *gid, *kvois, *indi;
+    /* original-order scratch */
+    double *oxp, *tmp;
+    int *oityp, *ostatu, *inc, *ngid, *nac, *naac, *ia1th, *itmp;
+    double vtensor[9];
+    int epc_on, epc_enable[ORC_MXGROUP];
+    double epc_te[ORC_MXGROUP], epc_alpha[ORC_MXGROUP], epc_cut[ORC_MXGROUP], epc_he[ORC_MXGROUP];
+};
+
+orc_md *orc_md_create(int nbox, int napb, const double *xp, const double *xp1, const int *ityp, const int *statu,
+                      int ng, const double *cm, const double boxlow[3], const double zl[3], const int ifpd[3],
+                      const double *nb_rm, int mxkvois, const orc_tables *t)
+{
+    orc_md *m = (orc_md *)calloc(1, sizeof(orc_md));
+    int n = nbox * napb;
+    m->nbox = nbox; m->napb = napb; m->n = n; m->ng = ng; m->mxkvois = mxkvois;
+    for (int d = 0; d < 3; d++) {
+        m->boxlow[d] = boxlow[d];
+        m->zl[d] = zl[d];
+        m->boxup[d] = boxlow[d] + zl[d];
+        m->ifpd[d] = ifpd[d];
+    }
+    m->bs[0] = m->bs[4] = m->bs[8] = 1.0;
+    memcpy(m->cm, cm, sizeof(double) * ng);
+    memcpy(m->nb_rm, nb_rm, sizeof(double) * ng * ng);
+    m->t = *t;
+    size_t n3 = (size_t)n * 3;
+    m->xp = (double *)malloc(sizeof(double) * n3);
+    m->xp1 = (double *)malloc(sizeof(double) * n3);
+    m->fp = (double *)calloc(n3, sizeof(double));
+    m->dis = (double *)calloc(n3, sizeof(double));
+    m->den = (double *)calloc(n, sizeof(double));
+    m->epot = (double *)calloc(n, sizeof(double));
+    m->ekin = (double *)calloc(n, sizeof(double));
+    m->ityp = (int *)malloc(sizeof(int) * n);
+    m->statu = (int *)malloc(sizeof(int) * n);
+    m->gid = (int *)malloc(sizeof(int) * n);
+    m->kvois = (int *)calloc(n, sizeof(int));
+    m->indi = (int *)malloc(sizeof(int) * (size_t)n * mxkvois);
+    m->oxp = (double *)malloc(sizeof(double) * n3);
+    m->tmp = (double *)malloc(sizeof(double) * n3);
+    m->oityp = (int *)malloc(sizeof(int) * n);
+    m->ostatu = (int *)malloc(sizeof(int) * n);
+    m->inc = (int *)malloc(sizeof(int) * n);
+    m->ngid = (int *)malloc(sizeof(int) * n);
+    m->itmp = (int *)malloc(sizeof(int) * n);
+    memcpy(m->xp, xp, sizeof(double) * n3);
+    memcpy(m->xp1, xp1, sizeof(double) * n3);
+    memcpy(m->ityp, ityp, sizeof(int) * n);
+    memcpy(m->statu, statu, sizeof(int) * n);
+    for (int i = 0; i < n; i++) m->gid[i] = i + 1;
+    double rmmax = 0.0;
+    for (int i = 0; i < ng * ng; i++)
+        if (nb_rm[i] > rmmax) rmmax = nb_rm[i];
+    orc_ncell(zl, rmmax, m->ncell);
+    size_t nc = (size_t)m->ncell[0] * m->ncell[1] * m->ncell[2] * nbox;
+    m->nac = (int *)malloc(sizeof(int) * nc);
+    m->naac = (int *)malloc(sizeof(int) * nc);
+    m->ia1th = (int *)malloc(sizeof(int) * nc);
+    return m;
+}
+
+void orc_md_destroy(orc_md *m)
+{
+    if (!m) return;
+    free(m->xp); free(m->xp1); free(m->fp); free(m->dis); free(m->den); free(m->epot); free(m->ekin);
+    free(m->ityp); free(m->statu); free(m->gid); free(m->kvois); free(m->indi);
+    free(m->oxp); free(m->tmp); free(m->oityp); free(m->ostatu); free(m->inc); free(m->ngid); free(m->itmp);
+    free(m->nac); free(m->naac); free(m->ia1th);
+    free(m);
+}
+
+void orc_md_set_epc(orc_md *m, const int *enable, const double *te, const double *alpha, const double *cut,
+                    const double *he)
+{
+    m->epc_on = 0;
+    for (int g = 0; g < m->ng; g++) {
+        m->epc_enable[g] = enable[g];
+        m->epc_te[g] = te[g];
+        m->epc_alpha[g] = alpha[g];
+        m->epc_cut[g] = cut[g];
+        m->epc_he[g] = he[g];
+        if (enable[g] > 0) m->epc_on = 1;
+    }
+}
+
+/* permute a (n,ld) column-major array: dst[new] = src[perm[new]] */
+static void permute_d(double *a, double *tmp, const int *perm, int n, int ncol)
+{
+    for (int c = 0; c < ncol; c++) {
+        for (int i = 0; i < n; i++) tmp[i] = a[perm[i] + (size_t)c * n];
+        memcpy(a + (size_t)c * n, tmp, sizeof(double) * n);
+    }
+}
+
+int orc_md_rebuild(orc_md *m)
+{
+    /* Cal_NeighBoreList2C_0_DEV, MD_NeighborsList_GPU.F90:1421-1695: un-permute to the
+     * original order, re-bin, re-sort every per-atom array (FP is not re-sorted by the
+     * reference because it is recomputed right after; we carry it so that getters stay valid). */
+    int n = m->n;
+    for (int s = 0; s < n; s++) {
+        int o = m->gid[s] - 1;
+        for (int d = 0; d < 3; d++) m->oxp[o + (size_t)d * n] = m->xp[s + (size_t)d * n];
+        m->oityp[o] = m->ityp[s];
+        m->ostatu[o] = m->statu[s];
+    }
+    int nnmax = 0;
+    int nout = orc_nlist_build_dev(m->nbox, m->napb, m->oxp, m->oityp, m->ostatu, m->boxlow, m->zl, m->ifpd,
+                                   m->bs, m->ng, m->nb_rm, m->mxkvois, m->ncell, m->inc, m->ngid, m->nac,
+                                   m->naac, m->ia1th, m->kvois, m->indi, &nnmax);
+    /* perm[new sorted pos] = old sorted pos */
+    int *ginv = m->inc; /* reuse: original id -> old sorted pos */
+    for (int s = 0; s < n; s++) ginv[m->gid[s] - 1] = s;
+    int *perm = m->itmp;
+    for (int s = 0; s < n; s++) perm[s] = ginv[m->ngid[s] - 1];
+    permute_d(m->xp, m->tmp, perm, n, 3);
+    permute_d(m->xp1, m->tmp, perm, n, 3);
+    permute_d(m->fp, m->tmp, perm, n, 3);
+    permute_d(m->dis, m->tmp, perm, n, 3);
+    permute_d(m->epot, m->tmp, perm, n, 1);
+    permute_d(m->ekin, m->tmp, perm, n, 1);
+    for (int s = 0; s < n; s++) {
+        m->ityp[s] = m->oityp[m->ngid[s] - 1];
+        m->statu[s] = m->ostatu[m->ngid[s] - 1];
+    }
+    memcpy(m->gid, m->ngid, sizeof(int) * n);
+    m->haspart++;
+    (void)nnmax;
+    return nout;
+}
+
+void orc_md_force(orc_md *m, int with_virial)
+{
+    int n = m->n;
+    orc_force_pass1(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->den);
+    orc_force_pass2(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->den,
+                    m->fp, n, with_virial ? m->vtensor : NULL);
+    if (with_virial) /* COPYOUT_VIRIALTENSOR, MD_EAM_ForceTable_GPU.F90:1462-1463 */
+        for (int i = 0; i < 9; i++) m->vtensor[i] = m->vtensor[i] / (double)(m->n / m->napb);
+}
+
+void orc_md_epot(orc_md *m)
+{
+    int n = m->n;
+    orc_force_epot(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->epot);
+}
+
+int orc_md_step(orc_md *m, int itime, int it0, int nb_uptab, double h)
+{
+    /* For_One_Step, Appshell/MD_Method_GenericMD_GPU.F90:596-627 */
+    int n = m->n, rebuilt = 0;
+    orc_predictor(n, m->xp, m->xp1, m->fp, m->dis, m->statu, m->ityp, m->cm, h, m->boxlow, m->boxup, m->zl, m->ifpd);
+    if ((itime - it0) % nb_uptab == 0) { /* Fortran MOD keeps the sign, as C % does */
+        orc_md_rebuild(m);
+        rebuilt = 1;
+    }
+    orc_md_force(m, 0);
+    if (m->epc_on)
+        orc_epc(n, m->xp1, m->fp, m->statu, m->ityp, m->ng, m->epc_enable, m->cm, m->epc_te, m->epc_alpha,
+                m->epc_cut, m->epc_he);
+    orc_corrector(n, m->xp1, m->fp, m->statu, m->ityp, m->cm, h);
+    return rebuilt;
+}
+
+void orc_md_get(orc_md *m, double *xp, double *xp1, double *fp, double *epot, double *ekin, double *dis, int *statu,
+                int *gid, double *vtensor)
+{
+    int n = m->n;
+    if (ekin) orc_ekin(n, m->xp1, m->statu, m->ityp, m->cm, m->ekin);
+    for (int s = 0; s < n; s++) {
+        int o = m->gid[s] - 1;
+        for (int d = 0; d < 3; d++) {
+            if (xp) xp[o + (size_t)d * n] = m->xp[s + (size_t)d * n];
+            if (xp1) xp1[o + (size_t)d * n] = m->xp1[s + (size_t)d * n];
+            if (fp) fp[o + (size_t)d * n] = m->fp[s + (size_t)d * n];
+            if (dis) dis[o + (size_t)d * n] = m->dis[s + (size_t)d * n];
+        }
+        if (epot) epot[o] = m->epot[s];
+        if (ekin) ekin[o] = m->ekin[s];
+        if (statu) statu[o] = m->statu[s];
+        if (gid) gid[s] = m->gid[s];
+    }
+    if (vtensor) memcpy(vtensor, m->vtensor, sizeof(double) * 9);
+}
+
+int orc_md_natom(orc_md *m) { return m->n; }
+const int *orc_md_kvois(orc_md *m) { return m->kvois; }
+const int *orc_md_indi(orc_md *m) { return m->indi; }
+void orc_md_ncell(orc_md *m, int ncell[3]) { for (int d = 0; d < 3; d++) ncell[d] = m->ncell[d]; }

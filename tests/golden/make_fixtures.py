@@ -1,0 +1,73 @@
+"""Regenerates the committed golden fixtures from the reference tree (run in the build
+container only: /root/reference does not exist on the GPU box).
+
+    python tests/golden/make_fixtures.py [/root/reference]
+
+Outputs (small, committed):
+  neb_gmd_react.npz / neb_gmd_product.npz
+      the reference GPU build's own step-0 output for examples/NEB_Test (2000 W + 1 H,
+      Bonny EAM1): per-atom type, position [LU], force [eV/LU], POT [eV] (= -EPOT)
+      from examples/NEB_Test/GMD/{React,Product}P0000_0001.0000 (&BOXCFG18 columns
+      TYPE, POS(3), VEL(3), STATU, FOR(3), POT, K.E., DISPLACE(3)).
+  bonny_eam1_embd_rows.npz
+      sampled rows of examples/use_ForceTableGen/EAM_WHeH_Bonny_JPCM26_2014.embd
+      (Export_ForceTable output: RHO, F_k(RHO), dF_k/dRHO for the 9 ids).
+  box/control text files used by those runs are copied verbatim (inputs, not source code).
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def read_cfg18(path):
+    rows = []
+    with open(path) as f:
+        started = False
+        for line in f:
+            if not started:
+                if line.lstrip().upper().startswith("&TYPE "):
+                    started = True
+                continue
+            p = line.split()
+            if len(p) >= 16:
+                rows.append([float(x) for x in p[:16]])
+    a = np.array(rows)
+    return dict(ityp=a[:, 0].astype(np.int32), pos=a[:, 1:4], vel=a[:, 4:7], statu=a[:, 7].astype(np.int32),
+                force=a[:, 8:11], pot=a[:, 11], ekin=a[:, 12], dis=a[:, 13:16])
+
+
+def main():
+    neb = os.path.join(REF, "examples", "NEB_Test")
+    for tag, name in (("react", "ReactP0000_0001.0000"), ("product", "ProductP0000_0001.0000")):
+        d = read_cfg18(os.path.join(neb, "GMD", name))
+        assert d["pos"].shape == (2001, 3)
+        np.savez_compressed(os.path.join(HERE, "neb_gmd_%s.npz" % tag), ityp=d["ityp"], pos=d["pos"],
+                            statu=d["statu"], force=d["force"], pot=d["pot"])
+    for fn in ("W_2000_H1_EAM1_box.dat", "CtrlFile0K.dat"):
+        shutil.copyfile(os.path.join(neb, fn), os.path.join(HERE, fn))
+    with open(os.path.join(neb, "GMD", "thermP0000_0001")) as f:
+        open(os.path.join(HERE, "neb_gmd_therm.txt"), "w").write(f.read())
+
+    # exported embedding table (10 significant digits)
+    path = os.path.join(REF, "examples", "use_ForceTableGen", "EAM_WHeH_Bonny_JPCM26_2014.embd")
+    rows = []
+    with open(path) as f:
+        for line in f:
+            p = line.split()
+            if len(p) == 20 and p[0].isdigit():
+                rows.append([float(x) for x in p])
+    a = np.array(rows)
+    assert a.shape[0] == 10000, a.shape
+    sel = np.unique(np.concatenate([np.arange(0, 64), np.arange(64, 10000, 97), [9998, 9999]]))
+    np.savez_compressed(os.path.join(HERE, "bonny_eam1_embd_rows.npz"), index=a[sel, 0].astype(np.int32),
+                        rho=a[sel, 1], f=a[sel, 2::2], df=a[sel, 3::2])
+    print("fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
