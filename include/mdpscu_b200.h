@@ -1,0 +1,223 @@
+/*
+ * mdpscu_b200.h -- C ABI of the B200-native MDPSCU hot path (libmdpscu_b200.so).
+ *
+ * One context = one GPU = one host process/rank.  The context owns the device "box"
+ * (the reference's dm_WorkSpace), the neighbour list (dm_Neighbors), the force tables
+ * (dm_FTableWS) and a CUDA stream on which every kernel of the path is launched.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference root, MDLIB/sor/ prefix dropped).  All calls return an int status:
+ *   0 = ok, >0 = a count the caller may act on (out-of-box atoms, list overflow),
+ *   <0 = MDB_ERR_*.  Nothing here prints, reads stdin or stops the process
+ * (the reference does all three: CommonGPU/MD_NeighborsList_GPU.F90:1506-1524).
+ *
+ * Array conventions are the reference's: Fortran column-major, XP(N,3) = x[0..N) y z,
+ * 1-based atom ids / table ids / ITYP, CGS units.  "ORIGINAL" order = the order the
+ * atoms had when first uploaded (SimMDBox order); "CELL" order = current device order
+ * (cell-sorted; changes at every neighbour rebuild; GID maps CELL -> ORIGINAL).
+ */
+#ifndef MDPSCU_B200_H
+#define MDPSCU_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB_MXGROUP 10 /* mp_MXGROUP, Common/MD_Const.F90 */
+
+typedef struct mdb_ctx mdb_ctx;
+
+/* ---- status codes */
+#define MDB_OK               0
+#define MDB_ERR_CUDA        -1
+#define MDB_ERR_ARG         -2
+#define MDB_ERR_STATE       -3  /* call order: box/tables/nlist not set                       */
+#define MDB_ERR_UNSUPPORTED -4  /* e.g. non-identity BOXSHAPE in the fast force path           */
+#define MDB_ERR_NOMEM       -5
+#define MDB_ERR_NOGPU       -6  /* no CUDA device: the product path has no CPU fallback        */
+
+/* ---- orders */
+#define MDB_ORDER_ORIGINAL 0
+#define MDB_ORDER_CELL     1
+
+/* ---- fields (dm_WorkSpace / dm_Neighbors members, CommonGPU/MD_Globle_Variables_GPU.F90:158-194,
+ *      CommonGPU/MD_NeighborsList_GPU.F90:75-85).  Shapes as the reference declares them. */
+#define MDB_F_XP      0  /* double (N,3)  positions                                          */
+#define MDB_F_XP1     1  /* double (N,3)  velocities                                         */
+#define MDB_F_FP      2  /* double (N,3)  forces                                             */
+#define MDB_F_DIS     3  /* double (N,3)  accumulated displacement                           */
+#define MDB_F_EPOT    4  /* double (N)                                                       */
+#define MDB_F_EKIN    5  /* double (N)                                                       */
+#define MDB_F_DEN     6  /* double (N)    dF/drho (EAM) or -1/(2 sqrt(rho)) (FS)             */
+#define MDB_F_ITYP    7  /* int (N)                                                          */
+#define MDB_F_STATU   8  /* int (N)                                                          */
+#define MDB_F_GID     9  /* int (N)       CELL position -> ORIGINAL id (1-based)             */
+#define MDB_F_GIDINV 10  /* int (N)       ORIGINAL id -> CELL position (1-based)             */
+#define MDB_F_IC     11  /* int (N)       cell id of each atom (CELL order), -1/-2 if outside */
+#define MDB_F_KVOIS  12  /* int (N)                                                          */
+#define MDB_F_INDI   13  /* int (N,mxKVOIS) neighbour ids, 1-based CELL-order ids            */
+#define MDB_F_NAC    14  /* int (NC)      atoms per cell                                     */
+#define MDB_F_NAAC   15  /* int (NC)      ACTIVE atoms per cell                              */
+#define MDB_F_IA1TH  16  /* int (NC)      1-based id of the first atom of each cell          */
+#define MDB_F__COUNT 17
+
+/* ---- potential types: Register_ForceClass("EAM_TYPE"|"FS_TYPE"), CommonGPU/MD_ForceClass_Register_GPU.F90:363-442 */
+#define MDB_POT_EAM 0
+#define MDB_POT_FS  1
+
+/* ---- mdb_force flags */
+#define MDB_FORCE    1u  /* pCalForce  -> CALFORCE_EAM_Force_Table2A_DEV, CommonGPU/MD_EAM_ForceTable_GPU.F90:950      */
+#define MDB_VIRIAL   2u  /* pCalPTensor-> CALPTENSOR_EAM_Force_Table2A_DEV, :1366 (forces + virial)                     */
+#define MDB_EPOT     4u  /* pCalEpot0  -> UpdateEPOT_EAM_Force_Table2A_DEV, :1710                                       */
+#define MDB_DEN      8u  /* pCalEDen   -> CALDEN_EAM_Force_Table2A_DEV, :891 (pass 1 only)                              */
+
+/* ------------------------------------------------------------------------------------
+ * context / device selection
+ * replaces Initialize_DEVICES + m_DEVICES (MSMLIB/sor/CommonGPU/MSM_MultiGPU_Basic.F90:571-597):
+ * one rank per GPU instead of one host thread looping cudaSetDevice.
+ * ---------------------------------------------------------------------------------- */
+int         mdb_device_count(void);
+int         mdb_ctx_create(int device_id, mdb_ctx **out);
+void        mdb_ctx_destroy(mdb_ctx *ctx);
+const char *mdb_last_error(const mdb_ctx *ctx);
+const char *mdb_version(void);
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = the context's own */
+int         mdb_ctx_set_stream(mdb_ctx *ctx, void *cuda_stream);
+void       *mdb_ctx_stream(mdb_ctx *ctx);
+int         mdb_sync(mdb_ctx *ctx); /* SynchronizeDevices */
+
+/* ------------------------------------------------------------------------------------
+ * device box: Initialize_Globle_Variables_DEV / Allocate_Working_Variables
+ * (CommonGPU/MD_Globle_Variables_GPU.F90:585,767-857).  nbox boxes of natom_per_box atoms are
+ * concatenated (MULTIBOX, :601-606).  boxshape is column-major 3x3.
+ * ---------------------------------------------------------------------------------- */
+int mdb_box_set(mdb_ctx *ctx, int nbox, int natom_per_box, const double boxlow[3], const double boxsize[3],
+                const double boxshape[9], const int ifpd[3], int ngroup, const double mass[]);
+int mdb_natom(const mdb_ctx *ctx);
+
+/* CopyIn_SimBox_DEV / CopyOut_SimBox_DEV (CommonGPU/MD_SimBoxArray_GPU.F90:91-318) and the
+ * CopyXXFrom_Devices_to_Host family (MD_Globle_Variables_GPU.F90:196-510), one field at a time.
+ * host buffers have the reference shape of the field. */
+int mdb_state_upload(mdb_ctx *ctx, int field, const void *host, int order);
+int mdb_state_download(mdb_ctx *ctx, int field, void *host, int order);
+/* device pointer with the reference shape (CELL order), for CUDA(-Fortran) code that reads
+ * dm_WorkSpace / dm_Neighbors arrays directly (Analysis/, BoostMeths/ ...).  XP, DEN and INDI are
+ * materialised from the packed internal layout on request and stay valid until the next
+ * mdb_* call that changes them. */
+void *mdb_devptr(mdb_ctx *ctx, int field);
+
+/* ------------------------------------------------------------------------------------
+ * force tables: pIniForcetable -> INITIALIZE_EAM_Force_Table_DEV
+ * (CommonGPU/MD_EAM_ForceTable_GPU.F90:192-278; FS twin MD_FS_ForceTable_GPU.F90).
+ * Tables exactly as type MDForceTable holds them (Common/MD_TypeDef_ForceTable.F90:117-155):
+ * POTR,FPOTR,POTB,FPOTB(NKIND,NTAB), FEMBD,DFEMBD(NKIND1,NEMBD) column-major,
+ * KPAIR(NG,NG) column-major, KEMBD(NG), CSI, RHOD; ru2max = maxval(RU*RU) (:261-262).
+ * ---------------------------------------------------------------------------------- */
+int mdb_tables_set(mdb_ctx *ctx, int pot_type, int nkind, int ntab, double csi,
+                   const double *potr, const double *fpotr, const double *potb, const double *fpotb,
+                   int nkind1, int nembd, double rhod, const double *fembd, const double *dfembd,
+                   const int *kpair, const int *kembd, double ru2max);
+int mdb_tables_clear(mdb_ctx *ctx); /* pClrForcetable -> Clear_EAM_Force_Table_DEV :343 */
+
+/* ------------------------------------------------------------------------------------
+ * neighbour list: Initialize_NeighboreList_DEV / Cal_NeighBoreList_DEV / Copyout_NeighboreList_DEV /
+ * GetCellInform / Clear_NeighboreList_DEV (CommonGPU/MD_NeighborsList_GPU.F90:116-202,241-396,1347-1732)
+ * nb_rm(NG,NG) column-major in cm.  mdb_nlist_build returns the number of out-of-box atoms (they
+ * are marked OUTOFBOX and parked at the end of the CELL order, :1624-1637) or <0.
+ * mdb_nlist_overflow: atoms whose un-truncated count exceeded mxkvois (the reference truncates
+ * silently and warns once, :1126-1131,1709-1718).
+ * ---------------------------------------------------------------------------------- */
+int mdb_nlist_init(mdb_ctx *ctx, const double *nb_rm, int mxkvois);
+int mdb_nlist_build(mdb_ctx *ctx);
+int mdb_nlist_copyout(mdb_ctx *ctx, int *kvois, int *indi, int order);
+int mdb_nlist_cellinfo(const mdb_ctx *ctx, int ncell[3], int *nc_total, int *mxnac);
+int mdb_nlist_overflow(mdb_ctx *ctx);
+int mdb_nlist_clear(mdb_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------
+ * force class slots (type MDForceClassGPU, CommonGPU/MD_ForceClass_Register_GPU.F90:248-259)
+ * vtensor (3,3) column-major, already divided by the number of boxes (COPYOUT_VIRIALTENSOR :1462);
+ * may be NULL unless MDB_VIRIAL is set.
+ * ---------------------------------------------------------------------------------- */
+int mdb_force(mdb_ctx *ctx, unsigned flags, double vtensor[9]);
+
+/* ------------------------------------------------------------------------------------
+ * integrator: Predictor_DEV / Correction_DEV / CalEKin_DEV (CommonGPU/MD_DiffScheme_GPU.F90:604,821,1000)
+ * ---------------------------------------------------------------------------------- */
+int mdb_predict(mdb_ctx *ctx, double h);
+int mdb_correct(mdb_ctx *ctx, double h);
+int mdb_ekin(mdb_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------
+ * electron-phonon coupling: Do_ResetParam_DEV / Do_EPCForce_DEV
+ * (LocalTempCtrlMeths/MD_LocalTempMethod_GPU.F90:95-138 -> EPC/MD_EP_Coupling_GPU.F90:370-417,421-493)
+ * per-group arrays of length ngroup: enable flag, electron temperature TI [K], EPC_ALPHA [s],
+ * EPC_CUT, EPC_HE [erg] (Common/MD_TypeDef_EPCCtrl.F90:27-37).
+ * ---------------------------------------------------------------------------------- */
+int mdb_epc_set(mdb_ctx *ctx, const int *enable, const double *te, const double *alpha, const double *cut,
+                const double *he);
+int mdb_epc_apply(mdb_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------
+ * one whole MD step, For_One_Step (Appshell/MD_Method_GenericMD_GPU.F90:496-659):
+ * predictor -> [rebuild if MOD(itime-it0,nb_uptab)==0] -> force -> EPC -> corrector,
+ * with the element-wise stages fused into the force passes where no rebuild intervenes.
+ * mdb_run repeats it nsteps times without returning to the host (itime = itime0 .. itime0+nsteps-1).
+ * Both return the accumulated out-of-box count (>=0) or <0.
+ * ---------------------------------------------------------------------------------- */
+int mdb_step(mdb_ctx *ctx, int itime, int it0, int nb_uptab, double h);
+int mdb_run(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double h);
+
+/* ------------------------------------------------------------------------------------
+ * options.  MDB_OPT_FORCE_PATH selects the force/list implementation:
+ *   AUTO    the tiled fast path when the configuration fits it, else the generic one
+ *   GENERIC thread-per-atom over INDI, un-fused arithmetic in reference order (bit-faithful)
+ *   TILED   shared-memory staged halo tiles + two-phase (fp32 filter / fp64 evaluate) kernels
+ * ---------------------------------------------------------------------------------- */
+#define MDB_OPT_FORCE_PATH 0
+#define MDB_FORCE_PATH_AUTO    0
+#define MDB_FORCE_PATH_GENERIC 1
+#define MDB_FORCE_PATH_TILED   2
+int mdb_set_option(mdb_ctx *ctx, int option, int value);
+int mdb_get_option(const mdb_ctx *ctx, int option);
+
+/* ------------------------------------------------------------------------------------
+ * measurement support (not in the reference, which only has CPU_TIME stopwatches):
+ * CUDA-event timing per kernel class on the context's stream.  Class ids below.
+ * ---------------------------------------------------------------------------------- */
+#define MDB_K_CELLSORT 0
+#define MDB_K_NLIST    1
+#define MDB_K_PASS1    2
+#define MDB_K_PASS2    3
+#define MDB_K_EPOT     4
+#define MDB_K_PREDICT  5
+#define MDB_K_CORRECT  6
+#define MDB_K_OTHER    7
+#define MDB_K__COUNT   8
+int mdb_prof_enable(mdb_ctx *ctx, int on);
+int mdb_prof_reset(mdb_ctx *ctx);
+/* launches[k] = kernel launches recorded for class k, ms[k] = summed device time */
+int mdb_prof_get(mdb_ctx *ctx, long long launches[MDB_K__COUNT], double ms[MDB_K__COUNT]);
+long long mdb_launch_count(const mdb_ctx *ctx); /* all kernel launches since creation/reset */
+
+/* ------------------------------------------------------------------------------------
+ * host-side table generators mirroring the potential libraries' Register_Interaction_Table
+ * (Potentials/EAM_WW_Marinica_JPCM25_2013/EAM_ForceTable_Marinica_JPCM25_2013.F90:17-83,
+ *  Potentials/EAM_WHeH_Bonny_JPCM26_2014/EAM_ForceTable_Bonny_JPCM26_2014.F90:17-140) ->
+ * Create_Interaction_ForceTable (Common/MD_TypeDef_ForceTable.F90:1151-1230).
+ * In a Fortran deployment the unchanged potential modules fill MDForceTable and call
+ * mdb_tables_set; these exist so that C/C++/Python hosts can run the path standalone.
+ * ptype(NG,NG) column-major; rmax: table range (the shipped source uses max(RU), :591).
+ * Output arrays are caller-allocated: pair tables ng*ng*ntab doubles, embedding ng*nembd.
+ * ---------------------------------------------------------------------------------- */
+#define MDB_LIB_MARINICA_EAM2 1
+#define MDB_LIB_BONNY_EAM1    2
+int mdb_host_ftable_create(int lib, int ng, const int *ptype, int ntab, int nembd, double rhoscal, double rmax,
+                           int *nkind, int *nkind1, int *kpair, int *kembd,
+                           double *potr, double *fpotr, double *potb, double *fpotb,
+                           double *fembd, double *dfembd, double *csi, double *rhod);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

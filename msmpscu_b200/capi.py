@@ -1,0 +1,289 @@
+"""ctypes binding of libmdpscu_b200.so (the C ABI in include/mdpscu_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing this module raises at
+import of the symbol table, and creating a context without a CUDA device raises MDBError
+(MDB_ERR_NOGPU).  Nothing here imports the CPU oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmdpscu_b200.so")
+
+MXGROUP = 10
+
+OK = 0
+ERR_CUDA, ERR_ARG, ERR_STATE, ERR_UNSUPPORTED, ERR_NOMEM, ERR_NOGPU = -1, -2, -3, -4, -5, -6
+ORDER_ORIGINAL, ORDER_CELL = 0, 1
+(F_XP, F_XP1, F_FP, F_DIS, F_EPOT, F_EKIN, F_DEN, F_ITYP, F_STATU, F_GID, F_GIDINV, F_IC, F_KVOIS, F_INDI,
+ F_NAC, F_NAAC, F_IA1TH) = range(17)
+POT_EAM, POT_FS = 0, 1
+FORCE, VIRIAL, EPOT, DEN = 1, 2, 4, 8
+K_NAMES = ("cellsort", "nlist", "pass1", "pass2", "epot", "predict", "correct", "other")
+K_COUNT = 8
+LIB_MARINICA_EAM2, LIB_BONNY_EAM1 = 1, 2
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+# every symbol include/mdpscu_b200.h declares: (restype, argtypes)
+SYMBOLS = {
+    "mdb_device_count": (C.c_int, []),
+    "mdb_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "mdb_ctx_destroy": (None, [C.c_void_p]),
+    "mdb_last_error": (C.c_char_p, [C.c_void_p]),
+    "mdb_version": (C.c_char_p, []),
+    "mdb_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdb_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "mdb_sync": (C.c_int, [C.c_void_p]),
+    "mdb_box_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_ip, C.c_int, c_dp]),
+    "mdb_natom": (C.c_int, [C.c_void_p]),
+    "mdb_state_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "mdb_state_download": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "mdb_devptr": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "mdb_tables_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp, C.c_int,
+                                 C.c_int, C.c_double, c_dp, c_dp, c_ip, c_ip, C.c_double]),
+    "mdb_tables_clear": (C.c_int, [C.c_void_p]),
+    "mdb_nlist_init": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
+    "mdb_nlist_build": (C.c_int, [C.c_void_p]),
+    "mdb_nlist_copyout": (C.c_int, [C.c_void_p, c_ip, c_ip, C.c_int]),
+    "mdb_nlist_cellinfo": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip]),
+    "mdb_nlist_overflow": (C.c_int, [C.c_void_p]),
+    "mdb_nlist_clear": (C.c_int, [C.c_void_p]),
+    "mdb_force": (C.c_int, [C.c_void_p, C.c_uint, c_dp]),
+    "mdb_predict": (C.c_int, [C.c_void_p, C.c_double]),
+    "mdb_correct": (C.c_int, [C.c_void_p, C.c_double]),
+    "mdb_ekin": (C.c_int, [C.c_void_p]),
+    "mdb_epc_set": (C.c_int, [C.c_void_p, c_ip, c_dp, c_dp, c_dp, c_dp]),
+    "mdb_epc_apply": (C.c_int, [C.c_void_p]),
+    "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mdb_get_option": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdb_prof_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdb_prof_reset": (C.c_int, [C.c_void_p]),
+    "mdb_prof_get": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), c_dp]),
+    "mdb_launch_count": (C.c_longlong, [C.c_void_p]),
+    "mdb_host_ftable_create": (C.c_int, [C.c_int, C.c_int, c_ip, C.c_int, C.c_int, C.c_double, C.c_double, c_ip, c_ip,
+                                         c_ip, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+}
+
+OPT_FORCE_PATH = 0
+FORCE_PATH_AUTO, FORCE_PATH_GENERIC, FORCE_PATH_TILED = 0, 1, 2
+
+_lib = None
+
+
+class MDBError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mdpscu_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    """Load the shared library and bind every symbol.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "msmpscu_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C msmpscu_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def colmajor(a):
+    """(N,k) -> flat Fortran-order copy (the reference's array layout)."""
+    a = np.asarray(a, dtype=np.float64)
+    return np.ascontiguousarray(a.T).ravel() if a.ndim == 2 else np.ascontiguousarray(a)
+
+
+def from_colmajor(flat, n, ncol):
+    return np.ascontiguousarray(flat.reshape(ncol, n).T) if ncol > 1 else flat
+
+
+class Context:
+    """Thin RAII wrapper of mdb_ctx; methods map 1:1 to the C ABI."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.mdb_ctx_create(int(device), C.byref(h))
+        if rc != OK:
+            msg = {ERR_NOGPU: "no CUDA device visible (the product path has no CPU fallback)"}.get(rc, "mdb_ctx_create failed")
+            raise MDBError(rc, msg)
+        self.h = h
+        self.n = 0
+        self.mxkvois = 0
+        self.nc = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mdb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise MDBError(rc, self.lib.mdb_last_error(self.h).decode())
+        return rc
+
+    # ---- box / state
+    def box_set(self, nbox, napb, boxlow, boxsize, ifpd, mass, boxshape=None):
+        lo, sz, m = f64(boxlow), f64(boxsize), f64(mass)
+        pd = i32(ifpd)
+        bs = f64(boxshape).T.ravel().copy() if boxshape is not None else None
+        self._chk(self.lib.mdb_box_set(self.h, nbox, napb, dp(lo), dp(sz), dp(bs) if bs is not None else None, ip(pd),
+                                       len(m), dp(m)))
+        self.n = nbox * napb
+        self.ng = len(m)
+
+    def upload(self, field, arr, order=ORDER_ORIGINAL):
+        if field in (F_ITYP, F_STATU):
+            a = i32(arr)
+        else:
+            a = colmajor(arr)
+        self._chk(self.lib.mdb_state_upload(self.h, field, a.ctypes.data_as(C.c_void_p), order))
+
+    def upload_raw(self, field, ptr, order=ORDER_ORIGINAL):
+        """host pointer (int) with the reference layout, e.g. a pinned torch tensor's data_ptr()."""
+        self._chk(self.lib.mdb_state_upload(self.h, field, C.c_void_p(ptr), order))
+
+    def download_raw(self, field, ptr, order=ORDER_ORIGINAL):
+        self._chk(self.lib.mdb_state_download(self.h, field, C.c_void_p(ptr), order))
+
+    def download(self, field, order=ORDER_ORIGINAL):
+        n = self.n
+        if field in (F_XP, F_XP1, F_FP, F_DIS):
+            buf = np.empty(3 * n)
+            self._chk(self.lib.mdb_state_download(self.h, field, buf.ctypes.data_as(C.c_void_p), order))
+            return from_colmajor(buf, n, 3)
+        if field in (F_EPOT, F_EKIN, F_DEN):
+            buf = np.empty(n)
+        elif field in (F_NAC, F_NAAC, F_IA1TH):
+            buf = np.empty(self.cellinfo()[1], dtype=np.int32)
+        else:
+            buf = np.empty(n, dtype=np.int32)
+        self._chk(self.lib.mdb_state_download(self.h, field, buf.ctypes.data_as(C.c_void_p), order))
+        return buf
+
+    def devptr(self, field):
+        return self.lib.mdb_devptr(self.h, field)
+
+    # ---- tables
+    def tables_set(self, t, ru2max):
+        """t: host MDForceTable-like object with Fortran-layout arrays (see forcetable.MDForceTable)."""
+        self._chk(self.lib.mdb_tables_set(
+            self.h, t.pot_type, t.nkind, t.ntab, t.csi, dp(t.potr), dp(t.fpotr), dp(t.potb), dp(t.fpotb), t.nkind1,
+            t.nembd, t.rhod, dp(t.fembd), dp(t.dfembd), ip(t.kpair), ip(t.kembd), float(ru2max)))
+
+    def tables_clear(self):
+        self._chk(self.lib.mdb_tables_clear(self.h))
+
+    # ---- neighbour list
+    def nlist_init(self, nb_rm, mxkvois):
+        a = f64(np.asarray(nb_rm, dtype=np.float64).T).ravel().copy()
+        self._chk(self.lib.mdb_nlist_init(self.h, dp(a), int(mxkvois)))
+        self.mxkvois = int(mxkvois)
+
+    def nlist_build(self):
+        return self._chk(self.lib.mdb_nlist_build(self.h))
+
+    def nlist_copyout(self, order=ORDER_CELL):
+        kv = np.empty(self.n, dtype=np.int32)
+        ind = np.empty(self.n * self.mxkvois, dtype=np.int32)
+        self._chk(self.lib.mdb_nlist_copyout(self.h, ip(kv), ip(ind), order))
+        return kv, ind.reshape(self.mxkvois, self.n)
+
+    def cellinfo(self):
+        nc3 = (C.c_int * 3)()
+        nc, mx = C.c_int(), C.c_int()
+        self._chk(self.lib.mdb_nlist_cellinfo(self.h, nc3, C.byref(nc), C.byref(mx)))
+        return list(nc3), nc.value, mx.value
+
+    def nlist_overflow(self):
+        return self._chk(self.lib.mdb_nlist_overflow(self.h))
+
+    # ---- force / integrator
+    def force(self, flags=FORCE):
+        vt = np.zeros(9)
+        self._chk(self.lib.mdb_force(self.h, flags, dp(vt)))
+        return vt.reshape(3, 3).T if (flags & VIRIAL) else None
+
+    def predict(self, h):
+        self._chk(self.lib.mdb_predict(self.h, float(h)))
+
+    def correct(self, h):
+        self._chk(self.lib.mdb_correct(self.h, float(h)))
+
+    def ekin(self):
+        self._chk(self.lib.mdb_ekin(self.h))
+
+    def epc_set(self, enable, te, alpha, cut, he):
+        self._chk(self.lib.mdb_epc_set(self.h, ip(i32(enable)), dp(f64(te)), dp(f64(alpha)), dp(f64(cut)), dp(f64(he))))
+
+    def epc_apply(self):
+        self._chk(self.lib.mdb_epc_apply(self.h))
+
+    def step(self, itime, it0, nb_uptab, h):
+        return self._chk(self.lib.mdb_step(self.h, itime, it0, nb_uptab, float(h)))
+
+    def run(self, itime0, nsteps, it0, nb_uptab, h):
+        return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    def sync(self):
+        self._chk(self.lib.mdb_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self.lib.mdb_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_option(self, opt, val):
+        self._chk(self.lib.mdb_set_option(self.h, opt, val))
+
+    def get_option(self, opt):
+        return self.lib.mdb_get_option(self.h, opt)
+
+    # ---- measurement
+    def prof_enable(self, on=True):
+        self._chk(self.lib.mdb_prof_enable(self.h, 1 if on else 0))
+
+    def prof_reset(self):
+        self._chk(self.lib.mdb_prof_reset(self.h))
+
+    def prof_get(self):
+        ln = (C.c_longlong * K_COUNT)()
+        ms = (C.c_double * K_COUNT)()
+        self._chk(self.lib.mdb_prof_get(self.h, ln, ms))
+        return {K_NAMES[k]: (int(ln[k]), float(ms[k])) for k in range(K_COUNT)}
+
+    def launch_count(self):
+        return int(self.lib.mdb_launch_count(self.h))

@@ -1,0 +1,633 @@
+// mdb_api.cu -- context, device box, host<->device field transfer, tables, profiling.
+// C ABI declared in include/mdpscu_b200.h (each entry cites the reference interface it replaces).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include "mdb_internal.cuh"
+
+// ------------------------------------------------------------------------------------
+// errors / profiling
+// ------------------------------------------------------------------------------------
+int mdb_fail(mdb_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+ProfScope::ProfScope(mdb_ctx *ctx, int klass, int nlaunch) : c(ctx), k(klass)
+{
+    c->launches_total += nlaunch;
+    c->prof_launches[k] += nlaunch;
+    if (!c->prof) return;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, c->stream);
+}
+ProfScope::~ProfScope()
+{
+    if (!a) return;
+    cudaEventRecord(b, c->stream);
+    c->ev_pending.push_back({a, b, k});
+    if (c->ev_pending.size() > 4096) mdb_prof_collect(c);
+}
+void mdb_prof_collect(mdb_ctx *c)
+{
+    if (c->ev_pending.empty()) return;
+    cudaEventSynchronize(c->ev_pending.back().b);
+    for (auto &e : c->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->prof_ms[e.k] += ms;
+        c->ev_pool.push_back(e.a);
+        c->ev_pool.push_back(e.b);
+    }
+    c->ev_pending.clear();
+}
+
+extern "C" int mdb_prof_enable(mdb_ctx *c, int on)
+{
+    if (!c) return MDB_ERR_ARG;
+    mdb_prof_collect(c);
+    c->prof = on != 0;
+    return MDB_OK;
+}
+extern "C" int mdb_prof_reset(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    mdb_prof_collect(c);
+    for (int k = 0; k < MDB_K__COUNT; k++) { c->prof_launches[k] = 0; c->prof_ms[k] = 0.0; }
+    c->launches_total = 0;
+    return MDB_OK;
+}
+extern "C" int mdb_prof_get(mdb_ctx *c, long long launches[MDB_K__COUNT], double ms[MDB_K__COUNT])
+{
+    if (!c) return MDB_ERR_ARG;
+    mdb_prof_collect(c);
+    for (int k = 0; k < MDB_K__COUNT; k++) { launches[k] = c->prof_launches[k]; ms[k] = c->prof_ms[k]; }
+    return MDB_OK;
+}
+extern "C" long long mdb_launch_count(const mdb_ctx *c) { return c ? c->launches_total : 0; }
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+extern "C" const char *mdb_version(void) { return "mdpscu_b200 0.1 (sm_100a)"; }
+
+extern "C" int mdb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int mdb_ctx_create(int device_id, mdb_ctx **out)
+{
+    if (!out) return MDB_ERR_ARG;
+    *out = nullptr;
+    int n = mdb_device_count();
+    if (n <= 0) return MDB_ERR_NOGPU; // no CPU fallback, by design
+    if (device_id < 0 || device_id >= n) return MDB_ERR_ARG;
+    if (cudaSetDevice(device_id) != cudaSuccess) return MDB_ERR_CUDA;
+    mdb_ctx *c = new mdb_ctx();
+    c->dev = device_id;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MDB_ERR_CUDA; }
+    c->stream = c->own_stream;
+    memset(&c->epc, 0, sizeof(c->epc));
+    memset(&c->tab, 0, sizeof(c->tab));
+    for (int k = 0; k < MDB_K__COUNT; k++) { c->prof_launches[k] = 0; c->prof_ms[k] = 0.0; }
+    if (cudaMalloc(&c->counters, sizeof(int) * CNT__N) != cudaSuccess ||
+        cudaMallocHost(&c->h_counters, sizeof(int) * CNT__N) != cudaSuccess) { delete c; return MDB_ERR_NOMEM; }
+    cudaMemset(c->counters, 0, sizeof(int) * CNT__N);
+    *out = c;
+    return MDB_OK;
+}
+
+template <class T> static void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
+
+static void free_state(mdb_ctx *c)
+{
+    dfree(c->pos); dfree(c->pos_alt); dfree(c->xp1); dfree(c->xp1_alt); dfree(c->fp); dfree(c->fp_alt);
+    dfree(c->dis); dfree(c->dis_alt); dfree(c->epot); dfree(c->ekin); dfree(c->ityp); dfree(c->ityp_alt);
+    dfree(c->statu); dfree(c->statu_alt); dfree(c->gid); dfree(c->gid_alt); dfree(c->gidinv);
+    dfree(c->ic); dfree(c->ic_alt); dfree(c->xp_view); dfree(c->den_view);
+    dfree(c->slot); dfree(c->srcof); dfree(c->tmp_orig); dfree(c->oob); dfree(c->vpart);
+    if (c->stage) { cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
+    c->has_box = false;
+}
+static void free_nlist(mdb_ctx *c)
+{
+    dfree(c->nac); dfree(c->naac); dfree(c->ia1th); dfree(c->kvois); dfree(c->indi);
+    c->has_nlist = false; c->list_valid = false;
+}
+static void free_tables(mdb_ctx *c)
+{
+    for (void *p : c->tab_allocs) cudaFree(p);
+    c->tab_allocs.clear();
+    c->has_tables = false;
+}
+
+extern "C" void mdb_ctx_destroy(mdb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->stream);
+    mdb_prof_collect(c);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    free_state(c); free_nlist(c); free_tables(c);
+    if (c->counters) cudaFree(c->counters);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->hstage) cudaFreeHost(c->hstage);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (option == MDB_OPT_FORCE_PATH && value >= MDB_FORCE_PATH_AUTO && value <= MDB_FORCE_PATH_TILED) {
+        c->opt_force_path = value;
+        c->list_valid = false; // the two paths keep different list formats
+        return MDB_OK;
+    }
+    return mdb_fail(c, MDB_ERR_ARG, "mdb_set_option: unknown option %d / value %d", option, value);
+}
+extern "C" int mdb_get_option(const mdb_ctx *c, int option)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (option == MDB_OPT_FORCE_PATH) return c->opt_force_path;
+    return MDB_ERR_ARG;
+}
+
+extern "C" const char *mdb_last_error(const mdb_ctx *c) { return c ? c->err.c_str() : "null context"; }
+extern "C" int mdb_ctx_set_stream(mdb_ctx *c, void *s)
+{
+    if (!c) return MDB_ERR_ARG;
+    cudaStreamSynchronize(c->stream);
+    mdb_prof_collect(c);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return MDB_OK;
+}
+extern "C" void *mdb_ctx_stream(mdb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int mdb_sync(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// box
+// ------------------------------------------------------------------------------------
+__global__ void k_iota(int n, int *a, int *b)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = i + 1; b[i] = i + 1; }
+}
+
+extern "C" int mdb_box_set(mdb_ctx *c, int nbox, int napb, const double boxlow[3], const double boxsize[3],
+                           const double boxshape[9], const int ifpd[3], int ngroup, const double mass[])
+{
+    if (!c || nbox < 1 || napb < 1 || ngroup < 1 || ngroup > MDB_MXGROUP) return mdb_fail(c, MDB_ERR_ARG, "mdb_box_set: bad argument");
+    if ((long long)nbox * napb > 2000000000LL) return mdb_fail(c, MDB_ERR_ARG, "mdb_box_set: too many atoms for int32 ids");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    int n = nbox * napb;
+    bool realloc = !c->has_box || n != c->n;
+    c->nbox = nbox; c->napb = napb; c->ng = ngroup;
+    for (int d = 0; d < 3; d++) {
+        c->box.lo[d] = boxlow[d];
+        c->box.size[d] = boxsize[d];
+        c->box.up[d] = boxlow[d] + boxsize[d]; // BOXUP = BOXLOW + ZL, Common/MD_Gvar.F90:927
+        c->box.half[d] = boxsize[d] * 0.5;     // HBX = BX*C_HALF
+        c->box.pd[d] = ifpd[d];
+    }
+    c->shape_identity = true;
+    for (int i = 0; i < 9; i++) {
+        c->boxshape[i] = boxshape ? boxshape[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+        if (c->boxshape[i] != ((i % 4 == 0) ? 1.0 : 0.0)) c->shape_identity = false;
+    }
+    for (int g = 0; g < ngroup; g++) c->mass.cm[g] = mass[g];
+    if (realloc) {
+        free_state(c);
+        free_nlist(c);
+        c->n = n;
+        size_t n3 = (size_t)n * 3;
+#define ALLOC(p, T, cnt) CUDA_TRY(c, cudaMalloc(&c->p, sizeof(T) * (cnt)))
+        ALLOC(pos, double4, n); ALLOC(pos_alt, double4, n);
+        ALLOC(xp1, double, n3); ALLOC(xp1_alt, double, n3);
+        ALLOC(fp, double, n3); ALLOC(fp_alt, double, n3);
+        ALLOC(dis, double, n3); ALLOC(dis_alt, double, n3);
+        ALLOC(epot, double, n); ALLOC(ekin, double, n);
+        ALLOC(ityp, int, n); ALLOC(ityp_alt, int, n);
+        ALLOC(statu, int, n); ALLOC(statu_alt, int, n);
+        ALLOC(gid, int, n); ALLOC(gid_alt, int, n); ALLOC(gidinv, int, n);
+        ALLOC(ic, int, n); ALLOC(ic_alt, int, n);
+        ALLOC(slot, int, n); ALLOC(srcof, int, n); ALLOC(tmp_orig, int, n); ALLOC(oob, int, n);
+#undef ALLOC
+        CUDA_TRY(c, cudaMemsetAsync(c->pos, 0, sizeof(double4) * n, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->xp1, 0, sizeof(double) * n3, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->fp, 0, sizeof(double) * n3, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->dis, 0, sizeof(double) * n3, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->epot, 0, sizeof(double) * n, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->ekin, 0, sizeof(double) * n, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->ityp, 0, sizeof(int) * n, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->statu, 0, sizeof(int) * n, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->ic, 0, sizeof(int) * n, c->stream));
+        k_iota<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->gid, c->gidinv);
+        CUDA_TRY(c, cudaGetLastError());
+        c->oob_total = 0;
+    }
+    c->has_box = true;
+    c->list_valid = false;
+    return MDB_OK;
+}
+
+extern "C" int mdb_natom(const mdb_ctx *c) { return c ? c->n : 0; }
+
+// ------------------------------------------------------------------------------------
+// field transfer
+// ------------------------------------------------------------------------------------
+// map == nullptr : CELL order, identity.  map = gidinv : host index o (ORIGINAL) <-> device map[o]-1
+__global__ void k_up_d(int n, int ncol, const double *__restrict__ src, double *__restrict__ dst,
+                       const int *__restrict__ map)
+{
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    int d = map ? map[o] - 1 : o;
+    for (int cc = 0; cc < ncol; cc++) dst[d + (size_t)cc * n] = src[o + (size_t)cc * n];
+}
+__global__ void k_down_d(int n, int ncol, const double *__restrict__ src, double *__restrict__ dst,
+                         const int *__restrict__ map)
+{
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    int d = map ? map[o] - 1 : o;
+    for (int cc = 0; cc < ncol; cc++) dst[o + (size_t)cc * n] = src[d + (size_t)cc * n];
+}
+__global__ void k_up_i(int n, const int *__restrict__ src, int *__restrict__ dst, const int *__restrict__ map)
+{
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    dst[map ? map[o] - 1 : o] = src[o];
+}
+__global__ void k_down_i(int n, const int *__restrict__ src, int *__restrict__ dst, const int *__restrict__ map)
+{
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    dst[o] = src[map ? map[o] - 1 : o];
+}
+// pos {x,y,z,den}: which = 0 -> xyz (3 cols), 1 -> den (1 col)
+__global__ void k_up_pos(int n, int which, const double *__restrict__ src, double4 *__restrict__ pos,
+                         const int *__restrict__ map)
+{
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    int d = map ? map[o] - 1 : o;
+    double4 p = pos[d];
+    if (which == 0) { p.x = src[o]; p.y = src[o + (size_t)n]; p.z = src[o + 2 * (size_t)n]; }
+    else p.w = src[o];
+    pos[d] = p;
+}
+__global__ void k_down_pos(int n, int which, const double4 *__restrict__ pos, double *__restrict__ dst,
+                           const int *__restrict__ map)
+{
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    double4 p = pos[map ? map[o] - 1 : o];
+    if (which == 0) { dst[o] = p.x; dst[o + (size_t)n] = p.y; dst[o + 2 * (size_t)n] = p.z; }
+    else dst[o] = p.w;
+}
+
+static int ensure_stage(mdb_ctx *c, size_t bytes)
+{
+    if (c->stage_bytes >= bytes) return MDB_OK;
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr; c->stage_bytes = 0;
+    CUDA_TRY(c, cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return MDB_OK;
+}
+
+struct FieldInfo { int ncol; bool is_int; bool per_cell; };
+static bool field_info(int f, FieldInfo &fi)
+{
+    switch (f) {
+    case MDB_F_XP: case MDB_F_XP1: case MDB_F_FP: case MDB_F_DIS: fi = {3, false, false}; return true;
+    case MDB_F_EPOT: case MDB_F_EKIN: case MDB_F_DEN: fi = {1, false, false}; return true;
+    case MDB_F_ITYP: case MDB_F_STATU: case MDB_F_GID: case MDB_F_GIDINV: case MDB_F_IC: case MDB_F_KVOIS:
+        fi = {1, true, false}; return true;
+    case MDB_F_NAC: case MDB_F_NAAC: case MDB_F_IA1TH: fi = {1, true, true}; return true;
+    }
+    return false;
+}
+
+static double *dptr_d(mdb_ctx *c, int f)
+{
+    switch (f) {
+    case MDB_F_XP1: return c->xp1; case MDB_F_FP: return c->fp; case MDB_F_DIS: return c->dis;
+    case MDB_F_EPOT: return c->epot; case MDB_F_EKIN: return c->ekin;
+    }
+    return nullptr;
+}
+static int *dptr_i(mdb_ctx *c, int f)
+{
+    switch (f) {
+    case MDB_F_ITYP: return c->ityp; case MDB_F_STATU: return c->statu; case MDB_F_GID: return c->gid;
+    case MDB_F_GIDINV: return c->gidinv; case MDB_F_IC: return c->ic; case MDB_F_KVOIS: return c->kvois;
+    case MDB_F_NAC: return c->nac; case MDB_F_NAAC: return c->naac; case MDB_F_IA1TH: return c->ia1th;
+    }
+    return nullptr;
+}
+
+extern "C" int mdb_state_upload(mdb_ctx *c, int field, const void *host, int order)
+{
+    if (!c || !host) return mdb_fail(c, MDB_ERR_ARG, "mdb_state_upload: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_upload: mdb_box_set first");
+    FieldInfo fi;
+    if (!field_info(field, fi) || fi.per_cell || field == MDB_F_GID || field == MDB_F_GIDINV || field == MDB_F_KVOIS ||
+        field == MDB_F_IC)
+        return mdb_fail(c, MDB_ERR_ARG, "mdb_state_upload: field %d is not uploadable", field);
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    int n = c->n;
+    size_t bytes = (size_t)n * fi.ncol * (fi.is_int ? sizeof(int) : sizeof(double));
+    int rc = ensure_stage(c, bytes);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->stage, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    const int *map = (order == MDB_ORDER_ORIGINAL) ? c->gidinv : nullptr;
+    int nb = cdiv(n, 256);
+    ProfScope ps(c, MDB_K_OTHER);
+    if (field == MDB_F_XP) k_up_pos<<<nb, 256, 0, c->stream>>>(n, 0, (const double *)c->stage, c->pos, map);
+    else if (field == MDB_F_DEN) k_up_pos<<<nb, 256, 0, c->stream>>>(n, 1, (const double *)c->stage, c->pos, map);
+    else if (fi.is_int) k_up_i<<<nb, 256, 0, c->stream>>>(n, (const int *)c->stage, dptr_i(c, field), map);
+    else k_up_d<<<nb, 256, 0, c->stream>>>(n, fi.ncol, (const double *)c->stage, dptr_d(c, field), map);
+    CUDA_TRY(c, cudaGetLastError());
+    if (field == MDB_F_XP || field == MDB_F_ITYP || field == MDB_F_STATU) c->list_valid = c->list_valid && (field != MDB_F_ITYP);
+    return MDB_OK;
+}
+
+extern "C" int mdb_state_download(mdb_ctx *c, int field, void *host, int order)
+{
+    if (!c || !host) return mdb_fail(c, MDB_ERR_ARG, "mdb_state_download: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_download: mdb_box_set first");
+    FieldInfo fi;
+    if (!field_info(field, fi)) return mdb_fail(c, MDB_ERR_ARG, "mdb_state_download: bad field %d", field);
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    if (fi.per_cell) {
+        if (!c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_download: no cell data yet");
+        CUDA_TRY(c, cudaMemcpyAsync(host, dptr_i(c, field), sizeof(int) * (size_t)c->nc, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        return MDB_OK;
+    }
+    if (field == MDB_F_KVOIS && !c->kvois) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_download: no list yet");
+    int n = c->n;
+    size_t bytes = (size_t)n * fi.ncol * (fi.is_int ? sizeof(int) : sizeof(double));
+    int rc = ensure_stage(c, bytes);
+    if (rc) return rc;
+    bool id_only = (field == MDB_F_GID || field == MDB_F_GIDINV);
+    const int *map = (order == MDB_ORDER_ORIGINAL && !id_only) ? c->gidinv : nullptr;
+    int nb = cdiv(n, 256);
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        if (field == MDB_F_XP) k_down_pos<<<nb, 256, 0, c->stream>>>(n, 0, c->pos, (double *)c->stage, map);
+        else if (field == MDB_F_DEN) k_down_pos<<<nb, 256, 0, c->stream>>>(n, 1, c->pos, (double *)c->stage, map);
+        else if (fi.is_int) k_down_i<<<nb, 256, 0, c->stream>>>(n, dptr_i(c, field), (int *)c->stage, map);
+        else k_down_d<<<nb, 256, 0, c->stream>>>(n, fi.ncol, dptr_d(c, field), (double *)c->stage, map);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(host, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MDB_OK;
+}
+
+extern "C" void *mdb_devptr(mdb_ctx *c, int field)
+{
+    if (!c || !c->has_box) return nullptr;
+    cudaSetDevice(c->dev);
+    int n = c->n, nb = cdiv(n, 256);
+    switch (field) {
+    case MDB_F_XP:
+        if (!c->xp_view && cudaMalloc(&c->xp_view, sizeof(double) * 3 * (size_t)n) != cudaSuccess) return nullptr;
+        k_down_pos<<<nb, 256, 0, c->stream>>>(n, 0, c->pos, c->xp_view, nullptr);
+        c->launches_total++;
+        return c->xp_view;
+    case MDB_F_DEN:
+        if (!c->den_view && cudaMalloc(&c->den_view, sizeof(double) * (size_t)n) != cudaSuccess) return nullptr;
+        k_down_pos<<<nb, 256, 0, c->stream>>>(n, 1, c->pos, c->den_view, nullptr);
+        c->launches_total++;
+        return c->den_view;
+    case MDB_F_INDI: return c->indi;
+    }
+    if (double *p = dptr_d(c, field)) return p;
+    return dptr_i(c, field);
+}
+
+// ------------------------------------------------------------------------------------
+// tables
+// ------------------------------------------------------------------------------------
+// pack T(NKIND,NTAB) Fortran layout -> per kind (ntab+2) entries {T[KK], T[KK+1]-T[KK]}, KK = 0..ntab+1,
+// with T[0] = T[ntab+1] = 0 : the reference reads those two out of bounds
+// (CommonGPU/MD_EAM_ForceTable_GPU.F90:522-530 at r == Rmax); the oracle defines them as 0 and so do we.
+static int pack_table(mdb_ctx *c, const double *t, int nkind, int ntab, double2 **out)
+{
+    size_t cnt = (size_t)nkind * (ntab + 2);
+    std::vector<double2> h(cnt);
+    for (int k = 0; k < nkind; k++)
+        for (int kk = 0; kk <= ntab + 1; kk++) {
+            double a = (kk >= 1 && kk <= ntab) ? t[(size_t)(kk - 1) * nkind + k] : 0.0;
+            double b = (kk + 1 >= 1 && kk + 1 <= ntab) ? t[(size_t)kk * nkind + k] : 0.0;
+            h[(size_t)k * (ntab + 2) + kk] = make_double2(a, b - a);
+        }
+    void *d = nullptr;
+    CUDA_TRY(c, cudaMalloc(&d, sizeof(double2) * cnt));
+    c->tab_allocs.push_back(d);
+    CUDA_TRY(c, cudaMemcpy(d, h.data(), sizeof(double2) * cnt, cudaMemcpyHostToDevice));
+    *out = (double2 *)d;
+    return MDB_OK;
+}
+
+extern "C" int mdb_tables_set(mdb_ctx *c, int pot_type, int nkind, int ntab, double csi, const double *potr,
+                              const double *fpotr, const double *potb, const double *fpotb, int nkind1, int nembd,
+                              double rhod, const double *fembd, const double *dfembd, const int *kpair,
+                              const int *kembd, double ru2max)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_tables_set: mdb_box_set first");
+    if (nkind < 1 || ntab < 2 || !potr || !fpotr || !potb || !fpotb || !kpair)
+        return mdb_fail(c, MDB_ERR_ARG, "mdb_tables_set: bad pair-table argument");
+    if (pot_type == MDB_POT_EAM && (nkind1 < 1 || nembd < 2 || !fembd || !dfembd || !kembd || !(rhod > 0.0)))
+        return mdb_fail(c, MDB_ERR_ARG, "mdb_tables_set: bad embedding-table argument");
+    if (pot_type != MDB_POT_EAM && pot_type != MDB_POT_FS) return mdb_fail(c, MDB_ERR_ARG, "mdb_tables_set: pot_type");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    free_tables(c);
+    TableSet &t = c->tab;
+    memset(&t, 0, sizeof(t));
+    t.pot_type = pot_type; t.ng = c->ng; t.nkind = nkind; t.ntab = ntab; t.csi = csi; t.ru2max = ru2max;
+    t.nkind1 = nkind1; t.nembd = nembd; t.rhod = rhod;
+    int rc;
+    if ((rc = pack_table(c, potr, nkind, ntab, &t.potr))) return rc;
+    if ((rc = pack_table(c, fpotr, nkind, ntab, &t.fpotr))) return rc;
+    if ((rc = pack_table(c, potb, nkind, ntab, &t.potb))) return rc;
+    if ((rc = pack_table(c, fpotb, nkind, ntab, &t.fpotb))) return rc;
+    if (pot_type == MDB_POT_EAM) {
+        if ((rc = pack_table(c, fembd, nkind1, nembd, &t.fembd))) return rc;
+        if ((rc = pack_table(c, dfembd, nkind1, nembd, &t.dfembd))) return rc;
+    }
+    for (int i = 0; i < c->ng; i++) {
+        for (int j = 0; j < c->ng; j++) {
+            int k = kpair[i + c->ng * j];
+            if (k < 1 || k > nkind) return mdb_fail(c, MDB_ERR_ARG, "mdb_tables_set: KPAIR(%d,%d)=%d out of range", i + 1, j + 1, k);
+            t.kpair[i + c->ng * j] = k - 1;
+        }
+        if (pot_type == MDB_POT_EAM) {
+            int k = kembd[i];
+            if (k < 1 || k > nkind1) return mdb_fail(c, MDB_ERR_ARG, "mdb_tables_set: KEMBD(%d)=%d out of range", i + 1, k);
+            t.kembd[i] = k - 1;
+        }
+    }
+    c->has_tables = true;
+    return MDB_OK;
+}
+
+extern "C" int mdb_tables_clear(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->stream);
+    free_tables(c);
+    return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// neighbour-list container management (kernels live in mdb_cells.cu / mdb_nlist.cu)
+// ------------------------------------------------------------------------------------
+extern "C" int mdb_nlist_init(mdb_ctx *c, const double *nb_rm, int mxkvois)
+{
+    if (!c || !nb_rm || mxkvois < 1) return mdb_fail(c, MDB_ERR_ARG, "mdb_nlist_init: bad argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_nlist_init: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    free_nlist(c);
+    double rmmax = 0.0;
+    for (int i = 0; i < c->ng * c->ng; i++) {
+        c->nb_rm[i] = nb_rm[i];
+        // m_RM2 = NB_RM*NB_RM (double) assigned to real(KINDSF) RM2, CommonGPU/MD_NeighborsList_GPU.F90:1377,1387,1394
+        c->rm2f[i] = (float)(nb_rm[i] * nb_rm[i]);
+        if (nb_rm[i] > rmmax) rmmax = nb_rm[i];
+    }
+    if (!(rmmax > 0.0)) return mdb_fail(c, MDB_ERR_ARG, "mdb_nlist_init: NB_RM must be positive");
+    const double eps = (double)0.0001f; // real(KINDDF),parameter::EPS=0.0001 (a REAL literal) :260
+    for (int k = 0; k < 3; k++) {       // :289-298
+        c->ncell[k] = (int)(c->box.size[k] / (1.0 * rmmax) - eps);
+        if (c->ncell[k] < 3) c->ncell[k] = 3;
+    }
+    long long nc0 = (long long)c->ncell[0] * c->ncell[1] * c->ncell[2];
+    if (nc0 * c->nbox > 2000000000LL) return mdb_fail(c, MDB_ERR_ARG, "mdb_nlist_init: too many cells");
+    c->nc0 = (int)nc0;
+    c->nc = c->nc0 * c->nbox;
+    c->mxkvois = mxkvois;
+    CUDA_TRY(c, cudaMalloc(&c->nac, sizeof(int) * (size_t)c->nc));
+    CUDA_TRY(c, cudaMalloc(&c->naac, sizeof(int) * (size_t)c->nc));
+    CUDA_TRY(c, cudaMalloc(&c->ia1th, sizeof(int) * (size_t)c->nc));
+    CUDA_TRY(c, cudaMalloc(&c->kvois, sizeof(int) * (size_t)c->n));
+    CUDA_TRY(c, cudaMalloc(&c->indi, sizeof(int) * (size_t)c->n * mxkvois));
+    CUDA_TRY(c, cudaMemsetAsync(c->kvois, 0, sizeof(int) * (size_t)c->n, c->stream)); // DevSet(KVOIS,0) :285
+    CUDA_TRY(c, cudaMemsetAsync(c->indi, 0, sizeof(int) * (size_t)c->n * mxkvois, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->nac, 0, sizeof(int) * (size_t)c->nc, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->naac, 0, sizeof(int) * (size_t)c->nc, c->stream));
+    c->has_nlist = true;
+    c->list_valid = false;
+    return MDB_OK;
+}
+
+extern "C" int mdb_nlist_clear(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->stream);
+    free_nlist(c);
+    return MDB_OK;
+}
+
+extern "C" int mdb_nlist_cellinfo(const mdb_ctx *c, int ncell[3], int *nc_total, int *mxnac)
+{
+    if (!c || !c->has_nlist) return MDB_ERR_STATE;
+    for (int d = 0; d < 3; d++) ncell[d] = c->ncell[d];
+    if (nc_total) *nc_total = c->nc;
+    if (mxnac) *mxnac = c->mxnac;
+    return MDB_OK;
+}
+
+extern "C" int mdb_nlist_build(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_nlist_build: mdb_nlist_init first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    int rc = mdb_cells_build(c);
+    if (rc < 0) return rc;
+    rc = mdb_nlist_kernel(c);
+    if (rc < 0) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->mxnac = c->h_counters[CNT_MXNAC];
+    c->list_valid = true;
+    return c->h_counters[CNT_OOB];
+}
+
+extern "C" int mdb_nlist_overflow(mdb_ctx *c)
+{
+    if (!c || !c->has_nlist) return MDB_ERR_STATE;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return c->h_counters[CNT_OVERFLOW];
+}
+
+__global__ void k_indi_to_original(int n, int k, const int *__restrict__ indi, const int *__restrict__ kvois,
+                                   const int *__restrict__ gid, int *__restrict__ out)
+{
+    // list of ORIGINAL atom o = list of CELL atom s with ids mapped through GID
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int o = gid[s] - 1, kv = kvois[s];
+    for (int w = 0; w < k; w++) out[o + (size_t)w * n] = (w < kv) ? gid[indi[s + (size_t)w * n] - 1] : 0;
+}
+
+extern "C" int mdb_nlist_copyout(mdb_ctx *c, int *kvois, int *indi, int order)
+{
+    // Copyout_NeighboreList_DEV, CommonGPU/MD_NeighborsList_GPU.F90:560-755
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_nlist || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_nlist_copyout: no valid list");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    int n = c->n;
+    if (kvois) {
+        int rc = mdb_state_download(c, MDB_F_KVOIS, kvois, order);
+        if (rc) return rc;
+    }
+    if (indi) {
+        size_t bytes = sizeof(int) * (size_t)n * c->mxkvois;
+        if (order == MDB_ORDER_CELL) {
+            CUDA_TRY(c, cudaMemcpyAsync(indi, c->indi, bytes, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            int rc = ensure_stage(c, bytes);
+            if (rc) return rc;
+            {
+                ProfScope ps(c, MDB_K_OTHER);
+                k_indi_to_original<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->mxkvois, c->indi, c->kvois, c->gid, (int *)c->stage);
+            }
+            CUDA_TRY(c, cudaGetLastError());
+            CUDA_TRY(c, cudaMemcpyAsync(indi, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return MDB_OK;
+}

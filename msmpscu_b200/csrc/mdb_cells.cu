@@ -1,0 +1,186 @@
+// mdb_cells.cu -- cell binning and cell-ordered re-sort, entirely on the device.
+//
+// Replaces the cell-id kernel + the SERIAL HOST linked-cell sort of the reference
+// (CommonGPU/MD_NeighborsList_GPU.F90:759-819 and :1421-1574,1624-1695: ~10 full-array
+// host<->device copies and an O(N) serial loop per rebuild).  The resulting order is
+// bit-identical to the reference's: cells ascending (x fastest, then y, z, box), atoms
+// inside a cell by DESCENDING original id (head/link insertion order, :1493-1495,1558-1565),
+// out-of-box atoms parked at the end, smallest original id last (:1627-1637).
+//
+// Pipeline (all on ctx->stream, no host round trip):
+//   k_cell_assign   cell id per atom + per-cell counts by warp-aggregated atomics
+//   k_cell_scan     exclusive prefix -> IA1th, max count
+//   k_cell_scatter  provisional placement inside the cell segment (atomic order)
+//   k_cell_rank     deterministic in-cell order: rank by descending original id
+//   k_oob_place     out-of-box atoms to the tail
+//   k_permute       gather every per-atom array into the new order (double-buffered)
+#include "mdb_internal.cuh"
+
+// (x-LB)/BS*NC - eps, un-fused and in source order: cell assignment must be bit-exact
+__device__ __forceinline__ int cell_coord(double x, double lo, double bs, int nc, double eps)
+{
+    double t = __ddiv_rn(__dsub_rn(x, lo), bs);
+    t = __dsub_rn(__dmul_rn(t, (double)nc), eps);
+    return (int)t; // truncation toward zero, like Fortran int()
+}
+
+__global__ void k_cell_assign(int n, int napb, const double4 *__restrict__ pos, const int *__restrict__ gid,
+                              int *__restrict__ statu, BoxParams box, int ncx, int ncy, int ncz, int nc0,
+                              int *__restrict__ ic, int *__restrict__ nac, int *__restrict__ naac,
+                              int *__restrict__ slot, int *__restrict__ oob, int *__restrict__ counters)
+{
+    const double eps = (double)0.0001f; // real(KINDDF),parameter::eps=0.0001 :789
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    int cell = 0, active = 0, orig = 0;
+    if (s < n) {
+        int st = statu[s];
+        orig = gid[s];
+        int ib = (orig - 1) / napb; // :800
+        if ((st & ST_OUTOFBOX) != ST_OUTOFBOX) {
+            double4 p = pos[s];
+            int ix = cell_coord(p.x, box.lo[0], box.size[0], ncx, eps);
+            int iy = cell_coord(p.y, box.lo[1], box.size[1], ncy, eps);
+            int iz = cell_coord(p.z, box.lo[2], box.size[2], ncz, eps);
+            if (ix < 0 || ix >= ncx || iy < 0 || iy >= ncy || iz < 0 || iz >= ncz) cell = -2;
+            else cell = 1 + (ix + ncx * (iy + ncy * iz)) + ib * nc0;
+        } else {
+            cell = -1;
+        }
+        ic[s] = cell;
+        active = (st & ST_ACTIVE) == ST_ACTIVE;
+        if (cell < 0) {
+            // the reference asks on stdin here and, on 'C', marks the atom out of box (:1505-1526)
+            if (cell < -1) statu[s] = ST_OUTOFBOX;
+            int k = atomicAdd(&counters[CNT_OOB], 1);
+            oob[k] = orig;
+        }
+    }
+    // warp-aggregated counting: lanes of the same cell elect a leader that issues one atomic
+    int key = (cell > 0) ? cell : -(lane + 1);
+    unsigned grp = __match_any_sync(0xffffffffu, key);
+    unsigned act = __ballot_sync(0xffffffffu, active && cell > 0);
+    int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (cell > 0 && lane == leader) {
+        base = atomicAdd(&nac[cell - 1], __popc(grp));
+        int na = __popc(grp & act);
+        if (na) atomicAdd(&naac[cell - 1], na);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (cell > 0) slot[s] = base + __popc(grp & ((1u << lane) - 1u));
+}
+
+// single-block exclusive scan over the cells (run once per rebuild; nc <= ~1e6)
+__global__ void k_cell_scan(int nc, const int *__restrict__ nac, int *__restrict__ ia1th, int *__restrict__ counters)
+{
+    __shared__ int part[1024];
+    __shared__ int pmax[1024];
+    int t = threadIdx.x, nt = blockDim.x;
+    int chunk = (nc + nt - 1) / nt;
+    int b = t * chunk, e = min(b + chunk, nc);
+    int sum = 0, mx = 0;
+    for (int i = b; i < e; i++) { int v = nac[i]; sum += v; mx = max(mx, v); }
+    part[t] = sum;
+    pmax[t] = mx;
+    __syncthreads();
+    // Hillis-Steele inclusive scan of the partials
+    for (int off = 1; off < nt; off <<= 1) {
+        int v = (t >= off) ? part[t - off] : 0;
+        int m = (t >= off) ? pmax[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        pmax[t] = max(pmax[t], m);
+        __syncthreads();
+    }
+    int run = part[t] - sum; // exclusive prefix of this chunk
+    for (int i = b; i < e; i++) { ia1th[i] = run + 1; run += nac[i]; } // hm_IA1th is 1-based :1542-1551
+    if (t == nt - 1) { counters[CNT_MXNAC] = pmax[t]; counters[CNT_INCELL] = part[t]; }
+}
+
+__global__ void k_cell_scatter(int n, const int *__restrict__ ic, const int *__restrict__ slot,
+                               const int *__restrict__ ia1th, const int *__restrict__ gid, int *__restrict__ tmp_orig)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int cell = ic[s];
+    if (cell > 0) tmp_orig[ia1th[cell - 1] - 1 + slot[s]] = gid[s];
+}
+
+__global__ void k_cell_rank(int n, const int *__restrict__ ic, const int *__restrict__ ia1th, const int *__restrict__ nac,
+                            const int *__restrict__ gid, const int *__restrict__ tmp_orig, int *__restrict__ gid_new,
+                            int *__restrict__ srcof)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int cell = ic[s];
+    if (cell <= 0) return;
+    int base = ia1th[cell - 1] - 1, cnt = nac[cell - 1], me = gid[s], rank = 0;
+    for (int k = 0; k < cnt; k++) rank += (tmp_orig[base + k] > me); // descending original id
+    gid_new[base + rank] = me;
+    srcof[base + rank] = s;
+}
+
+__global__ void k_oob_place(int n, int *__restrict__ counters, const int *__restrict__ oob,
+                            const int *__restrict__ gidinv, int *__restrict__ gid_new, int *__restrict__ srcof)
+{
+    int m = counters[CNT_OOB];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[CNT_OOB_TOTAL] += m;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < m; q += gridDim.x * blockDim.x) {
+        int o = oob[q], rank = 0;
+        for (int k = 0; k < m; k++) rank += (oob[k] < o);
+        int dest = n - 1 - rank; // IP = NPART, NPART-1, ... over ascending original id :1628-1636
+        gid_new[dest] = o;
+        srcof[dest] = gidinv[o - 1] - 1;
+    }
+}
+
+__global__ void k_permute(int n, const int *__restrict__ srcof, const int *__restrict__ gid_new,
+                          const double4 *__restrict__ pos, double4 *__restrict__ pos_o,
+                          const double *__restrict__ xp1, double *__restrict__ xp1_o,
+                          const double *__restrict__ fp, double *__restrict__ fp_o,
+                          const double *__restrict__ dis, double *__restrict__ dis_o,
+                          const int *__restrict__ ityp, int *__restrict__ ityp_o,
+                          const int *__restrict__ statu, int *__restrict__ statu_o,
+                          const int *__restrict__ ic, int *__restrict__ ic_o, int *__restrict__ gidinv)
+{
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    int s = srcof[d];
+    pos_o[d] = pos[s];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        xp1_o[d + (size_t)k * n] = xp1[s + (size_t)k * n];
+        fp_o[d + (size_t)k * n] = fp[s + (size_t)k * n];
+        dis_o[d + (size_t)k * n] = dis[s + (size_t)k * n];
+    }
+    ityp_o[d] = ityp[s];
+    statu_o[d] = statu[s];
+    ic_o[d] = ic[s];
+    gidinv[gid_new[d] - 1] = d + 1;
+}
+
+template <class T> static inline void swp(T *&a, T *&b) { T *t = a; a = b; b = t; }
+
+int mdb_cells_build(mdb_ctx *c)
+{
+    int n = c->n, nb = cdiv(n, 256);
+    cudaStream_t st = c->stream;
+    ProfScope ps(c, MDB_K_CELLSORT, 6);
+    CUDA_TRY(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * CNT_PERBUILD_N, st)); // CNT_OOB_TOTAL accumulates
+    CUDA_TRY(c, cudaMemsetAsync(c->nac, 0, sizeof(int) * (size_t)c->nc, st));  // hm_NAC = 0 :1431
+    CUDA_TRY(c, cudaMemsetAsync(c->naac, 0, sizeof(int) * (size_t)c->nc, st));
+    k_cell_assign<<<nb, 256, 0, st>>>(n, c->napb, c->pos, c->gid, c->statu, c->box, c->ncell[0], c->ncell[1],
+                                      c->ncell[2], c->nc0, c->ic, c->nac, c->naac, c->slot, c->oob, c->counters);
+    k_cell_scan<<<1, 1024, 0, st>>>(c->nc, c->nac, c->ia1th, c->counters);
+    k_cell_scatter<<<nb, 256, 0, st>>>(n, c->ic, c->slot, c->ia1th, c->gid, c->tmp_orig);
+    k_cell_rank<<<nb, 256, 0, st>>>(n, c->ic, c->ia1th, c->nac, c->gid, c->tmp_orig, c->gid_alt, c->srcof);
+    k_oob_place<<<64, 256, 0, st>>>(n, c->counters, c->oob, c->gidinv, c->gid_alt, c->srcof);
+    k_permute<<<nb, 256, 0, st>>>(n, c->srcof, c->gid_alt, c->pos, c->pos_alt, c->xp1, c->xp1_alt, c->fp, c->fp_alt,
+                                  c->dis, c->dis_alt, c->ityp, c->ityp_alt, c->statu, c->statu_alt, c->ic, c->ic_alt,
+                                  c->gidinv);
+    CUDA_TRY(c, cudaGetLastError());
+    swp(c->pos, c->pos_alt); swp(c->xp1, c->xp1_alt); swp(c->fp, c->fp_alt); swp(c->dis, c->dis_alt);
+    swp(c->ityp, c->ityp_alt); swp(c->statu, c->statu_alt); swp(c->ic, c->ic_alt); swp(c->gid, c->gid_alt);
+    return MDB_OK;
+}

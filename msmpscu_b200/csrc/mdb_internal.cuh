@@ -1,0 +1,142 @@
+// mdb_internal.cuh -- context layout and helpers shared by the translation units of
+// libmdpscu_b200.so.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/mdpscu_b200.h"
+
+// STATU bits, Common/MD_Const.F90:79-99
+#define ST_ACTIVE    1
+#define ST_FIXPOSX   2
+#define ST_FIXPOSY   4
+#define ST_FIXPOSZ   8
+#define ST_FIXPOS    14
+#define ST_FIXVELX   16
+#define ST_FIXVELY   32
+#define ST_FIXVELZ   64
+#define ST_OUTOFBOX  65536
+#define ST_REFLECT   131072
+#define ST_TRANSMIT  262144
+
+#define KB_CGS 1.38054e-16 // CP_KB, MSMLIB/sor/Common/MSM_Const.F90:82
+
+// device counters block (one int each)
+enum { CNT_OOB = 0, CNT_OVERFLOW, CNT_NNMAX, CNT_MXNAC, CNT_INCELL, CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N, CNT__N = 8 };
+
+struct BoxParams { // passed by value to kernels
+    double lo[3], up[3], size[3], half[3];
+    int pd[3];
+};
+
+struct TableSet { // device tables in the packed layouts the kernels read
+    int pot_type, ng, nkind, ntab, nkind1, nembd;
+    double csi, rhod, inv_rhod_unused, ru2max;
+    // pair tables, per kind k: entry KK (0..ntab+1, Fortran index; 0 and ntab+1 are zero pads)
+    //   v2[(k*(ntab+2)+KK)] = {T[KK], T[KK+1]-T[KK]}   (value, forward difference)
+    double2 *potr, *fpotr, *potb, *fpotb;
+    double2 *fembd, *dfembd; // same packing over nembd
+    int kpair[MDB_MXGROUP * MDB_MXGROUP]; // 0-based kind for (i,j) at i+ng*j ; -1 if none
+    int kembd[MDB_MXGROUP];
+};
+
+struct EpcParams {
+    int on;
+    int enable[MDB_MXGROUP];
+    double te[MDB_MXGROUP], epa[MDB_MXGROUP], v2ti[MDB_MXGROUP], tcut[MDB_MXGROUP], eup[MDB_MXGROUP];
+};
+
+struct MassParams { double cm[MDB_MXGROUP]; };
+
+struct mdb_ctx {
+    int dev = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    // ---- box
+    bool has_box = false;
+    int nbox = 0, napb = 0, n = 0, ng = 0;
+    double boxshape[9];
+    bool shape_identity = true;
+    BoxParams box;
+    MassParams mass;
+
+    // ---- state, CELL order.  pos = {x,y,z,den}
+    double4 *pos = nullptr, *pos_alt = nullptr;
+    double *xp1 = nullptr, *xp1_alt = nullptr;
+    double *fp = nullptr, *fp_alt = nullptr;
+    double *dis = nullptr, *dis_alt = nullptr;
+    double *epot = nullptr, *ekin = nullptr;
+    int *ityp = nullptr, *ityp_alt = nullptr;
+    int *statu = nullptr, *statu_alt = nullptr;
+    int *gid = nullptr, *gid_alt = nullptr, *gidinv = nullptr;
+    int *ic = nullptr, *ic_alt = nullptr;
+    // materialised reference-shaped views
+    double *xp_view = nullptr, *den_view = nullptr;
+    // staging for up/download
+    void *stage = nullptr; size_t stage_bytes = 0;
+    void *hstage = nullptr; size_t hstage_bytes = 0; // pinned
+
+    // ---- cells
+    bool has_nlist = false, list_valid = false;
+    double nb_rm[MDB_MXGROUP * MDB_MXGROUP];
+    float rm2f[MDB_MXGROUP * MDB_MXGROUP];
+    int ncell[3] = {0, 0, 0}, nc0 = 0, nc = 0, mxnac = 0;
+    int *nac = nullptr, *naac = nullptr, *ia1th = nullptr;
+    int *slot = nullptr, *srcof = nullptr, *tmp_orig = nullptr, *oob = nullptr;
+    int *counters = nullptr; // CNT__N ints on device
+    int *h_counters = nullptr; // pinned mirror
+    int mxkvois = 0;
+    int *kvois = nullptr, *indi = nullptr;
+    int oob_total = 0;
+
+    // ---- tables
+    bool has_tables = false;
+    TableSet tab;
+    std::vector<void *> tab_allocs;
+
+    // ---- epc
+    EpcParams epc;
+
+    // ---- options
+    int opt_force_path = MDB_FORCE_PATH_AUTO;
+
+    // ---- virial partials
+    double *vpart = nullptr; int vpart_n = 0;
+
+    // ---- profiling
+    bool prof = false;
+    long long launches_total = 0;
+    long long prof_launches[MDB_K__COUNT];
+    double prof_ms[MDB_K__COUNT];
+    struct Ev { cudaEvent_t a, b; int k; };
+    std::vector<Ev> ev_pending;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+// ---- error helpers
+int mdb_fail(mdb_ctx *c, int code, const char *fmt, ...);
+#define CUDA_TRY(c, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return mdb_fail((c), MDB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// ---- profiling bracket: ProfScope p(ctx, MDB_K_PASS1); launch...; (destructor records end)
+struct ProfScope {
+    mdb_ctx *c; int k; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(mdb_ctx *ctx, int klass, int nlaunch = 1);
+    ~ProfScope();
+};
+void mdb_prof_collect(mdb_ctx *c);
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- internal entry points across translation units
+int mdb_cells_build(mdb_ctx *c);             // mdb_cells.cu : bin, sort, permute
+int mdb_nlist_kernel(mdb_ctx *c);            // mdb_nlist.cu : fill KVOIS/INDI
+int mdb_force_generic(mdb_ctx *c, unsigned flags, double *vt); // mdb_force.cu
+int mdb_views_refresh(mdb_ctx *c, int field); // mdb_api.cu

@@ -1,0 +1,214 @@
+// mdb_step.cu -- velocity-Verlet (Swope) predictor / corrector, kinetic energy, electron-phonon
+// coupling, and the whole-step driver.
+//
+// Reference: CommonGPU/MD_DiffScheme_GPU.F90:242-384 (Predictor_KERNEL0), :686-758
+// (Correction_KERNEL), :851-902 (CALEKIN_KERNEL); LocalTempCtrlMeths/EPC/MD_EP_Coupling_GPU.F90
+// :370-417 (parameters) and :421-493 (EPC_MOD_KERNEL); step order
+// Appshell/MD_Method_GenericMD_GPU.F90:596-627.
+//
+// Positions feed the bit-exact cell assignment, so the predictor's position update is written
+// with un-fused intrinsics in the reference's source order; velocities likewise so that long
+// trajectories track the oracle as closely as the force sums allow.
+#include "mdb_internal.cuh"
+
+__global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, const double *__restrict__ fp,
+                          double *__restrict__ dis, int *__restrict__ statu, const int *__restrict__ ityp,
+                          MassParams M, BoxParams box, double th, double h2s2, double hs2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int stat = statu[i];
+    if ((stat & ST_ACTIVE) != ST_ACTIVE) return; // :295
+    const double cm0 = M.cm[ityp[i] - 1];
+    double4 p = pos[i];
+    double x[3] = {p.x, p.y, p.z};
+    const int fixp[3] = {ST_FIXPOSX, ST_FIXPOSY, ST_FIXPOSZ};
+    const int fixv[3] = {ST_FIXVELX, ST_FIXVELY, ST_FIXVELZ};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const size_t o = i + (size_t)d * n;
+        const double v = xp1[o];
+        const double a = __ddiv_rn(fp[o], cm0);                                  // FP/CM0 :309-311
+        double dd = __dadd_rn(__dmul_rn(th, v), __dmul_rn(h2s2, a));           // TH*XP1 + H2S2*FP :314
+        if ((stat & fixp[d]) == fixp[d]) dd = 0.0;
+        double xx = __dadd_rn(x[d], dd);
+        if (box.pd[d]) {                                                         // :317-325
+            if (xx > box.up[d]) xx = __dsub_rn(xx, box.size[d]);
+            else if (xx < box.lo[d]) xx = __dadd_rn(xx, box.size[d]);
+        }
+        x[d] = xx;
+        if ((stat & fixv[d]) == 0 && (stat & fixp[d]) == 0) xp1[o] = __dadd_rn(v, __dmul_rn(hs2, a)); // :353-361
+        dis[o] = __dadd_rn(dis[o], dd);                                          // :371-373
+    }
+    p.x = x[0]; p.y = x[1]; p.z = x[2];
+    pos[i] = p;
+    // :375-379 (the PASSBOUND bit set at :320 is never stored by the reference)
+    if (x[0] > box.up[0] || x[1] > box.up[1] || x[2] > box.up[2]) statu[i] = ST_OUTOFBOX | ST_REFLECT;
+    else if (x[0] < box.lo[0] || x[1] < box.lo[1] || x[2] < box.lo[2]) statu[i] = ST_OUTOFBOX | ST_TRANSMIT;
+}
+
+// EPC friction on FP followed by the second half kick: one read of XP1/FP instead of the
+// reference's two kernels (EPC_MOD_KERNEL then Correction_KERNEL).  do_epc / do_corr select stages.
+__global__ void k_epc_correct(int n, double *__restrict__ xp1, double *__restrict__ fp, const int *__restrict__ statu,
+                              const int *__restrict__ ityp, MassParams M, EpcParams E, double hs2, int do_epc, int do_corr)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int stat = statu[i];
+    if ((stat & ST_ACTIVE) != ST_ACTIVE) return;
+    const int kk = ityp[i] - 1;
+    const size_t n1 = n, n2 = 2 * (size_t)n;
+    double vx = xp1[i], vy = xp1[i + n1], vz = xp1[i + n2];
+    double fx = fp[i], fy = fp[i + n1], fz = fp[i + n2];
+    if (do_epc && E.enable[kk] > 0) { // EPC_MOD_KERNEL :473-490
+        const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+        if (v2 <= E.eup[kk]) {
+            const double tm = __dmul_rn(v2, E.v2ti[kk]);
+            const double mu = __ddiv_rn(__dmul_rn(E.epa[kk], __dsub_rn(tm, E.te[kk])), fmax(tm, E.tcut[kk]));
+            fx = __dsub_rn(fx, __dmul_rn(mu, vx));
+            fy = __dsub_rn(fy, __dmul_rn(mu, vy));
+            fz = __dsub_rn(fz, __dmul_rn(mu, vz));
+            fp[i] = fx; fp[i + n1] = fy; fp[i + n2] = fz;
+        }
+    }
+    if (do_corr) { // Correction_KERNEL :735-753
+        const double cm0 = M.cm[kk];
+        if ((stat & ST_FIXVELX) == 0 && (stat & ST_FIXPOSX) == 0) xp1[i] = __dadd_rn(vx, __dmul_rn(hs2, __ddiv_rn(fx, cm0)));
+        if ((stat & ST_FIXVELY) == 0 && (stat & ST_FIXPOSY) == 0) xp1[i + n1] = __dadd_rn(vy, __dmul_rn(hs2, __ddiv_rn(fy, cm0)));
+        if ((stat & ST_FIXVELZ) == 0 && (stat & ST_FIXPOSZ) == 0) xp1[i + n2] = __dadd_rn(vz, __dmul_rn(hs2, __ddiv_rn(fz, cm0)));
+    }
+}
+
+__global__ void k_ekin(int n, const double *__restrict__ xp1, const int *__restrict__ statu, const int *__restrict__ ityp,
+                       MassParams M, double *__restrict__ ekin)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ek = -1.0e32; // :886
+    const int st = statu[i];
+    if ((st & ST_ACTIVE) == ST_ACTIVE && (st & ST_FIXPOS) == 0) {
+        const double cm0 = M.cm[ityp[i] - 1];
+        const double vx = xp1[i], vy = xp1[i + (size_t)n], vz = xp1[i + 2 * (size_t)n];
+        const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+        ek = __dmul_rn(__dmul_rn(0.5, cm0), v2); // C_HALF*CM0*(...) :896
+    }
+    ekin[i] = ek;
+}
+
+// ------------------------------------------------------------------------------------
+extern "C" int mdb_predict(mdb_ctx *c, double h)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_predict: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    // Predictor_DEV :660-662 : TH = H, HS2 = TH/2, H2S2 = TH*TH/2
+    const double th = h, hs2 = th * 0.5, h2s2 = th * th * 0.5;
+    ProfScope ps(c, MDB_K_PREDICT);
+    k_predict<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp, c->mass,
+                                                      c->box, th, h2s2, hs2);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+extern "C" int mdb_correct(mdb_ctx *c, double h)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_correct: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    ProfScope ps(c, MDB_K_CORRECT);
+    k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
+                                                          h * 0.5, 0, 1);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+extern "C" int mdb_ekin(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_ekin: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    ProfScope ps(c, MDB_K_OTHER);
+    k_ekin<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->statu, c->ityp, c->mass, c->ekin);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+extern "C" int mdb_epc_set(mdb_ctx *c, const int *enable, const double *te, const double *alpha, const double *cut,
+                           const double *he)
+{
+    if (!c || !enable || !te || !alpha || !cut || !he) return mdb_fail(c, MDB_ERR_ARG, "mdb_epc_set: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_epc_set: mdb_box_set first");
+    EpcParams &E = c->epc;
+    memset(&E, 0, sizeof(E));
+    for (int g = 0; g < c->ng; g++) { // Reset_EPCMOD_DEV :387-394
+        E.enable[g] = enable[g];
+        E.te[g] = te[g];
+        E.v2ti[g] = c->mass.cm[g] * (1.0 / 3.0) / KB_CGS; // CM*C_UTH/CP_KB
+        E.epa[g] = c->mass.cm[g] / alpha[g];
+        E.tcut[g] = te[g] * cut[g];
+        E.eup[g] = 2.0 * he[g] / c->mass.cm[g];
+        if (enable[g] > 0) E.on = 1;
+    }
+    return MDB_OK;
+}
+
+extern "C" int mdb_epc_apply(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_epc_apply: mdb_box_set first");
+    if (!c->epc.on) return MDB_OK; // hm_NEEDDO = .false. :403-405
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    ProfScope ps(c, MDB_K_CORRECT);
+    k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, 0.0, 1, 0);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box || !c->has_tables) return mdb_fail(c, MDB_ERR_STATE, "mdb_force: box and tables must be set");
+    if (!c->has_nlist || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_force: no valid neighbour list (mdb_nlist_build)");
+    if (!c->shape_identity) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: non-identity BOXSHAPE is not supported yet");
+    if ((flags & MDB_VIRIAL) && !vtensor) return mdb_fail(c, MDB_ERR_ARG, "mdb_force: MDB_VIRIAL needs vtensor");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    return mdb_force_generic(c, flags, vtensor);
+}
+
+static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)
+{
+    int rc;
+    if ((rc = mdb_predict(c, h)) < 0) return rc;
+    if (nb_uptab > 0 && (itime - it0) % nb_uptab == 0) { // MOD(ITIME-IT0,NB_UPTAB)==0, GenericMD:599-601
+        if ((rc = mdb_cells_build(c)) < 0) return rc;
+        if ((rc = mdb_nlist_kernel(c)) < 0) return rc;
+        c->list_valid = true;
+    }
+    if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
+    ProfScope ps(c, MDB_K_CORRECT);
+    k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
+                                                          h * 0.5, c->epc.on, 1);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+extern "C" int mdb_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab, double h)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box || !c->has_tables || !c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_run: box, tables and list must be set");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    CUDA_TRY(c, cudaMemsetAsync(c->counters + CNT_OOB_TOTAL, 0, sizeof(int), c->stream));
+    for (int s = 0; s < nsteps; s++) {
+        int rc = step_nosync(c, itime0 + s, it0, nb_uptab, h);
+        if (rc < 0) return rc;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return c->h_counters[CNT_OOB_TOTAL];
+}
+
+extern "C" int mdb_step(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)
+{
+    return mdb_run(c, itime, 1, it0, nb_uptab, h);
+}

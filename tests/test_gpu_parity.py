@@ -1,0 +1,191 @@
+"""GPU parity tests: every check goes through the C ABI (msmpscu_b200.capi) and compares with the
+CPU oracle on the same seeded inputs.  Bars (BASELINE.json north_star): cell assignments and
+neighbour sets bit-exact; forces, energies, virial within 1e-10 relative in fp64."""
+import numpy as np
+import pytest
+
+import util
+from msmpscu_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+FORCE_RTOL = 1e-10
+
+
+def _oracle_list(O, c):
+    return O.nlist_build_dev(c.nbox, c.napb, c.xp, c.ityp, c.statu, c.boxlow, c.zl, c.ifpd,
+                             np.ascontiguousarray(c.nb_rm.T).ravel(), c.mxkvois)
+
+
+CASES = {
+    "bcc8": lambda: util.bcc_case((8, 8, 8)),
+    "bcc_7x9x11": lambda: util.bcc_case((7, 9, 11), seed=7),
+    "multibox3": lambda: util.bcc_case((7, 7, 7), nbox=3, seed=99),
+    "neb_WH": lambda: util.neb_case("react"),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_cells_and_list_bit_exact(oracle, name):
+    """NeighboresListTest.F90:92-121 restated: identical KVOIS and identical ORDER of INDI, plus the
+    cell assignment / sort (GID, NAC, IA1th) the list is built on."""
+    c = CASES[name]()
+    ref = _oracle_list(oracle, c)
+    ctx = util.make_ctx(c)
+    ncell, nc, mxnac = ctx.cellinfo()
+    assert ncell == ref["ncell"]
+    assert np.array_equal(ctx.download(capi.F_GID, capi.ORDER_CELL), ref["gid"])
+    assert np.array_equal(ctx.download(capi.F_NAC), ref["nac"])
+    assert np.array_equal(ctx.download(capi.F_NAAC), ref["naac"])
+    assert np.array_equal(ctx.download(capi.F_IA1TH), ref["ia1th"])
+    assert np.array_equal(ctx.download(capi.F_IC, capi.ORDER_ORIGINAL), ref["inc"])
+    assert mxnac == ref["nac"].max()
+    kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
+    assert np.array_equal(kv, ref["kvois"])
+    for w in range(c.mxkvois):
+        m = kv > w
+        assert np.array_equal(ind[w][m], ref["indi"][w][m]), "neighbour order differs in row %d" % w
+    assert ctx.nlist_overflow() == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_force_energy_virial_parity(oracle, name):
+    """CalForceTest.F90:113-147 restated for EAM: forces, DEN, EPOT, virial against the CPU oracle."""
+    c = CASES[name]()
+    ref = _oracle_list(oracle, c)
+    gid = ref["gid"] - 1
+    T = util.oracle_tables(oracle, c)
+    fp, den, vt, ep = oracle.force(c.xp[gid], c.ityp[gid], ref["statu"][gid], ref["kvois"], ref["indi"], c.zl, c.ifpd,
+                                   T, virial=True, epot=True)
+    ctx = util.make_ctx(c)
+    vt_gpu = ctx.force(capi.FORCE | capi.VIRIAL | capi.EPOT)
+    f_gpu = ctx.download(capi.F_FP, capi.ORDER_CELL)
+    d_gpu = ctx.download(capi.F_DEN, capi.ORDER_CELL)
+    e_gpu = ctx.download(capi.F_EPOT, capi.ORDER_CELL)
+    assert util.relerr(f_gpu, fp) < FORCE_RTOL
+    assert util.relerr(d_gpu, den) < FORCE_RTOL
+    assert util.relerr(e_gpu, ep) < FORCE_RTOL
+    assert util.relerr(vt_gpu, vt / c.nbox) < FORCE_RTOL
+    # force-only entry point gives the same forces as the virial one
+    ctx.force(capi.FORCE)
+    assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < FORCE_RTOL
+    # ORIGINAL-order download un-permutes through GID
+    f_orig = ctx.download(capi.F_FP, capi.ORDER_ORIGINAL)
+    assert np.array_equal(f_orig[gid], f_gpu)
+    ctx.close()
+
+
+@pytest.mark.parametrize("tag", ["react", "product"])
+def test_golden_known_answer_through_cuda(tag):
+    """The reference GPU build's own output (examples/NEB_Test/GMD/*P0000_0001.0000): force [eV/LU]
+    and POT [eV] to 9 digits.  That binary used Rmax = max(NB_RM)."""
+    c = util.neb_case(tag, rmax_mode="NB_RM")
+    ctx = util.make_ctx(c)
+    ctx.force(capi.FORCE | capi.EPOT)
+    F = ctx.download(capi.F_FP) * c.rr / util.CP_EVERG
+    POT = -ctx.download(capi.F_EPOT) / util.CP_EVERG
+    assert np.max(np.abs(F - c.gold_force)) < 2e-9      # printed with 9 significant digits, |F| <= 0.39
+    assert np.max(np.abs(POT / c.gold_pot - 1.0)) < 2e-9
+    ctx.close()
+
+
+def test_integrator_epc_ekin_bit_exact(oracle):
+    """Predictor / EPC / corrector / EKIN are element-wise: un-fused arithmetic must match bit for bit."""
+    c = util.bcc_case((8, 8, 8), seed=5)
+    ctx = util.make_ctx(c)
+    ctx.force(capi.FORCE)
+    h = 0.5e-15
+    fp0 = ctx.download(capi.F_FP)
+    x0, v0 = ctx.download(capi.F_XP), ctx.download(capi.F_XP1)
+    st0 = ctx.download(capi.F_STATU)
+    assert np.array_equal(x0, c.xp) and np.array_equal(v0, c.xp1)
+    ctx.predict(h)
+    x1, v1, d1, st1 = oracle.predictor(x0, v0, fp0, np.zeros_like(x0), st0, c.ityp, c.mass, h, c.boxlow, c.zl, c.ifpd)
+    assert np.array_equal(ctx.download(capi.F_XP), x1)
+    assert np.array_equal(ctx.download(capi.F_XP1), v1)
+    assert np.array_equal(ctx.download(capi.F_DIS), d1)
+    assert np.array_equal(ctx.download(capi.F_STATU), st1)
+    te, al, cut, he = [300.0], [1.0e-12], [0.1], [100.0 * util.CP_EVERG]
+    ctx.epc_set([1], te, al, cut, he)
+    ctx.epc_apply()
+    f2 = oracle.epc(v1, fp0, st1, c.ityp, [1], c.mass, te, al, cut, he)
+    assert np.array_equal(ctx.download(capi.F_FP), f2)
+    assert not np.array_equal(f2, fp0)
+    ctx.correct(h)
+    v2 = oracle.corrector(v1, f2, st1, c.ityp, c.mass, h)
+    assert np.array_equal(ctx.download(capi.F_XP1), v2)
+    ctx.ekin()
+    assert np.array_equal(ctx.download(capi.F_EKIN), oracle.ekin(v2, st1, c.ityp, c.mass))
+    ctx.close()
+
+
+def test_truncated_list_matches_reference_truncation(oracle):
+    """mxKVOIS smaller than the true count: the reference silently keeps the first mxKVOIS in scan order."""
+    c = util.bcc_case((7, 7, 7), mxkvois=60)
+    ref = _oracle_list(oracle, c)
+    ctx = util.make_ctx(c)
+    kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
+    assert kv.max() == 60 and np.array_equal(kv, ref["kvois"])
+    assert np.array_equal(ind, ref["indi"])
+    assert ctx.nlist_overflow() == c.xp.shape[0]  # every bcc atom has > 60 neighbours inside 2.28 a0
+    ctx.close()
+
+
+def test_md_trajectory_tracks_oracle(oracle):
+    """For_One_Step sequence (predictor -> rebuild when MOD(ITIME-IT0,NB_UPTAB)==0 -> force -> corrector):
+    25 steps with rebuilds at ITIME=1,11,21; positions/velocities stay within round-off growth of the
+    oracle's, the lists built on them stay identical, and the NVE Hamiltonian drift matches."""
+    c = util.bcc_case((8, 8, 8), seed=11, temp=600.0)
+    h, it0, nup = 0.5e-15, 1, 10
+    md = util.oracle_md(oracle, c)
+    md.rebuild(); md.force()
+    ctx = util.make_ctx(c)
+    ctx.force(capi.FORCE)
+    for it in range(25):
+        md.step(it, it0, nup, h)
+    ctx.run(0, 25, it0, nup, h)
+    ref = md.get()
+    x, v = ctx.download(capi.F_XP), ctx.download(capi.F_XP1)
+    assert util.relerr(x, ref["xp"]) < 1e-12
+    assert util.relerr(v, ref["xp1"]) < 1e-9
+    assert np.array_equal(ctx.download(capi.F_GID, capi.ORDER_CELL), ref["gid"])
+    kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
+    okv, oind = md.nlist()
+    assert np.array_equal(kv, okv)
+    assert all(np.array_equal(ind[w][kv > w], oind[w][kv > w]) for w in range(c.mxkvois))
+    # Hamiltonian per atom (Common/MD_TypeDef_SimBox.F90:5155-5163)
+    md.epot(); ctx.force(capi.EPOT); ctx.ekin()
+    ref = md.get()
+    ham_ref = (ref["epot"].sum() + ref["ekin"].sum()) / c.xp.shape[0]
+    ham = (ctx.download(capi.F_EPOT).sum() + ctx.download(capi.F_EKIN).sum()) / c.xp.shape[0]
+    assert abs(ham - ham_ref) < 1e-10 * abs(ham_ref)
+    ctx.close()
+
+
+def test_out_of_box_atoms_are_parked_like_the_reference(oracle):
+    """Non-periodic x: atoms pushed outside are flagged OUTOFBOX, counted, and placed at the end of the
+    CELL order (smallest original id last), MD_NeighborsList_GPU.F90:1505-1526,1627-1637."""
+    c = util.bcc_case((7, 7, 7), ifpd=(0, 1, 1), seed=3)
+    c.xp = c.xp.copy()
+    c.xp[[5, 77, 300], 0] += 2.0 * c.zl[0]
+    c.xp[[10], 0] -= 2.0 * c.zl[0]
+    ref = _oracle_list(oracle, c)
+    ctx = util.make_ctx(c, build=False)
+    assert ctx.nlist_build() == 4 == ref["nout"]
+    assert np.array_equal(ctx.download(capi.F_GID, capi.ORDER_CELL), ref["gid"])
+    assert np.array_equal(ctx.download(capi.F_STATU, capi.ORDER_ORIGINAL), ref["statu"])
+    kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
+    n_in = c.xp.shape[0] - 4
+    assert np.array_equal(kv[:n_in], ref["kvois"][:n_in])
+    ctx.close()
+
+
+def test_errors_are_status_codes_not_stops():
+    ctx = capi.Context(0)
+    with pytest.raises(capi.MDBError) as e:
+        ctx.nlist_build()
+    assert e.value.code == capi.ERR_STATE
+    with pytest.raises(capi.MDBError):
+        ctx.force(capi.FORCE)
+    ctx.close()

@@ -1,0 +1,93 @@
+"""Shared builders for test cases: the same seeded inputs go to the CPU oracle and to the CUDA path."""
+import os
+
+import numpy as np
+
+from msmpscu_b200 import capi, forcetable, lattice
+from msmpscu_b200.constants import CP_A2CM, CP_AU2G, CP_EVERG
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class Case:
+    pass
+
+
+def bcc_case(ncell=(8, 8, 8), a0=3.1652, seed=12345, nbox=1, ru_lu=1.9, nb_fac=1.2, mxkvois=256, ntab=10000,
+             temp=600.0, disp=0.02, ifpd=(1, 1, 1)):
+    """bcc W, Marinica EAM2 -- the BASELINE config family (C1: ncell 16^3; C2: 80^3)."""
+    c = Case()
+    d = lattice.bcc_box(ncell, a0, seed, disp_lu=disp, temp_k=temp, nbox=nbox)
+    c.__dict__.update(d)
+    c.ifpd = list(ifpd)
+    c.ng = 1
+    c.ru = ru_lu * c.rr
+    c.nb_rm = np.full((1, 1), nb_fac * c.ru)
+    c.mxkvois = mxkvois
+    c.ntab = c.nembd = ntab
+    c.lib = capi.LIB_MARINICA_EAM2
+    c.ptype = np.array([[1]])
+    c.rmax = c.ru
+    return c
+
+
+def neb_case(tag="react", rmax_mode="RU"):
+    """examples/NEB_Test: 2000 W + 1 H, Bonny EAM1 (the reference's own known-answer run)."""
+    g = np.load(os.path.join(GOLD, "neb_gmd_%s.npz" % tag))
+    c = Case()
+    c.rr = 3.14 * CP_A2CM
+    c.xp = g["pos"] * c.rr
+    c.xp1 = np.zeros_like(c.xp)
+    c.ityp = g["ityp"].astype(np.int32)
+    c.statu = g["statu"].astype(np.int32)
+    c.napb, c.nbox = 2001, 1
+    c.zl = np.array([10.0, 10.0, 10.0]) * c.rr
+    c.boxlow = -0.5 * c.zl
+    c.ifpd = [1, 1, 1]
+    c.ng = 2
+    c.mass = np.array([183.84, 1.0]) * CP_AU2G
+    c.ru = 1.9 * c.rr
+    c.nb_rm = np.full((2, 2), 1.2 * c.ru)
+    c.mxkvois = 256
+    c.ntab = c.nembd = 10000
+    c.lib = capi.LIB_BONNY_EAM1
+    c.ptype = np.array([[1, 2], [4, 5]])
+    c.rmax = c.ru if rmax_mode == "RU" else 1.2 * c.ru
+    c.gold_force = g["force"]
+    c.gold_pot = g["pot"]
+    return c
+
+
+def product_tables(c):
+    return forcetable.Create_Interaction_ForceTable(c.lib, c.ptype, c.ntab, c.nembd, c.rmax)
+
+
+def oracle_tables(O, c):
+    lib = {capi.LIB_MARINICA_EAM2: O.LIB_MARINICA_EAM2, capi.LIB_BONNY_EAM1: O.LIB_BONNY_EAM1}[c.lib]
+    return O.Tables(lib, c.ptype, c.ntab, c.nembd, c.ru, rmax=c.rmax)
+
+
+def make_ctx(c, build=True, force_path=None):
+    ctx = capi.Context(0)
+    ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
+    ctx.upload(capi.F_XP, c.xp)
+    ctx.upload(capi.F_XP1, c.xp1)
+    ctx.upload(capi.F_ITYP, c.ityp)
+    ctx.upload(capi.F_STATU, c.statu)
+    ctx.tables_set(product_tables(c), c.ru * c.ru)
+    if force_path is not None:
+        ctx.set_option(capi.OPT_FORCE_PATH, force_path)
+    ctx.nlist_init(c.nb_rm, c.mxkvois)
+    if build:
+        ctx.nlist_build()
+    return ctx
+
+
+def oracle_md(O, c):
+    return O.MD(c.nbox, c.napb, c.xp, c.xp1, c.ityp, c.statu, c.mass, c.boxlow, c.zl, c.ifpd,
+                np.ascontiguousarray(c.nb_rm.T).ravel(), c.mxkvois, oracle_tables(O, c))
+
+
+def relerr(a, b):
+    """max |a-b| / max |b| : the parity metric for per-atom vectors"""
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
