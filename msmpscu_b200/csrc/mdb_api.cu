@@ -127,6 +127,8 @@ static void free_state(mdb_ctx *c)
 }
 static void free_nlist(mdb_ctx *c)
 {
+    if (c->tiled.nbl) { cudaFree(c->tiled.nbl); c->tiled.nbl = nullptr; c->tiled.nbl_elems = 0; }
+    c->tiled.ok = false; c->tiled.dirty = true; c->tiled.active = false;
     dfree(c->nac); dfree(c->naac); dfree(c->ia1th); dfree(c->kvois); dfree(c->indi);
     c->has_nlist = false; c->list_valid = false;
 }
@@ -158,6 +160,7 @@ extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
     if (option == MDB_OPT_FORCE_PATH && value >= MDB_FORCE_PATH_AUTO && value <= MDB_FORCE_PATH_TILED) {
         c->opt_force_path = value;
         c->list_valid = false; // the two paths keep different list formats
+        c->tiled.dirty = true;
         return MDB_OK;
     }
     return mdb_fail(c, MDB_ERR_ARG, "mdb_set_option: unknown option %d / value %d", option, value);
@@ -249,6 +252,7 @@ extern "C" int mdb_box_set(mdb_ctx *c, int nbox, int napb, const double boxlow[3
     }
     c->has_box = true;
     c->list_valid = false;
+    c->tiled.dirty = true;
     return MDB_OK;
 }
 
@@ -495,7 +499,11 @@ extern "C" int mdb_tables_set(mdb_ctx *c, int pot_type, int nkind, int ntab, dou
             t.kembd[i] = k - 1;
         }
     }
+    c->h_potb.assign(potb, potb + (size_t)nkind * ntab);
+    c->h_fpotr.assign(fpotr, fpotr + (size_t)nkind * ntab);
+    c->h_fpotb.assign(fpotb, fpotb + (size_t)nkind * ntab);
     c->has_tables = true;
+    c->tiled.dirty = true;
     return MDB_OK;
 }
 
@@ -547,6 +555,7 @@ extern "C" int mdb_nlist_init(mdb_ctx *c, const double *nb_rm, int mxkvois)
     CUDA_TRY(c, cudaMemsetAsync(c->naac, 0, sizeof(int) * (size_t)c->nc, c->stream));
     c->has_nlist = true;
     c->list_valid = false;
+    c->tiled.dirty = true;
     return MDB_OK;
 }
 
@@ -573,15 +582,44 @@ extern "C" int mdb_nlist_build(mdb_ctx *c)
     if (!c) return MDB_ERR_ARG;
     if (!c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_nlist_build: mdb_nlist_init first");
     CUDA_TRY(c, cudaSetDevice(c->dev));
-    int rc = mdb_cells_build(c);
-    if (rc < 0) return rc;
-    rc = mdb_nlist_kernel(c);
+    int rc = mdb_list_rebuild(c);
     if (rc < 0) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->tiled.active && c->h_counters[CNT_TILE_OVERFLOW] > 0) {
+        // a tile's halo did not fit its shared-memory budget (strongly non-uniform density)
+        if (c->opt_force_path == MDB_FORCE_PATH_TILED)
+            return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path: %d tiles exceed the halo capacity", c->h_counters[CNT_TILE_OVERFLOW]);
+        c->tiled.ok = false; // AUTO: fall back to the generic path and rebuild
+        rc = mdb_list_rebuild(c);
+        if (rc < 0) return rc;
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
     c->mxnac = c->h_counters[CNT_MXNAC];
-    c->list_valid = true;
     return c->h_counters[CNT_OOB];
+}
+
+// cell sort + list kernel of the active path, no host synchronisation
+int mdb_list_rebuild(mdb_ctx *c)
+{
+    if (c->tiled.dirty) {
+        c->tiled.ok = false;
+        if (c->opt_force_path != MDB_FORCE_PATH_GENERIC) {
+            int rc = mdb_tiled_plan(c);
+            if (rc < 0) return rc;
+        }
+        c->tiled.dirty = false;
+    }
+    if (c->opt_force_path == MDB_FORCE_PATH_TILED && !c->tiled.ok)
+        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path not available for this configuration (tables, BOXSHAPE or density)");
+    c->tiled.active = c->tiled.ok && c->opt_force_path != MDB_FORCE_PATH_GENERIC;
+    int rc = mdb_cells_build(c);
+    if (rc < 0) return rc;
+    rc = c->tiled.active ? mdb_tiled_nlist(c) : mdb_nlist_kernel(c);
+    if (rc < 0) return rc;
+    c->list_valid = true;
+    return MDB_OK;
 }
 
 extern "C" int mdb_nlist_overflow(mdb_ctx *c)

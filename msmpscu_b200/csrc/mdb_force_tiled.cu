@@ -1,0 +1,596 @@
+// mdb_force_tiled.cu -- the TILED fast path: neighbour-list build, density pass and force pass
+// over shared-memory staged halo tiles (geometry in mdb_tiled.cuh).
+//
+// Why: with one thread per atom over a global-id list (the reference design, kept as the generic
+// path) every (atom, neighbour) visit is a 32-byte random gather that costs a full L1 wavefront
+// per lane and an un-fused sqrt/sqrt/div/div chain on the fp64 pipe; on B200 that runs at ~5 % of
+// the HBM roofline (profiles/r01_generic_path_summary.md).  Here, per tile:
+//   stage   the <=27 contiguous halo runs are copied once into shared memory as fp64 {x,y,z,den}
+//           records with the periodic image already resolved, plus a 32-bit fixed-point copy
+//           (12/10/10 bits, tile-relative) used only for filtering;
+//   phase A each lane streams its share of the 16-bit slot list (8-byte coalesced loads), tests the
+//           packed copy with integer arithmetic (conservative: quantisation error is added to the
+//           radius, out-of-range atoms always pass) and pushes survivors into a private queue;
+//   phase B the queue is drained in lock-step: fp64 separation from the staged records, the exact
+//           r2 <= RU2 test of the reference, one rsqrt-based evaluation of r, 1/r, sqrt(r), table
+//           rows from shared memory, accumulation.  G lanes share an atom and are reduced with
+//           shuffles; no atomics anywhere, summation order per lane is the reference list order.
+// Pairs beyond the last non-zero table row contribute exactly 0 in the reference arithmetic, so
+// the filter radius is min(RU, table support): fewer phase-B visits, bit-identical sums.
+// The list itself (members, order, truncation) is the reference's: the build kernel evaluates the
+// same fp32 expression as Cal_NeighboreList_Kernel2C (CommonGPU/MD_NeighborsList_GPU.F90:1097-1131)
+// and emits both the slot list and the reference-format KVOIS/INDI.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "mdb_tiled.cuh"
+
+#define QCAP 16 // private queue depth per lane (entries)
+
+__constant__ int t_nix[27] = {0, -1, -1, -1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1, 1, 1, 1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1};
+__constant__ int t_niy[27] = {0, 0, -1, 1, 1, 0, 0, 0, -1, -1, -1, 1, 1, 1, 0, 1, -1, -1, 0, 0, 0, -1, -1, -1, 1, 1, 1};
+__constant__ int t_niz[27] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+
+struct HaloTab { // per-tile halo cell table in shared memory
+    int slot[TILE_MAX_HC + 1]; // first slot of each halo cell (exclusive prefix), [nhc] = total
+    int cnt[TILE_MAX_HC];
+    int gst[TILE_MAX_HC];      // first global (cell-order, 0-based) atom of the cell
+    int cid[TILE_MAX_HC];      // wrapped global cell id, -1 if absent
+    signed char sh[TILE_MAX_HC][4];
+};
+
+// fills the halo table; must be called by all threads of the CTA (contains __syncthreads)
+__device__ __forceinline__ void build_halo_table(const TileParams &P, const TileGeom &g, const int *__restrict__ nac,
+                                                 const int *__restrict__ ia1th, HaloTab &H)
+{
+    for (int hc = threadIdx.x; hc < g.nhc; hc += blockDim.x) {
+        int sh[3], u[3];
+        const int cid = halo_cell(P, g, hc, sh, u);
+        H.cid[hc] = cid;
+        H.cnt[hc] = cid >= 0 ? nac[cid] : 0;
+        H.gst[hc] = cid >= 0 ? ia1th[cid] - 1 : 0;
+        H.sh[hc][0] = (signed char)sh[0]; H.sh[hc][1] = (signed char)sh[1]; H.sh[hc][2] = (signed char)sh[2];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) { // one warp scans the <= 126 counts
+        int run = 0;
+        for (int b = 0; b < g.nhc; b += 32) {
+            const int hc = b + threadIdx.x;
+            const int v = hc < g.nhc ? H.cnt[hc] : 0;
+            int inc = v;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, off);
+                if ((int)threadIdx.x >= off) inc += t;
+            }
+            if (hc < g.nhc) H.slot[hc] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) H.slot[g.nhc] = run;
+    }
+    __syncthreads();
+}
+
+// =====================================================================================
+// list build
+// =====================================================================================
+struct TileListArgs {
+    const double4 *pos; const int *ityp; const int *nac; const int *naac; const int *ia1th;
+    int *kvois; int *indi; unsigned short *nbl; int *counters;
+    float rm2[MDB_MXGROUP * MDB_MXGROUP];
+};
+
+template <int G>
+__global__ void __launch_bounds__(256)
+k_tile_nlist(TileParams P, TileListArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    HaloTab &H = *reinterpret_cast<HaloTab *>(smem);
+    float4 *spos = reinterpret_cast<float4 *>(smem + ((sizeof(HaloTab) + 15) & ~15));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const TileGeom g = tile_geom(P, tile);
+        __syncthreads(); // previous tile fully consumed
+        build_halo_table(P, g, A.nac, A.ia1th, H);
+        const int htot = H.slot[g.nhc];
+        if (htot > P.hcap) { // cannot happen for the build kernel's own capacity unless density is extreme
+            if (threadIdx.x == 0) atomicAdd(&A.counters[CNT_TILE_OVERFLOW], 1);
+            continue;
+        }
+        // stage SPOS = (float)(XP + (double)(float)shift) and the type  (:1100-1103)
+        for (int hc = warp; hc < g.nhc; hc += nwarps) {
+            const int cnt = H.cnt[hc], gst = H.gst[hc], sl = H.slot[hc];
+            const float s0 = H.sh[hc][0] * P.fbs[0], s1 = H.sh[hc][1] * P.fbs[1], s2 = H.sh[hc][2] * P.fbs[2];
+            for (int a = lane; a < cnt; a += 32) {
+                const double4 q = A.pos[gst + a];
+                float4 s;
+                s.x = __double2float_rn(__dadd_rn(q.x, (double)s0));
+                s.y = __double2float_rn(__dadd_rn(q.y, (double)s1));
+                s.z = __double2float_rn(__dadd_rn(q.z, (double)s2));
+                s.w = __int_as_float(A.ityp[gst + a]);
+                spos[sl + a] = s;
+            }
+        }
+        __syncthreads();
+        // owned atoms: centre row (hy = hz = 1), cells hx = 1..wt, contiguous in global order
+        const int hc_own0 = (1 * 3 + 1) * g.nhx + 1;
+        const int own_start = H.gst[hc_own0];
+        const int own_count = H.slot[hc_own0 + g.wt] - H.slot[hc_own0];
+        for (int o = threadIdx.x; o < own_count; o += blockDim.x) {
+            const int ia = own_start + o;
+            // which cell of the tile is this atom in
+            int hxc = 1;
+            while (hxc < g.wt && o >= H.slot[hc_own0 + hxc] - H.slot[hc_own0]) hxc++;
+            const int myhc = hc_own0 + hxc - 1;
+            if (A.naac[H.cid[myhc]] <= 0) continue; // cells without ACTIVE atoms are skipped (:981-982)
+            const float4 me = spos[H.slot[hc_own0] + o]; // own cell is never shifted: (float)XP_i
+            const int ity = __float_as_int(me.w);
+            int nn = 0;
+            for (int k = 0; k < 27; k++) {
+                const int hc = ((1 + t_niz[k]) * 3 + (1 + t_niy[k])) * g.nhx + (hxc + t_nix[k]);
+                if (H.cid[hc] < 0) continue;
+                const int sl = H.slot[hc], cnt = H.cnt[hc], gst = H.gst[hc];
+                for (int t = 0; t < cnt; t++) {
+                    const float4 s = spos[sl + t];
+                    const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
+                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
+                    const int jty = __float_as_int(s.w);
+                    const int j = gst + t;
+                    if (r2 <= A.rm2[(ity - 1) + P.ng * (jty - 1)] && !(k == 0 && j == ia)) { // :1123-1124
+                        nn++;
+                        if (nn <= P.mxkvois) {
+                            A.indi[ia + (size_t)(nn - 1) * P.n] = j + 1;
+                            A.nbl[nbl_index<G>(P, (size_t)ia, nn - 1)] = (unsigned short)(sl + t);
+                        }
+                    }
+                }
+            }
+            A.kvois[ia] = min(nn, P.mxkvois); // :1195
+            if (nn > P.mxkvois) atomicAdd(&A.counters[CNT_OVERFLOW], 1);
+            atomicMax(&A.counters[CNT_NNMAX], nn);
+        }
+    }
+}
+
+// =====================================================================================
+// force passes
+// =====================================================================================
+struct TilePassArgs {
+    double4 *pos; const int *ityp; const int *statu; const int *nac; const int *ia1th; const int *kvois;
+    const unsigned short *nbl; double *fp; int *counters;
+    // tables: global packed {T[kk], T[kk+1]-T[kk]} (stride ntab+2 per kind) for the rare fall-backs
+    const double2 *g_potb, *g_fpotr, *g_fpotb, *g_dfembd;
+    int ntab, nembd, pot_type;
+    double csi, rhod, ru2max;
+    double r2eff;          // min(RU2, table support) for this pass
+    int r2int;             // phase-A radius in LSB^2 units (conservative)
+    int kmin, ktab;        // shared-memory table window: rows kmin .. kmin+ktab-1 (needs row kk and kk+1)
+    int kind0;             // the kind held in shared memory = KPAIR(1,1)
+    int kpair[MDB_MXGROUP * MDB_MXGROUP];
+    int kembd[MDB_MXGROUP];
+};
+
+__device__ __forceinline__ double rsqrt_fast(double a)
+{
+    // MUFU.RSQ64H seed (>= 20 good bits) + one Halley step: y = y0 (1 + e/2 + 3e^2/8), e = 1 - a y0^2.
+    // Residual 5/16 e^3 < 2^-60: the result is within an ulp of the correctly rounded value.
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+    const double t = a * y0;
+    const double e = fma(-t, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y0 * e, p, y0);
+}
+
+__device__ __forceinline__ double lerp_g(const double2 *__restrict__ t, int stride, int k, int kk, double dk)
+{
+    kk = min(max(kk, 0), stride - 1);
+    const double2 e = __ldg(t + (size_t)k * stride + kk);
+    return fma(dk, e.y, e.x);
+}
+
+// PASS 1: rho -> DEN.  PASS 2: forces.  G lanes per atom.  MT: more than one atom type.
+template <int PASS, int G, bool MT>
+__global__ void __launch_bounds__(1024, 1)
+k_tile_pass(TileParams P, TilePassArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    // ---- carve shared memory
+    HaloTab &H = *reinterpret_cast<HaloTab *>(smem);
+    size_t off = (sizeof(HaloTab) + 15) & ~(size_t)15;
+    double2 *s_tab = reinterpret_cast<double2 *>(smem + off);       off += sizeof(double2) * (size_t)(A.ktab + 1);
+    double4 *s_pos = reinterpret_cast<double4 *>(smem + off);       off += sizeof(double4) * (size_t)P.hcap;
+    unsigned *s_pk = reinterpret_cast<unsigned *>(smem + off);      off += sizeof(unsigned) * (size_t)P.hcap;
+    unsigned short *s_q = reinterpret_cast<unsigned short *>(smem + off); off += sizeof(unsigned short) * QCAP * (size_t)blockDim.x;
+    unsigned char *s_typ = smem + off;                              // hcap bytes, only if MT
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int T = blockDim.x;
+    const int gl = threadIdx.x % G;      // lane within the atom's group
+    const int apr = T / G;               // atoms per round
+
+    // ---- tables for kind0, rows kmin..kmin+ktab : staged once per (persistent) CTA
+    //      pass 1: {POTB[kk], POTB[kk+1]}         (one 16-byte read per pair)
+    //      pass 2: {FPOTR[kk], FPOTB[kk]}         (rows kk and kk+1 are two 16-byte reads)
+    {
+        const int stride = A.ntab + 2;
+        for (int r = threadIdx.x; r <= A.ktab; r += T) {
+            const int kk = min(A.kmin + r, stride - 1);
+            if (PASS == 1) {
+                const int k1 = min(kk + 1, stride - 1);
+                s_tab[r] = make_double2(A.g_potb[(size_t)A.kind0 * stride + kk].x, A.g_potb[(size_t)A.kind0 * stride + k1].x);
+            } else {
+                s_tab[r] = make_double2(A.g_fpotr[(size_t)A.kind0 * stride + kk].x, A.g_fpotb[(size_t)A.kind0 * stride + kk].x);
+            }
+        }
+    }
+    __syncthreads();
+
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const TileGeom g = tile_geom(P, tile);
+        __syncthreads();
+        build_halo_table(P, g, A.nac, A.ia1th, H);
+        const int htot = H.slot[g.nhc];
+        if (htot > P.hcap) {
+            if (threadIdx.x == 0) atomicAdd(&A.counters[CNT_TILE_OVERFLOW], 1);
+            continue;
+        }
+        // ---- stage the halo: fp64 record with the periodic image resolved against the nominal
+        //      position of its halo cell, and the packed fixed-point copy for phase A
+        const double ox = P.lo[0] + ((double)(g.cx0 - 1) - 0.5) * P.cell[0];
+        const double oy = P.lo[1] + ((double)(g.cy - 1) - 0.5) * P.cell[1];
+        const double oz = P.lo[2] + ((double)(g.cz - 1) - 0.5) * P.cell[2];
+        for (int hc = warp; hc < g.nhc; hc += nwarps) {
+            const int cnt = H.cnt[hc];
+            if (cnt == 0) continue;
+            const int gst = H.gst[hc], sl = H.slot[hc];
+            const int hx = hc % g.nhx, hyz = hc / g.nhx, hy = hyz % 3, hz = hyz / 3;
+            const double cx = P.lo[0] + ((double)(g.cx0 - 1 + hx) + 0.5) * P.cell[0];
+            const double cy = P.lo[1] + ((double)(g.cy - 1 + hy) + 0.5) * P.cell[1];
+            const double cz = P.lo[2] + ((double)(g.cz - 1 + hz) + 0.5) * P.cell[2];
+            for (int a = lane; a < cnt; a += 32) {
+                double4 p = A.pos[gst + a];
+                if (P.pd[0]) p.x -= P.size[0] * rint((p.x - cx) / P.size[0]);
+                if (P.pd[1]) p.y -= P.size[1] * rint((p.y - cy) / P.size[1]);
+                if (P.pd[2]) p.z -= P.size[2] * rint((p.z - cz) / P.size[2]);
+                const double fx = (p.x - ox) * P.inv_lsb, fy = (p.y - oy) * P.inv_lsb, fz = (p.z - oz) * P.inv_lsb;
+                unsigned pk = 0xFFFFFFFFu; // "always a candidate"
+                if (fx >= 0.0 && fx < 4095.0 && fy >= 0.0 && fy < 1023.0 && fz >= 0.0 && fz < 1022.0) {
+                    const unsigned qx = (unsigned)(fx + 0.5), qy = (unsigned)(fy + 0.5), qz = (unsigned)(fz + 0.5);
+                    pk = (qx << 20) | (qy << 10) | qz;
+                }
+                s_pos[sl + a] = p;
+                s_pk[sl + a] = pk;
+                if (MT) s_typ[sl + a] = (unsigned char)(A.ityp[gst + a] - 1);
+            }
+        }
+        __syncthreads();
+
+        const int hc_own0 = (1 * 3 + 1) * g.nhx + 1;
+        const int own_start = H.gst[hc_own0];
+        const int own_slot0 = H.slot[hc_own0];
+        const int own_count = H.slot[hc_own0 + g.wt] - own_slot0;
+
+        for (int base = 0; base < own_count; base += apr) {
+            const int o = base + (int)threadIdx.x / G;
+            const bool have = o < own_count;
+            const int ia = own_start + (have ? o : 0);
+            const int myslot = own_slot0 + (have ? o : 0);
+            const double4 me = s_pos[myslot];
+            const unsigned mypk = s_pk[myslot];
+            const bool active = have && ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE);
+            const int kv = active ? A.kvois[ia] : 0;
+            const int ti = MT ? (int)s_typ[myslot] : 0;
+            const int qix = (int)(mypk >> 20), qiy = (int)((mypk >> 10) & 1023u), qiz = (int)(mypk & 1023u);
+            const bool me_far = (mypk == 0xFFFFFFFFu);
+
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+            const int nm = (kv - gl + G - 1) / G; // my entries are k = gl + G*m, m < nm (0 if kv <= gl)
+            int m = 0;
+            unsigned short *myq = s_q + threadIdx.x;
+
+            while (true) {
+                int cnt = 0;
+                // ---------------- phase A: fill the private queue
+                while (__any_sync(0xffffffffu, m < nm && cnt <= QCAP - NBL_UNROLL)) {
+                    if (m < nm && cnt <= QCAP - NBL_UNROLL) {
+                        // 4 consecutive entries m..m+3 of this lane: one 8-byte load
+                        const size_t idx = ((((size_t)(m >> 2) * P.npad + (size_t)ia) * G + gl) << 2);
+                        const uint2 raw = __ldcs(reinterpret_cast<const uint2 *>(A.nbl + idx));
+                        unsigned short sl4[4] = {(unsigned short)(raw.x & 0xffffu), (unsigned short)(raw.x >> 16),
+                                                 (unsigned short)(raw.y & 0xffffu), (unsigned short)(raw.y >> 16)};
+                        unsigned pk4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) pk4[u] = (m + u < nm) ? s_pk[sl4[u]] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int dx = qix - (int)(pk4[u] >> 20), dy = qiy - (int)((pk4[u] >> 10) & 1023u),
+                                      dz = qiz - (int)(pk4[u] & 1023u);
+                            const int d2 = dx * dx + dy * dy + dz * dz;
+                            const bool pass = (m + u < nm) && (d2 <= A.r2int || me_far || pk4[u] == 0xFFFFFFFFu);
+                            if (pass) { myq[cnt * T] = sl4[u]; cnt++; }
+                        }
+                        m += 4;
+                    }
+                }
+                const int mx = __reduce_max_sync(0xffffffffu, cnt);
+                if (mx == 0) break;
+                // ---------------- phase B: drain in lock-step
+                for (int q = 0; q < mx; q++) {
+                    const bool on = q < cnt;
+                    const int s = on ? (int)myq[q * T] : myslot;
+                    const double4 pj = s_pos[s];
+                    const double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
+                    const double r2 = fma(sz, sz, fma(sy, sy, sx * sx));
+                    const bool in = on && (r2 <= A.r2eff); // r2eff <= RU2; rows beyond the table support are exactly 0
+                    const double y = rsqrt_fast(in ? r2 : 1.0);
+                    const double r = r2 * y;
+                    const double z = rsqrt_fast(in ? r : 1.0);
+                    const double sk = (r * z) * A.csi;            // sqrt(r)*CSI
+                    const double tk = __dadd_rd(sk, 4503599627370496.0);
+                    const int kk = __double2loint(tk);            // KK = int(SK)
+                    const double dk = sk - (tk - 4503599627370496.0);
+                    const int rr = kk - A.kmin;
+                    int k0 = A.kind0, k1 = A.kind0;
+                    bool smem_ok = (rr >= 0 && rr < A.ktab);
+                    if (MT) {
+                        const int tj = (int)s_typ[s];
+                        k0 = A.kpair[ti + P.ng * tj];
+                        k1 = A.kpair[tj + P.ng * ti];
+                        smem_ok = smem_ok && k0 == A.kind0 && k1 == A.kind0;
+                    }
+                    if (PASS == 1) {
+                        double val;
+                        if (smem_ok) {
+                            const double2 e = s_tab[rr];
+                            val = fma(dk, e.y - e.x, e.x);
+                        } else {
+                            val = in ? lerp_g(A.g_potb, A.ntab + 2, k0, kk, dk) : 0.0;
+                        }
+                        acc0 += in ? val : 0.0;
+                    } else {
+                        double fr, fb0, fb1;
+                        if (smem_ok) {
+                            const double2 e0 = s_tab[rr], e1 = s_tab[rr + 1];
+                            fr = fma(dk, e1.x - e0.x, e0.x);
+                            fb0 = fma(dk, e1.y - e0.y, e0.y);
+                            fb1 = fb0;
+                        } else if (in) {
+                            fr = lerp_g(A.g_fpotr, A.ntab + 2, k0, kk, dk);
+                            fb0 = lerp_g(A.g_fpotb, A.ntab + 2, k0, kk, dk);
+                            fb1 = MT ? lerp_g(A.g_fpotb, A.ntab + 2, k1, kk, dk) : fb0;
+                        } else {
+                            fr = fb0 = fb1 = 0.0;
+                        }
+                        // FORTOT = FPOTR/R2 + (FPOTB_ij*DEN_i + FPOTB_ji*DEN_j)/R     (:811-813)
+                        double ft = y * fma(fr, y, fma(fb0, me.w, fb1 * pj.w));
+                        ft = in ? ft : 0.0;
+                        acc0 = fma(ft, sx, acc0);
+                        acc1 = fma(ft, sy, acc1);
+                        acc2 = fma(ft, sz, acc2);
+                    }
+                }
+            }
+            // ---------------- reduce the G partial sums of the atom and write
+#pragma unroll
+            for (int w = 1; w < G; w <<= 1) {
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, w);
+                if (PASS == 2) {
+                    acc1 += __shfl_xor_sync(0xffffffffu, acc1, w);
+                    acc2 += __shfl_xor_sync(0xffffffffu, acc2, w);
+                }
+            }
+            if (have && gl == 0) {
+                if (PASS == 1) {
+                    double den0 = acc0;
+                    if (active) {
+                        if (A.pot_type == MDB_POT_FS) {
+                            if (den0 > 0.0) den0 = -0.5 / sqrt(den0);
+                        } else if (den0 > 0.0) {
+                            const double sk = den0 / A.rhod + 1.0;
+                            const int kk = (int)(sk + 0.000001);
+                            den0 = lerp_g(A.g_dfembd, A.nembd + 2, A.kembd[ti], kk, sk - (double)kk);
+                        }
+                    } else den0 = 0.0;
+                    reinterpret_cast<double *>(A.pos + ia)[3] = den0;
+                } else {
+                    A.fp[ia] = acc0;
+                    A.fp[ia + (size_t)P.n] = acc1;
+                    A.fp[ia + 2 * (size_t)P.n] = acc2;
+                }
+            }
+        }
+    }
+    // atoms parked outside the cells (out of box, inactive): zero outputs, as the generic path does
+    if (blockIdx.x == 0) {
+        const int n_in = A.counters[CNT_INCELL];
+        for (int i = n_in + threadIdx.x; i < P.n; i += T) {
+            if (PASS == 1) reinterpret_cast<double *>(A.pos + i)[3] = 0.0;
+            else { A.fp[i] = 0.0; A.fp[i + (size_t)P.n] = 0.0; A.fp[i + 2 * (size_t)P.n] = 0.0; }
+        }
+    }
+}
+
+// =====================================================================================
+// host side: planning and launch
+// =====================================================================================
+static const int SMEM_BUDGET = 227 * 1024;
+
+static size_t pass_smem_bytes(int hcap, int ktab, int threads, bool mt)
+{
+    size_t b = (sizeof(HaloTab) + 15) & ~(size_t)15;
+    b += sizeof(double2) * (size_t)(ktab + 1);
+    b += (sizeof(double4) + sizeof(unsigned)) * (size_t)hcap;
+    b += sizeof(unsigned short) * QCAP * (size_t)threads;
+    if (mt) b += hcap;
+    return b + 32;
+}
+
+// largest Fortran row index with a non-zero entry in the kind-major host copy kept by the context
+static int last_nonzero_row(const std::vector<double> &t, int nkind, int ntab)
+{
+    for (int i = ntab; i >= 1; i--)
+        for (int k = 0; k < nkind; k++)
+            if (t[(size_t)(i - 1) * nkind + k] != 0.0) return i;
+    return 0;
+}
+
+int mdb_tiled_plan(mdb_ctx *c)
+{
+    TiledState &S = c->tiled;
+    S.ok = false;
+    if (!c->has_tables || !c->has_nlist || !c->shape_identity) return MDB_OK;
+    if (c->mxkvois > 4096 || c->nc <= 0) return MDB_OK;
+    const TableSet &t = c->tab;
+    // ---- table support -> effective cut-offs (rows >= kz+1 interpolate to exactly 0)
+    const double csi = t.csi;
+    auto r2_of_row = [&](int kz) { const double r = ((double)(kz + 2) / csi) * ((double)(kz + 2) / csi); return r * r; };
+    const int kz1 = last_nonzero_row(c->h_potb, t.nkind, t.ntab);
+    const int kz2 = std::max(last_nonzero_row(c->h_fpotr, t.nkind, t.ntab), last_nonzero_row(c->h_fpotb, t.nkind, t.ntab));
+    S.r2eff[0] = std::min(t.ru2max, r2_of_row(kz1));
+    S.r2eff[1] = std::min(t.ru2max, r2_of_row(kz2));
+    const int kru = std::min(t.ntab + 1, (int)(std::sqrt(std::sqrt(t.ru2max)) * csi) + 1);
+    S.khi[0] = std::min(kru, kz1 + 2);
+    S.khi[1] = std::min(kru, kz2 + 2);
+
+    // ---- tile geometry
+    const int G = S.G;
+    const double rho_cell = (double)c->n / (double)c->nc;
+    const bool mt = c->ng > 1;
+    int best_w = 0;
+    for (int w = std::min(c->ncell[0], TILE_MAX_W); w >= 1; w--) {
+        const int ntx = (c->ncell[0] + w - 1) / w;
+        const int wt = (c->ncell[0] + ntx - 1) / ntx;
+        const int own = (int)(wt * rho_cell * 1.3) + 8;
+        if (own * G > 1024 && w > 1) continue;
+        const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.25) + 64;
+        if (hcap > 65000) continue;
+        const int threads = std::min(1024, ((own * G + 31) / 32) * 32);
+        // table window: as many rows below khi as fit
+        const size_t fixed = pass_smem_bytes(hcap, 0, threads, mt);
+        if (fixed + 16 * 512 > (size_t)SMEM_BUDGET) continue;
+        const int maxrows = (int)((SMEM_BUDGET - fixed) / 16) - 2;
+        const int need = std::max(S.khi[0], S.khi[1]) + 1;
+        // require the window to reach down to r = 0.6 * (nearest plausible approach) ... or everything
+        const int want = std::min(need, maxrows);
+        if (want < need && want < need / 2) continue; // too little room for tables: try a narrower tile
+        best_w = w;
+        S.ntx = ntx; S.hcap = hcap; S.threads = threads;
+        for (int p = 0; p < 2; p++) {
+            S.ktab[p] = std::min(S.khi[p] + 1, maxrows);
+            S.kmin[p] = S.khi[p] + 1 - S.ktab[p];
+        }
+        break;
+    }
+    if (!best_w) return MDB_OK;
+
+    TileParams &P = S.P;
+    memset(&P, 0, sizeof(P));
+    P.n = c->n; P.nbox = c->nbox; P.ncx = c->ncell[0]; P.ncy = c->ncell[1]; P.ncz = c->ncell[2]; P.nc0 = c->nc0;
+    P.ntx = S.ntx; P.nrows = c->nbox * c->ncell[1] * c->ncell[2]; P.ntiles = P.nrows * P.ntx; P.hcap = S.hcap;
+    double cellmax = 0.0;
+    for (int d = 0; d < 3; d++) {
+        P.pd[d] = c->box.pd[d]; P.lo[d] = c->box.lo[d]; P.size[d] = c->box.size[d];
+        P.cell[d] = c->box.size[d] / (double)c->ncell[d];
+        P.fbs[d] = (float)c->box.size[d];
+        cellmax = std::max(cellmax, P.cell[d]);
+    }
+    const double lsb = cellmax / 256.0;
+    P.inv_lsb = 1.0 / lsb;
+    P.ng = c->ng; P.mxkvois = c->mxkvois;
+    const int rows_per_lane = (c->mxkvois + G - 1) / G;
+    P.nrow4 = (rows_per_lane + 3) / 4;
+    P.npad = (size_t)c->n;
+    for (int p = 0; p < 2; p++) {
+        // |quantised distance - true distance| <= sqrt(3) LSB (each coordinate difference is off by <= 1 LSB)
+        const double rl = std::sqrt(S.r2eff[p]) / lsb + 1.7321 + 0.01;
+        S.r2int[p] = (int)(rl * rl) + 1;
+    }
+    // ---- slot list storage
+    const size_t nbl_elems = (size_t)P.nrow4 * P.npad * G * 4;
+    if (S.nbl_elems < nbl_elems) {
+        if (S.nbl) cudaFree(S.nbl);
+        S.nbl = nullptr; S.nbl_elems = 0;
+        if (cudaMalloc(&S.nbl, nbl_elems * sizeof(unsigned short)) != cudaSuccess) { cudaGetLastError(); return MDB_OK; }
+        S.nbl_elems = nbl_elems;
+    }
+    // ---- launch configuration
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev);
+    S.grid = std::min(P.ntiles, nsm);
+    S.smem_list = ((sizeof(HaloTab) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap + 32;
+    S.grid_list = std::min(P.ntiles, nsm * std::max(1, std::min(8, (int)(SMEM_BUDGET / S.smem_list))));
+    for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads, mt);
+    S.ok = true;
+    return MDB_OK;
+}
+
+template <int G>
+static int launch_list(mdb_ctx *c)
+{
+    TiledState &S = c->tiled;
+    TileListArgs A;
+    A.pos = c->pos; A.ityp = c->ityp; A.nac = c->nac; A.naac = c->naac; A.ia1th = c->ia1th;
+    A.kvois = c->kvois; A.indi = c->indi; A.nbl = S.nbl; A.counters = c->counters;
+    for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
+    CUDA_TRY(c, cudaFuncSetAttribute(k_tile_nlist<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
+    ProfScope ps(c, MDB_K_NLIST);
+    k_tile_nlist<G><<<S.grid_list, 256, S.smem_list, c->stream>>>(S.P, A);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+int mdb_tiled_nlist(mdb_ctx *c)
+{
+    switch (c->tiled.G) {
+    case 1: return launch_list<1>(c);
+    case 2: return launch_list<2>(c);
+    case 4: return launch_list<4>(c);
+    case 8: return launch_list<8>(c);
+    }
+    return mdb_fail(c, MDB_ERR_ARG, "tiled path: unsupported lane-group size %d", c->tiled.G);
+}
+
+template <int PASS, int G, bool MT>
+static int launch_pass(mdb_ctx *c)
+{
+    TiledState &S = c->tiled;
+    const TableSet &t = c->tab;
+    TilePassArgs A;
+    A.pos = c->pos; A.ityp = c->ityp; A.statu = c->statu; A.nac = c->nac; A.ia1th = c->ia1th; A.kvois = c->kvois;
+    A.nbl = S.nbl; A.fp = c->fp; A.counters = c->counters;
+    A.g_potb = t.potb; A.g_fpotr = t.fpotr; A.g_fpotb = t.fpotb; A.g_dfembd = t.dfembd;
+    A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod; A.ru2max = t.ru2max;
+    A.r2eff = S.r2eff[PASS - 1]; A.r2int = S.r2int[PASS - 1]; A.kmin = S.kmin[PASS - 1]; A.ktab = S.ktab[PASS - 1];
+    A.kind0 = t.kpair[0];
+    for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
+    for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
+    auto kern = k_tile_pass<PASS, G, MT>;
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_pass[PASS - 1]));
+    ProfScope ps(c, PASS == 1 ? MDB_K_PASS1 : MDB_K_PASS2);
+    kern<<<S.grid, S.threads, S.smem_pass[PASS - 1], c->stream>>>(S.P, A);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+template <int G>
+static int launch_force(mdb_ctx *c, unsigned flags)
+{
+    const bool mt = c->ng > 1;
+    int rc = MDB_OK;
+    if (flags & (MDB_FORCE | MDB_DEN)) rc = mt ? launch_pass<1, G, true>(c) : launch_pass<1, G, false>(c);
+    if (rc < 0) return rc;
+    if (flags & MDB_FORCE) rc = mt ? launch_pass<2, G, true>(c) : launch_pass<2, G, false>(c);
+    return rc;
+}
+
+int mdb_force_tiled(mdb_ctx *c, unsigned flags)
+{
+    switch (c->tiled.G) {
+    case 1: return launch_force<1>(c, flags);
+    case 2: return launch_force<2>(c, flags);
+    case 4: return launch_force<4>(c, flags);
+    case 8: return launch_force<8>(c, flags);
+    }
+    return mdb_fail(c, MDB_ERR_ARG, "tiled path: unsupported lane-group size %d", c->tiled.G);
+}

@@ -23,7 +23,8 @@
 #define KB_CGS 1.38054e-16 // CP_KB, MSMLIB/sor/Common/MSM_Const.F90:82
 
 // device counters block (one int each)
-enum { CNT_OOB = 0, CNT_OVERFLOW, CNT_NNMAX, CNT_MXNAC, CNT_INCELL, CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N, CNT__N = 8 };
+enum { CNT_OOB = 0, CNT_OVERFLOW, CNT_NNMAX, CNT_MXNAC, CNT_INCELL, CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N,
+       CNT_TILE_OVERFLOW, CNT__N = 8 };
 
 struct BoxParams { // passed by value to kernels
     double lo[3], up[3], size[3], half[3];
@@ -48,6 +49,31 @@ struct EpcParams {
 };
 
 struct MassParams { double cm[MDB_MXGROUP]; };
+
+// geometry of the tiled path, passed by value to its kernels (see mdb_tiled.cuh)
+struct TileParams {
+    int n, nbox, ncx, ncy, ncz, nc0;
+    int ntx, nrows, ntiles;        // tiles per x-row, rows, total tiles
+    int hcap;                      // halo capacity in atoms (shared-memory budget)
+    int pd[3];
+    double lo[3], size[3], cell[3];
+    float fbs[3];                  // (float)BOXSIZE: the fp32 image shift of the list kernel
+    double inv_lsb;                // 1 / LSB of the packed fixed-point filter coordinates
+    int ng, mxkvois, nrow4;        // nrow4 = 4-entry index groups per (atom, lane)
+    size_t npad;                   // padded atom count of the slot list
+};
+
+// state of the tiled fast path (mdb_force_tiled.cu)
+struct TiledState {
+    TileParams P;
+    bool ok = false, dirty = true, active = false;
+    int G = 4;                 // lanes per atom
+    int ntx = 0, hcap = 0, threads = 0, grid = 0, grid_list = 0;
+    int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0}, r2int[2] = {0, 0};
+    double r2eff[2] = {0.0, 0.0};
+    size_t smem_list = 0, smem_pass[2] = {0, 0};
+    unsigned short *nbl = nullptr; size_t nbl_elems = 0;
+};
 
 struct mdb_ctx {
     int dev = 0;
@@ -99,6 +125,12 @@ struct mdb_ctx {
     // ---- epc
     EpcParams epc;
 
+    // ---- host copies of the pair tables (Fortran layout) for planning the tiled path
+    std::vector<double> h_potb, h_fpotr, h_fpotb;
+
+    // ---- tiled fast path
+    TiledState tiled;
+
     // ---- options
     int opt_force_path = MDB_FORCE_PATH_AUTO;
 
@@ -139,4 +171,7 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 int mdb_cells_build(mdb_ctx *c);             // mdb_cells.cu : bin, sort, permute
 int mdb_nlist_kernel(mdb_ctx *c);            // mdb_nlist.cu : fill KVOIS/INDI
 int mdb_force_generic(mdb_ctx *c, unsigned flags, double *vt); // mdb_force.cu
-int mdb_views_refresh(mdb_ctx *c, int field); // mdb_api.cu
+int mdb_tiled_plan(mdb_ctx *c);               // mdb_force_tiled.cu
+int mdb_tiled_nlist(mdb_ctx *c);
+int mdb_force_tiled(mdb_ctx *c, unsigned flags);
+int mdb_list_rebuild(mdb_ctx *c);             // mdb_api.cu : cells + list kernel of the active path (no sync)

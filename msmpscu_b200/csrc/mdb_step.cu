@@ -173,6 +173,19 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     if (!c->shape_identity) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: non-identity BOXSHAPE is not supported yet");
     if ((flags & MDB_VIRIAL) && !vtensor) return mdb_fail(c, MDB_ERR_ARG, "mdb_force: MDB_VIRIAL needs vtensor");
     CUDA_TRY(c, cudaSetDevice(c->dev));
+    if (c->tiled.active) {
+        // density + force passes on the tiled path; virial / per-atom energy (output steps only)
+        // run on the generic kernels over the reference-format list the tiled build also emits
+        unsigned fast = flags & (MDB_FORCE | MDB_DEN);
+        if (flags & MDB_VIRIAL) fast = 0;
+        if (fast) {
+            int rc = mdb_force_tiled(c, fast);
+            if (rc < 0) return rc;
+        }
+        const unsigned rest = flags & ~fast;
+        if (rest & (MDB_VIRIAL | MDB_EPOT)) return mdb_force_generic(c, rest & ~MDB_DEN, vtensor);
+        return MDB_OK;
+    }
     return mdb_force_generic(c, flags, vtensor);
 }
 
@@ -181,9 +194,7 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)
     int rc;
     if ((rc = mdb_predict(c, h)) < 0) return rc;
     if (nb_uptab > 0 && (itime - it0) % nb_uptab == 0) { // MOD(ITIME-IT0,NB_UPTAB)==0, GenericMD:599-601
-        if ((rc = mdb_cells_build(c)) < 0) return rc;
-        if ((rc = mdb_nlist_kernel(c)) < 0) return rc;
-        c->list_valid = true;
+        if ((rc = mdb_list_rebuild(c)) < 0) return rc;
     }
     if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
     ProfScope ps(c, MDB_K_CORRECT);
@@ -205,6 +216,12 @@ extern "C" int mdb_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab
     }
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->tiled.active && c->h_counters[CNT_TILE_OVERFLOW] > 0) {
+        c->tiled.ok = false; // later rebuilds use the generic path
+        c->list_valid = false;
+        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path: a tile exceeded its halo capacity during mdb_run; state is unreliable, "
+                                                 "re-upload and rerun (the generic path is now selected)");
+    }
     return c->h_counters[CNT_OOB_TOTAL];
 }
 

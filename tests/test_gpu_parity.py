@@ -10,6 +10,7 @@ from msmpscu_b200 import capi
 pytestmark = pytest.mark.gpu
 
 FORCE_RTOL = 1e-10
+PATHS = {"generic": capi.FORCE_PATH_GENERIC, "tiled": capi.FORCE_PATH_TILED}
 
 
 def _oracle_list(O, c):
@@ -25,13 +26,14 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("name", list(CASES))
-def test_cells_and_list_bit_exact(oracle, name):
+def test_cells_and_list_bit_exact(oracle, name, path):
     """NeighboresListTest.F90:92-121 restated: identical KVOIS and identical ORDER of INDI, plus the
     cell assignment / sort (GID, NAC, IA1th) the list is built on."""
     c = CASES[name]()
     ref = _oracle_list(oracle, c)
-    ctx = util.make_ctx(c)
+    ctx = util.make_ctx(c, force_path=PATHS[path])
     ncell, nc, mxnac = ctx.cellinfo()
     assert ncell == ref["ncell"]
     assert np.array_equal(ctx.download(capi.F_GID, capi.ORDER_CELL), ref["gid"])
@@ -49,8 +51,9 @@ def test_cells_and_list_bit_exact(oracle, name):
     ctx.close()
 
 
+@pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("name", list(CASES))
-def test_force_energy_virial_parity(oracle, name):
+def test_force_energy_virial_parity(oracle, name, path):
     """CalForceTest.F90:113-147 restated for EAM: forces, DEN, EPOT, virial against the CPU oracle."""
     c = CASES[name]()
     ref = _oracle_list(oracle, c)
@@ -58,7 +61,7 @@ def test_force_energy_virial_parity(oracle, name):
     T = util.oracle_tables(oracle, c)
     fp, den, vt, ep = oracle.force(c.xp[gid], c.ityp[gid], ref["statu"][gid], ref["kvois"], ref["indi"], c.zl, c.ifpd,
                                    T, virial=True, epot=True)
-    ctx = util.make_ctx(c)
+    ctx = util.make_ctx(c, force_path=PATHS[path])
     vt_gpu = ctx.force(capi.FORCE | capi.VIRIAL | capi.EPOT)
     f_gpu = ctx.download(capi.F_FP, capi.ORDER_CELL)
     d_gpu = ctx.download(capi.F_DEN, capi.ORDER_CELL)
@@ -69,19 +72,22 @@ def test_force_energy_virial_parity(oracle, name):
     assert util.relerr(vt_gpu, vt / c.nbox) < FORCE_RTOL
     # force-only entry point gives the same forces as the virial one
     ctx.force(capi.FORCE)
-    assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < FORCE_RTOL
+    f_gpu = ctx.download(capi.F_FP, capi.ORDER_CELL)
+    assert util.relerr(f_gpu, fp) < FORCE_RTOL
+    assert util.relerr(ctx.download(capi.F_DEN, capi.ORDER_CELL), den) < FORCE_RTOL
     # ORIGINAL-order download un-permutes through GID
     f_orig = ctx.download(capi.F_FP, capi.ORDER_ORIGINAL)
     assert np.array_equal(f_orig[gid], f_gpu)
     ctx.close()
 
 
+@pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("tag", ["react", "product"])
-def test_golden_known_answer_through_cuda(tag):
+def test_golden_known_answer_through_cuda(tag, path):
     """The reference GPU build's own output (examples/NEB_Test/GMD/*P0000_0001.0000): force [eV/LU]
     and POT [eV] to 9 digits.  That binary used Rmax = max(NB_RM)."""
     c = util.neb_case(tag, rmax_mode="NB_RM")
-    ctx = util.make_ctx(c)
+    ctx = util.make_ctx(c, force_path=PATHS[path])
     ctx.force(capi.FORCE | capi.EPOT)
     F = ctx.download(capi.F_FP) * c.rr / util.CP_EVERG
     POT = -ctx.download(capi.F_EPOT) / util.CP_EVERG
@@ -120,11 +126,12 @@ def test_integrator_epc_ekin_bit_exact(oracle):
     ctx.close()
 
 
-def test_truncated_list_matches_reference_truncation(oracle):
+@pytest.mark.parametrize("path", list(PATHS))
+def test_truncated_list_matches_reference_truncation(oracle, path):
     """mxKVOIS smaller than the true count: the reference silently keeps the first mxKVOIS in scan order."""
     c = util.bcc_case((7, 7, 7), mxkvois=60)
     ref = _oracle_list(oracle, c)
-    ctx = util.make_ctx(c)
+    ctx = util.make_ctx(c, force_path=PATHS[path])
     kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
     assert kv.max() == 60 and np.array_equal(kv, ref["kvois"])
     assert np.array_equal(ind, ref["indi"])
@@ -132,7 +139,8 @@ def test_truncated_list_matches_reference_truncation(oracle):
     ctx.close()
 
 
-def test_md_trajectory_tracks_oracle(oracle):
+@pytest.mark.parametrize("path", list(PATHS))
+def test_md_trajectory_tracks_oracle(oracle, path):
     """For_One_Step sequence (predictor -> rebuild when MOD(ITIME-IT0,NB_UPTAB)==0 -> force -> corrector):
     25 steps with rebuilds at ITIME=1,11,21; positions/velocities stay within round-off growth of the
     oracle's, the lists built on them stay identical, and the NVE Hamiltonian drift matches."""
@@ -140,7 +148,7 @@ def test_md_trajectory_tracks_oracle(oracle):
     h, it0, nup = 0.5e-15, 1, 10
     md = util.oracle_md(oracle, c)
     md.rebuild(); md.force()
-    ctx = util.make_ctx(c)
+    ctx = util.make_ctx(c, force_path=PATHS[path])
     ctx.force(capi.FORCE)
     for it in range(25):
         md.step(it, it0, nup, h)
@@ -163,7 +171,8 @@ def test_md_trajectory_tracks_oracle(oracle):
     ctx.close()
 
 
-def test_out_of_box_atoms_are_parked_like_the_reference(oracle):
+@pytest.mark.parametrize("path", list(PATHS))
+def test_out_of_box_atoms_are_parked_like_the_reference(oracle, path):
     """Non-periodic x: atoms pushed outside are flagged OUTOFBOX, counted, and placed at the end of the
     CELL order (smallest original id last), MD_NeighborsList_GPU.F90:1505-1526,1627-1637."""
     c = util.bcc_case((7, 7, 7), ifpd=(0, 1, 1), seed=3)
@@ -171,14 +180,39 @@ def test_out_of_box_atoms_are_parked_like_the_reference(oracle):
     c.xp[[5, 77, 300], 0] += 2.0 * c.zl[0]
     c.xp[[10], 0] -= 2.0 * c.zl[0]
     ref = _oracle_list(oracle, c)
-    ctx = util.make_ctx(c, build=False)
+    ctx = util.make_ctx(c, build=False, force_path=PATHS[path])
     assert ctx.nlist_build() == 4 == ref["nout"]
     assert np.array_equal(ctx.download(capi.F_GID, capi.ORDER_CELL), ref["gid"])
     assert np.array_equal(ctx.download(capi.F_STATU, capi.ORDER_ORIGINAL), ref["statu"])
     kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
     n_in = c.xp.shape[0] - 4
     assert np.array_equal(kv[:n_in], ref["kvois"][:n_in])
+    # forces with missing neighbours / parked atoms still match
+    gid = ref["gid"] - 1
+    fp, den, _, _ = oracle.force(c.xp[gid], c.ityp[gid], ref["statu"][gid], ref["kvois"], ref["indi"], c.zl, c.ifpd,
+                                 util.oracle_tables(oracle, c))
+    ctx.force(capi.FORCE)
+    assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < FORCE_RTOL
+    assert np.all(ctx.download(capi.F_FP, capi.ORDER_CELL)[n_in:] == 0.0)
     ctx.close()
+
+
+def test_tiled_matches_generic_at_scale():
+    """128 000 atoms (too slow for the CPU oracle in a unit test): the tiled fast path against the
+    bit-faithful generic kernels on the device, lists identical, forces to 1e-12."""
+    c = util.bcc_case((40, 40, 40), seed=31)
+    a = util.make_ctx(c, force_path=capi.FORCE_PATH_GENERIC)
+    b = util.make_ctx(c, force_path=capi.FORCE_PATH_TILED)
+    ka, ia = a.nlist_copyout(capi.ORDER_CELL)
+    kb, ib = b.nlist_copyout(capi.ORDER_CELL)
+    assert np.array_equal(ka, kb) and all(np.array_equal(ia[w][ka > w], ib[w][ka > w]) for w in range(c.mxkvois))
+    a.force(capi.FORCE); b.force(capi.FORCE)
+    assert util.relerr(b.download(capi.F_DEN, capi.ORDER_CELL), a.download(capi.F_DEN, capi.ORDER_CELL)) < 1e-12
+    assert util.relerr(b.download(capi.F_FP, capi.ORDER_CELL), a.download(capi.F_FP, capi.ORDER_CELL)) < 1e-12
+    a.run(0, 12, 1, 10, 0.5e-15); b.run(0, 12, 1, 10, 0.5e-15)
+    assert np.array_equal(a.download(capi.F_GID, capi.ORDER_CELL), b.download(capi.F_GID, capi.ORDER_CELL))
+    assert util.relerr(b.download(capi.F_XP), a.download(capi.F_XP)) < 1e-13
+    a.close(); b.close()
 
 
 def test_errors_are_status_codes_not_stops():
