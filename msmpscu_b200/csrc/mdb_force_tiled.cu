@@ -25,7 +25,6 @@
 #include <cstring>
 #include "mdb_tiled.cuh"
 
-#define QCAP 16 // private queue depth per lane (entries)
 
 __constant__ int t_nix[27] = {0, -1, -1, -1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1, 1, 1, 1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1};
 __constant__ int t_niy[27] = {0, 0, -1, 1, 1, 0, 0, 0, -1, -1, -1, 1, 1, 1, 0, 1, -1, -1, 0, 0, 0, -1, -1, -1, 1, 1, 1};
@@ -36,7 +35,8 @@ struct HaloTab { // per-tile halo cell table in shared memory
     int cnt[TILE_MAX_HC];
     int gst[TILE_MAX_HC];      // first global (cell-order, 0-based) atom of the cell
     int cid[TILE_MAX_HC];      // wrapped global cell id, -1 if absent
-    signed char sh[TILE_MAX_HC][4];
+    signed char sh[TILE_MAX_HC][4]; // image shift per dim, [3] = edge flag
+    int edge_any;
 };
 
 // fills the halo table; must be called by all threads of the CTA (contains __syncthreads)
@@ -50,13 +50,21 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
         H.cnt[hc] = cid >= 0 ? nac[cid] : 0;
         H.gst[hc] = cid >= 0 ? ia1th[cid] - 1 : 0;
         H.sh[hc][0] = (signed char)sh[0]; H.sh[hc][1] = (signed char)sh[1]; H.sh[hc][2] = (signed char)sh[2];
+        // edge flag: a wrapped cell, or a cell on a periodic face of the box (its atoms may have been
+        // wrapped by the predictor since the rebuild)
+        const int nc[3] = {P.ncx, P.ncy, P.ncz};
+        bool edge = false;
+        for (int d = 0; d < 3; d++) edge = edge || (P.pd[d] && (u[d] <= 0 || u[d] >= nc[d] - 1));
+        H.sh[hc][3] = (signed char)((cid >= 0 && edge) ? 1 : 0);
     }
     __syncthreads();
     if (threadIdx.x < 32) { // one warp scans the <= 126 counts
         int run = 0;
+        bool edge = false;
         for (int b = 0; b < g.nhc; b += 32) {
             const int hc = b + threadIdx.x;
             const int v = hc < g.nhc ? H.cnt[hc] : 0;
+            edge = edge || (hc < g.nhc && H.sh[hc][3] != 0);
             int inc = v;
             for (int off = 1; off < 32; off <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, inc, off);
@@ -65,7 +73,8 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
             if (hc < g.nhc) H.slot[hc] = run + inc - v;
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (threadIdx.x == 0) H.slot[g.nhc] = run;
+        edge = __any_sync(0xffffffffu, edge);
+        if (threadIdx.x == 0) { H.slot[g.nhc] = run; H.edge_any = edge ? 1 : 0; }
     }
     __syncthreads();
 }
@@ -163,9 +172,10 @@ struct TilePassArgs {
     int ntab, nembd, pot_type;
     double csi, rhod, ru2max;
     double r2eff;          // min(RU2, table support) for this pass
-    int r2int;             // phase-A radius in LSB^2 units (conservative)
-    int kmin, ktab;        // shared-memory table window: rows kmin .. kmin+ktab-1 (needs row kk and kk+1)
+    int r2int;             // phase-A radius^2 in LSB units (conservative)
+    int kmin, ktab;        // shared-memory table window: rows kmin .. kmin+ktab (row kk and kk+1 are read)
     int kind0;             // the kind held in shared memory = KPAIR(1,1)
+    int qcap;              // queue entries per atom group
     int kpair[MDB_MXGROUP * MDB_MXGROUP];
     int kembd[MDB_MXGROUP];
 };
@@ -189,29 +199,73 @@ __device__ __forceinline__ double lerp_g(const double2 *__restrict__ t, int stri
     return fma(dk, e.y, e.x);
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// byte-modular packed coordinates for phase A: q_d = floor(x_d / LSB) mod 256.  For two atoms in the
+// same (image-resolved) tile frame, a pair with r <= r_eff has |dq_d| <= r_eff/LSB + 1 <= 127 in every
+// coordinate, so the signed 8-bit differences are exact and  |dq|^2 <= (r_eff/LSB + sqrt(3))^2 :
+// the filter can only err towards passing a pair (wrap-around of far pairs), never towards dropping one.
+__device__ __forceinline__ unsigned pack_q(double x, double y, double z, double inv_lsb)
+{
+    const unsigned qx = (unsigned)__double2int_rd(x * inv_lsb) & 255u;
+    const unsigned qy = (unsigned)__double2int_rd(y * inv_lsb) & 255u;
+    const unsigned qz = (unsigned)__double2int_rd(z * inv_lsb) & 255u;
+    return qx | (qy << 8) | (qz << 16);
+}
+
 // PASS 1: rho -> DEN.  PASS 2: forces.  G lanes per atom.  MT: more than one atom type.
 template <int PASS, int G, bool MT>
 __global__ void __launch_bounds__(1024, 1)
 k_tile_pass(TileParams P, TilePassArgs A)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     // ---- carve shared memory
     HaloTab &H = *reinterpret_cast<HaloTab *>(smem);
     size_t off = (sizeof(HaloTab) + 15) & ~(size_t)15;
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + off);   off += 16;
     double2 *s_tab = reinterpret_cast<double2 *>(smem + off);       off += sizeof(double2) * (size_t)(A.ktab + 1);
+    off = (off + 127) & ~(size_t)127;
     double4 *s_pos = reinterpret_cast<double4 *>(smem + off);       off += sizeof(double4) * (size_t)P.hcap;
     unsigned *s_pk = reinterpret_cast<unsigned *>(smem + off);      off += sizeof(unsigned) * (size_t)P.hcap;
-    unsigned short *s_q = reinterpret_cast<unsigned short *>(smem + off); off += sizeof(unsigned short) * QCAP * (size_t)blockDim.x;
+    const int T = blockDim.x;
+    const int ngrp = T / G;              // atom groups per CTA = atoms per round
+    unsigned short *s_q = reinterpret_cast<unsigned short *>(smem + off); off += sizeof(unsigned short) * (size_t)A.qcap * ngrp;
     unsigned char *s_typ = smem + off;                              // hcap bytes, only if MT
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int T = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
     const int gl = threadIdx.x % G;      // lane within the atom's group
-    const int apr = T / G;               // atoms per round
+    const int grp = threadIdx.x / G;
 
     // ---- tables for kind0, rows kmin..kmin+ktab : staged once per (persistent) CTA
     //      pass 1: {POTB[kk], POTB[kk+1]}         (one 16-byte read per pair)
-    //      pass 2: {FPOTR[kk], FPOTB[kk]}         (rows kk and kk+1 are two 16-byte reads)
+    //      pass 2: {FPOTR[kk], FPOTB[kk]}         (rows kk and kk+1: two 16-byte reads)
     {
         const int stride = A.ntab + 2;
         for (int r = threadIdx.x; r <= A.ktab; r += T) {
@@ -223,45 +277,61 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 s_tab[r] = make_double2(A.g_fpotr[(size_t)A.kind0 * stride + kk].x, A.g_fpotb[(size_t)A.kind0 * stride + kk].x);
             }
         }
+        if (threadIdx.x == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     }
     __syncthreads();
+    unsigned phase = 0;
 
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const TileGeom g = tile_geom(P, tile);
-        __syncthreads();
+        __syncthreads();                       // every lane is done with the previous halo
         build_halo_table(P, g, A.nac, A.ia1th, H);
         const int htot = H.slot[g.nhc];
         if (htot > P.hcap) {
             if (threadIdx.x == 0) atomicAdd(&A.counters[CNT_TILE_OVERFLOW], 1);
             continue;
         }
-        // ---- stage the halo: fp64 record with the periodic image resolved against the nominal
-        //      position of its halo cell, and the packed fixed-point copy for phase A
-        const double ox = P.lo[0] + ((double)(g.cx0 - 1) - 0.5) * P.cell[0];
-        const double oy = P.lo[1] + ((double)(g.cy - 1) - 0.5) * P.cell[1];
-        const double oz = P.lo[2] + ((double)(g.cz - 1) - 0.5) * P.cell[2];
-        for (int hc = warp; hc < g.nhc; hc += nwarps) {
+        // ---- stage the halo: one TMA bulk copy per halo cell (contiguous run of 32-byte records)
+        if (threadIdx.x == 0) mbar_expect_tx(mbar, (unsigned)htot * 32u);
+        const bool edge_any = H.edge_any != 0;
+        for (int hc = threadIdx.x; hc < g.nhc; hc += T) {
             const int cnt = H.cnt[hc];
-            if (cnt == 0) continue;
-            const int gst = H.gst[hc], sl = H.slot[hc];
-            const int hx = hc % g.nhx, hyz = hc / g.nhx, hy = hyz % 3, hz = hyz / 3;
-            const double cx = P.lo[0] + ((double)(g.cx0 - 1 + hx) + 0.5) * P.cell[0];
-            const double cy = P.lo[1] + ((double)(g.cy - 1 + hy) + 0.5) * P.cell[1];
-            const double cz = P.lo[2] + ((double)(g.cz - 1 + hz) + 0.5) * P.cell[2];
-            for (int a = lane; a < cnt; a += 32) {
-                double4 p = A.pos[gst + a];
-                if (P.pd[0]) p.x -= P.size[0] * rint((p.x - cx) / P.size[0]);
-                if (P.pd[1]) p.y -= P.size[1] * rint((p.y - cy) / P.size[1]);
-                if (P.pd[2]) p.z -= P.size[2] * rint((p.z - cz) / P.size[2]);
-                const double fx = (p.x - ox) * P.inv_lsb, fy = (p.y - oy) * P.inv_lsb, fz = (p.z - oz) * P.inv_lsb;
-                unsigned pk = 0xFFFFFFFFu; // "always a candidate"
-                if (fx >= 0.0 && fx < 4095.0 && fy >= 0.0 && fy < 1023.0 && fz >= 0.0 && fz < 1022.0) {
-                    const unsigned qx = (unsigned)(fx + 0.5), qy = (unsigned)(fy + 0.5), qz = (unsigned)(fz + 0.5);
-                    pk = (qx << 20) | (qy << 10) | qz;
+            if (cnt > 0) {
+                fence_proxy_async();
+                bulk_g2s(s_pos + H.slot[hc], A.pos + H.gst[hc], (unsigned)cnt * 32u, mbar);
+            }
+        }
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+        if (edge_any) {
+            for (int hc = warp; hc < g.nhc; hc += nwarps) {
+                if (H.sh[hc][3] == 0) continue;
+                const int cnt = H.cnt[hc], sl = H.slot[hc];
+                const int hx = hc % g.nhx, hyz = hc / g.nhx, hy = hyz % 3, hz = hyz / 3;
+                const double cx = P.lo[0] + ((double)(g.cx0 - 1 + hx) + 0.5) * P.cell[0];
+                const double cy = P.lo[1] + ((double)(g.cy - 1 + hy) + 0.5) * P.cell[1];
+                const double cz = P.lo[2] + ((double)(g.cz - 1 + hz) + 0.5) * P.cell[2];
+                for (int a = lane; a < cnt; a += 32) {
+                    double4 p = s_pos[sl + a];
+                    if (P.pd[0]) { const double d = p.x - cx; if (d > 0.5 * P.size[0]) p.x -= P.size[0]; else if (d < -0.5 * P.size[0]) p.x += P.size[0]; }
+                    if (P.pd[1]) { const double d = p.y - cy; if (d > 0.5 * P.size[1]) p.y -= P.size[1]; else if (d < -0.5 * P.size[1]) p.y += P.size[1]; }
+                    if (P.pd[2]) { const double d = p.z - cz; if (d > 0.5 * P.size[2]) p.z -= P.size[2]; else if (d < -0.5 * P.size[2]) p.z += P.size[2]; }
+                    s_pos[sl + a] = p;
                 }
-                s_pos[sl + a] = p;
-                s_pk[sl + a] = pk;
-                if (MT) s_typ[sl + a] = (unsigned char)(A.ityp[gst + a] - 1);
+            }
+            __syncthreads();
+        }
+        // (edge cells: wrapped cells and cells on a periodic face, whose atoms may have been wrapped by the
+        //  predictor since the rebuild, were brought into the tile frame above)
+        // packed filter coordinates (and types) for every staged atom
+        for (int s = threadIdx.x; s < htot; s += T) {
+            const double4 p = s_pos[s];
+            s_pk[s] = pack_q(p.x, p.y, p.z, P.inv_lsb);
+        }
+        if (MT) {
+            for (int hc = warp; hc < g.nhc; hc += nwarps) {
+                const int cnt = H.cnt[hc], sl = H.slot[hc], gst = H.gst[hc];
+                for (int a = lane; a < cnt; a += 32) s_typ[sl + a] = (unsigned char)(A.ityp[gst + a] - 1);
             }
         }
         __syncthreads();
@@ -271,8 +341,8 @@ k_tile_pass(TileParams P, TilePassArgs A)
         const int own_slot0 = H.slot[hc_own0];
         const int own_count = H.slot[hc_own0 + g.wt] - own_slot0;
 
-        for (int base = 0; base < own_count; base += apr) {
-            const int o = base + (int)threadIdx.x / G;
+        for (int base = 0; base < own_count; base += ngrp) {
+            const int o = base + grp;
             const bool have = o < own_count;
             const int ia = own_start + (have ? o : 0);
             const int myslot = own_slot0 + (have ? o : 0);
@@ -281,95 +351,107 @@ k_tile_pass(TileParams P, TilePassArgs A)
             const bool active = have && ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE);
             const int kv = active ? A.kvois[ia] : 0;
             const int ti = MT ? (int)s_typ[myslot] : 0;
-            const int qix = (int)(mypk >> 20), qiy = (int)((mypk >> 10) & 1023u), qiz = (int)(mypk & 1023u);
-            const bool me_far = (mypk == 0xFFFFFFFFu);
 
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-            const int nm = (kv - gl + G - 1) / G; // my entries are k = gl + G*m, m < nm (0 if kv <= gl)
-            int m = 0;
-            unsigned short *myq = s_q + threadIdx.x;
+            const int nm = (kv - gl + G - 1) / G;      // my entries are k = gl + G*m, m < nm
+            const int n4 = (nm + 3) >> 2;              // my 4-entry index groups
+            int it = 0;
+            const uint2 *ip = reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl);
+            const size_t ipstride = P.npad * G;
+            unsigned short *gq = s_q + grp;            // this atom's queue: entry e at gq[e * ngrp]
 
             while (true) {
-                int cnt = 0;
-                // ---------------- phase A: fill the private queue
-                while (__any_sync(0xffffffffu, m < nm && cnt <= QCAP - NBL_UNROLL)) {
-                    if (m < nm && cnt <= QCAP - NBL_UNROLL) {
-                        // 4 consecutive entries m..m+3 of this lane: one 8-byte load
-                        const size_t idx = ((((size_t)(m >> 2) * P.npad + (size_t)ia) * G + gl) << 2);
-                        const uint2 raw = __ldcs(reinterpret_cast<const uint2 *>(A.nbl + idx));
-                        unsigned short sl4[4] = {(unsigned short)(raw.x & 0xffffu), (unsigned short)(raw.x >> 16),
-                                                 (unsigned short)(raw.y & 0xffffu), (unsigned short)(raw.y >> 16)};
-                        unsigned pk4[4];
+                int gcnt = 0;                           // entries in the atom's queue (same on its G lanes)
+                // ---------------- phase A: stream the slot list, filter, push survivors
+                while (__any_sync(0xffffffffu, it < n4 && gcnt <= A.qcap - 4 * G)) {
+                    const bool go = it < n4 && gcnt <= A.qcap - 4 * G;
+                    uint2 raw = make_uint2(0u, 0u);
+                    if (go) raw = __ldcs(ip);
+                    const int left = go ? nm - 4 * it : 0; // valid entries in this group of 4
+                    const unsigned s0 = raw.x & 0xffffu, s1 = raw.x >> 16, s2 = raw.y & 0xffffu, s3 = raw.y >> 16;
+                    const unsigned p0 = s_pk[left > 0 ? s0 : 0], p1 = s_pk[left > 1 ? s1 : 0],
+                                   p2 = s_pk[left > 2 ? s2 : 0], p3 = s_pk[left > 3 ? s3 : 0];
+                    const int d0 = (int)__vsub4(mypk, p0), d1 = (int)__vsub4(mypk, p1), d2 = (int)__vsub4(mypk, p2),
+                              d3 = (int)__vsub4(mypk, p3);
+                    const bool k0 = left > 0 && __dp4a(d0, d0, 0) <= A.r2int;
+                    const bool k1 = left > 1 && __dp4a(d1, d1, 0) <= A.r2int;
+                    const bool k2 = left > 2 && __dp4a(d2, d2, 0) <= A.r2int;
+                    const bool k3 = left > 3 && __dp4a(d3, d3, 0) <= A.r2int;
+                    const int c = (int)k0 + (int)k1 + (int)k2 + (int)k3;
+                    // exclusive prefix of c over the G lanes of the atom
+                    int incl = c;
 #pragma unroll
-                        for (int u = 0; u < 4; u++) pk4[u] = (m + u < nm) ? s_pk[sl4[u]] : 0u;
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int dx = qix - (int)(pk4[u] >> 20), dy = qiy - (int)((pk4[u] >> 10) & 1023u),
-                                      dz = qiz - (int)(pk4[u] & 1023u);
-                            const int d2 = dx * dx + dy * dy + dz * dz;
-                            const bool pass = (m + u < nm) && (d2 <= A.r2int || me_far || pk4[u] == 0xFFFFFFFFu);
-                            if (pass) { myq[cnt * T] = sl4[u]; cnt++; }
-                        }
-                        m += 4;
+                    for (int w = 1; w < G; w <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, w, G);
+                        if (gl >= w) incl += t;
                     }
+                    const int total = __shfl_sync(0xffffffffu, incl, G - 1, G);
+                    unsigned short *w = gq + (size_t)(gcnt + incl - c) * ngrp;
+                    if (k0) { *w = (unsigned short)s0; w += ngrp; }
+                    if (k1) { *w = (unsigned short)s1; w += ngrp; }
+                    if (k2) { *w = (unsigned short)s2; w += ngrp; }
+                    if (k3) { *w = (unsigned short)s3; }
+                    gcnt += total;
+                    if (go) { it++; ip += ipstride; }
                 }
-                const int mx = __reduce_max_sync(0xffffffffu, cnt);
+                const int mx = __reduce_max_sync(0xffffffffu, gcnt);
                 if (mx == 0) break;
-                // ---------------- phase B: drain in lock-step
-                for (int q = 0; q < mx; q++) {
-                    const bool on = q < cnt;
-                    const int s = on ? (int)myq[q * T] : myslot;
+                __syncwarp();
+                // ---------------- phase B: drain in lock-step, lane gl takes entries gl, gl+G, ...
+                const unsigned short *rq = gq + (size_t)gl * ngrp;
+                for (int e = gl; e - gl < mx; e += G, rq += (size_t)G * ngrp) {
+                    const bool on = e < gcnt;
+                    const int s = on ? (int)*rq : myslot;
                     const double4 pj = s_pos[s];
                     const double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
                     const double r2 = fma(sz, sz, fma(sy, sy, sx * sx));
-                    const bool in = on && (r2 <= A.r2eff); // r2eff <= RU2; rows beyond the table support are exactly 0
-                    const double y = rsqrt_fast(in ? r2 : 1.0);
+                    const bool in = on && (r2 <= A.r2eff); // rows beyond the table support interpolate to exactly 0
+                    const double y = rsqrt_fast(r2);              // 1/r
                     const double r = r2 * y;
-                    const double z = rsqrt_fast(in ? r : 1.0);
-                    const double sk = (r * z) * A.csi;            // sqrt(r)*CSI
+                    const double z = rsqrt_fast(r);               // 1/sqrt(r)
+                    const double sk = (r * z) * A.csi;            // SK = sqrt(r)*CSI
                     const double tk = __dadd_rd(sk, 4503599627370496.0);
                     const int kk = __double2loint(tk);            // KK = int(SK)
                     const double dk = sk - (tk - 4503599627370496.0);
-                    const int rr = kk - A.kmin;
+                    const unsigned rr = (unsigned)(kk - A.kmin);
                     int k0 = A.kind0, k1 = A.kind0;
-                    bool smem_ok = (rr >= 0 && rr < A.ktab);
+                    bool fast = in && rr < (unsigned)A.ktab;
                     if (MT) {
                         const int tj = (int)s_typ[s];
                         k0 = A.kpair[ti + P.ng * tj];
                         k1 = A.kpair[tj + P.ng * ti];
-                        smem_ok = smem_ok && k0 == A.kind0 && k1 == A.kind0;
+                        fast = fast && k0 == A.kind0 && k1 == A.kind0;
                     }
+                    const unsigned rs = fast ? rr : 0u;
                     if (PASS == 1) {
-                        double val;
-                        if (smem_ok) {
-                            const double2 e = s_tab[rr];
-                            val = fma(dk, e.y - e.x, e.x);
-                        } else {
-                            val = in ? lerp_g(A.g_potb, A.ntab + 2, k0, kk, dk) : 0.0;
+                        const double2 t0 = s_tab[rs];
+                        double val = fma(dk, t0.y - t0.x, t0.x);
+                        if (__any_sync(0xffffffffu, in && !fast)) { // outside the staged window / other kinds: rare
+                            if (in && !fast) val = lerp_g(A.g_potb, A.ntab + 2, k0, kk, dk);
                         }
-                        acc0 += in ? val : 0.0;
+                        if (in) acc0 += val;
                     } else {
-                        double fr, fb0, fb1;
-                        if (smem_ok) {
-                            const double2 e0 = s_tab[rr], e1 = s_tab[rr + 1];
-                            fr = fma(dk, e1.x - e0.x, e0.x);
-                            fb0 = fma(dk, e1.y - e0.y, e0.y);
-                            fb1 = fb0;
-                        } else if (in) {
-                            fr = lerp_g(A.g_fpotr, A.ntab + 2, k0, kk, dk);
-                            fb0 = lerp_g(A.g_fpotb, A.ntab + 2, k0, kk, dk);
-                            fb1 = MT ? lerp_g(A.g_fpotb, A.ntab + 2, k1, kk, dk) : fb0;
-                        } else {
-                            fr = fb0 = fb1 = 0.0;
+                        const double2 t0 = s_tab[rs], t1 = s_tab[rs + 1];
+                        double fr = fma(dk, t1.x - t0.x, t0.x);
+                        double fb0 = fma(dk, t1.y - t0.y, t0.y);
+                        double fb1 = fb0;
+                        if (__any_sync(0xffffffffu, in && !fast)) {
+                            if (in && !fast) {
+                                fr = lerp_g(A.g_fpotr, A.ntab + 2, k0, kk, dk);
+                                fb0 = lerp_g(A.g_fpotb, A.ntab + 2, k0, kk, dk);
+                                fb1 = MT ? lerp_g(A.g_fpotb, A.ntab + 2, k1, kk, dk) : fb0;
+                            }
                         }
                         // FORTOT = FPOTR/R2 + (FPOTB_ij*DEN_i + FPOTB_ji*DEN_j)/R     (:811-813)
-                        double ft = y * fma(fr, y, fma(fb0, me.w, fb1 * pj.w));
-                        ft = in ? ft : 0.0;
-                        acc0 = fma(ft, sx, acc0);
-                        acc1 = fma(ft, sy, acc1);
-                        acc2 = fma(ft, sz, acc2);
+                        const double ft = y * fma(fr, y, fma(fb0, me.w, fb1 * pj.w));
+                        if (in) {
+                            acc0 = fma(ft, sx, acc0);
+                            acc1 = fma(ft, sy, acc1);
+                            acc2 = fma(ft, sz, acc2);
+                        }
                     }
                 }
+                __syncwarp();
             }
             // ---------------- reduce the G partial sums of the atom and write
 #pragma unroll
@@ -416,14 +498,16 @@ k_tile_pass(TileParams P, TilePassArgs A)
 // =====================================================================================
 static const int SMEM_BUDGET = 227 * 1024;
 
-static size_t pass_smem_bytes(int hcap, int ktab, int threads, bool mt)
+static size_t pass_smem_bytes(int hcap, int ktab, int threads, int G, int qcap, bool mt)
 {
     size_t b = (sizeof(HaloTab) + 15) & ~(size_t)15;
+    b += 16;
     b += sizeof(double2) * (size_t)(ktab + 1);
+    b = (b + 127) & ~(size_t)127;
     b += (sizeof(double4) + sizeof(unsigned)) * (size_t)hcap;
-    b += sizeof(unsigned short) * QCAP * (size_t)threads;
+    b += sizeof(unsigned short) * (size_t)qcap * (threads / G);
     if (mt) b += hcap;
-    return b + 32;
+    return b + 128;
 }
 
 // largest Fortran row index with a non-zero entry in the kind-major host copy kept by the context
@@ -466,10 +550,18 @@ int mdb_tiled_plan(mdb_ctx *c)
         const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.25) + 64;
         if (hcap > 65000) continue;
         const int threads = std::min(1024, ((own * G + 31) / 32) * 32);
+        // queue depth per atom: expected candidates inside the filter radius (+30 %) plus one full push round
+        const double dens = (double)c->n / ((double)c->nbox * c->box.size[0] * c->box.size[1] * c->box.size[2]);
+        for (int p = 0; p < 2; p++) {
+            const double rf = std::sqrt(S.r2eff[p]);
+            const int expect = (int)(4.18879 * rf * rf * rf * dens * 1.3) + 4 * G;
+            S.qcap[p] = std::max(8 * G, ((expect + 4 * G + 7) / 8) * 8);
+        }
+        const int qmax = std::max(S.qcap[0], S.qcap[1]);
         // table window: as many rows below khi as fit
-        const size_t fixed = pass_smem_bytes(hcap, 0, threads, mt);
-        if (fixed + 16 * 512 > (size_t)SMEM_BUDGET) continue;
-        const int maxrows = (int)((SMEM_BUDGET - fixed) / 16) - 2;
+        const size_t fixed = pass_smem_bytes(hcap, 0, threads, G, qmax, mt);
+        if (fixed + 16 * 512 + 1024 > (size_t)SMEM_BUDGET) continue;
+        const int maxrows = (int)((SMEM_BUDGET - fixed - 1024) / 16) - 2;
         const int need = std::max(S.khi[0], S.khi[1]) + 1;
         // require the window to reach down to r = 0.6 * (nearest plausible approach) ... or everything
         const int want = std::min(need, maxrows);
@@ -495,15 +587,18 @@ int mdb_tiled_plan(mdb_ctx *c)
         P.fbs[d] = (float)c->box.size[d];
         cellmax = std::max(cellmax, P.cell[d]);
     }
-    const double lsb = cellmax / 256.0;
+    (void)cellmax;
+    // phase-A quantum: RU spans 120 LSB, so every in-range coordinate difference fits a signed byte
+    const double lsb = std::sqrt(t.ru2max) / 120.0;
     P.inv_lsb = 1.0 / lsb;
     P.ng = c->ng; P.mxkvois = c->mxkvois;
     const int rows_per_lane = (c->mxkvois + G - 1) / G;
     P.nrow4 = (rows_per_lane + 3) / 4;
     P.npad = (size_t)c->n;
     for (int p = 0; p < 2; p++) {
-        // |quantised distance - true distance| <= sqrt(3) LSB (each coordinate difference is off by <= 1 LSB)
-        const double rl = std::sqrt(S.r2eff[p]) / lsb + 1.7321 + 0.01;
+        // floor() quantisation: each coordinate difference is off by < 1 LSB, the distance by < sqrt(3) LSB;
+        // 3 LSB leaves room for the rounding of x*inv_lsb itself
+        const double rl = std::sqrt(S.r2eff[p]) / lsb + 3.0;
         S.r2int[p] = (int)(rl * rl) + 1;
     }
     // ---- slot list storage
@@ -520,7 +615,7 @@ int mdb_tiled_plan(mdb_ctx *c)
     S.grid = std::min(P.ntiles, nsm);
     S.smem_list = ((sizeof(HaloTab) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap + 32;
     S.grid_list = std::min(P.ntiles, nsm * std::max(1, std::min(8, (int)(SMEM_BUDGET / S.smem_list))));
-    for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads, mt);
+    for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads, G, S.qcap[p], mt);
     S.ok = true;
     return MDB_OK;
 }
@@ -563,6 +658,7 @@ static int launch_pass(mdb_ctx *c)
     A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod; A.ru2max = t.ru2max;
     A.r2eff = S.r2eff[PASS - 1]; A.r2int = S.r2int[PASS - 1]; A.kmin = S.kmin[PASS - 1]; A.ktab = S.ktab[PASS - 1];
     A.kind0 = t.kpair[0];
+    A.qcap = S.qcap[PASS - 1];
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
     auto kern = k_tile_pass<PASS, G, MT>;

@@ -69,7 +69,7 @@ struct TiledState {
     bool ok = false, dirty = true, active = false;
     int G = 4;                 // lanes per atom
     int ntx = 0, hcap = 0, threads = 0, grid = 0, grid_list = 0;
-    int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0}, r2int[2] = {0, 0};
+    int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0}, r2int[2] = {0, 0}, qcap[2] = {0, 0};
     double r2eff[2] = {0.0, 0.0};
     size_t smem_list = 0, smem_pass[2] = {0, 0};
     unsigned short *nbl = nullptr; size_t nbl_elems = 0;
