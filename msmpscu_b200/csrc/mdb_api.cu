@@ -122,13 +122,13 @@ static void free_state(mdb_ctx *c)
     dfree(c->statu); dfree(c->statu_alt); dfree(c->gid); dfree(c->gid_alt); dfree(c->gidinv);
     dfree(c->ic); dfree(c->ic_alt); dfree(c->xp_view); dfree(c->den_view);
     dfree(c->slot); dfree(c->srcof); dfree(c->tmp_orig); dfree(c->oob); dfree(c->vpart);
+    dfree(c->dsr); c->dsr_bytes = 0;
     if (c->stage) { cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
     c->has_box = false;
 }
 static void free_nlist(mdb_ctx *c)
 {
-    if (c->tiled.nbl) { cudaFree(c->tiled.nbl); c->tiled.nbl = nullptr; c->tiled.nbl_elems = 0; }
-    c->tiled.ok = false; c->tiled.dirty = true; c->tiled.active = false;
+    mdb_tiled_free(c);
     dfree(c->nac); dfree(c->naac); dfree(c->ia1th); dfree(c->kvois); dfree(c->indi);
     c->has_nlist = false; c->list_valid = false;
 }
@@ -157,6 +157,14 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
 extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
 {
     if (!c) return MDB_ERR_ARG;
+    if (option == MDB_OPT_TILED_LANES && (value == 2 || value == 4 || value == 8)) {
+        c->tiled.G = value; c->tiled.dirty = true; c->list_valid = false;
+        return MDB_OK;
+    }
+    if (option == MDB_OPT_TILED_CLASSES && (value == 0 || value == 1)) {
+        c->tiled.use_classes = value != 0;
+        return MDB_OK;
+    }
     if (option == MDB_OPT_FORCE_PATH && value >= MDB_FORCE_PATH_AUTO && value <= MDB_FORCE_PATH_TILED) {
         c->opt_force_path = value;
         c->list_valid = false; // the two paths keep different list formats
@@ -169,6 +177,9 @@ extern "C" int mdb_get_option(const mdb_ctx *c, int option)
 {
     if (!c) return MDB_ERR_ARG;
     if (option == MDB_OPT_FORCE_PATH) return c->opt_force_path;
+    if (option == MDB_OPT_TILED_LANES) return c->tiled.G;
+    if (option == MDB_OPT_TILED_CLASSES) return c->tiled.use_classes ? 1 : 0;
+    if (option == MDB_OPT_ACTIVE_PATH) return c->tiled.active ? MDB_FORCE_PATH_TILED : MDB_FORCE_PATH_GENERIC;
     return MDB_ERR_ARG;
 }
 
@@ -192,6 +203,15 @@ extern "C" int mdb_sync(mdb_ctx *c)
 // ------------------------------------------------------------------------------------
 // box
 // ------------------------------------------------------------------------------------
+__global__ void k_set_int(int *p, int v) { *p = v; }
+
+// positions were changed by the host (upload): the displacement-since-rebuild bound is unknown,
+// so the tiled passes must scan whole lists until the next rebuild
+void mdb_mark_positions_dirty(mdb_ctx *c)
+{
+    if (c->counters) k_set_int<<<1, 1, 0, c->stream>>>(c->counters + CNT_D2MAX, 0x7f800000);
+}
+
 __global__ void k_iota(int n, int *a, int *b)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,7 +395,8 @@ extern "C" int mdb_state_upload(mdb_ctx *c, int field, const void *host, int ord
     else if (fi.is_int) k_up_i<<<nb, 256, 0, c->stream>>>(n, (const int *)c->stage, dptr_i(c, field), map);
     else k_up_d<<<nb, 256, 0, c->stream>>>(n, fi.ncol, (const double *)c->stage, dptr_d(c, field), map);
     CUDA_TRY(c, cudaGetLastError());
-    if (field == MDB_F_XP || field == MDB_F_ITYP || field == MDB_F_STATU) c->list_valid = c->list_valid && (field != MDB_F_ITYP);
+    if (field == MDB_F_XP) mdb_mark_positions_dirty(c);
+    if (field == MDB_F_ITYP) c->list_valid = false;
     return MDB_OK;
 }
 

@@ -170,6 +170,7 @@ int mdb_cells_build(mdb_ctx *c)
     CUDA_TRY(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * CNT_PERBUILD_N, st)); // CNT_OOB_TOTAL accumulates
     CUDA_TRY(c, cudaMemsetAsync(c->nac, 0, sizeof(int) * (size_t)c->nc, st));  // hm_NAC = 0 :1431
     CUDA_TRY(c, cudaMemsetAsync(c->naac, 0, sizeof(int) * (size_t)c->nc, st));
+    if (c->dsr) CUDA_TRY(c, cudaMemsetAsync(c->dsr, 0, 3 * (size_t)n * sizeof(float), st)); // displacement since THIS rebuild
     k_cell_assign<<<nb, 256, 0, st>>>(n, c->napb, c->pos, c->gid, c->statu, c->box, c->ncell[0], c->ncell[1],
                                       c->ncell[2], c->nc0, c->ic, c->nac, c->naac, c->slot, c->oob, c->counters);
     k_cell_scan<<<1, 1024, 0, st>>>(c->nc, c->nac, c->ia1th, c->counters);

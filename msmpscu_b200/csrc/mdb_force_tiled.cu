@@ -5,43 +5,50 @@
 // path) every (atom, neighbour) visit is a 32-byte random gather that costs a full L1 wavefront
 // per lane and an un-fused sqrt/sqrt/div/div chain on the fp64 pipe; on B200 that runs at ~5 % of
 // the HBM roofline (profiles/r01_generic_path_summary.md).  Here, per tile:
-//   stage   the <=27 contiguous halo runs are copied once into shared memory as fp64 {x,y,z,den}
-//           records with the periodic image already resolved, plus a 32-bit fixed-point copy
-//           (12/10/10 bits, tile-relative) used only for filtering;
-//   phase A each lane streams its share of the 16-bit slot list (8-byte coalesced loads), tests the
-//           packed copy with integer arithmetic (conservative: quantisation error is added to the
-//           radius, out-of-range atoms always pass) and pushes survivors into a private queue;
+//   stage   the <=27 contiguous halo runs are brought into shared memory by TMA bulk copies
+//           (cp.async.bulk + mbarrier) as fp64 {x,y,z,den} records; cells on a periodic face are
+//           moved into the tile frame; a byte-modular packed copy (8 bits per axis) is derived for
+//           filtering;
+//   phase A each lane streams its share of the 16-bit slot list (8-byte coalesced loads, next load
+//           in flight), filters with one SIMD byte subtract + one dp4a per entry (conservative:
+//           it can pass a far pair, never drop an in-range one) and pushes survivors into the
+//           atom's queue (shared by the G lanes of the atom);
 //   phase B the queue is drained in lock-step: fp64 separation from the staged records, the exact
-//           r2 <= RU2 test of the reference, one rsqrt-based evaluation of r, 1/r, sqrt(r), table
-//           rows from shared memory, accumulation.  G lanes share an atom and are reduced with
-//           shuffles; no atomics anywhere, summation order per lane is the reference list order.
-// Pairs beyond the last non-zero table row contribute exactly 0 in the reference arithmetic, so
-// the filter radius is min(RU, table support): fewer phase-B visits, bit-identical sums.
+//           r2 test, one rsqrt-based evaluation of r, 1/r, sqrt(r), table rows from shared memory.
+// The CTA is split into two halves that each own a tile: while one half waits for its TMA copies
+// or sits at a tile barrier the other computes (two tiles in flight per SM, one shared table copy).
+//
+// Exact work reductions (results identical to evaluating every listed pair):
+//   * rows beyond the last non-zero table row interpolate to exactly 0, so the in-range test uses
+//     min(RU, table support);
+//   * the slot list is stored in three classes by BUILD-time distance (<= r_eff(pass1)+m,
+//     <= r_eff(pass2)+m, rest).  A pass scans only its classes while every atom has moved less
+//     than m/2 since the rebuild (tracked by the predictor); otherwise it scans the whole list.
 // The list itself (members, order, truncation) is the reference's: the build kernel evaluates the
 // same fp32 expression as Cal_NeighboreList_Kernel2C (CommonGPU/MD_NeighborsList_GPU.F90:1097-1131)
-// and emits both the slot list and the reference-format KVOIS/INDI.
+// and emits the reference-format KVOIS/INDI next to the slot list.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include "mdb_tiled.cuh"
 
-
 __constant__ int t_nix[27] = {0, -1, -1, -1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1, 1, 1, 1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1};
 __constant__ int t_niy[27] = {0, 0, -1, 1, 1, 0, 0, 0, -1, -1, -1, 1, 1, 1, 0, 1, -1, -1, 0, 0, 0, -1, -1, -1, 1, 1, 1};
 __constant__ int t_niz[27] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 
-struct HaloTab { // per-tile halo cell table in shared memory
-    int slot[TILE_MAX_HC + 1]; // first slot of each halo cell (exclusive prefix), [nhc] = total
+// per-tile halo description: computed once per rebuild by the list kernel, read by the force passes
+struct TileDesc {
+    int htot, own_start, own_slot0, own_count, edge_any, nhc, pad0, pad1;
+    int slot[TILE_MAX_HC + 2]; // first slot of each halo cell (exclusive prefix), [nhc] = total
     int cnt[TILE_MAX_HC];
     int gst[TILE_MAX_HC];      // first global (cell-order, 0-based) atom of the cell
     int cid[TILE_MAX_HC];      // wrapped global cell id, -1 if absent
     signed char sh[TILE_MAX_HC][4]; // image shift per dim, [3] = edge flag
-    int edge_any;
 };
 
-// fills the halo table; must be called by all threads of the CTA (contains __syncthreads)
+// fills the halo table in shared memory; must be called by all threads of the CTA
 __device__ __forceinline__ void build_halo_table(const TileParams &P, const TileGeom &g, const int *__restrict__ nac,
-                                                 const int *__restrict__ ia1th, HaloTab &H)
+                                                 const int *__restrict__ ia1th, TileDesc &H)
 {
     for (int hc = threadIdx.x; hc < g.nhc; hc += blockDim.x) {
         int sh[3], u[3];
@@ -74,7 +81,17 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
         edge = __any_sync(0xffffffffu, edge);
-        if (threadIdx.x == 0) { H.slot[g.nhc] = run; H.edge_any = edge ? 1 : 0; }
+        if (threadIdx.x == 0) {
+            H.slot[g.nhc] = run;
+            H.htot = run; H.edge_any = edge ? 1 : 0; H.nhc = g.nhc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int hc_own0 = (1 * 3 + 1) * g.nhx + 1; // centre row (hy = hz = 1), cells hx = 1..wt
+        H.own_start = H.gst[hc_own0];
+        H.own_slot0 = H.slot[hc_own0];
+        H.own_count = H.slot[hc_own0 + g.wt] - H.slot[hc_own0];
     }
     __syncthreads();
 }
@@ -84,25 +101,30 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
 // =====================================================================================
 struct TileListArgs {
     const double4 *pos; const int *ityp; const int *nac; const int *naac; const int *ia1th;
-    int *kvois; int *indi; unsigned short *nbl; int *counters;
+    int *kvois; int *indi; unsigned short *raw; int *counters; TileDesc *desc;
     float rm2[MDB_MXGROUP * MDB_MXGROUP];
+    float rc2[2]; // class radii^2 (build-time, fp32): class 0 <= rc2[0] < class 1 <= rc2[1] < class 2
 };
 
-template <int G>
 __global__ void __launch_bounds__(256)
 k_tile_nlist(TileParams P, TileListArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    HaloTab &H = *reinterpret_cast<HaloTab *>(smem);
-    float4 *spos = reinterpret_cast<float4 *>(smem + ((sizeof(HaloTab) + 15) & ~15));
+    TileDesc &H = *reinterpret_cast<TileDesc *>(smem);
+    float4 *spos = reinterpret_cast<float4 *>(smem + ((sizeof(TileDesc) + 15) & ~15));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const TileGeom g = tile_geom(P, tile);
         __syncthreads(); // previous tile fully consumed
         build_halo_table(P, g, A.nac, A.ia1th, H);
-        const int htot = H.slot[g.nhc];
-        if (htot > P.hcap) { // cannot happen for the build kernel's own capacity unless density is extreme
+        { // publish the descriptor for the force passes
+            const int *src = reinterpret_cast<const int *>(&H);
+            int *dst = reinterpret_cast<int *>(A.desc + tile);
+            for (int i = threadIdx.x; i < (int)(sizeof(TileDesc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        }
+        const int htot = H.htot;
+        if (htot > P.hcap) { // halo does not fit the shared-memory budget: the host falls back to the generic path
             if (threadIdx.x == 0) atomicAdd(&A.counters[CNT_TILE_OVERFLOW], 1);
             continue;
         }
@@ -121,18 +143,15 @@ k_tile_nlist(TileParams P, TileListArgs A)
             }
         }
         __syncthreads();
-        // owned atoms: centre row (hy = hz = 1), cells hx = 1..wt, contiguous in global order
         const int hc_own0 = (1 * 3 + 1) * g.nhx + 1;
-        const int own_start = H.gst[hc_own0];
-        const int own_count = H.slot[hc_own0 + g.wt] - H.slot[hc_own0];
+        const int own_start = H.own_start, own_count = H.own_count, own_slot0 = H.own_slot0;
         for (int o = threadIdx.x; o < own_count; o += blockDim.x) {
             const int ia = own_start + o;
-            // which cell of the tile is this atom in
-            int hxc = 1;
-            while (hxc < g.wt && o >= H.slot[hc_own0 + hxc] - H.slot[hc_own0]) hxc++;
+            int hxc = 1; // which cell of the tile is this atom in
+            while (hxc < g.wt && o >= H.slot[hc_own0 + hxc] - own_slot0) hxc++;
             const int myhc = hc_own0 + hxc - 1;
             if (A.naac[H.cid[myhc]] <= 0) continue; // cells without ACTIVE atoms are skipped (:981-982)
-            const float4 me = spos[H.slot[hc_own0] + o]; // own cell is never shifted: (float)XP_i
+            const float4 me = spos[own_slot0 + o];   // own cell is never shifted: (float)XP_i
             const int ity = __float_as_int(me.w);
             int nn = 0;
             for (int k = 0; k < 27; k++) {
@@ -149,7 +168,8 @@ k_tile_nlist(TileParams P, TileListArgs A)
                         nn++;
                         if (nn <= P.mxkvois) {
                             A.indi[ia + (size_t)(nn - 1) * P.n] = j + 1;
-                            A.nbl[nbl_index<G>(P, (size_t)ia, nn - 1)] = (unsigned short)(sl + t);
+                            const unsigned cls = r2 <= A.rc2[0] ? 0u : (r2 <= A.rc2[1] ? 1u : 2u);
+                            A.raw[ia + (size_t)(nn - 1) * P.n] = (unsigned short)((unsigned)(sl + t) | (cls << 14));
                         }
                     }
                 }
@@ -161,21 +181,53 @@ k_tile_nlist(TileParams P, TileListArgs A)
     }
 }
 
+// stable partition of every atom's slot list into its three distance classes, written in the
+// lane-interleaved layout the passes stream (see nbl_index); tails are padded with slot 0 so that
+// every 4-entry group a lane can touch holds valid slots.
+template <int G>
+__global__ void k_tile_classify(TileParams P, const int *__restrict__ counters, const int *__restrict__ kvois,
+                                const unsigned short *__restrict__ raw, unsigned short *__restrict__ nbl,
+                                unsigned short *__restrict__ ncls)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= counters[CNT_INCELL]) return;
+    const int kv = kvois[a];
+    int n0 = 0, n1 = 0;
+    for (int k = 0; k < kv; k++) {
+        const unsigned c = raw[a + (size_t)k * P.n] >> 14;
+        n0 += (c == 0u);
+        n1 += (c == 1u);
+    }
+    int p0 = 0, p1 = n0, p2 = n0 + n1;
+    for (int k = 0; k < kv; k++) {
+        const unsigned e = raw[a + (size_t)k * P.n];
+        const unsigned c = e >> 14;
+        int d;
+        if (c == 0u) d = p0++; else if (c == 1u) d = p1++; else d = p2++;
+        nbl[nbl_index<G>(P, (size_t)a, d)] = (unsigned short)(e & 0x3fffu);
+    }
+    const int kend = min(((kv + 4 * G - 1) / (4 * G)) * (4 * G), P.nrow4 * 4 * G);
+    for (int k = kv; k < kend; k++) nbl[nbl_index<G>(P, (size_t)a, k)] = 0;
+    ncls[a] = (unsigned short)n0;
+    ncls[a + P.npad] = (unsigned short)(n0 + n1);
+}
+
 // =====================================================================================
 // force passes
 // =====================================================================================
 struct TilePassArgs {
-    double4 *pos; const int *ityp; const int *statu; const int *nac; const int *ia1th; const int *kvois;
-    const unsigned short *nbl; double *fp; int *counters;
+    double4 *pos; const int *ityp; const int *statu; const int *kvois; const unsigned short *ncls;
+    const unsigned short *nbl; double *fp; int *counters; const TileDesc *desc;
     // tables: global packed {T[kk], T[kk+1]-T[kk]} (stride ntab+2 per kind) for the rare fall-backs
     const double2 *g_potb, *g_fpotr, *g_fpotb, *g_dfembd;
     int ntab, nembd, pot_type;
-    double csi, rhod, ru2max;
+    double csi, rhod;
     double r2eff;          // min(RU2, table support) for this pass
     int r2int;             // phase-A radius^2 in LSB units (conservative)
     int kmin, ktab;        // shared-memory table window: rows kmin .. kmin+ktab (row kk and kk+1 are read)
     int kind0;             // the kind held in shared memory = KPAIR(1,1)
-    int qcap;              // queue entries per atom group
+    int qcap;              // queue entries per atom
+    float safe_d2;         // classes are valid while max |displacement since rebuild|^2 <= safe_d2
     int kpair[MDB_MXGROUP * MDB_MXGROUP];
     int kembd[MDB_MXGROUP];
 };
@@ -227,6 +279,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_named(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // byte-modular packed coordinates for phase A: q_d = floor(x_d / LSB) mod 256.  For two atoms in the
 // same (image-resolved) tile frame, a pair with r <= r_eff has |dq_d| <= r_eff/LSB + 1 <= 127 in every
@@ -240,28 +296,40 @@ __device__ __forceinline__ unsigned pack_q(double x, double y, double z, double 
     return qx | (qy << 8) | (qz << 16);
 }
 
+// 1 if the quantised distance^2 of the two packed positions is <= r2int
+__device__ __forceinline__ unsigned filt(unsigned a, unsigned b, int r2int)
+{
+    const int d = (int)__vsub4(a, b);
+    return (unsigned)(__dp4a(d, d, 0) - r2int - 1) >> 31;
+}
+
 // PASS 1: rho -> DEN.  PASS 2: forces.  G lanes per atom.  MT: more than one atom type.
+// The CTA runs as two independent halves (threads [0,T/2) and [T/2,T)), each with its own tile.
 template <int PASS, int G, bool MT>
 __global__ void __launch_bounds__(1024, 1)
 k_tile_pass(TileParams P, TilePassArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    // ---- carve shared memory
-    HaloTab &H = *reinterpret_cast<HaloTab *>(smem);
-    size_t off = (sizeof(HaloTab) + 15) & ~(size_t)15;
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + off);   off += 16;
+    const int T = blockDim.x, TH = T >> 1;
+    const int half = (int)threadIdx.x >= TH ? 1 : 0;
+    const int tid = (int)threadIdx.x - half * TH;  // thread id inside the half
+    const int ngrp = TH / G;                        // atoms per round of a half
+    // ---- carve shared memory: [tables][half 0: mbar, pos, pk, queue, types][half 1: ...]
+    size_t off = 0;
     double2 *s_tab = reinterpret_cast<double2 *>(smem + off);       off += sizeof(double2) * (size_t)(A.ktab + 1);
     off = (off + 127) & ~(size_t)127;
-    double4 *s_pos = reinterpret_cast<double4 *>(smem + off);       off += sizeof(double4) * (size_t)P.hcap;
-    unsigned *s_pk = reinterpret_cast<unsigned *>(smem + off);      off += sizeof(unsigned) * (size_t)P.hcap;
-    const int T = blockDim.x;
-    const int ngrp = T / G;              // atom groups per CTA = atoms per round
-    unsigned short *s_q = reinterpret_cast<unsigned short *>(smem + off); off += sizeof(unsigned short) * (size_t)A.qcap * ngrp;
-    unsigned char *s_typ = smem + off;                              // hcap bytes, only if MT
+    const size_t half_bytes = (((size_t)128 + (sizeof(double4) + sizeof(unsigned)) * (size_t)P.hcap +
+                                sizeof(unsigned short) * (size_t)A.qcap * ngrp + (MT ? (size_t)P.hcap : 0)) + 127) & ~(size_t)127;
+    unsigned char *hb = smem + off + (size_t)half * half_bytes;
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(hb);
+    double4 *s_pos = reinterpret_cast<double4 *>(hb + 128);
+    unsigned *s_pk = reinterpret_cast<unsigned *>(hb + 128 + sizeof(double4) * (size_t)P.hcap);
+    unsigned short *s_q = reinterpret_cast<unsigned short *>(hb + 128 + (sizeof(double4) + sizeof(unsigned)) * (size_t)P.hcap);
+    unsigned char *s_typ = reinterpret_cast<unsigned char *>(s_q + (size_t)A.qcap * ngrp); // hcap bytes, only if MT
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = T >> 5;
-    const int gl = threadIdx.x % G;      // lane within the atom's group
-    const int grp = threadIdx.x / G;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = TH >> 5;
+    const int gl = tid % G;      // lane within the atom's group
+    const int grp = tid / G;
 
     // ---- tables for kind0, rows kmin..kmin+ktab : staged once per (persistent) CTA
     //      pass 1: {POTB[kk], POTB[kk+1]}         (one 16-byte read per pair)
@@ -277,36 +345,38 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 s_tab[r] = make_double2(A.g_fpotr[(size_t)A.kind0 * stride + kk].x, A.g_fpotb[(size_t)A.kind0 * stride + kk].x);
             }
         }
-        if (threadIdx.x == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     }
     __syncthreads();
     unsigned phase = 0;
+    // distance classes are usable while no atom has moved more than half the class margin since the rebuild
+    const bool safe = __int_as_float(A.counters[CNT_D2MAX]) <= A.safe_d2;
 
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        const TileGeom g = tile_geom(P, tile);
-        __syncthreads();                       // every lane is done with the previous halo
-        build_halo_table(P, g, A.nac, A.ia1th, H);
-        const int htot = H.slot[g.nhc];
-        if (htot > P.hcap) {
-            if (threadIdx.x == 0) atomicAdd(&A.counters[CNT_TILE_OVERFLOW], 1);
-            continue;
-        }
+    for (int tile = 2 * blockIdx.x + half; tile < P.ntiles; tile += 2 * gridDim.x) {
+        const TileDesc &D = A.desc[tile];
+        bar_named(1 + half, TH);                     // every lane of the half is done with the previous halo
+        const int htot = D.htot, nhc = D.nhc;
+        if (htot > P.hcap) continue;                 // counted by the list kernel; the host falls back
         // ---- stage the halo: one TMA bulk copy per halo cell (contiguous run of 32-byte records)
-        if (threadIdx.x == 0) mbar_expect_tx(mbar, (unsigned)htot * 32u);
-        const bool edge_any = H.edge_any != 0;
-        for (int hc = threadIdx.x; hc < g.nhc; hc += T) {
-            const int cnt = H.cnt[hc];
+        if (tid == 0) mbar_expect_tx(mbar, (unsigned)htot * 32u);
+        for (int hc = tid; hc < nhc; hc += TH) {
+            const int cnt = D.cnt[hc];
             if (cnt > 0) {
                 fence_proxy_async();
-                bulk_g2s(s_pos + H.slot[hc], A.pos + H.gst[hc], (unsigned)cnt * 32u, mbar);
+                bulk_g2s(s_pos + D.slot[hc], A.pos + D.gst[hc], (unsigned)cnt * 32u, mbar);
             }
         }
+        const bool edge_any = D.edge_any != 0;
+        const int own_start = D.own_start, own_slot0 = D.own_slot0, own_count = D.own_count;
         mbar_wait(mbar, phase);
         phase ^= 1u;
         if (edge_any) {
-            for (int hc = warp; hc < g.nhc; hc += nwarps) {
-                if (H.sh[hc][3] == 0) continue;
-                const int cnt = H.cnt[hc], sl = H.slot[hc];
+            // wrapped cells and cells on a periodic face (atoms the predictor may have wrapped since the
+            // rebuild): bring every atom to the image nearest to the nominal centre of its halo cell
+            const TileGeom g = tile_geom(P, tile);
+            for (int hc = warp; hc < nhc; hc += nwarps) {
+                if (D.sh[hc][3] == 0) continue;
+                const int cnt = D.cnt[hc], sl = D.slot[hc];
                 const int hx = hc % g.nhx, hyz = hc / g.nhx, hy = hyz % 3, hz = hyz / 3;
                 const double cx = P.lo[0] + ((double)(g.cx0 - 1 + hx) + 0.5) * P.cell[0];
                 const double cy = P.lo[1] + ((double)(g.cy - 1 + hy) + 0.5) * P.cell[1];
@@ -319,27 +389,20 @@ k_tile_pass(TileParams P, TilePassArgs A)
                     s_pos[sl + a] = p;
                 }
             }
-            __syncthreads();
+            bar_named(1 + half, TH);
         }
-        // (edge cells: wrapped cells and cells on a periodic face, whose atoms may have been wrapped by the
-        //  predictor since the rebuild, were brought into the tile frame above)
         // packed filter coordinates (and types) for every staged atom
-        for (int s = threadIdx.x; s < htot; s += T) {
+        for (int s = tid; s < htot; s += TH) {
             const double4 p = s_pos[s];
             s_pk[s] = pack_q(p.x, p.y, p.z, P.inv_lsb);
         }
         if (MT) {
-            for (int hc = warp; hc < g.nhc; hc += nwarps) {
-                const int cnt = H.cnt[hc], sl = H.slot[hc], gst = H.gst[hc];
+            for (int hc = warp; hc < nhc; hc += nwarps) {
+                const int cnt = D.cnt[hc], sl = D.slot[hc], gst = D.gst[hc];
                 for (int a = lane; a < cnt; a += 32) s_typ[sl + a] = (unsigned char)(A.ityp[gst + a] - 1);
             }
         }
-        __syncthreads();
-
-        const int hc_own0 = (1 * 3 + 1) * g.nhx + 1;
-        const int own_start = H.gst[hc_own0];
-        const int own_slot0 = H.slot[hc_own0];
-        const int own_count = H.slot[hc_own0 + g.wt] - own_slot0;
+        bar_named(1 + half, TH);
 
         for (int base = 0; base < own_count; base += ngrp) {
             const int o = base + grp;
@@ -349,7 +412,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
             const double4 me = s_pos[myslot];
             const unsigned mypk = s_pk[myslot];
             const bool active = have && ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE);
-            const int kv = active ? A.kvois[ia] : 0;
+            const int kv = active ? (safe ? (int)A.ncls[ia + (PASS - 1) * P.npad] : A.kvois[ia]) : 0;
             const int ti = MT ? (int)s_typ[myslot] : 0;
 
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
@@ -359,27 +422,27 @@ k_tile_pass(TileParams P, TilePassArgs A)
             const uint2 *ip = reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl);
             const size_t ipstride = P.npad * G;
             unsigned short *gq = s_q + grp;            // this atom's queue: entry e at gq[e * ngrp]
+            uint2 nxt = make_uint2(0u, 0u);
+            if (n4 > 0) nxt = __ldcs(ip);              // software pipeline: the next index group is always in flight
 
             while (true) {
                 int gcnt = 0;                           // entries in the atom's queue (same on its G lanes)
                 // ---------------- phase A: stream the slot list, filter, push survivors
                 while (__any_sync(0xffffffffu, it < n4 && gcnt <= A.qcap - 4 * G)) {
                     const bool go = it < n4 && gcnt <= A.qcap - 4 * G;
-                    uint2 raw = make_uint2(0u, 0u);
-                    if (go) raw = __ldcs(ip);
-                    const int left = go ? nm - 4 * it : 0; // valid entries in this group of 4
+                    const uint2 raw = nxt;
+                    const int lim = go ? nm - 4 * it : 0;   // valid entries in this group (>= 4 except in the tail)
+                    if (go) {
+                        it++; ip += ipstride;
+                        if (it < n4) nxt = __ldcs(ip);
+                    }
                     const unsigned s0 = raw.x & 0xffffu, s1 = raw.x >> 16, s2 = raw.y & 0xffffu, s3 = raw.y >> 16;
-                    const unsigned p0 = s_pk[left > 0 ? s0 : 0], p1 = s_pk[left > 1 ? s1 : 0],
-                                   p2 = s_pk[left > 2 ? s2 : 0], p3 = s_pk[left > 3 ? s3 : 0];
-                    const int d0 = (int)__vsub4(mypk, p0), d1 = (int)__vsub4(mypk, p1), d2 = (int)__vsub4(mypk, p2),
-                              d3 = (int)__vsub4(mypk, p3);
-                    const bool k0 = left > 0 && __dp4a(d0, d0, 0) <= A.r2int;
-                    const bool k1 = left > 1 && __dp4a(d1, d1, 0) <= A.r2int;
-                    const bool k2 = left > 2 && __dp4a(d2, d2, 0) <= A.r2int;
-                    const bool k3 = left > 3 && __dp4a(d3, d3, 0) <= A.r2int;
-                    const int c = (int)k0 + (int)k1 + (int)k2 + (int)k3;
-                    // exclusive prefix of c over the G lanes of the atom
-                    int incl = c;
+                    const unsigned p0 = s_pk[s0], p1 = s_pk[s1], p2 = s_pk[s2], p3 = s_pk[s3]; // tails are padded with slot 0
+                    unsigned m4 = filt(mypk, p0, A.r2int) | (filt(mypk, p1, A.r2int) << 1) | (filt(mypk, p2, A.r2int) << 2) |
+                                  (filt(mypk, p3, A.r2int) << 3);
+                    m4 &= (lim >= 4) ? 0xfu : ((1u << max(lim, 0)) - 1u);
+                    const int c = __popc(m4);
+                    int incl = c;                       // exclusive prefix of c over the G lanes of the atom
 #pragma unroll
                     for (int w = 1; w < G; w <<= 1) {
                         const int t = __shfl_up_sync(0xffffffffu, incl, w, G);
@@ -387,12 +450,11 @@ k_tile_pass(TileParams P, TilePassArgs A)
                     }
                     const int total = __shfl_sync(0xffffffffu, incl, G - 1, G);
                     unsigned short *w = gq + (size_t)(gcnt + incl - c) * ngrp;
-                    if (k0) { *w = (unsigned short)s0; w += ngrp; }
-                    if (k1) { *w = (unsigned short)s1; w += ngrp; }
-                    if (k2) { *w = (unsigned short)s2; w += ngrp; }
-                    if (k3) { *w = (unsigned short)s3; }
+                    if (m4 & 1u) { *w = (unsigned short)s0; w += ngrp; }
+                    if (m4 & 2u) { *w = (unsigned short)s1; w += ngrp; }
+                    if (m4 & 4u) { *w = (unsigned short)s2; w += ngrp; }
+                    if (m4 & 8u) { *w = (unsigned short)s3; }
                     gcnt += total;
-                    if (go) { it++; ip += ipstride; }
                 }
                 const int mx = __reduce_max_sync(0xffffffffu, gcnt);
                 if (mx == 0) break;
@@ -498,16 +560,17 @@ k_tile_pass(TileParams P, TilePassArgs A)
 // =====================================================================================
 static const int SMEM_BUDGET = 227 * 1024;
 
-static size_t pass_smem_bytes(int hcap, int ktab, int threads, int G, int qcap, bool mt)
+static size_t half_smem_bytes(int hcap, int threads_half, int G, int qcap, bool mt)
 {
-    size_t b = (sizeof(HaloTab) + 15) & ~(size_t)15;
-    b += 16;
-    b += sizeof(double2) * (size_t)(ktab + 1);
+    size_t b = 128 + (sizeof(double4) + sizeof(unsigned)) * (size_t)hcap + sizeof(unsigned short) * (size_t)qcap * (threads_half / G) +
+               (mt ? (size_t)hcap : 0);
+    return (b + 127) & ~(size_t)127;
+}
+static size_t pass_smem_bytes(int hcap, int ktab, int threads_half, int G, int qcap, bool mt)
+{
+    size_t b = sizeof(double2) * (size_t)(ktab + 1);
     b = (b + 127) & ~(size_t)127;
-    b += (sizeof(double4) + sizeof(unsigned)) * (size_t)hcap;
-    b += sizeof(unsigned short) * (size_t)qcap * (threads / G);
-    if (mt) b += hcap;
-    return b + 128;
+    return b + 2 * half_smem_bytes(hcap, threads_half, G, qcap, mt) + 128;
 }
 
 // largest Fortran row index with a non-zero entry in the kind-major host copy kept by the context
@@ -537,37 +600,41 @@ int mdb_tiled_plan(mdb_ctx *c)
     S.khi[0] = std::min(kru, kz1 + 2);
     S.khi[1] = std::min(kru, kz2 + 2);
 
-    // ---- tile geometry
+    // ---- class margin: a quarter of the list skin (NB_RM - RU), see header
+    double rmmax = 0.0;
+    for (int i = 0; i < c->ng * c->ng; i++) rmmax = std::max(rmmax, c->nb_rm[i]);
+    const double ru = std::sqrt(t.ru2max);
+    S.margin = std::max(0.0, 0.25 * (rmmax - ru));
+
+    // ---- tile geometry: widest tile whose two halo buffers, queues and a useful table window fit
     const int G = S.G;
     const double rho_cell = (double)c->n / (double)c->nc;
     const bool mt = c->ng > 1;
+    const double dens = (double)c->n / ((double)c->nbox * c->box.size[0] * c->box.size[1] * c->box.size[2]);
+    for (int p = 0; p < 2; p++) {
+        const double rf = std::sqrt(S.r2eff[p]) + S.margin;
+        const int expect = (int)(4.18879 * rf * rf * rf * dens * 1.25) + 4 * G;
+        S.qcap[p] = std::max(8 * G, ((expect + 4 * G + 7) / 8) * 8);
+    }
+    const int qmax = std::max(S.qcap[0], S.qcap[1]);
     int best_w = 0;
     for (int w = std::min(c->ncell[0], TILE_MAX_W); w >= 1; w--) {
         const int ntx = (c->ncell[0] + w - 1) / w;
         const int wt = (c->ncell[0] + ntx - 1) / ntx;
-        const int own = (int)(wt * rho_cell * 1.3) + 8;
-        if (own * G > 1024 && w > 1) continue;
-        const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.25) + 64;
-        if (hcap > 65000) continue;
-        const int threads = std::min(1024, ((own * G + 31) / 32) * 32);
-        // queue depth per atom: expected candidates inside the filter radius (+30 %) plus one full push round
-        const double dens = (double)c->n / ((double)c->nbox * c->box.size[0] * c->box.size[1] * c->box.size[2]);
-        for (int p = 0; p < 2; p++) {
-            const double rf = std::sqrt(S.r2eff[p]);
-            const int expect = (int)(4.18879 * rf * rf * rf * dens * 1.3) + 4 * G;
-            S.qcap[p] = std::max(8 * G, ((expect + 4 * G + 7) / 8) * 8);
-        }
-        const int qmax = std::max(S.qcap[0], S.qcap[1]);
-        // table window: as many rows below khi as fit
-        const size_t fixed = pass_smem_bytes(hcap, 0, threads, G, qmax, mt);
+        const int own = (int)(wt * rho_cell * 1.06) + 3;              // atoms per round: mean + 6 %
+        const int grp_per_warp = 32 / G;
+        int th = ((own + grp_per_warp - 1) / grp_per_warp) * 32;       // threads per half
+        if (th > 512) { if (w > 1) continue; th = 512; }
+        const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64;
+        if (hcap > 16000) continue; // slots carry a 2-bit class tag in the raw list
+        const size_t fixed = pass_smem_bytes(hcap, 0, th, G, qmax, mt);
         if (fixed + 16 * 512 + 1024 > (size_t)SMEM_BUDGET) continue;
         const int maxrows = (int)((SMEM_BUDGET - fixed - 1024) / 16) - 2;
         const int need = std::max(S.khi[0], S.khi[1]) + 1;
-        // require the window to reach down to r = 0.6 * (nearest plausible approach) ... or everything
-        const int want = std::min(need, maxrows);
-        if (want < need && want < need / 2) continue; // too little room for tables: try a narrower tile
+        // the window must at least reach down to half the table index of the support edge (r ~ r_eff/4)
+        if (maxrows < need && maxrows < need / 2) continue;
         best_w = w;
-        S.ntx = ntx; S.hcap = hcap; S.threads = threads;
+        S.ntx = ntx; S.hcap = hcap; S.threads = 2 * th;
         for (int p = 0; p < 2; p++) {
             S.ktab[p] = std::min(S.khi[p] + 1, maxrows);
             S.kmin[p] = S.khi[p] + 1 - S.ktab[p];
@@ -580,16 +647,13 @@ int mdb_tiled_plan(mdb_ctx *c)
     memset(&P, 0, sizeof(P));
     P.n = c->n; P.nbox = c->nbox; P.ncx = c->ncell[0]; P.ncy = c->ncell[1]; P.ncz = c->ncell[2]; P.nc0 = c->nc0;
     P.ntx = S.ntx; P.nrows = c->nbox * c->ncell[1] * c->ncell[2]; P.ntiles = P.nrows * P.ntx; P.hcap = S.hcap;
-    double cellmax = 0.0;
     for (int d = 0; d < 3; d++) {
         P.pd[d] = c->box.pd[d]; P.lo[d] = c->box.lo[d]; P.size[d] = c->box.size[d];
         P.cell[d] = c->box.size[d] / (double)c->ncell[d];
         P.fbs[d] = (float)c->box.size[d];
-        cellmax = std::max(cellmax, P.cell[d]);
     }
-    (void)cellmax;
     // phase-A quantum: RU spans 120 LSB, so every in-range coordinate difference fits a signed byte
-    const double lsb = std::sqrt(t.ru2max) / 120.0;
+    const double lsb = ru / 120.0;
     P.inv_lsb = 1.0 / lsb;
     P.ng = c->ng; P.mxkvois = c->mxkvois;
     const int rows_per_lane = (c->mxkvois + G - 1) / G;
@@ -600,24 +664,50 @@ int mdb_tiled_plan(mdb_ctx *c)
         // 3 LSB leaves room for the rounding of x*inv_lsb itself
         const double rl = std::sqrt(S.r2eff[p]) / lsb + 3.0;
         S.r2int[p] = (int)(rl * rl) + 1;
+        const double rc = std::sqrt(S.r2eff[p]) + S.margin;
+        S.rc2f[p] = (float)(rc * rc);
     }
-    // ---- slot list storage
-    const size_t nbl_elems = (size_t)P.nrow4 * P.npad * G * 4;
-    if (S.nbl_elems < nbl_elems) {
-        if (S.nbl) cudaFree(S.nbl);
-        S.nbl = nullptr; S.nbl_elems = 0;
-        if (cudaMalloc(&S.nbl, nbl_elems * sizeof(unsigned short)) != cudaSuccess) { cudaGetLastError(); return MDB_OK; }
-        S.nbl_elems = nbl_elems;
-    }
+    // classes hold while 2*d_max <= 0.98*margin
+    S.safe_d2 = (float)(0.49 * 0.49 * S.margin * S.margin);
+
+    // ---- storage: slot list, raw list, class counts, tile descriptors
+    auto ensure = [&](void **ptr, size_t &have, size_t want) -> bool {
+        if (have >= want) return true;
+        if (*ptr) cudaFree(*ptr);
+        *ptr = nullptr; have = 0;
+        if (cudaMalloc(ptr, want) != cudaSuccess) { cudaGetLastError(); return false; }
+        have = want;
+        return true;
+    };
+    const size_t nbl_bytes = (size_t)P.nrow4 * P.npad * G * 4 * sizeof(unsigned short);
+    if (!ensure((void **)&S.nbl, S.nbl_elems, nbl_bytes)) return MDB_OK;
+    if (!ensure((void **)&S.raw, S.raw_bytes, (size_t)c->mxkvois * c->n * sizeof(unsigned short))) return MDB_OK;
+    if (!ensure((void **)&S.ncls, S.ncls_bytes, 2 * P.npad * sizeof(unsigned short))) return MDB_OK;
+    if (!ensure((void **)&S.desc, S.desc_bytes, (size_t)P.ntiles * sizeof(TileDesc))) return MDB_OK;
+    if (!ensure((void **)&c->dsr, c->dsr_bytes, 3 * (size_t)c->n * sizeof(float))) return MDB_OK;
+    cudaMemsetAsync(c->dsr, 0, 3 * (size_t)c->n * sizeof(float), c->stream);
+
     // ---- launch configuration
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev);
-    S.grid = std::min(P.ntiles, nsm);
-    S.smem_list = ((sizeof(HaloTab) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap + 32;
+    S.grid = std::min((P.ntiles + 1) / 2, nsm);
+    S.smem_list = ((sizeof(TileDesc) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap + 32;
     S.grid_list = std::min(P.ntiles, nsm * std::max(1, std::min(8, (int)(SMEM_BUDGET / S.smem_list))));
-    for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads, G, S.qcap[p], mt);
+    for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads / 2, G, S.qcap[p], mt);
     S.ok = true;
     return MDB_OK;
+}
+
+void mdb_tiled_free(mdb_ctx *c)
+{
+    TiledState &S = c->tiled;
+    if (S.nbl) cudaFree(S.nbl);
+    if (S.raw) cudaFree(S.raw);
+    if (S.ncls) cudaFree(S.ncls);
+    if (S.desc) cudaFree(S.desc);
+    S.nbl = nullptr; S.raw = nullptr; S.ncls = nullptr; S.desc = nullptr;
+    S.nbl_elems = S.raw_bytes = S.ncls_bytes = S.desc_bytes = 0;
+    S.ok = false; S.dirty = true; S.active = false;
 }
 
 template <int G>
@@ -626,11 +716,18 @@ static int launch_list(mdb_ctx *c)
     TiledState &S = c->tiled;
     TileListArgs A;
     A.pos = c->pos; A.ityp = c->ityp; A.nac = c->nac; A.naac = c->naac; A.ia1th = c->ia1th;
-    A.kvois = c->kvois; A.indi = c->indi; A.nbl = S.nbl; A.counters = c->counters;
+    A.kvois = c->kvois; A.indi = c->indi; A.raw = S.raw; A.counters = c->counters; A.desc = (TileDesc *)S.desc;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
-    CUDA_TRY(c, cudaFuncSetAttribute(k_tile_nlist<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
-    ProfScope ps(c, MDB_K_NLIST);
-    k_tile_nlist<G><<<S.grid_list, 256, S.smem_list, c->stream>>>(S.P, A);
+    A.rc2[0] = S.rc2f[0]; A.rc2[1] = S.rc2f[1];
+    CUDA_TRY(c, cudaFuncSetAttribute(k_tile_nlist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
+    {
+        ProfScope ps(c, MDB_K_NLIST);
+        k_tile_nlist<<<S.grid_list, 256, S.smem_list, c->stream>>>(S.P, A);
+    }
+    {
+        ProfScope ps(c, MDB_K_NLIST);
+        k_tile_classify<G><<<cdiv(c->n, 128), 128, 0, c->stream>>>(S.P, c->counters, c->kvois, S.raw, S.nbl, S.ncls);
+    }
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -638,7 +735,6 @@ static int launch_list(mdb_ctx *c)
 int mdb_tiled_nlist(mdb_ctx *c)
 {
     switch (c->tiled.G) {
-    case 1: return launch_list<1>(c);
     case 2: return launch_list<2>(c);
     case 4: return launch_list<4>(c);
     case 8: return launch_list<8>(c);
@@ -652,13 +748,14 @@ static int launch_pass(mdb_ctx *c)
     TiledState &S = c->tiled;
     const TableSet &t = c->tab;
     TilePassArgs A;
-    A.pos = c->pos; A.ityp = c->ityp; A.statu = c->statu; A.nac = c->nac; A.ia1th = c->ia1th; A.kvois = c->kvois;
-    A.nbl = S.nbl; A.fp = c->fp; A.counters = c->counters;
+    A.pos = c->pos; A.ityp = c->ityp; A.statu = c->statu; A.kvois = c->kvois; A.ncls = S.ncls;
+    A.nbl = S.nbl; A.fp = c->fp; A.counters = c->counters; A.desc = (const TileDesc *)S.desc;
     A.g_potb = t.potb; A.g_fpotr = t.fpotr; A.g_fpotb = t.fpotb; A.g_dfembd = t.dfembd;
-    A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod; A.ru2max = t.ru2max;
+    A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod;
     A.r2eff = S.r2eff[PASS - 1]; A.r2int = S.r2int[PASS - 1]; A.kmin = S.kmin[PASS - 1]; A.ktab = S.ktab[PASS - 1];
     A.kind0 = t.kpair[0];
     A.qcap = S.qcap[PASS - 1];
+    A.safe_d2 = S.use_classes ? S.safe_d2 : -1.0f;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
     auto kern = k_tile_pass<PASS, G, MT>;
@@ -683,7 +780,6 @@ static int launch_force(mdb_ctx *c, unsigned flags)
 int mdb_force_tiled(mdb_ctx *c, unsigned flags)
 {
     switch (c->tiled.G) {
-    case 1: return launch_force<1>(c, flags);
     case 2: return launch_force<2>(c, flags);
     case 4: return launch_force<4>(c, flags);
     case 8: return launch_force<8>(c, flags);

@@ -23,8 +23,10 @@
 #define KB_CGS 1.38054e-16 // CP_KB, MSMLIB/sor/Common/MSM_Const.F90:82
 
 // device counters block (one int each)
-enum { CNT_OOB = 0, CNT_OVERFLOW, CNT_NNMAX, CNT_MXNAC, CNT_INCELL, CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N,
-       CNT_TILE_OVERFLOW, CNT__N = 8 };
+// the first CNT_PERBUILD_N are reset at every rebuild
+enum { CNT_OOB = 0, CNT_OVERFLOW, CNT_NNMAX, CNT_MXNAC, CNT_INCELL, CNT_TILE_OVERFLOW,
+       CNT_D2MAX,       // float bits: max |displacement since the rebuild|^2 over all atoms (predictor)
+       CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N, CNT__N = 12 };
 
 struct BoxParams { // passed by value to kernels
     double lo[3], up[3], size[3], half[3];
@@ -72,7 +74,13 @@ struct TiledState {
     int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0}, r2int[2] = {0, 0}, qcap[2] = {0, 0};
     double r2eff[2] = {0.0, 0.0};
     size_t smem_list = 0, smem_pass[2] = {0, 0};
-    unsigned short *nbl = nullptr; size_t nbl_elems = 0;
+    double margin = 0.0;       // class margin (length): classes hold while every atom moved < margin/2
+    float rc2f[2] = {0.f, 0.f}, safe_d2 = 0.f;
+    bool use_classes = true;
+    unsigned short *nbl = nullptr; size_t nbl_elems = 0;   // slot list (bytes in nbl_elems)
+    unsigned short *raw = nullptr; size_t raw_bytes = 0;   // reference-order slots + class tag
+    unsigned short *ncls = nullptr; size_t ncls_bytes = 0; // per-atom class counts [2][npad]
+    void *desc = nullptr; size_t desc_bytes = 0;           // TileDesc per tile
 };
 
 struct mdb_ctx {
@@ -98,6 +106,7 @@ struct mdb_ctx {
     int *statu = nullptr, *statu_alt = nullptr;
     int *gid = nullptr, *gid_alt = nullptr, *gidinv = nullptr;
     int *ic = nullptr, *ic_alt = nullptr;
+    float *dsr = nullptr; size_t dsr_bytes = 0; // displacement since the last rebuild, (N,3) fp32
     // materialised reference-shaped views
     double *xp_view = nullptr, *den_view = nullptr;
     // staging for up/download
@@ -173,5 +182,7 @@ int mdb_nlist_kernel(mdb_ctx *c);            // mdb_nlist.cu : fill KVOIS/INDI
 int mdb_force_generic(mdb_ctx *c, unsigned flags, double *vt); // mdb_force.cu
 int mdb_tiled_plan(mdb_ctx *c);               // mdb_force_tiled.cu
 int mdb_tiled_nlist(mdb_ctx *c);
+void mdb_tiled_free(mdb_ctx *c);
+void mdb_mark_positions_dirty(mdb_ctx *c);    // mdb_api.cu : positions changed outside the predictor
 int mdb_force_tiled(mdb_ctx *c, unsigned flags);
 int mdb_list_rebuild(mdb_ctx *c);             // mdb_api.cu : cells + list kernel of the active path (no sync)

@@ -11,19 +11,20 @@
 // trajectories track the oracle as closely as the force sums allow.
 #include "mdb_internal.cuh"
 
-__global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, const double *__restrict__ fp,
-                          double *__restrict__ dis, int *__restrict__ statu, const int *__restrict__ ityp,
-                          MassParams M, BoxParams box, double th, double h2s2, double hs2)
+// one atom of the predictor; returns |displacement since the last rebuild|^2 (0 when not tracked)
+__device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict__ pos, double *__restrict__ xp1,
+                                              const double *__restrict__ fp, double *__restrict__ dis,
+                                              int *__restrict__ statu, const int *__restrict__ ityp, const MassParams &M,
+                                              const BoxParams &box, double th, double h2s2, double hs2,
+                                              float *__restrict__ dsr)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     const int stat = statu[i];
-    if ((stat & ST_ACTIVE) != ST_ACTIVE) return; // :295
     const double cm0 = M.cm[ityp[i] - 1];
     double4 p = pos[i];
     double x[3] = {p.x, p.y, p.z};
     const int fixp[3] = {ST_FIXPOSX, ST_FIXPOSY, ST_FIXPOSZ};
     const int fixv[3] = {ST_FIXVELX, ST_FIXVELY, ST_FIXVELZ};
+    float d2 = 0.f;
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         const size_t o = i + (size_t)d * n;
@@ -39,12 +40,40 @@ __global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__
         x[d] = xx;
         if ((stat & fixv[d]) == 0 && (stat & fixp[d]) == 0) xp1[o] = __dadd_rn(v, __dmul_rn(hs2, a)); // :353-361
         dis[o] = __dadd_rn(dis[o], dd);                                          // :371-373
+        if (dsr) { // un-wrapped displacement accumulated since the last neighbour rebuild (fp32 is ample)
+            const float t = dsr[o] + (float)dd;
+            dsr[o] = t;
+            d2 += t * t;
+        }
     }
     p.x = x[0]; p.y = x[1]; p.z = x[2];
     pos[i] = p;
     // :375-379 (the PASSBOUND bit set at :320 is never stored by the reference)
     if (x[0] > box.up[0] || x[1] > box.up[1] || x[2] > box.up[2]) statu[i] = ST_OUTOFBOX | ST_REFLECT;
     else if (x[0] < box.lo[0] || x[1] < box.lo[1] || x[2] < box.lo[2]) statu[i] = ST_OUTOFBOX | ST_TRANSMIT;
+    return d2;
+}
+
+__global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, const double *__restrict__ fp,
+                          double *__restrict__ dis, int *__restrict__ statu, const int *__restrict__ ityp,
+                          MassParams M, BoxParams box, double th, double h2s2, double hs2,
+                          float *__restrict__ dsr, int *__restrict__ counters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float d2 = 0.f;
+    if (i < n && (statu[i] & ST_ACTIVE) == ST_ACTIVE) // :295
+        d2 = predict_atom(i, n, pos, xp1, fp, dis, statu, ityp, M, box, th, h2s2, hs2, dsr);
+    if (dsr) { // block maximum -> one atomic per block; the tiled passes compare it with their class margin
+        for (int off = 16; off > 0; off >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, off));
+        __shared__ float smax[8];
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = d2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m = smax[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, smax[w]);
+            if (m > 0.f) atomicMax(&counters[CNT_D2MAX], __float_as_int(m)); // non-negative floats order like ints
+        }
+    }
 }
 
 // EPC friction on FP followed by the second half kick: one read of XP1/FP instead of the
@@ -105,7 +134,7 @@ extern "C" int mdb_predict(mdb_ctx *c, double h)
     const double th = h, hs2 = th * 0.5, h2s2 = th * th * 0.5;
     ProfScope ps(c, MDB_K_PREDICT);
     k_predict<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp, c->mass,
-                                                      c->box, th, h2s2, hs2);
+                                                      c->box, th, h2s2, hs2, c->dsr, c->counters);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }

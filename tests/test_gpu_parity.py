@@ -215,6 +215,35 @@ def test_tiled_matches_generic_at_scale():
     a.close(); b.close()
 
 
+def test_distance_classes_are_exact(oracle):
+    """The tiled passes scan only the build-time distance classes they need while every atom has moved
+    less than half the class margin since the rebuild.  (i) with and without the classes the results
+    agree to round-off; (ii) a large move between rebuilds (here: the host overwrites positions) must
+    switch the passes to the full list, and the forces must still match the oracle on that list."""
+    c = util.bcc_case((8, 8, 8), seed=21)
+    a = util.make_ctx(c, force_path=capi.FORCE_PATH_TILED)
+    b = util.make_ctx(c, force_path=capi.FORCE_PATH_TILED)
+    b.set_option(capi.OPT_TILED_CLASSES, 0)
+    assert a.get_option(capi.OPT_ACTIVE_PATH) == capi.FORCE_PATH_TILED
+    a.run(0, 8, 1, 10, 0.5e-15); b.run(0, 8, 1, 10, 0.5e-15)
+    assert util.relerr(a.download(capi.F_FP), b.download(capi.F_FP)) < 1e-13
+    assert util.relerr(a.download(capi.F_XP), b.download(capi.F_XP)) < 1e-14
+    # (ii) stale list + moved atoms: displace every atom by up to 0.45 A without rebuilding
+    ref = _oracle_list(oracle, c)
+    gid = ref["gid"] - 1
+    rng = np.random.default_rng(5)
+    xnew = c.xp + rng.uniform(-0.45e-8, 0.45e-8, size=c.xp.shape)
+    ctx = util.make_ctx(c, force_path=capi.FORCE_PATH_TILED)
+    ctx.upload(capi.F_XP, xnew)           # no rebuild: the reference would use the stale list as is
+    ctx.force(capi.FORCE)
+    fp, den, _, _ = oracle.force(xnew[gid], c.ityp[gid], ref["statu"][gid], ref["kvois"], ref["indi"], c.zl, c.ifpd,
+                                 util.oracle_tables(oracle, c))
+    assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < FORCE_RTOL
+    assert util.relerr(ctx.download(capi.F_DEN, capi.ORDER_CELL), den) < FORCE_RTOL
+    for x in (a, b, ctx):
+        x.close()
+
+
 def test_errors_are_status_codes_not_stops():
     ctx = capi.Context(0)
     with pytest.raises(capi.MDBError) as e:
