@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "tiled"])
     ap.add_argument("--cpu-cells", type=int, default=32, help="edge of the CPU sample box (32 -> 65 536 atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="tiled path: lanes per atom (2/4/8), 0 = default")
+    ap.add_argument("--classes", type=int, default=1, help="tiled path: distance-classified lists on/off")
+    ap.add_argument("--parts", type=int, default=0, help="tiled path: tiles in flight per SM (1..4), 0 = default")
     return ap.parse_args()
 
 
@@ -178,6 +181,11 @@ def run_ours(args):
     ctx.set_option(capi.OPT_FORCE_PATH, {"auto": 0, "generic": 1, "tiled": 2}[args.path])
     ctx.tables_set(util.product_tables(c), c.ru * c.ru)
     ctx.nlist_init(c.nb_rm, c.mxkvois)
+    if args.lanes:
+        ctx.set_option(capi.OPT_TILED_LANES, args.lanes)
+    if args.parts:
+        ctx.set_option(capi.OPT_TILED_PARTS, args.parts)
+    ctx.set_option(capi.OPT_TILED_CLASSES, args.classes)
     ctx.epc_set(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
 
     # host buffers in pinned memory, reference layout XP(N,3) column-major

@@ -101,17 +101,26 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
 // =====================================================================================
 struct TileListArgs {
     const double4 *pos; const int *ityp; const int *nac; const int *naac; const int *ia1th;
-    int *kvois; int *indi; unsigned short *raw; int *counters; TileDesc *desc;
+    int *kvois; int *indi; unsigned short *nbl; unsigned short *ncls; int *counters; TileDesc *desc;
     float rm2[MDB_MXGROUP * MDB_MXGROUP];
     float rc2[2]; // class radii^2 (build-time, fp32): class 0 <= rc2[0] < class 1 <= rc2[1] < class 2
 };
 
-__global__ void __launch_bounds__(256)
+#define NL_THREADS 128
+
+// One CTA per tile.  Candidates are scanned in the reference order; accepted neighbours go to the
+// reference-format INDI (global ids, reference order) and, tagged with their distance class, to a
+// per-thread list in shared memory that is then written out class by class in the lane-interleaved
+// layout the passes stream (nbl_index); tails are padded with slot 0 so that every 4-entry group a
+// lane can touch holds valid slots.
+template <int G>
+__global__ void __launch_bounds__(NL_THREADS)
 k_tile_nlist(TileParams P, TileListArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     TileDesc &H = *reinterpret_cast<TileDesc *>(smem);
     float4 *spos = reinterpret_cast<float4 *>(smem + ((sizeof(TileDesc) + 15) & ~15));
+    unsigned short *slist = reinterpret_cast<unsigned short *>(spos + P.hcap); // [mxkvois][NL_THREADS]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
@@ -145,6 +154,7 @@ k_tile_nlist(TileParams P, TileListArgs A)
         __syncthreads();
         const int hc_own0 = (1 * 3 + 1) * g.nhx + 1;
         const int own_start = H.own_start, own_count = H.own_count, own_slot0 = H.own_slot0;
+        unsigned short *mylist = slist + threadIdx.x;
         for (int o = threadIdx.x; o < own_count; o += blockDim.x) {
             const int ia = own_start + o;
             int hxc = 1; // which cell of the tile is this atom in
@@ -153,63 +163,49 @@ k_tile_nlist(TileParams P, TileListArgs A)
             if (A.naac[H.cid[myhc]] <= 0) continue; // cells without ACTIVE atoms are skipped (:981-982)
             const float4 me = spos[own_slot0 + o];   // own cell is never shifted: (float)XP_i
             const int ity = __float_as_int(me.w);
-            int nn = 0;
+            const float *rmrow = A.rm2 + (ity - 1);
+            int nn = 0, n0 = 0, n1 = 0;
             for (int k = 0; k < 27; k++) {
                 const int hc = ((1 + t_niz[k]) * 3 + (1 + t_niy[k])) * g.nhx + (hxc + t_nix[k]);
                 if (H.cid[hc] < 0) continue;
                 const int sl = H.slot[hc], cnt = H.cnt[hc], gst = H.gst[hc];
+                const int self = (k == 0) ? (own_slot0 + o) : -1;
                 for (int t = 0; t < cnt; t++) {
                     const float4 s = spos[sl + t];
                     const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
                     const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
-                    const int jty = __float_as_int(s.w);
-                    const int j = gst + t;
-                    if (r2 <= A.rm2[(ity - 1) + P.ng * (jty - 1)] && !(k == 0 && j == ia)) { // :1123-1124
-                        nn++;
-                        if (nn <= P.mxkvois) {
-                            A.indi[ia + (size_t)(nn - 1) * P.n] = j + 1;
-                            const unsigned cls = r2 <= A.rc2[0] ? 0u : (r2 <= A.rc2[1] ? 1u : 2u);
-                            A.raw[ia + (size_t)(nn - 1) * P.n] = (unsigned short)((unsigned)(sl + t) | (cls << 14));
+                    const float rm = (P.ng == 1) ? A.rm2[0] : rmrow[P.ng * (__float_as_int(s.w) - 1)];
+                    if (r2 <= rm && (sl + t) != self) { // :1123-1124
+                        if (nn < P.mxkvois) {
+                            A.indi[ia + (size_t)nn * P.n] = gst + t + 1;
+                            const unsigned c0 = r2 <= A.rc2[0], c1 = r2 <= A.rc2[1];
+                            n0 += c0; n1 += c1;
+                            mylist[nn * NL_THREADS] = (unsigned short)((unsigned)(sl + t) | ((2u - c0 - c1) << 14));
                         }
+                        nn++;
                     }
                 }
             }
-            A.kvois[ia] = min(nn, P.mxkvois); // :1195
+            const int kv = min(nn, P.mxkvois);
+            A.kvois[ia] = kv; // silently truncated :1195
             if (nn > P.mxkvois) atomicAdd(&A.counters[CNT_OVERFLOW], 1);
             atomicMax(&A.counters[CNT_NNMAX], nn);
+            // class-ordered, lane-interleaved slot list
+            n1 -= n0; // n0 = class 0, n1 = class 1
+            int p0 = 0, p1 = n0, p2 = n0 + n1;
+            for (int k = 0; k < kv; k++) {
+                const unsigned e = mylist[k * NL_THREADS];
+                const unsigned c = e >> 14;
+                int d;
+                if (c == 0u) d = p0++; else if (c == 1u) d = p1++; else d = p2++;
+                A.nbl[nbl_index<G>(P, (size_t)ia, d)] = (unsigned short)(e & 0x3fffu);
+            }
+            const int kend = min(((kv + 4 * G - 1) / (4 * G)) * (4 * G), P.nrow4 * 4 * G);
+            for (int k = kv; k < kend; k++) A.nbl[nbl_index<G>(P, (size_t)ia, k)] = 0;
+            A.ncls[ia] = (unsigned short)n0;
+            A.ncls[ia + P.npad] = (unsigned short)(n0 + n1);
         }
     }
-}
-
-// stable partition of every atom's slot list into its three distance classes, written in the
-// lane-interleaved layout the passes stream (see nbl_index); tails are padded with slot 0 so that
-// every 4-entry group a lane can touch holds valid slots.
-template <int G>
-__global__ void k_tile_classify(TileParams P, const int *__restrict__ counters, const int *__restrict__ kvois,
-                                const unsigned short *__restrict__ raw, unsigned short *__restrict__ nbl,
-                                unsigned short *__restrict__ ncls)
-{
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= counters[CNT_INCELL]) return;
-    const int kv = kvois[a];
-    int n0 = 0, n1 = 0;
-    for (int k = 0; k < kv; k++) {
-        const unsigned c = raw[a + (size_t)k * P.n] >> 14;
-        n0 += (c == 0u);
-        n1 += (c == 1u);
-    }
-    int p0 = 0, p1 = n0, p2 = n0 + n1;
-    for (int k = 0; k < kv; k++) {
-        const unsigned e = raw[a + (size_t)k * P.n];
-        const unsigned c = e >> 14;
-        int d;
-        if (c == 0u) d = p0++; else if (c == 1u) d = p1++; else d = p2++;
-        nbl[nbl_index<G>(P, (size_t)a, d)] = (unsigned short)(e & 0x3fffu);
-    }
-    const int kend = min(((kv + 4 * G - 1) / (4 * G)) * (4 * G), P.nrow4 * 4 * G);
-    for (int k = kv; k < kend; k++) nbl[nbl_index<G>(P, (size_t)a, k)] = 0;
-    ncls[a] = (unsigned short)n0;
-    ncls[a + P.npad] = (unsigned short)(n0 + n1);
 }
 
 // =====================================================================================
@@ -227,6 +223,7 @@ struct TilePassArgs {
     int kmin, ktab;        // shared-memory table window: rows kmin .. kmin+ktab (row kk and kk+1 are read)
     int kind0;             // the kind held in shared memory = KPAIR(1,1)
     int qcap;              // queue entries per atom
+    int nparts;            // independent partitions of the CTA (tiles in flight per SM)
     float safe_d2;         // classes are valid while max |displacement since rebuild|^2 <= safe_d2
     int kpair[MDB_MXGROUP * MDB_MXGROUP];
     int kembd[MDB_MXGROUP];
@@ -304,16 +301,17 @@ __device__ __forceinline__ unsigned filt(unsigned a, unsigned b, int r2int)
 }
 
 // PASS 1: rho -> DEN.  PASS 2: forces.  G lanes per atom.  MT: more than one atom type.
-// The CTA runs as two independent halves (threads [0,T/2) and [T/2,T)), each with its own tile.
+// The CTA runs as A.nparts independent partitions of TH = T/nparts threads, each with its own tile in
+// flight ("half" below is the partition index; the first version had two).
 template <int PASS, int G, bool MT>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(G == 2 ? 512 : 768, 1)
 k_tile_pass(TileParams P, TilePassArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int T = blockDim.x, TH = T >> 1;
-    const int half = (int)threadIdx.x >= TH ? 1 : 0;
-    const int tid = (int)threadIdx.x - half * TH;  // thread id inside the half
-    const int ngrp = TH / G;                        // atoms per round of a half
+    const int T = blockDim.x, TH = T / A.nparts;
+    const int half = (int)threadIdx.x / TH;
+    const int tid = (int)threadIdx.x - half * TH;  // thread id inside the partition
+    const int ngrp = TH / G;                        // atoms per round of a partition
     // ---- carve shared memory: [tables][half 0: mbar, pos, pk, queue, types][half 1: ...]
     size_t off = 0;
     double2 *s_tab = reinterpret_cast<double2 *>(smem + off);       off += sizeof(double2) * (size_t)(A.ktab + 1);
@@ -352,22 +350,49 @@ k_tile_pass(TileParams P, TilePassArgs A)
     // distance classes are usable while no atom has moved more than half the class margin since the rebuild
     const bool safe = __int_as_float(A.counters[CNT_D2MAX]) <= A.safe_d2;
 
-    for (int tile = 2 * blockIdx.x + half; tile < P.ntiles; tile += 2 * gridDim.x) {
+    // ---- per-tile descriptor values are prefetched one tile ahead so that no global-memory round trip
+    //      sits between the end of one tile and the TMA issue of the next
+    struct Pre { int htot, nhc, edge_any, own_start, own_slot0, own_count, cnt, slot, gst; };
+    auto prefetch = [&](int tile) {
+        Pre q;
+        q.htot = 0; q.nhc = 0; q.edge_any = 0; q.own_start = 0; q.own_slot0 = 0; q.own_count = 0; q.cnt = 0; q.slot = 0; q.gst = 0;
+        if (tile < P.ntiles) {
+            const TileDesc &D = A.desc[tile];
+            q.htot = D.htot; q.nhc = D.nhc; q.edge_any = D.edge_any;
+            q.own_start = D.own_start; q.own_slot0 = D.own_slot0; q.own_count = D.own_count;
+            if (tid < TILE_MAX_HC) { q.cnt = D.cnt[tid]; q.slot = D.slot[tid]; q.gst = D.gst[tid]; }
+        }
+        return q;
+    };
+    const int tile_step = A.nparts * gridDim.x;
+    Pre cur = prefetch(A.nparts * blockIdx.x + half);
+
+    for (int tile = A.nparts * blockIdx.x + half; tile < P.ntiles; tile += tile_step) {
         const TileDesc &D = A.desc[tile];
         bar_named(1 + half, TH);                     // every lane of the half is done with the previous halo
-        const int htot = D.htot, nhc = D.nhc;
-        if (htot > P.hcap) continue;                 // counted by the list kernel; the host falls back
+        const int htot = cur.htot, nhc = cur.nhc;
+        const bool edge_any = cur.edge_any != 0;
+        const int own_start = cur.own_start, own_slot0 = cur.own_slot0, own_count = cur.own_count;
+        if (htot > P.hcap) { cur = prefetch(tile + tile_step); continue; } // counted by the list kernel; the host falls back
         // ---- stage the halo: one TMA bulk copy per halo cell (contiguous run of 32-byte records)
         if (tid == 0) mbar_expect_tx(mbar, (unsigned)htot * 32u);
-        for (int hc = tid; hc < nhc; hc += TH) {
-            const int cnt = D.cnt[hc];
-            if (cnt > 0) {
-                fence_proxy_async();
-                bulk_g2s(s_pos + D.slot[hc], A.pos + D.gst[hc], (unsigned)cnt * 32u, mbar);
+        if (tid < nhc && cur.cnt > 0) {
+            fence_proxy_async();
+            bulk_g2s(s_pos + cur.slot, A.pos + cur.gst, (unsigned)cur.cnt * 32u, mbar);
+        }
+        // while the copies are in flight: next tile's descriptor and this round's per-atom scalars / first indices
+        cur = prefetch(tile + tile_step);
+        int pre_kv = 0;
+        uint2 pre_idx = make_uint2(0u, 0u);
+        {
+            const int o = grp;
+            if (o < own_count) {
+                const int ia = own_start + o;
+                if ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE)
+                    pre_kv = safe ? (int)A.ncls[ia + (PASS - 1) * P.npad] : A.kvois[ia];
+                pre_idx = __ldcs(reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl));
             }
         }
-        const bool edge_any = D.edge_any != 0;
-        const int own_start = D.own_start, own_slot0 = D.own_slot0, own_count = D.own_count;
         mbar_wait(mbar, phase);
         phase ^= 1u;
         if (edge_any) {
@@ -411,8 +436,16 @@ k_tile_pass(TileParams P, TilePassArgs A)
             const int myslot = own_slot0 + (have ? o : 0);
             const double4 me = s_pos[myslot];
             const unsigned mypk = s_pk[myslot];
-            const bool active = have && ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE);
-            const int kv = active ? (safe ? (int)A.ncls[ia + (PASS - 1) * P.npad] : A.kvois[ia]) : 0;
+            int kv;
+            uint2 nxt;
+            if (base == 0) { kv = pre_kv; nxt = pre_idx; }
+            else {
+                const bool active = have && ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE);
+                kv = active ? (safe ? (int)A.ncls[ia + (PASS - 1) * P.npad] : A.kvois[ia]) : 0;
+                nxt = make_uint2(0u, 0u);
+                if (kv > gl) nxt = __ldcs(reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl));
+            }
+            const bool active = kv > 0 || (have && ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE));
             const int ti = MT ? (int)s_typ[myslot] : 0;
 
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
@@ -422,8 +455,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
             const uint2 *ip = reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl);
             const size_t ipstride = P.npad * G;
             unsigned short *gq = s_q + grp;            // this atom's queue: entry e at gq[e * ngrp]
-            uint2 nxt = make_uint2(0u, 0u);
-            if (n4 > 0) nxt = __ldcs(ip);              // software pipeline: the next index group is always in flight
+            // software pipeline: nxt holds this lane's next 4-entry index group (already requested)
 
             while (true) {
                 int gcnt = 0;                           // entries in the atom's queue (same on its G lanes)
@@ -461,6 +493,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 __syncwarp();
                 // ---------------- phase B: drain in lock-step, lane gl takes entries gl, gl+G, ...
                 const unsigned short *rq = gq + (size_t)gl * ngrp;
+#pragma unroll 1
                 for (int e = gl; e - gl < mx; e += G, rq += (size_t)G * ngrp) {
                     const bool on = e < gcnt;
                     const int s = on ? (int)*rq : myslot;
@@ -566,11 +599,11 @@ static size_t half_smem_bytes(int hcap, int threads_half, int G, int qcap, bool 
                (mt ? (size_t)hcap : 0);
     return (b + 127) & ~(size_t)127;
 }
-static size_t pass_smem_bytes(int hcap, int ktab, int threads_half, int G, int qcap, bool mt)
+static size_t pass_smem_bytes(int hcap, int ktab, int threads_half, int G, int qcap, bool mt, int nparts)
 {
     size_t b = sizeof(double2) * (size_t)(ktab + 1);
     b = (b + 127) & ~(size_t)127;
-    return b + 2 * half_smem_bytes(hcap, threads_half, G, qcap, mt) + 128;
+    return b + (size_t)nparts * half_smem_bytes(hcap, threads_half, G, qcap, mt) + 128;
 }
 
 // largest Fortran row index with a non-zero entry in the kind-major host copy kept by the context
@@ -617,29 +650,35 @@ int mdb_tiled_plan(mdb_ctx *c)
         S.qcap[p] = std::max(8 * G, ((expect + 4 * G + 7) / 8) * 8);
     }
     const int qmax = std::max(S.qcap[0], S.qcap[1]);
+    // The CTA is split into np partitions of th threads, each owning one tile at a time.  Thread budget:
+    // 768 (G=4/8: 80 registers) or 512 (G=2: 128 registers).  Tiles are cut so that the mean number of owned
+    // atoms (+6 %) fills the th/G atom slots of a partition.
     int best_w = 0;
-    for (int w = std::min(c->ncell[0], TILE_MAX_W); w >= 1; w--) {
-        const int ntx = (c->ncell[0] + w - 1) / w;
-        const int wt = (c->ncell[0] + ntx - 1) / ntx;
-        const int own = (int)(wt * rho_cell * 1.06) + 3;              // atoms per round: mean + 6 %
-        const int grp_per_warp = 32 / G;
-        int th = ((own + grp_per_warp - 1) / grp_per_warp) * 32;       // threads per half
-        if (th > 512) { if (w > 1) continue; th = 512; }
-        const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64;
-        if (hcap > 16000) continue; // slots carry a 2-bit class tag in the raw list
-        const size_t fixed = pass_smem_bytes(hcap, 0, th, G, qmax, mt);
-        if (fixed + 16 * 512 + 1024 > (size_t)SMEM_BUDGET) continue;
-        const int maxrows = (int)((SMEM_BUDGET - fixed - 1024) / 16) - 2;
-        const int need = std::max(S.khi[0], S.khi[1]) + 1;
-        // the window must at least reach down to half the table index of the support edge (r ~ r_eff/4)
-        if (maxrows < need && maxrows < need / 2) continue;
-        best_w = w;
-        S.ntx = ntx; S.hcap = hcap; S.threads = 2 * th;
-        for (int p = 0; p < 2; p++) {
-            S.ktab[p] = std::min(S.khi[p] + 1, maxrows);
-            S.kmin[p] = S.khi[p] + 1 - S.ktab[p];
+    const int tmax = (G == 2) ? 512 : 768;
+    for (int np = std::max(1, std::min(4, S.nparts_opt)); np >= 1 && !best_w; np--) {
+        const int th = (tmax / np / 32) * 32;               // threads per partition
+        const int slots = th / G;                            // owned atoms per round
+        const double own_target = (double)slots / 1.06 - 3.0;
+        int ntx0 = std::max(1, (int)std::ceil(c->ncell[0] * rho_cell / std::max(own_target, 1.0)));
+        ntx0 = std::min(ntx0, c->ncell[0]);
+        for (int ntx = ntx0; ntx <= c->ncell[0] && !best_w; ntx++) { // narrower tiles until everything fits
+            const int wt = (c->ncell[0] + ntx - 1) / ntx;
+            if (wt > TILE_MAX_W) continue;
+            const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64;
+            if (hcap > 16000) continue; // slots carry a 2-bit class tag while the list is built
+            const size_t fixed = pass_smem_bytes(hcap, 0, th, G, qmax, mt, np);
+            if (fixed + 16 * 512 + 1024 > (size_t)SMEM_BUDGET) continue;
+            const int maxrows = (int)((SMEM_BUDGET - fixed - 1024) / 16) - 2;
+            const int need = std::max(S.khi[0], S.khi[1]) + 1;
+            // the window must at least reach down to half the table index of the support edge (r ~ r_eff/4)
+            if (maxrows < need && maxrows < need / 2) continue;
+            best_w = wt;
+            S.ntx = ntx; S.hcap = hcap; S.threads = np * th; S.nparts = np;
+            for (int p = 0; p < 2; p++) {
+                S.ktab[p] = std::min(S.khi[p] + 1, maxrows);
+                S.kmin[p] = S.khi[p] + 1 - S.ktab[p];
+            }
         }
-        break;
     }
     if (!best_w) return MDB_OK;
 
@@ -681,7 +720,6 @@ int mdb_tiled_plan(mdb_ctx *c)
     };
     const size_t nbl_bytes = (size_t)P.nrow4 * P.npad * G * 4 * sizeof(unsigned short);
     if (!ensure((void **)&S.nbl, S.nbl_elems, nbl_bytes)) return MDB_OK;
-    if (!ensure((void **)&S.raw, S.raw_bytes, (size_t)c->mxkvois * c->n * sizeof(unsigned short))) return MDB_OK;
     if (!ensure((void **)&S.ncls, S.ncls_bytes, 2 * P.npad * sizeof(unsigned short))) return MDB_OK;
     if (!ensure((void **)&S.desc, S.desc_bytes, (size_t)P.ntiles * sizeof(TileDesc))) return MDB_OK;
     if (!ensure((void **)&c->dsr, c->dsr_bytes, 3 * (size_t)c->n * sizeof(float))) return MDB_OK;
@@ -690,10 +728,12 @@ int mdb_tiled_plan(mdb_ctx *c)
     // ---- launch configuration
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev);
-    S.grid = std::min((P.ntiles + 1) / 2, nsm);
-    S.smem_list = ((sizeof(TileDesc) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap + 32;
-    S.grid_list = std::min(P.ntiles, nsm * std::max(1, std::min(8, (int)(SMEM_BUDGET / S.smem_list))));
-    for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads / 2, G, S.qcap[p], mt);
+    S.grid = std::min((P.ntiles + S.nparts - 1) / S.nparts, nsm);
+    S.smem_list = ((sizeof(TileDesc) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap +
+                  sizeof(unsigned short) * (size_t)c->mxkvois * NL_THREADS + 32;
+    if (S.smem_list > (size_t)SMEM_BUDGET) return MDB_OK;
+    S.grid_list = std::min(P.ntiles, nsm * std::max(1, std::min(8, (int)((SMEM_BUDGET + 1024) / (S.smem_list + 1024)))));
+    for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads / S.nparts, G, S.qcap[p], mt, S.nparts);
     S.ok = true;
     return MDB_OK;
 }
@@ -702,11 +742,10 @@ void mdb_tiled_free(mdb_ctx *c)
 {
     TiledState &S = c->tiled;
     if (S.nbl) cudaFree(S.nbl);
-    if (S.raw) cudaFree(S.raw);
     if (S.ncls) cudaFree(S.ncls);
     if (S.desc) cudaFree(S.desc);
-    S.nbl = nullptr; S.raw = nullptr; S.ncls = nullptr; S.desc = nullptr;
-    S.nbl_elems = S.raw_bytes = S.ncls_bytes = S.desc_bytes = 0;
+    S.nbl = nullptr; S.ncls = nullptr; S.desc = nullptr;
+    S.nbl_elems = S.ncls_bytes = S.desc_bytes = 0;
     S.ok = false; S.dirty = true; S.active = false;
 }
 
@@ -716,18 +755,12 @@ static int launch_list(mdb_ctx *c)
     TiledState &S = c->tiled;
     TileListArgs A;
     A.pos = c->pos; A.ityp = c->ityp; A.nac = c->nac; A.naac = c->naac; A.ia1th = c->ia1th;
-    A.kvois = c->kvois; A.indi = c->indi; A.raw = S.raw; A.counters = c->counters; A.desc = (TileDesc *)S.desc;
+    A.kvois = c->kvois; A.indi = c->indi; A.nbl = S.nbl; A.ncls = S.ncls; A.counters = c->counters; A.desc = (TileDesc *)S.desc;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
     A.rc2[0] = S.rc2f[0]; A.rc2[1] = S.rc2f[1];
-    CUDA_TRY(c, cudaFuncSetAttribute(k_tile_nlist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
-    {
-        ProfScope ps(c, MDB_K_NLIST);
-        k_tile_nlist<<<S.grid_list, 256, S.smem_list, c->stream>>>(S.P, A);
-    }
-    {
-        ProfScope ps(c, MDB_K_NLIST);
-        k_tile_classify<G><<<cdiv(c->n, 128), 128, 0, c->stream>>>(S.P, c->counters, c->kvois, S.raw, S.nbl, S.ncls);
-    }
+    CUDA_TRY(c, cudaFuncSetAttribute(k_tile_nlist<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
+    ProfScope ps(c, MDB_K_NLIST);
+    k_tile_nlist<G><<<S.grid_list, NL_THREADS, S.smem_list, c->stream>>>(S.P, A);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -755,6 +788,7 @@ static int launch_pass(mdb_ctx *c)
     A.r2eff = S.r2eff[PASS - 1]; A.r2int = S.r2int[PASS - 1]; A.kmin = S.kmin[PASS - 1]; A.ktab = S.ktab[PASS - 1];
     A.kind0 = t.kpair[0];
     A.qcap = S.qcap[PASS - 1];
+    A.nparts = S.nparts;
     A.safe_d2 = S.use_classes ? S.safe_d2 : -1.0f;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];

@@ -77,6 +77,7 @@ struct TiledState {
     double margin = 0.0;       // class margin (length): classes hold while every atom moved < margin/2
     float rc2f[2] = {0.f, 0.f}, safe_d2 = 0.f;
     bool use_classes = true;
+    int nparts = 2, nparts_opt = 3; // tiles in flight per SM (partitions of the pass CTA)
     unsigned short *nbl = nullptr; size_t nbl_elems = 0;   // slot list (bytes in nbl_elems)
     unsigned short *raw = nullptr; size_t raw_bytes = 0;   // reference-order slots + class tag
     unsigned short *ncls = nullptr; size_t ncls_bytes = 0; // per-atom class counts [2][npad]
