@@ -101,18 +101,19 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
 // =====================================================================================
 struct TileListArgs {
     const double4 *pos; const int *ityp; const int *nac; const int *naac; const int *ia1th;
-    int *kvois; int *indi; unsigned short *nbl; unsigned short *ncls; int *counters; TileDesc *desc;
+    int *kvois; int *indi; unsigned short *nbl; unsigned short *ncls; unsigned short *raw; int *counters; TileDesc *desc;
     float rm2[MDB_MXGROUP * MDB_MXGROUP];
     float rc2[2]; // class radii^2 (build-time, fp32): class 0 <= rc2[0] < class 1 <= rc2[1] < class 2
 };
 
 #define NL_THREADS 128
 
-// One CTA per tile.  Candidates are scanned in the reference order; accepted neighbours go to the
-// reference-format INDI (global ids, reference order) and, tagged with their distance class, to a
-// per-thread list in shared memory that is then written out class by class in the lane-interleaved
-// layout the passes stream (nbl_index); tails are padded with slot 0 so that every 4-entry group a
-// lane can touch holds valid slots.
+// One CTA per tile, one warp per owned cell (lanes = atoms of the cell), so every lane of a warp walks
+// the same 27-cell candidate stream: shared-memory reads are broadcasts and there is no divergence in
+// the scan.  Accepted neighbours go to the reference-format INDI (global ids, reference order) and,
+// tagged with their distance class, to a scratch list in global memory ([k][atom], coalesced); the
+// lane then partitions its own scratch list by class into the lane-interleaved layout the passes
+// stream (nbl_index).  Tails are padded with slot 0 so every 4-entry group a lane can touch is valid.
 template <int G>
 __global__ void __launch_bounds__(NL_THREADS)
 k_tile_nlist(TileParams P, TileListArgs A)
@@ -120,7 +121,6 @@ k_tile_nlist(TileParams P, TileListArgs A)
     extern __shared__ __align__(16) unsigned char smem[];
     TileDesc &H = *reinterpret_cast<TileDesc *>(smem);
     float4 *spos = reinterpret_cast<float4 *>(smem + ((sizeof(TileDesc) + 15) & ~15));
-    unsigned short *slist = reinterpret_cast<unsigned short *>(spos + P.hcap); // [mxkvois][NL_THREADS]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
@@ -153,57 +153,92 @@ k_tile_nlist(TileParams P, TileListArgs A)
         }
         __syncthreads();
         const int hc_own0 = (1 * 3 + 1) * g.nhx + 1;
-        const int own_start = H.own_start, own_count = H.own_count, own_slot0 = H.own_slot0;
-        unsigned short *mylist = slist + threadIdx.x;
-        for (int o = threadIdx.x; o < own_count; o += blockDim.x) {
-            const int ia = own_start + o;
-            int hxc = 1; // which cell of the tile is this atom in
-            while (hxc < g.wt && o >= H.slot[hc_own0 + hxc] - own_slot0) hxc++;
+        for (int hxc = 1 + warp; hxc <= g.wt; hxc += nwarps) {        // owned cells of the tile
             const int myhc = hc_own0 + hxc - 1;
-            if (A.naac[H.cid[myhc]] <= 0) continue; // cells without ACTIVE atoms are skipped (:981-982)
-            const float4 me = spos[own_slot0 + o];   // own cell is never shifted: (float)XP_i
-            const int ity = __float_as_int(me.w);
-            const float *rmrow = A.rm2 + (ity - 1);
-            int nn = 0, n0 = 0, n1 = 0;
-            for (int k = 0; k < 27; k++) {
-                const int hc = ((1 + t_niz[k]) * 3 + (1 + t_niy[k])) * g.nhx + (hxc + t_nix[k]);
-                if (H.cid[hc] < 0) continue;
-                const int sl = H.slot[hc], cnt = H.cnt[hc], gst = H.gst[hc];
-                const int self = (k == 0) ? (own_slot0 + o) : -1;
-                for (int t = 0; t < cnt; t++) {
-                    const float4 s = spos[sl + t];
-                    const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
-                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
-                    const float rm = (P.ng == 1) ? A.rm2[0] : rmrow[P.ng * (__float_as_int(s.w) - 1)];
-                    if (r2 <= rm && (sl + t) != self) { // :1123-1124
-                        if (nn < P.mxkvois) {
-                            A.indi[ia + (size_t)nn * P.n] = gst + t + 1;
-                            const unsigned c0 = r2 <= A.rc2[0], c1 = r2 <= A.rc2[1];
-                            n0 += c0; n1 += c1;
-                            mylist[nn * NL_THREADS] = (unsigned short)((unsigned)(sl + t) | ((2u - c0 - c1) << 14));
+            if (A.naac[H.cid[myhc]] <= 0) continue;                   // cells without ACTIVE atoms are skipped (:981-982)
+            const int csl = H.slot[myhc], ccnt = H.cnt[myhc], cgst = H.gst[myhc];
+            for (int ab = 0; ab < ccnt; ab += 32) {
+                const bool valid = ab + lane < ccnt;
+                const int myslot = csl + ab + (valid ? lane : 0);
+                const int ia = cgst + ab + lane;
+                const float4 me = spos[myslot];                       // own cell is never shifted: (float)XP_i
+                const int ity = __float_as_int(me.w);
+                int nn = 0, n0 = 0, n1 = 0;
+                int *pI = A.indi + ia;                 // next INDI / scratch entry of this atom (stride N per entry)
+                unsigned short *pR = A.raw + ia;
+                const int room = valid ? P.mxkvois : 0;
+                const float rm1 = A.rm2[0], rc0 = A.rc2[0], rc1 = A.rc2[1];
+                for (int k = 0; k < 27; k++) {
+                    const int hc = ((1 + t_niz[k]) * 3 + (1 + t_niy[k])) * g.nhx + (hxc + t_nix[k]);
+                    if (H.cid[hc] < 0) continue;
+                    const int sl = H.slot[hc], cnt = H.cnt[hc], gst1 = H.gst[hc] + 1 - sl;
+                    // scan 32 candidates at a time into a per-lane acceptance mask (no branch per candidate),
+                    // then emit the set bits in ascending order: the list order stays the reference's
+                    for (int cb = sl; cb < sl + cnt; cb += 32) {
+                        const int nb = min(32, sl + cnt - cb);
+                        unsigned mask = 0u;
+#pragma unroll 4
+                        for (int t = 0; t < nb; t++) {
+                            const float4 s = spos[cb + t];
+                            const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
+                            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
+                            const float rm = (P.ng == 1) ? rm1 : A.rm2[(ity - 1) + P.ng * (__float_as_int(s.w) - 1)];
+                            mask |= (unsigned)(r2 <= rm) << t; // :1123
                         }
-                        nn++;
+                        if ((unsigned)(myslot - cb) < 32u) mask &= ~(1u << (myslot - cb)); // I .ne. IA :1124
+                        while (__any_sync(0xffffffffu, mask != 0u)) {
+                            if (mask) {
+                                const int t = __ffs(mask) - 1;
+                                mask &= mask - 1u;
+                                const int s_ = cb + t;
+                                if (nn < room) {
+                                    const float4 s = spos[s_];
+                                    const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
+                                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
+                                    *pI = gst1 + s_;
+                                    const unsigned c0 = r2 <= rc0, c1 = r2 <= rc1;
+                                    n0 += c0; n1 += c1;
+                                    *pR = (unsigned short)((unsigned)s_ | ((2u - c0 - c1) << 14));
+                                    pI += P.n; pR += P.n;
+                                }
+                                nn++;
+                            }
+                        }
                     }
                 }
+                if (!valid) continue;
+                const int kv = min(nn, P.mxkvois);
+                A.kvois[ia] = kv; // silently truncated :1195
+                if (nn > P.mxkvois) atomicAdd(&A.counters[CNT_OVERFLOW], 1);
+                atomicMax(&A.counters[CNT_NNMAX], nn);
+                // class-ordered, lane-interleaved slot list (the scratch entries were written by this lane)
+                n1 -= n0; // n0 = class 0, n1 = class 1
+                int p0 = 0, p1 = n0, p2 = n0 + n1;
+                int k = 0;
+                for (; k + 4 <= kv; k += 4) { // four independent loads in flight
+                    unsigned e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) e[u] = A.raw[ia + (size_t)(k + u) * P.n];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const unsigned c = e[u] >> 14;
+                        int d;
+                        if (c == 0u) d = p0++; else if (c == 1u) d = p1++; else d = p2++;
+                        A.nbl[nbl_index<G>(P, (size_t)ia, d)] = (unsigned short)(e[u] & 0x3fffu);
+                    }
+                }
+                for (; k < kv; k++) {
+                    const unsigned e = A.raw[ia + (size_t)k * P.n];
+                    const unsigned c = e >> 14;
+                    int d;
+                    if (c == 0u) d = p0++; else if (c == 1u) d = p1++; else d = p2++;
+                    A.nbl[nbl_index<G>(P, (size_t)ia, d)] = (unsigned short)(e & 0x3fffu);
+                }
+                const int kend = min(((kv + 4 * G - 1) / (4 * G)) * (4 * G), P.nrow4 * 4 * G);
+                for (k = kv; k < kend; k++) A.nbl[nbl_index<G>(P, (size_t)ia, k)] = 0;
+                A.ncls[ia] = (unsigned short)n0;
+                A.ncls[ia + P.npad] = (unsigned short)(n0 + n1);
             }
-            const int kv = min(nn, P.mxkvois);
-            A.kvois[ia] = kv; // silently truncated :1195
-            if (nn > P.mxkvois) atomicAdd(&A.counters[CNT_OVERFLOW], 1);
-            atomicMax(&A.counters[CNT_NNMAX], nn);
-            // class-ordered, lane-interleaved slot list
-            n1 -= n0; // n0 = class 0, n1 = class 1
-            int p0 = 0, p1 = n0, p2 = n0 + n1;
-            for (int k = 0; k < kv; k++) {
-                const unsigned e = mylist[k * NL_THREADS];
-                const unsigned c = e >> 14;
-                int d;
-                if (c == 0u) d = p0++; else if (c == 1u) d = p1++; else d = p2++;
-                A.nbl[nbl_index<G>(P, (size_t)ia, d)] = (unsigned short)(e & 0x3fffu);
-            }
-            const int kend = min(((kv + 4 * G - 1) / (4 * G)) * (4 * G), P.nrow4 * 4 * G);
-            for (int k = kv; k < kend; k++) A.nbl[nbl_index<G>(P, (size_t)ia, k)] = 0;
-            A.ncls[ia] = (unsigned short)n0;
-            A.ncls[ia + P.npad] = (unsigned short)(n0 + n1);
         }
     }
 }
@@ -721,6 +756,7 @@ int mdb_tiled_plan(mdb_ctx *c)
     const size_t nbl_bytes = (size_t)P.nrow4 * P.npad * G * 4 * sizeof(unsigned short);
     if (!ensure((void **)&S.nbl, S.nbl_elems, nbl_bytes)) return MDB_OK;
     if (!ensure((void **)&S.ncls, S.ncls_bytes, 2 * P.npad * sizeof(unsigned short))) return MDB_OK;
+    if (!ensure((void **)&S.raw, S.raw_bytes, (size_t)c->mxkvois * c->n * sizeof(unsigned short))) return MDB_OK;
     if (!ensure((void **)&S.desc, S.desc_bytes, (size_t)P.ntiles * sizeof(TileDesc))) return MDB_OK;
     if (!ensure((void **)&c->dsr, c->dsr_bytes, 3 * (size_t)c->n * sizeof(float))) return MDB_OK;
     cudaMemsetAsync(c->dsr, 0, 3 * (size_t)c->n * sizeof(float), c->stream);
@@ -729,8 +765,7 @@ int mdb_tiled_plan(mdb_ctx *c)
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev);
     S.grid = std::min((P.ntiles + S.nparts - 1) / S.nparts, nsm);
-    S.smem_list = ((sizeof(TileDesc) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap +
-                  sizeof(unsigned short) * (size_t)c->mxkvois * NL_THREADS + 32;
+    S.smem_list = ((sizeof(TileDesc) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap + 32;
     if (S.smem_list > (size_t)SMEM_BUDGET) return MDB_OK;
     S.grid_list = std::min(P.ntiles, nsm * std::max(1, std::min(8, (int)((SMEM_BUDGET + 1024) / (S.smem_list + 1024)))));
     for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads / S.nparts, G, S.qcap[p], mt, S.nparts);
@@ -743,9 +778,10 @@ void mdb_tiled_free(mdb_ctx *c)
     TiledState &S = c->tiled;
     if (S.nbl) cudaFree(S.nbl);
     if (S.ncls) cudaFree(S.ncls);
+    if (S.raw) cudaFree(S.raw);
     if (S.desc) cudaFree(S.desc);
-    S.nbl = nullptr; S.ncls = nullptr; S.desc = nullptr;
-    S.nbl_elems = S.ncls_bytes = S.desc_bytes = 0;
+    S.nbl = nullptr; S.ncls = nullptr; S.raw = nullptr; S.desc = nullptr;
+    S.nbl_elems = S.raw_bytes = S.ncls_bytes = S.desc_bytes = 0;
     S.ok = false; S.dirty = true; S.active = false;
 }
 
@@ -755,7 +791,7 @@ static int launch_list(mdb_ctx *c)
     TiledState &S = c->tiled;
     TileListArgs A;
     A.pos = c->pos; A.ityp = c->ityp; A.nac = c->nac; A.naac = c->naac; A.ia1th = c->ia1th;
-    A.kvois = c->kvois; A.indi = c->indi; A.nbl = S.nbl; A.ncls = S.ncls; A.counters = c->counters; A.desc = (TileDesc *)S.desc;
+    A.kvois = c->kvois; A.indi = c->indi; A.nbl = S.nbl; A.ncls = S.ncls; A.raw = S.raw; A.counters = c->counters; A.desc = (TileDesc *)S.desc;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
     A.rc2[0] = S.rc2f[0]; A.rc2[1] = S.rc2f[1];
     CUDA_TRY(c, cudaFuncSetAttribute(k_tile_nlist<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
