@@ -1,0 +1,98 @@
+!  mdb_shims.F90 -- drop-in bodies for the reference procedures on the hot path.  Each keeps the reference's
+!  name and dummy arguments, so MD_ForceClass_Register_GPU.F90 (Register_ForceClass), MD_Method_GenericMD_GPU.F90
+!  (For_One_Step) and the application shell link unchanged; the CUDA-Fortran module bodies they replace are listed.
+!  NOT COMPILED HERE (no Fortran compiler in the build image); see INTEGRATION.md.
+!
+module MD_EAM_Force_Table_GPU            ! replaces MDLIB/sor/CommonGPU/MD_EAM_ForceTable_GPU.F90
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MD_TYPEDEF_ForceTable
+  use MDB_C_BINDING
+  implicit none
+contains
+  subroutine INITIALIZE_EAM_Force_Table_DEV(SimBox, CtrlParam, FTable, RelaseTable, MULTIBOX)   ! :192-278
+    type(SimMDBox),     intent(inout)::SimBox
+    type(SimMDCtrl),    intent(in)   ::CtrlParam
+    type(MDForceTable), intent(in)   ::FTable
+    integer,            optional     ::RelaseTable, MULTIBOX
+    integer(c_int)::ERR
+      ERR = mdb_tables_set(m_CTX, MDB_POT_EAM, size(FTable%POTR,1), size(FTable%POTR,2), FTable%CSI,            &
+                           FTable%POTR, FTable%FPOTR, FTable%POTB, FTable%FPOTB,                                 &
+                           size(FTable%FEMBD,1), size(FTable%FEMBD,2), FTable%RHOD, FTable%FEMBD, FTable%DFEMBD, &
+                           FTable%KPAIR, FTable%KEMBD, maxval(CtrlParam%RU*CtrlParam%RU))
+      if(ERR .lt. 0) stop "MDPSCU Error: mdb_tables_set failed"
+  end subroutine
+  subroutine CALFORCE_EAM_Force_Table2A_DEV(SimBox, CtrlParam)                                   ! :950-1010
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+    real(c_double)::VT(3,3)
+      if(mdb_force(m_CTX, MDB_FORCE, VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+  end subroutine
+  subroutine CALPTENSOR_EAM_Force_Table2A_DEV(SimBox, CtrlParam)                                 ! :1366-1430
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+      if(mdb_force(m_CTX, ior(MDB_FORCE, MDB_VIRIAL), SimBox%VTENSOR) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+  end subroutine
+  subroutine UpdateEPOT_EAM_Force_Table2A_DEV(SimBox, CtrlParam)                                 ! :1710-1745
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+    real(c_double)::VT(3,3)
+      if(mdb_force(m_CTX, MDB_EPOT, VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+  end subroutine
+  subroutine CALDEN_EAM_Force_Table2A_DEV(SimBox, CtrlParam)                                     ! :891-945
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+    real(c_double)::VT(3,3)
+      if(mdb_force(m_CTX, MDB_DEN, VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+  end subroutine
+  subroutine Clear_EAM_Force_Table_DEV()                                                         ! :343-365
+    integer(c_int)::ERR
+      ERR = mdb_tables_clear(m_CTX)
+  end subroutine
+end module MD_EAM_Force_Table_GPU
+
+module MD_NeighborsList_GPU              ! replaces MDLIB/sor/CommonGPU/MD_NeighborsList_GPU.F90 (entry points :116-202)
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MDB_C_BINDING
+  implicit none
+contains
+  subroutine Initialize_NeighboreList_DEV(SimBox, CtrlParam)                                     ! :241-396
+    type(SimMDBox) ::SimBox
+    type(SimMDCtrl)::CtrlParam
+      if(mdb_nlist_init(m_CTX, CtrlParam%NB_RM, CtrlParam%NB_MXNBS) .lt. 0) stop "MDPSCU Error: mdb_nlist_init failed"
+  end subroutine
+  subroutine Cal_NeighBoreList_DEV(SimBox, CtrlParam)                                            ! :1347-1732
+    type(SimMDBox) ::SimBox
+    type(SimMDCtrl)::CtrlParam
+    integer(c_int)::NOUT
+      NOUT = mdb_nlist_build(m_CTX)
+      if(NOUT .lt. 0) stop "MDPSCU Error: mdb_nlist_build failed"
+      if(NOUT .gt. 0) write(*,fmt="(A, I8, A)") " MDPSCU Warning: there are ",NOUT," atoms out of box found in MD_NeighborsList."
+  end subroutine
+end module MD_NeighborsList_GPU
+
+module MD_DiffScheme_GPU                 ! replaces MDLIB/sor/CommonGPU/MD_DiffScheme_GPU.F90 (:604, :821, :1000)
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MDB_C_BINDING
+  implicit none
+contains
+  subroutine Predictor_DEV(ITIME, SimBox, CtrlParam)
+    integer, intent(in)::ITIME
+    type(SimMDBox)     ::SimBox
+    type(SimMDCtrl)    ::CtrlParam
+      if(mdb_predict(m_CTX, CtrlParam%H) .lt. 0) stop "MDPSCU Error: mdb_predict failed"
+  end subroutine
+  subroutine Correction_DEV(ITIME, SimBox, CtrlParam)
+    integer, intent(in)::ITIME
+    type(SimMDBox)     ::SimBox
+    type(SimMDCtrl)    ::CtrlParam
+      if(mdb_correct(m_CTX, CtrlParam%H) .lt. 0) stop "MDPSCU Error: mdb_correct failed"
+  end subroutine
+  subroutine CalEKin_DEV(SimBox, CtrlParam)
+    type(SimMDBox) ::SimBox
+    type(SimMDCtrl)::CtrlParam
+      if(mdb_ekin(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_ekin failed"
+  end subroutine
+end module MD_DiffScheme_GPU

@@ -1,0 +1,171 @@
+"""Readers for the reference's keyword-driven input files, enough for the hot path:
+box file (&BOXF ... &ENDBOX), control file (&CTLF ... &ENDCTLF), configurations (&BOXCFG14-18, &CFGXYZ or
+bare rows).  Formats: DOC/BoxFile.readme, DOC/CtrlFile_GMD.readme; parsers being mirrored:
+MDLIB/sor/Common/MD_TypeDef_SimBox.F90:377-795,1823-1979 and MD_TypeDef_SimCtrlParam.F90 / MD_SimCtrlParam_GMD.F90.
+Unit conversion follows Check_Globle_Variables, MDLIB/sor/Common/MD_Gvar.F90:918-951:
+  RR = a0[A]*1e-8, ZL = LATT*RR, BOXLOW = -ZL/2 unless &LOWB, CM = amu*1.66053e-24,
+  H = fs*1e-15, RU = RU[LU]*RR, NB_RM = factor*RU."""
+import re
+
+import numpy as np
+
+from .constants import CP_A2CM, CP_AU2G, CP_FS2S, CP_STATU_ACTIVE
+from .mdlib import SimMDBox, SimMDCtrl, TiCtrlParam
+
+_NUM = re.compile(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eEdD][-+]?\d+)?")
+
+
+def _lines(path):
+    with open(path) as f:
+        for raw in f:
+            s = raw.split("!")[0].strip()
+            if s:
+                yield s
+
+
+def _numbers(s):
+    s = re.sub(r'"[^"]*"', " ", s)
+    # numbers that are part of a word (e.g. "A-B=") are fine; identifiers with digits (#1) are stripped
+    s = re.sub(r"#\s*\d+", " ", s)
+    return [float(t.replace("d", "e").replace("D", "e")) for t in _NUM.findall(re.sub(r"[A-Za-z_][A-Za-z_0-9]*", " ", s))]
+
+
+def _strings(s):
+    return re.findall(r'"([^"]*)"', s)
+
+
+def _kw(s):
+    m = re.match(r"&([A-Za-z_0-9:]+)", s)
+    return m.group(1).upper() if m else ""
+
+
+def read_box_file(path):
+    """Returns a SimMDBox with sizes in CGS, masses in g, PTYPE filled from &TABLE rows."""
+    box = SimMDBox()
+    size = latt = None
+    lowb = None
+    groups, tables = [], []
+    cur = None
+    for s in _lines(path):
+        k = _kw(s)
+        if k == "SIZE":
+            size = np.array(_numbers(s[5:])[:3])
+        elif k == "LATT":
+            latt = _numbers(s[5:])[0]
+        elif k == "LOWB":
+            lowb = np.array(_numbers(s[5:])[:3])
+        elif k == "NGROUP":
+            box.NGROUP = int(_numbers(s[7:])[0])
+        elif k == "GROUPSUBCTL":
+            cur = dict(natom=0, mass=0.0, symb="", stat=CP_STATU_ACTIVE)
+            groups.append(cur)
+        elif k == "NATOM":
+            n = int(_numbers(s[6:])[0])
+            if cur is not None and len(groups) and "done" not in cur:
+                cur["natom"] = n
+            else:
+                box.NPRT = n
+        elif k == "ATOMP" and cur is not None:
+            nums = _numbers(s[6:])
+            cur["symb"] = (_strings(s) or [""])[0]
+            cur["mass"] = nums[-1]
+        elif k == "ENDSUBCTL" and cur is not None:
+            cur["done"] = True
+            cur = None
+        elif k == "TYPE":
+            box.PotType = (_strings(s) or ["EAM_TYPE"])[0].upper()
+        elif k == "LIBNAME":
+            st = _strings(s)
+            box.PotLibname = st[0] if st else ""
+            box.PotSubLibname = st[1] if len(st) > 1 else ""
+        elif k == "TABLE":
+            tables.append([int(v) for v in _numbers(re.sub(r"&TABLE\s+\S+", "", s, count=1))])
+    if box.NPRT == 0:
+        box.NPRT = sum(g["natom"] for g in groups)
+    box.NGROUP = box.NGROUP or len(groups)
+    box.RR = latt * CP_A2CM
+    box.ZL = size * box.RR
+    box.BOXLOW = -0.5 * box.ZL if lowb is None else lowb * box.RR
+    box.BOXUP = box.BOXLOW + box.ZL
+    box.CM = np.array([g["mass"] for g in groups]) * CP_AU2G
+    box.SYMB = [g["symb"] for g in groups]
+    box.NA = [g["natom"] for g in groups]
+    ng = box.NGROUP
+    box.PTYPE = np.array([row[:ng] for row in tables[:ng]], dtype=np.int32) if tables else np.ones((ng, ng), np.int32)
+    return box
+
+
+def read_ctrl_file(path, box):
+    """First time section of a &CTLF:GMD file -> SimMDCtrl (CGS)."""
+    c = SimMDCtrl()
+    ng = box.NGROUP
+    ru_lu = np.full((ng, ng), 0.0)
+    nb_fac = 1.2
+    temp = 0.0
+    epc = False
+    for s in _lines(path):
+        k = _kw(s)
+        if k == "BOXS":
+            c.MULTIBOX = int(_numbers(s[5:])[0])
+        elif k == "CUTOFF" and "NEIGH" not in s.upper() and not np.any(ru_lu):
+            v = _numbers(s[7:])
+            ru_lu[:] = v[0]
+            for i, x in enumerate(v[: ng * ng]):
+                ru_lu[i // ng, i % ng] = x
+        elif k == "CUTOFF":
+            nb_fac = _numbers(s[7:])[0]
+        elif k == "TABLESIZE":
+            v = _numbers(s[10:])
+            c.NUMFTABR = int(v[0])
+            c.NUMFTABE = int(v[1]) if len(v) > 1 else int(v[0])
+            if len(v) > 2:
+                c.RHOSCAL = v[2]
+        elif k == "TEMPERATURE":
+            temp = _numbers(s[12:])[0]
+        elif k == "E_P_COUPLE":
+            epc = True
+        elif k == "STEPSIZE":
+            v = _numbers(s[9:])
+            c.H = v[1] * CP_FS2S  # flag, hmi, hmx, dmx
+        elif k == "PERIDIC":
+            c.IFPD = np.array([int(x) for x in _numbers(s[8:])[:3]], dtype=np.int32)
+        elif k == "MAXNB":
+            c.NB_MXNBS = int(_numbers(s[6:])[0])
+        elif k == "UPDATEFRE":
+            c.NB_UPTAB = int(_numbers(s[10:])[0])
+    c.RU = ru_lu * box.RR
+    c.NB_RM = nb_fac * c.RU
+    c.LT_CTRL = [TiCtrlParam(TI=temp, METH_EPC=1 if epc else 0) for _ in range(ng)]
+    c.TEMP = temp
+    return c
+
+
+def read_config(path, box):
+    """Rows 'type x y z [vx vy vz ...]' in lattice units (positions) -> fills box.ITYP / XP (/XP1 = 0)."""
+    rows = []
+    started = False
+    header = False
+    with open(path) as f:
+        for raw in f:
+            s = raw.split("!")[0].strip()
+            if not s:
+                continue
+            if s.startswith("&"):
+                header = True
+                if s.upper().startswith("&TYPE"):
+                    started = True
+                continue
+            if header and not started:
+                continue
+            p = s.split()
+            try:
+                rows.append([float(x.replace("D", "e").replace("d", "e")) for x in p[:4]])
+            except ValueError:
+                continue
+    a = np.array(rows)
+    if a.shape[0] != box.NPRT:
+        raise ValueError("configuration holds %d atoms, the box file says %d" % (a.shape[0], box.NPRT))
+    box.ITYP = a[:, 0].astype(np.int32)
+    box.XP = a[:, 1:4] * box.RR
+    box.allocate()
+    return box

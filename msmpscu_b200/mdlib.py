@@ -1,0 +1,274 @@
+"""Host-side mirror of the reference's MDLIB interface for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the Fortran procedures the GMD / PARREP step loop
+calls (paths relative to the reference root, MDLIB/sor/ prefix dropped):
+
+    SimMDBox / SimMDCtrl                 Common/MD_TypeDef_SimBox.F90:43-132, MD_TypeDef_SimCtrlParam.F90:26-264
+    Initialize_Globle_Variables_DEV      CommonGPU/MD_Globle_Variables_GPU.F90:585
+    Register_ForceClass / MDForceClassGPU  CommonGPU/MD_ForceClass_Register_GPU.F90:248-259,363-442
+    Init_Forcetable_Dev                  :483-559
+    Initialize_NeighboreList_DEV, Cal_NeighBoreList_DEV, Copyout_NeighboreList_DEV   CommonGPU/MD_NeighborsList_GPU.F90
+    CalForce_ForceClass, CalPTensor_ForceClass, CalEpot_ForceClass   MD_ForceClass_Register_GPU.F90:636-704
+    Predictor_DEV, Correction_DEV, CalEKin_DEV    CommonGPU/MD_DiffScheme_GPU.F90:604,821,1000
+    Do_ResetParam_DEV, Do_EPCForce_DEV   LocalTempCtrlMeths/MD_LocalTempMethod_GPU.F90:95-138
+    CopyOut_SimBox_DEV                   CommonGPU/MD_SimBoxArray_GPU.F90:202-318
+    For_One_Step                         Appshell/MD_Method_GenericMD_GPU.F90:496-659
+
+The reference keeps one module-level device state per process; here that state is the `DeviceState`
+object (one per GPU / rank).  Errors are exceptions carrying the ABI status code instead of `stop`.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi, forcetable
+from .constants import (CP_A2CM, CP_AU2G, CP_EVERG, CP_FS2S, CP_KB, CP_PS2S, CP_STATU_ACTIVE)
+
+
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class SimMDBox:
+    """The fields of type(SimMDBox) the hot path reads.  Arrays are (NPRT,3) / (NPRT,), CGS units."""
+    NPRT: int = 0
+    NGROUP: int = 1
+    RR: float = 0.0                      # lattice unit in cm
+    ZL: np.ndarray = None                # box size (3)
+    BOXLOW: np.ndarray = None
+    BOXUP: np.ndarray = None
+    BOXSHAPE: np.ndarray = field(default_factory=lambda: np.eye(3))
+    CM: np.ndarray = None                # mass per group (g)
+    SYMB: list = field(default_factory=list)
+    PTYPE: np.ndarray = None             # (NGROUP,NGROUP) interaction-table ids
+    PotType: str = "EAM_TYPE"
+    PotLibname: str = ""
+    PotSubLibname: str = ""
+    ITYP: np.ndarray = None
+    XP: np.ndarray = None
+    XP1: np.ndarray = None
+    FP: np.ndarray = None
+    DIS: np.ndarray = None
+    EPOT: np.ndarray = None
+    EKIN: np.ndarray = None
+    STATU: np.ndarray = None
+    VTENSOR: np.ndarray = field(default_factory=lambda: np.zeros((3, 3)))
+
+    def allocate(self):
+        n = self.NPRT
+        for name in ("XP", "XP1", "FP", "DIS"):
+            if getattr(self, name) is None:
+                setattr(self, name, np.zeros((n, 3)))
+        for name in ("EPOT", "EKIN"):
+            if getattr(self, name) is None:
+                setattr(self, name, np.zeros(n))
+        if self.STATU is None:
+            self.STATU = np.full(n, CP_STATU_ACTIVE, dtype=np.int32)
+        if self.ITYP is None:
+            self.ITYP = np.ones(n, dtype=np.int32)
+
+
+@dataclass
+class TiCtrlParam:
+    """Common/MD_TypeDef_EPCCtrl.F90:27-37 defaults."""
+    TI: float = 0.0
+    METH_EPC: int = 0
+    EPC_HE: float = 100.0 * CP_EVERG
+    EPC_ALPHA: float = 1.0 * CP_PS2S
+    EPC_CUT: float = 0.1
+
+
+@dataclass
+class SimMDCtrl:
+    """The fields of type(SimMDCtrl) the hot path reads (already converted to CGS)."""
+    MULTIBOX: int = 1
+    IFPD: np.ndarray = field(default_factory=lambda: np.ones(3, dtype=np.int32))
+    RU: np.ndarray = None                # (NGROUP,NGROUP) force cut-offs, cm
+    NB_RM: np.ndarray = None             # (NGROUP,NGROUP) list cut-offs, cm
+    NB_MXNBS: int = 256
+    NB_UPTAB: int = 10
+    IT0: int = 1
+    H: float = 0.5 * CP_FS2S
+    NUMFTABR: int = 10000
+    NUMFTABE: int = 10000
+    RHOSCAL: float = 20.0
+    LT_CTRL: list = field(default_factory=list)
+
+
+class MDPSCUError(RuntimeError):
+    """Raised where the reference prints 'MDPSCU Error: ...' and stops."""
+
+
+# ----------------------------------------------------------------------------------------------
+class MDForceClassGPU:
+    """type(MDForceClassGPU): eight procedure slots filled by Register_ForceClass."""
+    SLOTS = ("pIniForcetable", "pClrForcetable", "pCalForce", "pCalEpot0", "pCalEpot", "pCalEDen", "pCalPTensor",
+             "pCalAVStress")
+
+    def __init__(self):
+        for s in self.SLOTS:
+            setattr(self, s, None)
+        self.ExtForces = []  # AddExtForce_ForceClass list (boost, springs): not on the hot path
+        self.PotType = ""
+
+
+class DeviceState:
+    """The reference's module-level singletons (dm_WorkSpace, dm_Neighbors, dm_FTableWS) for one GPU."""
+
+    def __init__(self, device=0):
+        self.ctx = capi.Context(device)
+        self.SimBox = None
+        self.nbox = 1
+        self.ForceClass = None
+        self.FTable = None
+
+
+gm_ForceClass = MDForceClassGPU()
+
+
+def Initialize_Globle_Variables_DEV(dev: DeviceState, SimBox, CtrlParam: SimMDCtrl):
+    """SimBox may be one box or a list of MULTIBOX identical-size boxes (concatenated on the device)."""
+    boxes = SimBox if isinstance(SimBox, (list, tuple)) else [SimBox]
+    b0 = boxes[0]
+    for b in boxes:
+        if b.NPRT != b0.NPRT:
+            raise MDPSCUError("MDPSCU Error: boxes of one run must hold the same number of particles")
+    dev.SimBox, dev.nbox = boxes, len(boxes)
+    dev.ctx.box_set(len(boxes), b0.NPRT, b0.BOXLOW, b0.ZL, CtrlParam.IFPD, b0.CM, boxshape=b0.BOXSHAPE)
+    CopyIn_SimBox_DEV(dev, boxes)
+
+
+def CopyIn_SimBox_DEV(dev, boxes):
+    cat = lambda name: np.concatenate([getattr(b, name) for b in boxes])
+    dev.ctx.upload(capi.F_XP, cat("XP"))
+    dev.ctx.upload(capi.F_XP1, cat("XP1"))
+    dev.ctx.upload(capi.F_DIS, cat("DIS"))
+    dev.ctx.upload(capi.F_FP, cat("FP"))
+    dev.ctx.upload(capi.F_ITYP, cat("ITYP"))
+    dev.ctx.upload(capi.F_STATU, cat("STATU"))
+
+
+def CopyOut_SimBox_DEV(dev, boxes=None):
+    """Un-permutes through GIDINV into the SimBox order (MD_SimBoxArray_GPU.F90:202-238)."""
+    boxes = boxes or dev.SimBox
+    n = boxes[0].NPRT
+    for name, f in (("XP", capi.F_XP), ("XP1", capi.F_XP1), ("FP", capi.F_FP), ("DIS", capi.F_DIS), ("EPOT", capi.F_EPOT),
+                    ("EKIN", capi.F_EKIN), ("STATU", capi.F_STATU)):
+        a = dev.ctx.download(f, capi.ORDER_ORIGINAL)
+        for i, b in enumerate(boxes):
+            setattr(b, name, a[i * n:(i + 1) * n].copy())
+
+
+def Register_ForceClass(pottype: str, ForceClass: MDForceClassGPU = gm_ForceClass):
+    """Fills the slots for "EAM_TYPE" or "FS_TYPE" (MD_ForceClass_Register_GPU.F90:363-442)."""
+    if pottype not in ("EAM_TYPE", "FS_TYPE"):
+        raise MDPSCUError("MDPSCU Error: the potential type %s is not supported" % pottype)
+    fc = ForceClass
+    fc.PotType = pottype
+
+    def ini(dev, SimBox, CtrlParam, FTable):
+        dev.ctx.tables_set(FTable, float(np.max(CtrlParam.RU)) ** 2)
+        dev.FTable = FTable
+
+    fc.pIniForcetable = ini
+    fc.pClrForcetable = lambda dev: dev.ctx.tables_clear()
+    fc.pCalForce = lambda dev, SimBox, CtrlParam: dev.ctx.force(capi.FORCE)
+    fc.pCalEpot0 = lambda dev, SimBox, CtrlParam: dev.ctx.force(capi.EPOT)
+
+    def epot(dev, SimBox, CtrlParam):
+        dev.ctx.force(capi.EPOT)
+        return dev.ctx.download(capi.F_EPOT, capi.ORDER_ORIGINAL)
+
+    fc.pCalEpot = epot
+    fc.pCalEDen = lambda dev, SimBox, CtrlParam: dev.ctx.force(capi.DEN)
+
+    def ptensor(dev, SimBox, CtrlParam):
+        vt = dev.ctx.force(capi.FORCE | capi.VIRIAL)
+        for b in (dev.SimBox or []):
+            b.VTENSOR = vt.copy()
+        return vt
+
+    fc.pCalPTensor = ptensor
+    fc.pCalAVStress = None  # atomic stress: analysis, a "next" row
+    return fc
+
+
+def Init_Forcetable_Dev(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, FTable=None):
+    if ForceClass.pIniForcetable is None:
+        raise MDPSCUError("MDPSCU Error: force class is not registered")
+    b0 = SimBox[0] if isinstance(SimBox, (list, tuple)) else SimBox
+    FTable = FTable or forcetable.Register_Interaction_Table(b0, CtrlParam)
+    ForceClass.pIniForcetable(dev, SimBox, CtrlParam, FTable)
+    dev.ForceClass = ForceClass
+    return FTable
+
+
+def Initialize_NeighboreList_DEV(dev, SimBox, CtrlParam):
+    dev.ctx.nlist_init(CtrlParam.NB_RM, CtrlParam.NB_MXNBS)
+
+
+def Cal_NeighBoreList_DEV(dev, SimBox, CtrlParam):
+    """Returns the number of atoms found out of the box (the reference warns / prompts)."""
+    return dev.ctx.nlist_build()
+
+
+def Copyout_NeighboreList_DEV(dev, order=capi.ORDER_ORIGINAL):
+    return dev.ctx.nlist_copyout(order)
+
+
+def CalForce_ForceClass(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass):
+    ForceClass.pCalForce(dev, SimBox, CtrlParam)
+
+
+def CalPTensor_ForceClass(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass):
+    return ForceClass.pCalPTensor(dev, SimBox, CtrlParam)
+
+
+def CalEpot_ForceClass(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass):
+    return ForceClass.pCalEpot(dev, SimBox, CtrlParam)
+
+
+def Predictor_DEV(dev, ITIME, SimBox, CtrlParam):
+    dev.ctx.predict(CtrlParam.H)
+
+
+def Correction_DEV(dev, ITIME, SimBox, CtrlParam):
+    dev.ctx.correct(CtrlParam.H)
+
+
+def CalEKin_DEV(dev, SimBox, CtrlParam):
+    dev.ctx.ekin()
+    return dev.ctx.download(capi.F_EKIN, capi.ORDER_ORIGINAL)
+
+
+def Do_ResetParam_DEV(dev, SimBox, CtrlParam):
+    b0 = SimBox[0] if isinstance(SimBox, (list, tuple)) else SimBox
+    lt = CtrlParam.LT_CTRL or [TiCtrlParam() for _ in range(b0.NGROUP)]
+    dev.ctx.epc_set([t.METH_EPC for t in lt], [t.TI for t in lt], [t.EPC_ALPHA for t in lt], [t.EPC_CUT for t in lt],
+                    [t.EPC_HE for t in lt])
+
+
+def Do_EPCForce_DEV(dev, SimBox, CtrlParam):
+    dev.ctx.epc_apply()
+
+
+def For_One_Step(dev, ITIME, SimBox, CtrlParam, ForceClass=gm_ForceClass):
+    """One GMD step with the reference's call sequence (each call is one C-ABI entry point)."""
+    Predictor_DEV(dev, ITIME, SimBox, CtrlParam)
+    if (ITIME - CtrlParam.IT0) % CtrlParam.NB_UPTAB == 0:
+        Cal_NeighBoreList_DEV(dev, SimBox, CtrlParam)
+    CalForce_ForceClass(dev, SimBox, CtrlParam, ForceClass)
+    Do_EPCForce_DEV(dev, SimBox, CtrlParam)
+    Correction_DEV(dev, ITIME, SimBox, CtrlParam)
+
+
+def For_Steps(dev, ITIME0, nsteps, SimBox, CtrlParam):
+    """The same sequence for nsteps steps inside the library (mdb_run): no host round trip per step."""
+    return dev.ctx.run(ITIME0, nsteps, CtrlParam.IT0, CtrlParam.NB_UPTAB, CtrlParam.H)
+
+
+def Cal_thermal_quantities(SimBox):
+    """T, cohesive energy, Hamiltonian per atom (Common/MD_TypeDef_SimBox.F90:5048-5170)."""
+    act = (SimBox.STATU & CP_STATU_ACTIVE) == CP_STATU_ACTIVE
+    ek = SimBox.EKIN[act & (SimBox.EKIN > -1e31)]
+    n = int(act.sum())
+    return dict(TEMP=2.0 * ek.sum() / (3.0 * CP_KB * max(len(ek), 1)), AVEPOT=SimBox.EPOT[act].sum() / max(n, 1),
+                HARMIL=(SimBox.EPOT[act].sum() + ek.sum()) / max(n, 1))

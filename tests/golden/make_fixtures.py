@@ -53,6 +53,11 @@ def main():
     with open(os.path.join(neb, "GMD", "thermP0000_0001")) as f:
         open(os.path.join(HERE, "neb_gmd_therm.txt"), "w").write(f.read())
 
+    # the reference's own CPU-runnable example (BASELINE.json configs[0]): inputs only
+    gmd = os.path.join(REF, "examples", "GMD_Test")
+    for fn in ("W_2000_He1_EAM1_box.dat", "CtrlFile300K.dat", "W_2000_Tetra.cfg"):
+        shutil.copyfile(os.path.join(gmd, fn), os.path.join(HERE, "gmd_" + fn))
+
     # exported embedding table (10 significant digits)
     path = os.path.join(REF, "examples", "use_ForceTableGen", "EAM_WHeH_Bonny_JPCM26_2014.embd")
     rows = []

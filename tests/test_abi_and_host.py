@@ -1,0 +1,79 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/mdpscu_b200.h declares,
+refuses to run without a GPU (no CPU fallback), and its host-side table generator matches the oracle bit for bit."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import util
+from msmpscu_b200 import capi, forcetable
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mdpscu_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    names = _declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), "libmdpscu_b200.so does not export %s" % n
+    # and the python binding table covers the header
+    assert set(names) == set(capi.SYMBOLS)
+    assert lib.mdb_version().decode().startswith("mdpscu_b200")
+
+
+def test_header_is_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "mdpscu_b200.h"\nint main(void){ mdb_ctx *c = 0; (void)c; return MDB_OK; }\n')
+    import subprocess
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                           "-o", str(tmp_path / "t.o")])
+
+
+@pytest.mark.skipif(capi.load().mdb_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(capi.MDBError) as e:
+        capi.Context(0)
+    assert e.value.code == capi.ERR_NOGPU
+
+
+def test_product_tables_equal_oracle_tables(oracle):
+    """Two independent implementations of Create_Interaction_ForceTable (C oracle, C++ product)."""
+    for c in (util.bcc_case((4, 4, 4)), util.neb_case("react")):
+        t = util.product_tables(c)
+        o = util.oracle_tables(oracle, c)
+        assert (t.nkind, t.nkind1, t.csi, t.rhod) == (o.nkind, o.nkind1, o.csi, o.rhod)
+        assert np.array_equal(t.kpair, o.kpair) and np.array_equal(t.kembd, o.kembd)
+        for name in ("potr", "fpotr", "potb", "fpotb", "fembd", "dfembd"):
+            assert np.array_equal(getattr(t, name), getattr(o, name)), name
+
+
+def test_table_grid_definition():
+    """r_i = (i*sqrt(Rmax)/NTAB)^2, POTR = V/2*r, FPOTR = -V'*r, POTB = rho, FPOTB = -rho'
+    (MD_TypeDef_ForceTable.F90:949-976): spot-check the grid against direct evaluation."""
+    c = util.bcc_case((4, 4, 4))
+    t = util.product_tables(c)
+    potb = t.as_2d("potb")[0]
+    csiv = 1.0 / t.csi
+    i = 8000
+    r = (i * csiv) ** 2
+    # Marinica rho: sum b_k (rho_k - r)^3 H(rho_k - r), knots as float32 literals
+    b = [-0.420429107805055e1, 0.518217702261442e0, 0.562720834534370e-1, 0.344164178842340e-1]
+    rk = [float(np.float32(v)) for v in (2.5, 3.1, 3.5, 4.9)]
+    ra = r * 1e8
+    want = sum(bk * (k - ra) ** 3 for bk, k in zip(b, rk) if k - ra >= 0)
+    assert abs(potb[i - 1] - want) <= 4e-16 * abs(want)
+    assert t.rhod == pytest.approx(potb.max() * 20.0 / t.nembd, rel=1e-15)
+
+
+def test_unknown_potential_id_is_an_error_code():
+    with pytest.raises(capi.MDBError):
+        forcetable.Create_Interaction_ForceTable(capi.LIB_MARINICA_EAM2, [[7]], 100, 100, 6e-8)

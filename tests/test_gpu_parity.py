@@ -252,3 +252,50 @@ def test_errors_are_status_codes_not_stops():
     with pytest.raises(capi.MDBError):
         ctx.force(capi.FORCE)
     ctx.close()
+
+
+def test_gmd_example_inputs_through_the_mdlib_interface(oracle):
+    """examples/GMD_Test (BASELINE configs[0] family): box, control and configuration files as shipped
+    (2000 W + 1 He, Bonny EAM1, 300 K control file), driven through the reference's own call sequence
+    (Initialize_Globle_Variables_DEV -> Register_ForceClass -> Init_Forcetable_Dev ->
+    Initialize_NeighboreList_DEV -> Cal_NeighBoreList_DEV -> For_One_Step ...) and compared with the oracle."""
+    import os
+    from msmpscu_b200 import inputs, mdlib
+    g = util.GOLD
+    box = inputs.read_box_file(os.path.join(g, "gmd_W_2000_He1_EAM1_box.dat"))
+    ctl = inputs.read_ctrl_file(os.path.join(g, "gmd_CtrlFile300K.dat"), box)
+    inputs.read_config(os.path.join(g, "gmd_W_2000_Tetra.cfg"), box)
+    rng = np.random.default_rng(300)
+    box.XP1 = rng.normal(0.0, 1.0, size=box.XP.shape) * np.sqrt(1.38054e-16 * 300.0 / box.CM[box.ITYP - 1])[:, None]
+    dev = mdlib.DeviceState(0)
+    fc = mdlib.Register_ForceClass(box.PotType)
+    mdlib.Initialize_Globle_Variables_DEV(dev, box, ctl)
+    ft = mdlib.Init_Forcetable_Dev(dev, box, ctl, fc)
+    mdlib.Initialize_NeighboreList_DEV(dev, box, ctl)
+    assert mdlib.Cal_NeighBoreList_DEV(dev, box, ctl) == 0
+    mdlib.CalForce_ForceClass(dev, box, ctl, fc)
+    # oracle with the same tables / list rule
+    T = oracle.Tables(oracle.LIB_BONNY_EAM1, box.PTYPE, ctl.NUMFTABR, ctl.NUMFTABE, float(ctl.RU.max()))
+    md = oracle.MD(1, box.NPRT, box.XP, box.XP1, box.ITYP, box.STATU, box.CM, box.BOXLOW, box.ZL, ctl.IFPD,
+                   np.ascontiguousarray(ctl.NB_RM.T).ravel(), ctl.NB_MXNBS, T)
+    md.rebuild(); md.force()
+    for name in ("potr", "fpotb", "dfembd"):
+        assert np.array_equal(getattr(ft, name), getattr(T, name))
+    for it in range(12):
+        mdlib.For_One_Step(dev, it, box, ctl, fc)
+        md.step(it, ctl.IT0, ctl.NB_UPTAB, ctl.H)
+    mdlib.CalEpot_ForceClass(dev, box, ctl, fc)
+    mdlib.CalEKin_DEV(dev, box, ctl)
+    mdlib.CopyOut_SimBox_DEV(dev)
+    md.epot()
+    ref = md.get()
+    assert util.relerr(box.XP, ref["xp"]) < 1e-12
+    assert util.relerr(box.FP, ref["fp"]) < FORCE_RTOL
+    assert util.relerr(box.EPOT, ref["epot"]) < FORCE_RTOL
+    th = mdlib.Cal_thermal_quantities(box)
+    ham_ref = (ref["epot"].sum() + ref["ekin"].sum()) / box.NPRT
+    assert abs(th["HARMIL"] - ham_ref) < 1e-10 * abs(ham_ref)
+    vt = mdlib.CalPTensor_ForceClass(dev, box, ctl, fc)
+    md.force(virial=True)
+    assert util.relerr(vt, md.get()["vtensor"]) < FORCE_RTOL
+    dev.ctx.close()
