@@ -107,139 +107,174 @@ struct TileListArgs {
 };
 
 #define NL_THREADS 128
+#define NL_WARPS (NL_THREADS / 32)
 
-// One CTA per tile, one warp per owned cell (lanes = atoms of the cell), so every lane of a warp walks
-// the same 27-cell candidate stream: shared-memory reads are broadcasts and there is no divergence in
-// the scan.  Accepted neighbours go to the reference-format INDI (global ids, reference order) and,
-// tagged with their distance class, to a scratch list in global memory ([k][atom], coalesced); the
-// lane then partitions its own scratch list by class into the lane-interleaved layout the passes
-// stream (nbl_index).  Tails are padded with slot 0 so every 4-entry group a lane can touch is valid.
+// tile descriptors: one small CTA per tile
+__global__ void __launch_bounds__(NL_THREADS)
+k_tile_desc(TileParams P, const int *__restrict__ nac, const int *__restrict__ ia1th, TileDesc *__restrict__ desc,
+            int *__restrict__ counters)
+{
+    __shared__ TileDesc H;
+    const int tile = blockIdx.x;
+    const TileGeom g = tile_geom(P, tile);
+    build_halo_table(P, g, nac, ia1th, H);
+    const int *src = reinterpret_cast<const int *>(&H);
+    int *dst = reinterpret_cast<int *>(desc + tile);
+    for (int i = threadIdx.x; i < (int)(sizeof(TileDesc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    // a halo that does not fit the shared-memory budget of the passes: the host falls back to the generic path
+    if (threadIdx.x == 0 && H.htot > P.hcap) atomicAdd(&counters[CNT_TILE_OVERFLOW], 1);
+}
+
+// One warp per cell (lanes = atoms of the cell), no block-level synchronisation: every lane of the warp walks
+// the same 27-cell candidate stream, staged 32 at a time in a warp-private tile as
+// SPOS = (float)(XP + (double)(float)shift) (:1100-1103).  Accepted neighbours go to the reference-format INDI
+// (global ids, reference order) and, as halo SLOTS of the cell's tile tagged with their distance class, to a
+// scratch list ([k][atom], coalesced); the lane then partitions its own scratch list by class into the
+// lane-interleaved layout the passes stream (nbl_index).  Tails are padded with slot 0.
 template <int G>
 __global__ void __launch_bounds__(NL_THREADS)
 k_tile_nlist(TileParams P, TileListArgs A)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    TileDesc &H = *reinterpret_cast<TileDesc *>(smem);
-    float4 *spos = reinterpret_cast<float4 *>(smem + ((sizeof(TileDesc) + 15) & ~15));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __shared__ float4 tile_s[NL_WARPS][32];
+    __shared__ unsigned short stage[4 * G][NL_THREADS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int ic0 = blockIdx.x * NL_WARPS + wib;               // global cell id (0-based)
+    if (ic0 >= P.nbox * P.nc0) return;
+    if (A.naac[ic0] <= 0) return;                              // cells without ACTIVE atoms are skipped (:981-982)
+    const int ccnt = A.nac[ic0];
+    if (ccnt <= 0) return;                                     // :1018
+    // which tile / which cell of the tile
+    const int box = ic0 / P.nc0, icl = ic0 - box * P.nc0;
+    const int ncxy = P.ncx * P.ncy;
+    const int iz = icl / ncxy, iy = (icl - iz * ncxy) / P.ncx, ix = icl - iz * ncxy - iy * P.ncx;
+    const int tx = ((ix + 1) * P.ntx + P.ncx - 1) / P.ncx - 1;
+    const int tileid = ((box * P.ncz + iz) * P.ncy + iy) * P.ntx + tx;
+    const TileDesc &D = A.desc[tileid];
+    if (D.htot > P.hcap) return;
+    const int cx0 = (int)(((long long)tx * P.ncx) / P.ntx);
+    const int nhx = (int)(((long long)(tx + 1) * P.ncx) / P.ntx) - cx0 + 2;
+    const int hxc = ix - cx0 + 1;
+    const int myhc = (1 * 3 + 1) * nhx + hxc;
+    const int cgst = A.ia1th[ic0] - 1, csl = D.slot[myhc];
+    const float rm1 = A.rm2[0], rc0 = A.rc2[0], rc1 = A.rc2[1];
+    float4 *tl = tile_s[wib];
 
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        const TileGeom g = tile_geom(P, tile);
-        __syncthreads(); // previous tile fully consumed
-        build_halo_table(P, g, A.nac, A.ia1th, H);
-        { // publish the descriptor for the force passes
-            const int *src = reinterpret_cast<const int *>(&H);
-            int *dst = reinterpret_cast<int *>(A.desc + tile);
-            for (int i = threadIdx.x; i < (int)(sizeof(TileDesc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    for (int ab = 0; ab < ccnt; ab += 32) {
+        const bool valid = ab + lane < ccnt;
+        const int ia = cgst + ab + lane;
+        const int myslot = csl + ab + (valid ? lane : 0);
+        float4 me = make_float4(0.f, 0.f, 0.f, __int_as_float(1));
+        if (valid) {
+            const double4 p = A.pos[ia];
+            me = make_float4(__double2float_rn(p.x), __double2float_rn(p.y), __double2float_rn(p.z),
+                             __int_as_float(A.ityp[ia]));  // POS = (float)XP_i :1080-1082
         }
-        const int htot = H.htot;
-        if (htot > P.hcap) { // halo does not fit the shared-memory budget: the host falls back to the generic path
-            if (threadIdx.x == 0) atomicAdd(&A.counters[CNT_TILE_OVERFLOW], 1);
-            continue;
-        }
-        // stage SPOS = (float)(XP + (double)(float)shift) and the type  (:1100-1103)
-        for (int hc = warp; hc < g.nhc; hc += nwarps) {
-            const int cnt = H.cnt[hc], gst = H.gst[hc], sl = H.slot[hc];
-            const float s0 = H.sh[hc][0] * P.fbs[0], s1 = H.sh[hc][1] * P.fbs[1], s2 = H.sh[hc][2] * P.fbs[2];
-            for (int a = lane; a < cnt; a += 32) {
-                const double4 q = A.pos[gst + a];
-                float4 s;
-                s.x = __double2float_rn(__dadd_rn(q.x, (double)s0));
-                s.y = __double2float_rn(__dadd_rn(q.y, (double)s1));
-                s.z = __double2float_rn(__dadd_rn(q.z, (double)s2));
-                s.w = __int_as_float(A.ityp[gst + a]);
-                spos[sl + a] = s;
-            }
-        }
-        __syncthreads();
-        const int hc_own0 = (1 * 3 + 1) * g.nhx + 1;
-        for (int hxc = 1 + warp; hxc <= g.wt; hxc += nwarps) {        // owned cells of the tile
-            const int myhc = hc_own0 + hxc - 1;
-            if (A.naac[H.cid[myhc]] <= 0) continue;                   // cells without ACTIVE atoms are skipped (:981-982)
-            const int csl = H.slot[myhc], ccnt = H.cnt[myhc], cgst = H.gst[myhc];
-            for (int ab = 0; ab < ccnt; ab += 32) {
-                const bool valid = ab + lane < ccnt;
-                const int myslot = csl + ab + (valid ? lane : 0);
-                const int ia = cgst + ab + lane;
-                const float4 me = spos[myslot];                       // own cell is never shifted: (float)XP_i
-                const int ity = __float_as_int(me.w);
-                int nn = 0, n0 = 0, n1 = 0;
-                int *pI = A.indi + ia;                 // next INDI / scratch entry of this atom (stride N per entry)
-                unsigned short *pR = A.raw + ia;
-                const int room = valid ? P.mxkvois : 0;
-                const float rm1 = A.rm2[0], rc0 = A.rc2[0], rc1 = A.rc2[1];
-                for (int k = 0; k < 27; k++) {
-                    const int hc = ((1 + t_niz[k]) * 3 + (1 + t_niy[k])) * g.nhx + (hxc + t_nix[k]);
-                    if (H.cid[hc] < 0) continue;
-                    const int sl = H.slot[hc], cnt = H.cnt[hc], gst1 = H.gst[hc] + 1 - sl;
-                    // scan 32 candidates at a time into a per-lane acceptance mask (no branch per candidate),
-                    // then emit the set bits in ascending order: the list order stays the reference's
-                    for (int cb = sl; cb < sl + cnt; cb += 32) {
-                        const int nb = min(32, sl + cnt - cb);
-                        unsigned mask = 0u;
+        const int ity = __float_as_int(me.w);
+        int nn = 0, n0 = 0, n1 = 0;
+        int *pI = A.indi + ia;                 // next INDI / scratch entry of this atom (stride N per entry)
+        unsigned short *pR = A.raw + ia;
+        const int room = valid ? P.mxkvois : 0;
+        for (int k = 0; k < 27; k++) {
+            const int hc = ((1 + t_niz[k]) * 3 + (1 + t_niy[k])) * nhx + (hxc + t_nix[k]);
+            if (D.cid[hc] < 0) continue;
+            const int sl = D.slot[hc], cnt = D.cnt[hc], gst = D.gst[hc];
+            const float s0 = D.sh[hc][0] * P.fbs[0], s1 = D.sh[hc][1] * P.fbs[1], s2 = D.sh[hc][2] * P.fbs[2];
+            for (int cb = 0; cb < cnt; cb += 32) {
+                const int nb = min(32, cnt - cb);
+                if (lane < nb) {
+                    const double4 q = A.pos[gst + cb + lane];
+                    float4 s;
+                    s.x = __double2float_rn(__dadd_rn(q.x, (double)s0));
+                    s.y = __double2float_rn(__dadd_rn(q.y, (double)s1));
+                    s.z = __double2float_rn(__dadd_rn(q.z, (double)s2));
+                    s.w = __int_as_float(A.ityp[gst + cb + lane]);
+                    tl[lane] = s;
+                }
+                __syncwarp();
+                // acceptance mask over the 32 staged candidates (no branch per candidate) ...
+                unsigned mask = 0u;
 #pragma unroll 4
-                        for (int t = 0; t < nb; t++) {
-                            const float4 s = spos[cb + t];
+                for (int t = 0; t < nb; t++) {
+                    const float4 s = tl[t];
+                    const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
+                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
+                    const float rm = (P.ng == 1) ? rm1 : A.rm2[(ity - 1) + P.ng * (__float_as_int(s.w) - 1)];
+                    mask |= (unsigned)(r2 <= rm) << t; // :1123
+                }
+                const int selfbit = myslot - (sl + cb);
+                if ((unsigned)selfbit < 32u) mask &= ~(1u << selfbit); // I .ne. IA :1124
+                // ... then the set bits are emitted in ascending order: the list order stays the reference's
+                while (__any_sync(0xffffffffu, mask != 0u)) {
+                    if (mask) {
+                        const int t = __ffs(mask) - 1;
+                        mask &= mask - 1u;
+                        if (nn < room) {
+                            const float4 s = tl[t];
                             const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
                             const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
-                            const float rm = (P.ng == 1) ? rm1 : A.rm2[(ity - 1) + P.ng * (__float_as_int(s.w) - 1)];
-                            mask |= (unsigned)(r2 <= rm) << t; // :1123
+                            *pI = gst + cb + t + 1;
+                            const unsigned c0 = r2 <= rc0, c1 = r2 <= rc1;
+                            n0 += c0; n1 += c1;
+                            *pR = (unsigned short)((unsigned)(sl + cb + t) | ((2u - c0 - c1) << 14));
+                            pI += P.n; pR += P.n;
                         }
-                        if ((unsigned)(myslot - cb) < 32u) mask &= ~(1u << (myslot - cb)); // I .ne. IA :1124
-                        while (__any_sync(0xffffffffu, mask != 0u)) {
-                            if (mask) {
-                                const int t = __ffs(mask) - 1;
-                                mask &= mask - 1u;
-                                const int s_ = cb + t;
-                                if (nn < room) {
-                                    const float4 s = spos[s_];
-                                    const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
-                                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
-                                    *pI = gst1 + s_;
-                                    const unsigned c0 = r2 <= rc0, c1 = r2 <= rc1;
-                                    n0 += c0; n1 += c1;
-                                    *pR = (unsigned short)((unsigned)s_ | ((2u - c0 - c1) << 14));
-                                    pI += P.n; pR += P.n;
-                                }
-                                nn++;
-                            }
-                        }
+                        nn++;
                     }
                 }
-                if (!valid) continue;
-                const int kv = min(nn, P.mxkvois);
-                A.kvois[ia] = kv; // silently truncated :1195
-                if (nn > P.mxkvois) atomicAdd(&A.counters[CNT_OVERFLOW], 1);
-                atomicMax(&A.counters[CNT_NNMAX], nn);
-                // class-ordered, lane-interleaved slot list (the scratch entries were written by this lane)
-                n1 -= n0; // n0 = class 0, n1 = class 1
-                int p0 = 0, p1 = n0, p2 = n0 + n1;
-                int k = 0;
-                for (; k + 4 <= kv; k += 4) { // four independent loads in flight
-                    unsigned e[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) e[u] = A.raw[ia + (size_t)(k + u) * P.n];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const unsigned c = e[u] >> 14;
-                        int d;
-                        if (c == 0u) d = p0++; else if (c == 1u) d = p1++; else d = p2++;
-                        A.nbl[nbl_index<G>(P, (size_t)ia, d)] = (unsigned short)(e[u] & 0x3fffu);
-                    }
-                }
-                for (; k < kv; k++) {
-                    const unsigned e = A.raw[ia + (size_t)k * P.n];
-                    const unsigned c = e >> 14;
-                    int d;
-                    if (c == 0u) d = p0++; else if (c == 1u) d = p1++; else d = p2++;
-                    A.nbl[nbl_index<G>(P, (size_t)ia, d)] = (unsigned short)(e & 0x3fffu);
-                }
-                const int kend = min(((kv + 4 * G - 1) / (4 * G)) * (4 * G), P.nrow4 * 4 * G);
-                for (k = kv; k < kend; k++) A.nbl[nbl_index<G>(P, (size_t)ia, k)] = 0;
-                A.ncls[ia] = (unsigned short)n0;
-                A.ncls[ia + P.npad] = (unsigned short)(n0 + n1);
+                __syncwarp();
             }
         }
+        if (!valid) continue;
+        const int kv = min(nn, P.mxkvois);
+        A.kvois[ia] = kv; // silently truncated :1195
+        if (nn > P.mxkvois) atomicAdd(&A.counters[CNT_OVERFLOW], 1);
+        atomicMax(&A.counters[CNT_NNMAX], nn);
+        // class-ordered, lane-interleaved slot list: three sweeps over the lane's own scratch entries (one per
+        // class); 4G consecutive output entries form one contiguous 8G-byte block [gl][m%4] of the layout, so
+        // they are collected in a shared staging column and written with full 16-byte stores
+        n1 -= n0; // n0 = class 0, n1 = class 1
+        int pos = 0, dbase = 0;
+        auto flush = [&]() {
+            unsigned short blk[4 * G];
+#pragma unroll
+            for (int j = 0; j < 4 * G; j++) blk[(j % G) * 4 + j / G] = (j < pos) ? stage[j][threadIdx.x] : (unsigned short)0;
+            uint4 *dst = reinterpret_cast<uint4 *>(A.nbl + ((((size_t)(dbase / (4 * G)) * P.npad + (size_t)ia) * G) << 2));
+#pragma unroll
+            for (int v = 0; v < (4 * G) / 8; v++) {
+                uint4 w;
+                w.x = blk[8 * v] | ((unsigned)blk[8 * v + 1] << 16);
+                w.y = blk[8 * v + 2] | ((unsigned)blk[8 * v + 3] << 16);
+                w.z = blk[8 * v + 4] | ((unsigned)blk[8 * v + 5] << 16);
+                w.w = blk[8 * v + 6] | ((unsigned)blk[8 * v + 7] << 16);
+                dst[v] = w;
+            }
+            dbase += 4 * G;
+            pos = 0;
+        };
+        for (unsigned cls = 0; cls < 3u; cls++) {
+            int k = 0;
+            for (; k + 4 <= kv; k += 4) { // four independent loads in flight
+                unsigned e[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) e[u] = A.raw[ia + (size_t)(k + u) * P.n];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if ((e[u] >> 14) == cls) {
+                        stage[pos][threadIdx.x] = (unsigned short)(e[u] & 0x3fffu);
+                        if (++pos == 4 * G) flush();
+                    }
+            }
+            for (; k < kv; k++) {
+                const unsigned e = A.raw[ia + (size_t)k * P.n];
+                if ((e >> 14) == cls) {
+                    stage[pos][threadIdx.x] = (unsigned short)(e & 0x3fffu);
+                    if (++pos == 4 * G) flush();
+                }
+            }
+        }
+        if (pos > 0) flush(); // the tail block is padded with slot 0
+        A.ncls[ia] = (unsigned short)n0;
+        A.ncls[ia + P.npad] = (unsigned short)(n0 + n1);
     }
 }
 
@@ -791,12 +826,13 @@ static int launch_list(mdb_ctx *c)
     TiledState &S = c->tiled;
     TileListArgs A;
     A.pos = c->pos; A.ityp = c->ityp; A.nac = c->nac; A.naac = c->naac; A.ia1th = c->ia1th;
-    A.kvois = c->kvois; A.indi = c->indi; A.nbl = S.nbl; A.ncls = S.ncls; A.raw = S.raw; A.counters = c->counters; A.desc = (TileDesc *)S.desc;
+    A.kvois = c->kvois; A.indi = c->indi; A.nbl = S.nbl; A.ncls = S.ncls; A.raw = S.raw; A.counters = c->counters;
+    A.desc = (TileDesc *)S.desc;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
     A.rc2[0] = S.rc2f[0]; A.rc2[1] = S.rc2f[1];
-    CUDA_TRY(c, cudaFuncSetAttribute(k_tile_nlist<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
-    ProfScope ps(c, MDB_K_NLIST);
-    k_tile_nlist<G><<<S.grid_list, NL_THREADS, S.smem_list, c->stream>>>(S.P, A);
+    ProfScope ps(c, MDB_K_NLIST, 2);
+    k_tile_desc<<<S.P.ntiles, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters);
+    k_tile_nlist<G><<<cdiv(c->nc, NL_WARPS), NL_THREADS, 0, c->stream>>>(S.P, A);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
