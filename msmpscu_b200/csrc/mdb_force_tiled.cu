@@ -370,6 +370,12 @@ __device__ __forceinline__ unsigned filt(unsigned a, unsigned b, int r2int)
     return (unsigned)(__dp4a(d, d, 0) - r2int - 1) >> 31;
 }
 
+// rare out-of-line path: table row outside the shared-memory window, or a pair of kinds other than KPAIR(1,1)
+__device__ __noinline__ double lerp_slow(const double2 *__restrict__ t, int stride, int k, int kk, double dk)
+{
+    return lerp_g(t, stride, k, kk, dk);
+}
+
 // PASS 1: rho -> DEN.  PASS 2: forces.  G lanes per atom.  MT: more than one atom type.
 // The CTA runs as A.nparts independent partitions of TH = T/nparts threads, each with its own tile in
 // flight ("half" below is the partition index; the first version had two).
@@ -562,12 +568,20 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 if (mx == 0) break;
                 __syncwarp();
                 // ---------------- phase B: drain in lock-step, lane gl takes entries gl, gl+G, ...
+                // software-pipelined: the next entry's slot and staged record are fetched before the current
+                // entry's arithmetic, so only the table read sits on the dependent chain
                 const unsigned short *rq = gq + (size_t)gl * ngrp;
+                const size_t rqstep = (size_t)G * ngrp;
+                int s_nxt = (gl < gcnt) ? (int)*rq : myslot;
+                double4 p_nxt = s_pos[s_nxt];
 #pragma unroll 1
-                for (int e = gl; e - gl < mx; e += G, rq += (size_t)G * ngrp) {
+                for (int e = gl; e - gl < mx; e += G) {
                     const bool on = e < gcnt;
-                    const int s = on ? (int)*rq : myslot;
-                    const double4 pj = s_pos[s];
+                    const int s = s_nxt;
+                    const double4 pj = p_nxt;
+                    rq += rqstep;
+                    s_nxt = (e + G < gcnt) ? (int)*rq : myslot;
+                    p_nxt = s_pos[s_nxt];
                     const double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
                     const double r2 = fma(sz, sz, fma(sy, sy, sx * sx));
                     const bool in = on && (r2 <= A.r2eff); // rows beyond the table support interpolate to exactly 0
@@ -579,20 +593,18 @@ k_tile_pass(TileParams P, TilePassArgs A)
                     const int kk = __double2loint(tk);            // KK = int(SK)
                     const double dk = sk - (tk - 4503599627370496.0);
                     const unsigned rr = (unsigned)(kk - A.kmin);
-                    int k0 = A.kind0, k1 = A.kind0;
                     bool fast = in && rr < (unsigned)A.ktab;
+                    int tj = 0;
                     if (MT) {
-                        const int tj = (int)s_typ[s];
-                        k0 = A.kpair[ti + P.ng * tj];
-                        k1 = A.kpair[tj + P.ng * ti];
-                        fast = fast && k0 == A.kind0 && k1 == A.kind0;
+                        tj = (int)s_typ[s];
+                        fast = fast && A.kpair[ti + P.ng * tj] == A.kind0 && A.kpair[tj + P.ng * ti] == A.kind0;
                     }
                     const unsigned rs = fast ? rr : 0u;
                     if (PASS == 1) {
                         const double2 t0 = s_tab[rs];
                         double val = fma(dk, t0.y - t0.x, t0.x);
-                        if (__any_sync(0xffffffffu, in && !fast)) { // outside the staged window / other kinds: rare
-                            if (in && !fast) val = lerp_g(A.g_potb, A.ntab + 2, k0, kk, dk);
+                        if (__any_sync(0xffffffffu, in && !fast)) { // outside the staged window / other kinds: rare, out of line
+                            if (in && !fast) val = lerp_slow(A.g_potb, A.ntab + 2, MT ? A.kpair[ti + P.ng * tj] : A.kind0, kk, dk);
                         }
                         if (in) acc0 += val;
                     } else {
@@ -602,18 +614,18 @@ k_tile_pass(TileParams P, TilePassArgs A)
                         double fb1 = fb0;
                         if (__any_sync(0xffffffffu, in && !fast)) {
                             if (in && !fast) {
-                                fr = lerp_g(A.g_fpotr, A.ntab + 2, k0, kk, dk);
-                                fb0 = lerp_g(A.g_fpotb, A.ntab + 2, k0, kk, dk);
-                                fb1 = MT ? lerp_g(A.g_fpotb, A.ntab + 2, k1, kk, dk) : fb0;
+                                const int k0 = MT ? A.kpair[ti + P.ng * tj] : A.kind0, k1 = MT ? A.kpair[tj + P.ng * ti] : A.kind0;
+                                fr = lerp_slow(A.g_fpotr, A.ntab + 2, k0, kk, dk);
+                                fb0 = lerp_slow(A.g_fpotb, A.ntab + 2, k0, kk, dk);
+                                fb1 = MT ? lerp_slow(A.g_fpotb, A.ntab + 2, k1, kk, dk) : fb0;
                             }
                         }
                         // FORTOT = FPOTR/R2 + (FPOTB_ij*DEN_i + FPOTB_ji*DEN_j)/R     (:811-813)
-                        const double ft = y * fma(fr, y, fma(fb0, me.w, fb1 * pj.w));
-                        if (in) {
-                            acc0 = fma(ft, sx, acc0);
-                            acc1 = fma(ft, sy, acc1);
-                            acc2 = fma(ft, sz, acc2);
-                        }
+                        double ft = y * fma(fr, y, fma(fb0, me.w, fb1 * pj.w));
+                        ft = in ? ft : 0.0;
+                        acc0 = fma(ft, sx, acc0);
+                        acc1 = fma(ft, sy, acc1);
+                        acc2 = fma(ft, sz, acc2);
                     }
                 }
                 __syncwarp();
