@@ -178,7 +178,9 @@ int mdb_run(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double 
 #define MDB_OPT_TILED_LANES   1  /* lanes sharing one atom in the tiled kernels: 2, 4 (default) or 8            */
 #define MDB_OPT_TILED_CLASSES 2  /* 1 (default): scan only the distance classes a pass needs while safe; 0: all */
 #define MDB_OPT_ACTIVE_PATH   3  /* read-only: the path the last list build selected                            */
-#define MDB_OPT_TILED_PARTS   4  /* tiles in flight per SM (partitions of the pass CTA): 1..4, default 3          */
+#define MDB_OPT_TILED_PARTS   4  /* tiles in flight per SM (partitions of the pass CTA): 1..4, default 2          */
+#define MDB_OPT_FUSE_EPILOGUE 5  /* mdb_run on the tiled path: EPC friction + corrector inside the force-pass   */
+                                 /* epilogue (1) or as one separate element-wise kernel (0, default: faster)    */
 #define MDB_FORCE_PATH_AUTO    0
 #define MDB_FORCE_PATH_GENERIC 1
 #define MDB_FORCE_PATH_TILED   2

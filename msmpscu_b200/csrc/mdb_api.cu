@@ -165,6 +165,10 @@ extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
         c->tiled.nparts_opt = value; c->tiled.dirty = true; c->list_valid = false;
         return MDB_OK;
     }
+    if (option == MDB_OPT_FUSE_EPILOGUE && (value == 0 || value == 1)) {
+        c->opt_fuse_epilogue = value;
+        return MDB_OK;
+    }
     if (option == MDB_OPT_TILED_CLASSES && (value == 0 || value == 1)) {
         c->tiled.use_classes = value != 0;
         return MDB_OK;
@@ -183,6 +187,7 @@ extern "C" int mdb_get_option(const mdb_ctx *c, int option)
     if (option == MDB_OPT_FORCE_PATH) return c->opt_force_path;
     if (option == MDB_OPT_TILED_LANES) return c->tiled.G;
     if (option == MDB_OPT_TILED_PARTS) return c->tiled.nparts_opt;
+    if (option == MDB_OPT_FUSE_EPILOGUE) return c->opt_fuse_epilogue;
     if (option == MDB_OPT_TILED_CLASSES) return c->tiled.use_classes ? 1 : 0;
     if (option == MDB_OPT_ACTIVE_PATH) return c->tiled.active ? MDB_FORCE_PATH_TILED : MDB_FORCE_PATH_GENERIC;
     return MDB_ERR_ARG;

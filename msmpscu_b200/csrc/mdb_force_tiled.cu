@@ -295,6 +295,12 @@ struct TilePassArgs {
     int qcap;              // queue entries per atom
     int nparts;            // independent partitions of the CTA (tiles in flight per SM)
     float safe_d2;         // classes are valid while max |displacement since rebuild|^2 <= safe_d2
+    // fused epilogue of pass 2 (mdb_run): EPC friction on the fresh force, then the corrector half-kick
+    int fuse;              // bit 0: EPC, bit 1: corrector
+    double hs2;            // H/2
+    double *xp1;
+    EpcParams epc;
+    MassParams mass;
     int kpair[MDB_MXGROUP * MDB_MXGROUP];
     int kembd[MDB_MXGROUP];
 };
@@ -521,8 +527,12 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 nxt = make_uint2(0u, 0u);
                 if (kv > gl) nxt = __ldcs(reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl));
             }
-            const bool active = kv > 0 || (have && ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE));
+            const int stat = have ? A.statu[ia] : 0;
+            const bool active = (stat & ST_ACTIVE) == ST_ACTIVE;
             const int ti = MT ? (int)s_typ[myslot] : 0;
+            // fused epilogue: lane gl < 3 of the atom owns velocity/force component gl; its velocity is requested now
+            double vpre = 0.0;
+            if (PASS == 2 && A.fuse && active && gl < 3) vpre = A.xp1[ia + (size_t)gl * P.n];
 
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
             const int nm = (kv - gl + G - 1) / G;      // my entries are k = gl + G*m, m < nm
@@ -652,10 +662,34 @@ k_tile_pass(TileParams P, TilePassArgs A)
                         }
                     } else den0 = 0.0;
                     reinterpret_cast<double *>(A.pos + ia)[3] = den0;
-                } else {
+                } else if (!A.fuse) {
                     A.fp[ia] = acc0;
                     A.fp[ia + (size_t)P.n] = acc1;
                     A.fp[ia + 2 * (size_t)P.n] = acc2;
+                }
+            }
+            if (PASS == 2 && A.fuse) {
+                // EPC_MOD_KERNEL (MD_EP_Coupling_GPU.F90:468-490) + Correction_KERNEL (MD_DiffScheme_GPU.F90:735-753)
+                // on the fresh force; every lane of the group holds the reduced sums, lane d < 3 handles component d
+                const int l0 = (threadIdx.x & 31) & ~(G - 1);
+                const double vx = __shfl_sync(0xffffffffu, vpre, l0), vy = __shfl_sync(0xffffffffu, vpre, l0 + 1),
+                             vz = __shfl_sync(0xffffffffu, vpre, l0 + 2);
+                if (have && gl < 3) {
+                    double f = gl == 0 ? acc0 : (gl == 1 ? acc1 : acc2);
+                    if (active) {
+                        if ((A.fuse & 1) && A.epc.enable[ti] > 0) {
+                            const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+                            if (v2 <= A.epc.eup[ti]) {
+                                const double tm = __dmul_rn(v2, A.epc.v2ti[ti]);
+                                const double mu = __ddiv_rn(__dmul_rn(A.epc.epa[ti], __dsub_rn(tm, A.epc.te[ti])), fmax(tm, A.epc.tcut[ti]));
+                                f = __dsub_rn(f, __dmul_rn(mu, vpre));
+                            }
+                        }
+                        const int fixbits = (ST_FIXVELX << gl) | (ST_FIXPOSX << gl);
+                        if ((A.fuse & 2) && (stat & fixbits) == 0)
+                            A.xp1[ia + (size_t)gl * P.n] = __dadd_rn(vpre, __dmul_rn(A.hs2, __ddiv_rn(f, A.mass.cm[ti])));
+                    }
+                    A.fp[ia + (size_t)gl * P.n] = f;
                 }
             }
         }
@@ -860,7 +894,7 @@ int mdb_tiled_nlist(mdb_ctx *c)
 }
 
 template <int PASS, int G, bool MT>
-static int launch_pass(mdb_ctx *c)
+static int launch_pass(mdb_ctx *c, int fuse, double hs2)
 {
     TiledState &S = c->tiled;
     const TableSet &t = c->tab;
@@ -874,6 +908,8 @@ static int launch_pass(mdb_ctx *c)
     A.qcap = S.qcap[PASS - 1];
     A.nparts = S.nparts;
     A.safe_d2 = S.use_classes ? S.safe_d2 : -1.0f;
+    A.fuse = (PASS == 2) ? fuse : 0; A.hs2 = hs2; A.xp1 = c->xp1; A.epc = c->epc; A.mass = c->mass;
+    if (!c->epc.on) A.fuse &= ~1;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
     auto kern = k_tile_pass<PASS, G, MT>;
@@ -885,22 +921,23 @@ static int launch_pass(mdb_ctx *c)
 }
 
 template <int G>
-static int launch_force(mdb_ctx *c, unsigned flags)
+static int launch_force(mdb_ctx *c, unsigned flags, int fuse, double hs2)
 {
     const bool mt = c->ng > 1;
     int rc = MDB_OK;
-    if (flags & (MDB_FORCE | MDB_DEN)) rc = mt ? launch_pass<1, G, true>(c) : launch_pass<1, G, false>(c);
+    if (flags & (MDB_FORCE | MDB_DEN)) rc = mt ? launch_pass<1, G, true>(c, 0, 0.0) : launch_pass<1, G, false>(c, 0, 0.0);
     if (rc < 0) return rc;
-    if (flags & MDB_FORCE) rc = mt ? launch_pass<2, G, true>(c) : launch_pass<2, G, false>(c);
+    if (flags & MDB_FORCE) rc = mt ? launch_pass<2, G, true>(c, fuse, hs2) : launch_pass<2, G, false>(c, fuse, hs2);
     return rc;
 }
 
-int mdb_force_tiled(mdb_ctx *c, unsigned flags)
+// fuse: bit 0 = EPC friction, bit 1 = corrector half-kick with hs2 = H/2, applied in the epilogue of pass 2
+int mdb_force_tiled(mdb_ctx *c, unsigned flags, int fuse, double hs2)
 {
     switch (c->tiled.G) {
-    case 2: return launch_force<2>(c, flags);
-    case 4: return launch_force<4>(c, flags);
-    case 8: return launch_force<8>(c, flags);
+    case 2: return launch_force<2>(c, flags, fuse, hs2);
+    case 4: return launch_force<4>(c, flags, fuse, hs2);
+    case 8: return launch_force<8>(c, flags, fuse, hs2);
     }
     return mdb_fail(c, MDB_ERR_ARG, "tiled path: unsupported lane-group size %d", c->tiled.G);
 }

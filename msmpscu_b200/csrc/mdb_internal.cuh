@@ -77,7 +77,7 @@ struct TiledState {
     double margin = 0.0;       // class margin (length): classes hold while every atom moved < margin/2
     float rc2f[2] = {0.f, 0.f}, safe_d2 = 0.f;
     bool use_classes = true;
-    int nparts = 2, nparts_opt = 3; // tiles in flight per SM (partitions of the pass CTA)
+    int nparts = 2, nparts_opt = 2; // tiles in flight per SM (partitions of the pass CTA)
     unsigned short *nbl = nullptr; size_t nbl_elems = 0;   // slot list (bytes in nbl_elems)
     unsigned short *raw = nullptr; size_t raw_bytes = 0;   // reference-order slots + class tag
     unsigned short *ncls = nullptr; size_t ncls_bytes = 0; // per-atom class counts [2][npad]
@@ -143,6 +143,7 @@ struct mdb_ctx {
 
     // ---- options
     int opt_force_path = MDB_FORCE_PATH_AUTO;
+    int opt_fuse_epilogue = 0; // measured slower than the separate 27 us kernel on B200 (profiles/r01_summary.md)
 
     // ---- virial partials
     double *vpart = nullptr; int vpart_n = 0;
@@ -185,5 +186,5 @@ int mdb_tiled_plan(mdb_ctx *c);               // mdb_force_tiled.cu
 int mdb_tiled_nlist(mdb_ctx *c);
 void mdb_tiled_free(mdb_ctx *c);
 void mdb_mark_positions_dirty(mdb_ctx *c);    // mdb_api.cu : positions changed outside the predictor
-int mdb_force_tiled(mdb_ctx *c, unsigned flags);
+int mdb_force_tiled(mdb_ctx *c, unsigned flags, int fuse = 0, double hs2 = 0.0);
 int mdb_list_rebuild(mdb_ctx *c);             // mdb_api.cu : cells + list kernel of the active path (no sync)

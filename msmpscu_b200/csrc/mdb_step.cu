@@ -225,6 +225,10 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)
     if (nb_uptab > 0 && (itime - it0) % nb_uptab == 0) { // MOD(ITIME-IT0,NB_UPTAB)==0, GenericMD:599-601
         if ((rc = mdb_list_rebuild(c)) < 0) return rc;
     }
+    if (c->opt_fuse_epilogue && c->tiled.active && c->has_tables && c->list_valid && c->shape_identity) {
+        // EPC friction and the corrector are fused into the epilogue of the force pass
+        return mdb_force_tiled(c, MDB_FORCE, 3, h * 0.5);
+    }
     if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
     ProfScope ps(c, MDB_K_CORRECT);
     k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,

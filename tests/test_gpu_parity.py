@@ -299,3 +299,26 @@ def test_gmd_example_inputs_through_the_mdlib_interface(oracle):
     md.force(virial=True)
     assert util.relerr(vt, md.get()["vtensor"]) < FORCE_RTOL
     dev.ctx.close()
+
+
+@pytest.mark.parametrize("path", ["generic", "tiled", "tiled_fused"])
+def test_nvt_epc_steps_track_oracle(oracle, path):
+    """BASELINE configs[1] dynamics in small: NVT through the electron-phonon thermostat (EPC friction applied
+    to the fresh force, then the corrector -- fused into the force-pass epilogue on the tiled path)."""
+    c = util.bcc_case((8, 8, 8), seed=77, temp=900.0)
+    te, al, cut, he = [300.0], [1.0e-12], [0.1], [100.0 * util.CP_EVERG]
+    md = util.oracle_md(oracle, c)
+    md.set_epc([1], te, al, cut, he)
+    md.rebuild(); md.force()
+    ctx = util.make_ctx(c, force_path=PATHS[path.split("_")[0]])
+    ctx.set_option(capi.OPT_FUSE_EPILOGUE, 1 if path.endswith("fused") else 0)
+    ctx.epc_set([1], te, al, cut, he)
+    ctx.force(capi.FORCE)
+    for it in range(15):
+        md.step(it, 1, 10, 0.5e-15)
+    ctx.run(0, 15, 1, 10, 0.5e-15)
+    ref = md.get()
+    assert util.relerr(ctx.download(capi.F_XP), ref["xp"]) < 1e-12
+    assert util.relerr(ctx.download(capi.F_XP1), ref["xp1"]) < 1e-9
+    assert util.relerr(ctx.download(capi.F_FP), ref["fp"]) < FORCE_RTOL   # FP holds the force after the EPC friction
+    ctx.close()
