@@ -59,7 +59,9 @@ typedef struct mdb_ctx mdb_ctx;
 #define MDB_F_NAC    14  /* int (NC)      atoms per cell                                     */
 #define MDB_F_NAAC   15  /* int (NC)      ACTIVE atoms per cell                              */
 #define MDB_F_IA1TH  16  /* int (NC)      1-based id of the first atom of each cell          */
-#define MDB_F__COUNT 17
+#define MDB_F_POS4   17  /* mdb_devptr only: the internal packed records double {x,y,z,den} per atom        */
+#define MDB_F_D2MAX  18  /* mdb_devptr only: int holding the float bits of max |displacement since rebuild|^2 */
+#define MDB_F__COUNT 19
 
 /* ---- potential types: Register_ForceClass("EAM_TYPE"|"FS_TYPE"), CommonGPU/MD_ForceClass_Register_GPU.F90:363-442 */
 #define MDB_POT_EAM 0
@@ -70,6 +72,7 @@ typedef struct mdb_ctx mdb_ctx;
 #define MDB_VIRIAL   2u  /* pCalPTensor-> CALPTENSOR_EAM_Force_Table2A_DEV, :1366 (forces + virial)                     */
 #define MDB_EPOT     4u  /* pCalEpot0  -> UpdateEPOT_EAM_Force_Table2A_DEV, :1710                                       */
 #define MDB_DEN      8u  /* pCalEDen   -> CALDEN_EAM_Force_Table2A_DEV, :891 (pass 1 only)                              */
+#define MDB_NOPASS1 16u  /* with MDB_FORCE: DEN is already current (slab runs exchange it between the passes)          */
 
 /* ------------------------------------------------------------------------------------
  * context / device selection
@@ -167,6 +170,23 @@ int mdb_epc_apply(mdb_ctx *ctx);
  * ---------------------------------------------------------------------------------- */
 int mdb_step(mdb_ctx *ctx, int itime, int it0, int nb_uptab, double h);
 int mdb_run(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double h);
+
+/* ------------------------------------------------------------------------------------
+ * single huge box over several GPUs: slab decomposition along z (whole z-layers of cells per rank).
+ * Upgrades the reference's scheme -- contiguous cell ranges per device with REPLICATED positions and
+ * host-staged copies (CommonGPU/MD_NeighborsList_GPU.F90:1576-1605, MD_Globle_Variables_GPU.F90:2026-2040,
+ * Synchroniz_DEN_on_Devices MD_EAM_ForceTable_GPU.F90:617-642) -- to owned + ghost layers: every rank keeps
+ * full-size arrays in the common cell-sorted order but only its owned layers and one ghost layer on each
+ * side are kept current.  Per step the caller exchanges the boundary layers' packed records
+ * (mdb_devptr(MDB_F_POS4), contiguous ranges from mdb_dd_info) after mdb_predict and again (DEN) between
+ * mdb_force(MDB_DEN) and mdb_force(MDB_FORCE|MDB_NOPASS1); before a rebuild every rank's owned ranges are
+ * gathered so that all ranks perform the same deterministic cell sort.  msmpscu_b200/domain.py does this
+ * over torch.distributed (NCCL send/recv).
+ * info: a0,a1 owned atoms | gb0,gb1 ghost below | ga0,ga1 ghost above | sb0,sb1 my bottom layer |
+ *       st0,st1 my top layer | rank below, rank above | cell_lo,cell_hi | tile_lo,tile_hi   (0-based, CELL order)
+ * ---------------------------------------------------------------------------------- */
+int mdb_dd_set(mdb_ctx *ctx, int rank, int nranks);
+int mdb_dd_info(const mdb_ctx *ctx, int info[16]);
 
 /* ------------------------------------------------------------------------------------
  * options.  MDB_OPT_FORCE_PATH selects the force/list implementation:

@@ -20,7 +20,8 @@ ORDER_ORIGINAL, ORDER_CELL = 0, 1
 (F_XP, F_XP1, F_FP, F_DIS, F_EPOT, F_EKIN, F_DEN, F_ITYP, F_STATU, F_GID, F_GIDINV, F_IC, F_KVOIS, F_INDI,
  F_NAC, F_NAAC, F_IA1TH) = range(17)
 POT_EAM, POT_FS = 0, 1
-FORCE, VIRIAL, EPOT, DEN = 1, 2, 4, 8
+FORCE, VIRIAL, EPOT, DEN, NOPASS1 = 1, 2, 4, 8, 16
+F_POS4, F_D2MAX = 17, 18
 K_NAMES = ("cellsort", "nlist", "pass1", "pass2", "epot", "predict", "correct", "other")
 K_COUNT = 8
 LIB_MARINICA_EAM2, LIB_BONNY_EAM1 = 1, 2
@@ -60,6 +61,8 @@ SYMBOLS = {
     "mdb_epc_apply": (C.c_int, [C.c_void_p]),
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_dd_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mdb_dd_info": (C.c_int, [C.c_void_p, c_ip]),
     "mdb_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdb_get_option": (C.c_int, [C.c_void_p, C.c_int]),
     "mdb_prof_enable": (C.c_int, [C.c_void_p, C.c_int]),
@@ -259,6 +262,16 @@ class Context:
 
     def run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    def dd_set(self, rank, nranks):
+        self._chk(self.lib.mdb_dd_set(self.h, int(rank), int(nranks)))
+
+    def dd_info(self):
+        out = (C.c_int * 16)()
+        self._chk(self.lib.mdb_dd_info(self.h, out))
+        keys = ("a0", "a1", "gb0", "gb1", "ga0", "ga1", "sb0", "sb1", "st0", "st1", "below", "above", "cell_lo", "cell_hi",
+                "tile_lo", "tile_hi")
+        return dict(zip(keys, list(out)))
 
     def sync(self):
         self._chk(self.lib.mdb_sync(self.h))

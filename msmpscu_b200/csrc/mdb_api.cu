@@ -149,6 +149,7 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
     free_state(c); free_nlist(c); free_tables(c);
     if (c->counters) cudaFree(c->counters);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_dd) cudaFreeHost(c->h_dd);
     if (c->hstage) cudaFreeHost(c->hstage);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -461,6 +462,8 @@ extern "C" void *mdb_devptr(mdb_ctx *c, int field)
         c->launches_total++;
         return c->den_view;
     case MDB_F_INDI: return c->indi;
+    case MDB_F_POS4: return c->pos;                      // internal {x,y,z,den} records (ghost exchange)
+    case MDB_F_D2MAX: return c->counters + CNT_D2MAX;    // max displacement^2 since the rebuild (float bits)
     }
     if (double *p = dptr_d(c, field)) return p;
     return dptr_i(c, field);
@@ -628,6 +631,10 @@ extern "C" int mdb_nlist_build(mdb_ctx *c)
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     c->mxnac = c->h_counters[CNT_MXNAC];
+    if (c->dd_on) {
+        if (!c->tiled.active) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "slab decomposition needs the tiled path");
+        if ((rc = mdb_dd_update(c)) < 0) return rc;
+    }
     return c->h_counters[CNT_OOB];
 }
 
@@ -650,6 +657,54 @@ int mdb_list_rebuild(mdb_ctx *c)
     rc = c->tiled.active ? mdb_tiled_nlist(c) : mdb_nlist_kernel(c);
     if (rc < 0) return rc;
     c->list_valid = true;
+    return MDB_OK;
+}
+
+// owned / ghost atom ranges of this rank after a rebuild (slab decomposition along z, cell-sorted order makes every
+// z-layer of cells one contiguous atom range)
+int mdb_dd_update(mdb_ctx *c)
+{
+    if (!c->dd_on) return MDB_OK;
+    const int cl = c->ncell[0] * c->ncell[1], ncz = c->ncell[2], R = c->dd_n, r = c->dd_rank;
+    const int zl0 = (int)(((long long)r * ncz) / R), zl1 = (int)(((long long)(r + 1) * ncz) / R);
+    if (zl1 - zl0 < 1) return mdb_fail(c, MDB_ERR_ARG, "slab decomposition: more ranks than z-layers of cells");
+    const int zb = (zl0 - 1 + ncz) % ncz, za = zl1 % ncz; // ghost layers below / above (periodic wrap)
+    if (!c->h_dd) CUDA_TRY(c, cudaMallocHost(&c->h_dd, sizeof(int) * 16));
+    // first atom (0-based) of a z-layer = IA1th of its first cell - 1; layer ncz -> number of atoms in cells
+    const int layers[8] = {zl0, zl1, zb, zb + 1, za, za + 1, zl0 + 1, zl1 - 1};
+    for (int i = 0; i < 8; i++) {
+        if (layers[i] >= ncz) CUDA_TRY(c, cudaMemcpyAsync(c->h_dd + i, c->counters + CNT_INCELL, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        else CUDA_TRY(c, cudaMemcpyAsync(c->h_dd + i, c->ia1th + (size_t)layers[i] * cl, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    auto first = [&](int i) { return layers[i] >= ncz ? c->h_dd[i] : c->h_dd[i] - 1; };
+    int *d = c->dd_info;
+    d[0] = first(0); d[1] = first(1);            // owned atoms [a0, a1)
+    d[2] = first(2); d[3] = first(3);            // ghost layer below
+    d[4] = first(4); d[5] = first(5);            // ghost layer above
+    d[6] = first(0); d[7] = first(6);            // my bottom layer (sent to the rank below)
+    d[8] = first(7); d[9] = first(1);            // my top layer (sent to the rank above)
+    d[10] = (r - 1 + R) % R; d[11] = (r + 1) % R;
+    d[12] = zl0 * cl; d[13] = zl1 * cl;
+    const int tiles_per_layer = c->ncell[1] * c->tiled.ntx;
+    d[14] = zl0 * tiles_per_layer; d[15] = zl1 * tiles_per_layer;
+    return MDB_OK;
+}
+
+extern "C" int mdb_dd_set(mdb_ctx *c, int rank, int nranks)
+{
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return mdb_fail(c, MDB_ERR_ARG, "mdb_dd_set: bad rank/nranks");
+    if (nranks > 1 && c->nbox != 1) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_dd_set: slab decomposition is for a single box");
+    c->dd_on = nranks > 1;
+    c->dd_rank = rank; c->dd_n = nranks;
+    c->list_valid = false;
+    return MDB_OK;
+}
+
+extern "C" int mdb_dd_info(const mdb_ctx *c, int out[16])
+{
+    if (!c || !c->dd_on) return MDB_ERR_STATE;
+    for (int i = 0; i < 16; i++) out[i] = c->dd_info[i];
     return MDB_OK;
 }
 

@@ -102,6 +102,7 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
 struct TileListArgs {
     const double4 *pos; const int *ityp; const int *nac; const int *naac; const int *ia1th;
     int *kvois; int *indi; unsigned short *nbl; unsigned short *ncls; unsigned short *raw; int *counters; TileDesc *desc;
+    int cell_lo, cell_hi; // cells of this rank (slab decomposition), all cells otherwise
     float rm2[MDB_MXGROUP * MDB_MXGROUP];
     float rc2[2]; // class radii^2 (build-time, fp32): class 0 <= rc2[0] < class 1 <= rc2[1] < class 2
 };
@@ -138,8 +139,8 @@ k_tile_nlist(TileParams P, TileListArgs A)
     __shared__ float4 tile_s[NL_WARPS][32];
     __shared__ unsigned short stage[4 * G][NL_THREADS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int ic0 = blockIdx.x * NL_WARPS + wib;               // global cell id (0-based)
-    if (ic0 >= P.nbox * P.nc0) return;
+    const int ic0 = A.cell_lo + blockIdx.x * NL_WARPS + wib;   // global cell id (0-based)
+    if (ic0 >= A.cell_hi) return;
     if (A.naac[ic0] <= 0) return;                              // cells without ACTIVE atoms are skipped (:981-982)
     const int ccnt = A.nac[ic0];
     if (ccnt <= 0) return;                                     // :1018
@@ -297,6 +298,8 @@ struct TilePassArgs {
     float safe_d2;         // classes are valid while max |displacement since rebuild|^2 <= safe_d2
     // fused epilogue of pass 2 (mdb_run): EPC friction on the fresh force, then the corrector half-kick
     int fuse;              // bit 0: EPC, bit 1: corrector
+    int tile_lo, tile_hi;  // tiles of this rank (slab decomposition), [0, ntiles) otherwise
+    int zero_parked;       // block 0 zeroes the outputs of atoms parked outside the cells
     double hs2;            // H/2
     double *xp1;
     EpcParams epc;
@@ -438,7 +441,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
     auto prefetch = [&](int tile) {
         Pre q;
         q.htot = 0; q.nhc = 0; q.edge_any = 0; q.own_start = 0; q.own_slot0 = 0; q.own_count = 0; q.cnt = 0; q.slot = 0; q.gst = 0;
-        if (tile < P.ntiles) {
+        if (tile < A.tile_hi) {
             const TileDesc &D = A.desc[tile];
             q.htot = D.htot; q.nhc = D.nhc; q.edge_any = D.edge_any;
             q.own_start = D.own_start; q.own_slot0 = D.own_slot0; q.own_count = D.own_count;
@@ -447,9 +450,9 @@ k_tile_pass(TileParams P, TilePassArgs A)
         return q;
     };
     const int tile_step = A.nparts * gridDim.x;
-    Pre cur = prefetch(A.nparts * blockIdx.x + half);
+    Pre cur = prefetch(A.tile_lo + A.nparts * blockIdx.x + half);
 
-    for (int tile = A.nparts * blockIdx.x + half; tile < P.ntiles; tile += tile_step) {
+    for (int tile = A.tile_lo + A.nparts * blockIdx.x + half; tile < A.tile_hi; tile += tile_step) {
         const TileDesc &D = A.desc[tile];
         bar_named(1 + half, TH);                     // every lane of the half is done with the previous halo
         const int htot = cur.htot, nhc = cur.nhc;
@@ -695,7 +698,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
         }
     }
     // atoms parked outside the cells (out of box, inactive): zero outputs, as the generic path does
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && A.zero_parked) {
         const int n_in = A.counters[CNT_INCELL];
         for (int i = n_in + threadIdx.x; i < P.n; i += T) {
             if (PASS == 1) reinterpret_cast<double *>(A.pos + i)[3] = 0.0;
@@ -876,9 +879,15 @@ static int launch_list(mdb_ctx *c)
     A.desc = (TileDesc *)S.desc;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
     A.rc2[0] = S.rc2f[0]; A.rc2[1] = S.rc2f[1];
+    A.cell_lo = 0; A.cell_hi = c->nc;
+    if (c->dd_on) { // owned z-layers of cells: the descriptors are cheap and built for every tile
+        const int cl = c->ncell[0] * c->ncell[1];
+        A.cell_lo = (int)(((long long)c->dd_rank * c->ncell[2]) / c->dd_n) * cl;
+        A.cell_hi = (int)(((long long)(c->dd_rank + 1) * c->ncell[2]) / c->dd_n) * cl;
+    }
     ProfScope ps(c, MDB_K_NLIST, 2);
     k_tile_desc<<<S.P.ntiles, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters);
-    k_tile_nlist<G><<<cdiv(c->nc, NL_WARPS), NL_THREADS, 0, c->stream>>>(S.P, A);
+    k_tile_nlist<G><<<cdiv(A.cell_hi - A.cell_lo, NL_WARPS), NL_THREADS, 0, c->stream>>>(S.P, A);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -909,6 +918,9 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.nparts = S.nparts;
     A.safe_d2 = S.use_classes ? S.safe_d2 : -1.0f;
     A.fuse = (PASS == 2) ? fuse : 0; A.hs2 = hs2; A.xp1 = c->xp1; A.epc = c->epc; A.mass = c->mass;
+    A.tile_lo = c->dd_on ? c->dd_info[14] : 0;
+    A.tile_hi = c->dd_on ? c->dd_info[15] : S.P.ntiles;
+    A.zero_parked = c->dd_on ? 0 : 1;
     if (!c->epc.on) A.fuse &= ~1;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
@@ -925,7 +937,8 @@ static int launch_force(mdb_ctx *c, unsigned flags, int fuse, double hs2)
 {
     const bool mt = c->ng > 1;
     int rc = MDB_OK;
-    if (flags & (MDB_FORCE | MDB_DEN)) rc = mt ? launch_pass<1, G, true>(c, 0, 0.0) : launch_pass<1, G, false>(c, 0, 0.0);
+    if ((flags & (MDB_FORCE | MDB_DEN)) && !(flags & MDB_NOPASS1))
+        rc = mt ? launch_pass<1, G, true>(c, 0, 0.0) : launch_pass<1, G, false>(c, 0, 0.0);
     if (rc < 0) return rc;
     if (flags & MDB_FORCE) rc = mt ? launch_pass<2, G, true>(c, fuse, hs2) : launch_pass<2, G, false>(c, fuse, hs2);
     return rc;

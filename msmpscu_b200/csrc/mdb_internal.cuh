@@ -141,6 +141,12 @@ struct mdb_ctx {
     // ---- tiled fast path
     TiledState tiled;
 
+    // ---- slab domain decomposition (single huge box over several ranks, z-layers of cells)
+    bool dd_on = false;
+    int dd_rank = 0, dd_n = 1;
+    int dd_info[16] = {0}; // a0,a1, gb0,gb1, ga0,ga1, sb0,sb1, st0,st1, below,above, cell_lo,cell_hi, tile_lo,tile_hi
+    int *h_dd = nullptr;   // pinned scratch
+
     // ---- options
     int opt_force_path = MDB_FORCE_PATH_AUTO;
     int opt_fuse_epilogue = 0; // measured slower than the separate 27 us kernel on B200 (profiles/r01_summary.md)
@@ -187,4 +193,7 @@ int mdb_tiled_nlist(mdb_ctx *c);
 void mdb_tiled_free(mdb_ctx *c);
 void mdb_mark_positions_dirty(mdb_ctx *c);    // mdb_api.cu : positions changed outside the predictor
 int mdb_force_tiled(mdb_ctx *c, unsigned flags, int fuse = 0, double hs2 = 0.0);
-int mdb_list_rebuild(mdb_ctx *c);             // mdb_api.cu : cells + list kernel of the active path (no sync)
+int mdb_list_rebuild(mdb_ctx *c);
+int mdb_dd_update(mdb_ctx *c);                // mdb_api.cu : owned / ghost ranges after a rebuild (syncs)
+static inline int own_a0(const mdb_ctx *c) { return c->dd_on ? c->dd_info[0] : 0; }
+static inline int own_a1(const mdb_ctx *c) { return c->dd_on ? c->dd_info[1] : c->n; }             // mdb_api.cu : cells + list kernel of the active path (no sync)

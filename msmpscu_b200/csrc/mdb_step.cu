@@ -57,11 +57,11 @@ __device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict_
 __global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, const double *__restrict__ fp,
                           double *__restrict__ dis, int *__restrict__ statu, const int *__restrict__ ityp,
                           MassParams M, BoxParams box, double th, double h2s2, double hs2,
-                          float *__restrict__ dsr, int *__restrict__ counters)
+                          float *__restrict__ dsr, int *__restrict__ counters, int a0, int a1)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     float d2 = 0.f;
-    if (i < n && (statu[i] & ST_ACTIVE) == ST_ACTIVE) // :295
+    if (i < a1 && (statu[i] & ST_ACTIVE) == ST_ACTIVE) // :295
         d2 = predict_atom(i, n, pos, xp1, fp, dis, statu, ityp, M, box, th, h2s2, hs2, dsr);
     if (dsr) { // block maximum -> one atomic per block; the tiled passes compare it with their class margin
         for (int off = 16; off > 0; off >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, off));
@@ -79,10 +79,11 @@ __global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__
 // EPC friction on FP followed by the second half kick: one read of XP1/FP instead of the
 // reference's two kernels (EPC_MOD_KERNEL then Correction_KERNEL).  do_epc / do_corr select stages.
 __global__ void k_epc_correct(int n, double *__restrict__ xp1, double *__restrict__ fp, const int *__restrict__ statu,
-                              const int *__restrict__ ityp, MassParams M, EpcParams E, double hs2, int do_epc, int do_corr)
+                              const int *__restrict__ ityp, MassParams M, EpcParams E, double hs2, int do_epc, int do_corr,
+                              int a0, int a1)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a1) return;
     const int stat = statu[i];
     if ((stat & ST_ACTIVE) != ST_ACTIVE) return;
     const int kk = ityp[i] - 1;
@@ -133,8 +134,9 @@ extern "C" int mdb_predict(mdb_ctx *c, double h)
     // Predictor_DEV :660-662 : TH = H, HS2 = TH/2, H2S2 = TH*TH/2
     const double th = h, hs2 = th * 0.5, h2s2 = th * th * 0.5;
     ProfScope ps(c, MDB_K_PREDICT);
-    k_predict<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp, c->mass,
-                                                      c->box, th, h2s2, hs2, c->dsr, c->counters);
+    k_predict<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp,
+                                                                     c->mass, c->box, th, h2s2, hs2, c->dsr, c->counters,
+                                                                     own_a0(c), own_a1(c));
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -145,8 +147,8 @@ extern "C" int mdb_correct(mdb_ctx *c, double h)
     if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_correct: mdb_box_set first");
     CUDA_TRY(c, cudaSetDevice(c->dev));
     ProfScope ps(c, MDB_K_CORRECT);
-    k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
-                                                          h * 0.5, 0, 1);
+    k_epc_correct<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
+                                                                         h * 0.5, 0, 1, own_a0(c), own_a1(c));
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -188,7 +190,8 @@ extern "C" int mdb_epc_apply(mdb_ctx *c)
     if (!c->epc.on) return MDB_OK; // hm_NEEDDO = .false. :403-405
     CUDA_TRY(c, cudaSetDevice(c->dev));
     ProfScope ps(c, MDB_K_CORRECT);
-    k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, 0.0, 1, 0);
+    k_epc_correct<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
+                                                                         0.0, 1, 0, own_a0(c), own_a1(c));
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -202,10 +205,14 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     if (!c->shape_identity) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: non-identity BOXSHAPE is not supported yet");
     if ((flags & MDB_VIRIAL) && !vtensor) return mdb_fail(c, MDB_ERR_ARG, "mdb_force: MDB_VIRIAL needs vtensor");
     CUDA_TRY(c, cudaSetDevice(c->dev));
+    if (c->dd_on && !c->tiled.active)
+        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: slab decomposition needs the tiled path");
+    if (c->dd_on && (flags & (MDB_VIRIAL | MDB_EPOT)))
+        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: virial / per-atom energy are not available in slab-decomposed runs yet");
     if (c->tiled.active) {
         // density + force passes on the tiled path; virial / per-atom energy (output steps only)
         // run on the generic kernels over the reference-format list the tiled build also emits
-        unsigned fast = flags & (MDB_FORCE | MDB_DEN);
+        unsigned fast = flags & (MDB_FORCE | MDB_DEN | MDB_NOPASS1);
         if (flags & MDB_VIRIAL) fast = 0;
         if (fast) {
             int rc = mdb_force_tiled(c, fast);
@@ -232,7 +239,7 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)
     if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
     ProfScope ps(c, MDB_K_CORRECT);
     k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
-                                                          h * 0.5, c->epc.on, 1);
+                                                          h * 0.5, c->epc.on, 1, 0, c->n);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -240,6 +247,8 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)
 extern "C" int mdb_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab, double h)
 {
     if (!c) return MDB_ERR_ARG;
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_run: a slab-decomposed step needs the ghost exchanges between its "
+                                                           "kernels; drive it with mdb_predict / mdb_force / mdb_correct (msmpscu_b200/domain.py)");
     if (!c->has_box || !c->has_tables || !c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_run: box, tables and list must be set");
     CUDA_TRY(c, cudaSetDevice(c->dev));
     CUDA_TRY(c, cudaMemsetAsync(c->counters + CNT_OOB_TOTAL, 0, sizeof(int), c->stream));

@@ -1,0 +1,122 @@
+"""Single huge box over several GPUs: z-slab domain decomposition with ghost-layer exchange (NCCL).
+
+The reference's multi-GPU scheme for one box is "contiguous cell range per device, REPLICATED positions,
+host-staged copies" (XP all-gather through the host after the predictor, MD_Globle_Variables_GPU.F90:2026-2040;
+DEN all-gather between the passes, MD_EAM_ForceTable_GPU.F90:617-642).  Here every rank keeps full-size
+arrays in the common cell-sorted order -- so neighbour slots, tiles and ids mean the same everywhere -- but
+only its owned z-layers of cells plus ONE ghost layer on each side are kept current:
+
+  per step      predictor (owned) -> send bottom/top layer records to the ranks below/above, receive the two
+                ghost layers (NCCL send/recv on contiguous ranges of the packed {x,y,z,den} array)
+                -> density pass (owned tiles) -> the same exchange again (now carrying DEN)
+                -> force pass -> EPC + corrector (owned)
+  per rebuild   every rank broadcasts its owned ranges of {pos, XP1, DIS, STATU}; all ranks run the same
+                deterministic device cell sort on identical data, then build lists for their own layers.
+  the distance-class shortcut of the tiled passes needs the GLOBAL max displacement: one 4-byte all-reduce.
+
+A z-layer of cells is one contiguous atom range in cell order (cells are x-fastest, z-slowest), which is
+what makes the exchange two plain range copies per neighbour.
+"""
+import numpy as np
+
+from . import capi
+
+
+class _DevArray:
+    """Zero-copy view of device memory for torch (torch.as_tensor understands __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def slab_layers(ncz, world, rank):
+    """z-layers [z0, z1) of cells owned by `rank` (same formula as mdb_dd_update)."""
+    return (rank * ncz) // world, ((rank + 1) * ncz) // world
+
+
+class SlabDomain:
+    def __init__(self, ctx: capi.Context, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.ctx, self.device, self.group = ctx, torch.device("cuda", device), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ctx.dd_set(self.rank, self.world)
+        self.info = None
+
+    # ---- tensor views (pointers change at every rebuild: the re-sort double-buffers)
+    def _views(self):
+        t, n = self.torch, self.ctx.n
+        mk = lambda f, shape, ts: t.as_tensor(_DevArray(self.ctx.devptr(f), shape, ts), device=self.device)
+        self.pos = mk(capi.F_POS4, (n, 4), "<f8")
+        self.xp1 = mk(capi.F_XP1, (3, n), "<f8")
+        self.dis = mk(capi.F_DIS, (3, n), "<f8")
+        self.statu = mk(capi.F_STATU, (n,), "<i4")
+        self.d2max = mk(capi.F_D2MAX, (1,), "<i4")
+
+    def _sync_stream(self):
+        self.ctx.sync()  # the library runs on its own stream; torch.distributed on torch's
+
+    def rebuild(self):
+        """All ranks obtain every rank's owned ranges, sort, and build the lists of their own layers."""
+        if self.world > 1 and self.info is not None:
+            self._views()
+            self._sync_stream()
+            ranges = [None] * self.world
+            mine = self.torch.tensor([self.info["a0"], self.info["a1"]], device=self.device, dtype=self.torch.int64)
+            allr = [self.torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(allr, mine, group=self.group)
+            for r in range(self.world):
+                a0, a1 = (int(v) for v in allr[r].tolist())
+                ranges[r] = (a0, a1)
+            for r, (a0, a1) in enumerate(ranges):
+                if a1 <= a0:
+                    continue
+                self.dist.broadcast(self.pos[a0:a1], src=r, group=self.group)
+                for arr in (self.xp1, self.dis):
+                    for d in range(3):
+                        self.dist.broadcast(arr[d, a0:a1], src=r, group=self.group)
+                self.dist.broadcast(self.statu[a0:a1], src=r, group=self.group)
+            self.torch.cuda.synchronize(self.device)
+        nout = self.ctx.nlist_build()
+        if self.world > 1:
+            self.info = self.ctx.dd_info()
+            self._views()
+        return nout
+
+    def exchange(self):
+        """Boundary-layer records to the neighbours, ghost layers from them (positions, and DEN after pass 1)."""
+        if self.world == 1:
+            return
+        i, dist = self.info, self.dist
+        self._sync_stream()
+        ops = [dist.P2POp(dist.isend, self.pos[i["sb0"]:i["sb1"]], i["below"], self.group),
+               dist.P2POp(dist.isend, self.pos[i["st0"]:i["st1"]], i["above"], self.group),
+               # order matters when both neighbours are the same rank (world == 2): its first send is its bottom layer
+               dist.P2POp(dist.irecv, self.pos[i["ga0"]:i["ga1"]], i["above"], self.group),
+               dist.P2POp(dist.irecv, self.pos[i["gb0"]:i["gb1"]], i["below"], self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        self.torch.cuda.synchronize(self.device)
+
+    def step(self, itime, it0, nb_uptab, h):
+        """One GMD step (Appshell/MD_Method_GenericMD_GPU.F90:596-627) on the decomposed box."""
+        c = self.ctx
+        c.predict(h)
+        if (itime - it0) % nb_uptab == 0:
+            self.rebuild()
+        else:
+            if self.world > 1:
+                self._sync_stream()
+                self.dist.all_reduce(self.d2max, op=self.dist.ReduceOp.MAX, group=self.group)
+            self.exchange()
+        c.force(capi.DEN)
+        self.exchange()
+        c.force(capi.FORCE | capi.NOPASS1)
+        c.epc_apply()
+        c.correct(h)
+
+    def owned(self):
+        """(a0, a1) of this rank in CELL order."""
+        return (self.info["a0"], self.info["a1"]) if self.world > 1 else (0, self.ctx.n)

@@ -1,0 +1,74 @@
+"""Worker of tests/test_gpu_dd.py (run under torchrun, one rank per GPU): a slab-decomposed run of one box
+against the same box on a single GPU."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+import torch.distributed as dist
+
+import util
+from msmpscu_b200 import capi
+from msmpscu_b200.domain import SlabDomain
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 25
+    c = util.bcc_case((8, 8, 20), seed=404, temp=900.0)
+    h, it0, nup = 0.5e-15, 1, 10
+    epc = ([1], [300.0], [1.0e-12], [0.1], [100.0 * util.CP_EVERG])
+
+    def make(dev):
+        ctx = capi.Context(dev)
+        ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
+        ctx.upload(capi.F_XP, c.xp); ctx.upload(capi.F_XP1, c.xp1)
+        ctx.upload(capi.F_ITYP, c.ityp); ctx.upload(capi.F_STATU, c.statu)
+        ctx.tables_set(util.product_tables(c), c.ru * c.ru)
+        ctx.set_option(capi.OPT_FORCE_PATH, capi.FORCE_PATH_TILED)
+        ctx.nlist_init(c.nb_rm, c.mxkvois)
+        ctx.epc_set(*epc)
+        return ctx
+
+    full = make(local)             # the whole box on this GPU: the reference for this test
+    full.nlist_build(); full.force(capi.FORCE)
+    full.run(0, nsteps, it0, nup, h)
+
+    ctx = make(local)
+    dom = SlabDomain(ctx, local)
+    dom.rebuild()
+    ctx.force(capi.DEN); dom.exchange(); ctx.force(capi.FORCE | capi.NOPASS1)
+    for it in range(nsteps):
+        dom.step(it, it0, nup, h)
+    a0, a1 = dom.owned()
+    ok = True
+    gid_f, gid_d = full.download(capi.F_GID, capi.ORDER_CELL), ctx.download(capi.F_GID, capi.ORDER_CELL)
+    ok &= bool(np.array_equal(gid_f, gid_d))
+    worst = {}
+    for name, f, tol in (("xp", capi.F_XP, 1e-13), ("xp1", capi.F_XP1, 1e-10), ("fp", capi.F_FP, 1e-10), ("den", capi.F_DEN, 1e-10)):
+        x, y = full.download(f, capi.ORDER_CELL)[a0:a1], ctx.download(f, capi.ORDER_CELL)[a0:a1]
+        worst[name] = util.relerr(y, x)
+        ok &= worst[name] < tol
+    kf, _ = full.nlist_copyout(capi.ORDER_CELL)
+    kd, _ = ctx.nlist_copyout(capi.ORDER_CELL)
+    ok &= bool(np.array_equal(kf[a0:a1], kd[a0:a1]))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    counts = torch.tensor([a1 - a0], device="cuda")
+    dist.all_reduce(counts)
+    print("rank %d owns [%d,%d) of %d  worst rel err %s  ok=%s" % (rank, a0, a1, ctx.n, worst, ok), flush=True)
+    if rank == 0:
+        print("DD_RESULT", "PASS" if int(flag.item()) == 1 and int(counts.item()) == ctx.n else "FAIL", flush=True)
+    full.close(); ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

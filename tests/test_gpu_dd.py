@@ -1,0 +1,36 @@
+"""Slab domain decomposition (BASELINE configs[4] family) on 2 GPUs: needs a 2-GPU box
+(`gpurun --gpus 2 -- python -m pytest tests/test_gpu_dd.py -m gpu`); skipped on a single GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from msmpscu_b200 import capi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(capi.load().mdb_device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_slab_run_matches_single_gpu():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "dd_worker.py"), "25"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(out.stdout[-3000:], out.stderr[-3000:])
+    assert out.returncode == 0
+    assert "DD_RESULT PASS" in out.stdout
+
+
+def test_slab_layers_cover_the_box():
+    from msmpscu_b200.domain import slab_layers
+    for ncz in (3, 7, 35, 87):
+        for world in (1, 2, 3, 4, 8):
+            if world > ncz:
+                continue
+            got = []
+            for r in range(world):
+                z0, z1 = slab_layers(ncz, world, r)
+                assert z1 > z0
+                got += list(range(z0, z1))
+            assert got == list(range(ncz))
