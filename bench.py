@@ -51,7 +51,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=0, help="tiled path: lanes per atom (2/4/8), 0 = default")
     ap.add_argument("--classes", type=int, default=1, help="tiled path: distance-classified lists on/off")
-    ap.add_argument("--parts", type=int, default=0, help="tiled path: tiles in flight per SM (1..4), 0 = default")
+    ap.add_argument("--threads", type=int, default=0, help="tiled path: threads of the pass CTA (512/768), 0 = default")
+    ap.add_argument("--stages", type=int, default=0, help="tiled path: pipeline stages of the pass kernel (2/3), 0 = default")
     return ap.parse_args()
 
 
@@ -183,8 +184,10 @@ def run_ours(args):
     ctx.nlist_init(c.nb_rm, c.mxkvois)
     if args.lanes:
         ctx.set_option(capi.OPT_TILED_LANES, args.lanes)
-    if args.parts:
-        ctx.set_option(capi.OPT_TILED_PARTS, args.parts)
+    if args.threads:
+        ctx.set_option(capi.OPT_TILED_THREADS, args.threads)
+    if args.stages:
+        ctx.set_option(capi.OPT_TILED_STAGES, args.stages)
     ctx.set_option(capi.OPT_TILED_CLASSES, args.classes)
     ctx.epc_set(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
 

@@ -192,15 +192,16 @@ int mdb_dd_info(const mdb_ctx *ctx, int info[16]);
  * options.  MDB_OPT_FORCE_PATH selects the force/list implementation:
  *   AUTO    the tiled fast path when the configuration fits it, else the generic one
  *   GENERIC thread-per-atom over INDI, un-fused arithmetic in reference order (bit-faithful)
- *   TILED   shared-memory staged halo tiles + two-phase (fp32 filter / fp64 evaluate) kernels
+ *   TILED   shared-memory staged halo tiles (TMA producer warp + consumer warps), 16-bit slot lists
  * ---------------------------------------------------------------------------------- */
 #define MDB_OPT_FORCE_PATH    0
 #define MDB_OPT_TILED_LANES   1  /* lanes sharing one atom in the tiled kernels: 2, 4 (default) or 8            */
 #define MDB_OPT_TILED_CLASSES 2  /* 1 (default): scan only the distance classes a pass needs while safe; 0: all */
 #define MDB_OPT_ACTIVE_PATH   3  /* read-only: the path the last list build selected                            */
-#define MDB_OPT_TILED_PARTS   4  /* tiles in flight per SM (partitions of the pass CTA): 1..4, default 2          */
+#define MDB_OPT_TILED_THREADS 4  /* threads of the persistent pass CTA (one producer warp + consumers): 512 or 768 (default) */
 #define MDB_OPT_FUSE_EPILOGUE 5  /* mdb_run on the tiled path: EPC friction + corrector inside the force-pass   */
                                  /* epilogue (1) or as one separate element-wise kernel (0, default: faster)    */
+#define MDB_OPT_TILED_STAGES  6  /* shared-memory pipeline stages of the pass kernel: 2 (default) or 3           */
 #define MDB_FORCE_PATH_AUTO    0
 #define MDB_FORCE_PATH_GENERIC 1
 #define MDB_FORCE_PATH_TILED   2

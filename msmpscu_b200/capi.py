@@ -73,7 +73,7 @@ SYMBOLS = {
                                          c_ip, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
 }
 
-OPT_FORCE_PATH, OPT_TILED_LANES, OPT_TILED_CLASSES, OPT_ACTIVE_PATH, OPT_TILED_PARTS, OPT_FUSE_EPILOGUE = 0, 1, 2, 3, 4, 5
+OPT_FORCE_PATH, OPT_TILED_LANES, OPT_TILED_CLASSES, OPT_ACTIVE_PATH, OPT_TILED_THREADS, OPT_FUSE_EPILOGUE, OPT_TILED_STAGES = 0, 1, 2, 3, 4, 5, 6
 FORCE_PATH_AUTO, FORCE_PATH_GENERIC, FORCE_PATH_TILED = 0, 1, 2
 
 _lib = None

@@ -162,8 +162,12 @@ extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
         c->tiled.G = value; c->tiled.dirty = true; c->list_valid = false;
         return MDB_OK;
     }
-    if (option == MDB_OPT_TILED_PARTS && value >= 1 && value <= 4) {
-        c->tiled.nparts_opt = value; c->tiled.dirty = true; c->list_valid = false;
+    if (option == MDB_OPT_TILED_THREADS && (value == 512 || value == 768)) {
+        c->tiled.threads_opt = value; c->tiled.dirty = true; c->list_valid = false;
+        return MDB_OK;
+    }
+    if (option == MDB_OPT_TILED_STAGES && (value == 2 || value == 3)) {
+        c->tiled.stages_opt = value; c->tiled.dirty = true; c->list_valid = false;
         return MDB_OK;
     }
     if (option == MDB_OPT_FUSE_EPILOGUE && (value == 0 || value == 1)) {
@@ -187,7 +191,8 @@ extern "C" int mdb_get_option(const mdb_ctx *c, int option)
     if (!c) return MDB_ERR_ARG;
     if (option == MDB_OPT_FORCE_PATH) return c->opt_force_path;
     if (option == MDB_OPT_TILED_LANES) return c->tiled.G;
-    if (option == MDB_OPT_TILED_PARTS) return c->tiled.nparts_opt;
+    if (option == MDB_OPT_TILED_THREADS) return c->tiled.threads_opt;
+    if (option == MDB_OPT_TILED_STAGES) return c->tiled.stages_opt;
     if (option == MDB_OPT_FUSE_EPILOGUE) return c->opt_fuse_epilogue;
     if (option == MDB_OPT_TILED_CLASSES) return c->tiled.use_classes ? 1 : 0;
     if (option == MDB_OPT_ACTIVE_PATH) return c->tiled.active ? MDB_FORCE_PATH_TILED : MDB_FORCE_PATH_GENERIC;
@@ -263,7 +268,7 @@ extern "C" int mdb_box_set(mdb_ctx *c, int nbox, int napb, const double boxlow[3
         ALLOC(dis, double, n3); ALLOC(dis_alt, double, n3);
         ALLOC(epot, double, n); ALLOC(ekin, double, n);
         ALLOC(ityp, int, n); ALLOC(ityp_alt, int, n);
-        ALLOC(statu, int, n); ALLOC(statu_alt, int, n);
+        ALLOC(statu, int, n + 8); ALLOC(statu_alt, int, n + 8); // +8: 16-byte aligned TMA windows may overshoot
         ALLOC(gid, int, n); ALLOC(gid_alt, int, n); ALLOC(gidinv, int, n);
         ALLOC(ic, int, n); ALLOC(ic_alt, int, n);
         ALLOC(slot, int, n); ALLOC(srcof, int, n); ALLOC(tmp_orig, int, n); ALLOC(oob, int, n);
@@ -581,7 +586,7 @@ extern "C" int mdb_nlist_init(mdb_ctx *c, const double *nb_rm, int mxkvois)
     CUDA_TRY(c, cudaMalloc(&c->nac, sizeof(int) * (size_t)c->nc));
     CUDA_TRY(c, cudaMalloc(&c->naac, sizeof(int) * (size_t)c->nc));
     CUDA_TRY(c, cudaMalloc(&c->ia1th, sizeof(int) * (size_t)c->nc));
-    CUDA_TRY(c, cudaMalloc(&c->kvois, sizeof(int) * (size_t)c->n));
+    CUDA_TRY(c, cudaMalloc(&c->kvois, sizeof(int) * ((size_t)c->n + 8))); // +8: aligned TMA windows
     CUDA_TRY(c, cudaMalloc(&c->indi, sizeof(int) * (size_t)c->n * mxkvois));
     CUDA_TRY(c, cudaMemsetAsync(c->kvois, 0, sizeof(int) * (size_t)c->n, c->stream)); // DevSet(KVOIS,0) :285
     CUDA_TRY(c, cudaMemsetAsync(c->indi, 0, sizeof(int) * (size_t)c->n * mxkvois, c->stream));

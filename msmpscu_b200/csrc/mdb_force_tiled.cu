@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 #include "mdb_tiled.cuh"
 
 __constant__ int t_nix[27] = {0, -1, -1, -1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1, 1, 1, 1, 0, 0, -1, 1, -1, 0, 1, -1, 0, 1};
@@ -44,6 +45,11 @@ struct TileDesc {
     int gst[TILE_MAX_HC];      // first global (cell-order, 0-based) atom of the cell
     int cid[TILE_MAX_HC];      // wrapped global cell id, -1 if absent
     signed char sh[TILE_MAX_HC][4]; // image shift per dim, [3] = edge flag
+    // RUNS: maximal stretches of halo cells of one row that are contiguous in the cell-sorted arrays (a row
+    // breaks only where it wraps around a periodic face) -> one TMA bulk copy each, at most 3 per row
+    int nrun, rpad[3];
+    int rslot[TILE_MAX_RUN + 1];   // first slot of each run, [nrun] = htot
+    int rgst[TILE_MAX_RUN];        // first global atom of each run
 };
 
 // fills the halo table in shared memory; must be called by all threads of the CTA
@@ -93,6 +99,23 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
         H.own_slot0 = H.slot[hc_own0];
         H.own_count = H.slot[hc_own0 + g.wt] - H.slot[hc_own0];
     }
+    if (threadIdx.x < 32) { // runs (IA1th is a running prefix over ALL cells, so empty cells do not break a run)
+        const int lane = threadIdx.x;
+        int nrun = 0;
+        for (int b = 0; b < g.nhc; b += 32) {
+            const int hc = b + lane;
+            bool start = false;
+            if (hc < g.nhc && H.cid[hc] >= 0)
+                start = !((hc % g.nhx) != 0 && H.cid[hc - 1] >= 0 && H.gst[hc - 1] + H.cnt[hc - 1] == H.gst[hc]);
+            const unsigned m = __ballot_sync(0xffffffffu, start);
+            if (start) {
+                const int rid = nrun + __popc(m & ((1u << lane) - 1u));
+                if (rid < TILE_MAX_RUN) { H.rslot[rid] = H.slot[hc]; H.rgst[rid] = H.gst[hc]; }
+            }
+            nrun += __popc(m);
+        }
+        if (lane == 0) { H.nrun = nrun; H.rslot[min(nrun, TILE_MAX_RUN)] = H.slot[g.nhc]; }
+    }
     __syncthreads();
 }
 
@@ -123,7 +146,7 @@ k_tile_desc(TileParams P, const int *__restrict__ nac, const int *__restrict__ i
     int *dst = reinterpret_cast<int *>(desc + tile);
     for (int i = threadIdx.x; i < (int)(sizeof(TileDesc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     // a halo that does not fit the shared-memory budget of the passes: the host falls back to the generic path
-    if (threadIdx.x == 0 && H.htot > P.hcap) atomicAdd(&counters[CNT_TILE_OVERFLOW], 1);
+    if (threadIdx.x == 0 && (H.htot > P.hcap || H.own_count > P.ocap || H.nrun > TILE_MAX_RUN)) atomicAdd(&counters[CNT_TILE_OVERFLOW], 1);
 }
 
 // One warp per cell (lanes = atoms of the cell), no block-level synchronisation: every lane of the warp walks
@@ -131,7 +154,7 @@ k_tile_desc(TileParams P, const int *__restrict__ nac, const int *__restrict__ i
 // SPOS = (float)(XP + (double)(float)shift) (:1100-1103).  Accepted neighbours go to the reference-format INDI
 // (global ids, reference order) and, as halo SLOTS of the cell's tile tagged with their distance class, to a
 // scratch list ([k][atom], coalesced); the lane then partitions its own scratch list by class into the
-// lane-interleaved layout the passes stream (nbl_index).  Tails are padded with slot 0.
+// lane-interleaved layout the passes stream (nbl_index).  Tails are padded with the dummy slot P.hcap.
 template <int G>
 __global__ void __launch_bounds__(NL_THREADS)
 k_tile_nlist(TileParams P, TileListArgs A)
@@ -238,7 +261,7 @@ k_tile_nlist(TileParams P, TileListArgs A)
         auto flush = [&]() {
             unsigned short blk[4 * G];
 #pragma unroll
-            for (int j = 0; j < 4 * G; j++) blk[(j % G) * 4 + j / G] = (j < pos) ? stage[j][threadIdx.x] : (unsigned short)0;
+            for (int j = 0; j < 4 * G; j++) blk[(j % G) * 4 + j / G] = (j < pos) ? stage[j][threadIdx.x] : (unsigned short)P.hcap;
             uint4 *dst = reinterpret_cast<uint4 *>(A.nbl + ((((size_t)(dbase / (4 * G)) * P.npad + (size_t)ia) * G) << 2));
 #pragma unroll
             for (int v = 0; v < (4 * G) / 8; v++) {
@@ -273,15 +296,29 @@ k_tile_nlist(TileParams P, TileListArgs A)
                 }
             }
         }
-        if (pos > 0) flush(); // the tail block is padded with slot 0
+        if (pos > 0) flush(); // the tail block is padded with the dummy slot (hcap: a record far from everything)
         A.ncls[ia] = (unsigned short)n0;
         A.ncls[ia + P.npad] = (unsigned short)(n0 + n1);
     }
 }
 
+
 // =====================================================================================
 // force passes
 // =====================================================================================
+// One persistent CTA per SM: NT/32 - 1 CONSUMER warps and one PRODUCER warp around a two-stage
+// shared-memory pipeline of halo tiles.
+//   producer  per tile: waits until the stage is free (mbarrier "empty"), issues one TMA bulk copy per halo
+//             cell (contiguous run of {x,y,z,den} records) plus one for the first index group of the owned
+//             atoms, fetches the per-atom scan counts, moves cells on a periodic face into the tile frame,
+//             then publishes the stage (mbarrier "ready").  It runs one tile ahead of the consumers.
+//   consumers grab chunks of 32/G owned atoms from a shared counter (no CTA-wide barrier anywhere: a warp that
+//             runs out of chunks moves on to the next stage by itself) and stream each atom's class-ordered
+//             slot list: first 4-entry group from shared memory, later groups from global memory one group
+//             ahead.  Every listed entry is evaluated -- fp64 separation from the staged records, exact
+//             r2 <= r_eff^2, one MUFU.RSQ64H + Halley step each for 1/r and 1/sqrt(r), table rows from
+//             shared memory -- and masked by the range test.  List tails are padded with a dummy slot whose
+//             record sits at 1e30, so no per-entry validity logic exists.
 struct TilePassArgs {
     double4 *pos; const int *ityp; const int *statu; const int *kvois; const unsigned short *ncls;
     const unsigned short *nbl; double *fp; int *counters; const TileDesc *desc;
@@ -290,16 +327,13 @@ struct TilePassArgs {
     int ntab, nembd, pot_type;
     double csi, rhod;
     double r2eff;          // min(RU2, table support) for this pass
-    int r2int;             // phase-A radius^2 in LSB units (conservative)
     int kmin, ktab;        // shared-memory table window: rows kmin .. kmin+ktab (row kk and kk+1 are read)
     int kind0;             // the kind held in shared memory = KPAIR(1,1)
-    int qcap;              // queue entries per atom
-    int nparts;            // independent partitions of the CTA (tiles in flight per SM)
     float safe_d2;         // classes are valid while max |displacement since rebuild|^2 <= safe_d2
-    // fused epilogue of pass 2 (mdb_run): EPC friction on the fresh force, then the corrector half-kick
-    int fuse;              // bit 0: EPC, bit 1: corrector
+    int fuse;              // fused epilogue of pass 2 (mdb_run): bit 0 EPC friction, bit 1 corrector half-kick
     int tile_lo, tile_hi;  // tiles of this rank (slab decomposition), [0, ntiles) otherwise
     int zero_parked;       // block 0 zeroes the outputs of atoms parked outside the cells
+    int nbuf;              // pipeline stages (2 or 3)
     double hs2;            // H/2
     double *xp1;
     EpcParams epc;
@@ -326,6 +360,28 @@ __device__ __forceinline__ double lerp_g(const double2 *__restrict__ t, int stri
     const double2 e = __ldg(t + (size_t)k * stride + kk);
     return fma(dk, e.y, e.x);
 }
+// rare out-of-line path of the passes: a pair whose table row lies outside the shared-memory window, or whose
+// kinds are not KPAIR(1,1).  Same arithmetic as the in-line path, tables read from global memory.
+// PASS 1: ta = POTB, returns the density term.  PASS 2: ta = FPOTR, tb = FPOTB, returns FORTOT.
+template <int PASS>
+__device__ __noinline__ double pair_slow(double4 me, double4 pj, double csi, const double2 *__restrict__ ta,
+                                         const double2 *__restrict__ tb, int stride, int k0, int k1)
+{
+    const double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
+    const double r2 = fma(sz, sz, fma(sy, sy, sx * sx));
+    const double y = rsqrt_fast(r2);
+    const double r = r2 * y;
+    const double z = rsqrt_fast(r);
+    const double sk = (r * z) * csi;
+    const double tk = __dadd_rd(sk, 4503599627370496.0);
+    const int kk = __double2loint(tk);
+    const double dk = sk - (tk - 4503599627370496.0);
+    if (PASS == 1) return lerp_g(ta, stride, k0, kk, dk);
+    const double fr = lerp_g(ta, stride, k0, kk, dk);
+    const double fb0 = lerp_g(tb, stride, k0, kk, dk);
+    const double fb1 = (k1 == k0) ? fb0 : lerp_g(tb, stride, k1, kk, dk);
+    return y * fma(fr, y, fma(fb0, me.w, fb1 * pj.w));
+}
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -336,6 +392,10 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
@@ -355,71 +415,50 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bar_named(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
-// byte-modular packed coordinates for phase A: q_d = floor(x_d / LSB) mod 256.  For two atoms in the
-// same (image-resolved) tile frame, a pair with r <= r_eff has |dq_d| <= r_eff/LSB + 1 <= 127 in every
-// coordinate, so the signed 8-bit differences are exact and  |dq|^2 <= (r_eff/LSB + sqrt(3))^2 :
-// the filter can only err towards passing a pair (wrap-around of far pairs), never towards dropping one.
-__device__ __forceinline__ unsigned pack_q(double x, double y, double z, double inv_lsb)
+// ---- shared-memory plan of the pass kernel (host and device agree through these)
+#define TP_MAXBUF 3
+#define TP_HDR_BYTES 256 // mbarriers [full, ready, empty] x stages, stage info, chunk counters
+__host__ __device__ __forceinline__ size_t al128(size_t x) { return (x + 127) & ~(size_t)127; }
+__host__ __device__ __forceinline__ size_t tp_pos_bytes(int hcap) { return al128(sizeof(double4) * (size_t)(hcap + 1)); } // +1: dummy record
+__host__ __device__ __forceinline__ size_t tp_idx_bytes(int ocap, int G) { return al128(sizeof(uint2) * (size_t)ocap * G); }
+// 16-byte aligned windows of STATU / KVOIS (int32) and of the class counts (uint16) around the owned range
+__host__ __device__ __forceinline__ size_t tp_i32_bytes(int ocap) { return al128(sizeof(int) * (size_t)(ocap + 8)); }
+__host__ __device__ __forceinline__ size_t tp_u16_bytes(int ocap) { return al128(sizeof(unsigned short) * (size_t)(ocap + 16)); }
+__host__ __device__ __forceinline__ size_t tp_buf_bytes(int hcap, int ocap, int G, bool mt)
 {
-    const unsigned qx = (unsigned)__double2int_rd(x * inv_lsb) & 255u;
-    const unsigned qy = (unsigned)__double2int_rd(y * inv_lsb) & 255u;
-    const unsigned qz = (unsigned)__double2int_rd(z * inv_lsb) & 255u;
-    return qx | (qy << 8) | (qz << 16);
+    return tp_pos_bytes(hcap) + tp_idx_bytes(ocap, G) + 2 * tp_i32_bytes(ocap) + tp_u16_bytes(ocap) + (mt ? al128((size_t)hcap + 1) : 0);
 }
+__host__ __device__ __forceinline__ size_t tp_tab_bytes(int ktab) { return al128(sizeof(double2) * (size_t)(ktab + 2)); }
 
-// 1 if the quantised distance^2 of the two packed positions is <= r2int
-__device__ __forceinline__ unsigned filt(unsigned a, unsigned b, int r2int)
-{
-    const int d = (int)__vsub4(a, b);
-    return (unsigned)(__dp4a(d, d, 0) - r2int - 1) >> 31;
-}
-
-// rare out-of-line path: table row outside the shared-memory window, or a pair of kinds other than KPAIR(1,1)
-__device__ __noinline__ double lerp_slow(const double2 *__restrict__ t, int stride, int k, int kk, double dk)
-{
-    return lerp_g(t, stride, k, kk, dk);
-}
-
-// PASS 1: rho -> DEN.  PASS 2: forces.  G lanes per atom.  MT: more than one atom type.
-// The CTA runs as A.nparts independent partitions of TH = T/nparts threads, each with its own tile in
-// flight ("half" below is the partition index; the first version had two).
-template <int PASS, int G, bool MT>
-__global__ void __launch_bounds__(G == 2 ? 512 : 768, 1)
+// PASS 1: rho -> DEN.  PASS 2: forces.  G lanes per atom.  MT: more than one atom type.  FUSE: EPC + corrector epilogue.
+template <int PASS, int G, bool MT, bool FUSE, int NT>
+__global__ void __launch_bounds__(NT, 1)
 k_tile_pass(TileParams P, TilePassArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int T = blockDim.x, TH = T / A.nparts;
-    const int half = (int)threadIdx.x / TH;
-    const int tid = (int)threadIdx.x - half * TH;  // thread id inside the partition
-    const int ngrp = TH / G;                        // atoms per round of a partition
-    // ---- carve shared memory: [tables][half 0: mbar, pos, pk, queue, types][half 1: ...]
-    size_t off = 0;
-    double2 *s_tab = reinterpret_cast<double2 *>(smem + off);       off += sizeof(double2) * (size_t)(A.ktab + 1);
-    off = (off + 127) & ~(size_t)127;
-    const size_t half_bytes = (((size_t)128 + (sizeof(double4) + sizeof(unsigned)) * (size_t)P.hcap +
-                                sizeof(unsigned short) * (size_t)A.qcap * ngrp + (MT ? (size_t)P.hcap : 0)) + 127) & ~(size_t)127;
-    unsigned char *hb = smem + off + (size_t)half * half_bytes;
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(hb);
-    double4 *s_pos = reinterpret_cast<double4 *>(hb + 128);
-    unsigned *s_pk = reinterpret_cast<unsigned *>(hb + 128 + sizeof(double4) * (size_t)P.hcap);
-    unsigned short *s_q = reinterpret_cast<unsigned short *>(hb + 128 + (sizeof(double4) + sizeof(unsigned)) * (size_t)P.hcap);
-    unsigned char *s_typ = reinterpret_cast<unsigned char *>(s_q + (size_t)A.qcap * ngrp); // hcap bytes, only if MT
+    constexpr int NW = NT / 32, NCW = NW - 1, APW = 32 / G;
+    unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // TMA bytes landed
+    unsigned long long *bar_ready = bar_full + TP_MAXBUF;                        // producer finished the stage
+    unsigned long long *bar_empty = bar_ready + TP_MAXBUF;                       // every consumer warp left the stage
+    int *s_info = reinterpret_cast<int *>(smem + 96);                             // [stage][own_start, own_slot0, own_count, edge]
+    int *s_ctr = reinterpret_cast<int *>(smem + 160);                             // [stage] next owned atom to hand out
+    double2 *s_tab = reinterpret_cast<double2 *>(smem + TP_HDR_BYTES);
+    unsigned char *buf0 = smem + TP_HDR_BYTES + tp_tab_bytes(A.ktab);
+    const size_t bufb = tp_buf_bytes(P.hcap, P.ocap, G, MT);
+    const size_t o_idx = tp_pos_bytes(P.hcap), o_stat = o_idx + tp_idx_bytes(P.ocap, G), o_kvo = o_stat + tp_i32_bytes(P.ocap),
+                 o_ncl = o_kvo + tp_i32_bytes(P.ocap), o_typ = o_ncl + tp_u16_bytes(P.ocap);
+    const int nbuf = A.nbuf;
 
-    const int lane = tid & 31, warp = tid >> 5, nwarps = TH >> 5;
-    const int gl = tid % G;      // lane within the atom's group
-    const int grp = tid / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane % G;      // lane within the atom's group
 
     // ---- tables for kind0, rows kmin..kmin+ktab : staged once per (persistent) CTA
     //      pass 1: {POTB[kk], POTB[kk+1]}         (one 16-byte read per pair)
     //      pass 2: {FPOTR[kk], FPOTB[kk]}         (rows kk and kk+1: two 16-byte reads)
     {
         const int stride = A.ntab + 2;
-        for (int r = threadIdx.x; r <= A.ktab; r += T) {
+        for (int r = threadIdx.x; r <= A.ktab + 1; r += NT) {
             const int kk = min(A.kmin + r, stride - 1);
             if (PASS == 1) {
                 const int k1 = min(kk + 1, stride - 1);
@@ -428,176 +467,156 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 s_tab[r] = make_double2(A.g_fpotr[(size_t)A.kind0 * stride + kk].x, A.g_fpotb[(size_t)A.kind0 * stride + kk].x);
             }
         }
-        if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        if (threadIdx.x == 0) {
+            for (int b = 0; b < nbuf; b++) {
+                mbar_init(&bar_full[b], 1);
+                mbar_init(&bar_ready[b], 32);
+                mbar_init(&bar_empty[b], NCW);
+                // the dummy record list tails point at: far from everything, finite
+                reinterpret_cast<double4 *>(buf0 + b * bufb)[P.hcap] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
+                if (MT) (buf0 + b * bufb + o_typ)[P.hcap] = 0;
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
-    unsigned phase = 0;
     // distance classes are usable while no atom has moved more than half the class margin since the rebuild
     const bool safe = __int_as_float(A.counters[CNT_D2MAX]) <= A.safe_d2;
+    const uint2 *nbl2 = reinterpret_cast<const uint2 *>(A.nbl);
+    // flat index of the class count of owned atom 0 (uint16 array [2][npad]) = ncl_base + own_start
+    const size_t ncl_base = (size_t)(PASS - 1) * P.npad;
 
-    // ---- per-tile descriptor values are prefetched one tile ahead so that no global-memory round trip
-    //      sits between the end of one tile and the TMA issue of the next
-    struct Pre { int htot, nhc, edge_any, own_start, own_slot0, own_count, cnt, slot, gst; };
-    auto prefetch = [&](int tile) {
-        Pre q;
-        q.htot = 0; q.nhc = 0; q.edge_any = 0; q.own_start = 0; q.own_slot0 = 0; q.own_count = 0; q.cnt = 0; q.slot = 0; q.gst = 0;
-        if (tile < A.tile_hi) {
-            const TileDesc &D = A.desc[tile];
-            q.htot = D.htot; q.nhc = D.nhc; q.edge_any = D.edge_any;
-            q.own_start = D.own_start; q.own_slot0 = D.own_slot0; q.own_count = D.own_count;
-            if (tid < TILE_MAX_HC) { q.cnt = D.cnt[tid]; q.slot = D.slot[tid]; q.gst = D.gst[tid]; }
-        }
-        return q;
-    };
-    const int tile_step = A.nparts * gridDim.x;
-    Pre cur = prefetch(A.tile_lo + A.nparts * blockIdx.x + half);
-
-    for (int tile = A.tile_lo + A.nparts * blockIdx.x + half; tile < A.tile_hi; tile += tile_step) {
-        const TileDesc &D = A.desc[tile];
-        bar_named(1 + half, TH);                     // every lane of the half is done with the previous halo
-        const int htot = cur.htot, nhc = cur.nhc;
-        const bool edge_any = cur.edge_any != 0;
-        const int own_start = cur.own_start, own_slot0 = cur.own_slot0, own_count = cur.own_count;
-        if (htot > P.hcap) { cur = prefetch(tile + tile_step); continue; } // counted by the list kernel; the host falls back
-        // ---- stage the halo: one TMA bulk copy per halo cell (contiguous run of 32-byte records)
-        if (tid == 0) mbar_expect_tx(mbar, (unsigned)htot * 32u);
-        if (tid < nhc && cur.cnt > 0) {
-            fence_proxy_async();
-            bulk_g2s(s_pos + cur.slot, A.pos + cur.gst, (unsigned)cur.cnt * 32u, mbar);
-        }
-        // while the copies are in flight: next tile's descriptor and this round's per-atom scalars / first indices
-        cur = prefetch(tile + tile_step);
-        int pre_kv = 0;
-        uint2 pre_idx = make_uint2(0u, 0u);
-        {
-            const int o = grp;
-            if (o < own_count) {
-                const int ia = own_start + o;
-                if ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE)
-                    pre_kv = safe ? (int)A.ncls[ia + (PASS - 1) * P.npad] : A.kvois[ia];
-                pre_idx = __ldcs(reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl));
+    if (warp == NCW) {
+        // =========================== producer warp ===========================
+        // Everything a stage needs arrives by TMA: halo runs, the first index group, and 16-byte aligned windows of
+        // STATU and of the scan counts around the owned range.  The descriptor of the NEXT tile is loaded one tile
+        // ahead and only used in the next iteration, so no global-memory round trip sits on the per-tile path.
+        struct Pre { int htot, nrun, edge_any, own_start, own_slot0, own_count, rs0, rs1, rgst; };
+        auto prefetch = [&](int tile) {
+            Pre q;
+            q.htot = 0; q.nrun = 0; q.edge_any = 0; q.own_start = 0; q.own_slot0 = 0; q.own_count = 0; q.rs0 = 0; q.rs1 = 0; q.rgst = 0;
+            if (tile < A.tile_hi) {
+                const TileDesc &D = A.desc[tile];
+                q.htot = D.htot; q.nrun = D.nrun; q.edge_any = D.edge_any;
+                q.own_start = D.own_start; q.own_slot0 = D.own_slot0; q.own_count = D.own_count;
+                q.rs0 = D.rslot[lane]; q.rs1 = D.rslot[lane + 1]; q.rgst = D.rgst[lane]; // lane r: run r (entries past nrun unused)
             }
-        }
-        mbar_wait(mbar, phase);
-        phase ^= 1u;
-        if (edge_any) {
-            // wrapped cells and cells on a periodic face (atoms the predictor may have wrapped since the
-            // rebuild): bring every atom to the image nearest to the nominal centre of its halo cell
-            const TileGeom g = tile_geom(P, tile);
-            for (int hc = warp; hc < nhc; hc += nwarps) {
-                if (D.sh[hc][3] == 0) continue;
-                const int cnt = D.cnt[hc], sl = D.slot[hc];
-                const int hx = hc % g.nhx, hyz = hc / g.nhx, hy = hyz % 3, hz = hyz / 3;
-                const double cx = P.lo[0] + ((double)(g.cx0 - 1 + hx) + 0.5) * P.cell[0];
-                const double cy = P.lo[1] + ((double)(g.cy - 1 + hy) + 0.5) * P.cell[1];
-                const double cz = P.lo[2] + ((double)(g.cz - 1 + hz) + 0.5) * P.cell[2];
-                for (int a = lane; a < cnt; a += 32) {
-                    double4 p = s_pos[sl + a];
-                    if (P.pd[0]) { const double d = p.x - cx; if (d > 0.5 * P.size[0]) p.x -= P.size[0]; else if (d < -0.5 * P.size[0]) p.x += P.size[0]; }
-                    if (P.pd[1]) { const double d = p.y - cy; if (d > 0.5 * P.size[1]) p.y -= P.size[1]; else if (d < -0.5 * P.size[1]) p.y += P.size[1]; }
-                    if (P.pd[2]) { const double d = p.z - cz; if (d > 0.5 * P.size[2]) p.z -= P.size[2]; else if (d < -0.5 * P.size[2]) p.z += P.size[2]; }
-                    s_pos[sl + a] = p;
+            return q;
+        };
+        int b = 0;
+        unsigned u = 0;
+        Pre nx = prefetch(A.tile_lo + blockIdx.x);
+        for (int tile = A.tile_lo + blockIdx.x; tile < A.tile_hi; tile += gridDim.x) {
+            const Pre cur = nx;
+            int own_count = cur.own_count;
+            const bool fits = cur.htot <= P.hcap && own_count <= P.ocap && cur.nrun <= TILE_MAX_RUN;
+            mbar_wait(&bar_empty[b], (u & 1u) ^ 1u);
+            unsigned char *bp = buf0 + b * bufb;
+            double4 *sp = reinterpret_cast<double4 *>(bp);
+            if (fits) {
+                // aligned windows: int32 arrays in units of 4 atoms, the uint16 counts in units of 8
+                const int a4 = cur.own_start & ~3, n4b = (((cur.own_start + own_count + 3) & ~3) - a4) * 4;
+                const size_t c0 = ncl_base + (size_t)cur.own_start, c8 = c0 & ~(size_t)7;
+                const int n8b = (int)(((c0 + own_count + 7) & ~(size_t)7) - c8) * 2;
+                if (lane == 0) {
+                    unsigned bytes = (unsigned)cur.htot * 32u;
+                    if (own_count > 0) bytes += (unsigned)own_count * (unsigned)(G * 8) + (unsigned)n4b + (unsigned)(safe ? n8b : n4b);
+                    mbar_expect_tx(&bar_full[b], bytes);
                 }
-            }
-            bar_named(1 + half, TH);
-        }
-        // packed filter coordinates (and types) for every staged atom
-        for (int s = tid; s < htot; s += TH) {
-            const double4 p = s_pos[s];
-            s_pk[s] = pack_q(p.x, p.y, p.z, P.inv_lsb);
-        }
-        if (MT) {
-            for (int hc = warp; hc < nhc; hc += nwarps) {
-                const int cnt = D.cnt[hc], sl = D.slot[hc], gst = D.gst[hc];
-                for (int a = lane; a < cnt; a += 32) s_typ[sl + a] = (unsigned char)(A.ityp[gst + a] - 1);
-            }
-        }
-        bar_named(1 + half, TH);
-
-        for (int base = 0; base < own_count; base += ngrp) {
-            const int o = base + grp;
-            const bool have = o < own_count;
-            const int ia = own_start + (have ? o : 0);
-            const int myslot = own_slot0 + (have ? o : 0);
-            const double4 me = s_pos[myslot];
-            const unsigned mypk = s_pk[myslot];
-            int kv;
-            uint2 nxt;
-            if (base == 0) { kv = pre_kv; nxt = pre_idx; }
-            else {
-                const bool active = have && ((A.statu[ia] & ST_ACTIVE) == ST_ACTIVE);
-                kv = active ? (safe ? (int)A.ncls[ia + (PASS - 1) * P.npad] : A.kvois[ia]) : 0;
-                nxt = make_uint2(0u, 0u);
-                if (kv > gl) nxt = __ldcs(reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl));
-            }
-            const int stat = have ? A.statu[ia] : 0;
-            const bool active = (stat & ST_ACTIVE) == ST_ACTIVE;
-            const int ti = MT ? (int)s_typ[myslot] : 0;
-            // fused epilogue: lane gl < 3 of the atom owns velocity/force component gl; its velocity is requested now
-            double vpre = 0.0;
-            if (PASS == 2 && A.fuse && active && gl < 3) vpre = A.xp1[ia + (size_t)gl * P.n];
-
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-            const int nm = (kv - gl + G - 1) / G;      // my entries are k = gl + G*m, m < nm
-            const int n4 = (nm + 3) >> 2;              // my 4-entry index groups
-            int it = 0;
-            const uint2 *ip = reinterpret_cast<const uint2 *>(A.nbl) + ((size_t)ia * G + gl);
-            const size_t ipstride = P.npad * G;
-            unsigned short *gq = s_q + grp;            // this atom's queue: entry e at gq[e * ngrp]
-            // software pipeline: nxt holds this lane's next 4-entry index group (already requested)
-
-            while (true) {
-                int gcnt = 0;                           // entries in the atom's queue (same on its G lanes)
-                // ---------------- phase A: stream the slot list, filter, push survivors
-                while (__any_sync(0xffffffffu, it < n4 && gcnt <= A.qcap - 4 * G)) {
-                    const bool go = it < n4 && gcnt <= A.qcap - 4 * G;
-                    const uint2 raw = nxt;
-                    const int lim = go ? nm - 4 * it : 0;   // valid entries in this group (>= 4 except in the tail)
-                    if (go) {
-                        it++; ip += ipstride;
-                        if (it < n4) nxt = __ldcs(ip);
-                    }
-                    const unsigned s0 = raw.x & 0xffffu, s1 = raw.x >> 16, s2 = raw.y & 0xffffu, s3 = raw.y >> 16;
-                    const unsigned p0 = s_pk[s0], p1 = s_pk[s1], p2 = s_pk[s2], p3 = s_pk[s3]; // tails are padded with slot 0
-                    unsigned m4 = filt(mypk, p0, A.r2int) | (filt(mypk, p1, A.r2int) << 1) | (filt(mypk, p2, A.r2int) << 2) |
-                                  (filt(mypk, p3, A.r2int) << 3);
-                    m4 &= (lim >= 4) ? 0xfu : ((1u << max(lim, 0)) - 1u);
-                    const int c = __popc(m4);
-                    int incl = c;                       // exclusive prefix of c over the G lanes of the atom
-#pragma unroll
-                    for (int w = 1; w < G; w <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, w, G);
-                        if (gl >= w) incl += t;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, incl, G - 1, G);
-                    unsigned short *w = gq + (size_t)(gcnt + incl - c) * ngrp;
-                    if (m4 & 1u) { *w = (unsigned short)s0; w += ngrp; }
-                    if (m4 & 2u) { *w = (unsigned short)s1; w += ngrp; }
-                    if (m4 & 4u) { *w = (unsigned short)s2; w += ngrp; }
-                    if (m4 & 8u) { *w = (unsigned short)s3; }
-                    gcnt += total;
-                }
-                const int mx = __reduce_max_sync(0xffffffffu, gcnt);
-                if (mx == 0) break;
                 __syncwarp();
-                // ---------------- phase B: drain in lock-step, lane gl takes entries gl, gl+G, ...
-                // software-pipelined: the next entry's slot and staged record are fetched before the current
-                // entry's arithmetic, so only the table read sits on the dependent chain
-                const unsigned short *rq = gq + (size_t)gl * ngrp;
-                const size_t rqstep = (size_t)G * ngrp;
-                int s_nxt = (gl < gcnt) ? (int)*rq : myslot;
-                double4 p_nxt = s_pos[s_nxt];
-#pragma unroll 1
-                for (int e = gl; e - gl < mx; e += G) {
-                    const bool on = e < gcnt;
-                    const int s = s_nxt;
-                    const double4 pj = p_nxt;
-                    rq += rqstep;
-                    s_nxt = (e + G < gcnt) ? (int)*rq : myslot;
-                    p_nxt = s_pos[s_nxt];
-                    const double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
+                fence_proxy_async(); // earlier generic accesses to the stage are ordered before the bulk copies
+                const int rcnt = lane < cur.nrun ? cur.rs1 - cur.rs0 : 0;
+                if (rcnt > 0) bulk_g2s(sp + cur.rs0, A.pos + cur.rgst, (unsigned)rcnt * 32u, &bar_full[b]);
+                if (own_count > 0) {
+                    if (lane == 0) bulk_g2s(bp + o_idx, nbl2 + (size_t)cur.own_start * G, (unsigned)own_count * (unsigned)(G * 8), &bar_full[b]);
+                    if (lane == 1) bulk_g2s(bp + o_stat, A.statu + a4, (unsigned)n4b, &bar_full[b]);
+                    if (lane == 2) {
+                        if (safe) bulk_g2s(bp + o_ncl, A.ncls + c8, (unsigned)n8b, &bar_full[b]);
+                        else bulk_g2s(bp + o_kvo, A.kvois + a4, (unsigned)n4b, &bar_full[b]);
+                    }
+                }
+            }
+            // next tile's descriptor: in flight while this tile's copies land, first used in the next iteration
+            nx = prefetch(tile + gridDim.x);
+            if (fits) {
+                if (MT) { // lane per halo cell: copy the types of its atoms
+                    const TileDesc &D = A.desc[tile];
+                    unsigned char *styp = bp + o_typ;
+                    const int nhc = D.nhc;
+                    for (int hc = lane; hc < nhc; hc += 32) {
+                        const int cnt = D.cnt[hc], sl = D.slot[hc], gst = D.gst[hc];
+#pragma unroll 4
+                        for (int a = 0; a < cnt; a++) styp[sl + a] = (unsigned char)(A.ityp[gst + a] - 1);
+                    }
+                }
+            } else {
+                // counted by the list kernel; the host falls back to the generic path
+                own_count = 0;
+                if (lane == 0) mbar_arrive(&bar_full[b]);
+            }
+            if (lane == 0) {
+                s_info[4 * b + 0] = cur.own_start; s_info[4 * b + 1] = cur.own_slot0; s_info[4 * b + 2] = own_count;
+                s_info[4 * b + 3] = cur.edge_any;
+                s_ctr[b] = 0;
+            }
+            mbar_arrive(&bar_ready[b]); // all 32 lanes: their writes to the stage are released to the consumers
+            if (++b == nbuf) { b = 0; u++; }
+        }
+    } else {
+        // =========================== consumer warps ===========================
+        int b = 0;
+        unsigned u = 0;
+        for (int tile = A.tile_lo + blockIdx.x; tile < A.tile_hi; tile += gridDim.x) {
+            mbar_wait(&bar_ready[b], u & 1u);
+            mbar_wait(&bar_full[b], u & 1u);
+            const int own_start = s_info[4 * b + 0], own_slot0 = s_info[4 * b + 1], own_count = s_info[4 * b + 2];
+            const bool edge_tile = s_info[4 * b + 3] != 0;
+            const unsigned char *bp = buf0 + b * bufb;
+            const double4 *sp = reinterpret_cast<const double4 *>(bp);
+            const uint2 *sidx = reinterpret_cast<const uint2 *>(bp + o_idx);
+            const int *sstat = reinterpret_cast<const int *>(bp + o_stat) + (own_start & 3);
+            const int *skvo = reinterpret_cast<const int *>(bp + o_kvo) + (own_start & 3);
+            const unsigned short *sncl = reinterpret_cast<const unsigned short *>(bp + o_ncl) + (int)((ncl_base + (size_t)own_start) & 7);
+            const unsigned char *styp = bp + o_typ;
+
+            // one chunk of APW owned atoms; EDGE: the tile touches a periodic face, separations take the minimum image
+            // exactly as the reference does (|SEP| > HBS -> SEP -= sign(BS, SEP), MD_EAM_ForceTable_GPU.F90:500-512)
+            auto chunk = [&](auto edge_tag, const int c0) {
+                constexpr bool EDGE = decltype(edge_tag)::value;
+                const int o = c0 + lane / G;
+                const bool have = o < own_count;
+                const int ia = own_start + (have ? o : 0);
+                const int myslot = have ? own_slot0 + o : P.hcap;
+                const double4 me = sp[myslot];
+                const int stat = have ? sstat[o] : 0;
+                const bool active = (stat & ST_ACTIVE) == ST_ACTIVE;
+                const int kv = active ? (safe ? (int)sncl[o] : skvo[o]) : 0;
+                const int n4 = (kv + 4 * G - 1) / (4 * G);   // 4-entry index groups per lane (same on the G lanes)
+                const int ti = MT ? (int)styp[myslot] : 0;
+                uint2 nxt = make_uint2(0u, 0u);
+                if (n4 > 0) nxt = sidx[o * G + gl];
+                const size_t gstride = P.npad * G;
+                const uint2 *gp = nbl2 + (gstride + (size_t)ia * G + gl);
+                double vpre = 0.0;
+                if (PASS == 2 && FUSE) {
+                    // lane gl < 3 of the atom owns velocity/force component gl; its velocity is requested now
+                    if (active && gl < 3) vpre = A.xp1[ia + (size_t)gl * P.n];
+                }
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+
+                // One listed entry, branch-free: the rare cases (table row outside the staged window, a pair of kinds
+                // other than KPAIR(1,1)) contribute nothing here and are flagged for pair_slow below, so the four
+                // entries of a group are independent straight-line code the scheduler can interleave.
+                auto eval = [&](const unsigned s) -> bool {
+                    const double4 pj = sp[s];
+                    double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
+                    if (EDGE) {
+                        if (P.pd[0]) { if (sx > 0.5 * P.size[0]) sx -= P.size[0]; else if (sx < -0.5 * P.size[0]) sx += P.size[0]; }
+                        if (P.pd[1]) { if (sy > 0.5 * P.size[1]) sy -= P.size[1]; else if (sy < -0.5 * P.size[1]) sy += P.size[1]; }
+                        if (P.pd[2]) { if (sz > 0.5 * P.size[2]) sz -= P.size[2]; else if (sz < -0.5 * P.size[2]) sz += P.size[2]; }
+                    }
                     const double r2 = fma(sz, sz, fma(sy, sy, sx * sx));
-                    const bool in = on && (r2 <= A.r2eff); // rows beyond the table support interpolate to exactly 0
+                    const bool in = r2 <= A.r2eff;                // rows beyond the table support interpolate to exactly 0
                     const double y = rsqrt_fast(r2);              // 1/r
                     const double r = r2 * y;
                     const double z = rsqrt_fast(r);               // 1/sqrt(r)
@@ -607,55 +626,71 @@ k_tile_pass(TileParams P, TilePassArgs A)
                     const double dk = sk - (tk - 4503599627370496.0);
                     const unsigned rr = (unsigned)(kk - A.kmin);
                     bool fast = in && rr < (unsigned)A.ktab;
-                    int tj = 0;
                     if (MT) {
-                        tj = (int)s_typ[s];
+                        const int tj = (int)styp[s];
                         fast = fast && A.kpair[ti + P.ng * tj] == A.kind0 && A.kpair[tj + P.ng * ti] == A.kind0;
                     }
                     const unsigned rs = fast ? rr : 0u;
                     if (PASS == 1) {
                         const double2 t0 = s_tab[rs];
-                        double val = fma(dk, t0.y - t0.x, t0.x);
-                        if (__any_sync(0xffffffffu, in && !fast)) { // outside the staged window / other kinds: rare, out of line
-                            if (in && !fast) val = lerp_slow(A.g_potb, A.ntab + 2, MT ? A.kpair[ti + P.ng * tj] : A.kind0, kk, dk);
-                        }
-                        if (in) acc0 += val;
+                        const double val = fma(dk, t0.y - t0.x, t0.x);
+                        if (fast) acc0 += val;
                     } else {
                         const double2 t0 = s_tab[rs], t1 = s_tab[rs + 1];
-                        double fr = fma(dk, t1.x - t0.x, t0.x);
-                        double fb0 = fma(dk, t1.y - t0.y, t0.y);
-                        double fb1 = fb0;
-                        if (__any_sync(0xffffffffu, in && !fast)) {
-                            if (in && !fast) {
-                                const int k0 = MT ? A.kpair[ti + P.ng * tj] : A.kind0, k1 = MT ? A.kpair[tj + P.ng * ti] : A.kind0;
-                                fr = lerp_slow(A.g_fpotr, A.ntab + 2, k0, kk, dk);
-                                fb0 = lerp_slow(A.g_fpotb, A.ntab + 2, k0, kk, dk);
-                                fb1 = MT ? lerp_slow(A.g_fpotb, A.ntab + 2, k1, kk, dk) : fb0;
-                            }
-                        }
+                        const double fr = fma(dk, t1.x - t0.x, t0.x);
+                        const double fb = fma(dk, t1.y - t0.y, t0.y);
                         // FORTOT = FPOTR/R2 + (FPOTB_ij*DEN_i + FPOTB_ji*DEN_j)/R     (:811-813)
-                        double ft = y * fma(fr, y, fma(fb0, me.w, fb1 * pj.w));
-                        ft = in ? ft : 0.0;
+                        double ft = y * fma(fr, y, fma(fb, me.w, fb * pj.w));
+                        ft = fast ? ft : 0.0;
                         acc0 = fma(ft, sx, acc0);
                         acc1 = fma(ft, sy, acc1);
                         acc2 = fma(ft, sz, acc2);
                     }
+                    return in && !fast;
+                };
+                auto redo = [&](const unsigned s) {
+                    double4 pj = sp[s];
+                    if (EDGE) { // the image of j nearest to i
+                        if (P.pd[0]) { const double d = me.x - pj.x; if (d > 0.5 * P.size[0]) pj.x += P.size[0]; else if (d < -0.5 * P.size[0]) pj.x -= P.size[0]; }
+                        if (P.pd[1]) { const double d = me.y - pj.y; if (d > 0.5 * P.size[1]) pj.y += P.size[1]; else if (d < -0.5 * P.size[1]) pj.y -= P.size[1]; }
+                        if (P.pd[2]) { const double d = me.z - pj.z; if (d > 0.5 * P.size[2]) pj.z += P.size[2]; else if (d < -0.5 * P.size[2]) pj.z -= P.size[2]; }
+                    }
+                    const int tj = MT ? (int)styp[s] : 0;
+                    const int k0 = MT ? A.kpair[ti + P.ng * tj] : A.kind0, k1 = MT ? A.kpair[tj + P.ng * ti] : A.kind0;
+                    const double f = pair_slow<PASS>(me, pj, A.csi, PASS == 1 ? A.g_potb : A.g_fpotr, A.g_fpotb, A.ntab + 2, k0, k1);
+                    if (PASS == 1) acc0 += f;
+                    else {
+                        acc0 = fma(f, me.x - pj.x, acc0);
+                        acc1 = fma(f, me.y - pj.y, acc1);
+                        acc2 = fma(f, me.z - pj.z, acc2);
+                    }
+                };
+
+#pragma unroll 1
+                for (int it = 0; it < n4; it++) {
+                    const uint2 raw = nxt;
+                    if (it + 1 < n4) { nxt = __ldcs(gp); gp += gstride; } // next group in flight during this one's arithmetic
+                    const unsigned s0 = raw.x & 0xffffu, s1 = raw.x >> 16, s2 = raw.y & 0xffffu, s3 = raw.y >> 16;
+                    const bool w0 = eval(s0), w1 = eval(s1), w2 = eval(s2), w3 = eval(s3);
+                    if (w0 | w1 | w2 | w3) {
+                        if (w0) redo(s0);
+                        if (w1) redo(s1);
+                        if (w2) redo(s2);
+                        if (w3) redo(s3);
+                    }
                 }
-                __syncwarp();
-            }
-            // ---------------- reduce the G partial sums of the atom and write
+                // ---------------- reduce the G partial sums of the atom and write
 #pragma unroll
-            for (int w = 1; w < G; w <<= 1) {
-                acc0 += __shfl_xor_sync(0xffffffffu, acc0, w);
-                if (PASS == 2) {
-                    acc1 += __shfl_xor_sync(0xffffffffu, acc1, w);
-                    acc2 += __shfl_xor_sync(0xffffffffu, acc2, w);
+                for (int w = 1; w < G; w <<= 1) {
+                    acc0 += __shfl_xor_sync(0xffffffffu, acc0, w);
+                    if (PASS == 2) {
+                        acc1 += __shfl_xor_sync(0xffffffffu, acc1, w);
+                        acc2 += __shfl_xor_sync(0xffffffffu, acc2, w);
+                    }
                 }
-            }
-            if (have && gl == 0) {
                 if (PASS == 1) {
-                    double den0 = acc0;
-                    if (active) {
+                    if (have && gl == 0) {
+                        double den0 = acc0; // kv = 0 for inactive atoms: 0
                         if (A.pot_type == MDB_POT_FS) {
                             if (den0 > 0.0) den0 = -0.5 / sqrt(den0);
                         } else if (den0 > 0.0) {
@@ -663,44 +698,57 @@ k_tile_pass(TileParams P, TilePassArgs A)
                             const int kk = (int)(sk + 0.000001);
                             den0 = lerp_g(A.g_dfembd, A.nembd + 2, A.kembd[ti], kk, sk - (double)kk);
                         }
-                    } else den0 = 0.0;
-                    reinterpret_cast<double *>(A.pos + ia)[3] = den0;
-                } else if (!A.fuse) {
-                    A.fp[ia] = acc0;
-                    A.fp[ia + (size_t)P.n] = acc1;
-                    A.fp[ia + 2 * (size_t)P.n] = acc2;
-                }
-            }
-            if (PASS == 2 && A.fuse) {
-                // EPC_MOD_KERNEL (MD_EP_Coupling_GPU.F90:468-490) + Correction_KERNEL (MD_DiffScheme_GPU.F90:735-753)
-                // on the fresh force; every lane of the group holds the reduced sums, lane d < 3 handles component d
-                const int l0 = (threadIdx.x & 31) & ~(G - 1);
-                const double vx = __shfl_sync(0xffffffffu, vpre, l0), vy = __shfl_sync(0xffffffffu, vpre, l0 + 1),
-                             vz = __shfl_sync(0xffffffffu, vpre, l0 + 2);
-                if (have && gl < 3) {
-                    double f = gl == 0 ? acc0 : (gl == 1 ? acc1 : acc2);
-                    if (active) {
-                        if ((A.fuse & 1) && A.epc.enable[ti] > 0) {
-                            const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
-                            if (v2 <= A.epc.eup[ti]) {
-                                const double tm = __dmul_rn(v2, A.epc.v2ti[ti]);
-                                const double mu = __ddiv_rn(__dmul_rn(A.epc.epa[ti], __dsub_rn(tm, A.epc.te[ti])), fmax(tm, A.epc.tcut[ti]));
-                                f = __dsub_rn(f, __dmul_rn(mu, vpre));
-                            }
-                        }
-                        const int fixbits = (ST_FIXVELX << gl) | (ST_FIXPOSX << gl);
-                        if ((A.fuse & 2) && (stat & fixbits) == 0)
-                            A.xp1[ia + (size_t)gl * P.n] = __dadd_rn(vpre, __dmul_rn(A.hs2, __ddiv_rn(f, A.mass.cm[ti])));
+                        reinterpret_cast<double *>(A.pos + ia)[3] = den0;
                     }
-                    A.fp[ia + (size_t)gl * P.n] = f;
+                } else if (!FUSE) {
+                    if (have && gl == 0) {
+                        A.fp[ia] = acc0;
+                        A.fp[ia + (size_t)P.n] = acc1;
+                        A.fp[ia + 2 * (size_t)P.n] = acc2;
+                    }
+                } else {
+                    // EPC_MOD_KERNEL (MD_EP_Coupling_GPU.F90:468-490) + Correction_KERNEL (MD_DiffScheme_GPU.F90:735-753)
+                    // on the fresh force; every lane of the group holds the reduced sums, lane d < 3 handles component d
+                    const int l0 = lane & ~(G - 1);
+                    const double vx = __shfl_sync(0xffffffffu, vpre, l0), vy = __shfl_sync(0xffffffffu, vpre, l0 + 1),
+                                 vz = __shfl_sync(0xffffffffu, vpre, l0 + 2);
+                    if (have && gl < 3) {
+                        double f = gl == 0 ? acc0 : (gl == 1 ? acc1 : acc2);
+                        if (active) {
+                            if ((A.fuse & 1) && A.epc.enable[ti] > 0) {
+                                const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+                                if (v2 <= A.epc.eup[ti]) {
+                                    const double tm = __dmul_rn(v2, A.epc.v2ti[ti]);
+                                    const double mu = __ddiv_rn(__dmul_rn(A.epc.epa[ti], __dsub_rn(tm, A.epc.te[ti])), fmax(tm, A.epc.tcut[ti]));
+                                    f = __dsub_rn(f, __dmul_rn(mu, vpre));
+                                }
+                            }
+                            const int fixbits = (ST_FIXVELX << gl) | (ST_FIXPOSX << gl);
+                            if ((A.fuse & 2) && (stat & fixbits) == 0)
+                                A.xp1[ia + (size_t)gl * P.n] = __dadd_rn(vpre, __dmul_rn(A.hs2, __ddiv_rn(f, A.mass.cm[ti])));
+                        }
+                        A.fp[ia + (size_t)gl * P.n] = f;
+                    }
                 }
+            };
+
+            while (true) {
+                int c0 = 0;
+                if (lane == 0) c0 = atomicAdd(&s_ctr[b], APW);
+                c0 = __shfl_sync(0xffffffffu, c0, 0);
+                if (c0 >= own_count) break;
+                if (edge_tile) chunk(std::true_type(), c0);
+                else chunk(std::false_type(), c0);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[b]);
+            if (++b == nbuf) { b = 0; u++; }
         }
     }
     // atoms parked outside the cells (out of box, inactive): zero outputs, as the generic path does
     if (blockIdx.x == 0 && A.zero_parked) {
         const int n_in = A.counters[CNT_INCELL];
-        for (int i = n_in + threadIdx.x; i < P.n; i += T) {
+        for (int i = n_in + threadIdx.x; i < P.n; i += NT) {
             if (PASS == 1) reinterpret_cast<double *>(A.pos + i)[3] = 0.0;
             else { A.fp[i] = 0.0; A.fp[i + (size_t)P.n] = 0.0; A.fp[i + 2 * (size_t)P.n] = 0.0; }
         }
@@ -711,19 +759,6 @@ k_tile_pass(TileParams P, TilePassArgs A)
 // host side: planning and launch
 // =====================================================================================
 static const int SMEM_BUDGET = 227 * 1024;
-
-static size_t half_smem_bytes(int hcap, int threads_half, int G, int qcap, bool mt)
-{
-    size_t b = 128 + (sizeof(double4) + sizeof(unsigned)) * (size_t)hcap + sizeof(unsigned short) * (size_t)qcap * (threads_half / G) +
-               (mt ? (size_t)hcap : 0);
-    return (b + 127) & ~(size_t)127;
-}
-static size_t pass_smem_bytes(int hcap, int ktab, int threads_half, int G, int qcap, bool mt, int nparts)
-{
-    size_t b = sizeof(double2) * (size_t)(ktab + 1);
-    b = (b + 127) & ~(size_t)127;
-    return b + (size_t)nparts * half_smem_bytes(hcap, threads_half, G, qcap, mt) + 128;
-}
 
 // largest Fortran row index with a non-zero entry in the kind-major host copy kept by the context
 static int last_nonzero_row(const std::vector<double> &t, int nkind, int ntab)
@@ -758,70 +793,50 @@ int mdb_tiled_plan(mdb_ctx *c)
     const double ru = std::sqrt(t.ru2max);
     S.margin = std::max(0.0, 0.25 * (rmmax - ru));
 
-    // ---- tile geometry: widest tile whose two halo buffers, queues and a useful table window fit
+    // ---- tile geometry: the widest tile (fewest halo atoms staged per owned atom) whose two pipeline stages
+    //      leave room for a table window that reaches down to 0.6 of the support edge's row (r ~ 0.36 r_eff;
+    //      closer pairs read the tables from global memory)
     const int G = S.G;
     const double rho_cell = (double)c->n / (double)c->nc;
     const bool mt = c->ng > 1;
-    const double dens = (double)c->n / ((double)c->nbox * c->box.size[0] * c->box.size[1] * c->box.size[2]);
-    for (int p = 0; p < 2; p++) {
-        const double rf = std::sqrt(S.r2eff[p]) + S.margin;
-        const int expect = (int)(4.18879 * rf * rf * rf * dens * 1.25) + 4 * G;
-        S.qcap[p] = std::max(8 * G, ((expect + 4 * G + 7) / 8) * 8);
-    }
-    const int qmax = std::max(S.qcap[0], S.qcap[1]);
-    // The CTA is split into np partitions of th threads, each owning one tile at a time.  Thread budget:
-    // 768 (G=4/8: 80 registers) or 512 (G=2: 128 registers).  Tiles are cut so that the mean number of owned
-    // atoms (+6 %) fills the th/G atom slots of a partition.
+    const int need = std::max(S.khi[0], S.khi[1]) + 1;
+    const int minrows = std::min(need, std::max(512, (int)(0.4 * need)));
     int best_w = 0;
-    const int tmax = (G == 2) ? 512 : 768;
-    for (int np = std::max(1, std::min(4, S.nparts_opt)); np >= 1 && !best_w; np--) {
-        const int th = (tmax / np / 32) * 32;               // threads per partition
-        const int slots = th / G;                            // owned atoms per round
-        const double own_target = (double)slots / 1.06 - 3.0;
-        int ntx0 = std::max(1, (int)std::ceil(c->ncell[0] * rho_cell / std::max(own_target, 1.0)));
-        ntx0 = std::min(ntx0, c->ncell[0]);
-        for (int ntx = ntx0; ntx <= c->ncell[0] && !best_w; ntx++) { // narrower tiles until everything fits
-            const int wt = (c->ncell[0] + ntx - 1) / ntx;
-            if (wt > TILE_MAX_W) continue;
-            const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64;
-            if (hcap > 16000) continue; // slots carry a 2-bit class tag while the list is built
-            const size_t fixed = pass_smem_bytes(hcap, 0, th, G, qmax, mt, np);
-            if (fixed + 16 * 512 + 1024 > (size_t)SMEM_BUDGET) continue;
-            const int maxrows = (int)((SMEM_BUDGET - fixed - 1024) / 16) - 2;
-            const int need = std::max(S.khi[0], S.khi[1]) + 1;
-            // the window must at least reach down to half the table index of the support edge (r ~ r_eff/4)
-            if (maxrows < need && maxrows < need / 2) continue;
-            best_w = wt;
-            S.ntx = ntx; S.hcap = hcap; S.threads = np * th; S.nparts = np;
-            for (int p = 0; p < 2; p++) {
-                S.ktab[p] = std::min(S.khi[p] + 1, maxrows);
-                S.kmin[p] = S.khi[p] + 1 - S.ktab[p];
-            }
+    const int nbuf = (S.stages_opt == 3) ? 3 : 2;
+    for (int ntx = 1; ntx <= c->ncell[0] && !best_w; ntx++) {
+        const int wt = (c->ncell[0] + ntx - 1) / ntx;
+        if (wt > TILE_MAX_W) continue;
+        const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64;
+        const int ocap = (((int)(wt * rho_cell * 1.25) + 32) + 7) & ~7;
+        if (hcap >= 16000) continue; // slots carry a 2-bit class tag while the list is built
+        const size_t fixed = TP_HDR_BYTES + nbuf * tp_buf_bytes(hcap, ocap, G, mt);
+        if (fixed + tp_tab_bytes(minrows) + 1024 > (size_t)SMEM_BUDGET) continue;
+        const int maxrows = (int)((SMEM_BUDGET - fixed - 1024) / 16) - 2;
+        best_w = wt;
+        S.ntx = ntx; S.hcap = hcap; S.ocap = ocap; S.nbuf = nbuf;
+        for (int p = 0; p < 2; p++) {
+            S.ktab[p] = std::min(S.khi[p] + 1, maxrows);
+            S.kmin[p] = S.khi[p] + 1 - S.ktab[p];
         }
     }
     if (!best_w) return MDB_OK;
+    if (S.threads_opt != 512 && S.threads_opt != 768) S.threads_opt = 768;
+    S.threads = S.threads_opt;
 
     TileParams &P = S.P;
     memset(&P, 0, sizeof(P));
     P.n = c->n; P.nbox = c->nbox; P.ncx = c->ncell[0]; P.ncy = c->ncell[1]; P.ncz = c->ncell[2]; P.nc0 = c->nc0;
-    P.ntx = S.ntx; P.nrows = c->nbox * c->ncell[1] * c->ncell[2]; P.ntiles = P.nrows * P.ntx; P.hcap = S.hcap;
+    P.ntx = S.ntx; P.nrows = c->nbox * c->ncell[1] * c->ncell[2]; P.ntiles = P.nrows * P.ntx; P.hcap = S.hcap; P.ocap = S.ocap;
     for (int d = 0; d < 3; d++) {
         P.pd[d] = c->box.pd[d]; P.lo[d] = c->box.lo[d]; P.size[d] = c->box.size[d];
         P.cell[d] = c->box.size[d] / (double)c->ncell[d];
         P.fbs[d] = (float)c->box.size[d];
     }
-    // phase-A quantum: RU spans 120 LSB, so every in-range coordinate difference fits a signed byte
-    const double lsb = ru / 120.0;
-    P.inv_lsb = 1.0 / lsb;
     P.ng = c->ng; P.mxkvois = c->mxkvois;
     const int rows_per_lane = (c->mxkvois + G - 1) / G;
     P.nrow4 = (rows_per_lane + 3) / 4;
     P.npad = (size_t)c->n;
     for (int p = 0; p < 2; p++) {
-        // floor() quantisation: each coordinate difference is off by < 1 LSB, the distance by < sqrt(3) LSB;
-        // 3 LSB leaves room for the rounding of x*inv_lsb itself
-        const double rl = std::sqrt(S.r2eff[p]) / lsb + 3.0;
-        S.r2int[p] = (int)(rl * rl) + 1;
         const double rc = std::sqrt(S.r2eff[p]) + S.margin;
         S.rc2f[p] = (float)(rc * rc);
     }
@@ -839,20 +854,17 @@ int mdb_tiled_plan(mdb_ctx *c)
     };
     const size_t nbl_bytes = (size_t)P.nrow4 * P.npad * G * 4 * sizeof(unsigned short);
     if (!ensure((void **)&S.nbl, S.nbl_elems, nbl_bytes)) return MDB_OK;
-    if (!ensure((void **)&S.ncls, S.ncls_bytes, 2 * P.npad * sizeof(unsigned short))) return MDB_OK;
+    if (!ensure((void **)&S.ncls, S.ncls_bytes, 2 * P.npad * sizeof(unsigned short) + 32)) return MDB_OK; // +32: aligned TMA windows
     if (!ensure((void **)&S.raw, S.raw_bytes, (size_t)c->mxkvois * c->n * sizeof(unsigned short))) return MDB_OK;
     if (!ensure((void **)&S.desc, S.desc_bytes, (size_t)P.ntiles * sizeof(TileDesc))) return MDB_OK;
     if (!ensure((void **)&c->dsr, c->dsr_bytes, 3 * (size_t)c->n * sizeof(float))) return MDB_OK;
     cudaMemsetAsync(c->dsr, 0, 3 * (size_t)c->n * sizeof(float), c->stream);
 
-    // ---- launch configuration
+    // ---- launch configuration: one persistent CTA per SM
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev);
-    S.grid = std::min((P.ntiles + S.nparts - 1) / S.nparts, nsm);
-    S.smem_list = ((sizeof(TileDesc) + 15) & ~(size_t)15) + sizeof(float4) * (size_t)S.hcap + 32;
-    if (S.smem_list > (size_t)SMEM_BUDGET) return MDB_OK;
-    S.grid_list = std::min(P.ntiles, nsm * std::max(1, std::min(8, (int)((SMEM_BUDGET + 1024) / (S.smem_list + 1024)))));
-    for (int p = 0; p < 2; p++) S.smem_pass[p] = pass_smem_bytes(S.hcap, S.ktab[p], S.threads / S.nparts, G, S.qcap[p], mt, S.nparts);
+    S.grid = std::min(P.ntiles, nsm);
+    for (int p = 0; p < 2; p++) S.smem_pass[p] = TP_HDR_BYTES + tp_tab_bytes(S.ktab[p]) + S.nbuf * tp_buf_bytes(S.hcap, S.ocap, G, mt);
     S.ok = true;
     return MDB_OK;
 }
@@ -902,7 +914,7 @@ int mdb_tiled_nlist(mdb_ctx *c)
     return mdb_fail(c, MDB_ERR_ARG, "tiled path: unsupported lane-group size %d", c->tiled.G);
 }
 
-template <int PASS, int G, bool MT>
+template <int PASS, int G, bool MT, bool FUSE, int NT>
 static int launch_pass(mdb_ctx *c, int fuse, double hs2)
 {
     TiledState &S = c->tiled;
@@ -912,45 +924,51 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.nbl = S.nbl; A.fp = c->fp; A.counters = c->counters; A.desc = (const TileDesc *)S.desc;
     A.g_potb = t.potb; A.g_fpotr = t.fpotr; A.g_fpotb = t.fpotb; A.g_dfembd = t.dfembd;
     A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod;
-    A.r2eff = S.r2eff[PASS - 1]; A.r2int = S.r2int[PASS - 1]; A.kmin = S.kmin[PASS - 1]; A.ktab = S.ktab[PASS - 1];
+    A.r2eff = S.r2eff[PASS - 1]; A.kmin = S.kmin[PASS - 1]; A.ktab = S.ktab[PASS - 1];
     A.kind0 = t.kpair[0];
-    A.qcap = S.qcap[PASS - 1];
-    A.nparts = S.nparts;
     A.safe_d2 = S.use_classes ? S.safe_d2 : -1.0f;
-    A.fuse = (PASS == 2) ? fuse : 0; A.hs2 = hs2; A.xp1 = c->xp1; A.epc = c->epc; A.mass = c->mass;
+    A.fuse = fuse; A.hs2 = hs2; A.xp1 = c->xp1; A.epc = c->epc; A.mass = c->mass;
     A.tile_lo = c->dd_on ? c->dd_info[14] : 0;
     A.tile_hi = c->dd_on ? c->dd_info[15] : S.P.ntiles;
     A.zero_parked = c->dd_on ? 0 : 1;
+    A.nbuf = S.nbuf;
     if (!c->epc.on) A.fuse &= ~1;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
-    auto kern = k_tile_pass<PASS, G, MT>;
+    auto kern = k_tile_pass<PASS, G, MT, FUSE, NT>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_pass[PASS - 1]));
     ProfScope ps(c, PASS == 1 ? MDB_K_PASS1 : MDB_K_PASS2);
-    kern<<<S.grid, S.threads, S.smem_pass[PASS - 1], c->stream>>>(S.P, A);
+    kern<<<S.grid, NT, S.smem_pass[PASS - 1], c->stream>>>(S.P, A);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
 
-template <int G>
+template <int G, bool MT, int NT>
 static int launch_force(mdb_ctx *c, unsigned flags, int fuse, double hs2)
 {
-    const bool mt = c->ng > 1;
     int rc = MDB_OK;
-    if ((flags & (MDB_FORCE | MDB_DEN)) && !(flags & MDB_NOPASS1))
-        rc = mt ? launch_pass<1, G, true>(c, 0, 0.0) : launch_pass<1, G, false>(c, 0, 0.0);
+    if ((flags & (MDB_FORCE | MDB_DEN)) && !(flags & MDB_NOPASS1)) rc = launch_pass<1, G, MT, false, NT>(c, 0, 0.0);
     if (rc < 0) return rc;
-    if (flags & MDB_FORCE) rc = mt ? launch_pass<2, G, true>(c, fuse, hs2) : launch_pass<2, G, false>(c, fuse, hs2);
+    if (flags & MDB_FORCE) rc = fuse ? launch_pass<2, G, MT, true, NT>(c, fuse, hs2) : launch_pass<2, G, MT, false, NT>(c, 0, 0.0);
     return rc;
+}
+
+template <int G>
+static int launch_force_g(mdb_ctx *c, unsigned flags, int fuse, double hs2)
+{
+    const bool mt = c->ng > 1;
+    if (c->tiled.threads == 512)
+        return mt ? launch_force<G, true, 512>(c, flags, fuse, hs2) : launch_force<G, false, 512>(c, flags, fuse, hs2);
+    return mt ? launch_force<G, true, 768>(c, flags, fuse, hs2) : launch_force<G, false, 768>(c, flags, fuse, hs2);
 }
 
 // fuse: bit 0 = EPC friction, bit 1 = corrector half-kick with hs2 = H/2, applied in the epilogue of pass 2
 int mdb_force_tiled(mdb_ctx *c, unsigned flags, int fuse, double hs2)
 {
     switch (c->tiled.G) {
-    case 2: return launch_force<2>(c, flags, fuse, hs2);
-    case 4: return launch_force<4>(c, flags, fuse, hs2);
-    case 8: return launch_force<8>(c, flags, fuse, hs2);
+    case 2: return launch_force_g<2>(c, flags, fuse, hs2);
+    case 4: return launch_force_g<4>(c, flags, fuse, hs2);
+    case 8: return launch_force_g<8>(c, flags, fuse, hs2);
     }
     return mdb_fail(c, MDB_ERR_ARG, "tiled path: unsupported lane-group size %d", c->tiled.G);
 }

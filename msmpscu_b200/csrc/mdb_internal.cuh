@@ -57,10 +57,10 @@ struct TileParams {
     int n, nbox, ncx, ncy, ncz, nc0;
     int ntx, nrows, ntiles;        // tiles per x-row, rows, total tiles
     int hcap;                      // halo capacity in atoms (shared-memory budget)
+    int ocap;                      // owned-atom capacity of a tile
     int pd[3];
     double lo[3], size[3], cell[3];
     float fbs[3];                  // (float)BOXSIZE: the fp32 image shift of the list kernel
-    double inv_lsb;                // 1 / LSB of the packed fixed-point filter coordinates
     int ng, mxkvois, nrow4;        // nrow4 = 4-entry index groups per (atom, lane)
     size_t npad;                   // padded atom count of the slot list
 };
@@ -70,14 +70,13 @@ struct TiledState {
     TileParams P;
     bool ok = false, dirty = true, active = false;
     int G = 4;                 // lanes per atom
-    int ntx = 0, hcap = 0, threads = 0, grid = 0, grid_list = 0;
-    int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0}, r2int[2] = {0, 0}, qcap[2] = {0, 0};
+    int ntx = 0, hcap = 0, ocap = 0, threads = 0, threads_opt = 768, grid = 0, nbuf = 2, stages_opt = 2;
+    int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0};
     double r2eff[2] = {0.0, 0.0};
-    size_t smem_list = 0, smem_pass[2] = {0, 0};
+    size_t smem_pass[2] = {0, 0};
     double margin = 0.0;       // class margin (length): classes hold while every atom moved < margin/2
     float rc2f[2] = {0.f, 0.f}, safe_d2 = 0.f;
     bool use_classes = true;
-    int nparts = 2, nparts_opt = 2; // tiles in flight per SM (partitions of the pass CTA)
     unsigned short *nbl = nullptr; size_t nbl_elems = 0;   // slot list (bytes in nbl_elems)
     unsigned short *raw = nullptr; size_t raw_bytes = 0;   // reference-order slots + class tag
     unsigned short *ncls = nullptr; size_t ncls_bytes = 0; // per-atom class counts [2][npad]

@@ -13,8 +13,9 @@
 #pragma once
 #include "mdb_internal.cuh"
 
-#define TILE_MAX_W      12                         // cells per tile along x: (W+3)*256 packed codes must fit 12 bits
+#define TILE_MAX_W      12                         // cells per tile along x
 #define TILE_MAX_HC     ((TILE_MAX_W + 2) * 9)     // halo cells per tile
+#define TILE_MAX_RUN    32                         // contiguous runs of halo cells per tile (one per producer lane)
 #define NBL_UNROLL      4                          // list entries per 8-byte index load
 
 struct TileGeom { // per-tile values, computed by every thread from blockIdx-independent tile id
