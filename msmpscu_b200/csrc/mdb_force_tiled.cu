@@ -608,12 +608,16 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 // other than KPAIR(1,1)) contribute nothing here and are flagged for pair_slow below, so the four
                 // entries of a group are independent straight-line code the scheduler can interleave.
                 auto eval = [&](const unsigned s) -> bool {
-                    const double4 pj = sp[s];
-                    double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
-                    if (EDGE) {
-                        if (P.pd[0]) { if (sx > 0.5 * P.size[0]) sx -= P.size[0]; else if (sx < -0.5 * P.size[0]) sx += P.size[0]; }
-                        if (P.pd[1]) { if (sy > 0.5 * P.size[1]) sy -= P.size[1]; else if (sy < -0.5 * P.size[1]) sy += P.size[1]; }
-                        if (P.pd[2]) { if (sz > 0.5 * P.size[2]) sz -= P.size[2]; else if (sz < -0.5 * P.size[2]) sz += P.size[2]; }
+                    // the record is read as two 16-byte halves; odd lanes fetch {z,den} first, so that each LDS.128 of the
+                    // warp spreads over all eight 16-byte bank groups instead of the four a 32-byte stride allows
+                    const double2 *rec = reinterpret_cast<const double2 *>(sp + s);
+                    const double2 ha = rec[lane & 1], hb = rec[(lane & 1) ^ 1];
+                    const double2 pxy = (lane & 1) ? hb : ha, pzw = (lane & 1) ? ha : hb;
+                    double sx = me.x - pxy.x, sy = me.y - pxy.y, sz = me.z - pzw.x;
+                    if (EDGE) { // P.half = BOXSIZE/2 on periodic axes, huge otherwise
+                        if (fabs(sx) > P.half[0]) sx -= copysign(P.size[0], sx);
+                        if (fabs(sy) > P.half[1]) sy -= copysign(P.size[1], sy);
+                        if (fabs(sz) > P.half[2]) sz -= copysign(P.size[2], sz);
                     }
                     const double r2 = fma(sz, sz, fma(sy, sy, sx * sx));
                     const bool in = r2 <= A.r2eff;                // rows beyond the table support interpolate to exactly 0
@@ -640,7 +644,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
                         const double fr = fma(dk, t1.x - t0.x, t0.x);
                         const double fb = fma(dk, t1.y - t0.y, t0.y);
                         // FORTOT = FPOTR/R2 + (FPOTB_ij*DEN_i + FPOTB_ji*DEN_j)/R     (:811-813)
-                        double ft = y * fma(fr, y, fma(fb, me.w, fb * pj.w));
+                        double ft = y * fma(fr, y, fma(fb, me.w, fb * pzw.y));
                         ft = fast ? ft : 0.0;
                         acc0 = fma(ft, sx, acc0);
                         acc1 = fma(ft, sy, acc1);
@@ -651,9 +655,9 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 auto redo = [&](const unsigned s) {
                     double4 pj = sp[s];
                     if (EDGE) { // the image of j nearest to i
-                        if (P.pd[0]) { const double d = me.x - pj.x; if (d > 0.5 * P.size[0]) pj.x += P.size[0]; else if (d < -0.5 * P.size[0]) pj.x -= P.size[0]; }
-                        if (P.pd[1]) { const double d = me.y - pj.y; if (d > 0.5 * P.size[1]) pj.y += P.size[1]; else if (d < -0.5 * P.size[1]) pj.y -= P.size[1]; }
-                        if (P.pd[2]) { const double d = me.z - pj.z; if (d > 0.5 * P.size[2]) pj.z += P.size[2]; else if (d < -0.5 * P.size[2]) pj.z -= P.size[2]; }
+                        if (fabs(me.x - pj.x) > P.half[0]) pj.x += copysign(P.size[0], me.x - pj.x);
+                        if (fabs(me.y - pj.y) > P.half[1]) pj.y += copysign(P.size[1], me.y - pj.y);
+                        if (fabs(me.z - pj.z) > P.half[2]) pj.z += copysign(P.size[2], me.z - pj.z);
                     }
                     const int tj = MT ? (int)styp[s] : 0;
                     const int k0 = MT ? A.kpair[ti + P.ng * tj] : A.kind0, k1 = MT ? A.kpair[tj + P.ng * ti] : A.kind0;
@@ -831,6 +835,7 @@ int mdb_tiled_plan(mdb_ctx *c)
         P.pd[d] = c->box.pd[d]; P.lo[d] = c->box.lo[d]; P.size[d] = c->box.size[d];
         P.cell[d] = c->box.size[d] / (double)c->ncell[d];
         P.fbs[d] = (float)c->box.size[d];
+        P.half[d] = c->box.pd[d] ? 0.5 * c->box.size[d] : 1.0e300;
     }
     P.ng = c->ng; P.mxkvois = c->mxkvois;
     const int rows_per_lane = (c->mxkvois + G - 1) / G;

@@ -60,6 +60,7 @@ struct TileParams {
     int ocap;                      // owned-atom capacity of a tile
     int pd[3];
     double lo[3], size[3], cell[3];
+    double half[3];                // BOXSIZE/2 on periodic axes, 1e300 otherwise (minimum-image test of the passes)
     float fbs[3];                  // (float)BOXSIZE: the fp32 image shift of the list kernel
     int ng, mxkvois, nrow4;        // nrow4 = 4-entry index groups per (atom, lane)
     size_t npad;                   // padded atom count of the slot list
