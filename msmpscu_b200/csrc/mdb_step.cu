@@ -11,26 +11,42 @@
 // trajectories track the oracle as closely as the force sums allow.
 #include "mdb_internal.cuh"
 
-// one atom of the predictor; returns |displacement since the last rebuild|^2 (0 when not tracked)
+// one atom of the predictor; returns |displacement since the last rebuild|^2 (0 when not tracked).
+// pre != 0: the EPC friction (bit 0) and the corrector half-kick (bit 1) of the PREVIOUS step are applied first, on
+// the values already in registers -- the same operations k_epc_correct performs, one pass over XP1/FP saved.
 __device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict__ pos, double *__restrict__ xp1,
-                                              const double *__restrict__ fp, double *__restrict__ dis,
+                                              double *__restrict__ fp, double *__restrict__ dis,
                                               int *__restrict__ statu, const int *__restrict__ ityp, const MassParams &M,
                                               const BoxParams &box, double th, double h2s2, double hs2,
-                                              float *__restrict__ dsr)
+                                              float *__restrict__ dsr, int pre, const EpcParams &E)
 {
     const int stat = statu[i];
-    const double cm0 = M.cm[ityp[i] - 1];
+    const int kk = ityp[i] - 1;
+    const double cm0 = M.cm[kk];
     double4 p = pos[i];
     double x[3] = {p.x, p.y, p.z};
     const int fixp[3] = {ST_FIXPOSX, ST_FIXPOSY, ST_FIXPOSZ};
     const int fixv[3] = {ST_FIXVELX, ST_FIXVELY, ST_FIXVELZ};
+    double v[3], f[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { v[d] = xp1[i + (size_t)d * n]; f[d] = fp[i + (size_t)d * n]; }
+    if ((pre & 1) && E.enable[kk] > 0) { // EPC_MOD_KERNEL, MD_EP_Coupling_GPU.F90:473-490
+        const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2]));
+        if (v2 <= E.eup[kk]) {
+            const double tm = __dmul_rn(v2, E.v2ti[kk]);
+            const double mu = __ddiv_rn(__dmul_rn(E.epa[kk], __dsub_rn(tm, E.te[kk])), fmax(tm, E.tcut[kk]));
+#pragma unroll
+            for (int d = 0; d < 3; d++) { f[d] = __dsub_rn(f[d], __dmul_rn(mu, v[d])); fp[i + (size_t)d * n] = f[d]; }
+        }
+    }
     float d2 = 0.f;
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         const size_t o = i + (size_t)d * n;
-        const double v = xp1[o];
-        const double a = __ddiv_rn(fp[o], cm0);                                  // FP/CM0 :309-311
-        double dd = __dadd_rn(__dmul_rn(th, v), __dmul_rn(h2s2, a));           // TH*XP1 + H2S2*FP :314
+        const double a = __ddiv_rn(f[d], cm0);                                  // FP/CM0 :309-311
+        const bool freev = (stat & fixv[d]) == 0 && (stat & fixp[d]) == 0;
+        if ((pre & 2) && freev) v[d] = __dadd_rn(v[d], __dmul_rn(hs2, a));      // Correction_KERNEL :735-753
+        double dd = __dadd_rn(__dmul_rn(th, v[d]), __dmul_rn(h2s2, a));        // TH*XP1 + H2S2*FP :314
         if ((stat & fixp[d]) == fixp[d]) dd = 0.0;
         double xx = __dadd_rn(x[d], dd);
         if (box.pd[d]) {                                                         // :317-325
@@ -38,7 +54,7 @@ __device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict_
             else if (xx < box.lo[d]) xx = __dadd_rn(xx, box.size[d]);
         }
         x[d] = xx;
-        if ((stat & fixv[d]) == 0 && (stat & fixp[d]) == 0) xp1[o] = __dadd_rn(v, __dmul_rn(hs2, a)); // :353-361
+        if (freev) xp1[o] = __dadd_rn(v[d], __dmul_rn(hs2, a));                 // :353-361
         dis[o] = __dadd_rn(dis[o], dd);                                          // :371-373
         if (dsr) { // un-wrapped displacement accumulated since the last neighbour rebuild (fp32 is ample)
             const float t = dsr[o] + (float)dd;
@@ -54,15 +70,15 @@ __device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict_
     return d2;
 }
 
-__global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, const double *__restrict__ fp,
+__global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, double *__restrict__ fp,
                           double *__restrict__ dis, int *__restrict__ statu, const int *__restrict__ ityp,
                           MassParams M, BoxParams box, double th, double h2s2, double hs2,
-                          float *__restrict__ dsr, int *__restrict__ counters, int a0, int a1)
+                          float *__restrict__ dsr, int *__restrict__ counters, int a0, int a1, int pre, EpcParams E)
 {
     const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     float d2 = 0.f;
     if (i < a1 && (statu[i] & ST_ACTIVE) == ST_ACTIVE) // :295
-        d2 = predict_atom(i, n, pos, xp1, fp, dis, statu, ityp, M, box, th, h2s2, hs2, dsr);
+        d2 = predict_atom(i, n, pos, xp1, fp, dis, statu, ityp, M, box, th, h2s2, hs2, dsr, pre, E);
     if (dsr) { // block maximum -> one atomic per block; the tiled passes compare it with their class margin
         for (int off = 16; off > 0; off >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, off));
         __shared__ float smax[8];
@@ -126,19 +142,26 @@ __global__ void k_ekin(int n, const double *__restrict__ xp1, const int *__restr
 }
 
 // ------------------------------------------------------------------------------------
+// pre: bit 0 = EPC friction, bit 1 = corrector of the previous step, fused in front of this predictor (mdb_run)
+static int predict_launch(mdb_ctx *c, double h, int pre)
+{
+    // Predictor_DEV :660-662 : TH = H, HS2 = TH/2, H2S2 = TH*TH/2
+    const double th = h, hs2 = th * 0.5, h2s2 = th * th * 0.5;
+    if (!c->epc.on) pre &= ~1;
+    ProfScope ps(c, MDB_K_PREDICT);
+    k_predict<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp,
+                                                                     c->mass, c->box, th, h2s2, hs2, c->dsr, c->counters,
+                                                                     own_a0(c), own_a1(c), pre, c->epc);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
 extern "C" int mdb_predict(mdb_ctx *c, double h)
 {
     if (!c) return MDB_ERR_ARG;
     if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_predict: mdb_box_set first");
     CUDA_TRY(c, cudaSetDevice(c->dev));
-    // Predictor_DEV :660-662 : TH = H, HS2 = TH/2, H2S2 = TH*TH/2
-    const double th = h, hs2 = th * 0.5, h2s2 = th * th * 0.5;
-    ProfScope ps(c, MDB_K_PREDICT);
-    k_predict<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp,
-                                                                     c->mass, c->box, th, h2s2, hs2, c->dsr, c->counters,
-                                                                     own_a0(c), own_a1(c));
-    CUDA_TRY(c, cudaGetLastError());
-    return MDB_OK;
+    return predict_launch(c, h, 0);
 }
 
 extern "C" int mdb_correct(mdb_ctx *c, double h)
@@ -225,18 +248,22 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     return mdb_force_generic(c, flags, vtensor);
 }
 
-static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)
+// One For_One_Step without host synchronisation.  first / last: position inside an mdb_run block -- between two
+// steps of a block the EPC friction + corrector of step s run fused in front of the predictor of step s+1.
+static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h, bool first, bool last)
 {
     int rc;
-    if ((rc = mdb_predict(c, h)) < 0) return rc;
+    const bool fused_epilogue = c->opt_fuse_epilogue && c->tiled.active && c->has_tables && c->shape_identity;
+    if ((rc = predict_launch(c, h, (first || fused_epilogue) ? 0 : 3)) < 0) return rc;
     if (nb_uptab > 0 && (itime - it0) % nb_uptab == 0) { // MOD(ITIME-IT0,NB_UPTAB)==0, GenericMD:599-601
         if ((rc = mdb_list_rebuild(c)) < 0) return rc;
     }
-    if (c->opt_fuse_epilogue && c->tiled.active && c->has_tables && c->list_valid && c->shape_identity) {
+    if (fused_epilogue && c->list_valid) {
         // EPC friction and the corrector are fused into the epilogue of the force pass
         return mdb_force_tiled(c, MDB_FORCE, 3, h * 0.5);
     }
     if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
+    if (!last) return MDB_OK; // applied by the next step's predictor kernel
     ProfScope ps(c, MDB_K_CORRECT);
     k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
                                                           h * 0.5, c->epc.on, 1, 0, c->n);
@@ -253,7 +280,7 @@ extern "C" int mdb_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab
     CUDA_TRY(c, cudaSetDevice(c->dev));
     CUDA_TRY(c, cudaMemsetAsync(c->counters + CNT_OOB_TOTAL, 0, sizeof(int), c->stream));
     for (int s = 0; s < nsteps; s++) {
-        int rc = step_nosync(c, itime0 + s, it0, nb_uptab, h);
+        int rc = step_nosync(c, itime0 + s, it0, nb_uptab, h, s == 0, s == nsteps - 1);
         if (rc < 0) return rc;
     }
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
