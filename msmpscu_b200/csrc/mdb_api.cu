@@ -123,6 +123,7 @@ static void free_state(mdb_ctx *c)
     dfree(c->ic); dfree(c->ic_alt); dfree(c->xp_view); dfree(c->den_view);
     dfree(c->slot); dfree(c->srcof); dfree(c->tmp_orig); dfree(c->oob); dfree(c->vpart);
     dfree(c->dsr); c->dsr_bytes = 0;
+    dfree(c->pos_snap); c->pos_snap_bytes = 0;
     if (c->stage) { cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
     c->has_box = false;
 }
@@ -466,7 +467,7 @@ extern "C" void *mdb_devptr(mdb_ctx *c, int field)
         k_down_pos<<<nb, 256, 0, c->stream>>>(n, 1, c->pos, c->den_view, nullptr);
         c->launches_total++;
         return c->den_view;
-    case MDB_F_INDI: return c->indi;
+    case MDB_F_INDI: return mdb_indi_ensure(c) == MDB_OK ? c->indi : nullptr;
     case MDB_F_POS4: return c->pos;                      // internal {x,y,z,den} records (ghost exchange)
     case MDB_F_D2MAX: return c->counters + CNT_D2MAX;    // max displacement^2 since the rebuild (float bits)
     }
@@ -626,9 +627,12 @@ extern "C" int mdb_nlist_build(mdb_ctx *c)
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (c->tiled.active && c->h_counters[CNT_TILE_OVERFLOW] > 0) {
-        // a tile's halo did not fit its shared-memory budget (strongly non-uniform density)
+        // a tile's halo / an atom's list did not fit its shared-memory budget (strongly non-uniform density), or an
+        // atom has more than mxKVOIS neighbours (the reference truncates in ITS scan order, which only the generic
+        // kernel reproduces)
         if (c->opt_force_path == MDB_FORCE_PATH_TILED)
-            return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path: %d tiles exceed the halo capacity", c->h_counters[CNT_TILE_OVERFLOW]);
+            return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path: %d tiles / cells exceed the halo, list or mxKVOIS capacity",
+                            c->h_counters[CNT_TILE_OVERFLOW]);
         c->tiled.ok = false; // AUTO: fall back to the generic path and rebuild
         rc = mdb_list_rebuild(c);
         if (rc < 0) return rc;
@@ -641,6 +645,19 @@ extern "C" int mdb_nlist_build(mdb_ctx *c)
         if ((rc = mdb_dd_update(c)) < 0) return rc;
     }
     return c->h_counters[CNT_OOB];
+}
+
+// After a rebuild on the tiled path only the slot lists exist.  The reference-format INDI(N,mxKVOIS) -- same
+// members, reference order -- is produced here, on demand, by the generic list kernel from the positions saved at
+// that rebuild (cells, types and the sort order are frozen between rebuilds).
+int mdb_indi_ensure(mdb_ctx *c)
+{
+    if (!c->has_nlist || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "no valid neighbour list");
+    if (!c->tiled.active || !c->indi_stale) return MDB_OK;
+    int rc = mdb_nlist_kernel(c, c->pos_snap);
+    if (rc < 0) return rc;
+    c->indi_stale = false;
+    return MDB_OK;
 }
 
 // cell sort + list kernel of the active path, no host synchronisation
@@ -659,6 +676,7 @@ int mdb_list_rebuild(mdb_ctx *c)
     c->tiled.active = c->tiled.ok && c->opt_force_path != MDB_FORCE_PATH_GENERIC;
     int rc = mdb_cells_build(c);
     if (rc < 0) return rc;
+    c->indi_stale = false;
     rc = c->tiled.active ? mdb_tiled_nlist(c) : mdb_nlist_kernel(c);
     if (rc < 0) return rc;
     c->list_valid = true;
@@ -743,6 +761,8 @@ extern "C" int mdb_nlist_copyout(mdb_ctx *c, int *kvois, int *indi, int order)
         if (rc) return rc;
     }
     if (indi) {
+        int rc = mdb_indi_ensure(c);
+        if (rc < 0) return rc;
         size_t bytes = sizeof(int) * (size_t)n * c->mxkvois;
         if (order == MDB_ORDER_CELL) {
             CUDA_TRY(c, cudaMemcpyAsync(indi, c->indi, bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -123,15 +123,15 @@ __device__ __forceinline__ void build_halo_table(const TileParams &P, const Tile
 // list build
 // =====================================================================================
 struct TileListArgs {
-    const double4 *pos; const int *ityp; const int *nac; const int *naac; const int *ia1th;
-    int *kvois; int *indi; unsigned short *nbl; unsigned short *ncls; unsigned short *raw; int *counters; TileDesc *desc;
-    int cell_lo, cell_hi; // cells of this rank (slab decomposition), all cells otherwise
+    const double4 *pos; const int *ityp; const int *naac;
+    int *kvois; unsigned short *nbl; unsigned short *ncls; int *counters; const TileDesc *desc;
+    int tile_lo;          // first tile of this rank (slab decomposition), 0 otherwise
+    int lcap;             // rows of the per-atom shared-memory list
     float rm2[MDB_MXGROUP * MDB_MXGROUP];
     float rc2[2]; // class radii^2 (build-time, fp32): class 0 <= rc2[0] < class 1 <= rc2[1] < class 2
 };
 
 #define NL_THREADS 128
-#define NL_WARPS (NL_THREADS / 32)
 
 // tile descriptors: one small CTA per tile
 __global__ void __launch_bounds__(NL_THREADS)
@@ -149,120 +149,190 @@ k_tile_desc(TileParams P, const int *__restrict__ nac, const int *__restrict__ i
     if (threadIdx.x == 0 && (H.htot > P.hcap || H.own_count > P.ocap || H.nrun > TILE_MAX_RUN)) atomicAdd(&counters[CNT_TILE_OVERFLOW], 1);
 }
 
-// One warp per cell (lanes = atoms of the cell), no block-level synchronisation: every lane of the warp walks
-// the same 27-cell candidate stream, staged 32 at a time in a warp-private tile as
-// SPOS = (float)(XP + (double)(float)shift) (:1100-1103).  Accepted neighbours go to the reference-format INDI
-// (global ids, reference order) and, as halo SLOTS of the cell's tile tagged with their distance class, to a
-// scratch list ([k][atom], coalesced); the lane then partitions its own scratch list by class into the
-// lane-interleaved layout the passes stream (nbl_index).  Tails are padded with the dummy slot P.hcap.
-template <int G>
-__global__ void __launch_bounds__(NL_THREADS)
+// One CTA per tile, one warp per owned cell (lanes = atoms of the cell).  The tile's halo is staged once in shared
+// memory as the reference's fp32 candidate SPOS = (float)(XP + (double)(float)shift) (:1100-1103) with the type in
+// .w; every lane then walks the 27 neighbour cells as 9 contiguous slot ranges (broadcast reads), decides
+// membership with the reference's fp32 expression and appends accepted halo SLOTS, tagged with their build-distance
+// class, to its own column of a shared-memory list.  The column is then partitioned by class in place and written
+// out in the lane-interleaved layout the passes stream (nbl_index); tails are padded with the dummy slot P.hcap.
+// The ORDER of a list is free here (the passes only sum over it): the reference-ordered KVOIS/INDI pair is
+// produced on demand by the generic kernel from the positions saved at the rebuild (mdb_indi_ensure).  An atom
+// with more neighbours than the list capacity or than mxKVOIS (where the reference truncates in ITS order) sends
+// the whole build to the generic path through CNT_TILE_OVERFLOW.
+// ---- packed fp32 helpers: two candidates per instruction (FADD2 / FMUL2).  Only the subtraction and the squares
+// are packed: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would change the reference's rounding,
+// so the two sums stay scalar add.rn.f32 (never contracted).
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi)
+{
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long f2_sq(unsigned long long a)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(d) : "l"(a));
+    return d;
+}
+__device__ __forceinline__ float f2_lo(unsigned long long a) { return __uint_as_float((unsigned)a); }
+__device__ __forceinline__ float f2_hi(unsigned long long a) { return __uint_as_float((unsigned)(a >> 32)); }
+// predicated 16-bit shared-memory store through a 32-bit shared address
+__device__ __forceinline__ void sts16_if(unsigned addr, unsigned val, bool p)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.u16 [%0], %1;\n}\n" ::"r"(addr), "h"((unsigned short)val), "r"((unsigned)p) : "memory");
+}
+
+template <int G, bool MT>
+__global__ void __launch_bounds__(32 * TILE_MAX_W)
 k_tile_nlist(TileParams P, TileListArgs A)
 {
-    __shared__ float4 tile_s[NL_WARPS][32];
-    __shared__ unsigned short stage[4 * G][NL_THREADS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int ic0 = A.cell_lo + blockIdx.x * NL_WARPS + wib;   // global cell id (0-based)
-    if (ic0 >= A.cell_hi) return;
-    if (A.naac[ic0] <= 0) return;                              // cells without ACTIVE atoms are skipped (:981-982)
-    const int ccnt = A.nac[ic0];
-    if (ccnt <= 0) return;                                     // :1018
-    // which tile / which cell of the tile
-    const int box = ic0 / P.nc0, icl = ic0 - box * P.nc0;
-    const int ncxy = P.ncx * P.ncy;
-    const int iz = icl / ncxy, iy = (icl - iz * ncxy) / P.ncx, ix = icl - iz * ncxy - iy * P.ncx;
-    const int tx = ((ix + 1) * P.ntx + P.ncx - 1) / P.ncx - 1;
-    const int tileid = ((box * P.ncz + iz) * P.ncy + iy) * P.ntx + tx;
-    const TileDesc &D = A.desc[tileid];
-    if (D.htot > P.hcap) return;
-    const int cx0 = (int)(((long long)tx * P.ncx) / P.ntx);
-    const int nhx = (int)(((long long)(tx + 1) * P.ncx) / P.ntx) - cx0 + 2;
-    const int hxc = ix - cx0 + 1;
-    const int myhc = (1 * 3 + 1) * nhx + hxc;
-    const int cgst = A.ia1th[ic0] - 1, csl = D.slot[myhc];
+    extern __shared__ __align__(16) unsigned char nl_smem[];
+    __shared__ TileDesc H;
+    // halo as PAIRS of candidates: hxy[p] = {x(2p), x(2p+1), y(2p), y(2p+1)}, hzt[p] = {z, z, type, type}
+    const int npair = (P.hcap + 2) / 2;
+    float4 *hxy = reinterpret_cast<float4 *>(nl_smem);
+    float4 *hzt = hxy + npair;
+    float *fxy = reinterpret_cast<float *>(hxy), *fzt = reinterpret_cast<float *>(hzt);
+    unsigned short *lists = reinterpret_cast<unsigned short *>(hzt + npair);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int tile = A.tile_lo + blockIdx.x;
+    {
+        const int *src = reinterpret_cast<const int *>(A.desc + tile);
+        int *dst = reinterpret_cast<int *>(&H);
+        for (int i = threadIdx.x; i < (int)(sizeof(TileDesc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (H.htot > P.hcap || H.own_count > P.ocap || H.nrun > TILE_MAX_RUN) return; // counted by k_tile_desc
+    const int nhc = H.nhc, nhx = nhc / 9;
+    // ---- stage the halo
+    for (int hc = warp; hc < nhc; hc += nwarps) {
+        const int cnt = H.cnt[hc];
+        if (H.cid[hc] < 0 || cnt <= 0) continue;
+        const int sl = H.slot[hc], gst = H.gst[hc];
+        const float s0 = H.sh[hc][0] * P.fbs[0], s1 = H.sh[hc][1] * P.fbs[1], s2 = H.sh[hc][2] * P.fbs[2];
+        for (int a = lane; a < cnt; a += 32) {
+            const double4 q = A.pos[gst + a];
+            const int s = sl + a, o = (s >> 1) * 4 + (s & 1);
+            fxy[o] = __double2float_rn(__dadd_rn(q.x, (double)s0));
+            fxy[o + 2] = __double2float_rn(__dadd_rn(q.y, (double)s1));
+            fzt[o] = __double2float_rn(__dadd_rn(q.z, (double)s2));
+            fzt[o + 2] = __int_as_float(MT ? A.ityp[gst + a] : 1);
+        }
+    }
+    __syncthreads();
+    const int wt = nhx - 2;
+    if (warp >= wt) return;
+    const int myhc = 4 * nhx + warp + 1;           // centre row (hy = hz = 1), cell hx = warp + 1
+    const int ccnt = H.cnt[myhc];
+    if (ccnt <= 0) return;                         // :1018
+    if (A.naac[H.cid[myhc]] <= 0) return;          // cells without ACTIVE atoms are skipped (:981-982)
+    const int cgst = H.gst[myhc], csl = H.slot[myhc];
     const float rm1 = A.rm2[0], rc0 = A.rc2[0], rc1 = A.rc2[1];
-    float4 *tl = tile_s[wib];
+    unsigned short *col = lists + (size_t)warp * A.lcap * 32 + lane;   // entry k of this lane at col[k * 32]
+    const unsigned col_a = (unsigned)__cvta_generic_to_shared(col);
+    const int lcap = A.lcap;
 
     for (int ab = 0; ab < ccnt; ab += 32) {
         const bool valid = ab + lane < ccnt;
-        const int ia = cgst + ab + lane;
+        const int ia = cgst + ab + (valid ? lane : 0);
         const int myslot = csl + ab + (valid ? lane : 0);
-        float4 me = make_float4(0.f, 0.f, 0.f, __int_as_float(1));
-        if (valid) {
-            const double4 p = A.pos[ia];
-            me = make_float4(__double2float_rn(p.x), __double2float_rn(p.y), __double2float_rn(p.z),
-                             __int_as_float(A.ityp[ia]));  // POS = (float)XP_i :1080-1082
-        }
-        const int ity = __float_as_int(me.w);
-        int nn = 0, n0 = 0, n1 = 0;
-        int *pI = A.indi + ia;                 // next INDI / scratch entry of this atom (stride N per entry)
-        unsigned short *pR = A.raw + ia;
-        const int room = valid ? P.mxkvois : 0;
-        for (int k = 0; k < 27; k++) {
-            const int hc = ((1 + t_niz[k]) * 3 + (1 + t_niy[k])) * nhx + (hxc + t_nix[k]);
-            if (D.cid[hc] < 0) continue;
-            const int sl = D.slot[hc], cnt = D.cnt[hc], gst = D.gst[hc];
-            const float s0 = D.sh[hc][0] * P.fbs[0], s1 = D.sh[hc][1] * P.fbs[1], s2 = D.sh[hc][2] * P.fbs[2];
-            for (int cb = 0; cb < cnt; cb += 32) {
-                const int nb = min(32, cnt - cb);
-                if (lane < nb) {
-                    const double4 q = A.pos[gst + cb + lane];
-                    float4 s;
-                    s.x = __double2float_rn(__dadd_rn(q.x, (double)s0));
-                    s.y = __double2float_rn(__dadd_rn(q.y, (double)s1));
-                    s.z = __double2float_rn(__dadd_rn(q.z, (double)s2));
-                    s.w = __int_as_float(A.ityp[gst + cb + lane]);
-                    tl[lane] = s;
-                }
-                __syncwarp();
-                // acceptance mask over the 32 staged candidates (no branch per candidate) ...
-                unsigned mask = 0u;
-#pragma unroll 4
-                for (int t = 0; t < nb; t++) {
-                    const float4 s = tl[t];
-                    const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
-                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
-                    const float rm = (P.ng == 1) ? rm1 : A.rm2[(ity - 1) + P.ng * (__float_as_int(s.w) - 1)];
-                    mask |= (unsigned)(r2 <= rm) << t; // :1123
-                }
-                const int selfbit = myslot - (sl + cb);
-                if ((unsigned)selfbit < 32u) mask &= ~(1u << selfbit); // I .ne. IA :1124
-                // ... then the set bits are emitted in ascending order: the list order stays the reference's
-                while (__any_sync(0xffffffffu, mask != 0u)) {
-                    if (mask) {
-                        const int t = __ffs(mask) - 1;
-                        mask &= mask - 1u;
-                        if (nn < room) {
-                            const float4 s = tl[t];
-                            const float e1 = __fsub_rn(me.x, s.x), e2 = __fsub_rn(me.y, s.y), e3 = __fsub_rn(me.z, s.z);
-                            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
-                            *pI = gst + cb + t + 1;
-                            const unsigned c0 = r2 <= rc0, c1 = r2 <= rc1;
-                            n0 += c0; n1 += c1;
-                            *pR = (unsigned short)((unsigned)(sl + cb + t) | ((2u - c0 - c1) << 14));
-                            pI += P.n; pR += P.n;
-                        }
-                        nn++;
-                    }
-                }
-                __syncwarp();
+        const int mo = (myslot >> 1) * 4 + (myslot & 1);
+        const float mx = fxy[mo], my = fxy[mo + 2], mz = fzt[mo];   // POS = (float)XP_i :1080-1082 (own cells carry no shift)
+        const int ity = MT ? __float_as_int(fzt[mo + 2]) : 1;
+        const unsigned long long mx2 = f2_pack(mx, mx), my2 = f2_pack(my, my), mz2 = f2_pack(mz, mz);
+        unsigned pa = col_a;                           // shared address of the next free entry of this lane
+        const unsigned pa_end = col_a + (valid ? (unsigned)lcap * 64u : 0u); // invalid lanes accept nothing
+        int nover = 0;                                 // accepted beyond the capacity
+
+        // one candidate / one aligned pair of candidates; SELF: the range holds the lane's own atom (:1124);
+        // CAP: the list may fill up inside this range
+        auto accept = [&](auto self_tag, auto cap_tag, const int s, const float r2, const float rm) {
+            constexpr bool SELF = decltype(self_tag)::value, CAP = decltype(cap_tag)::value;
+            bool hit = r2 <= rm;                                            // :1123
+            if (SELF) hit = hit && (s != myslot);
+            const unsigned e = (unsigned)s + ((r2 > rc0) ? 0x4000u : 0u) + ((r2 > rc1) ? 0x4000u : 0u);
+            bool st = hit;
+            if (CAP) { st = hit && (pa < pa_end); nover += (hit && !st) ? 1 : 0; }
+            sts16_if(pa, e, st);
+            pa += st ? 64u : 0u;
+        };
+        auto one = [&](auto self_tag, auto cap_tag, const int s) {
+            const int o = (s >> 1) * 4 + (s & 1);
+            const float e1 = __fsub_rn(mx, fxy[o]), e2 = __fsub_rn(my, fxy[o + 2]), e3 = __fsub_rn(mz, fzt[o]);
+            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(e1, e1), __fmul_rn(e2, e2)), __fmul_rn(e3, e3));
+            const float rm = MT ? A.rm2[(ity - 1) + P.ng * (__float_as_int(fzt[o + 2]) - 1)] : rm1;
+            accept(self_tag, cap_tag, s, r2, rm);
+        };
+        auto range = [&](auto self_tag, auto cap_tag, int s, const int s_hi) {
+            if (s < s_hi && (s & 1)) { one(self_tag, cap_tag, s); s++; }
+#pragma unroll 2
+            for (; s + 1 < s_hi; s += 2) {
+                const float4 a = hxy[s >> 1], b = hzt[s >> 1];
+                const unsigned long long ex = f2_sub(mx2, f2_pack(a.x, a.y)), ey = f2_sub(my2, f2_pack(a.z, a.w)),
+                                         ez = f2_sub(mz2, f2_pack(b.x, b.y));
+                const unsigned long long qx = f2_sq(ex), qy = f2_sq(ey), qz = f2_sq(ez);
+                const float r20 = __fadd_rn(__fadd_rn(f2_lo(qx), f2_lo(qy)), f2_lo(qz));
+                const float r21 = __fadd_rn(__fadd_rn(f2_hi(qx), f2_hi(qy)), f2_hi(qz));
+                const float rma = MT ? A.rm2[(ity - 1) + P.ng * (__float_as_int(b.z) - 1)] : rm1;
+                const float rmb = MT ? A.rm2[(ity - 1) + P.ng * (__float_as_int(b.w) - 1)] : rm1;
+                accept(self_tag, cap_tag, s, r20, rma);
+                accept(self_tag, cap_tag, s + 1, r21, rmb);
+            }
+            if (s < s_hi) one(self_tag, cap_tag, s);
+        };
+#pragma unroll 1
+        for (int r = 0; r < 9; r++) {
+            const int hc0 = r * nhx + warp;            // cells hx = warp, warp+1, warp+2 of halo row r: contiguous slots
+            const int s_lo = H.slot[hc0], s_hi = H.slot[hc0 + 3];
+            // warp-uniform choice: can any lane run out of list rows inside this range?
+            const int used = (int)((pa - col_a) >> 6);
+            const bool tight = __any_sync(0xffffffffu, used + (s_hi - s_lo) > lcap);
+            if (r == 4) {
+                if (tight) range(std::true_type(), std::true_type(), s_lo, s_hi);
+                else range(std::true_type(), std::false_type(), s_lo, s_hi);
+            } else {
+                if (tight) range(std::false_type(), std::true_type(), s_lo, s_hi);
+                else range(std::false_type(), std::false_type(), s_lo, s_hi);
             }
         }
+        int nn = (int)((pa - col_a) >> 6);
+        if (!valid) { nn = 0; nover = 0; }
+        const int nall = nn + nover;
+        if (__any_sync(0xffffffffu, nover > 0 || nall > P.mxkvois)) {
+            if (lane == 0) atomicAdd(&A.counters[CNT_TILE_OVERFLOW], 1);
+        }
+        {
+            int m = nall;
+            for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+            if (lane == 0) atomicMax(&A.counters[CNT_NNMAX], m);
+        }
         if (!valid) continue;
-        const int kv = min(nn, P.mxkvois);
-        A.kvois[ia] = kv; // silently truncated :1195
-        if (nn > P.mxkvois) atomicAdd(&A.counters[CNT_OVERFLOW], 1);
-        atomicMax(&A.counters[CNT_NNMAX], nn);
-        // class-ordered, lane-interleaved slot list: three sweeps over the lane's own scratch entries (one per
-        // class); 4G consecutive output entries form one contiguous 8G-byte block [gl][m%4] of the layout, so
-        // they are collected in a shared staging column and written with full 16-byte stores
-        n1 -= n0; // n0 = class 0, n1 = class 1
-        int pos = 0, dbase = 0;
-        auto flush = [&]() {
+        A.kvois[ia] = min(nn, P.mxkvois);
+        // ---- three-way partition of the column by class tag (order inside a class is free)
+        int lo = 0, mid = 0, hi = nn - 1;
+        while (mid <= hi) {
+            const unsigned e = col[mid * 32];
+            const unsigned t = e >> 14;
+            if (t == 0u) { const unsigned f = col[lo * 32]; col[lo * 32] = (unsigned short)e; col[mid * 32] = (unsigned short)f; lo++; mid++; }
+            else if (t == 1u) mid++;
+            else { const unsigned f = col[hi * 32]; col[hi * 32] = (unsigned short)e; col[mid * 32] = (unsigned short)f; hi--; }
+        }
+        A.ncls[ia] = (unsigned short)lo;               // class 0
+        A.ncls[ia + P.npad] = (unsigned short)mid;     // classes 0+1
+        // ---- write out: 4G consecutive entries form one contiguous 8G-byte block [gl][m%4] of the layout
+        const unsigned pad = (unsigned)P.hcap;
+        for (int q = 0; q * 4 * G < nn; q++) {
             unsigned short blk[4 * G];
 #pragma unroll
-            for (int j = 0; j < 4 * G; j++) blk[(j % G) * 4 + j / G] = (j < pos) ? stage[j][threadIdx.x] : (unsigned short)P.hcap;
-            uint4 *dst = reinterpret_cast<uint4 *>(A.nbl + ((((size_t)(dbase / (4 * G)) * P.npad + (size_t)ia) * G) << 2));
+            for (int j = 0; j < 4 * G; j++) {
+                const int k = q * 4 * G + j;
+                blk[(j % G) * 4 + j / G] = (k < nn) ? (unsigned short)(col[k * 32] & 0x3fffu) : (unsigned short)pad;
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(A.nbl + ((((size_t)q * P.npad + (size_t)ia) * G) << 2));
 #pragma unroll
             for (int v = 0; v < (4 * G) / 8; v++) {
                 uint4 w;
@@ -272,36 +342,9 @@ k_tile_nlist(TileParams P, TileListArgs A)
                 w.w = blk[8 * v + 6] | ((unsigned)blk[8 * v + 7] << 16);
                 dst[v] = w;
             }
-            dbase += 4 * G;
-            pos = 0;
-        };
-        for (unsigned cls = 0; cls < 3u; cls++) {
-            int k = 0;
-            for (; k + 4 <= kv; k += 4) { // four independent loads in flight
-                unsigned e[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) e[u] = A.raw[ia + (size_t)(k + u) * P.n];
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if ((e[u] >> 14) == cls) {
-                        stage[pos][threadIdx.x] = (unsigned short)(e[u] & 0x3fffu);
-                        if (++pos == 4 * G) flush();
-                    }
-            }
-            for (; k < kv; k++) {
-                const unsigned e = A.raw[ia + (size_t)k * P.n];
-                if ((e >> 14) == cls) {
-                    stage[pos][threadIdx.x] = (unsigned short)(e & 0x3fffu);
-                    if (++pos == 4 * G) flush();
-                }
-            }
         }
-        if (pos > 0) flush(); // the tail block is padded with the dummy slot (hcap: a record far from everything)
-        A.ncls[ia] = (unsigned short)n0;
-        A.ncls[ia + P.npad] = (unsigned short)(n0 + n1);
     }
 }
-
 
 // =====================================================================================
 // force passes
@@ -860,7 +903,7 @@ int mdb_tiled_plan(mdb_ctx *c)
     const size_t nbl_bytes = (size_t)P.nrow4 * P.npad * G * 4 * sizeof(unsigned short);
     if (!ensure((void **)&S.nbl, S.nbl_elems, nbl_bytes)) return MDB_OK;
     if (!ensure((void **)&S.ncls, S.ncls_bytes, 2 * P.npad * sizeof(unsigned short) + 32)) return MDB_OK; // +32: aligned TMA windows
-    if (!ensure((void **)&S.raw, S.raw_bytes, (size_t)c->mxkvois * c->n * sizeof(unsigned short))) return MDB_OK;
+    if (!ensure((void **)&c->pos_snap, c->pos_snap_bytes, sizeof(double4) * (size_t)c->n)) return MDB_OK;
     if (!ensure((void **)&S.desc, S.desc_bytes, (size_t)P.ntiles * sizeof(TileDesc))) return MDB_OK;
     if (!ensure((void **)&c->dsr, c->dsr_bytes, 3 * (size_t)c->n * sizeof(float))) return MDB_OK;
     cudaMemsetAsync(c->dsr, 0, 3 * (size_t)c->n * sizeof(float), c->stream);
@@ -869,6 +912,19 @@ int mdb_tiled_plan(mdb_ctx *c)
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->dev);
     S.grid = std::min(P.ntiles, nsm);
+    // list kernel: one warp per owned cell; per-atom shared-memory list of lcap rows (expected neighbours + 45 %)
+    {
+        const double dens = (double)c->n / ((double)c->nbox * c->box.size[0] * c->box.size[1] * c->box.size[2]);
+        const int expect = (int)(4.18879 * rmmax * rmmax * rmmax * dens);
+        S.wmax = best_w;
+        S.lcap = std::min(c->mxkvois, ((int)(1.45 * expect) + 24 + 7) & ~7);
+        S.smem_list = sizeof(float4) * 2 * (size_t)((S.hcap + 2) / 2) + sizeof(unsigned short) * 32 * (size_t)S.lcap * S.wmax;
+        while (S.smem_list > (size_t)SMEM_BUDGET - 4096 && S.lcap > 32) {
+            S.lcap -= 8;
+            S.smem_list = sizeof(float4) * 2 * (size_t)((S.hcap + 2) / 2) + sizeof(unsigned short) * 32 * (size_t)S.lcap * S.wmax;
+        }
+        if (S.smem_list > (size_t)SMEM_BUDGET - 4096) return MDB_OK;
+    }
     for (int p = 0; p < 2; p++) S.smem_pass[p] = TP_HDR_BYTES + tp_tab_bytes(S.ktab[p]) + S.nbuf * tp_buf_bytes(S.hcap, S.ocap, G, mt);
     S.ok = true;
     return MDB_OK;
@@ -879,42 +935,49 @@ void mdb_tiled_free(mdb_ctx *c)
     TiledState &S = c->tiled;
     if (S.nbl) cudaFree(S.nbl);
     if (S.ncls) cudaFree(S.ncls);
-    if (S.raw) cudaFree(S.raw);
     if (S.desc) cudaFree(S.desc);
-    S.nbl = nullptr; S.ncls = nullptr; S.raw = nullptr; S.desc = nullptr;
-    S.nbl_elems = S.raw_bytes = S.ncls_bytes = S.desc_bytes = 0;
+    S.nbl = nullptr; S.ncls = nullptr; S.desc = nullptr;
+    S.nbl_elems = S.ncls_bytes = S.desc_bytes = 0;
     S.ok = false; S.dirty = true; S.active = false;
 }
 
-template <int G>
+template <int G, bool MT>
 static int launch_list(mdb_ctx *c)
 {
     TiledState &S = c->tiled;
     TileListArgs A;
-    A.pos = c->pos; A.ityp = c->ityp; A.nac = c->nac; A.naac = c->naac; A.ia1th = c->ia1th;
-    A.kvois = c->kvois; A.indi = c->indi; A.nbl = S.nbl; A.ncls = S.ncls; A.raw = S.raw; A.counters = c->counters;
-    A.desc = (TileDesc *)S.desc;
+    A.pos = c->pos; A.ityp = c->ityp; A.naac = c->naac;
+    A.kvois = c->kvois; A.nbl = S.nbl; A.ncls = S.ncls; A.counters = c->counters;
+    A.desc = (const TileDesc *)S.desc;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
     A.rc2[0] = S.rc2f[0]; A.rc2[1] = S.rc2f[1];
-    A.cell_lo = 0; A.cell_hi = c->nc;
+    A.lcap = S.lcap;
+    int tile_lo = 0, tile_hi = S.P.ntiles;
     if (c->dd_on) { // owned z-layers of cells: the descriptors are cheap and built for every tile
-        const int cl = c->ncell[0] * c->ncell[1];
-        A.cell_lo = (int)(((long long)c->dd_rank * c->ncell[2]) / c->dd_n) * cl;
-        A.cell_hi = (int)(((long long)(c->dd_rank + 1) * c->ncell[2]) / c->dd_n) * cl;
+        const int tiles_per_layer = c->ncell[1] * S.ntx;
+        tile_lo = (int)(((long long)c->dd_rank * c->ncell[2]) / c->dd_n) * tiles_per_layer;
+        tile_hi = (int)(((long long)(c->dd_rank + 1) * c->ncell[2]) / c->dd_n) * tiles_per_layer;
     }
+    A.tile_lo = tile_lo;
+    auto kern = k_tile_nlist<G, MT>;
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
     ProfScope ps(c, MDB_K_NLIST, 2);
     k_tile_desc<<<S.P.ntiles, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters);
-    k_tile_nlist<G><<<cdiv(A.cell_hi - A.cell_lo, NL_WARPS), NL_THREADS, 0, c->stream>>>(S.P, A);
+    if (tile_hi > tile_lo) kern<<<tile_hi - tile_lo, 32 * S.wmax, S.smem_list, c->stream>>>(S.P, A);
     CUDA_TRY(c, cudaGetLastError());
+    // the reference-format KVOIS/INDI pair is rebuilt on demand from the positions of this moment
+    CUDA_TRY(c, cudaMemcpyAsync(c->pos_snap, c->pos, sizeof(double4) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    c->indi_stale = true;
     return MDB_OK;
 }
 
 int mdb_tiled_nlist(mdb_ctx *c)
 {
+    const bool mt = c->ng > 1;
     switch (c->tiled.G) {
-    case 2: return launch_list<2>(c);
-    case 4: return launch_list<4>(c);
-    case 8: return launch_list<8>(c);
+    case 2: return mt ? launch_list<2, true>(c) : launch_list<2, false>(c);
+    case 4: return mt ? launch_list<4, true>(c) : launch_list<4, false>(c);
+    case 8: return mt ? launch_list<8, true>(c) : launch_list<8, false>(c);
     }
     return mdb_fail(c, MDB_ERR_ARG, "tiled path: unsupported lane-group size %d", c->tiled.G);
 }

@@ -71,15 +71,14 @@ struct TiledState {
     TileParams P;
     bool ok = false, dirty = true, active = false;
     int G = 4;                 // lanes per atom
-    int ntx = 0, hcap = 0, ocap = 0, threads = 0, threads_opt = 768, grid = 0, nbuf = 2, stages_opt = 2;
+    int ntx = 0, hcap = 0, ocap = 0, wmax = 0, lcap = 0, threads = 0, threads_opt = 768, grid = 0, nbuf = 2, stages_opt = 2;
     int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0};
     double r2eff[2] = {0.0, 0.0};
-    size_t smem_pass[2] = {0, 0};
+    size_t smem_pass[2] = {0, 0}, smem_list = 0;
     double margin = 0.0;       // class margin (length): classes hold while every atom moved < margin/2
     float rc2f[2] = {0.f, 0.f}, safe_d2 = 0.f;
     bool use_classes = true;
     unsigned short *nbl = nullptr; size_t nbl_elems = 0;   // slot list (bytes in nbl_elems)
-    unsigned short *raw = nullptr; size_t raw_bytes = 0;   // reference-order slots + class tag
     unsigned short *ncls = nullptr; size_t ncls_bytes = 0; // per-atom class counts [2][npad]
     void *desc = nullptr; size_t desc_bytes = 0;           // TileDesc per tile
 };
@@ -125,6 +124,9 @@ struct mdb_ctx {
     int *h_counters = nullptr; // pinned mirror
     int mxkvois = 0;
     int *kvois = nullptr, *indi = nullptr;
+    // tiled path: INDI (and the reference-ordered KVOIS) are produced on demand from the positions of the last rebuild
+    bool indi_stale = false;
+    double4 *pos_snap = nullptr; size_t pos_snap_bytes = 0;
     int oob_total = 0;
 
     // ---- tables
@@ -186,7 +188,8 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 // ---- internal entry points across translation units
 int mdb_cells_build(mdb_ctx *c);             // mdb_cells.cu : bin, sort, permute
-int mdb_nlist_kernel(mdb_ctx *c);            // mdb_nlist.cu : fill KVOIS/INDI
+int mdb_nlist_kernel(mdb_ctx *c, const double4 *pos = nullptr); // mdb_nlist.cu : fill KVOIS/INDI (pos: override positions)
+int mdb_indi_ensure(mdb_ctx *c);             // mdb_api.cu : materialise INDI after a tiled rebuild
 int mdb_force_generic(mdb_ctx *c, unsigned flags, double *vt); // mdb_force.cu
 int mdb_tiled_plan(mdb_ctx *c);               // mdb_force_tiled.cu
 int mdb_tiled_nlist(mdb_ctx *c);

@@ -113,7 +113,7 @@ k_nlist_cellwarp(NlistParams P, const double4 *__restrict__ pos, const int *__re
     }
 }
 
-int mdb_nlist_kernel(mdb_ctx *c)
+int mdb_nlist_kernel(mdb_ctx *c, const double4 *pos)
 {
     NlistParams P;
     P.n = c->n; P.nc = c->nc; P.nc0 = c->nc0; P.ncx = c->ncell[0]; P.ncy = c->ncell[1]; P.ncz = c->ncell[2];
@@ -123,7 +123,7 @@ int mdb_nlist_kernel(mdb_ctx *c)
     P.identity = c->shape_identity ? 1 : 0;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) P.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
     ProfScope ps(c, MDB_K_NLIST);
-    k_nlist_cellwarp<<<cdiv(c->nc, NL_WARPS), NL_WARPS * 32, 0, c->stream>>>(P, c->pos, c->ityp, c->nac, c->naac,
+    k_nlist_cellwarp<<<cdiv(c->nc, NL_WARPS), NL_WARPS * 32, 0, c->stream>>>(P, pos ? pos : c->pos, c->ityp, c->nac, c->naac,
                                                                              c->ia1th, c->kvois, c->indi, c->counters);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;

@@ -242,7 +242,11 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
             if (rc < 0) return rc;
         }
         const unsigned rest = flags & ~fast;
-        if (rest & (MDB_VIRIAL | MDB_EPOT)) return mdb_force_generic(c, rest & ~MDB_DEN, vtensor);
+        if (rest & (MDB_VIRIAL | MDB_EPOT)) {
+            int rc = mdb_indi_ensure(c); // the generic kernels walk the reference-format list
+            if (rc < 0) return rc;
+            return mdb_force_generic(c, rest & ~MDB_DEN, vtensor);
+        }
         return MDB_OK;
     }
     return mdb_force_generic(c, flags, vtensor);

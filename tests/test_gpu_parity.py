@@ -126,17 +126,24 @@ def test_integrator_epc_ekin_bit_exact(oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("path", ["generic", "auto"])
 def test_truncated_list_matches_reference_truncation(oracle, path):
-    """mxKVOIS smaller than the true count: the reference silently keeps the first mxKVOIS in scan order."""
+    """mxKVOIS smaller than the true count: the reference silently keeps the first mxKVOIS in scan order.
+    The tiled builder keeps no scan order, so it reports such a build and AUTO falls back to the generic
+    (reference-ordered) kernels; forcing the tiled path is refused with a status code."""
     c = util.bcc_case((7, 7, 7), mxkvois=60)
     ref = _oracle_list(oracle, c)
-    ctx = util.make_ctx(c, force_path=PATHS[path])
+    ctx = util.make_ctx(c, force_path=capi.FORCE_PATH_GENERIC if path == "generic" else capi.FORCE_PATH_AUTO)
+    assert ctx.get_option(capi.OPT_ACTIVE_PATH) == capi.FORCE_PATH_GENERIC
     kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
     assert kv.max() == 60 and np.array_equal(kv, ref["kvois"])
     assert np.array_equal(ind, ref["indi"])
     assert ctx.nlist_overflow() == c.xp.shape[0]  # every bcc atom has > 60 neighbours inside 2.28 a0
     ctx.close()
+    if path == "auto":
+        with pytest.raises(capi.MDBError) as e:
+            util.make_ctx(c, force_path=capi.FORCE_PATH_TILED)
+        assert e.value.code == capi.ERR_UNSUPPORTED
 
 
 @pytest.mark.parametrize("path", list(PATHS))
