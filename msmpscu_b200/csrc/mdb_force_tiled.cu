@@ -180,10 +180,11 @@ __device__ __forceinline__ unsigned long long f2_sq(unsigned long long a)
 }
 __device__ __forceinline__ float f2_lo(unsigned long long a) { return __uint_as_float((unsigned)a); }
 __device__ __forceinline__ float f2_hi(unsigned long long a) { return __uint_as_float((unsigned)(a >> 32)); }
-// predicated 16-bit shared-memory store through a 32-bit shared address
-__device__ __forceinline__ void sts16_if(unsigned addr, unsigned val, bool p)
+// predicated push of a 16-bit entry onto a shared-memory column (32-bit shared address, row stride 64 bytes)
+__device__ __forceinline__ void sts16_push(unsigned &addr, unsigned val, bool p)
 {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.u16 [%0], %1;\n}\n" ::"r"(addr), "h"((unsigned short)val), "r"((unsigned)p) : "memory");
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.u16 [%0], %1;\n@q add.u32 %0, %0, 64;\n}\n"
+                 : "+r"(addr) : "h"((unsigned short)val), "r"((unsigned)p) : "memory");
 }
 
 template <int G, bool MT>
@@ -257,8 +258,7 @@ k_tile_nlist(TileParams P, TileListArgs A)
             const unsigned e = (unsigned)s + ((r2 > rc0) ? 0x4000u : 0u) + ((r2 > rc1) ? 0x4000u : 0u);
             bool st = hit;
             if (CAP) { st = hit && (pa < pa_end); nover += (hit && !st) ? 1 : 0; }
-            sts16_if(pa, e, st);
-            pa += st ? 64u : 0u;
+            sts16_push(pa, e, st);
         };
         auto one = [&](auto self_tag, auto cap_tag, const int s) {
             const int o = (s >> 1) * 4 + (s & 1);
@@ -269,9 +269,10 @@ k_tile_nlist(TileParams P, TileListArgs A)
         };
         auto range = [&](auto self_tag, auto cap_tag, int s, const int s_hi) {
             if (s < s_hi && (s & 1)) { one(self_tag, cap_tag, s); s++; }
+            const float4 *pxy = hxy + (s >> 1);
 #pragma unroll 2
-            for (; s + 1 < s_hi; s += 2) {
-                const float4 a = hxy[s >> 1], b = hzt[s >> 1];
+            for (; s + 1 < s_hi; s += 2, pxy++) {
+                const float4 a = pxy[0], b = pxy[npair];
                 const unsigned long long ex = f2_sub(mx2, f2_pack(a.x, a.y)), ey = f2_sub(my2, f2_pack(a.z, a.w)),
                                          ez = f2_sub(mz2, f2_pack(b.x, b.y));
                 const unsigned long long qx = f2_sq(ex), qy = f2_sq(ey), qz = f2_sq(ez);
@@ -314,12 +315,16 @@ k_tile_nlist(TileParams P, TileListArgs A)
         A.kvois[ia] = min(nn, P.mxkvois);
         // ---- three-way partition of the column by class tag (order inside a class is free)
         int lo = 0, mid = 0, hi = nn - 1;
-        while (mid <= hi) {
+        while (mid <= hi) { // branch-free: the entry at mid swaps with lo (class 0), itself (class 1) or hi (class 2)
             const unsigned e = col[mid * 32];
             const unsigned t = e >> 14;
-            if (t == 0u) { const unsigned f = col[lo * 32]; col[lo * 32] = (unsigned short)e; col[mid * 32] = (unsigned short)f; lo++; mid++; }
-            else if (t == 1u) mid++;
-            else { const unsigned f = col[hi * 32]; col[hi * 32] = (unsigned short)e; col[mid * 32] = (unsigned short)f; hi--; }
+            const int j = (t == 0u) ? lo : ((t == 1u) ? mid : hi);
+            const unsigned f = col[j * 32];
+            col[j * 32] = (unsigned short)e;
+            col[mid * 32] = (unsigned short)f;
+            lo += (t == 0u) ? 1 : 0;
+            mid += (t <= 1u) ? 1 : 0;
+            hi -= (t >= 2u) ? 1 : 0;
         }
         A.ncls[ia] = (unsigned short)lo;               // class 0
         A.ncls[ia + P.npad] = (unsigned short)mid;     // classes 0+1
