@@ -271,8 +271,15 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     per_launch_bytes = (BYTES_PASS1 if dom == "pass1" else BYTES_PASS2) * n
     achieved = per_launch_bytes / (tms / nl * 1e-3) / 1e9 if nl else 0.0
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same workload only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if int(tj.get("atoms", -1)) == n and args.path != "generic":
+            traffic = tj.get(dom)
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+            "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
             "algorithmic_bytes_per_atom": BYTES_PASS1 if dom == "pass1" else BYTES_PASS2,
             "avg_launch_ms": tms / nl if nl else None,
             "kernel_share_of_step": tms / tot if tot else None,
