@@ -121,6 +121,16 @@ module MDB_C_BINDING
        integer(c_int), value :: itime0, nsteps, it0, nb_uptab
        real(c_double), value :: h
      end function
+     !--- Do_Steepest_Forsteps_DEV (CommonGPU/MD_SteepestScheme_GPU.F90:263-290)
+     integer(c_int) function mdb_steepest(ctx, mxnumsteps, meth, alpha, maxdis, mindis, minepot, iflag, maxmove, delepot) &
+                                          bind(C, name="mdb_steepest")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: mxnumsteps, meth
+       real(c_double), value :: alpha, maxdis, mindis, minepot
+       integer(c_int)        :: iflag
+       real(c_double)        :: maxmove, delepot
+     end function
   end interface
 
   !--- one context per process: the reference keeps its device state in module variables too

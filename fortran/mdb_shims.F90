@@ -96,3 +96,31 @@ contains
       if(mdb_ekin(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_ekin failed"
   end subroutine
 end module MD_DiffScheme_GPU
+
+module MD_SteepestScheme_GPU             ! replaces MDLIB/sor/CommonGPU/MD_SteepestScheme_GPU.F90 (:263-290)
+  use MD_CONSTANTS
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MDB_C_BINDING
+  implicit none
+contains
+  subroutine Do_Steepest_Forsteps_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, METH)
+    use MD_Forceclass_Register_GPU
+    type(SimMDBox),dimension(:)       :: SimBox
+    type(SimMDCtrl),       intent(in) :: CtrlParam
+    type(MDForceClassGPU), intent(in) :: ForceClass
+    integer,               intent(in) :: MXNUMSTEPS, METH
+    integer(c_int)::IFLAG
+    real(c_double)::MAXMOVE, DELEPOT
+      if(mdb_steepest(m_CTX, MXNUMSTEPS, METH, CtrlParam%STEEPEST_Alpha, CtrlParam%STEEPEST_MxStep*SimBox(1)%RR,   &
+                      CtrlParam%STEEPEST_MiStep*SimBox(1)%RR, CtrlParam%STEEPEST_MiDelE*CP_EV2ERG,                 &
+                      IFLAG, MAXMOVE, DELEPOT) .lt. 0) stop "MDPSCU Error: mdb_steepest failed"
+      if(IFLAG .eq. 0) then
+         write(*,fmt="(A, I8)")      " MDPSCU WARNING: steepest finished after max steps: ", MXNUMSTEPS
+         write(*,fmt="(A, 1PE13.4)") "                 with the max movement (LU) of atoms:", MAXMOVE/SimBox(1)%RR
+      else
+         write(*,fmt="(A, I8)")      " MDPSCU Message: steepest finished after steps: ", IFLAG
+         write(*,fmt="(A, 1PE13.4)") "                 with max energy uncertainty(ev): ", DELEPOT*CP_ERG2EV
+      end if
+  end subroutine
+end module MD_SteepestScheme_GPU

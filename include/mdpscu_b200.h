@@ -189,6 +189,22 @@ int mdb_dd_set(mdb_ctx *ctx, int rank, int nranks);
 int mdb_dd_info(const mdb_ctx *ctx, int info[16]);
 
 /* ------------------------------------------------------------------------------------
+ * Quench.  Do_Steepest_Forsteps_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, METH),
+ * CommonGPU/MD_SteepestScheme_GPU.F90:263-290 -> Do_Steepest0_Forsteps_DEV :20-153: steepest descent with a
+ * Barzilai-Borwein step on the current neighbour list (no rebuild inside, as in the reference), called by
+ * For_One_Step's QUICKDAMP "ST" branch (Appshell/MD_Method_GenericMD_GPU.F90:540-546) and by the PARREP event
+ * quench.  alpha = STEEPEST_Alpha; maxdis / mindis = STEEPEST_MxStep / STEEPEST_MiStep * RR [cm];
+ * minepot = STEEPEST_MiDelE * CP_EV2ERG [erg].  meth = CtrlParam%DAMPSCHEME: with MDB_QUENCH_LSEARCH set the
+ * reference runs the line-search variant (:157-260), which returns MDB_ERR_UNSUPPORTED here for now.
+ * Outputs (may be NULL): iflag = iteration at which a criterion was met (0: ran out of steps, -1: converged at
+ * the first step), maxmove [cm], delepot [erg] as the reference prints them.  The scalars and the stop flag live on
+ * the device; the host synchronises once per 8 iterations instead of five times per iteration.
+ * ---------------------------------------------------------------------------------- */
+#define MDB_QUENCH_LSEARCH 65536 /* CP_DAMPSCHEME_LSEARCH, Common/MD_Const.F90:27 */
+int mdb_steepest(mdb_ctx *ctx, int mxnumsteps, int meth, double alpha, double maxdis, double mindis, double minepot,
+                 int *iflag, double *maxmove, double *delepot);
+
+/* ------------------------------------------------------------------------------------
  * options.  MDB_OPT_FORCE_PATH selects the force/list implementation:
  *   AUTO    the tiled fast path when the configuration fits it, else the generic one
  *   GENERIC thread-per-atom over INDI, un-fused arithmetic in reference order (bit-faithful)

@@ -61,6 +61,7 @@ SYMBOLS = {
     "mdb_epc_apply": (C.c_int, [C.c_void_p]),
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_steepest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_ip, c_dp, c_dp]),
     "mdb_dd_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdb_dd_info": (C.c_int, [C.c_void_p, c_ip]),
     "mdb_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -75,6 +76,7 @@ SYMBOLS = {
 
 OPT_FORCE_PATH, OPT_TILED_LANES, OPT_TILED_CLASSES, OPT_ACTIVE_PATH, OPT_TILED_THREADS, OPT_FUSE_EPILOGUE, OPT_TILED_STAGES = 0, 1, 2, 3, 4, 5, 6
 FORCE_PATH_AUTO, FORCE_PATH_GENERIC, FORCE_PATH_TILED = 0, 1, 2
+QUENCH_LSEARCH = 65536  # CP_DAMPSCHEME_LSEARCH
 
 _lib = None
 
@@ -262,6 +264,13 @@ class Context:
 
     def run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    def steepest(self, mxnumsteps, alpha, maxdis, mindis, minepot, meth=0):
+        """Do_Steepest_Forsteps_DEV on the current list; returns (IFLAG, MAXMOVE [cm], DELEPOT [erg])."""
+        fl, mm, de = C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+        self._chk(self.lib.mdb_steepest(self.h, int(mxnumsteps), int(meth), float(alpha), float(maxdis), float(mindis),
+                                        float(minepot), C.byref(fl), C.byref(mm), C.byref(de)))
+        return fl.value, mm.value, de.value
 
     def dd_set(self, rank, nranks):
         self._chk(self.lib.mdb_dd_set(self.h, int(rank), int(nranks)))

@@ -152,6 +152,8 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_dd) cudaFreeHost(c->h_dd);
     if (c->hstage) cudaFreeHost(c->hstage);
+    if (c->q_buf) cudaFree(c->q_buf);
+    if (c->q_host) cudaFreeHost(c->q_host);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

@@ -20,6 +20,7 @@ struct ForceParams {
     int pot_type, ng, ntab, nembd;
     double csi, rhod, ru2max;
     const double2 *potr, *fpotr, *potb, *fpotb, *fembd, *dfembd;
+    const int *skip; // device flag: the kernel returns at once when it is set (converged quench iterations)
     int kpair[MDB_MXGROUP * MDB_MXGROUP];
     int kembd[MDB_MXGROUP];
 };
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(128)
 k_pass1_generic(ForceParams P, double4 *__restrict__ pos, const int *__restrict__ ityp, const int *__restrict__ statu,
                 const int *__restrict__ kvois, const int *__restrict__ indi)
 {
+    if (P.skip && *P.skip) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     double den0 = 0.0;
@@ -95,6 +97,7 @@ k_pass2_generic(ForceParams P, const double4 *__restrict__ pos, const int *__res
                 const int *__restrict__ statu, const int *__restrict__ kvois, const int *__restrict__ indi,
                 double *__restrict__ fp, double *__restrict__ vpart)
 {
+    if (P.skip && *P.skip) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     double v[9];
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(128)
 k_epot_generic(ForceParams P, const double4 *__restrict__ pos, const int *__restrict__ ityp, const int *__restrict__ statu,
                const int *__restrict__ kvois, const int *__restrict__ indi, double *__restrict__ epot)
 {
+    if (P.skip && *P.skip) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     double er0 = 0.0, den0 = 0.0;
@@ -224,6 +228,7 @@ static void fill_params(mdb_ctx *c, ForceParams &P)
     P.n = c->n; P.box = c->box;
     P.pot_type = t.pot_type; P.ng = c->ng; P.ntab = t.ntab; P.nembd = t.nembd;
     P.csi = t.csi; P.rhod = t.rhod; P.ru2max = t.ru2max;
+    P.skip = c->skip_flag;
     P.potr = t.potr; P.fpotr = t.fpotr; P.potb = t.potb; P.fpotb = t.fpotb; P.fembd = t.fembd; P.dfembd = t.dfembd;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) P.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) P.kembd[i] = t.kembd[i];

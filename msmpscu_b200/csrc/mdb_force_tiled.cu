@@ -382,6 +382,7 @@ struct TilePassArgs {
     int tile_lo, tile_hi;  // tiles of this rank (slab decomposition), [0, ntiles) otherwise
     int zero_parked;       // block 0 zeroes the outputs of atoms parked outside the cells
     int nbuf;              // pipeline stages (2 or 3)
+    const int *skip;       // device flag: return at once when set (converged quench iterations)
     double hs2;            // H/2
     double *xp1;
     EpcParams epc;
@@ -485,6 +486,7 @@ __global__ void __launch_bounds__(NT, 1)
 k_tile_pass(TileParams P, TilePassArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    if (A.skip && *A.skip) return;
     constexpr int NW = NT / 32, NCW = NW - 1, APW = 32 / G;
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // TMA bytes landed
     unsigned long long *bar_ready = bar_full + TP_MAXBUF;                        // producer finished the stage
@@ -1005,6 +1007,7 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.tile_hi = c->dd_on ? c->dd_info[15] : S.P.ntiles;
     A.zero_parked = c->dd_on ? 0 : 1;
     A.nbuf = S.nbuf;
+    A.skip = c->skip_flag;
     if (!c->epc.on) A.fuse &= ~1;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];

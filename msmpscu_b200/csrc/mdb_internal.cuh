@@ -153,6 +153,11 @@ struct mdb_ctx {
     int opt_force_path = MDB_FORCE_PATH_AUTO;
     int opt_fuse_epilogue = 0; // measured slower than the separate 27 us kernel on B200 (profiles/r01_summary.md)
 
+    // ---- quench (mdb_quench.cu): work arrays, pinned scalar mirror, and the device flag that turns the force
+    //      kernels of already-converged iterations into no-ops
+    double *q_buf = nullptr; int q_n = 0; void *q_host = nullptr;
+    const int *skip_flag = nullptr;
+
     // ---- virial partials
     double *vpart = nullptr; int vpart_n = 0;
 

@@ -260,6 +260,26 @@ def For_One_Step(dev, ITIME, SimBox, CtrlParam, ForceClass=gm_ForceClass):
     Correction_DEV(dev, ITIME, SimBox, CtrlParam)
 
 
+def Do_Steepest_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, MXNUMSTEPS=1000, METH=0):
+    """CommonGPU/MD_SteepestScheme_GPU.F90:263-290: quench on the current neighbour list.  Control values as the
+    reference takes them from CtrlParam (defaults of Common/MD_TypeDef_SimCtrlParam.F90:213-217); returns
+    (IFLAG, max move [LU], max energy change [eV])."""
+    b0 = SimBox[0] if isinstance(SimBox, (list, tuple)) else SimBox
+    alpha = getattr(CtrlParam, "STEEPEST_Alpha", 0.1)
+    mxstep = getattr(CtrlParam, "STEEPEST_MxStep", 0.1)
+    mistep = getattr(CtrlParam, "STEEPEST_MiStep", 1.0e-5)
+    midele = getattr(CtrlParam, "STEEPEST_MiDelE", 0.001)
+    fl, mm, de = dev.ctx.steepest(MXNUMSTEPS, alpha, mxstep * b0.RR, mistep * b0.RR, midele * CP_EVERG, METH)
+    return fl, mm / b0.RR, de / CP_EVERG
+
+
+def ResetXP1(dev, SimBox):
+    """Appshell/MD_Method_GenericMD_GPU.F90 ResetXP1: velocities are zeroed after a quench."""
+    b0 = SimBox[0] if isinstance(SimBox, (list, tuple)) else SimBox
+    dev.ctx.upload(capi.F_XP1, np.zeros((dev.ctx.n, 3)))
+    b0.XP1[:] = 0.0
+
+
 def For_Steps(dev, ITIME0, nsteps, SimBox, CtrlParam):
     """The same sequence for nsteps steps inside the library (mdb_run): no host round trip per step."""
     return dev.ctx.run(ITIME0, nsteps, CtrlParam.IT0, CtrlParam.NB_UPTAB, CtrlParam.H)

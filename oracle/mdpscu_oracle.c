@@ -1036,6 +1036,83 @@ void orc_md_get(orc_md *m, double *xp, double *xp1, double *fp, double *epot, do
     if (vtensor) memcpy(vtensor, m->vtensor, sizeof(double) * 9);
 }
 
+/* ------------------------------------------------------------------------------------
+ * Quench by steepest descent with a Barzilai-Borwein step: Do_Steepest0_Forsteps_DEV,
+ * CommonGPU/MD_SteepestScheme_GPU.F90:20-153 (the "ST" QUICKDAMP scheme of For_One_Step,
+ * Appshell/MD_Method_GenericMD_GPU.F90:540-546; PARREP uses it for its event quench).
+ * Vector helpers restated from MSMLIB/sor/CommonGPU/MSM_MultiGPU_Basic.F90: DevMultiply,
+ * DevMaxAbsval (max |x| over all components of all atoms), DevDot, DevMinus and
+ * AddBD_DevVec_DF_KERNEL0 (:5444-5476: RT = V1+V2; RT > HB -> RT - (HB-LB); RT < LB -> RT + (HB-LB)).
+ * No neighbour-list rebuild happens inside the loop (the reference does none either).
+ * returns IFLAG (0 = ran out of steps, >0 = converged at that iteration, -1 = converged at
+ * the first step); *maxmove, *delepot as the reference prints them (cm, erg). */
+static double maxabs(const double *a, size_t n)
+{
+    double m = 0.0;
+    for (size_t i = 0; i < n; i++) { double v = fabs(a[i]); if (v > m) m = v; }
+    return m;
+}
+static void add_shift(int n, const double lb[3], const double hb[3], const double *dx, double *x)
+{
+    for (int d = 0; d < 3; d++)
+        for (int i = 0; i < n; i++) {
+            double rt = dx[i + (size_t)d * n] + x[i + (size_t)d * n];
+            if (rt > hb[d]) rt = rt - (hb[d] - lb[d]);
+            else if (rt < lb[d]) rt = rt + (hb[d] - lb[d]);
+            x[i + (size_t)d * n] = rt;
+        }
+}
+int orc_md_steepest0(orc_md *m, int mxnumsteps, double alpha0, double maxdis, double mindis, double minepot,
+                     double *maxmove_out, double *delepot_out)
+{
+    const int n = m->n;
+    const size_t n3 = (size_t)n * 3;
+    double *prefp = (double *)malloc(sizeof(double) * n3), *dxp = (double *)malloc(sizeof(double) * n3);
+    double *epot0 = (double *)malloc(sizeof(double) * n);
+    double lb[3], hb[3], maxmove = 0.0, delepot = 0.0, alpha = alpha0;
+    int iflag = 0;
+    for (int d = 0; d < 3; d++) { /* :52-59 */
+        lb[d] = m->ifpd[d] ? m->boxlow[d] : -1.0e108;
+        hb[d] = m->ifpd[d] ? m->boxup[d] : 1.0e108;
+    }
+    orc_md_force(m, 0);                                                    /* :70 */
+    memcpy(prefp, m->fp, sizeof(double) * n3);
+    for (size_t i = 0; i < n3; i++) dxp[i] = alpha * prefp[i];             /* :72 */
+    maxmove = maxabs(dxp, n3);
+    if (maxmove > maxdis) { const double sc = maxdis / maxmove; for (size_t i = 0; i < n3; i++) dxp[i] = sc * dxp[i]; }
+    else if (maxmove <= mindis) { iflag = -1; goto done; }                 /* :76-86 */
+    orc_md_epot(m);
+    memcpy(epot0, m->epot, sizeof(double) * n);
+    add_shift(n, lb, hb, dxp, m->xp);                                      /* :90 */
+    for (int it = 1; it <= mxnumsteps; it++) {
+        orc_md_force(m, 0);
+        double dotdxdf = 0.0, dotdf = 0.0;
+        for (size_t i = 0; i < n3; i++) {                                  /* :97-100 */
+            const double dfp = prefp[i] - m->fp[i];
+            dotdxdf += dxp[i] * dfp;
+            dotdf += dfp * dfp;
+        }
+        alpha = dotdxdf / dotdf;
+        if (alpha < 0.0) alpha = alpha0;                                   /* :102-104 */
+        for (size_t i = 0; i < n3; i++) dxp[i] = alpha * m->fp[i];
+        maxmove = maxabs(dxp, n3);
+        if (maxmove > maxdis) { const double sc = maxdis / maxmove; for (size_t i = 0; i < n3; i++) dxp[i] = sc * dxp[i]; }
+        add_shift(n, lb, hb, dxp, m->xp);                                  /* :112 */
+        if (maxmove <= mindis) { iflag = it; break; }                      /* :117-120 */
+        orc_md_epot(m);
+        delepot = 0.0;
+        for (int i = 0; i < n; i++) { const double v = fabs(m->epot[i] - epot0[i]); if (v > delepot) delepot = v; }
+        if (delepot <= minepot) { iflag = it; break; }                     /* :125-128 */
+        memcpy(epot0, m->epot, sizeof(double) * n);
+        memcpy(prefp, m->fp, sizeof(double) * n3);
+    }
+done:
+    if (maxmove_out) *maxmove_out = maxmove;
+    if (delepot_out) *delepot_out = delepot;
+    free(prefp); free(dxp); free(epot0);
+    return iflag;
+}
+
 int orc_md_natom(orc_md *m) { return m->n; }
 const int *orc_md_kvois(orc_md *m) { return m->kvois; }
 const int *orc_md_indi(orc_md *m) { return m->indi; }

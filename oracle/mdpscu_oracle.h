@@ -161,6 +161,10 @@ int   orc_md_step(orc_md *m, int itime, int it0, int nb_uptab, double h); /* ret
 /* copy out in ORIGINAL order; any pointer may be NULL */
 void  orc_md_get(orc_md *m, double *xp, double *xp1, double *fp, double *epot, double *ekin,
                  double *dis, int *statu, int *gid, double *vtensor);
+/* steepest-descent quench, Do_Steepest0_Forsteps_DEV (CommonGPU/MD_SteepestScheme_GPU.F90:20-153): lengths in cm,
+ * minepot in erg; returns IFLAG (0 not converged, >0 iteration of convergence, -1 converged at the first step) */
+int   orc_md_steepest0(orc_md *m, int mxnumsteps, double alpha0, double maxdis, double mindis, double minepot,
+                       double *maxmove_out, double *delepot_out);
 int   orc_md_natom(orc_md *m);
 const int *orc_md_kvois(orc_md *m);
 const int *orc_md_indi(orc_md *m);

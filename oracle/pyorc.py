@@ -282,6 +282,13 @@ class MD:
     def step(self, itime, it0, nb_uptab, h):
         return lib().orc_md_step(self.h, C.c_int(itime), C.c_int(it0), C.c_int(nb_uptab), C.c_double(h))
 
+    def steepest0(self, mxnumsteps, alpha0, maxdis, mindis, minepot):
+        """Do_Steepest0_Forsteps_DEV; returns (IFLAG, MAXMOVE [cm], DELEPOT [erg])"""
+        mm, de = C.c_double(0.0), C.c_double(0.0)
+        fl = lib().orc_md_steepest0(self.h, C.c_int(mxnumsteps), C.c_double(alpha0), C.c_double(maxdis), C.c_double(mindis),
+                                    C.c_double(minepot), C.byref(mm), C.byref(de))
+        return int(fl), mm.value, de.value
+
     def get(self):
         n = self.n
         xp, xp1, fp, dis = (np.zeros(3 * n) for _ in range(4))

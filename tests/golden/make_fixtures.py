@@ -9,6 +9,8 @@ Outputs (small, committed):
       Bonny EAM1): per-atom type, position [LU], force [eV/LU], POT [eV] (= -EPOT)
       from examples/NEB_Test/GMD/{React,Product}P0000_0001.0000 (&BOXCFG18 columns
       TYPE, POS(3), VEL(3), STATU, FOR(3), POT, K.E., DISPLACE(3)).
+  neb_gmd_react_quenched.npz
+      the same run's output after 1000 damping steps (ReactP0000_0001.0001): position, force, POT.
   bonny_eam1_embd_rows.npz
       sampled rows of examples/use_ForceTableGen/EAM_WHeH_Bonny_JPCM26_2014.embd
       (Export_ForceTable output: RHO, F_k(RHO), dF_k/dRHO for the 9 ids).
@@ -48,6 +50,10 @@ def main():
         assert d["pos"].shape == (2001, 3)
         np.savez_compressed(os.path.join(HERE, "neb_gmd_%s.npz" % tag), ityp=d["ityp"], pos=d["pos"],
                             statu=d["statu"], force=d["force"], pot=d["pot"])
+    # the same run after its QUICKDAMP section (1000 steps): a loose pin for the quench row -- the 2019 binary damped
+    # dynamically (the file carries velocities), so only the energy level and the force drop are comparable
+    d = read_cfg18(os.path.join(neb, "GMD", "ReactP0000_0001.0001"))
+    np.savez_compressed(os.path.join(HERE, "neb_gmd_react_quenched.npz"), pos=d["pos"], force=d["force"], pot=d["pot"])
     for fn in ("W_2000_H1_EAM1_box.dat", "CtrlFile0K.dat"):
         shutil.copyfile(os.path.join(neb, fn), os.path.join(HERE, fn))
     with open(os.path.join(neb, "GMD", "thermP0000_0001")) as f:

@@ -142,3 +142,21 @@ def test_force_is_minus_gradient_of_energy(oracle):
         ep = oracle.force(xp, *args, epot=True)[3].sum()
         em = oracle.force(xm, *args, epot=True)[3].sum()
         assert abs(-(ep - em) / (2 * h) - fp[i, d]) < 2e-3 * np.abs(fp).max()
+
+
+def test_oracle_steepest_quench_relaxes_and_stops_on_the_reference_criteria():
+    """Do_Steepest0_Forsteps_DEV restatement (CommonGPU/MD_SteepestScheme_GPU.F90:20-153): the energy criterion stops
+    it (IFLAG > 0), forces drop by orders of magnitude, and with impossible criteria it runs out of steps (IFLAG = 0)."""
+    import util
+    from oracle import pyorc as O
+    c = util.bcc_case((6, 6, 6), seed=5, temp=0.0, disp=0.04)
+    md = util.oracle_md(O, c)
+    md.rebuild(); md.force()
+    f0 = np.abs(md.get()["fp"]).max()
+    fl, mm, de = md.steepest0(60, 0.1, 0.1 * c.rr, 1.0e-5 * c.rr, 1.0e-3 * util.CP_EVERG)
+    assert 0 < fl < 60 and de <= 1.0e-3 * util.CP_EVERG and mm <= 0.1 * c.rr
+    md.force()
+    assert np.abs(md.get()["fp"]).max() < 0.05 * f0
+    md2 = util.oracle_md(O, c)
+    md2.rebuild()
+    assert md2.steepest0(5, 0.1, 0.1 * c.rr, 1.0e-12 * c.rr, 1.0e-16 * util.CP_EVERG)[0] == 0
