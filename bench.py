@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=80, help="bcc cells per edge (80 -> 1 024 000 atoms)")
+    ap.add_argument("--nbox", type=int, default=1, help="independent boxes per GPU, concatenated as MULTIBOX (configs[2] family)")
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "tiled"])
     ap.add_argument("--cpu-cells", type=int, default=32, help="edge of the CPU sample box (32 -> 65 536 atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -56,11 +57,11 @@ def parse():
     return ap.parse_args()
 
 
-def make_case(cells, seed):
+def make_case(cells, seed, nbox=1):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util
     return util.bcc_case((cells, cells, cells), a0=A0, seed=seed, ru_lu=RU_LU, nb_fac=NB_FAC, mxkvois=MXKVOIS,
-                         ntab=NTAB, temp=600.0, disp=0.02)
+                         ntab=NTAB, temp=600.0, disp=0.02, nbox=nbox)
 
 
 EPC = dict(enable=[1], te=[300.0], alpha=[1.0e-12], cut=[0.1], he=[100.0 * 1.60219e-12])
@@ -133,8 +134,10 @@ def base_line(args, n_atoms):
         "metric": "atom-steps/sec (W EAM, 1M atoms)", "unit": "atom-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: bcc W %d atoms (%d^3 bcc cells), Marinica EAM2 table force, NVT via "
-                               "MDLocalTempCtrl EPC (Te=300K), single box per GPU" % (n_atoms, args.cells),
+        "config": {"workload": ("configs[1]: bcc W %d atoms (%d^3 bcc cells), Marinica EAM2 table force, NVT via "
+                                "MDLocalTempCtrl EPC (Te=300K), single box per GPU" % (n_atoms, args.cells)) if args.nbox == 1 else
+                               ("configs[2] family: %d independent boxes x %d atoms (%d^3 bcc cells, W Marinica EAM2 tables), "
+                                "NVT via EPC, per GPU" % (args.nbox, n_atoms // args.nbox, args.cells)),
                    "atoms_per_gpu": n_atoms, "md_steps_per_step": MD_PER_STEP, "h_fs": 0.5, "cutoff_a0": RU_LU,
                    "list_cutoff_a0": RU_LU * NB_FAC, "rebuild_every": MD_PER_STEP, "ntab": NTAB,
                    "l2_policy": "inputs larger than L2 (neighbour list + state ~0.6 GB per step, L2 126 MB)",
@@ -171,7 +174,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    c = make_case(args.cells, 12346 + rank)
+    c = make_case(args.cells, 12346 + rank, args.nbox)
     n = c.xp.shape[0]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util

@@ -121,6 +121,23 @@ module MDB_C_BINDING
        integer(c_int), value :: itime0, nsteps, it0, nb_uptab
        real(c_double), value :: h
      end function
+     !--- Cal_GlobalT_DEV / VelScaling_DEV / CheckTimestep_DEV (CommonGPU/MD_DiffScheme_GPU.F90:1042, :1390, :1214)
+     integer(c_int) function mdb_global_t(ctx, curt) bind(C, name="mdb_global_t")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double)     :: curt
+     end function
+     integer(c_int) function mdb_vel_scaling(ctx, dt) bind(C, name="mdb_vel_scaling")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value    :: ctx
+       real(c_double), value :: dt
+     end function
+     integer(c_int) function mdb_check_timestep(ctx, th, h2s2, dmx2, iflag) bind(C, name="mdb_check_timestep")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value    :: ctx
+       real(c_double), value :: th, h2s2, dmx2
+       integer(c_int)        :: iflag
+     end function
      !--- Do_Steepest_Forsteps_DEV (CommonGPU/MD_SteepestScheme_GPU.F90:263-290)
      integer(c_int) function mdb_steepest(ctx, mxnumsteps, meth, alpha, maxdis, mindis, minepot, iflag, maxmove, delepot) &
                                           bind(C, name="mdb_steepest")

@@ -95,6 +95,29 @@ contains
     type(SimMDCtrl)::CtrlParam
       if(mdb_ekin(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_ekin failed"
   end subroutine
+  subroutine Cal_GlobalT_DEV(SimBox, CtrlParam, CURT)                                             ! :1042-1064
+    type(SimMDBox) ::SimBox
+    type(SimMDCtrl)::CtrlParam
+    real(KINDDF)   ::CURT
+      if(mdb_global_t(m_CTX, CURT) .lt. 0) stop "MDPSCU Error: mdb_global_t failed"
+  end subroutine
+  subroutine VelScaling_DEV(SimBox, CtrlParam, DT)                                                ! :1390-1446
+    type(SimMDBox) ::SimBox
+    type(SimMDCtrl)::CtrlParam
+    real(KINDDF)   ::DT
+      if(mdb_vel_scaling(m_CTX, DT) .lt. 0) then
+         write(*,fmt="(A)") " MDPSCU Error: current temperature of the system is zero in scaling velocity"
+         stop
+      end if
+  end subroutine
+  subroutine CheckTimestep_DEV(ITIME, SimBox, CtrlParam, TH, H2S2, DMX2, IFLAG)                   ! :1214-1258
+    integer,         intent(in)::ITIME
+    type(SimMDBox),  intent(in)::SimBox
+    type(SimMDCtrl)            ::CtrlParam
+    real(KINDDF),    intent(in)::TH, H2S2, DMX2
+    integer                    ::IFLAG
+      if(mdb_check_timestep(m_CTX, TH, H2S2, DMX2, IFLAG) .lt. 0) stop "MDPSCU Error: mdb_check_timestep failed"
+  end subroutine
 end module MD_DiffScheme_GPU
 
 module MD_SteepestScheme_GPU             ! replaces MDLIB/sor/CommonGPU/MD_SteepestScheme_GPU.F90 (:263-290)

@@ -189,6 +189,20 @@ int mdb_dd_set(mdb_ctx *ctx, int rank, int nranks);
 int mdb_dd_info(const mdb_ctx *ctx, int info[16]);
 
 /* ------------------------------------------------------------------------------------
+ * The other integrator-module procedures the step loops call (CommonGPU/MD_DiffScheme_GPU.F90):
+ *   mdb_global_t        Cal_GlobalT_DEV(SimBox, CtrlParam, CURT) :1042-1064 : EKIN kernel, then
+ *                       CURT = 2*sum(EKIN >= 0)/count(EKIN >= 0)/(3 k_B) (inactive and FIXPOS atoms carry -1e32)
+ *   mdb_vel_scaling     VelScaling_DEV(SimBox, CtrlParam, DT) :1262-1446 : per box, velocities times
+ *                       sqrt(DT*3*k_B/2 / <EKIN>_box); fixed components are zeroed; MDB_ERR_STATE where the
+ *                       reference stops (a box without kinetic energy)
+ *   mdb_check_timestep  CheckTimestep_DEV(ITIME, SimBox, CtrlParam, TH, H2S2, DMX2, IFLAG) :1066-1258 : IFLAG = 1 if any
+ *                       active atom would move more than sqrt(DMX2) in the next predictor step
+ * ---------------------------------------------------------------------------------- */
+int mdb_global_t(mdb_ctx *ctx, double *curt);
+int mdb_vel_scaling(mdb_ctx *ctx, double dt);
+int mdb_check_timestep(mdb_ctx *ctx, double th, double h2s2, double dmx2, int *iflag);
+
+/* ------------------------------------------------------------------------------------
  * Quench.  Do_Steepest_Forsteps_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, METH),
  * CommonGPU/MD_SteepestScheme_GPU.F90:263-290 -> Do_Steepest0_Forsteps_DEV :20-153: steepest descent with a
  * Barzilai-Borwein step on the current neighbour list (no rebuild inside, as in the reference), called by

@@ -61,6 +61,9 @@ SYMBOLS = {
     "mdb_epc_apply": (C.c_int, [C.c_void_p]),
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_global_t": (C.c_int, [C.c_void_p, c_dp]),
+    "mdb_vel_scaling": (C.c_int, [C.c_void_p, C.c_double]),
+    "mdb_check_timestep": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip]),
     "mdb_steepest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_ip, c_dp, c_dp]),
     "mdb_dd_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdb_dd_info": (C.c_int, [C.c_void_p, c_ip]),
@@ -264,6 +267,19 @@ class Context:
 
     def run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    def global_t(self):
+        t = C.c_double(0.0)
+        self._chk(self.lib.mdb_global_t(self.h, C.byref(t)))
+        return t.value
+
+    def vel_scaling(self, dt):
+        self._chk(self.lib.mdb_vel_scaling(self.h, float(dt)))
+
+    def check_timestep(self, th, h2s2, dmx2):
+        fl = C.c_int(0)
+        self._chk(self.lib.mdb_check_timestep(self.h, float(th), float(h2s2), float(dmx2), C.byref(fl)))
+        return fl.value
 
     def steepest(self, mxnumsteps, alpha, maxdis, mindis, minepot, meth=0):
         """Do_Steepest_Forsteps_DEV on the current list; returns (IFLAG, MAXMOVE [cm], DELEPOT [erg])."""

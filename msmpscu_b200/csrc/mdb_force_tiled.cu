@@ -377,7 +377,10 @@ struct TilePassArgs {
     double r2eff;          // min(RU2, table support) for this pass
     int kmin, ktab;        // shared-memory table window: rows kmin .. kmin+ktab (row kk and kk+1 are read)
     int kind0;             // the kind held in shared memory = KPAIR(1,1)
-    float safe_d2;         // classes are valid while max |displacement since rebuild|^2 <= safe_d2
+    // which per-atom scan count a pass uses, by the max |displacement since the rebuild|^2 (device counter): class-count row
+    // row_a while d2 <= safe_a, else row row_b while d2 <= safe_b, else the full list (KVOIS)
+    float safe_a, safe_b;
+    int row_a, row_b;
     int fuse;              // fused epilogue of pass 2 (mdb_run): bit 0 EPC friction, bit 1 corrector half-kick
     int tile_lo, tile_hi;  // tiles of this rank (slab decomposition), [0, ntiles) otherwise
     int zero_parked;       // block 0 zeroes the outputs of atoms parked outside the cells
@@ -531,10 +534,12 @@ k_tile_pass(TileParams P, TilePassArgs A)
     }
     __syncthreads();
     // distance classes are usable while no atom has moved more than half the class margin since the rebuild
-    const bool safe = __int_as_float(A.counters[CNT_D2MAX]) <= A.safe_d2;
+    const float d2max = __int_as_float(A.counters[CNT_D2MAX]);
+    const bool safe = d2max <= A.safe_a || d2max <= A.safe_b;
+    const int cls_row = d2max <= A.safe_a ? A.row_a : A.row_b;
     const uint2 *nbl2 = reinterpret_cast<const uint2 *>(A.nbl);
     // flat index of the class count of owned atom 0 (uint16 array [2][npad]) = ncl_base + own_start
-    const size_t ncl_base = (size_t)(PASS - 1) * P.npad;
+    const size_t ncl_base = (size_t)cls_row * P.npad;
 
     if (warp == NCW) {
         // =========================== producer warp ===========================
@@ -841,12 +846,15 @@ int mdb_tiled_plan(mdb_ctx *c)
     S.khi[0] = std::min(kru, kz1 + 2);
     S.khi[1] = std::min(kru, kz2 + 2);
 
-    // ---- class margin: a quarter of the list skin (NB_RM - RU), see header
+    // ---- class margins (see header): class 1 (what pass 2 scans) keeps a quarter of the list skin (NB_RM - RU); class 0
+    //      (pass 1) a tighter 0.12 of it, so that a neighbour shell just outside the density range does not leak into the
+    //      class and push the scan to another 4-entry group per lane; when atoms have moved more than half of that,
+    //      pass 1 falls back to classes 0+1, and only beyond half the wider margin to the full list
     double rmmax = 0.0;
     for (int i = 0; i < c->ng * c->ng; i++) rmmax = std::max(rmmax, c->nb_rm[i]);
     const double ru = std::sqrt(t.ru2max);
     S.margin = std::max(0.0, 0.25 * (rmmax - ru));
-
+    S.margin0 = std::max(0.0, 0.12 * (rmmax - ru));
     // ---- tile geometry: the widest tile (fewest halo atoms staged per owned atom) whose two pipeline stages
     //      leave room for a table window that reaches down to 0.6 of the support edge's row (r ~ 0.36 r_eff;
     //      closer pairs read the tables from global memory)
@@ -891,13 +899,16 @@ int mdb_tiled_plan(mdb_ctx *c)
     const int rows_per_lane = (c->mxkvois + G - 1) / G;
     P.nrow4 = (rows_per_lane + 3) / 4;
     P.npad = (size_t)c->n;
-    for (int p = 0; p < 2; p++) {
-        const double rc = std::sqrt(S.r2eff[p]) + S.margin;
-        S.rc2f[p] = (float)(rc * rc);
+    {
+        const double re0 = std::sqrt(S.r2eff[0]), re1 = std::sqrt(S.r2eff[1]);
+        const double rc0 = re0 + S.margin0, rc1 = std::max(re1 + S.margin, rc0);
+        S.rc2f[0] = (float)(rc0 * rc0);
+        S.rc2f[1] = (float)(rc1 * rc1);
+        // a class holds for a pass while 2*d_max <= 0.98*(class radius - the pass's range)
+        S.safe_d2[0] = (float)(0.49 * 0.49 * S.margin0 * S.margin0);                  // pass 1 on class 0
+        S.safe_d2[1] = (float)(0.49 * 0.49 * (rc1 - re1) * (rc1 - re1));              // pass 2 on classes 0+1
+        S.safe_d2[2] = (float)(0.49 * 0.49 * (rc1 - re0) * (rc1 - re0));              // pass 1 on classes 0+1
     }
-    // classes hold while 2*d_max <= 0.98*margin
-    S.safe_d2 = (float)(0.49 * 0.49 * S.margin * S.margin);
-
     // ---- storage: slot list, raw list, class counts, tile descriptors
     auto ensure = [&](void **ptr, size_t &have, size_t want) -> bool {
         if (have >= want) return true;
@@ -1001,7 +1012,9 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod;
     A.r2eff = S.r2eff[PASS - 1]; A.kmin = S.kmin[PASS - 1]; A.ktab = S.ktab[PASS - 1];
     A.kind0 = t.kpair[0];
-    A.safe_d2 = S.use_classes ? S.safe_d2 : -1.0f;
+    if (PASS == 1) { A.safe_a = S.safe_d2[0]; A.row_a = 0; A.safe_b = S.safe_d2[2]; A.row_b = 1; }
+    else { A.safe_a = S.safe_d2[1]; A.row_a = 1; A.safe_b = -1.0f; A.row_b = 1; }
+    if (!S.use_classes) { A.safe_a = -1.0f; A.safe_b = -1.0f; }
     A.fuse = fuse; A.hs2 = hs2; A.xp1 = c->xp1; A.epc = c->epc; A.mass = c->mass;
     A.tile_lo = c->dd_on ? c->dd_info[14] : 0;
     A.tile_hi = c->dd_on ? c->dd_info[15] : S.P.ntiles;

@@ -26,7 +26,7 @@
 // the first CNT_PERBUILD_N are reset at every rebuild
 enum { CNT_OOB = 0, CNT_OVERFLOW, CNT_NNMAX, CNT_MXNAC, CNT_INCELL, CNT_TILE_OVERFLOW,
        CNT_D2MAX,       // float bits: max |displacement since the rebuild|^2 over all atoms (predictor)
-       CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N, CNT__N = 12 };
+       CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N, CNT_SCRATCH, CNT__N = 12 };
 
 struct BoxParams { // passed by value to kernels
     double lo[3], up[3], size[3], half[3];
@@ -75,8 +75,8 @@ struct TiledState {
     int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0};
     double r2eff[2] = {0.0, 0.0};
     size_t smem_pass[2] = {0, 0}, smem_list = 0;
-    double margin = 0.0;       // class margin (length): classes hold while every atom moved < margin/2
-    float rc2f[2] = {0.f, 0.f}, safe_d2 = 0.f;
+    double margin = 0.0, margin0 = 0.0; // class margins (length): a class holds while every atom moved < margin/2
+    float rc2f[2] = {0.f, 0.f}, safe_d2[3] = {0.f, 0.f, 0.f};
     bool use_classes = true;
     unsigned short *nbl = nullptr; size_t nbl_elems = 0;   // slot list (bytes in nbl_elems)
     unsigned short *ncls = nullptr; size_t ncls_bytes = 0; // per-atom class counts [2][npad]

@@ -9,6 +9,8 @@
 // Positions feed the bit-exact cell assignment, so the predictor's position update is written
 // with un-fused intrinsics in the reference's source order; velocities likewise so that long
 // trajectories track the oracle as closely as the force sums allow.
+#include <cmath>
+#include <vector>
 #include "mdb_internal.cuh"
 
 // one atom of the predictor; returns |displacement since the last rebuild|^2 (0 when not tracked).
@@ -216,6 +218,156 @@ extern "C" int mdb_epc_apply(mdb_ctx *c)
     k_epc_correct<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
                                                                          0.0, 1, 0, own_a0(c), own_a1(c));
     CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------
+// The other procedures of the integrator module the step loops call: Cal_GlobalT_DEV (MD_DiffScheme_GPU.F90:1042-1064),
+// VelScaling_DEV (:1262-1446) and CheckTimestep_DEV (:1066-1258).  The reference copies EKIN to the host and sums
+// there; here the sums are deterministic two-stage device reductions and only the scalars come back.
+// ------------------------------------------------------------------------------------
+#define RT 256
+// per box b (block b): sum and count of EKIN >= 0 over the box's atoms in ORIGINAL order (hm_EKIN(hm_GIDINV(...)) :1418)
+__global__ void __launch_bounds__(RT) k_box_ekin(int napb, const double *__restrict__ ekin, const int *__restrict__ gidinv,
+                                                 double *__restrict__ bsum, int *__restrict__ bcnt)
+{
+    __shared__ double sh[RT / 32];
+    __shared__ int shc[RT / 32];
+    const int b = blockIdx.x;
+    double s = 0.0;
+    int cn = 0;
+    for (int o = threadIdx.x; o < napb; o += RT) {
+        const double e = ekin[gidinv[(size_t)b * napb + o] - 1];
+        if (e >= 0.0) { s += e; cn++; }
+    }
+    for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); cn += __shfl_xor_sync(0xffffffffu, cn, off); }
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = s; shc[threadIdx.x >> 5] = cn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0; int c = 0;
+        for (int w = 0; w < RT / 32; w++) { t += sh[w]; c += shc[w]; }
+        bsum[b] = t; bcnt[b] = c;
+    }
+}
+// VelScaling_KERNEL :1262-1320 : box of an atom = (sorted index)/NPRTPB; fixed components are zeroed
+__global__ void k_vel_scale(int n, int napb, double *__restrict__ xp1, const int *__restrict__ statu, const double *__restrict__ scal)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int st = statu[i];
+    if ((st & ST_ACTIVE) != ST_ACTIVE) return;
+    const double sc = scal[i / napb];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const bool fr = (st & (ST_FIXPOSX << d)) == 0 && (st & (ST_FIXVELX << d)) == 0;
+        const size_t o = i + (size_t)d * n;
+        xp1[o] = fr ? __dmul_rn(xp1[o], sc) : 0.0;
+    }
+}
+// CheckTimestep_KERNEL :1066-1140
+__global__ void k_check_timestep(int n, const double *__restrict__ xp1, const double *__restrict__ fp, const int *__restrict__ statu,
+                                 const int *__restrict__ ityp, MassParams M, double th, double h2s2, double mxd2, int *__restrict__ flag,
+                                 int a0, int a1)
+{
+    const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a1) return;
+    const int st = statu[i];
+    if ((st & ST_ACTIVE) != ST_ACTIVE) return;
+    const double cm0 = M.cm[ityp[i] - 1];
+    double d2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        double dd = 0.0;
+        if ((st & (ST_FIXPOSX << d)) == 0)
+            dd = __dadd_rn(__dmul_rn(th, xp1[i + (size_t)d * n]), __dmul_rn(h2s2, __ddiv_rn(fp[i + (size_t)d * n], cm0)));
+        d2 = __dadd_rn(d2, __dmul_rn(dd, dd));
+    }
+    if (d2 > mxd2) *flag = 1;
+}
+
+// fills per-box sums on the host (pinned staging); returns nbox or <0
+static int box_ekin_host(mdb_ctx *c, std::vector<double> &sum, std::vector<int> &cnt)
+{
+    int rc = mdb_ekin(c);
+    if (rc < 0) return rc;
+    const int nb = c->nbox;
+    if (c->vpart_n < nb + 2) {
+        if (c->vpart) cudaFree(c->vpart);
+        c->vpart = nullptr;
+        CUDA_TRY(c, cudaMalloc(&c->vpart, sizeof(double) * 9 * (size_t)(nb + 2)));
+        c->vpart_n = nb + 2;
+    }
+    double *bsum = c->vpart;
+    int *bcnt = reinterpret_cast<int *>(c->vpart + nb);
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        k_box_ekin<<<nb, RT, 0, c->stream>>>(c->napb, c->ekin, c->gidinv, bsum, bcnt);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    sum.resize(nb); cnt.resize(nb);
+    CUDA_TRY(c, cudaMemcpyAsync(sum.data(), bsum, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(cnt.data(), bcnt, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return nb;
+}
+
+extern "C" int mdb_global_t(mdb_ctx *c, double *curt)
+{
+    if (!c || !curt) return mdb_fail(c, MDB_ERR_ARG, "mdb_global_t: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_global_t: mdb_box_set first");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_global_t: reduce the per-rank kinetic energies in slab-decomposed runs");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    std::vector<double> sum; std::vector<int> cnt;
+    int nb = box_ekin_host(c, sum, cnt);
+    if (nb < 0) return nb;
+    double s = 0.0; long long n = 0;
+    for (int b = 0; b < nb; b++) { s += sum[b]; n += cnt[b]; }
+    *curt = 2.0 * s / (double)n / (3.0 * KB_CGS); // C_TWO*sum(hm_EKIN, mask)/count/(C_THR*CP_KB) :1062
+    return MDB_OK;
+}
+
+extern "C" int mdb_vel_scaling(mdb_ctx *c, double dt)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_vel_scaling: mdb_box_set first");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_vel_scaling: not available in slab-decomposed runs");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    std::vector<double> sum; std::vector<int> cnt;
+    int nb = box_ekin_host(c, sum, cnt);
+    if (nb < 0) return nb;
+    for (int b = 0; b < nb; b++) {
+        const double ce = sum[b] / (double)cnt[b];
+        if (!(ce > 0.0)) // the reference prints and stops :1424-1430
+            return mdb_fail(c, MDB_ERR_STATE, "mdb_vel_scaling: current temperature of box %d is zero in scaling velocity", b + 1);
+        sum[b] = sqrt(dt * 3.0 * KB_CGS * 0.5 / ce); // dsqrt(DT*C_THR*CP_KB*C_HALF/cEKIN) :1432
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->vpart, sum.data(), sizeof(double) * nb, cudaMemcpyHostToDevice, c->stream));
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        k_vel_scale<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->napb, c->xp1, c->statu, c->vpart);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream)); // sum[] is pageable host memory
+    return MDB_OK;
+}
+
+extern "C" int mdb_check_timestep(mdb_ctx *c, double th, double h2s2, double dmx2, int *iflag)
+{
+    if (!c || !iflag) return mdb_fail(c, MDB_ERR_ARG, "mdb_check_timestep: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_check_timestep: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    int *flag = c->counters + CNT_SCRATCH;
+    CUDA_TRY(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        k_check_timestep<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, th, h2s2,
+                                                                                 dmx2, flag, own_a0(c), own_a1(c));
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + CNT_SCRATCH, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *iflag = c->h_counters[CNT_SCRATCH] ? 1 : 0;
     return MDB_OK;
 }
 

@@ -239,6 +239,21 @@ def CalEKin_DEV(dev, SimBox, CtrlParam):
     return dev.ctx.download(capi.F_EKIN, capi.ORDER_ORIGINAL)
 
 
+def Cal_GlobalT_DEV(dev, SimBox, CtrlParam):
+    """MD_DiffScheme_GPU.F90:1042-1064: the average temperature of all boxes."""
+    return dev.ctx.global_t()
+
+
+def VelScaling_DEV(dev, SimBox, CtrlParam, DT):
+    """MD_DiffScheme_GPU.F90:1390-1446: scale the velocities of every box to temperature DT (K)."""
+    dev.ctx.vel_scaling(DT)
+
+
+def CheckTimestep_DEV(dev, ITIME, SimBox, CtrlParam, TH, H2S2, DMX2):
+    """MD_DiffScheme_GPU.F90:1214-1258: 1 if any atom would move more than sqrt(DMX2) with step TH."""
+    return dev.ctx.check_timestep(TH, H2S2, DMX2)
+
+
 def Do_ResetParam_DEV(dev, SimBox, CtrlParam):
     b0 = SimBox[0] if isinstance(SimBox, (list, tuple)) else SimBox
     lt = CtrlParam.LT_CTRL or [TiCtrlParam() for _ in range(b0.NGROUP)]

@@ -1113,6 +1113,71 @@ done:
     return iflag;
 }
 
+/* ------------------------------------------------------------------------------------
+ * Remaining procedures of the integrator module the step loop calls (MD_DiffScheme_GPU.F90):
+ * Cal_GlobalT_DEV :1042-1064, CheckTimestep_KERNEL/_DEV :1066-1258, VelScaling_KERNEL/_DEV :1262-1446.
+ * Arrays in any common order; gid[s] = 1-based original id of sorted atom s (box of an atom for the
+ * per-box kinetic energy = (original id)/NPRT as the reference's hm_GIDINV slices; box of an atom
+ * for the scaling factor = (sorted index)/NPRT as VelScaling_KERNEL's IB0). */
+double orc_global_t(int n, const double *xp1, const int *statu, const int *ityp, const double *cm)
+{
+    double *ek = (double *)malloc(sizeof(double) * n), sum = 0.0;
+    long cnt = 0;
+    orc_ekin(n, xp1, statu, ityp, cm, ek);
+    for (int i = 0; i < n; i++) if (ek[i] >= 0.0) { sum += ek[i]; cnt++; }
+    free(ek);
+    return 2.0 * sum / (double)cnt / (3.0 * 1.38054e-16); /* C_TWO*sum/count/(C_THR*CP_KB) :1062 */
+}
+int orc_check_timestep(int n, const double *xp1, const double *fp, const int *statu, const int *ityp, const double *cm,
+                       double th, double h2s2, double mxd2)
+{
+    for (int i = 0; i < n; i++) {
+        if ((statu[i] & 1) != 1) continue;
+        const double cm0 = cm[ityp[i] - 1];
+        double d[3] = {0.0, 0.0, 0.0};
+        for (int k = 0; k < 3; k++)
+            if ((statu[i] & (2 << k)) == 0) d[k] = th * xp1[i + (size_t)k * n] + h2s2 * (fp[i + (size_t)k * n] / cm0);
+        if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] > mxd2) return 1;
+    }
+    return 0;
+}
+int orc_vel_scaling(int n, int napb, double *xp1, const int *statu, const int *ityp, const int *gid, const double *cm, double dt)
+{
+    const int nbox = n / napb;
+    double *ek = (double *)malloc(sizeof(double) * n), *sum = (double *)calloc(nbox, sizeof(double));
+    long *cnt = (long *)calloc(nbox, sizeof(long));
+    int *pos_of = (int *)malloc(sizeof(int) * n);
+    orc_ekin(n, xp1, statu, ityp, cm, ek);
+    for (int s = 0; s < n; s++) pos_of[gid[s] - 1] = s;
+    for (int o = 0; o < n; o++) { /* original order, as sum(hm_EKIN(hm_GIDINV(IPA+1:IPA+NPRT))) :1418-1422 */
+        const double e = ek[pos_of[o]];
+        if (e >= 0.0) { sum[o / napb] += e; cnt[o / napb]++; }
+    }
+    int bad = 0;
+    for (int b = 0; b < nbox; b++) {
+        const double ce = sum[b] / (double)cnt[b];
+        if (!(ce > 0.0)) bad = 1;
+        sum[b] = sqrt(dt * 3.0 * 1.38054e-16 * 0.5 / ce); /* dsqrt(DT*C_THR*CP_KB*C_HALF/cEKIN) :1432 */
+    }
+    if (!bad)
+        for (int s = 0; s < n; s++) {
+            if ((statu[s] & 1) != 1) continue;
+            const double sc = sum[s / napb];
+            for (int k = 0; k < 3; k++) {
+                const int free_k = (statu[s] & (2 << k)) == 0 && (statu[s] & (16 << k)) == 0;
+                xp1[s + (size_t)k * n] = free_k ? xp1[s + (size_t)k * n] * sc : 0.0; /* fixed components are zeroed :1299-1315 */
+            }
+        }
+    free(ek); free(sum); free(cnt); free(pos_of);
+    return bad ? -1 : 0;
+}
+double orc_md_global_t(orc_md *m) { return orc_global_t(m->n, m->xp1, m->statu, m->ityp, m->cm); }
+int orc_md_vel_scaling(orc_md *m, double dt) { return orc_vel_scaling(m->n, m->napb, m->xp1, m->statu, m->ityp, m->gid, m->cm, dt); }
+int orc_md_check_timestep(orc_md *m, double th, double h2s2, double mxd2)
+{
+    return orc_check_timestep(m->n, m->xp1, m->fp, m->statu, m->ityp, m->cm, th, h2s2, mxd2);
+}
+
 int orc_md_natom(orc_md *m) { return m->n; }
 const int *orc_md_kvois(orc_md *m) { return m->kvois; }
 const int *orc_md_indi(orc_md *m) { return m->indi; }

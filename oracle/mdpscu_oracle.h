@@ -165,6 +165,10 @@ void  orc_md_get(orc_md *m, double *xp, double *xp1, double *fp, double *epot, d
  * minepot in erg; returns IFLAG (0 not converged, >0 iteration of convergence, -1 converged at the first step) */
 int   orc_md_steepest0(orc_md *m, int mxnumsteps, double alpha0, double maxdis, double mindis, double minepot,
                        double *maxmove_out, double *delepot_out);
+/* Cal_GlobalT_DEV :1042-1064, VelScaling_DEV :1262-1446, CheckTimestep_DEV :1066-1258 (MD_DiffScheme_GPU.F90) */
+double orc_md_global_t(orc_md *m);
+int   orc_md_vel_scaling(orc_md *m, double dt);          /* -1: a box with zero kinetic energy (the reference stops) */
+int   orc_md_check_timestep(orc_md *m, double th, double h2s2, double mxd2);
 int   orc_md_natom(orc_md *m);
 const int *orc_md_kvois(orc_md *m);
 const int *orc_md_indi(orc_md *m);

@@ -282,6 +282,16 @@ class MD:
     def step(self, itime, it0, nb_uptab, h):
         return lib().orc_md_step(self.h, C.c_int(itime), C.c_int(it0), C.c_int(nb_uptab), C.c_double(h))
 
+    def global_t(self):
+        lib().orc_md_global_t.restype = C.c_double
+        return float(lib().orc_md_global_t(self.h))
+
+    def vel_scaling(self, dt):
+        return int(lib().orc_md_vel_scaling(self.h, C.c_double(dt)))
+
+    def check_timestep(self, th, h2s2, mxd2):
+        return int(lib().orc_md_check_timestep(self.h, C.c_double(th), C.c_double(h2s2), C.c_double(mxd2)))
+
     def steepest0(self, mxnumsteps, alpha0, maxdis, mindis, minepot):
         """Do_Steepest0_Forsteps_DEV; returns (IFLAG, MAXMOVE [cm], DELEPOT [erg])"""
         mm, de = C.c_double(0.0), C.c_double(0.0)

@@ -379,3 +379,32 @@ def test_steepest_quench_of_the_reference_example():
     assert ce <= ce_ref + 5e-7 and abs(ce - ce_ref) < 1e-5   # at least as deep as the reference's damped state
     assert f1 <= np.abs(g["force"]).max() * 1.05
     ctx.close()
+
+
+def test_temperature_scaling_and_timestep_check_match_oracle(oracle):
+    """Cal_GlobalT_DEV, VelScaling_DEV (per box, 3 boxes) and CheckTimestep_DEV (MD_DiffScheme_GPU.F90:1042-1446)
+    against their restatements, with a fixed atom, a velocity-fixed component and an inactive atom in the mix."""
+    c = util.bcc_case((6, 6, 6), seed=9, temp=500.0, nbox=3)
+    c.statu = c.statu.copy()
+    c.statu[3] |= 2 | 4 | 8          # FIXPOS xyz: not counted in T, velocity zeroed by the scaling
+    c.statu[10] |= 32                # FIXVELY
+    c.statu[500] = 0                 # inactive
+    md = util.oracle_md(oracle, c)
+    md.rebuild(); md.force()
+    ctx = util.make_ctx(c)
+    ctx.force(capi.FORCE)
+    t0, t0_ref = ctx.global_t(), md.global_t()
+    assert abs(t0 - t0_ref) < 1e-12 * t0_ref and 150.0 < t0 < 350.0
+    h = 0.5e-15
+    d2 = np.sum((h * c.xp1) ** 2, axis=1).max()
+    for mxd2 in (0.25 * d2, 4.0 * d2):
+        assert ctx.check_timestep(h, 0.5 * h * h, mxd2) == md.check_timestep(h, 0.5 * h * h, mxd2)
+    assert ctx.check_timestep(h, 0.5 * h * h, 0.25 * d2) == 1 and ctx.check_timestep(h, 0.5 * h * h, 4.0 * d2) == 0
+    ctx.vel_scaling(300.0)
+    assert md.vel_scaling(300.0) == 0
+    assert util.relerr(ctx.download(capi.F_XP1), md.get()["xp1"]) < 1e-13
+    t1 = ctx.global_t()
+    assert abs(t1 - md.global_t()) < 1e-12 * t1 and abs(t1 - 300.0) < 1.0   # (the FIXVEL component was zeroed after the factor was set)
+    v = ctx.download(capi.F_XP1)
+    assert np.all(v[3] == 0.0) and v[10, 1] == 0.0 and v[10, 0] != 0.0
+    ctx.close()
