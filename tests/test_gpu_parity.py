@@ -394,7 +394,7 @@ def test_temperature_scaling_and_timestep_check_match_oracle(oracle):
     ctx = util.make_ctx(c)
     ctx.force(capi.FORCE)
     t0, t0_ref = ctx.global_t(), md.global_t()
-    assert abs(t0 - t0_ref) < 1e-12 * t0_ref and 150.0 < t0 < 350.0
+    assert abs(t0 - t0_ref) < 1e-12 * t0_ref and 400.0 < t0 < 600.0
     h = 0.5e-15
     d2 = np.sum((h * c.xp1) ** 2, axis=1).max()
     for mxd2 in (0.25 * d2, 4.0 * d2):
