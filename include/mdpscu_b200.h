@@ -274,6 +274,34 @@ int mdb_host_ftable_create(int lib, int ng, const int *ptype, int ntab, int nemb
                            double *potr, double *fpotr, double *potb, double *fpotb,
                            double *fembd, double *dfembd, double *csi, double *rhod);
 
+/* ------------------------------------------------------------------------------------
+ * external force tables (csrc/host_tables_io.cpp)
+ *
+ * mdb_host_setfl_*: the NIST "setfl" importer = Register_ForceTableProc_Setfl + Generate_NIST_ForceTalbe
+ *   (Potentials/EAM_NIST/Filedatas_Func_Setfl.F90:153-296,320-462,505-541; NIST_ForceTable.F90:332-398):
+ *   cubic splines with zero end curvature through the file's F(rho), rho(r), r*V(r); one table per id
+ *   it = (I-1)*NE+J ("I <- J"), kind index = id; table range and RHOMX from the file (rmax <= 0) .
+ *   Outputs caller-allocated: pair tables NE*NE*ntab doubles, embedding NE*NE*nembd, T(NKIND,N) column-major.
+ * mdb_host_ftable_export: Export_ForceTable (Common/MD_TypeDef_ForceTable.F90:1315-1459) -> fname.pair/.embd
+ * mdb_host_ftable_file_info / _import: Import_ForceTable (:1461-1591) + Register_Imported_ForceTable
+ *   (:1595-1855): re-grid the tables PTYPE(ng,ng) names onto the run's grid (SPLID1 IOP=5 / SPLID2).
+ * All return MDB_OK or MDB_ERR_ARG (unreadable / malformed file, id not in the file); nothing prints or stops.
+ * ---------------------------------------------------------------------------------- */
+int mdb_host_setfl_info(const char *path, int *nelem, int *nrho, int *nr, double *cutoff_cm, double *rhomx,
+                        char *names, int names_stride, int *z, double *mass, double *alat);
+int mdb_host_setfl_ftable(const char *path, int ntab, int nembd, double rmax, int *nkind,
+                          double *potr, double *fpotr, double *potb, double *fpotb, double *fembd, double *dfembd,
+                          double *csi, double *rhod, double *rmax_out);
+int mdb_host_ftable_export(const char *fname, int pot_type, int nkind, const int *ids, int ntab, double csi,
+                           const double *potr, const double *fpotr, const double *potb, const double *fpotb,
+                           int nkind1, const int *ids1, int nembd, double rhod, const double *fembd, const double *dfembd);
+int mdb_host_ftable_file_info(const char *fname, int *pot_type, int *nkind, int *ids, int *ntab, int *nkind1, int *ids1,
+                              int *nembd, double *rmax_cm, double *rhomx);
+int mdb_host_ftable_import(const char *fname, int ng, const int *ptype, int ntab, int nembd, double rmax,
+                           int *pot_type, int *nkind, int *nkind1, int *kpair, int *kembd,
+                           double *potr, double *fpotr, double *potb, double *fpotb, double *fembd, double *dfembd,
+                           double *csi, double *rhod);
+
 #ifdef __cplusplus
 }
 #endif

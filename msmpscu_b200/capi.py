@@ -75,6 +75,14 @@ SYMBOLS = {
     "mdb_launch_count": (C.c_longlong, [C.c_void_p]),
     "mdb_host_ftable_create": (C.c_int, [C.c_int, C.c_int, c_ip, C.c_int, C.c_int, C.c_double, C.c_double, c_ip, c_ip,
                                          c_ip, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "mdb_host_setfl_info": (C.c_int, [C.c_char_p, c_ip, c_ip, c_ip, c_dp, c_dp, C.c_char_p, C.c_int, c_ip, c_dp, c_dp]),
+    "mdb_host_setfl_ftable": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_double, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                        c_dp, c_dp, c_dp]),
+    "mdb_host_ftable_export": (C.c_int, [C.c_char_p, C.c_int, C.c_int, c_ip, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp,
+                                         C.c_int, c_ip, C.c_int, C.c_double, c_dp, c_dp]),
+    "mdb_host_ftable_file_info": (C.c_int, [C.c_char_p, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_dp, c_dp]),
+    "mdb_host_ftable_import": (C.c_int, [C.c_char_p, C.c_int, c_ip, C.c_int, C.c_int, C.c_double, c_ip, c_ip, c_ip, c_ip, c_ip,
+                                         c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
 }
 
 OPT_FORCE_PATH, OPT_TILED_LANES, OPT_TILED_CLASSES, OPT_ACTIVE_PATH, OPT_TILED_THREADS, OPT_FUSE_EPILOGUE, OPT_TILED_STAGES = 0, 1, 2, 3, 4, 5, 6

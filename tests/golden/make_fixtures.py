@@ -15,7 +15,13 @@ Outputs (small, committed):
       sampled rows of examples/use_ForceTableGen/EAM_WHeH_Bonny_JPCM26_2014.embd
       (Export_ForceTable output: RHO, F_k(RHO), dF_k/dRHO for the 9 ids).
   box/control text files used by those runs are copied verbatim (inputs, not source code).
+  Cu1.eam.fs.setfl.xz
+      examples/NIST_Potentials/Cu_EAM/Cu1.eam.fs.setfl (public NIST potential data file, an input), xz-compressed.
+  cu1_setfl_table_rows.npz
+      sampled rows of the reference's own import of that file, examples/NIST_Potentials/Cu_EAM/Cu1.eam.fs.setfl.pair
+      and .embd (Export_ForceTable output, 10 / 9 significant digits): pins the setfl importer.
 """
+import lzma
 import os
 import shutil
 import sys
@@ -77,6 +83,26 @@ def main():
     sel = np.unique(np.concatenate([np.arange(0, 64), np.arange(64, 10000, 97), [9998, 9999]]))
     np.savez_compressed(os.path.join(HERE, "bonny_eam1_embd_rows.npz"), index=a[sel, 0].astype(np.int32),
                         rho=a[sel, 1], f=a[sel, 2::2], df=a[sel, 3::2])
+    # NIST setfl input + the reference's exported tables for it
+    cu = os.path.join(REF, "examples", "NIST_Potentials", "Cu_EAM")
+    with open(os.path.join(cu, "Cu1.eam.fs.setfl"), "rb") as f, lzma.open(os.path.join(HERE, "Cu1.eam.fs.setfl.xz"), "wb", preset=9) as g:
+        g.write(f.read())
+
+    def rows_of(path, ncol):
+        out = []
+        with open(path) as f:
+            for line in f:
+                p = line.split()
+                if len(p) == ncol and p[0].isdigit():
+                    out.append([float(x) for x in p])
+        return np.array(out)
+
+    pr = rows_of(os.path.join(cu, "Cu1.eam.fs.setfl.pair"), 6)
+    em = rows_of(os.path.join(cu, "Cu1.eam.fs.setfl.embd"), 4)
+    assert pr.shape[0] == 10000 and em.shape[0] == 10000
+    sel = np.unique(np.concatenate([np.arange(0, 64), np.arange(64, 10000, 23), np.arange(1270, 1340), np.arange(9950, 10000)]))
+    np.savez_compressed(os.path.join(HERE, "cu1_setfl_table_rows.npz"), index=pr[sel, 0].astype(np.int32), r=pr[sel, 1],
+                        pair=pr[sel, 2:6], rho=em[sel, 1], embd=em[sel, 2:4])
     print("fixtures written to", HERE)
 
 

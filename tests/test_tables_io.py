@@ -1,0 +1,115 @@
+"""External force tables: the NIST setfl importer and the .pair/.embd files, pinned on the reference's
+own output for examples/NIST_Potentials/Cu_EAM (Cu1.eam.fs.setfl -> Cu1.eam.fs.setfl.pair/.embd written by the
+reference's Export_ForceTable, 10 and 9 significant digits).  CPU only: host logic, no kernels."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from msmpscu_b200 import capi, forcetable
+from oracle import tables_np
+
+PRINT_PAIR = 6e-10   # 1PE21.9: 10 significant digits
+PRINT_EMBD = 6e-9    # 1PE16.8: 9 significant digits
+# The file's rho(r) and r*V(r) hold 1e12 for r < 0.1 A and drop to O(10..100) within one grid step; spline values next to
+# that step are differences of O(1e12) terms, so they carry an absolute round-off of ~1e12 * 2^-52 * (a few), in the
+# reference's B-spline solve as much as in any other.  Rows there are compared with that absolute allowance.
+JUMP_ABS = 2e-3
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(util.GOLD, "cu1_setfl_table_rows.npz"))
+
+
+@pytest.fixture(scope="module")
+def setfl(tmp_path_factory):
+    return util.cu_setfl_path(tmp_path_factory.mktemp("setfl"))
+
+
+def _check_rows(pair, embd, r, rho, gold):
+    sel = gold["index"] - 1
+    assert np.allclose(r[sel], gold["r"], rtol=PRINT_PAIR, atol=0)
+    assert np.allclose(rho[sel], gold["rho"], rtol=PRINT_EMBD, atol=1e-300)
+    near_jump = gold["r"] < 0.12
+    for c in range(4):
+        g, m = gold["pair"][:, c], pair[sel, c]
+        # derivative columns: the same round-off divided by the file's grid step (6e-4 A)
+        tol = PRINT_PAIR * np.abs(g) + np.where(near_jump, JUMP_ABS if c in (0, 2) else JUMP_ABS / 6e-4, 1e-40)
+        bad = np.abs(m - g) > tol
+        assert not bad.any(), (c, gold["index"][bad][:5], g[bad][:5], m[bad][:5])
+    for c in range(2):
+        g, m = gold["embd"][:, c], embd[sel, c]
+        assert np.all(np.abs(m - g) <= PRINT_EMBD * np.abs(g) + 1e-40), c
+
+
+def test_oracle_setfl_matches_reference_tables(setfl, gold):
+    """the NumPy/SciPy restatement against the reference's exported tables"""
+    t = tables_np.setfl_tables(open(setfl).read(), 10000, 10000)
+    pair, embd = tables_np.export_columns(t)
+    r = (np.arange(1, 10001) / t["csi"]) ** 2 * 1e8
+    _check_rows(pair[0], embd[0], r, np.arange(10000) * t["rhod"], gold)
+
+
+def test_product_setfl_matches_reference_tables(setfl, gold):
+    """mdb_host_setfl_ftable (C++) against the reference's exported tables"""
+    info = forcetable.setfl_info(setfl)
+    assert info["elements"] == ["Cu"] and info["z"][0] == 29 and info["nr"] == 10000
+    assert abs(info["cutoff"] - 6.0e-8) < 1e-20 and abs(info["rhomx"] - 300.0) < 1e-12
+    t = forcetable.NIST_Register_Interaction_Table(setfl, 10000, 10000)
+    ergev = 1.0 / 1.60219e-12
+    pair = np.stack([t.potr * 2 * ergev * 1e8, t.fpotr * ergev, t.potb, t.fpotb * 1e-8], axis=1)
+    embd = np.stack([t.fembd * ergev, t.dfembd], axis=1)
+    r = (np.arange(1, 10001) / t.csi) ** 2 * 1e8
+    _check_rows(pair, embd, r, np.arange(10000) * t.rhod, gold)
+
+
+def test_product_setfl_matches_oracle_full_precision(setfl):
+    """both restatements agree far below print precision away from the 1e12 step (different algorithms: tridiagonal
+    second-derivative solve in C++ vs SciPy's CubicSpline)"""
+    o = tables_np.setfl_tables(open(setfl).read(), 4000, 3000, rmax=5.5e-8)
+    t = forcetable.NIST_Register_Interaction_Table(setfl, 4000, 3000, rmax=5.5e-8)
+    r = (np.arange(1, 4001) / t.csi) ** 2 * 1e8
+    far = r > 0.2
+    for name in ("potr", "fpotr", "potb", "fpotb"):
+        a, b = getattr(t, name)[far], o[name][0][far]
+        assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b)), name
+    for name in ("fembd", "dfembd"):
+        a, b = getattr(t, name), o[name][0]
+        assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b)), name
+    assert t.csi == o["csi"] and t.rhod == o["rhod"]
+
+
+def test_export_then_import_round_trip(setfl, gold, tmp_path):
+    """Export_ForceTable -> Import_ForceTable/Register_Imported_ForceTable on the same grid gives the tables back to
+    print precision, and the exported text carries the reference's numbers."""
+    t = forcetable.NIST_Register_Interaction_Table(setfl, 10000, 10000)
+    base = str(tmp_path / "cu1")
+    forcetable.Export_ForceTable(base, t)
+    rows = np.array([[float(v) for v in line.split()] for line in open(base + ".pair") if line.split() and line.split()[0].isdigit()])
+    erow = np.array([[float(v) for v in line.split()] for line in open(base + ".embd") if line.split() and line.split()[0].isdigit()])
+    assert rows.shape == (10000, 6) and erow.shape == (10000, 4)
+    _check_rows(rows[:, 2:], erow[:, 2:], rows[:, 1], erow[:, 1], gold)
+    head = open(base + ".pair").read(2000)
+    assert "&MDPSCU_POTTAB.Pair" in head and '&POTTYPE "EAM_TYPE"' in head and "&NUMPOINT   10000" in head
+    back = forcetable.Register_Imported_ForceTable(base, [[1]], 10000, 10000, t.Rmax)
+    assert back.PotType == "EAM_TYPE" and back.nkind == 1 and list(back.kpair) == [1] and list(back.kembd) == [1]
+    r = (np.arange(1, 10001) / t.csi) ** 2 * 1e8
+    far = r > 0.2
+    for name in ("potr", "fpotr", "potb", "fpotb"):
+        a, b = getattr(back, name)[far], getattr(t, name)[far]
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12 * np.max(np.abs(b)))) < 2e-9, name
+    assert abs(back.rhod - t.rhod) < 1e-8 * t.rhod
+    assert np.max(np.abs(back.fembd - t.fembd)) < 1e-8 * np.max(np.abs(t.fembd))
+    # a coarser run grid (the case Register_Imported_ForceTable exists for): values stay on the source curve
+    coarse = forcetable.Register_Imported_ForceTable(base, [[1]], 2500, 2500, t.Rmax)
+    a, b = coarse.potr[200:], t.potr[3::4][200:]   # r_k(2500) = r_4k(10000)
+    assert np.max(np.abs(a - b)) < 2e-9 * np.max(np.abs(b))
+
+
+def test_import_errors_are_status_codes(tmp_path):
+    with pytest.raises(capi.MDBError):
+        forcetable.setfl_info(str(tmp_path / "missing.setfl"))
+    with pytest.raises(capi.MDBError):
+        forcetable.Register_Imported_ForceTable(str(tmp_path / "missing"), [[1]], 100, 100, 1e-8)

@@ -58,11 +58,48 @@ def neb_case(tag="react", rmax_mode="RU"):
     return c
 
 
+def cu_setfl_path(tmpdir=None):
+    """examples/NIST_Potentials/Cu_EAM/Cu1.eam.fs.setfl, unpacked from the committed xz fixture"""
+    import lzma
+    import tempfile
+    d = tmpdir or tempfile.gettempdir()
+    p = os.path.join(str(d), "Cu1.eam.fs.setfl")
+    if not os.path.exists(p):
+        with lzma.open(os.path.join(GOLD, "Cu1.eam.fs.setfl.xz"), "rb") as f, open(p + ".tmp%d" % os.getpid(), "wb") as g:
+            g.write(f.read())
+        os.replace(p + ".tmp%d" % os.getpid(), p)
+    return p
+
+
+def fcc_cu_case(ncell=(8, 8, 8), seed=4242, nbox=1, ntab=10000):
+    """fcc Cu with the NIST setfl potential Cu1 (Mendelev 2008) imported like the reference's EAM_NIST library:
+    table range = the file's cutoff (6 A), list cutoff 1.2 x."""
+    c = Case()
+    c.__dict__.update(lattice.fcc_box(ncell, 3.639087, seed, nbox=nbox))
+    c.ifpd = [1, 1, 1]
+    c.ng = 1
+    c.ru = 6.0 * CP_A2CM
+    c.nb_rm = np.full((1, 1), 1.2 * c.ru)
+    c.mxkvois = 256
+    c.ntab = c.nembd = ntab
+    c.setfl = cu_setfl_path()
+    c.ptype = np.array([[1]])
+    c.rmax = c.ru
+    return c
+
+
 def product_tables(c):
+    if getattr(c, "setfl", None):
+        return forcetable.NIST_Register_Interaction_Table(c.setfl, c.ntab, c.nembd, c.ptype, rmax=c.rmax)
     return forcetable.Create_Interaction_ForceTable(c.lib, c.ptype, c.ntab, c.nembd, c.rmax)
 
 
 def oracle_tables(O, c):
+    if getattr(c, "setfl", None):
+        from oracle import tables_np
+        t = tables_np.setfl_tables(open(c.setfl).read(), c.ntab, c.nembd, rmax=c.rmax)
+        return O.Tables.from_arrays(c.ng, c.ptype, np.diag(c.ptype), c.ntab, c.nembd, t["csi"], t["rhod"], c.ru, t["potr"],
+                                    t["fpotr"], t["potb"], t["fpotb"], t["fembd"], t["dfembd"])
     lib = {capi.LIB_MARINICA_EAM2: O.LIB_MARINICA_EAM2, capi.LIB_BONNY_EAM1: O.LIB_BONNY_EAM1}[c.lib]
     return O.Tables(lib, c.ptype, c.ntab, c.nembd, c.ru, rmax=c.rmax)
 
