@@ -148,6 +148,14 @@ module MDB_C_BINDING
        integer(c_int)        :: iflag
        real(c_double)        :: maxmove, delepot
      end function
+     integer(c_int) function mdb_cg(ctx, mxnumsteps, meth, maxdis, mindis, minepot, iflag, delepot) bind(C, name="mdb_cg")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: mxnumsteps, meth
+       real(c_double), value :: maxdis, mindis, minepot
+       integer(c_int)        :: iflag
+       real(c_double)        :: delepot
+     end function
   end interface
 
   !--- one context per process: the reference keeps its device state in module variables too

@@ -147,3 +147,30 @@ contains
       end if
   end subroutine
 end module MD_SteepestScheme_GPU
+
+!--- CommonGPU/MD_CGScheme_GPU.F90:280-296
+module MD_CGScheme_GPU
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use mdb_c_binding
+  implicit none
+contains
+  subroutine Do_CG_Forsteps_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, METH)
+      use MD_Forceclass_Register_GPU
+      type(SimMDBox), dimension(:)      :: SimBox
+      type(SimMDCtrl),       intent(in) :: CtrlParam
+      type(MDForceClassGPU), intent(in) :: ForceClass
+      integer,               intent(in) :: MXNUMSTEPS, METH
+      integer(c_int) :: IFLAG
+      real(c_double) :: DELEPOT
+      if(mdb_cg(m_CTX, MXNUMSTEPS, METH, CtrlParam%STEEPEST_MxStep*SimBox(1)%RR, CtrlParam%STEEPEST_MiStep*SimBox(1)%RR,   &
+                CtrlParam%STEEPEST_MiDelE*CP_EV2ERG, IFLAG, DELEPOT) .lt. 0) stop "MDPSCU Error: mdb_cg failed"
+      if(IFLAG .eq. 0) then
+         write(*,fmt="(A, I8)")      " MDPSCU WARNING: CG finished after max steps: ", MXNUMSTEPS
+         call ONWARNING(gm_OnWarning)
+      else
+         write(*,fmt="(A, I8)")      " MDPSCU Message: CG finished after steps: ", IFLAG
+         write(*,fmt="(A, 1PE13.4)") "                 with max energy uncertainty(ev): ", DELEPOT*CP_ERG2EV
+      end if
+  end subroutine
+end module MD_CGScheme_GPU

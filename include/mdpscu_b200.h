@@ -209,7 +209,8 @@ int mdb_check_timestep(mdb_ctx *ctx, double th, double h2s2, double dmx2, int *i
  * For_One_Step's QUICKDAMP "ST" branch (Appshell/MD_Method_GenericMD_GPU.F90:540-546) and by the PARREP event
  * quench.  alpha = STEEPEST_Alpha; maxdis / mindis = STEEPEST_MxStep / STEEPEST_MiStep * RR [cm];
  * minepot = STEEPEST_MiDelE * CP_EV2ERG [erg].  meth = CtrlParam%DAMPSCHEME: with MDB_QUENCH_LSEARCH set the
- * reference runs the line-search variant (:157-260), which returns MDB_ERR_UNSUPPORTED here for now.
+ * reference runs the line-search variant Do_Steepest1_Forsteps_DEV (:157-260): normalised force direction, repeated
+ * secant steps until |STEPSIZE| <= mindis, energy criterion fixed at 0.001 eV (alpha and minepot unused, as there).
  * Outputs (may be NULL): iflag = iteration at which a criterion was met (0: ran out of steps, -1: converged at
  * the first step), maxmove [cm], delepot [erg] as the reference prints them.  The scalars and the stop flag live on
  * the device; the host synchronises once per 8 iterations instead of five times per iteration.
@@ -217,6 +218,14 @@ int mdb_check_timestep(mdb_ctx *ctx, double th, double h2s2, double dmx2, int *i
 #define MDB_QUENCH_LSEARCH 65536 /* CP_DAMPSCHEME_LSEARCH, Common/MD_Const.F90:27 */
 int mdb_steepest(mdb_ctx *ctx, int mxnumsteps, int meth, double alpha, double maxdis, double mindis, double minepot,
                  int *iflag, double *maxmove, double *delepot);
+
+/* Do_CG_Forsteps_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, METH), CommonGPU/MD_CGScheme_GPU.F90:280-296:
+ * Polak-Ribiere conjugate gradient on the current list; meth without MDB_QUENCH_LSEARCH -> Do_CG0_Forsteps_DEV (:16-133,
+ * one secant step per direction; scalars and stop flag device-resident, host looks once per 4 iterations), with it ->
+ * Do_CG1_Forsteps_DEV (:137-276, repeated secant steps until |STEPSIZE| <= mindis; one 128-byte readback per force
+ * evaluation).  iflag: the reference's ITER when DELEPOT <= minepot or F0NORM <= 1e-64 fired, 0 when the budget ran
+ * out, -1 when F0NORM <= 1e-64 before the first step. */
+int mdb_cg(mdb_ctx *ctx, int mxnumsteps, int meth, double maxdis, double mindis, double minepot, int *iflag, double *delepot);
 
 /* ------------------------------------------------------------------------------------
  * options.  MDB_OPT_FORCE_PATH selects the force/list implementation:

@@ -65,6 +65,7 @@ SYMBOLS = {
     "mdb_vel_scaling": (C.c_int, [C.c_void_p, C.c_double]),
     "mdb_check_timestep": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip]),
     "mdb_steepest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_ip, c_dp, c_dp]),
+    "mdb_cg": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, c_ip, c_dp]),
     "mdb_dd_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdb_dd_info": (C.c_int, [C.c_void_p, c_ip]),
     "mdb_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -295,6 +296,13 @@ class Context:
         self._chk(self.lib.mdb_steepest(self.h, int(mxnumsteps), int(meth), float(alpha), float(maxdis), float(mindis),
                                         float(minepot), C.byref(fl), C.byref(mm), C.byref(de)))
         return fl.value, mm.value, de.value
+
+    def cg(self, mxnumsteps, maxdis, mindis, minepot, meth=0):
+        """Do_CG_Forsteps_DEV on the current list (meth & QUENCH_LSEARCH: the line-search variant); returns (IFLAG, DELEPOT [erg])."""
+        fl, de = C.c_int(0), C.c_double(0.0)
+        self._chk(self.lib.mdb_cg(self.h, int(mxnumsteps), int(meth), float(maxdis), float(mindis), float(minepot),
+                                  C.byref(fl), C.byref(de)))
+        return fl.value, de.value
 
     def dd_set(self, rank, nranks):
         self._chk(self.lib.mdb_dd_set(self.h, int(rank), int(nranks)))

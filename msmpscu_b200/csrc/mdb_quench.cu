@@ -13,7 +13,10 @@
 struct QuenchScal {
     double dotdxdf, dotdf, maxmove, delepot, alpha, scale;
     int done, iflag, ticket, pending, iter, pad;
+    // conjugate-gradient / line-search schemes
+    double f0norm, pf0, pf1, step, coef, mf1;
 };
+static_assert(sizeof(QuenchScal) <= 128, "QuenchScal is mirrored in a 128-byte pinned host buffer");
 
 #define QT 256
 
@@ -198,6 +201,8 @@ __global__ void __launch_bounds__(QT) k_sd_save(size_t n3, int n, const double *
     for (size_t i = blockIdx.x * (size_t)QT + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * QT) epot0[i] = epot[i];
 }
 
+static int steepest1(mdb_ctx *c, int mxnumsteps, double maxdis, double mindis, int *iflag, double *delepot);
+
 extern "C" int mdb_steepest(mdb_ctx *c, int mxnumsteps, int meth, double alpha, double maxdis, double mindis, double minepot,
                             int *iflag, double *maxmove, double *delepot)
 {
@@ -205,8 +210,10 @@ extern "C" int mdb_steepest(mdb_ctx *c, int mxnumsteps, int meth, double alpha, 
     if (!c->has_box || !c->has_tables || !c->has_nlist || !c->list_valid)
         return mdb_fail(c, MDB_ERR_STATE, "mdb_steepest: box, tables and a valid neighbour list are required");
     if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_steepest: not available in slab-decomposed runs yet");
-    if (meth & MDB_QUENCH_LSEARCH)
-        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_steepest: the line-search variant (Do_Steepest1_Forsteps_DEV) is not implemented yet");
+    if (meth & MDB_QUENCH_LSEARCH) { // Do_Steepest_Forsteps_DEV :263-290 dispatches on CP_DAMPSCHEME_LSEARCH
+        if (maxmove) *maxmove = 0.0;
+        return steepest1(c, mxnumsteps, maxdis, mindis, iflag, delepot);
+    }
     CUDA_TRY(c, cudaSetDevice(c->dev));
     const int n = c->n;
     const size_t n3 = (size_t)n * 3;
@@ -260,4 +267,283 @@ extern "C" int mdb_steepest(mdb_ctx *c, int mxnumsteps, int meth, double alpha, 
     if (maxmove) *maxmove = H->maxmove;
     if (delepot) *delepot = H->delepot;
     return finish(MDB_OK);
+}
+
+
+// =====================================================================================================================
+// Conjugate gradient (Do_CG0/CG1_Forsteps_DEV, CommonGPU/MD_CGScheme_GPU.F90:16-276) and steepest descent with line
+// search (Do_Steepest1_Forsteps_DEV, CommonGPU/MD_SteepestScheme_GPU.F90:157-260).
+//
+// The reference expresses these with whole-array device operations (MSM_MultiGPU_Basic.F90: DevMultiply, DevAdd_shift,
+// DevMinus, DevDot, DevMaxAbsval), each dot product a blocking reduction finished on the host.  Here an iteration is a
+// handful of fused kernels whose reductions end in the last block to arrive, which also does the scalar update that
+// follows in the reference (secant step, clamp, Polak-Ribiere factor), so STEPSIZE, PF0/PF1, F0NORM and GAMA never leave
+// the device.  CG0 has no data-dependent branch inside an iteration: it runs exactly like mdb_steepest (stop flag on the
+// device, every later kernel -- force passes included -- returns at once, host looks once per batch).  The line-search
+// variants decide after every force evaluation whether |STEPSIZE| <= MINDIS; the host reads one 128-byte record per
+// force evaluation for that (the reference: two blocking reductions + host arithmetic per evaluation).
+// =====================================================================================================================
+enum { QD_PF1_CG = 0, QD_PF1_SD = 1, QD_MF1 = 2, QD_NORM = 3 };
+
+// sum a[i] * (b[i] - bsub[i]) (bsub may be null) and the scalar update `mode` that follows it in the reference
+__global__ void __launch_bounds__(QT) k_q_dot(size_t n3, const double *__restrict__ a, const double *__restrict__ b,
+                                              const double *__restrict__ bsub, double *__restrict__ part, QuenchScal *S, int mode,
+                                              double maxdis)
+{
+    if (S->done) return;
+    __shared__ double sh[QT / 32];
+    double v = 0.0;
+    for (size_t i = blockIdx.x * (size_t)QT + threadIdx.x; i < n3; i += (size_t)gridDim.x * QT) {
+        const double bb = bsub ? __dsub_rn(b[i], bsub[i]) : b[i];
+        v += a[i] * bb;
+    }
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+    if (last_block(S)) {
+        double sum = 0.0;
+        for (int k = 0; k < (int)gridDim.x; k++) sum += ((volatile double *)part)[k];
+        if (mode == QD_MF1) S->mf1 = sum;
+        else if (mode == QD_NORM) S->f0norm = sum;
+        else {
+            // STEPSIZE = -STEPSIZE*PF1/(PF1 - PF0), capped at MAXDIS with its sign (MD_CGScheme_GPU.F90:71-74, MD_SteepestScheme_GPU.F90:221-224)
+            const double pf1 = sum;
+            double step = -S->step * pf1 / (pf1 - S->pf0);
+            if (fabs(step) > maxdis) step = maxdis * fabs(step) / step;
+            S->pf1 = pf1;
+            S->step = step;
+            S->coef = (mode == QD_PF1_CG) ? step / sqrt(S->f0norm) : step;
+            S->pf0 = pf1; // PF0 = PF1 of the line search (:214 / :232); recomputed with the next direction otherwise
+        }
+    }
+}
+
+// DXP = coef*Dir ; XP = wrap(DXP + XP)   (DevMultiply_noshift + DevAdd_shift)
+__global__ void __launch_bounds__(QT) k_q_move(int n, const double *__restrict__ dir, double4 *__restrict__ pos, BoxParams box,
+                                               float *__restrict__ dsr, int *__restrict__ counters, const QuenchScal *S)
+{
+    if (S->done) return;
+    const double coef = S->coef;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float d2 = 0.f;
+    if (i < n) {
+        double4 p = pos[i];
+        double x[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const size_t o = i + (size_t)d * n;
+            const double dd = __dmul_rn(coef, dir[o]);
+            double rt = __dadd_rn(dd, x[d]);
+            const double lb = box.pd[d] ? box.lo[d] : -1.0e108, hb = box.pd[d] ? box.up[d] : 1.0e108;
+            if (rt > hb) rt = __dsub_rn(rt, __dsub_rn(hb, lb));
+            else if (rt < lb) rt = __dadd_rn(rt, __dsub_rn(hb, lb));
+            x[d] = rt;
+            if (dsr) { const float t = dsr[o] + (float)dd; dsr[o] = t; d2 += t * t; }
+        }
+        p.x = x[0]; p.y = x[1]; p.z = x[2];
+        pos[i] = p;
+    }
+    if (dsr) {
+        for (int off = 16; off > 0; off >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, off));
+        if ((threadIdx.x & 31) == 0 && d2 > 0.f) atomicMax(&counters[CNT_D2MAX], __float_as_int(d2));
+    }
+}
+
+// new direction.  first != 0: Dir = FP (:56-57).  Otherwise GAMA = MF1NORM/F0NORM, Dir = FP + GAMA*Dir (:93-99).
+// Then F0 = FP, F0NORM = F0.F0, PF0 = FP.Dir, and the trial step of the next iteration STEPSIZE = MAXDIS/sqrt(F0NORM) (:62).
+__global__ void __launch_bounds__(QT) k_q_cgdir(size_t n3, int first, const double *__restrict__ fp, double *__restrict__ f0,
+                                                double *__restrict__ dir, double *__restrict__ part, QuenchScal *S, double maxdis,
+                                                double eps, int it)
+{
+    if (S->done) return;
+    __shared__ double sh[QT / 32];
+    const double gama = first ? 0.0 : S->mf1 / S->f0norm;
+    double a = 0.0, b = 0.0;
+    for (size_t i = blockIdx.x * (size_t)QT + threadIdx.x; i < n3; i += (size_t)gridDim.x * QT) {
+        const double f = fp[i];
+        const double dnew = first ? f : __dadd_rn(f, __dmul_rn(gama, dir[i]));
+        dir[i] = dnew;
+        f0[i] = f;
+        a += f * f;
+        b += f * dnew;
+    }
+    a = block_sum(a, sh);
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
+    if (last_block(S)) {
+        double sa = 0.0, sb = 0.0;
+        for (int k = 0; k < (int)gridDim.x; k++) { sa += ((volatile double *)part)[2 * k]; sb += ((volatile double *)part)[2 * k + 1]; }
+        S->f0norm = sa; S->pf0 = sb;
+        S->step = maxdis / sqrt(sa);
+        S->coef = S->step;
+        if (sa <= eps) { S->done = 1; S->iflag = it; } // :46-54 (it = -1), :103-105
+    }
+}
+
+// Dir = (1/sqrt(FP.FP))*FP (DevNormalize), PF0 = FP.Dir, STEPSIZE = MAXDIS   (MD_SteepestScheme_GPU.F90:207-212)
+__global__ void __launch_bounds__(QT) k_q_sd1dir(size_t n3, const double *__restrict__ fp, double *__restrict__ dir,
+                                                 double *__restrict__ part, QuenchScal *S, double maxdis)
+{
+    __shared__ double sh[QT / 32];
+    const double sc = 1.0 / sqrt(S->f0norm);
+    double b = 0.0;
+    for (size_t i = blockIdx.x * (size_t)QT + threadIdx.x; i < n3; i += (size_t)gridDim.x * QT) {
+        const double f = fp[i], dnew = __dmul_rn(sc, f);
+        dir[i] = dnew;
+        b += f * dnew;
+    }
+    b = block_sum(b, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = b;
+    if (last_block(S)) {
+        double sb = 0.0;
+        for (int k = 0; k < (int)gridDim.x; k++) sb += ((volatile double *)part)[k];
+        S->pf0 = sb; S->step = maxdis; S->coef = maxdis;
+    }
+}
+
+namespace {
+struct QuenchWork {
+    double *f0, *dir, *epot0, *part;
+    QuenchScal *S, *H;
+    int nblk;
+    size_t n3;
+};
+int quench_setup(mdb_ctx *c, const char *who, QuenchWork &w)
+{
+    if (!c->has_box || !c->has_tables || !c->has_nlist || !c->list_valid)
+        return mdb_fail(c, MDB_ERR_STATE, "quench: box, tables and a valid neighbour list are required");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "quench: not available in slab-decomposed runs yet");
+    (void)who;
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    const int n = c->n;
+    w.n3 = (size_t)n * 3;
+    w.nblk = std::min(1024, cdiv((long long)w.n3, QT));
+    if (c->q_n != n) {
+        if (c->q_buf) cudaFree(c->q_buf);
+        c->q_buf = nullptr; c->q_n = 0;
+        CUDA_TRY(c, cudaMalloc(&c->q_buf, sizeof(double) * (2 * w.n3 + n + 2 * 1024 + 16)));
+        c->q_n = n;
+    }
+    if (!c->q_host) CUDA_TRY(c, cudaMallocHost(&c->q_host, 128));
+    w.f0 = c->q_buf; w.dir = w.f0 + w.n3; w.epot0 = w.dir + w.n3; w.part = w.epot0 + n;
+    w.S = reinterpret_cast<QuenchScal *>(w.part + 2 * 1024);
+    w.H = reinterpret_cast<QuenchScal *>(c->q_host);
+    CUDA_TRY(c, cudaMemsetAsync(c->q_buf, 0, sizeof(double) * (2 * w.n3 + n + 2 * 1024 + 16), c->stream));
+    return MDB_OK;
+}
+int quench_peek(mdb_ctx *c, QuenchWork &w)
+{
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(w.H, w.S, sizeof(QuenchScal), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MDB_OK;
+}
+} // namespace
+
+extern "C" int mdb_cg(mdb_ctx *c, int mxnumsteps, int meth, double maxdis, double mindis, double minepot, int *iflag, double *delepot)
+{
+    if (!c || mxnumsteps < 0) return mdb_fail(c, MDB_ERR_ARG, "mdb_cg: bad argument");
+    QuenchWork w;
+    int rc = quench_setup(c, "mdb_cg", w);
+    if (rc < 0) return rc;
+    const int n = c->n;
+    const double eps = 1.0e-64;
+    cudaStream_t st = c->stream;
+    QuenchScal *S = w.S;
+    auto finish = [&](int code) { c->skip_flag = nullptr; return code; };
+    auto move = [&]() { k_q_move<<<cdiv(n, QT), QT, 0, st>>>(n, w.dir, c->pos, c->box, c->dsr, c->counters, S); c->launches_total += 1; };
+    auto dot = [&](const double *b, const double *bsub, int mode) {
+        k_q_dot<<<w.nblk, QT, 0, st>>>(w.n3, c->fp, b, bsub, w.part, S, mode, maxdis); c->launches_total += 1; };
+    // ---- :50-61
+    if ((rc = mdb_force(c, MDB_FORCE | MDB_EPOT, nullptr)) < 0) return rc;
+    k_sd_save<<<w.nblk, QT, 0, st>>>(0, n, c->fp, w.f0, c->epot, w.epot0, S);
+    k_q_cgdir<<<w.nblk, QT, 0, st>>>(w.n3, 1, c->fp, w.f0, w.dir, w.part, S, maxdis, eps, -1);
+    c->launches_total += 2;
+    c->skip_flag = &S->done;
+    if ((rc = quench_peek(c, w)) < 0) return finish(rc);
+    const bool ls = (meth & MDB_QUENCH_LSEARCH) != 0;
+    // the tail of an iteration, :80-105 / :235-260: energy criterion, then the new direction
+    auto tail = [&](int it) -> int {
+        int r;
+        if ((r = mdb_force(c, MDB_EPOT, nullptr)) < 0) return r;
+        k_sd_echeck<<<w.nblk, QT, 0, st>>>(n, minepot, c->epot, w.epot0, w.part, S, it);
+        k_sd_save<<<w.nblk, QT, 0, st>>>(0, n, c->fp, w.f0, c->epot, w.epot0, S);
+        c->launches_total += 2;
+        if ((r = mdb_force(c, MDB_FORCE, nullptr)) < 0) return r;
+        dot(c->fp, w.f0, QD_MF1);
+        k_q_cgdir<<<w.nblk, QT, 0, st>>>(w.n3, 0, c->fp, w.f0, w.dir, w.part, S, maxdis, eps, it);
+        c->launches_total += 1;
+        return MDB_OK;
+    };
+    int iter = 0;
+    if (!ls) {
+        const int batch = 4;
+        iter = 1;
+        while (!w.H->done && iter <= mxnumsteps) {
+            for (int b = 0; b < batch && iter <= mxnumsteps; b++, iter++) {
+                move();                                                     // trial step :62-64
+                if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return finish(rc);
+                dot(w.dir, nullptr, QD_PF1_CG);                             // PF1 and the secant step :67-75
+                move();                                                     // :76
+                if ((rc = tail(iter)) < 0) return finish(rc);
+            }
+            if ((rc = quench_peek(c, w)) < 0) return finish(rc);
+        }
+    } else {
+        while (!w.H->done && iter <= mxnumsteps) {
+            move();                                                         // :203-205
+            if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return finish(rc);
+            dot(w.dir, nullptr, QD_PF1_CG);                                 // PF1 (+ the step of the first inner pass)
+            iter++;
+            while (iter <= mxnumsteps) {                                    // :211-233
+                move();
+                iter++;
+                if ((rc = quench_peek(c, w)) < 0) return finish(rc);
+                if (fabs(w.H->step) <= mindis) break;
+                if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return finish(rc);
+                dot(w.dir, nullptr, QD_PF1_CG);
+            }
+            if ((rc = tail(iter)) < 0) return finish(rc);
+            if ((rc = quench_peek(c, w)) < 0) return finish(rc);
+        }
+    }
+    if (iflag) *iflag = w.H->done ? w.H->iflag : 0;
+    if (delepot) *delepot = w.H->delepot;
+    return finish(MDB_OK);
+}
+
+// Do_Steepest1_Forsteps_DEV.  MINEPOT is the reference's literal 0.001 eV (:178).
+static int steepest1(mdb_ctx *c, int mxnumsteps, double maxdis, double mindis, int *iflag, double *delepot)
+{
+    QuenchWork w;
+    int rc = quench_setup(c, "mdb_steepest", w);
+    if (rc < 0) return rc;
+    const int n = c->n;
+    const double minepot = 0.001 * 1.60219e-12;
+    cudaStream_t st = c->stream;
+    QuenchScal *S = w.S;
+    int iter = 0;
+    if ((rc = quench_peek(c, w)) < 0) return rc;
+    while (!w.H->done && iter <= mxnumsteps) {
+        if ((rc = mdb_force(c, MDB_FORCE | MDB_EPOT, nullptr)) < 0) return rc;                   // :203-204
+        k_sd_save<<<w.nblk, QT, 0, st>>>(0, n, c->fp, w.f0, c->epot, w.epot0, S);               // EPOT0 :205
+        k_q_dot<<<w.nblk, QT, 0, st>>>(w.n3, c->fp, c->fp, nullptr, w.part, S, QD_NORM, maxdis);
+        k_q_sd1dir<<<w.nblk, QT, 0, st>>>(w.n3, c->fp, w.dir, w.part, S, maxdis);               // :206-212
+        c->launches_total += 3;
+        while (iter <= mxnumsteps) {                                                            // :213-233
+            k_q_move<<<cdiv(n, QT), QT, 0, st>>>(n, w.dir, c->pos, c->box, c->dsr, c->counters, S);
+            if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
+            k_q_dot<<<w.nblk, QT, 0, st>>>(w.n3, c->fp, w.dir, nullptr, w.part, S, QD_PF1_SD, maxdis);
+            c->launches_total += 2;
+            iter++;
+            if ((rc = quench_peek(c, w)) < 0) return rc;
+            if (fabs(w.H->step) <= mindis) break;
+        }
+        if ((rc = mdb_force(c, MDB_EPOT, nullptr)) < 0) return rc;
+        k_sd_echeck<<<w.nblk, QT, 0, st>>>(n, minepot, c->epot, w.epot0, w.part, S, iter);
+        c->launches_total += 1;
+        if ((rc = quench_peek(c, w)) < 0) return rc;
+    }
+    if (iflag) *iflag = w.H->done ? w.H->iflag : 0;
+    if (delepot) *delepot = w.H->delepot;
+    return MDB_OK;
 }

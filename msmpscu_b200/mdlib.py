@@ -288,6 +288,17 @@ def Do_Steepest_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, M
     return fl, mm / b0.RR, de / CP_EVERG
 
 
+def Do_CG_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, MXNUMSTEPS=1000, METH=0):
+    """CommonGPU/MD_CGScheme_GPU.F90:280-296: conjugate-gradient quench (METH & CP_DAMPSCHEME_LSEARCH selects the
+    line-search variant).  Returns (IFLAG, max energy change [eV])."""
+    b0 = SimBox[0] if isinstance(SimBox, (list, tuple)) else SimBox
+    mxstep = getattr(CtrlParam, "STEEPEST_MxStep", 0.1)
+    mistep = getattr(CtrlParam, "STEEPEST_MiStep", 1.0e-5)
+    midele = getattr(CtrlParam, "STEEPEST_MiDelE", 0.001)
+    fl, de = dev.ctx.cg(MXNUMSTEPS, mxstep * b0.RR, mistep * b0.RR, midele * CP_EVERG, METH)
+    return fl, de / CP_EVERG
+
+
 def ResetXP1(dev, SimBox):
     """Appshell/MD_Method_GenericMD_GPU.F90 ResetXP1: velocities are zeroed after a quench."""
     b0 = SimBox[0] if isinstance(SimBox, (list, tuple)) else SimBox

@@ -1113,6 +1113,141 @@ done:
     return iflag;
 }
 
+/* ---- the other quench schemes of the PARREP / GMD "QUICKDAMP" section.
+ * Vector helpers follow MSMLIB/sor/CommonGPU/MSM_MultiGPU_Basic.F90: Minus(V1,V2): V2 = V1 - V2 (:5246-5270),
+ * Multiply(a,V): V = a*V, Add(V1,V2): V2 = V1 + V2, Dot over all 3N components, MaxAbsval. */
+static double vdot(const double *a, const double *b, size_t n) { double s = 0.0; for (size_t i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+static void quench_bounds(const orc_md *m, double lb[3], double hb[3])
+{
+    for (int d = 0; d < 3; d++) {
+        lb[d] = m->ifpd[d] ? m->boxlow[d] : -1.0e108;
+        hb[d] = m->ifpd[d] ? m->boxup[d] : 1.0e108;
+    }
+}
+static double max_depot(const orc_md *m, const double *epot0)
+{
+    double v = 0.0;
+    for (int i = 0; i < m->n; i++) { const double t = fabs(m->epot[i] - epot0[i]); if (t > v) v = t; }
+    return v;
+}
+/* Do_CG0_Forsteps_DEV (lsearch = 0, CommonGPU/MD_CGScheme_GPU.F90:16-133) and Do_CG1_Forsteps_DEV (lsearch = 1, :137-276):
+ * Polak-Ribiere conjugate gradient; the step along a direction comes from one secant estimate (CG0) or from repeated
+ * secant estimates until |STEPSIZE| <= MINDIS (CG1).  Returns the reference's ITER at exit if a stop criterion fired
+ * (DELEPOT <= MINEPOT or F0NORM <= EPS), 0 if the step budget ran out, -1 if F0NORM <= EPS before the first step.
+ * Restated as written, including its mixed units: the secant STEPSIZE (a coefficient on the un-normalised direction)
+ * is compared with MAXDIS (a length) and then divided by sqrt(F0NORM) a second time, so in CGS units the cap nearly
+ * always binds and the second move of CG0 is +/- the trial move (a backward one returns the atoms to where they were,
+ * DELEPOT becomes ~0 and the loop ends). */
+int orc_md_cg(orc_md *m, int mxnumsteps, int lsearch, double maxdis, double mindis, double minepot, double *delepot_out)
+{
+    const int n = m->n;
+    const size_t n3 = (size_t)n * 3;
+    const double eps = 1.0e-64;
+    double *dir = (double *)malloc(sizeof(double) * n3), *f0 = (double *)malloc(sizeof(double) * n3);
+    double *dxp = (double *)malloc(sizeof(double) * n3), *epot0 = (double *)malloc(sizeof(double) * n);
+    double lb[3], hb[3], delepot = 0.0, f0norm, pf0, pf1, stepsize;
+    int iflag = 0, iter;
+    quench_bounds(m, lb, hb);
+    orc_md_force(m, 0);
+    orc_md_epot(m);
+    memcpy(epot0, m->epot, sizeof(double) * n);
+    memcpy(dir, m->fp, sizeof(double) * n3);
+    memcpy(f0, m->fp, sizeof(double) * n3);
+    f0norm = vdot(f0, f0, n3);
+    pf0 = vdot(m->fp, dir, n3);
+    if (f0norm <= eps) { iflag = -1; goto done; }
+    iter = lsearch ? 0 : 1;
+    while (iter <= mxnumsteps) {
+        stepsize = maxdis / sqrt(f0norm);
+        for (size_t i = 0; i < n3; i++) dxp[i] = stepsize * dir[i];
+        add_shift(n, lb, hb, dxp, m->xp);
+        orc_md_force(m, 0);
+        pf1 = vdot(m->fp, dir, n3);
+        if (!lsearch) {
+            stepsize = -stepsize * pf1 / (pf1 - pf0);
+            if (fabs(stepsize) > maxdis) stepsize = maxdis * fabs(stepsize) / stepsize;
+            { const double c = stepsize / sqrt(f0norm); for (size_t i = 0; i < n3; i++) dxp[i] = c * dir[i]; }
+            add_shift(n, lb, hb, dxp, m->xp);
+        } else {
+            iter++;
+            while (iter <= mxnumsteps) {
+                stepsize = -stepsize * pf1 / (pf1 - pf0);
+                if (fabs(stepsize) > maxdis) stepsize = maxdis * fabs(stepsize) / stepsize;
+                { const double c = stepsize / sqrt(f0norm); for (size_t i = 0; i < n3; i++) dxp[i] = c * dir[i]; }
+                add_shift(n, lb, hb, dxp, m->xp);
+                iter++;
+                if (fabs(stepsize) <= mindis) break;
+                pf0 = pf1;
+                orc_md_force(m, 0);
+                pf1 = vdot(m->fp, dir, n3);
+            }
+        }
+        orc_md_epot(m);
+        delepot = max_depot(m, epot0);
+        if (delepot <= minepot) { iflag = iter; break; }
+        memcpy(epot0, m->epot, sizeof(double) * n);
+        orc_md_force(m, 0);
+        for (size_t i = 0; i < n3; i++) f0[i] = m->fp[i] - f0[i];
+        {
+            const double mf1norm = vdot(m->fp, f0, n3), gama = mf1norm / f0norm;
+            for (size_t i = 0; i < n3; i++) dir[i] = gama * dir[i];
+            for (size_t i = 0; i < n3; i++) dir[i] = m->fp[i] + dir[i];
+        }
+        memcpy(f0, m->fp, sizeof(double) * n3);
+        f0norm = vdot(f0, f0, n3);
+        pf0 = vdot(m->fp, dir, n3);
+        if (f0norm <= eps) { iflag = iter; break; }
+        if (!lsearch) iter++;
+    }
+done:
+    if (delepot_out) *delepot_out = delepot;
+    free(dir); free(f0); free(dxp); free(epot0);
+    return iflag;
+}
+/* Do_Steepest1_Forsteps_DEV (CommonGPU/MD_SteepestScheme_GPU.F90:157-260): steepest descent along the normalised force
+ * with the same repeated-secant line search; MINEPOT is the literal 0.001 eV of :178.  Returns ITER at exit when the
+ * energy criterion fired, 0 when the step budget ran out. */
+int orc_md_steepest1(orc_md *m, int mxnumsteps, double maxdis, double mindis, double *delepot_out)
+{
+    const int n = m->n;
+    const size_t n3 = (size_t)n * 3;
+    const double minepot = 0.001 * 1.60219e-12;
+    double *dir = (double *)malloc(sizeof(double) * n3), *dxp = (double *)malloc(sizeof(double) * n3);
+    double *epot0 = (double *)malloc(sizeof(double) * n);
+    double lb[3], hb[3], delepot = 0.0, pf0, pf1, stepsize;
+    int iter = 0, iflag = 0;
+    quench_bounds(m, lb, hb);
+    while (iter <= mxnumsteps) {
+        orc_md_force(m, 0);
+        orc_md_epot(m);
+        memcpy(epot0, m->epot, sizeof(double) * n);
+        { /* DevNormalize: V = (1/dsqrt(V.V)) * V (CommonGPU/MD_Globle_Variables_GPU.F90:2775-2790) */
+            const double sc = 1.0 / sqrt(vdot(m->fp, m->fp, n3));
+            for (size_t i = 0; i < n3; i++) dir[i] = sc * m->fp[i];
+        }
+        stepsize = maxdis;
+        for (size_t i = 0; i < n3; i++) dxp[i] = stepsize * dir[i];
+        pf0 = vdot(m->fp, dir, n3);
+        while (iter <= mxnumsteps) {
+            add_shift(n, lb, hb, dxp, m->xp);
+            orc_md_force(m, 0);
+            pf1 = vdot(m->fp, dir, n3);
+            stepsize = -stepsize * pf1 / (pf1 - pf0);
+            if (fabs(stepsize) > maxdis) stepsize = maxdis * fabs(stepsize) / stepsize;
+            for (size_t i = 0; i < n3; i++) dxp[i] = stepsize * dir[i];
+            iter++;
+            if (fabs(stepsize) <= mindis) break;
+            pf0 = pf1;
+        }
+        orc_md_epot(m);
+        delepot = max_depot(m, epot0);
+        if (delepot <= minepot) { iflag = iter; break; }
+    }
+    if (delepot_out) *delepot_out = delepot;
+    free(dir); free(dxp); free(epot0);
+    return iflag;
+}
+
 /* ------------------------------------------------------------------------------------
  * Remaining procedures of the integrator module the step loop calls (MD_DiffScheme_GPU.F90):
  * Cal_GlobalT_DEV :1042-1064, CheckTimestep_KERNEL/_DEV :1066-1258, VelScaling_KERNEL/_DEV :1262-1446.

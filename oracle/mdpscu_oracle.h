@@ -165,6 +165,10 @@ void  orc_md_get(orc_md *m, double *xp, double *xp1, double *fp, double *epot, d
  * minepot in erg; returns IFLAG (0 not converged, >0 iteration of convergence, -1 converged at the first step) */
 int   orc_md_steepest0(orc_md *m, int mxnumsteps, double alpha0, double maxdis, double mindis, double minepot,
                        double *maxmove_out, double *delepot_out);
+/* Do_CG0/CG1_Forsteps_DEV (CommonGPU/MD_CGScheme_GPU.F90:16-276) and Do_Steepest1_Forsteps_DEV
+ * (CommonGPU/MD_SteepestScheme_GPU.F90:157-260); return values as documented at the definitions */
+int   orc_md_cg(orc_md *m, int mxnumsteps, int lsearch, double maxdis, double mindis, double minepot, double *delepot_out);
+int   orc_md_steepest1(orc_md *m, int mxnumsteps, double maxdis, double mindis, double *delepot_out);
 /* Cal_GlobalT_DEV :1042-1064, VelScaling_DEV :1262-1446, CheckTimestep_DEV :1066-1258 (MD_DiffScheme_GPU.F90) */
 double orc_md_global_t(orc_md *m);
 int   orc_md_vel_scaling(orc_md *m, double dt);          /* -1: a box with zero kinetic energy (the reference stops) */

@@ -358,6 +358,37 @@ def test_steepest_quench_tracks_oracle(oracle, path):
         ctx.close()
 
 
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("scheme", ["cg0", "cg1", "sd1"])
+def test_cg_and_linesearch_quench_track_oracle(oracle, path, scheme):
+    """Do_CG0/CG1_Forsteps_DEV (CommonGPU/MD_CGScheme_GPU.F90:16-276) and Do_Steepest1_Forsteps_DEV
+    (MD_SteepestScheme_GPU.F90:157-260) with device-resident scalars against the CPU restatements: same exit iteration
+    (one run that converges, one that runs out of steps) and the same final configuration."""
+    c = util.bcc_case((8, 8, 8), seed=5, temp=0.0, disp=0.04)
+    rr = c.rr
+    for mx, mistep, midele in ((80, 1.0e-5, 1.0e-3), (9, 1.0e-9, 1.0e-12)):
+        md = util.oracle_md(oracle, c)
+        md.rebuild()
+        ctx = util.make_ctx(c, force_path=PATHS[path])
+        ctx.force(capi.FORCE)
+        f0 = np.abs(ctx.download(capi.F_FP)).max()
+        if scheme == "sd1":
+            fl_o, de_o = md.steepest1(mx, 0.1 * rr, mistep * rr)
+            fl, _, de = ctx.steepest(mx, 0.1, 0.1 * rr, mistep * rr, midele * util.CP_EVERG, meth=capi.QUENCH_LSEARCH)
+        else:
+            ls = 1 if scheme == "cg1" else 0
+            fl_o, de_o = md.cg(mx, ls, 0.1 * rr, mistep * rr, midele * util.CP_EVERG)
+            fl, de = ctx.cg(mx, 0.1 * rr, mistep * rr, midele * util.CP_EVERG, meth=capi.QUENCH_LSEARCH if ls else 0)
+        assert fl == fl_o, (scheme, mx, fl, fl_o)
+        assert util.relerr(ctx.download(capi.F_XP), md.get()["xp"]) < 1e-10
+        # per-atom energies are ~1e-11 erg: differences below 1e-22 erg are last-bit noise (CG0's clamped secant step can
+        # return an atom exactly to where it started, see the oracle's header comment)
+        assert abs(de - de_o) <= 1e-6 * abs(de_o) + 1e-22
+        ctx.force(capi.FORCE)
+        assert np.abs(ctx.download(capi.F_FP)).max() < 0.5 * f0   # it did relax
+        ctx.close()
+
+
 def test_steepest_quench_of_the_reference_example():
     """examples/NEB_Test (2000 W + 1 H, Bonny EAM1): the reference's own run quenches this configuration for 1000
     steps; its printed cohesive energy stays -8.89488 eV/atom (GMD/thermP0000_0001) while max|F| drops from 0.39 to
