@@ -148,6 +148,13 @@ module MDB_C_BINDING
        integer(c_int)        :: iflag
        real(c_double)        :: maxmove, delepot
      end function
+     integer(c_int) function mdb_thermalize(ctx, ti, seed, draw) bind(C, name="mdb_thermalize")
+       import :: c_int, c_ptr, c_double, c_long_long
+       type(c_ptr), value          :: ctx
+       real(c_double), value       :: ti
+       integer(c_long_long), value :: seed
+       integer(c_int), value       :: draw
+     end function
      integer(c_int) function mdb_cg(ctx, mxnumsteps, meth, maxdis, mindis, minepot, iflag, delepot) bind(C, name="mdb_cg")
        import :: c_int, c_ptr, c_double
        type(c_ptr), value    :: ctx

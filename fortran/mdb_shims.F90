@@ -110,6 +110,14 @@ contains
          stop
       end if
   end subroutine
+  subroutine Thermalizing_MC_DEV(SimBox, CtrlParam, TI)                                           ! :1746-1805
+    type(SimMDBox), dimension(:)::SimBox
+    type(SimMDCtrl)             ::CtrlParam
+    real(KINDDF)                ::TI
+    integer, save               ::DRAW = 0
+      if(mdb_thermalize(m_CTX, TI, int(CtrlParam%SEED(1), c_long_long), DRAW) .lt. 0) stop "MDPSCU Error: mdb_thermalize failed"
+      DRAW = DRAW + 1
+  end subroutine
   subroutine CheckTimestep_DEV(ITIME, SimBox, CtrlParam, TH, H2S2, DMX2, IFLAG)                   ! :1214-1258
     integer,         intent(in)::ITIME
     type(SimMDBox),  intent(in)::SimBox

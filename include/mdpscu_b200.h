@@ -219,6 +219,21 @@ int mdb_check_timestep(mdb_ctx *ctx, double th, double h2s2, double dmx2, int *i
 int mdb_steepest(mdb_ctx *ctx, int mxnumsteps, int meth, double alpha, double maxdis, double mindis, double minepot,
                  int *iflag, double *maxmove, double *delepot);
 
+/* ------------------------------------------------------------------------------------
+ * Thermalisation.  Thermalizing_MC_DEV(SimBox, CtrlParam, TI), CommonGPU/MD_DiffScheme_GPU.F90:1746-1805
+ * (kernel :1608-1672): every free velocity component of an ACTIVE atom is redrawn from the Maxwell distribution at TI
+ * (V0*sqrt(-ln Z1)*cos(2 pi Z2)), inactive atoms get zero, then the mass-weighted mean velocity of each box is removed
+ * from all its atoms -- on the device here, on the host in the reference (:1782-1802).
+ * Random source: the reference uses per-thread cuRAND XORWOW states (Initialize_Rand_DEVICES, MSMLIB/sor/CommonGPU/
+ * MSM_MultiGPU_Basic.F90:661-750), so its numbers depend on launch geometry, device count and cell order.  Here Z is a
+ * pure function of (seed, draw, ORIGINAL atom id, component) through Philox4x32-10: the same call gives the same
+ * velocities on any number of GPUs and in any sort order.  `draw` numbers the calls (the shim increments it).
+ * mdb_thermalize_bits / mdb_philox4x32_10 expose the integers for known-answer tests (host code, no device needed).
+ * ---------------------------------------------------------------------------------- */
+int mdb_thermalize(mdb_ctx *ctx, double ti, unsigned long long seed, unsigned draw);
+int mdb_thermalize_bits(unsigned long long seed, unsigned draw, unsigned orig_id, unsigned *out8);
+int mdb_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned out[4]);
+
 /* Do_CG_Forsteps_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, METH), CommonGPU/MD_CGScheme_GPU.F90:280-296:
  * Polak-Ribiere conjugate gradient on the current list; meth without MDB_QUENCH_LSEARCH -> Do_CG0_Forsteps_DEV (:16-133,
  * one secant step per direction; scalars and stop flag device-resident, host looks once per 4 iterations), with it ->

@@ -65,6 +65,9 @@ SYMBOLS = {
     "mdb_vel_scaling": (C.c_int, [C.c_void_p, C.c_double]),
     "mdb_check_timestep": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip]),
     "mdb_steepest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_ip, c_dp, c_dp]),
+    "mdb_thermalize": (C.c_int, [C.c_void_p, C.c_double, C.c_ulonglong, C.c_uint]),
+    "mdb_thermalize_bits": (C.c_int, [C.c_ulonglong, C.c_uint, C.c_uint, C.POINTER(C.c_uint)]),
+    "mdb_philox4x32_10": (C.c_int, [C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "mdb_cg": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, c_ip, c_dp]),
     "mdb_dd_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdb_dd_info": (C.c_int, [C.c_void_p, c_ip]),
@@ -296,6 +299,10 @@ class Context:
         self._chk(self.lib.mdb_steepest(self.h, int(mxnumsteps), int(meth), float(alpha), float(maxdis), float(mindis),
                                         float(minepot), C.byref(fl), C.byref(mm), C.byref(de)))
         return fl.value, mm.value, de.value
+
+    def thermalize(self, ti, seed, draw=0):
+        """Thermalizing_MC_DEV: Maxwell velocities at ti [K] + per-box momentum removal (Philox4x32-10 keyed by seed/draw/atom id)."""
+        self._chk(self.lib.mdb_thermalize(self.h, float(ti), int(seed), int(draw)))
 
     def cg(self, mxnumsteps, maxdis, mindis, minepot, meth=0):
         """Do_CG_Forsteps_DEV on the current list (meth & QUENCH_LSEARCH: the line-search variant); returns (IFLAG, DELEPOT [erg])."""

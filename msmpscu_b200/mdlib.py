@@ -288,6 +288,17 @@ def Do_Steepest_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, M
     return fl, mm / b0.RR, de / CP_EVERG
 
 
+_thermalize_draw = [0]
+
+
+def Thermalizing_MC_DEV(dev, SimBox, CtrlParam, TI):
+    """CommonGPU/MD_DiffScheme_GPU.F90:1746-1805.  The seed is CtrlParam.SEED[0] (the reference seeds its device
+    generators from the same control value); every call uses a new draw number."""
+    seed = int(getattr(CtrlParam, "SEED", [43434])[0]) & 0xFFFFFFFFFFFFFFFF
+    dev.ctx.thermalize(TI, seed, _thermalize_draw[0])
+    _thermalize_draw[0] += 1
+
+
 def Do_CG_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, MXNUMSTEPS=1000, METH=0):
     """CommonGPU/MD_CGScheme_GPU.F90:280-296: conjugate-gradient quench (METH & CP_DAMPSCHEME_LSEARCH selects the
     line-search variant).  Returns (IFLAG, max energy change [eV])."""

@@ -1317,3 +1317,60 @@ int orc_md_natom(orc_md *m) { return m->n; }
 const int *orc_md_kvois(orc_md *m) { return m->kvois; }
 const int *orc_md_indi(orc_md *m) { return m->indi; }
 void orc_md_ncell(orc_md *m, int ncell[3]) { for (int d = 0; d < 3; d++) ncell[d] = m->ncell[d]; }
+
+
+/* ------------------------------------------------------------------------------------
+ * Thermalizing_MC_KERNEL / Thermalizing_MC_DEV, CommonGPU/MD_DiffScheme_GPU.F90:1608-1805, with the product's
+ * documented substitution of the random source: uniforms from Philox4x32-10 (Salmon et al., SC'11) keyed by the
+ * seed, counter = (original 1-based atom id, draw, block 0|1, 0), Z = (x + 1/2) 2^-32.  Everything after the
+ * uniforms is the reference's arithmetic: V0*DSQRT(-DLOG(Z1))*DCOS(CP_TWOPI*Z2), zero for inactive atoms,
+ * then per box WT = sum m, VT = sum m*v/WT over the box in original order, v -= VT for every atom. */
+void orc_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned out[4])
+{
+    unsigned c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+void orc_md_thermalize(orc_md *m, double ti, unsigned long long seed, unsigned draw)
+{
+    const int n = m->n, napb = m->napb;
+    const unsigned key[2] = {(unsigned)seed, (unsigned)(seed >> 32)};
+    for (int s = 0; s < n; s++) {
+        const int st = m->statu[s];
+        if ((st & ORC_STATU_ACTIVE) != ORC_STATU_ACTIVE) {
+            for (int d = 0; d < 3; d++) m->xp1[s + (size_t)d * n] = 0.0;
+            continue;
+        }
+        unsigned z[8];
+        const unsigned c0[4] = {(unsigned)m->gid[s], draw, 0u, 0u}, c1[4] = {(unsigned)m->gid[s], draw, 1u, 0u};
+        orc_philox4x32_10(c0, key, z);
+        orc_philox4x32_10(c1, key, z + 4);
+        const double v0 = sqrt(2.0 * ti * ORC_KB / m->cm[m->ityp[s] - 1]);
+        for (int d = 0; d < 3; d++) {
+            if ((st & (ORC_STATU_FIXVELX << d)) == 0 && (st & (ORC_STATU_FIXPOSX << d)) == 0) {
+                const double z1 = ((double)z[2 * d] + 0.5) * 2.3283064365386963e-10, z2 = ((double)z[2 * d + 1] + 0.5) * 2.3283064365386963e-10;
+                m->xp1[s + (size_t)d * n] = v0 * sqrt(-log(z1)) * cos(6.283185307179586 * z2);
+            }
+        }
+    }
+    int *pos_of = (int *)malloc(sizeof(int) * n);
+    for (int s = 0; s < n; s++) pos_of[m->gid[s] - 1] = s;
+    for (int b = 0; b < m->nbox; b++) { /* :1782-1798 */
+        double wt = 0.0, vt[3] = {0.0, 0.0, 0.0};
+        for (int o = 0; o < napb; o++) wt += m->cm[m->ityp[pos_of[b * napb + o]] - 1];
+        for (int o = 0; o < napb; o++) {
+            const int s = pos_of[b * napb + o];
+            for (int d = 0; d < 3; d++) vt[d] += m->cm[m->ityp[s] - 1] * m->xp1[s + (size_t)d * n] / wt;
+        }
+        for (int o = 0; o < napb; o++) {
+            const int s = pos_of[b * napb + o];
+            for (int d = 0; d < 3; d++) m->xp1[s + (size_t)d * n] -= vt[d];
+        }
+    }
+    free(pos_of);
+}

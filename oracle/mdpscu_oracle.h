@@ -170,6 +170,9 @@ int   orc_md_steepest0(orc_md *m, int mxnumsteps, double alpha0, double maxdis, 
 int   orc_md_cg(orc_md *m, int mxnumsteps, int lsearch, double maxdis, double mindis, double minepot, double *delepot_out);
 int   orc_md_steepest1(orc_md *m, int mxnumsteps, double maxdis, double mindis, double *delepot_out);
 /* Cal_GlobalT_DEV :1042-1064, VelScaling_DEV :1262-1446, CheckTimestep_DEV :1066-1258 (MD_DiffScheme_GPU.F90) */
+/* Thermalizing_MC_DEV :1608-1805 with Philox4x32-10 uniforms (see the definition) */
+void  orc_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned out[4]);
+void  orc_md_thermalize(orc_md *m, double ti, unsigned long long seed, unsigned draw);
 double orc_md_global_t(orc_md *m);
 int   orc_md_vel_scaling(orc_md *m, double dt);          /* -1: a box with zero kinetic energy (the reference stops) */
 int   orc_md_check_timestep(orc_md *m, double th, double h2s2, double mxd2);

@@ -77,3 +77,24 @@ def test_table_grid_definition():
 def test_unknown_potential_id_is_an_error_code():
     with pytest.raises(capi.MDBError):
         forcetable.Create_Interaction_ForceTable(capi.LIB_MARINICA_EAM2, [[7]], 100, 100, 6e-8)
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 (the generator behind mdb_thermalize): Random123's published known-answer vectors, through the
+    product's host entry point and through the oracle."""
+    import ctypes as C
+    from msmpscu_b200 import capi
+    from oracle import pyorc
+    lib = capi.load()
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        out = (C.c_uint * 4)()
+        assert lib.mdb_philox4x32_10((C.c_uint * 4)(*ctr), (C.c_uint * 2)(*key), out) == 0
+        assert tuple(out) == want
+        assert tuple(pyorc.philox4x32_10(ctr, key)) == want
+    bits = (C.c_uint * 8)()
+    assert lib.mdb_thermalize_bits(0x1234ABCD5678, 3, 42, bits) == 0
+    assert list(bits[:4]) == pyorc.philox4x32_10((42, 3, 0, 0), (0xABCD5678, 0x1234))
+    assert list(bits[4:]) == pyorc.philox4x32_10((42, 3, 1, 0), (0xABCD5678, 0x1234))

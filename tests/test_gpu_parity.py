@@ -440,3 +440,44 @@ def test_temperature_scaling_and_timestep_check_match_oracle(oracle):
     v = ctx.download(capi.F_XP1)
     assert np.all(v[3] == 0.0) and v[10, 1] == 0.0 and v[10, 0] != 0.0
     ctx.close()
+
+
+def test_thermalizing_mc_matches_oracle_and_maxwell(oracle):
+    """Thermalizing_MC_DEV (MD_DiffScheme_GPU.F90:1608-1805) with Philox4x32-10 uniforms keyed by the
+    ORIGINAL atom id.  (i) velocities equal the CPU restatement's (same integers; log/cos differ by ulps),
+    (ii) fixed / inactive atoms are treated as in the reference, (iii) per-box momentum is zero, (iv) the result does
+    not depend on the sort order (thermalise before and after a list build), (v) Maxwell statistics at TI."""
+    c = util.bcc_case((10, 10, 10), seed=3, temp=0.0, nbox=2)
+    c.statu = c.statu.copy()
+    c.statu[5] |= 16            # FIXVELX
+    c.statu[7] |= 2 | 4 | 8     # FIXPOS xyz
+    c.statu[11] = 0             # inactive
+    ti, seed = 450.0, 0x1234ABCD5678
+    md = util.oracle_md(oracle, c)
+    md.rebuild()
+    md.thermalize(ti, seed, 3)
+    ref = md.get()["xp1"]
+    ctx = util.make_ctx(c)                       # list built: cell order
+    ctx.thermalize(ti, seed, 3)
+    v = ctx.download(capi.F_XP1)
+    assert util.relerr(v, ref) < 1e-12
+    ctx2 = util.make_ctx(c, build=False)         # no sort yet: ORIGINAL order on the device
+    ctx2.thermalize(ti, seed, 3)
+    assert util.relerr(ctx2.download(capi.F_XP1), v) < 1e-15
+    ctx2.thermalize(ti, seed, 4)                 # another draw: different numbers
+    assert util.relerr(ctx2.download(capi.F_XP1), v) > 0.1
+    ctx2.close()
+    napb = c.napb
+    for b in range(2):
+        vb = v[b * napb:(b + 1) * napb]
+        assert np.abs(vb.mean(axis=0)).max() < 1e-12 * np.abs(vb).max()      # one species: plain mean
+    free = np.ones(len(v), bool); free[[5, 7, 11]] = False
+    # not redrawn (inactive -> 0; fixed -> kept, 0 here): these hold exactly minus the removed box velocity
+    assert np.array_equal(v[11], v[7]) and v[5, 0] == v[11, 0] and v[5, 1] != v[11, 1]
+    assert 0 < np.abs(v[11]).max() < 0.1 * np.abs(v).max()
+    m = c.mass[0]
+    t_kin = m * (v[free] ** 2).sum() / (3.0 * free.sum() * 1.38054e-16)
+    assert abs(t_kin - ti) < 0.03 * ti                                        # 4000 atoms: sigma ~ 1 %
+    s = v[free] / np.sqrt(1.38054e-16 * ti / m)
+    assert abs(s.std() - 1.0) < 0.03 and abs((s ** 4).mean() - 3.0) < 0.3     # Gaussian components
+    ctx.close()
