@@ -148,6 +148,16 @@ module MDB_C_BINDING
        integer(c_int)        :: iflag
        real(c_double)        :: maxmove, delepot
      end function
+     integer(c_int) function mdb_atomic_stress(ctx, d_avp) bind(C, name="mdb_atomic_stress")
+       import :: c_int, c_ptr, c_devptr
+       type(c_ptr), value    :: ctx
+       type(c_devptr), value :: d_avp
+     end function
+     integer(c_int) function mdb_nlist_reorder_nearest(ctx, nearest) bind(C, name="mdb_nlist_reorder_nearest")
+       import :: c_int, c_ptr
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: nearest
+     end function
      integer(c_int) function mdb_thermalize(ctx, ti, seed, draw) bind(C, name="mdb_thermalize")
        import :: c_int, c_ptr, c_double, c_long_long
        type(c_ptr), value          :: ctx

@@ -45,6 +45,11 @@ contains
     real(c_double)::VT(3,3)
       if(mdb_force(m_CTX, MDB_DEN, VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
   end subroutine
+  subroutine Cal_EAM_AtomicStressTensor_DEV(IDEV, dAVP)                                          ! :1973-1990 (pCalAVStress)
+    integer, intent(in)::IDEV
+    real(KINDDF), device, dimension(:,:), intent(out)::dAVP      ! the caller's device array, untouched CUDA-Fortran analysis code
+      if(mdb_atomic_stress(m_CTX, c_devloc(dAVP)) .lt. 0) stop "MDPSCU Error: mdb_atomic_stress failed"
+  end subroutine
   subroutine Clear_EAM_Force_Table_DEV()                                                         ! :343-365
     integer(c_int)::ERR
       ERR = mdb_tables_clear(m_CTX)
@@ -69,6 +74,13 @@ contains
       NOUT = mdb_nlist_build(m_CTX)
       if(NOUT .lt. 0) stop "MDPSCU Error: mdb_nlist_build failed"
       if(NOUT .gt. 0) write(*,fmt="(A, I8, A)") " MDPSCU Warning: there are ",NOUT," atoms out of box found in MD_NeighborsList."
+  end subroutine
+  subroutine Reorder_NeighBoreList_Nearest_Dev(Nearest)                                          ! :2016-2066
+    integer::Nearest
+      if(mdb_nlist_reorder_nearest(m_CTX, Nearest) .lt. 0) then
+         write(*,*) "MDPSCU Error: the number of required neighbors (NEAREST) in Reorder_NeighBoreList_Nearest_DEV is larger than the permitted value"
+         stop
+      end if
   end subroutine
 end module MD_NeighborsList_GPU
 

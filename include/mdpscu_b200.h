@@ -134,6 +134,10 @@ int mdb_nlist_init(mdb_ctx *ctx, const double *nb_rm, int mxkvois);
 int mdb_nlist_build(mdb_ctx *ctx);
 int mdb_nlist_copyout(mdb_ctx *ctx, int *kvois, int *indi, int order);
 int mdb_nlist_cellinfo(const mdb_ctx *ctx, int ncell[3], int *nc_total, int *mxnac);
+/* Reorder_NeighBoreList_Nearest_Dev(Nearest), MD_NeighborsList_GPU.F90:2016-2066 (kernel :1805-1946): in place, every atom
+ * keeps its `nearest` closest listed neighbours in order of increasing distance (1..512 = mp_MXNEAREST).  As in the
+ * reference the force procedures then see the truncated list until the next mdb_nlist_build. */
+int mdb_nlist_reorder_nearest(mdb_ctx *ctx, int nearest);
 int mdb_nlist_overflow(mdb_ctx *ctx);
 int mdb_nlist_clear(mdb_ctx *ctx);
 
@@ -218,6 +222,14 @@ int mdb_check_timestep(mdb_ctx *ctx, double th, double h2s2, double dmx2, int *i
 #define MDB_QUENCH_LSEARCH 65536 /* CP_DAMPSCHEME_LSEARCH, Common/MD_Const.F90:27 */
 int mdb_steepest(mdb_ctx *ctx, int mxnumsteps, int meth, double alpha, double maxdis, double mindis, double minepot,
                  int *iflag, double *maxmove, double *delepot);
+
+/* pCalAVStress(IDEV, dAVP) -> Cal_EAM_AtomicStressTensor_DEV, CommonGPU/MD_EAM_ForceTable_GPU.F90:1973-1990 (kernel
+ * :1775-1925; FS twin in MD_FS_ForceTable_GPU.F90): per-atom virial tensor AP(N,9) = sum_j DXYZ_a*DXYZ_b*FORTOT in the
+ * order 11,12,13,21,..,33, column-major, CELL order, written to the caller's DEVICE array like the reference's dAVP.
+ * The density pass is run first (the reference relies on the DEN of the last force call).  _host: the same into a
+ * host array in the requested order. */
+int mdb_atomic_stress(mdb_ctx *ctx, double *d_avp);
+int mdb_atomic_stress_host(mdb_ctx *ctx, double *h_avp, int order);
 
 /* ------------------------------------------------------------------------------------
  * Thermalisation.  Thermalizing_MC_DEV(SimBox, CtrlParam, TI), CommonGPU/MD_DiffScheme_GPU.F90:1746-1805

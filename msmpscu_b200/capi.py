@@ -65,6 +65,9 @@ SYMBOLS = {
     "mdb_vel_scaling": (C.c_int, [C.c_void_p, C.c_double]),
     "mdb_check_timestep": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip]),
     "mdb_steepest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_ip, c_dp, c_dp]),
+    "mdb_nlist_reorder_nearest": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdb_atomic_stress": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdb_atomic_stress_host": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
     "mdb_thermalize": (C.c_int, [C.c_void_p, C.c_double, C.c_ulonglong, C.c_uint]),
     "mdb_thermalize_bits": (C.c_int, [C.c_ulonglong, C.c_uint, C.c_uint, C.POINTER(C.c_uint)]),
     "mdb_philox4x32_10": (C.c_int, [C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
@@ -299,6 +302,16 @@ class Context:
         self._chk(self.lib.mdb_steepest(self.h, int(mxnumsteps), int(meth), float(alpha), float(maxdis), float(mindis),
                                         float(minepot), C.byref(fl), C.byref(mm), C.byref(de)))
         return fl.value, mm.value, de.value
+
+    def nlist_reorder_nearest(self, nearest):
+        """Reorder_NeighBoreList_Nearest_Dev: keep the `nearest` closest neighbours, by increasing distance, in place."""
+        self._chk(self.lib.mdb_nlist_reorder_nearest(self.h, int(nearest)))
+
+    def atomic_stress(self, order=ORDER_ORIGINAL):
+        """pCalAVStress: per-atom virial tensor (n, 9), columns 11,12,13,21,...,33."""
+        ap = np.zeros(9 * self.n)
+        self._chk(self.lib.mdb_atomic_stress_host(self.h, dp(ap), int(order)))
+        return np.ascontiguousarray(ap.reshape(9, self.n).T)
 
     def thermalize(self, ti, seed, draw=0):
         """Thermalizing_MC_DEV: Maxwell velocities at ti [K] + per-box momentum removal (Philox4x32-10 keyed by seed/draw/atom id)."""

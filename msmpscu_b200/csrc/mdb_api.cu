@@ -152,6 +152,7 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_dd) cudaFreeHost(c->h_dd);
     if (c->hstage) cudaFreeHost(c->hstage);
+    if (c->avp) cudaFree(c->avp);
     if (c->q_buf) cudaFree(c->q_buf);
     if (c->q_host) cudaFreeHost(c->q_host);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -453,6 +454,33 @@ extern "C" int mdb_state_download(mdb_ctx *c, int field, void *host, int order)
     return MDB_OK;
 }
 
+// host-side convenience over mdb_atomic_stress: AP(N,9) column-major in the requested order
+extern "C" int mdb_atomic_stress_host(mdb_ctx *c, double *h_avp, int order)
+{
+    if (!c || !h_avp) return mdb_fail(c, MDB_ERR_ARG, "mdb_atomic_stress_host: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_atomic_stress_host: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    const int n = c->n;
+    if (c->avp_n != n) {
+        if (c->avp) cudaFree(c->avp);
+        c->avp = nullptr; c->avp_n = 0;
+        CUDA_TRY(c, cudaMalloc(&c->avp, sizeof(double) * 9 * (size_t)n));
+        c->avp_n = n;
+    }
+    int rc = mdb_atomic_stress(c, c->avp);
+    if (rc < 0) return rc;
+    const size_t bytes = sizeof(double) * 9 * (size_t)n;
+    if ((rc = ensure_stage(c, bytes))) return rc;
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        k_down_d<<<cdiv(n, 256), 256, 0, c->stream>>>(n, 9, c->avp, (double *)c->stage, order == MDB_ORDER_ORIGINAL ? c->gidinv : nullptr);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(h_avp, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MDB_OK;
+}
+
 extern "C" void *mdb_devptr(mdb_ctx *c, int field)
 {
     if (!c || !c->has_box) return nullptr;
@@ -649,6 +677,23 @@ extern "C" int mdb_nlist_build(mdb_ctx *c)
     return c->h_counters[CNT_OOB];
 }
 
+// Reorder_NeighBoreList_Nearest_Dev(Nearest), CommonGPU/MD_NeighborsList_GPU.F90:2016-2066
+extern "C" int mdb_nlist_reorder_nearest(mdb_ctx *c, int nearest)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_nlist || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_nlist_reorder_nearest: no valid list");
+    if (nearest < 1 || nearest > 512) // the reference prints and stops above mp_MXNEAREST = 512 (:2024-2029)
+        return mdb_fail(c, MDB_ERR_ARG, "mdb_nlist_reorder_nearest: NEAREST = %d outside 1..512 (MXNEAREST)", nearest);
+    if (c->mxkvois > 512) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_nlist_reorder_nearest: lists longer than 512 entries");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_nlist_reorder_nearest: not available in slab-decomposed runs yet");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    int rc = mdb_indi_ensure(c);
+    if (rc < 0) return rc;
+    if ((rc = mdb_nlist_nearest(c, nearest)) < 0) return rc;
+    c->list_reordered = true; // forces now follow the truncated list (reference behaviour) until the next rebuild
+    return MDB_OK;
+}
+
 // After a rebuild on the tiled path only the slot lists exist.  The reference-format INDI(N,mxKVOIS) -- same
 // members, reference order -- is produced here, on demand, by the generic list kernel from the positions saved at
 // that rebuild (cells, types and the sort order are frozen between rebuilds).
@@ -679,6 +724,7 @@ int mdb_list_rebuild(mdb_ctx *c)
     int rc = mdb_cells_build(c);
     if (rc < 0) return rc;
     c->indi_stale = false;
+    c->list_reordered = false;
     rc = c->tiled.active ? mdb_tiled_nlist(c) : mdb_nlist_kernel(c);
     if (rc < 0) return rc;
     c->list_valid = true;

@@ -222,6 +222,65 @@ k_epot_generic(ForceParams P, const double4 *__restrict__ pos, const int *__rest
     epot[i] = er0 + den0; // :1633
 }
 
+// ---- per-atom virial tensor: CAL_EAM_AtomicStress_KERNEL, CommonGPU/MD_EAM_ForceTable_GPU.F90:1775-1925 (pCalAVStress).
+// AP(i, 1..9) = sum_j DXYZ_a * DXYZ_b * FORTOT in the order 11,12,13,21,...,33; the FULL pair term goes to atom i (no 1/2).
+__global__ void __launch_bounds__(128)
+k_avstress_generic(ForceParams P, const double4 *__restrict__ pos, const int *__restrict__ ityp, const int *__restrict__ statu,
+                   const int *__restrict__ kvois, const int *__restrict__ indi, double *__restrict__ ap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    double p[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) p[q] = 0.0;
+    if ((statu[i] & ST_ACTIVE) == ST_ACTIVE) {
+        const double4 pi = pos[i];
+        const int ti = ityp[i] - 1, kv = kvois[i];
+        const double denki = pi.w;
+        for (int w = 0; w < kv; w++) {
+            const int j = indi[i + (size_t)w * P.n] - 1;
+            const double4 pj = pos[j];
+            double sx = pi.x - pj.x, sy = pi.y - pj.y, sz = pi.z - pj.z;
+            min_image(sx, P.box.size[0], P.box.half[0], P.box.pd[0]);
+            min_image(sy, P.box.size[1], P.box.half[1], P.box.pd[1]);
+            min_image(sz, P.box.size[2], P.box.half[2], P.box.pd[2]);
+            const double r2 = sx * sx + sy * sy + sz * sz; // identity BOXSHAPE: DXYZ = SEP
+            if (r2 <= P.ru2max) {
+                int k0 = P.kpair[0], k1 = k0;
+                if (P.ng > 1) {
+                    const int tj = ityp[j] - 1;
+                    k0 = P.kpair[ti + P.ng * tj];
+                    k1 = P.kpair[tj + P.ng * ti];
+                }
+                const double r = sqrt(r2);
+                const double sk = sqrt(r) * P.csi;
+                const int kk = (int)sk;
+                const double dk = sk - (double)kk;
+                const double fortot = lerp_tab(P.fpotr, P.ntab + 2, k0, kk, dk) / r2 +
+                                      (lerp_tab(P.fpotb, P.ntab + 2, k0, kk, dk) * denki +
+                                       lerp_tab(P.fpotb, P.ntab + 2, k1, kk, dk) * pj.w) / r; // :1877-1880
+                p[0] = p[0] + sx * sx * fortot; p[1] = p[1] + sx * sy * fortot; p[2] = p[2] + sx * sz * fortot;
+                p[3] = p[3] + sy * sx * fortot; p[4] = p[4] + sy * sy * fortot; p[5] = p[5] + sy * sz * fortot;
+                p[6] = p[6] + sz * sx * fortot; p[7] = p[7] + sz * sy * fortot; p[8] = p[8] + sz * sz * fortot;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++) ap[i + (size_t)q * P.n] = p[q];
+}
+
+static void fill_params(mdb_ctx *c, ForceParams &P);
+int mdb_avstress_generic(mdb_ctx *c, double *d_ap)
+{
+    ForceParams P;
+    fill_params(c, P);
+    P.skip = nullptr;
+    ProfScope ps(c, MDB_K_OTHER);
+    k_avstress_generic<<<cdiv(c->n, 128), 128, 0, c->stream>>>(P, c->pos, c->ityp, c->statu, c->kvois, c->indi, d_ap);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
 static void fill_params(mdb_ctx *c, ForceParams &P)
 {
     const TableSet &t = c->tab;

@@ -115,6 +115,7 @@ struct mdb_ctx {
 
     // ---- cells
     bool has_nlist = false, list_valid = false;
+    bool list_reordered = false; // Reorder_NeighBoreList_Nearest_Dev truncated KVOIS/INDI in place (until the next rebuild)
     double nb_rm[MDB_MXGROUP * MDB_MXGROUP];
     float rm2f[MDB_MXGROUP * MDB_MXGROUP];
     int ncell[3] = {0, 0, 0}, nc0 = 0, nc = 0, mxnac = 0;
@@ -157,6 +158,7 @@ struct mdb_ctx {
     //      kernels of already-converged iterations into no-ops
     double *q_buf = nullptr; int q_n = 0; void *q_host = nullptr;
     const int *skip_flag = nullptr;
+    double *avp = nullptr; int avp_n = 0;                      // atomic stress scratch (mdb_atomic_stress_host)
 
     // ---- virial partials
     double *vpart = nullptr; int vpart_n = 0;
@@ -194,8 +196,10 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 // ---- internal entry points across translation units
 int mdb_cells_build(mdb_ctx *c);             // mdb_cells.cu : bin, sort, permute
 int mdb_nlist_kernel(mdb_ctx *c, const double4 *pos = nullptr); // mdb_nlist.cu : fill KVOIS/INDI (pos: override positions)
+int mdb_nlist_nearest(mdb_ctx *c, int nearest); // mdb_nlist.cu
 int mdb_indi_ensure(mdb_ctx *c);             // mdb_api.cu : materialise INDI after a tiled rebuild
 int mdb_force_generic(mdb_ctx *c, unsigned flags, double *vt); // mdb_force.cu
+int mdb_avstress_generic(mdb_ctx *c, double *d_ap);            // mdb_force.cu
 int mdb_tiled_plan(mdb_ctx *c);               // mdb_force_tiled.cu
 int mdb_tiled_nlist(mdb_ctx *c);
 void mdb_tiled_free(mdb_ctx *c);

@@ -128,3 +128,53 @@ int mdb_nlist_kernel(mdb_ctx *c, const double4 *pos)
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
+
+
+// ---- Reorder_NeighBoreList_Nearest_Dev (CommonGPU/MD_NeighborsList_GPU.F90:2016-2066, kernel :1805-1946): every atom keeps
+// its NEAREST closest listed neighbours, ordered by increasing distance (ties keep list order: strict '<'), in place.
+// One warp per atom: lanes take the entries w = lane, lane+32, ..., the (distance, list position) keys are ranked by counting
+// -- rank = #keys smaller -- which is the stable order the reference's insertion sort produces; no per-thread 512-entry
+// scratch arrays (the reference keeps R2SWAP/NEARSWAP(512) per thread in local memory).
+#define NEAREST_MAXLIST 512 // mp_MXNEAREST :59 (also the largest list the shared staging holds)
+__global__ void __launch_bounds__(128)
+k_nearest_reorder(int n, int mxkvois, int nearest, const double4 *__restrict__ pos, BoxParams box, int *__restrict__ kvois,
+                  int *__restrict__ indi)
+{
+    __shared__ double s_r2[4][NEAREST_MAXLIST];
+    __shared__ int s_j[4][NEAREST_MAXLIST];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + wib;
+    if (i >= n) return;
+    const int kv = min(kvois[i], NEAREST_MAXLIST);
+    const double4 pi = pos[i];
+    for (int w = lane; w < kv; w += 32) {
+        const int j = indi[i + (size_t)w * n];
+        const double4 pj = pos[j - 1];
+        double sx = pi.x - pj.x, sy = pi.y - pj.y, sz = pi.z - pj.z;
+        if (box.pd[0] > 0 && fabs(sx) > box.half[0]) sx = sx - copysign(box.size[0], sx);
+        if (box.pd[1] > 0 && fabs(sy) > box.half[1]) sy = sy - copysign(box.size[1], sy);
+        if (box.pd[2] > 0 && fabs(sz) > box.half[2]) sz = sz - copysign(box.size[2], sz);
+        s_r2[wib][w] = __dadd_rn(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)), __dmul_rn(sz, sz));
+        s_j[wib][w] = j;
+    }
+    __syncwarp();
+    const int nn = min(kv, nearest);
+    for (int w = lane; w < kv; w += 32) {
+        const double r2 = s_r2[wib][w];
+        int rank = 0;
+        for (int k = 0; k < kv; k++) {
+            const double q = s_r2[wib][k];
+            rank += (q < r2 || (q == r2 && k < w)) ? 1 : 0;
+        }
+        if (rank < nn) indi[i + (size_t)rank * n] = s_j[wib][w];
+    }
+    if (lane == 0) kvois[i] = nn;
+}
+
+int mdb_nlist_nearest(mdb_ctx *c, int nearest)
+{
+    ProfScope ps(c, MDB_K_NLIST);
+    k_nearest_reorder<<<cdiv(c->n, 4), 128, 0, c->stream>>>(c->n, c->mxkvois, nearest, c->pos, c->box, c->kvois, c->indi);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}

@@ -384,7 +384,7 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
         return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: slab decomposition needs the tiled path");
     if (c->dd_on && (flags & (MDB_VIRIAL | MDB_EPOT)))
         return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: virial / per-atom energy are not available in slab-decomposed runs yet");
-    if (c->tiled.active) {
+    if (c->tiled.active && !c->list_reordered) {
         // density + force passes on the tiled path; virial / per-atom energy (output steps only)
         // run on the generic kernels over the reference-format list the tiled build also emits
         unsigned fast = flags & (MDB_FORCE | MDB_DEN | MDB_NOPASS1);
@@ -404,6 +404,19 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     return mdb_force_generic(c, flags, vtensor);
 }
 
+// pCalAVStress -> Cal_EAM_AtomicStressTensor_DEV(IDEV, dAVP), CommonGPU/MD_EAM_ForceTable_GPU.F90:1973-1990.
+// The reference uses whatever DEN the last force call left; here the density pass runs first, so the result is the
+// same whenever DEN was current and well defined otherwise.
+extern "C" int mdb_atomic_stress(mdb_ctx *c, double *d_avp)
+{
+    if (!c || !d_avp) return mdb_fail(c, MDB_ERR_ARG, "mdb_atomic_stress: null argument");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_atomic_stress: not available in slab-decomposed runs yet");
+    int rc = mdb_force(c, MDB_DEN, nullptr);
+    if (rc < 0) return rc;
+    if ((rc = mdb_indi_ensure(c)) < 0) return rc;
+    return mdb_avstress_generic(c, d_avp);
+}
+
 // One For_One_Step without host synchronisation.  first / last: position inside an mdb_run block -- between two
 // steps of a block the EPC friction + corrector of step s run fused in front of the predictor of step s+1.
 static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h, bool first, bool last)
@@ -414,7 +427,7 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h, b
     if (nb_uptab > 0 && (itime - it0) % nb_uptab == 0) { // MOD(ITIME-IT0,NB_UPTAB)==0, GenericMD:599-601
         if ((rc = mdb_list_rebuild(c)) < 0) return rc;
     }
-    if (fused_epilogue && c->list_valid) {
+    if (fused_epilogue && c->list_valid && !c->list_reordered) {
         // EPC friction and the corrector are fused into the epilogue of the force pass
         return mdb_force_tiled(c, MDB_FORCE, 3, h * 0.5);
     }

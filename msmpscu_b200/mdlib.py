@@ -265,6 +265,16 @@ def Do_EPCForce_DEV(dev, SimBox, CtrlParam):
     dev.ctx.epc_apply()
 
 
+def Reorder_NeighBoreList_Nearest_Dev(dev, Nearest):
+    """CommonGPU/MD_NeighborsList_GPU.F90:2016-2066: keep the Nearest closest neighbours, ordered by distance."""
+    dev.ctx.nlist_reorder_nearest(Nearest)
+
+
+def Cal_AtomicStressTensor_DEV(dev, order=capi.ORDER_ORIGINAL):
+    """pCalAVStress of the force class (Cal_EAM_AtomicStressTensor_DEV, MD_EAM_ForceTable_GPU.F90:1973-1990): (N, 9)."""
+    return dev.ctx.atomic_stress(order)
+
+
 def For_One_Step(dev, ITIME, SimBox, CtrlParam, ForceClass=gm_ForceClass):
     """One GMD step with the reference's call sequence (each call is one C-ABI entry point)."""
     Predictor_DEV(dev, ITIME, SimBox, CtrlParam)

@@ -696,6 +696,52 @@ void orc_force_pass2(int n, int ia0, int npart, const double *xp, const int *ity
         for (int i = 0; i < 9; i++) vtensor[i] = v[i];
 }
 
+/* CAL_EAM_AtomicStress_KERNEL, CommonGPU/MD_EAM_ForceTable_GPU.F90:1775-1925: AP(NAPDEV,9), column q = 3*(a-1)+b,
+ * the whole pair term to atom i; BOXSHAPE applied to the separation (:1861-1864); DEN as left by pass 1. */
+void orc_force_avstress(int n, int ia0, int npart, const double *xp, const int *ityp, const int *statu,
+                        const int *kvois, const int *indi, int ldindi, const double zl[3], const int ifpd[3],
+                        const double bs[9], const orc_tables *t, const double *den, double *ap, int ldap)
+{
+#pragma omp parallel for schedule(static)
+    for (int ic = 1; ic <= npart; ic++) {
+        double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if ((statu[ic - 1] & ORC_STATU_ACTIVE) == ORC_STATU_ACTIVE) {
+            int gi = ic + ia0 - 1;
+            double px = xp[gi], py = xp[gi + n], pz = xp[gi + 2 * n];
+            int ti = ityp[gi], iiw = kvois[ic - 1];
+            double denki = den[gi];
+            for (int iw = 0; iw < iiw; iw++) {
+                int j = indi[(ic - 1) + (size_t)iw * ldindi] - 1;
+                double s[3] = {px - xp[j], py - xp[j + n], pz - xp[j + 2 * n]};
+                min_image(s, zl, ifpd);
+                double d[3];
+                d[0] = bs[0] * s[0] + bs[3] * s[1] + bs[6] * s[2];
+                d[1] = bs[1] * s[0] + bs[4] * s[1] + bs[7] * s[2];
+                d[2] = bs[2] * s[0] + bs[5] * s[1] + bs[8] * s[2];
+                double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                if (r2 <= t->ru2max) {
+                    int tj = ityp[j];
+                    int k0 = t->kpair[(ti - 1) + t->ng * (tj - 1)];
+                    int k1 = t->kpair[(tj - 1) + t->ng * (ti - 1)];
+                    double r = sqrt(r2);
+                    double sk = sqrt(r) * t->csi;
+                    int kk = (int)sk;
+                    double dk = sk - (double)kk;
+                    double a = tab(t->fpotr, t->nkind, t->ntab, k0, kk);
+                    double b = tab(t->fpotb, t->nkind, t->ntab, k0, kk);
+                    double c = tab(t->fpotb, t->nkind, t->ntab, k1, kk);
+                    double fortot = (a + dk * (tab(t->fpotr, t->nkind, t->ntab, k0, kk + 1) - a)) / r2 +
+                                    ((b + dk * (tab(t->fpotb, t->nkind, t->ntab, k0, kk + 1) - b)) * denki +
+                                     (c + dk * (tab(t->fpotb, t->nkind, t->ntab, k1, kk + 1) - c)) * den[j]) / r;
+                    for (int x = 0; x < 3; x++)
+                        for (int y = 0; y < 3; y++) p[3 * x + y] = p[3 * x + y] + d[x] * d[y] * fortot; /* :1882-1890 */
+                }
+            }
+        }
+        for (int q = 0; q < 9; q++) ap[(ic - 1) + (size_t)q * ldap] = p[q];
+    }
+}
+
 void orc_force_epot(int n, int ia0, int npart, const double *xp, const int *ityp, const int *statu,
                     const int *kvois, const int *indi, int ldindi, const double zl[3], const int ifpd[3],
                     const double bs[9], const orc_tables *t, double *epot)
@@ -990,6 +1036,49 @@ void orc_md_force(orc_md *m, int with_virial)
                     m->fp, n, with_virial ? m->vtensor : NULL);
     if (with_virial) /* COPYOUT_VIRIALTENSOR, MD_EAM_ForceTable_GPU.F90:1462-1463 */
         for (int i = 0; i < 9; i++) m->vtensor[i] = m->vtensor[i] / (double)(m->n / m->napb);
+}
+
+/* pCalAVStress on the driver's state: density pass, then the per-atom tensor; ap[n*9] in ORIGINAL order, column-major */
+void orc_md_avstress(orc_md *m, double *ap)
+{
+    int n = m->n;
+    double *tmp = (double *)malloc(sizeof(double) * 9 * (size_t)n);
+    orc_force_pass1(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->den);
+    orc_force_avstress(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->den, tmp, n);
+    for (int s = 0; s < n; s++)
+        for (int q = 0; q < 9; q++) ap[(m->gid[s] - 1) + (size_t)q * n] = tmp[s + (size_t)q * n];
+    free(tmp);
+}
+
+/* Cal_NearestNeighbor_Kernel, CommonGPU/MD_NeighborsList_GPU.F90:1805-1946: insertion of every listed neighbour into
+ * a distance-ordered buffer of at most NEAREST entries (strict '<': ties keep list order), written back in place. */
+void orc_md_reorder_nearest(orc_md *m, int nearest)
+{
+    const int n = m->n;
+    double *r2s = (double *)malloc(sizeof(double) * (nearest + 1));
+    int *ns = (int *)malloc(sizeof(int) * (nearest + 1));
+    for (int ic = 0; ic < n; ic++) {
+        int nn = 0;
+        for (int k = 0; k <= nearest; k++) r2s[k] = 1.0e32;
+        for (int iw = 0; iw < m->kvois[ic]; iw++) {
+            const int j = m->indi[ic + (size_t)iw * n];
+            double s[3] = {m->xp[ic] - m->xp[j - 1], m->xp[ic + n] - m->xp[j - 1 + n], m->xp[ic + 2 * n] - m->xp[j - 1 + 2 * n]};
+            min_image(s, m->zl, m->ifpd);
+            const double r2 = s[0] * s[0] + s[1] * s[1] + s[2] * s[2];
+            const int n1 = (nn + 1 < nearest) ? nn + 1 : nearest;
+            if (r2 < r2s[n1 - 1]) {
+                int i;
+                for (i = 1; i <= n1; i++) if (r2 < r2s[i - 1]) break;
+                for (int k = n1; k >= i + 1; k--) { r2s[k - 1] = r2s[k - 2]; ns[k - 1] = ns[k - 2]; }
+                r2s[i - 1] = r2; ns[i - 1] = j;
+                nn = nn + 1;
+                if (nn > nearest) nn = nearest;
+            }
+        }
+        m->kvois[ic] = nn;
+        for (int k = 0; k < nn; k++) m->indi[ic + (size_t)k * n] = ns[k];
+    }
+    free(r2s); free(ns);
 }
 
 void orc_md_epot(orc_md *m)

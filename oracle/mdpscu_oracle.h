@@ -125,6 +125,11 @@ void orc_force_pass2(int n, int ia0, int npart, const double *xp, const int *ity
                      const int *kvois, const int *indi, int ldindi,
                      const double zl[3], const int ifpd[3], const double boxshape[9],
                      const orc_tables *t, const double *den, double *fp, int ldfp, double *vtensor);
+/* CAL_EAM_AtomicStress_KERNEL (:1775-1925): AP(.,9), q = 3*(a-1)+(b-1) */
+void orc_force_avstress(int n, int ia0, int npart, const double *xp, const int *ityp, const int *statu,
+                        const int *kvois, const int *indi, int ldindi,
+                        const double zl[3], const int ifpd[3], const double boxshape[9],
+                        const orc_tables *t, const double *den, double *ap, int ldap);
 /* CALEPOT_KERNEL (:1563-1634) */
 void orc_force_epot(int n, int ia0, int npart, const double *xp, const int *ityp, const int *statu,
                     const int *kvois, const int *indi, int ldindi,
@@ -156,7 +161,9 @@ void  orc_md_set_epc(orc_md *m, const int *enable, const double *te, const doubl
                      const double *cut, const double *he);
 int   orc_md_rebuild(orc_md *m);                 /* neighbour list on current positions        */
 void  orc_md_force(orc_md *m, int with_virial);  /* pass1 + pass2 (+virial)                     */
+void  orc_md_reorder_nearest(orc_md *m, int nearest); /* Reorder_NeighBoreList_Nearest_Dev, in place */
 void  orc_md_epot(orc_md *m);
+void  orc_md_avstress(orc_md *m, double *ap);    /* ap[n*9], ORIGINAL order, column-major           */
 int   orc_md_step(orc_md *m, int itime, int it0, int nb_uptab, double h); /* returns 1 if rebuilt */
 /* copy out in ORIGINAL order; any pointer may be NULL */
 void  orc_md_get(orc_md *m, double *xp, double *xp1, double *fp, double *epot, double *ekin,

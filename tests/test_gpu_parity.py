@@ -481,3 +481,51 @@ def test_thermalizing_mc_matches_oracle_and_maxwell(oracle):
     s = v[free] / np.sqrt(1.38054e-16 * ti / m)
     assert abs(s.std() - 1.0) < 0.03 and abs((s ** 4).mean() - 3.0) < 0.3     # Gaussian components
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["bcc_7x9x11", "neb_WH", "fcc_cu_setfl"])
+def test_atomic_stress_parity(oracle, name):
+    """pCalAVStress (CAL_EAM_AtomicStress_KERNEL, MD_EAM_ForceTable_GPU.F90:1775-1925) against the oracle, on both list
+    paths; and the consistency the two reference kernels imply: sum_i AP_i / 2 = VTENSOR * nbox (CALPTENSOR_KERNEL halves
+    each directed pair, :1222, and COPYOUT_VIRIALTENSOR divides by the number of boxes, :1462-1463)."""
+    c = CASES[name]()
+    md = util.oracle_md(oracle, c)
+    md.rebuild()
+    ref = md.avstress()
+    for path in PATHS.values():
+        ctx = util.make_ctx(c, force_path=path)
+        ap = ctx.atomic_stress(capi.ORDER_ORIGINAL)
+        assert ap.shape == ref.shape
+        assert util.relerr(ap, ref) < FORCE_RTOL
+        vt = ctx.force(capi.FORCE | capi.VIRIAL)
+        assert np.allclose(0.5 * ap.sum(axis=0).reshape(3, 3), np.asarray(vt) * c.nbox, rtol=1e-9,
+                           atol=1e-12 * np.abs(ap).sum())
+        ctx.close()
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+@pytest.mark.parametrize("nearest", [14, 8, 300])
+def test_reorder_nearest_bit_exact(oracle, path, nearest):
+    """Reorder_NeighBoreList_Nearest_Dev (MD_NeighborsList_GPU.F90:1805-2066): the NEAREST closest neighbours in order
+    of increasing distance, in place, identical to the restatement of the reference's insertion sort (same entries, same
+    order, ties included); afterwards the force procedures follow the truncated list, as in the reference."""
+    c = util.bcc_case((7, 8, 9), seed=21)
+    md = util.oracle_md(oracle, c)
+    md.rebuild()
+    md.reorder_nearest(nearest)
+    kv_o, ind_o = md.nlist()
+    ctx = util.make_ctx(c, force_path=PATHS[path])
+    ctx.nlist_reorder_nearest(nearest)
+    kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
+    assert np.array_equal(kv, kv_o) and kv.max() == min(nearest, 112)
+    for w in range(kv.max()):
+        m = kv > w
+        assert np.array_equal(ind[w][m], ind_o[w][m]), "row %d" % w
+    md.force()
+    ctx.force(capi.FORCE)
+    assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), md.get_sorted_fp()) < FORCE_RTOL
+    ctx.nlist_build()                                  # a rebuild restores the full list
+    assert ctx.nlist_copyout(capi.ORDER_CELL)[0].max() == 112
+    with pytest.raises(capi.MDBError):
+        ctx.nlist_reorder_nearest(513)
+    ctx.close()
