@@ -305,6 +305,7 @@ long long mdb_launch_count(const mdb_ctx *ctx); /* all kernel launches since cre
  * ---------------------------------------------------------------------------------- */
 #define MDB_LIB_MARINICA_EAM2 1
 #define MDB_LIB_BONNY_EAM1    2
+#define MDB_LIB_ACKLAND_FS_W  3 /* FS_TYPE: Potentials/EM_TB_WangJun_W-HE_2010/FS_Ackland_WW.F90 (id 1, W-W) */
 int mdb_host_ftable_create(int lib, int ng, const int *ptype, int ntab, int nembd, double rhoscal, double rmax,
                            int *nkind, int *nkind1, int *kpair, int *kembd,
                            double *potr, double *fpotr, double *potb, double *fpotb,

@@ -24,7 +24,7 @@ FORCE, VIRIAL, EPOT, DEN, NOPASS1 = 1, 2, 4, 8, 16
 F_POS4, F_D2MAX = 17, 18
 K_NAMES = ("cellsort", "nlist", "pass1", "pass2", "epot", "predict", "correct", "other")
 K_COUNT = 8
-LIB_MARINICA_EAM2, LIB_BONNY_EAM1 = 1, 2
+LIB_MARINICA_EAM2, LIB_BONNY_EAM1, LIB_ACKLAND_FS_W = 1, 2, 3
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)

@@ -140,9 +140,42 @@ Entry bonny1_ww()
     return e;
 }
 
+// Finnis-Sinclair W of Ackland & Thetford: Potentials/EM_TB_WangJun_W-HE_2010/FS_Ackland_WW.F90:25-90, registered as id 1 of
+// the library EM_TB_WANGJUN_W-HE_2010 for FS_TYPE boxes (EM_TB_ForceTable_WangJun_W_HE_2010.F90:38-40).  No EMBDF: the
+// FS kernels take -sqrt(rho) themselves.
+Entry ackland_fs_ww()
+{
+    Entry e;
+    e.pair = [](double r) {
+        const double c = 3.25e-8, c0 = 47.1346499e16 * kEvErg, c1 = -33.7665655e24 * kEvErg, c2 = 6.2541999e32 * kEvErg;
+        const double ackb = 90.3e24 * kEvErg, acka = 1.2e8, ackb0 = 2.7411e-8;
+        double core = 0.0, dcore = 0.0;
+        if (r < ackb0) { // :60-66
+            const double t = ackb0 - r, ex = std::exp(-acka * r);
+            core = ackb * (t * t * t) * ex;
+            dcore = -ackb * (3.0 * (t * t) * ex + acka * (t * t * t) * ex);
+        }
+        if (r <= c) { // :68-76
+            const double q = c0 + c1 * r + c2 * (r * r), u = r - c;
+            return Val{0.5 * ((u * u) * q + core), -(2.0 * u * q + (u * u) * (c1 + 2.0 * c2 * r) + dcore)};
+        }
+        return Val{0.0, 0.0};
+    };
+    e.rho = [](double r) {
+        const double a = 1.896373e8 * kEvErg, d = 4.400224e-8;
+        if (r <= d) return Val{a * a * ((r - d) * (r - d)), -(a * a * 2.0 * (r - d))}; // :84-90
+        return Val{0.0, 0.0};
+    };
+    return e;
+}
+
 Registry make_registry(int lib)
 {
     Registry r;
+    if (lib == MDB_LIB_ACKLAND_FS_W) {
+        r[1] = ackland_fs_ww();
+        return r;
+    }
     if (lib == MDB_LIB_MARINICA_EAM2) {
         r[1] = marinica2(); // Register_ForceTableProc("W","W",...) EAM_ForceTable_Marinica_JPCM25_2013.F90:56-63
     } else if (lib == MDB_LIB_BONNY_EAM1) {

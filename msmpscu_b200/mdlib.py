@@ -187,7 +187,7 @@ def Register_ForceClass(pottype: str, ForceClass: MDForceClassGPU = gm_ForceClas
         return vt
 
     fc.pCalPTensor = ptensor
-    fc.pCalAVStress = None  # atomic stress: analysis, a "next" row
+    fc.pCalAVStress = lambda dev, order=capi.ORDER_CELL: dev.ctx.atomic_stress(order)  # Cal_EAM_AtomicStressTensor_DEV
     return fc
 
 
@@ -214,8 +214,21 @@ def Copyout_NeighboreList_DEV(dev, order=capi.ORDER_ORIGINAL):
     return dev.ctx.nlist_copyout(order)
 
 
+def AddExtForce_ForceClass(ForceClass, Tag, pForce, pEpot=None):
+    """MD_ForceClass_Register_GPU.F90:273-277: external force procedures (boost, springs) cumulated after pCalForce.
+    pForce(dev, SimBox, CtrlParam) adds to FP on the device (mdb_devptr gives it the arrays)."""
+    ForceClass.ExtForces.append((Tag, pForce, pEpot))
+
+
+def ClearExtForce_ForceClass(ForceClass):
+    ForceClass.ExtForces.clear()
+
+
 def CalForce_ForceClass(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass):
+    """Calforce_ForceClass0/1 (:636-662): pCalForce, then Cumulate_ExtForce over the registered list."""
     ForceClass.pCalForce(dev, SimBox, CtrlParam)
+    for _tag, pforce, _pepot in ForceClass.ExtForces:
+        pforce(dev, SimBox, CtrlParam)
 
 
 def CalPTensor_ForceClass(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass):

@@ -186,9 +186,35 @@ static int bon1_nn(int id, double r, double *p, double *f)
     return 0;
 }
 
+/* Finnis-Sinclair W of Ackland & Thetford, Potentials/EM_TB_WangJun_W-HE_2010/FS_Ackland_WW.F90:25-90 (id 1 of the
+ * library EM_TB_WANGJUN_W-HE_2010 when the box declares FS_TYPE, EM_TB_ForceTable_WangJun_W_HE_2010.F90:38-40).
+ * r in cm; TB_NN: (V/2, -dV/dr) with the short-range core term below ACKB0; TB_NE: (rho = A^2 (r-d)^2, -drho/dr). */
+static void ackfs_nn(double r, double *potr, double *fpotr)
+{
+    const double c = 3.25e-8, c0 = 47.1346499e16 * ORC_EVERG, c1 = -33.7665655e24 * ORC_EVERG, c2 = 6.2541999e32 * ORC_EVERG;
+    const double ackb = 90.3e24 * ORC_EVERG, acka = 1.2e8, ackb0 = 2.7411e-8;
+    double ackfs = 0.0, dackfs = 0.0;
+    if (r < ackb0) {
+        ackfs = ackb * pow(ackb0 - r, 3.0) * exp(-acka * r);
+        dackfs = -ackb * (3.0 * pow(ackb0 - r, 2.0) * exp(-acka * r) + acka * pow(ackb0 - r, 3.0) * exp(-acka * r));
+    }
+    if (r <= c) {
+        double v = pow(r - c, 2.0) * (c0 + c1 * r + c2 * pow(r, 2.0)) + ackfs;
+        *potr = 0.5 * v;
+        *fpotr = -(2.0 * (r - c) * (c0 + c1 * r + c2 * pow(r, 2.0)) + pow(r - c, 2.0) * (c1 + 2.0 * c2 * r) + dackfs);
+    } else { *potr = 0.0; *fpotr = 0.0; }
+}
+static void ackfs_rho(double r, double *potb, double *fpotb)
+{
+    const double a = 1.896373e8 * ORC_EVERG, d = 4.400224e-8;
+    if (r <= d) { *potb = a * a * pow(r - d, 2.0); *fpotb = -(a * a * 2.0 * (r - d)); }
+    else { *potb = 0.0; *fpotb = 0.0; }
+}
+
 int orc_pot_nn(int lib, int id, double r, double *p, double *f)
 {
     *p = 0.0; *f = 0.0;
+    if (lib == ORC_LIB_ACKLAND_FS_W && id == 1) { ackfs_nn(r, p, f); return 1; }
     if (lib == ORC_LIB_MARINICA_EAM2 && id == 1) { mar2_nn(r, p, f); return 1; }
     if (lib == ORC_LIB_BONNY_EAM1) return bon1_nn(id, r, p, f);
     return 0;
@@ -196,6 +222,7 @@ int orc_pot_nn(int lib, int id, double r, double *p, double *f)
 int orc_pot_rho(int lib, int id, double r, double *p, double *f)
 {
     *p = 0.0; *f = 0.0;
+    if (lib == ORC_LIB_ACKLAND_FS_W && id == 1) { ackfs_rho(r, p, f); return 1; }
     if (lib == ORC_LIB_MARINICA_EAM2 && id == 1) { mar2_rho(r, p, f); return 1; }
     if (lib == ORC_LIB_BONNY_EAM1 && id == 1) { bon_ww_rho(r, p, f); return 1; }
     return 0;

@@ -51,6 +51,7 @@ extern "C" {
 #define ORC_LIB_BONNY_EAM1    2 /* Potentials/EAM_WHeH_Bonny_JPCM26_2014, "EAM1": ids 1..9         */
 #define ORC_LIB_MARINICA_EAM3 3
 #define ORC_LIB_MARINICA_EAM4 4
+#define ORC_LIB_ACKLAND_FS_W  5 /* Potentials/EM_TB_WangJun_W-HE_2010, FS_TYPE: id 1 = W-W (Ackland, Thetford 1987) */
 
 #define ORC_POT_EAM 0
 #define ORC_POT_FS  1

@@ -15,6 +15,9 @@ Outputs (small, committed):
       sampled rows of examples/use_ForceTableGen/EAM_WHeH_Bonny_JPCM26_2014.embd
       (Export_ForceTable output: RHO, F_k(RHO), dF_k/dRHO for the 9 ids).
   box/control text files used by those runs are copied verbatim (inputs, not source code).
+  wangjun_fs_ww_pair_rows.npz
+      sampled rows of examples/use_ForceTableGen/EM_TB_WANGJUN_W-HE_2010.pair (FS_TYPE export, Rmax = 10 A): the four
+      columns of table id 1 = W-W (Ackland, Thetford): r*V, -r dV/dr, RHO [eV^2], -dRHO/dr.
   Cu1.eam.fs.setfl.xz
       examples/NIST_Potentials/Cu_EAM/Cu1.eam.fs.setfl (public NIST potential data file, an input), xz-compressed.
   cu1_setfl_table_rows.npz
@@ -103,6 +106,12 @@ def main():
     sel = np.unique(np.concatenate([np.arange(0, 64), np.arange(64, 10000, 23), np.arange(1270, 1340), np.arange(9950, 10000)]))
     np.savez_compressed(os.path.join(HERE, "cu1_setfl_table_rows.npz"), index=pr[sel, 0].astype(np.int32), r=pr[sel, 1],
                         pair=pr[sel, 2:6], rho=em[sel, 1], embd=em[sel, 2:4])
+    # exported Finnis-Sinclair tables: columns of table id 1 (W-W, Ackland & Thetford) of the 5-id library
+    pr = rows_of(os.path.join(REF, "examples", "use_ForceTableGen", "EM_TB_WANGJUN_W-HE_2010.pair"), 22)
+    assert pr.shape[0] == 10000
+    sel = np.unique(np.concatenate([np.arange(0, 32), np.arange(32, 10000, 19), np.arange(5200, 5260), np.arange(6600, 6660)]))
+    np.savez_compressed(os.path.join(HERE, "wangjun_fs_ww_pair_rows.npz"), index=pr[sel, 0].astype(np.int32), r=pr[sel, 1],
+                        pair=pr[sel, 2:6])
     print("fixtures written to", HERE)
 
 

@@ -25,6 +25,7 @@ CASES = {
     "bcc_7x9x11": lambda: util.bcc_case((7, 9, 11), seed=7),
     "multibox3": lambda: util.bcc_case((7, 7, 7), nbox=3, seed=99),
     "neb_WH": lambda: util.neb_case("react"),
+    "bcc_fs_ackland": lambda: util.bcc_fs_case((7, 8, 9)),   # FS_TYPE kernels (MD_FS_ForceTable_GPU.F90), a real FS potential
     "fcc_cu_setfl": lambda: util.fcc_cu_case((6, 7, 8)),   # imported NIST setfl tables (EAM_NIST library), 134-entry lists
 }
 

@@ -19,6 +19,12 @@ JUMP_ABS = 2e-3
 
 
 @pytest.fixture(scope="module")
+def oracle():
+    from oracle import pyorc
+    return pyorc
+
+
+@pytest.fixture(scope="module")
 def gold():
     return np.load(os.path.join(util.GOLD, "cu1_setfl_table_rows.npz"))
 
@@ -113,3 +119,22 @@ def test_import_errors_are_status_codes(tmp_path):
         forcetable.setfl_info(str(tmp_path / "missing.setfl"))
     with pytest.raises(capi.MDBError):
         forcetable.Register_Imported_ForceTable(str(tmp_path / "missing"), [[1]], 100, 100, 1e-8)
+
+
+def test_fs_ackland_tables_match_reference_export(oracle):
+    """FS_TYPE table generation (Create_Pairwise_ForceTable on the Ackland-Thetford W-W functions) against the reference's
+    exported examples/use_ForceTableGen/EM_TB_WANGJUN_W-HE_2010.pair, table id 1, for the product and the oracle."""
+    g = np.load(os.path.join(util.GOLD, "wangjun_fs_ww_pair_rows.npz"))
+    rmax = 10.0e-8                                                       # the export's range: r_1 = 1e-7 A
+    ergev = 1.0 / 1.60219e-12
+    tp = forcetable.Create_Interaction_ForceTable(capi.LIB_ACKLAND_FS_W, [[1]], 10000, 10000, rmax, pot_type="FS_TYPE")
+    to = oracle.Tables(oracle.LIB_ACKLAND_FS_W, [[1]], 10000, 10000, rmax, rmax=rmax, pot_type=oracle.POT_FS)
+    sel = g["index"] - 1
+    for t in (tp, to):
+        r = (np.arange(1, 10001) / t.csi) ** 2 * 1e8
+        assert np.allclose(r[sel], g["r"], rtol=PRINT_PAIR, atol=0)
+        cols = np.stack([t.potr * 2 * ergev * 1e8, t.fpotr * ergev, t.potb * ergev * ergev, t.fpotb * ergev * ergev * 1e-8], axis=1)
+        for c in range(4):
+            assert np.all(np.abs(cols[sel, c] - g["pair"][:, c]) <= PRINT_PAIR * np.abs(g["pair"][:, c]) + 1e-30), c
+    assert np.max(np.abs(tp.potr - to.potr)) <= 1e-13 * np.max(np.abs(to.potr))
+    assert np.max(np.abs(tp.fpotb - to.fpotb)) <= 1e-13 * np.max(np.abs(to.fpotb))

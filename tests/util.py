@@ -31,6 +31,15 @@ def bcc_case(ncell=(8, 8, 8), a0=3.1652, seed=12345, nbox=1, ru_lu=1.9, nb_fac=1
     return c
 
 
+def bcc_fs_case(ncell=(8, 8, 8), seed=77, nbox=1):
+    """bcc W with the Finnis-Sinclair potential of Ackland & Thetford (FS_TYPE path, MD_FS_ForceTable_GPU.F90):
+    id 1 of the reference's EM_TB_WANGJUN_W-HE_2010 library; RU = 1.4 a0 (rho reaches 4.400 A = 1.39 a0)."""
+    c = bcc_case(ncell, seed=seed, nbox=nbox, ru_lu=1.4)
+    c.lib = capi.LIB_ACKLAND_FS_W
+    c.pot_type = "FS_TYPE"
+    return c
+
+
 def neb_case(tag="react", rmax_mode="RU"):
     """examples/NEB_Test: 2000 W + 1 H, Bonny EAM1 (the reference's own known-answer run)."""
     g = np.load(os.path.join(GOLD, "neb_gmd_%s.npz" % tag))
@@ -91,7 +100,8 @@ def fcc_cu_case(ncell=(8, 8, 8), seed=4242, nbox=1, ntab=10000):
 def product_tables(c):
     if getattr(c, "setfl", None):
         return forcetable.NIST_Register_Interaction_Table(c.setfl, c.ntab, c.nembd, c.ptype, rmax=c.rmax)
-    return forcetable.Create_Interaction_ForceTable(c.lib, c.ptype, c.ntab, c.nembd, c.rmax)
+    return forcetable.Create_Interaction_ForceTable(c.lib, c.ptype, c.ntab, c.nembd, c.rmax,
+                                                    pot_type=getattr(c, "pot_type", "EAM_TYPE"))
 
 
 def oracle_tables(O, c):
@@ -100,8 +110,10 @@ def oracle_tables(O, c):
         t = tables_np.setfl_tables(open(c.setfl).read(), c.ntab, c.nembd, rmax=c.rmax)
         return O.Tables.from_arrays(c.ng, c.ptype, np.diag(c.ptype), c.ntab, c.nembd, t["csi"], t["rhod"], c.ru, t["potr"],
                                     t["fpotr"], t["potb"], t["fpotb"], t["fembd"], t["dfembd"])
-    lib = {capi.LIB_MARINICA_EAM2: O.LIB_MARINICA_EAM2, capi.LIB_BONNY_EAM1: O.LIB_BONNY_EAM1}[c.lib]
-    return O.Tables(lib, c.ptype, c.ntab, c.nembd, c.ru, rmax=c.rmax)
+    lib = {capi.LIB_MARINICA_EAM2: O.LIB_MARINICA_EAM2, capi.LIB_BONNY_EAM1: O.LIB_BONNY_EAM1,
+           capi.LIB_ACKLAND_FS_W: O.LIB_ACKLAND_FS_W}[c.lib]
+    return O.Tables(lib, c.ptype, c.ntab, c.nembd, c.ru, rmax=c.rmax,
+                    pot_type=O.POT_FS if getattr(c, "pot_type", "EAM_TYPE") == "FS_TYPE" else O.POT_EAM)
 
 
 def make_ctx(c, build=True, force_path=None):
