@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=80, help="bcc cells per edge (80 -> 1 024 000 atoms)")
     ap.add_argument("--nbox", type=int, default=1, help="independent boxes per GPU, concatenated as MULTIBOX (configs[2] family)")
+    ap.add_argument("--dd", action="store_true", help="configs[4] family: ONE box of --cells^3 bcc cells cut into z-slabs over the "
+                    "ranks (ghost-layer exchange over NCCL), strong scaling; not the default bench line")
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "tiled"])
     ap.add_argument("--cpu-cells", type=int, default=32, help="edge of the CPU sample box (32 -> 65 536 atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -309,9 +311,98 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_dd(args):
+    """One box over all ranks (slab decomposition, msmpscu_b200/domain.py): the box is the same on every rank (same
+    seed); value = atoms of the box x MD steps / max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    from msmpscu_b200 import capi
+    from msmpscu_b200.domain import SlabDomain
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c = make_case(args.cells, 777)
+    n = c.xp.shape[0]
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    ctx = capi.Context(local)
+    ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
+    ctx.set_option(capi.OPT_FORCE_PATH, capi.FORCE_PATH_TILED)
+    ctx.tables_set(util.product_tables(c), c.ru * c.ru)
+    ctx.nlist_init(c.nb_rm, c.mxkvois)
+    ctx.epc_set(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
+    ctx.upload(capi.F_XP, c.xp); ctx.upload(capi.F_XP1, c.xp1)
+    ctx.upload(capi.F_ITYP, c.ityp); ctx.upload(capi.F_STATU, c.statu)
+    dom = SlabDomain(ctx, local)
+    dom.rebuild()
+    ctx.force(capi.DEN); dom.exchange(); ctx.force(capi.FORCE | capi.NOPASS1)
+    stream = dom.stream
+    itime = [0]
+
+    def block(_):
+        for _i in range(MD_PER_STEP):
+            dom.step(itime[0], 1, MD_PER_STEP, H)
+            itime[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        block(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launch_count()
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        block(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = ctx.launch_count() - l0
+    clocks = sampler.result()
+    dom.phase_ms = {}
+    block(0)
+    phases = dom.phase_report()   # one extra block of 10 steps with per-phase CUDA events (not part of the timed region)
+    dom.phase_ms = None
+    if world > 1:
+        allp = [None] * world
+        dist.all_gather_object(allp, phases)
+        phases = {k: [round(p.get(k, 0.0), 3) for p in allp] for k in phases}
+    a0, a1 = dom.owned()
+    line = base_line(args, n)
+    line["scaling"] = "strong"
+    line["config"].update({"workload": "configs[4] family: ONE bcc W box of %d atoms (%d^3 cells) cut into %d z-slabs, ghost-layer "
+                                       "exchange of {x,y,z,den} records over NCCL twice per step, list rebuilt every %d steps "
+                                       "(owned ranges broadcast, identical device sort on every rank)" % (n, args.cells, world, MD_PER_STEP),
+                           "atoms_per_gpu": a1 - a0, "atoms_total": n,
+                           "parallelism": "z-slab domain decomposition, 1 ghost cell layer per side"})
+    line.update({"value": n * MD_PER_STEP * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "clocks": clocks,
+                 "gpu_launches": int(launches), "force_path": "tiled", "mode": "dd",
+                 "phase_ms_per_block_by_rank": phases})
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.dd:
+        run_dd(a)
     else:
         run_ours(a)

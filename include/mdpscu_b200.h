@@ -164,6 +164,8 @@ int mdb_ekin(mdb_ctx *ctx);
 int mdb_epc_set(mdb_ctx *ctx, const int *enable, const double *te, const double *alpha, const double *cut,
                 const double *he);
 int mdb_epc_apply(mdb_ctx *ctx);
+/* Do_EPCForce_DEV followed by Correction_DEV as ONE kernel (identical arithmetic; what mdb_run does inside a block) */
+int mdb_epc_correct(mdb_ctx *ctx, double h);
 
 /* ------------------------------------------------------------------------------------
  * one whole MD step, For_One_Step (Appshell/MD_Method_GenericMD_GPU.F90:496-659):

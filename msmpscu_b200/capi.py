@@ -66,6 +66,7 @@ SYMBOLS = {
     "mdb_check_timestep": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip]),
     "mdb_steepest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_ip, c_dp, c_dp]),
     "mdb_nlist_reorder_nearest": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdb_epc_correct": (C.c_int, [C.c_void_p, C.c_double]),
     "mdb_atomic_stress": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mdb_atomic_stress_host": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
     "mdb_thermalize": (C.c_int, [C.c_void_p, C.c_double, C.c_ulonglong, C.c_uint]),
@@ -264,6 +265,9 @@ class Context:
 
     def predict(self, h):
         self._chk(self.lib.mdb_predict(self.h, float(h)))
+
+    def epc_correct(self, h):
+        self._chk(self.lib.mdb_epc_correct(self.h, float(h)))
 
     def correct(self, h):
         self._chk(self.lib.mdb_correct(self.h, float(h)))

@@ -178,6 +178,19 @@ extern "C" int mdb_correct(mdb_ctx *c, double h)
     return MDB_OK;
 }
 
+// Do_EPCForce_DEV + Correction_DEV in one pass over XP1/FP (the same fused kernel mdb_run uses at the end of a block)
+extern "C" int mdb_epc_correct(mdb_ctx *c, double h)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_epc_correct: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    ProfScope ps(c, MDB_K_CORRECT);
+    k_epc_correct<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
+                                                                         h * 0.5, c->epc.on, 1, own_a0(c), own_a1(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
 extern "C" int mdb_ekin(mdb_ctx *c)
 {
     if (!c) return MDB_ERR_ARG;

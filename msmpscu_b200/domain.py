@@ -44,6 +44,16 @@ class SlabDomain:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         ctx.dd_set(self.rank, self.world)
         self.info = None
+        # The library launches on torch's current stream from here on: NCCL operations issued through torch.distributed
+        # are ordered against that stream on the device (the collective waits for the kernels before it, work.wait()
+        # makes the stream wait for the collective), so a step needs no host synchronisation between its kernels and
+        # its exchanges.
+        # (a dedicated non-default torch stream: the library keeps its own stream when handed the NULL stream)
+        self.stream = torch.cuda.Stream(device=self.device)
+        ctx.set_stream(self.stream.cuda_stream)
+        self.shared_stream = True
+        self.phase_ms = None   # set to {} to collect per-phase device times (CUDA events on the step's stream)
+        self._ev = []
 
     # ---- tensor views (pointers change at every rebuild: the re-sort double-buffers)
     def _views(self):
@@ -56,10 +66,15 @@ class SlabDomain:
         self.d2max = mk(capi.F_D2MAX, (1,), "<i4")
 
     def _sync_stream(self):
-        self.ctx.sync()  # the library runs on its own stream; torch.distributed on torch's
+        if not self.shared_stream:
+            self.ctx.sync()  # a library-private stream would have to be drained before torch.distributed touches the arrays
 
     def rebuild(self):
         """All ranks obtain every rank's owned ranges, sort, and build the lists of their own layers."""
+        with self.torch.cuda.stream(self.stream):
+            return self._rebuild()
+
+    def _rebuild(self):
         if self.world > 1 and self.info is not None:
             self._views()
             self._sync_stream()
@@ -70,15 +85,22 @@ class SlabDomain:
             for r in range(self.world):
                 a0, a1 = (int(v) for v in allr[r].tolist())
                 ranges[r] = (a0, a1)
+            # positions of every atom: the sort must be the same on all ranks
             for r, (a0, a1) in enumerate(ranges):
-                if a1 <= a0:
-                    continue
-                self.dist.broadcast(self.pos[a0:a1], src=r, group=self.group)
-                for arr in (self.xp1, self.dis):
-                    for d in range(3):
-                        self.dist.broadcast(arr[d, a0:a1], src=r, group=self.group)
-                self.dist.broadcast(self.statu[a0:a1], src=r, group=self.group)
-            self.torch.cuda.synchronize(self.device)
+                if a1 > a0:
+                    self.dist.broadcast(self.pos[a0:a1], src=r, group=self.group)
+            # velocities, displacements and status only travel with atoms that change owner: between two rebuilds an atom moves
+            # far less than a cell, so a new owned atom comes from the rank's own range or from a neighbour's boundary layer
+            # -- the ghost ranges.  (Values of atoms deeper inside other slabs stay stale here and are never read.)
+            i = self.info
+            ops = []
+            for arr in (self.xp1[0], self.xp1[1], self.xp1[2], self.dis[0], self.dis[1], self.dis[2], self.statu):
+                ops += [self.dist.P2POp(self.dist.isend, arr[i["sb0"]:i["sb1"]], i["below"], self.group),
+                        self.dist.P2POp(self.dist.isend, arr[i["st0"]:i["st1"]], i["above"], self.group),
+                        self.dist.P2POp(self.dist.irecv, arr[i["ga0"]:i["ga1"]], i["above"], self.group),
+                        self.dist.P2POp(self.dist.irecv, arr[i["gb0"]:i["gb1"]], i["below"], self.group)]
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
         nout = self.ctx.nlist_build()
         if self.world > 1:
             self.info = self.ctx.dd_info()
@@ -89,6 +111,10 @@ class SlabDomain:
         """Boundary-layer records to the neighbours, ghost layers from them (positions, and DEN after pass 1)."""
         if self.world == 1:
             return
+        with self.torch.cuda.stream(self.stream):
+            self._exchange()
+
+    def _exchange(self):
         i, dist = self.info, self.dist
         self._sync_stream()
         ops = [dist.P2POp(dist.isend, self.pos[i["sb0"]:i["sb1"]], i["below"], self.group),
@@ -97,25 +123,53 @@ class SlabDomain:
                dist.P2POp(dist.irecv, self.pos[i["ga0"]:i["ga1"]], i["above"], self.group),
                dist.P2POp(dist.irecv, self.pos[i["gb0"]:i["gb1"]], i["below"], self.group)]
         for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        self.torch.cuda.synchronize(self.device)
+            w.wait()   # stream-level wait: the next kernel on this stream starts after the ghost layers have landed
 
     def step(self, itime, it0, nb_uptab, h):
         """One GMD step (Appshell/MD_Method_GenericMD_GPU.F90:596-627) on the decomposed box."""
         c = self.ctx
-        c.predict(h)
-        if (itime - it0) % nb_uptab == 0:
-            self.rebuild()
-        else:
+        mark = self._mark
+        with self.torch.cuda.stream(self.stream):
+            mark(None)
+            c.predict(h)
+            mark("predict")
+            if (itime - it0) % nb_uptab == 0:
+                self._rebuild()
+                mark("rebuild")
+            else:
+                if self.world > 1:
+                    self._sync_stream()
+                    self.dist.all_reduce(self.d2max, op=self.dist.ReduceOp.MAX, group=self.group)
+                    mark("allreduce_d2max")
+                    self._exchange()
+                mark("exchange_pos")
+            c.force(capi.DEN)
+            mark("pass1")
             if self.world > 1:
-                self._sync_stream()
-                self.dist.all_reduce(self.d2max, op=self.dist.ReduceOp.MAX, group=self.group)
-            self.exchange()
-        c.force(capi.DEN)
-        self.exchange()
-        c.force(capi.FORCE | capi.NOPASS1)
-        c.epc_apply()
-        c.correct(h)
+                self._exchange()
+            mark("exchange_den")
+            c.force(capi.FORCE | capi.NOPASS1)
+            mark("pass2")
+            c.epc_correct(h)
+            mark("correct")
+
+    def _mark(self, name):
+        if self.phase_ms is None:
+            return
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(self.stream)
+        self._ev.append((name, e))
+
+    def phase_report(self):
+        """Sum of device time per phase since the last call (needs phase_ms = {} before the steps)."""
+        self.torch.cuda.synchronize(self.device)
+        out, prev = {}, None
+        for name, e in self._ev:
+            if name is not None and prev is not None:
+                out[name] = out.get(name, 0.0) + prev.elapsed_time(e)
+            prev = e
+        self._ev = []
+        return out
 
     def owned(self):
         """(a0, a1) of this rank in CELL order."""
