@@ -725,12 +725,22 @@ k_tile_pass(TileParams P, TilePassArgs A)
                     }
                 };
 
+                // Entry e of a list sits at group e/(4G), position (e%(4G))/G, lane e%G: position p of group `it` holds the
+                // entries 4G*it + p*G .. +G-1 of every atom of the warp, so once 4G*it + p*G reaches the longest scan count
+                // in the warp that position is padding for all lanes and is skipped (a warp-uniform test; in a crystal all
+                // counts are equal and the tail of the last group -- 6 of 32 entries in pass 1 -- costs nothing).
+                const int kvw = __reduce_max_sync(0xffffffffu, kv);
 #pragma unroll 1
                 for (int it = 0; it < n4; it++) {
                     const uint2 raw = nxt;
                     if (it + 1 < n4) { nxt = __ldcs(gp); gp += gstride; } // next group in flight during this one's arithmetic
                     const unsigned s0 = raw.x & 0xffffu, s1 = raw.x >> 16, s2 = raw.y & 0xffffu, s3 = raw.y >> 16;
-                    const bool w0 = eval(s0), w1 = eval(s1), w2 = eval(s2), w3 = eval(s3);
+                    const int left = kvw - it * 4 * G;   // > 0 for some lane of the warp when this lane iterates at all
+                    bool w0 = false, w1 = false, w2 = false, w3 = false;
+                    if (left > 3 * G) { w0 = eval(s0); w1 = eval(s1); w2 = eval(s2); w3 = eval(s3); }
+                    else if (left > 2 * G) { w0 = eval(s0); w1 = eval(s1); w2 = eval(s2); }
+                    else if (left > G) { w0 = eval(s0); w1 = eval(s1); }
+                    else if (left > 0) { w0 = eval(s0); }
                     if (w0 | w1 | w2 | w3) {
                         if (w0) redo(s0);
                         if (w1) redo(s1);
