@@ -165,6 +165,18 @@ module MDB_C_BINDING
        integer(c_long_long), value :: seed
        integer(c_int), value       :: draw
      end function
+     integer(c_int) function mdb_damping(ctx) bind(C, name="mdb_damping")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     integer(c_int) function mdb_dyndamp(ctx, mxnumsteps, h, minepot, iflag, delepot) bind(C, name="mdb_dyndamp")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: mxnumsteps
+       real(c_double), value :: h, minepot
+       integer(c_int)        :: iflag
+       real(c_double)        :: delepot
+     end function
      integer(c_int) function mdb_cg(ctx, mxnumsteps, meth, maxdis, mindis, minepot, iflag, delepot) bind(C, name="mdb_cg")
        import :: c_int, c_ptr, c_double
        type(c_ptr), value    :: ctx

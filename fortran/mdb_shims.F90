@@ -90,10 +90,24 @@ module MD_DiffScheme_GPU                 ! replaces MDLIB/sor/CommonGPU/MD_DiffS
   use MDB_C_BINDING
   implicit none
 contains
+  subroutine Do_DynDamp_Forsteps_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS)                  ! :1809-1860
+    use MD_Forceclass_Register_GPU
+    type(SimMDBox), dimension(:)      ::SimBox
+    type(SimMDCtrl),       intent(in) ::CtrlParam
+    type(MDForceClassGPU), intent(in) ::ForceClass
+    integer,               intent(in) ::MXNUMSTEPS
+    integer(c_int)::IFLAG
+    real(c_double)::DELEPOT
+      if(mdb_dyndamp(m_CTX, MXNUMSTEPS, CtrlParam%H, CtrlParam%STEEPEST_MiDelE*CP_EV2ERG, IFLAG, DELEPOT) .lt. 0) &
+         stop "MDPSCU Error: mdb_dyndamp failed"
+  end subroutine
   subroutine Predictor_DEV(ITIME, SimBox, CtrlParam)
     integer, intent(in)::ITIME
     type(SimMDBox)     ::SimBox
     type(SimMDCtrl)    ::CtrlParam
+      if(ITIME .ge. CtrlParam%DAMPTIME0 .and. ITIME .le. CtrlParam%DAMPTIME0 + CtrlParam%DAMPTIME1-1) then   ! :611-617
+         if(mdb_damping(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_damping failed"
+      end if
       if(mdb_predict(m_CTX, CtrlParam%H) .lt. 0) stop "MDPSCU Error: mdb_predict failed"
   end subroutine
   subroutine Correction_DEV(ITIME, SimBox, CtrlParam)

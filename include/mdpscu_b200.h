@@ -254,6 +254,12 @@ int mdb_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned out
  * Do_CG1_Forsteps_DEV (:137-276, repeated secant steps until |STEPSIZE| <= mindis; one 128-byte readback per force
  * evaluation).  iflag: the reference's ITER when DELEPOT <= minepot or F0NORM <= 1e-64 fired, 0 when the budget ran
  * out, -1 when F0NORM <= 1e-64 before the first step. */
+/* DAMPING_KERNEL (CommonGPU/MD_DiffScheme_GPU.F90:125-185): what Predictor_DEV runs in front of the predictor while
+ * DAMPTIME0 <= ITIME < DAMPTIME0 + DAMPTIME1 (:611-617).  mdb_dyndamp = Do_DynDamp_Forsteps_DEV (:1809-1860), the
+ * CP_DAMPSCHEME_DYN branch of Do_Damp: damped dynamics with step h until max|EPOT - EPOT0| <= minepot [erg]; iflag as for
+ * mdb_steepest (0: ran out of steps). */
+int mdb_damping(mdb_ctx *ctx);
+int mdb_dyndamp(mdb_ctx *ctx, int mxnumsteps, double h, double minepot, int *iflag, double *delepot);
 int mdb_cg(mdb_ctx *ctx, int mxnumsteps, int meth, double maxdis, double mindis, double minepot, int *iflag, double *delepot);
 
 /* ------------------------------------------------------------------------------------

@@ -72,6 +72,8 @@ SYMBOLS = {
     "mdb_thermalize": (C.c_int, [C.c_void_p, C.c_double, C.c_ulonglong, C.c_uint]),
     "mdb_thermalize_bits": (C.c_int, [C.c_ulonglong, C.c_uint, C.c_uint, C.POINTER(C.c_uint)]),
     "mdb_philox4x32_10": (C.c_int, [C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
+    "mdb_damping": (C.c_int, [C.c_void_p]),
+    "mdb_dyndamp": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, c_ip, c_dp]),
     "mdb_cg": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, c_ip, c_dp]),
     "mdb_dd_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mdb_dd_info": (C.c_int, [C.c_void_p, c_ip]),
@@ -320,6 +322,15 @@ class Context:
     def thermalize(self, ti, seed, draw=0):
         """Thermalizing_MC_DEV: Maxwell velocities at ti [K] + per-box momentum removal (Philox4x32-10 keyed by seed/draw/atom id)."""
         self._chk(self.lib.mdb_thermalize(self.h, float(ti), int(seed), int(draw)))
+
+    def damping(self):
+        self._chk(self.lib.mdb_damping(self.h))
+
+    def dyndamp(self, mxnumsteps, h, minepot):
+        """Do_DynDamp_Forsteps_DEV; returns (IFLAG, DELEPOT [erg])."""
+        fl, de = C.c_int(0), C.c_double(0.0)
+        self._chk(self.lib.mdb_dyndamp(self.h, int(mxnumsteps), float(h), float(minepot), C.byref(fl), C.byref(de)))
+        return fl.value, de.value
 
     def cg(self, mxnumsteps, maxdis, mindis, minepot, meth=0):
         """Do_CG_Forsteps_DEV on the current list (meth & QUENCH_LSEARCH: the line-search variant); returns (IFLAG, DELEPOT [erg])."""

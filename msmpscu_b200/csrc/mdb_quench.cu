@@ -547,3 +547,40 @@ static int steepest1(mdb_ctx *c, int mxnumsteps, double maxdis, double mindis, i
     if (delepot) *delepot = w.H->delepot;
     return MDB_OK;
 }
+
+
+// Do_DynDamp_Forsteps_DEV, CommonGPU/MD_DiffScheme_GPU.F90:1809-1860 (CP_DAMPSCHEME_DYN of Do_Damp): damped dynamics on the
+// current list -- DAMPING, predictor, force, energy criterion max|EPOT - EPOT0| <= STEEPEST_MiDelE, corrector -- with the stop
+// flag on the device: every kernel of a later iteration returns at once, the host looks once per 8 iterations.
+extern "C" int mdb_dyndamp(mdb_ctx *c, int mxnumsteps, double h, double minepot, int *iflag, double *delepot)
+{
+    if (!c || mxnumsteps < 0 || !(h > 0.0)) return mdb_fail(c, MDB_ERR_ARG, "mdb_dyndamp: bad argument");
+    QuenchWork w;
+    int rc = quench_setup(c, "mdb_dyndamp", w);
+    if (rc < 0) return rc;
+    const int n = c->n;
+    cudaStream_t st = c->stream;
+    QuenchScal *S = w.S;
+    auto finish = [&](int code) { c->skip_flag = nullptr; return code; };
+    if ((rc = mdb_force(c, MDB_EPOT, nullptr)) < 0) return rc;                                   // :1826-1827
+    k_sd_save<<<w.nblk, QT, 0, st>>>(0, n, c->fp, w.f0, c->epot, w.epot0, S);
+    c->launches_total += 1;
+    c->skip_flag = &S->done;
+    if ((rc = quench_peek(c, w)) < 0) return finish(rc);
+    int it = 1;
+    while (!w.H->done && it <= mxnumsteps) {
+        for (int b = 0; b < 8 && it <= mxnumsteps; b++, it++) {
+            if ((rc = mdb_damping(c)) < 0) return finish(rc);                                    // :1830-1832
+            if ((rc = mdb_predict(c, h)) < 0) return finish(rc);                                 // :1833-1836
+            if ((rc = mdb_force(c, MDB_FORCE | MDB_EPOT, nullptr)) < 0) return finish(rc);        // :1839-1840
+            k_sd_echeck<<<w.nblk, QT, 0, st>>>(n, minepot, c->epot, w.epot0, w.part, S, it);     // :1841-1845
+            k_sd_save<<<w.nblk, QT, 0, st>>>(0, n, c->fp, w.f0, c->epot, w.epot0, S);            // :1846
+            c->launches_total += 2;
+            if ((rc = mdb_correct(c, h)) < 0) return finish(rc);                                 // :1847-1851
+        }
+        if ((rc = quench_peek(c, w)) < 0) return finish(rc);
+    }
+    if (iflag) *iflag = w.H->done ? w.H->iflag : 0;
+    if (delepot) *delepot = w.H->delepot;
+    return finish(MDB_OK);
+}

@@ -75,8 +75,10 @@ __device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict_
 __global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, double *__restrict__ fp,
                           double *__restrict__ dis, int *__restrict__ statu, const int *__restrict__ ityp,
                           MassParams M, BoxParams box, double th, double h2s2, double hs2,
-                          float *__restrict__ dsr, int *__restrict__ counters, int a0, int a1, int pre, EpcParams E)
+                          float *__restrict__ dsr, int *__restrict__ counters, int a0, int a1, int pre, EpcParams E,
+                          const int *__restrict__ skip)
 {
+    if (skip && *skip) return; // converged quench iteration (mdb_dyndamp)
     const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     float d2 = 0.f;
     if (i < a1 && (statu[i] & ST_ACTIVE) == ST_ACTIVE) // :295
@@ -98,8 +100,9 @@ __global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__
 // reference's two kernels (EPC_MOD_KERNEL then Correction_KERNEL).  do_epc / do_corr select stages.
 __global__ void k_epc_correct(int n, double *__restrict__ xp1, double *__restrict__ fp, const int *__restrict__ statu,
                               const int *__restrict__ ityp, MassParams M, EpcParams E, double hs2, int do_epc, int do_corr,
-                              int a0, int a1)
+                              int a0, int a1, const int *__restrict__ skip = nullptr)
 {
+    if (skip && *skip) return;
     const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a1) return;
     const int stat = statu[i];
@@ -153,7 +156,36 @@ static int predict_launch(mdb_ctx *c, double h, int pre)
     ProfScope ps(c, MDB_K_PREDICT);
     k_predict<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp,
                                                                      c->mass, c->box, th, h2s2, hs2, c->dsr, c->counters,
-                                                                     own_a0(c), own_a1(c), pre, c->epc);
+                                                                     own_a0(c), own_a1(c), pre, c->epc, c->skip_flag);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+// DAMPING_KERNEL, CommonGPU/MD_DiffScheme_GPU.F90:125-185 (called by Predictor_DEV while DAMPTIME0 <= ITIME < DAMPTIME0+DAMPTIME1,
+// :611-617, and by Do_DynDamp_Forsteps_DEV): a velocity component opposing its force component, or with a fixed position, is zeroed
+__global__ void k_damping(int n, double *__restrict__ xp1, const double *__restrict__ fp, const int *__restrict__ statu, int a0, int a1,
+                          const int *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a1) return;
+    const int st = statu[i];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const size_t o = i + (size_t)d * n;
+        double v = xp1[o];
+        if (__dmul_rn(v, fp[o]) < 0.0) v = 0.0;
+        if ((st & (ST_FIXPOSX << d)) == (ST_FIXPOSX << d)) v = 0.0;
+        xp1[o] = v;
+    }
+}
+extern "C" int mdb_damping(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_damping: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    ProfScope ps(c, MDB_K_PREDICT);
+    k_damping<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, own_a0(c), own_a1(c), c->skip_flag);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -173,7 +205,7 @@ extern "C" int mdb_correct(mdb_ctx *c, double h)
     CUDA_TRY(c, cudaSetDevice(c->dev));
     ProfScope ps(c, MDB_K_CORRECT);
     k_epc_correct<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
-                                                                         h * 0.5, 0, 1, own_a0(c), own_a1(c));
+                                                                         h * 0.5, 0, 1, own_a0(c), own_a1(c), c->skip_flag);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }

@@ -239,7 +239,18 @@ def CalEpot_ForceClass(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass):
     return ForceClass.pCalEpot(dev, SimBox, CtrlParam)
 
 
+def Do_DynDamp_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, MXNUMSTEPS=1000):
+    """CommonGPU/MD_DiffScheme_GPU.F90:1809-1860; returns (IFLAG, max energy change [eV])."""
+    midele = getattr(CtrlParam, "STEEPEST_MiDelE", 0.001)
+    fl, de = dev.ctx.dyndamp(MXNUMSTEPS, CtrlParam.H, midele * CP_EVERG)
+    return fl, de / CP_EVERG
+
+
 def Predictor_DEV(dev, ITIME, SimBox, CtrlParam):
+    """MD_DiffScheme_GPU.F90:604-682: DAMPING while DAMPTIME0 <= ITIME <= DAMPTIME0 + DAMPTIME1 - 1 (:611-617), then the predictor."""
+    d0, d1 = getattr(CtrlParam, "DAMPTIME0", 0), getattr(CtrlParam, "DAMPTIME1", 0)
+    if d1 > 0 and d0 <= ITIME <= d0 + d1 - 1:
+        dev.ctx.damping()
     dev.ctx.predict(CtrlParam.H)
 
 

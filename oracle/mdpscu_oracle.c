@@ -1114,6 +1114,44 @@ void orc_md_epot(orc_md *m)
     orc_force_epot(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->epot);
 }
 
+/* DAMPING_KERNEL, CommonGPU/MD_DiffScheme_GPU.F90:125-185: a velocity component that opposes its force component is
+ * zeroed, as is any component whose position is fixed.  (All atoms of the range, no ACTIVE test, as in the reference.) */
+void orc_damping(int n, double *xp1, const double *fp, const int *statu)
+{
+    for (int i = 0; i < n; i++)
+        for (int d = 0; d < 3; d++) {
+            double v = xp1[i + (size_t)d * n];
+            if (v * fp[i + (size_t)d * n] < 0.0) v = 0.0;
+            if ((statu[i] & (ORC_STATU_FIXPOSX << d)) == (ORC_STATU_FIXPOSX << d)) v = 0.0;
+            xp1[i + (size_t)d * n] = v;
+        }
+}
+void orc_md_damping(orc_md *m) { orc_damping(m->n, m->xp1, m->fp, m->statu); }
+
+/* Do_DynDamp_Forsteps_DEV, CommonGPU/MD_DiffScheme_GPU.F90:1809-1860.  Returns ITER at exit, 0 when out of steps. */
+int orc_md_dyndamp(orc_md *m, int mxnumsteps, double h, double minepot, double *delepot_out)
+{
+    const int n = m->n;
+    double *epot0 = (double *)malloc(sizeof(double) * n), delepot = 0.0;
+    int iflag = 0;
+    orc_md_epot(m);
+    memcpy(epot0, m->epot, sizeof(double) * n);
+    for (int iter = 1; iter <= mxnumsteps; iter++) {
+        orc_damping(n, m->xp1, m->fp, m->statu);
+        orc_predictor(n, m->xp, m->xp1, m->fp, m->dis, m->statu, m->ityp, m->cm, h, m->boxlow, m->boxup, m->zl, m->ifpd);
+        orc_md_force(m, 0);
+        orc_md_epot(m);
+        delepot = 0.0;
+        for (int i = 0; i < n; i++) { const double v = fabs(m->epot[i] - epot0[i]); if (v > delepot) delepot = v; }
+        if (delepot <= minepot) { iflag = iter; break; }
+        memcpy(epot0, m->epot, sizeof(double) * n);
+        orc_corrector(n, m->xp1, m->fp, m->statu, m->ityp, m->cm, h);
+    }
+    if (delepot_out) *delepot_out = delepot;
+    free(epot0);
+    return iflag;
+}
+
 int orc_md_step(orc_md *m, int itime, int it0, int nb_uptab, double h)
 {
     /* For_One_Step, Appshell/MD_Method_GenericMD_GPU.F90:596-627 */

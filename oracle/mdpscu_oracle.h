@@ -165,6 +165,9 @@ void  orc_md_force(orc_md *m, int with_virial);  /* pass1 + pass2 (+virial)     
 void  orc_md_reorder_nearest(orc_md *m, int nearest); /* Reorder_NeighBoreList_Nearest_Dev, in place */
 void  orc_md_epot(orc_md *m);
 void  orc_md_avstress(orc_md *m, double *ap);    /* ap[n*9], ORIGINAL order, column-major           */
+void  orc_damping(int n, double *xp1, const double *fp, const int *statu); /* DAMPING_KERNEL, MD_DiffScheme_GPU.F90:125-185 */
+void  orc_md_damping(orc_md *m);
+int   orc_md_dyndamp(orc_md *m, int mxnumsteps, double h, double minepot, double *delepot_out); /* :1809-1860 */
 int   orc_md_step(orc_md *m, int itime, int it0, int nb_uptab, double h); /* returns 1 if rebuilt */
 /* copy out in ORIGINAL order; any pointer may be NULL */
 void  orc_md_get(orc_md *m, double *xp, double *xp1, double *fp, double *epot, double *ekin,

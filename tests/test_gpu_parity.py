@@ -530,3 +530,27 @@ def test_reorder_nearest_bit_exact(oracle, path, nearest):
     with pytest.raises(capi.MDBError):
         ctx.nlist_reorder_nearest(513)
     ctx.close()
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+def test_dynamic_damping_tracks_oracle(oracle, path):
+    """DAMPING_KERNEL (MD_DiffScheme_GPU.F90:125-185) is bit-exact; Do_DynDamp_Forsteps_DEV (:1809-1860) with the stop flag on
+    the device exits at the same iteration as the restatement with the same configuration and velocities."""
+    c = util.bcc_case((8, 8, 8), seed=15, temp=300.0, disp=0.04)
+    c.statu = c.statu.copy(); c.statu[3] |= 2 | 8            # FIXPOSX, FIXPOSZ
+    md = util.oracle_md(oracle, c)
+    md.rebuild(); md.force()
+    ctx = util.make_ctx(c, force_path=PATHS[path])
+    ctx.force(capi.FORCE)
+    md.damping(); ctx.damping()
+    v = ctx.download(capi.F_XP1)
+    assert np.array_equal(v, md.get()["xp1"]) and (v == 0.0).mean() > 0.3 and v[3, 0] == 0.0 and v[3, 2] == 0.0
+    for mx, midele in ((60, 2.0e-4), (7, 1.0e-12)):
+        fl_o, de_o = md.dyndamp(mx, 1.0e-15, midele * util.CP_EVERG)
+        fl, de = ctx.dyndamp(mx, 1.0e-15, midele * util.CP_EVERG)
+        assert fl == fl_o, (mx, fl, fl_o)
+        ref = md.get()
+        assert util.relerr(ctx.download(capi.F_XP), ref["xp"]) < 1e-12
+        assert util.relerr(ctx.download(capi.F_XP1), ref["xp1"]) < 1e-9
+        assert abs(de - de_o) <= 1e-6 * abs(de_o) + 1e-22
+    ctx.close()
