@@ -12,10 +12,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.skipif(capi.load().mdb_device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_slab_run_matches_single_gpu():
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "dd_worker.py"), "25"]
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_run_matches_single_gpu(world):
+    """world = 2: both neighbours of a rank are the same rank; world = 4: interior ranks with two distinct neighbours"""
+    if capi.load().mdb_device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(29533 + world), os.path.join(ROOT, "tests", "dd_worker.py"), "25"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:], out.stderr[-3000:])
     assert out.returncode == 0
