@@ -599,3 +599,57 @@ def test_c1_nve_energy_drift_matches_oracle(oracle):
     print("C1 NVE: max |dH/H| oracle %.3e, product %.3e, max difference %.3e" % (
         np.abs(drift_r).max(), np.abs(drift_g).max(), np.abs(drift_g - drift_r).max()))
     ctx.close()
+
+
+def _vacuum_slab_case():
+    """bcc W slab with a vacuum gap: the crystal fills the lower 60 % of a box that is open (non-periodic) along z --
+    empty cells, surface atoms with short lists, cells whose atoms are all inactive (NAAC = 0, skipped by the list kernel,
+    MD_NeighborsList_GPU.F90:981-982)."""
+    c = util.bcc_case((8, 8, 8), seed=31, ifpd=(1, 1, 0))
+    zl = c.zl.copy(); zl[2] = c.zl[2] / 0.6
+    c.zl, c.boxlow = zl, np.array([c.boxlow[0], c.boxlow[1], c.xp[:, 2].min() - 0.3 * c.rr])
+    c.statu = c.statu.copy()
+    corner = (c.xp[:, 0] < c.boxlow[0] + 2.66 * c.rr) & (c.xp[:, 1] < c.boxlow[1] + 2.66 * c.rr) & (c.xp[:, 2] < c.boxlow[2] + 2.66 * c.rr)
+    c.statu[corner] = 0                                   # one whole corner cell inactive
+    return c
+
+
+EDGE_CASES = {
+    "vacuum_slab": _vacuum_slab_case,
+    "three_cells_per_edge": lambda: util.bcc_case((7, 7, 7), seed=5, ru_lu=1.9, nb_fac=1.2),   # 7 a0 / 2.28 -> 3 cells (the minimum)
+    "one_atom_removed_and_one_added": lambda: _defect_case(),
+}
+
+
+def _defect_case():
+    """a vacancy and a self-interstitial: ragged list lengths (the interstitial's neighbours exceed the crystal count)"""
+    c = util.bcc_case((8, 8, 8), seed=8)
+    x = c.xp.copy()
+    x[100] = x[101] + np.array([0.5, 0.0, 0.0]) * c.rr * 0.9      # atom 100 leaves its site and sits next to atom 101
+    c.xp = x
+    return c
+
+
+@pytest.mark.parametrize("name", list(EDGE_CASES))
+def test_edge_configurations(oracle, name):
+    """Empty cells, inactive cells, the minimum cell grid, defects: cells, lists (bit-exact, reference order) and forces on
+    the generic path and on AUTO (tiled where the configuration fits its shared-memory plan, generic otherwise)."""
+    c = EDGE_CASES[name]()
+    ref = _oracle_list(oracle, c)
+    gid = ref["gid"] - 1
+    fp, den, _, ep = oracle.force(c.xp[gid], c.ityp[gid], ref["statu"][gid], ref["kvois"], ref["indi"], c.zl, c.ifpd,
+                                  util.oracle_tables(oracle, c), epot=True)
+    assert ref["kvois"].min() < ref["kvois"].max()
+    for path in (capi.FORCE_PATH_GENERIC, capi.FORCE_PATH_AUTO):
+        ctx = util.make_ctx(c, force_path=path)
+        assert np.array_equal(ctx.download(capi.F_GID, capi.ORDER_CELL), ref["gid"])
+        assert np.array_equal(ctx.download(capi.F_NAC), ref["nac"]) and np.array_equal(ctx.download(capi.F_NAAC), ref["naac"])
+        kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
+        assert np.array_equal(kv, ref["kvois"])
+        for w in range(kv.max()):
+            m = kv > w
+            assert np.array_equal(ind[w][m], ref["indi"][w][m])
+        ctx.force(capi.FORCE | capi.EPOT)
+        assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < FORCE_RTOL
+        assert util.relerr(ctx.download(capi.F_EPOT, capi.ORDER_CELL), ep) < FORCE_RTOL
+        ctx.close()
