@@ -165,6 +165,13 @@ module MDB_C_BINDING
        integer(c_long_long), value :: seed
        integer(c_int), value       :: draw
      end function
+     integer(c_int) function mdb_lbfgs(ctx, mxnumsteps, msave, factr, pgtol, iflag, nfg, niter) bind(C, name="mdb_lbfgs")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value    :: ctx
+       integer(c_int), value :: mxnumsteps, msave
+       real(c_double), value :: factr, pgtol
+       integer(c_int)        :: iflag, nfg, niter
+     end function
      integer(c_int) function mdb_damping(ctx) bind(C, name="mdb_damping")
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx

@@ -208,3 +208,27 @@ contains
       end if
   end subroutine
 end module MD_CGScheme_GPU
+
+!--- CommonGPU/MD_LBFGSScheme_GPU.F90:177-388
+module MD_LBFGSScheme_GPU
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MD_Forceclass_Register_GPU
+  use mdb_c_binding
+  implicit none
+contains
+  subroutine DO_LBFGSB_FORSTEPS_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, IFLAG)
+      type(SimMDBox), dimension(:)      :: SimBox
+      type(SimMDCtrl),       intent(in) :: CtrlParam
+      type(MDForceClassGPU), intent(in) :: ForceClass
+      integer,               intent(in) :: MXNUMSTEPS
+      integer                           :: IFLAG
+      integer(c_int) :: NFG, NITER
+      if(mdb_lbfgs(m_CTX, MXNUMSTEPS, CtrlParam%LBFGS_MSave, CtrlParam%LBFGS_Factr, CtrlParam%LBFGS_PGtol, IFLAG, NFG, NITER) .lt. 0) &
+         stop "MDPSCU Error: mdb_lbfgs failed"
+      if(IFLAG .gt. 0) then
+         write(*,fmt="(A, I2, A, I7, A)") " MDPSCU Warning: LBFG exit with code ", IFLAG, " after ", MXNUMSTEPS, " steps"
+         call ONWARNING(gm_OnWarning)
+      end if
+  end subroutine
+end module MD_LBFGSScheme_GPU

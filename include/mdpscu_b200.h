@@ -254,6 +254,13 @@ int mdb_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned out
  * Do_CG1_Forsteps_DEV (:137-276, repeated secant steps until |STEPSIZE| <= mindis; one 128-byte readback per force
  * evaluation).  iflag: the reference's ITER when DELEPOT <= minepot or F0NORM <= 1e-64 fired, 0 when the budget ran
  * out, -1 when F0NORM <= 1e-64 before the first step. */
+/* DO_LBFGSB_FORSTEPS_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, IFLAG), CommonGPU/MD_LBFGSScheme_GPU.F90:177-388: the
+ * limited-memory BFGS quench every method class uses (Do_Damp of PARREP / ART / BST / TAD, QUICKDAMP "LBFGS" of GMD).  The
+ * reference packs X and G on the host and calls the serial SETULB (L-BFGS-B, NBD = 0: no bounds) each iteration; here the
+ * vectors stay on the device and only scalars reach the host (csrc/mdb_lbfgs.cu).  msave = LBFGS_MSave (<= 16), factr =
+ * LBFGS_Factr, pgtol = LBFGS_PGtol (max |gradient component|, erg/cm).  mxnumsteps counts SETULB calls as the reference does
+ * (one per force evaluation, one per accepted step).  iflag: 0 finished, 1 out of steps.  Velocities are zeroed at the end. */
+int mdb_lbfgs(mdb_ctx *ctx, int mxnumsteps, int msave, double factr, double pgtol, int *iflag, int *nfg, int *niter);
 /* DAMPING_KERNEL (CommonGPU/MD_DiffScheme_GPU.F90:125-185): what Predictor_DEV runs in front of the predictor while
  * DAMPTIME0 <= ITIME < DAMPTIME0 + DAMPTIME1 (:611-617).  mdb_dyndamp = Do_DynDamp_Forsteps_DEV (:1809-1860), the
  * CP_DAMPSCHEME_DYN branch of Do_Damp: damped dynamics with step h until max|EPOT - EPOT0| <= minepot [erg]; iflag as for

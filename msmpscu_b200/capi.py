@@ -72,6 +72,7 @@ SYMBOLS = {
     "mdb_thermalize": (C.c_int, [C.c_void_p, C.c_double, C.c_ulonglong, C.c_uint]),
     "mdb_thermalize_bits": (C.c_int, [C.c_ulonglong, C.c_uint, C.c_uint, C.POINTER(C.c_uint)]),
     "mdb_philox4x32_10": (C.c_int, [C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
+    "mdb_lbfgs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, c_ip, c_ip, c_ip]),
     "mdb_damping": (C.c_int, [C.c_void_p]),
     "mdb_dyndamp": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, c_ip, c_dp]),
     "mdb_cg": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, c_ip, c_dp]),
@@ -322,6 +323,13 @@ class Context:
     def thermalize(self, ti, seed, draw=0):
         """Thermalizing_MC_DEV: Maxwell velocities at ti [K] + per-box momentum removal (Philox4x32-10 keyed by seed/draw/atom id)."""
         self._chk(self.lib.mdb_thermalize(self.h, float(ti), int(seed), int(draw)))
+
+    def lbfgs(self, mxnumsteps, msave, factr, pgtol):
+        """DO_LBFGSB_FORSTEPS_DEV; returns (IFLAG, force evaluations, accepted steps)."""
+        fl, nfg, nit = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._chk(self.lib.mdb_lbfgs(self.h, int(mxnumsteps), int(msave), float(factr), float(pgtol), C.byref(fl), C.byref(nfg),
+                                     C.byref(nit)))
+        return fl.value, nfg.value, nit.value
 
     def damping(self):
         self._chk(self.lib.mdb_damping(self.h))

@@ -239,6 +239,32 @@ def CalEpot_ForceClass(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass):
     return ForceClass.pCalEpot(dev, SimBox, CtrlParam)
 
 
+def DO_LBFGSB_FORSTEPS_DEV(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, MXNUMSTEPS=1000):
+    """CommonGPU/MD_LBFGSScheme_GPU.F90:177-388; returns IFLAG (0 finished, 1 out of steps).  Control values as the
+    reference takes them: CtrlParam.LBFGS_MSave, LBFGS_Factr, LBFGS_PGtol (Common/MD_TypeDef_SimCtrlParam.F90:207-209)."""
+    fl, _nfg, _nit = dev.ctx.lbfgs(MXNUMSTEPS, getattr(CtrlParam, "LBFGS_MSave", 7), getattr(CtrlParam, "LBFGS_Factr", 0.0),
+                                   getattr(CtrlParam, "LBFGS_PGtol", 0.0))
+    return fl
+
+
+def Do_Damp(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass):
+    """Appshell/MD_Method_ParRep_GPU.F90:883-955 (the same dispatch sits in the ART / BST / TAD method classes): quench by
+    the scheme named in the low word of CtrlParam.Quench_Meth, then the per-atom energies."""
+    meth = getattr(CtrlParam, "Quench_Meth", "ST")
+    steps = getattr(CtrlParam, "Quench_Steps", 1000)
+    flags = capi.QUENCH_LSEARCH if getattr(CtrlParam, "Quench_LSearch", False) else 0
+    if meth == "LBFGS":
+        out = DO_LBFGSB_FORSTEPS_DEV(dev, SimBox, CtrlParam, ForceClass, steps)
+    elif meth == "DYN":
+        out = Do_DynDamp_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass, steps)
+    elif meth == "CG":
+        out = Do_CG_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass, steps, flags)
+    else:
+        out = Do_Steepest_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass, steps, flags)
+    CalEpot_ForceClass(dev, SimBox, CtrlParam, ForceClass)
+    return out
+
+
 def Do_DynDamp_Forsteps_DEV(dev, SimBox, CtrlParam, ForceClass=gm_ForceClass, MXNUMSTEPS=1000):
     """CommonGPU/MD_DiffScheme_GPU.F90:1809-1860; returns (IFLAG, max energy change [eV])."""
     midele = getattr(CtrlParam, "STEEPEST_MiDelE", 0.001)

@@ -1528,3 +1528,250 @@ void orc_md_thermalize(orc_md *m, double ti, unsigned long long seed, unsigned d
     }
     free(pos_of);
 }
+
+
+/* ------------------------------------------------------------------------------------
+ * DO_LBFGSB_FORSTEPS_DEV, CommonGPU/MD_LBFGSScheme_GPU.F90:177-388: limited-memory BFGS quench driven through the
+ * reverse-communication routine SETULB (LIB/sor/f/LBFGSB/lbfgsb.f, L-BFGS-B of Zhu, Byrd, Lu, Nocedal) with NBD = 0 for
+ * every variable, i.e. WITHOUT bounds.  What SETULB does in that case is restated here:
+ *   - variables: the free position components (FIXPOS bit clear, not OUTOFBOX, ACTIVE), :213-243; objective = sum of
+ *     EPOT over all atoms, gradient = -FP, :332-337; the positions given to the force routine are X wrapped into the
+ *     periodic box, X itself stays unwrapped (:268-330);
+ *   - mainlb (lbfgsb.f:287-1000) without bounds: the generalized Cauchy point is x (:222 block "if (.not.cnstnd .and.
+ *     col.gt.0)") and the subspace minimisation (formk/cmprlb/subsm) returns the quasi-Newton step -H g of the compact
+ *     limited-memory matrix with B0 = theta*I, theta = y'y/s'y (matupd :2461); with an empty memory the step is -g/theta
+ *     (cauchy with no breakpoints).  That step is computed here by the two-loop recursion, which is the same vector in
+ *     exact arithmetic -- NOT the same floating-point operations as formk's LEL^T factorisation, so agreement with a
+ *     run of the reference binary is to round-off amplified by the iteration, not bit for bit ("parity unpinned": no
+ *     reference output of an L-BFGS quench ships);
+ *   - lnsrlb (:2285-2396): first step min(1/|d|, 1e10) at iteration 0, else 1; More'-Thuente search dcsrch/dcstep
+ *     (:3280-3530, :3534-3760) with ftol 1e-3, gtol 0.9, xtol 0.1, stpmin 0, stpmax 1e10; 20 evaluations at most;
+ *   - tests (:777 block): max|g_i| <= pgtol; (fold - f) <= factr*epsmch*max(|fold|,|f|,1); update skipped when
+ *     s'y <= epsmch*(-gdold*stp); memory reset and restart when the search fails with a non-empty memory.
+ * Every SETULB call counts against MXNUMSTEPS (:296): one per function evaluation and one per accepted step.
+ * Returns IFLAG (0 converged / abnormal line search, 1 out of steps); *nfg = force evaluations, *niter = accepted steps. */
+typedef struct { int brackt, stage; double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1; } orc_ls;
+static void orc_dcstep(double *stx, double *fx, double *dx, double *sty, double *fy, double *dy, double *stp, double fp, double dp,
+                       int *brackt, double stpmin, double stpmax)
+{
+    double gamma, p, q, r, s, sgnd, stpc, stpf, stpq, theta;
+    sgnd = dp * (*dx / fabs(*dx));
+    if (fp > *fx) { /* case 1: higher value -> bracketed; cubic vs quadratic, :3620-3640 */
+        theta = 3.0 * (*fx - fp) / (*stp - *stx) + *dx + dp;
+        s = fmax(fabs(theta), fmax(fabs(*dx), fabs(dp)));
+        gamma = s * sqrt((theta / s) * (theta / s) - (*dx / s) * (dp / s));
+        if (*stp < *stx) gamma = -gamma;
+        p = (gamma - *dx) + theta; q = ((gamma - *dx) + gamma) + dp; r = p / q;
+        stpc = *stx + r * (*stp - *stx);
+        stpq = *stx + ((*dx / ((*fx - fp) / (*stp - *stx) + *dx)) / 2.0) * (*stp - *stx);
+        stpf = (fabs(stpc - *stx) < fabs(stpq - *stx)) ? stpc : stpc + (stpq - stpc) / 2.0;
+        *brackt = 1;
+    } else if (sgnd < 0.0) { /* case 2: derivatives of opposite sign, :3648-3665 */
+        theta = 3.0 * (*fx - fp) / (*stp - *stx) + *dx + dp;
+        s = fmax(fabs(theta), fmax(fabs(*dx), fabs(dp)));
+        gamma = s * sqrt((theta / s) * (theta / s) - (*dx / s) * (dp / s));
+        if (*stp > *stx) gamma = -gamma;
+        p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + *dx; r = p / q;
+        stpc = *stp + r * (*stx - *stp);
+        stpq = *stp + (dp / (dp - *dx)) * (*stx - *stp);
+        stpf = (fabs(stpc - *stp) > fabs(stpq - *stp)) ? stpc : stpq;
+        *brackt = 1;
+    } else if (fabs(dp) < fabs(*dx)) { /* case 3: derivative decreases in magnitude, :3673-3715 */
+        double t;
+        theta = 3.0 * (*fx - fp) / (*stp - *stx) + *dx + dp;
+        s = fmax(fabs(theta), fmax(fabs(*dx), fabs(dp)));
+        t = (theta / s) * (theta / s) - (*dx / s) * (dp / s);
+        gamma = s * sqrt(t > 0.0 ? t : 0.0);
+        if (*stp > *stx) gamma = -gamma;
+        p = (gamma - dp) + theta; q = (gamma + (*dx - dp)) + gamma; r = p / q;
+        if (r < 0.0 && gamma != 0.0) stpc = *stp + r * (*stx - *stp);
+        else if (*stp > *stx) stpc = stpmax;
+        else stpc = stpmin;
+        stpq = *stp + (dp / (dp - *dx)) * (*stx - *stp);
+        if (*brackt) {
+            stpf = (fabs(stpc - *stp) < fabs(stpq - *stp)) ? stpc : stpq;
+            if (*stp > *stx) stpf = fmin(*stp + 0.66 * (*sty - *stp), stpf);
+            else stpf = fmax(*stp + 0.66 * (*sty - *stp), stpf);
+        } else {
+            stpf = (fabs(stpc - *stp) > fabs(stpq - *stp)) ? stpc : stpq;
+            stpf = fmin(stpmax, stpf);
+            stpf = fmax(stpmin, stpf);
+        }
+    } else { /* case 4, :3722-3738 */
+        if (*brackt) {
+            theta = 3.0 * (fp - *fy) / (*sty - *stp) + *dy + dp;
+            s = fmax(fabs(theta), fmax(fabs(*dy), fabs(dp)));
+            gamma = s * sqrt((theta / s) * (theta / s) - (*dy / s) * (dp / s));
+            if (*stp > *sty) gamma = -gamma;
+            p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + *dy; r = p / q;
+            stpf = *stp + r * (*sty - *stp);
+        } else stpf = (*stp > *stx) ? stpmax : stpmin;
+    }
+    if (fp > *fx) { *sty = *stp; *fy = fp; *dy = dp; }
+    else {
+        if (sgnd < 0.0) { *sty = *stx; *fy = *fx; *dy = *dx; }
+        *stx = *stp; *fx = fp; *dx = dp;
+    }
+    *stp = stpf;
+}
+/* dcsrch: returns 0 = evaluate at *stp, 1 = converged, 2 = warning (search ends), -1 = error */
+static int orc_dcsrch(orc_ls *L, int start, double f, double g, double *stp, double ftol, double gtol, double xtol, double stpmin, double stpmax)
+{
+    if (start) {
+        if (*stp < stpmin || *stp > stpmax || g >= 0.0) return -1;
+        L->brackt = 0; L->stage = 1; L->finit = f; L->ginit = g; L->gtest = ftol * g;
+        L->width = stpmax - stpmin; L->width1 = L->width / 0.5;
+        L->stx = 0.0; L->fx = f; L->gx = g; L->sty = 0.0; L->fy = f; L->gy = g;
+        L->stmin = 0.0; L->stmax = *stp + 4.0 * *stp;
+        return 0;
+    }
+    {
+        const double ftest = L->finit + *stp * L->gtest;
+        int warn = 0, conv = 0;
+        if (L->stage == 1 && f <= ftest && g >= 0.0) L->stage = 2;
+        if (L->brackt && (*stp <= L->stmin || *stp >= L->stmax)) warn = 1;
+        if (L->brackt && L->stmax - L->stmin <= xtol * L->stmax) warn = 1;
+        if (*stp == stpmax && f <= ftest && g <= L->gtest) warn = 1;
+        if (*stp == stpmin && (f > ftest || g >= L->gtest)) warn = 1;
+        if (f <= ftest && fabs(g) <= gtol * (-L->ginit)) conv = 1;
+        if (conv) return 1;
+        if (warn) return 2;
+        if (L->stage == 1 && f <= L->fx && f > ftest) { /* modified function, :3438-3456 */
+            double fm = f - *stp * L->gtest, fxm = L->fx - L->stx * L->gtest, fym = L->fy - L->sty * L->gtest;
+            double gm = g - L->gtest, gxm = L->gx - L->gtest, gym = L->gy - L->gtest;
+            orc_dcstep(&L->stx, &fxm, &gxm, &L->sty, &fym, &gym, stp, fm, gm, &L->brackt, L->stmin, L->stmax);
+            L->fx = fxm + L->stx * L->gtest; L->fy = fym + L->sty * L->gtest; L->gx = gxm + L->gtest; L->gy = gym + L->gtest;
+        } else
+            orc_dcstep(&L->stx, &L->fx, &L->gx, &L->sty, &L->fy, &L->gy, stp, f, g, &L->brackt, L->stmin, L->stmax);
+        if (L->brackt) {
+            if (fabs(L->sty - L->stx) >= 0.66 * L->width1) *stp = L->stx + 0.5 * (L->sty - L->stx);
+            L->width1 = L->width; L->width = fabs(L->sty - L->stx);
+        }
+        if (L->brackt) { L->stmin = fmin(L->stx, L->sty); L->stmax = fmax(L->stx, L->sty); }
+        else { L->stmin = *stp + 1.1 * (*stp - L->stx); L->stmax = *stp + 4.0 * (*stp - L->stx); }
+        *stp = fmax(*stp, stpmin);
+        *stp = fmin(*stp, stpmax);
+        if ((L->brackt && (*stp <= L->stmin || *stp >= L->stmax)) || (L->brackt && L->stmax - L->stmin <= xtol * L->stmax)) *stp = L->stx;
+    }
+    return 0;
+}
+
+int orc_md_lbfgsb(orc_md *m, int mxnumsteps, int msave, double factr, double pgtol, int *nfg_out, int *niter_out)
+{
+    const int n = m->n;
+    const size_t n3 = (size_t)n * 3;
+    const double epsmch = 2.220446049250313e-16, big = 1.0e10;
+    unsigned char *fre = (unsigned char *)malloc(n3);
+    double *x = (double *)malloc(sizeof(double) * n3), *g = (double *)malloc(sizeof(double) * n3), *d = (double *)malloc(sizeof(double) * n3);
+    double *t = (double *)malloc(sizeof(double) * n3), *r = (double *)malloc(sizeof(double) * n3);
+    double *ws = (double *)malloc(sizeof(double) * n3 * msave), *wy = (double *)malloc(sizeof(double) * n3 * msave);
+    double *rho = (double *)malloc(sizeof(double) * msave), *alpha = (double *)malloc(sizeof(double) * msave);
+    double f = 0.0, fold = 0.0, theta = 1.0, stp = 0.0, gd = 0.0, gdold = 0.0, dtd = 0.0, dnorm = 0.0, sbgnrm = 0.0;
+    const double tol = factr * epsmch;
+    int col = 0, head = 0, iter = 0, nfg = 0, calls = 0, iflag = 0, ifun = 0, done = 0;
+    orc_ls L;
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            const int st = m->statu[i];
+            fre[i + (size_t)k * n] = ((st & (ORC_STATU_FIXPOSX << k)) == 0 && (st & ORC_STATU_OUTOFBOX) == 0 &&
+                                      (st & ORC_STATU_ACTIVE) == ORC_STATU_ACTIVE) ? 1 : 0;
+        }
+    memcpy(x, m->xp, sizeof(double) * n3);
+#define LB_EVAL()                                                                                                          \
+    do { /* positions = X wrapped into the box (:268-330), force + energy, G = -FP on the free components (:332-337) */     \
+        for (int i_ = 0; i_ < n; i_++)                                                                                     \
+            for (int k_ = 0; k_ < 3; k_++) {                                                                               \
+                const size_t o_ = i_ + (size_t)k_ * n;                                                                     \
+                if (!fre[o_]) continue;                                                                                    \
+                double v_ = x[o_];                                                                                         \
+                if (m->ifpd[k_]) { if (v_ < m->boxlow[k_]) v_ = v_ + m->zl[k_]; else if (v_ > m->boxup[k_]) v_ = v_ - m->zl[k_]; } \
+                m->xp[o_] = v_;                                                                                            \
+            }                                                                                                              \
+        orc_md_force(m, 0); orc_md_epot(m);                                                                                \
+        f = 0.0; for (int i_ = 0; i_ < n; i_++) f += m->epot[i_];                                                          \
+        for (size_t o_ = 0; o_ < n3; o_++) g[o_] = fre[o_] ? -m->fp[o_] : 0.0;                                            \
+        nfg++;                                                                                                             \
+    } while (0)
+    /* call 1: 'START' -> 'FG_START' */
+    calls = 1;
+    if (calls > mxnumsteps) { iflag = 1; goto out; }
+    LB_EVAL();
+    sbgnrm = 0.0; for (size_t o = 0; o < n3; o++) if (fabs(g[o]) > sbgnrm) sbgnrm = fabs(g[o]);
+    if (sbgnrm <= pgtol) goto out;
+    while (!done) {
+        /* ---- direction: -H g by the two-loop recursion, H0 = I/theta */
+        memcpy(d, g, sizeof(double) * n3);
+        for (int j = col - 1; j >= 0; j--) {
+            const int p = (head + j) % msave;
+            alpha[j] = rho[p] * vdot(ws + (size_t)p * n3, d, n3);
+            for (size_t o = 0; o < n3; o++) d[o] = d[o] - alpha[j] * wy[(size_t)p * n3 + o];
+        }
+        for (size_t o = 0; o < n3; o++) d[o] = d[o] / theta;
+        for (int j = 0; j < col; j++) {
+            const int p = (head + j) % msave;
+            const double beta = rho[p] * vdot(wy + (size_t)p * n3, d, n3);
+            for (size_t o = 0; o < n3; o++) d[o] = d[o] + ws[(size_t)p * n3 + o] * (alpha[j] - beta);
+        }
+        for (size_t o = 0; o < n3; o++) d[o] = -d[o];
+        /* ---- lnsrlb :2313-2350 */
+        dtd = vdot(d, d, n3); dnorm = sqrt(dtd);
+        stp = (iter == 0) ? fmin(1.0 / dnorm, big) : 1.0;
+        memcpy(t, x, sizeof(double) * n3); memcpy(r, g, sizeof(double) * n3);
+        fold = f; ifun = 0;
+        {
+            int start = 1, failed = 0;
+            for (;;) {
+                int rc;
+                gd = vdot(g, d, n3);
+                if (ifun == 0) { gdold = gd; if (gd >= 0.0) { failed = 1; break; } } /* info = -4 */
+                rc = orc_dcsrch(&L, start, f, gd, &stp, 1.0e-3, 0.9, 0.1, 0.0, big);
+                start = 0;
+                if (rc != 0) break;                       /* CONVERGENCE or WARNING: task = NEW_X */
+                ifun++;
+                if (ifun - 1 >= 20) { failed = 1; break; } /* iback >= 20 (:906) */
+                for (size_t o = 0; o < n3; o++) x[o] = stp * d[o] + t[o];
+                calls++;
+                if (calls > mxnumsteps) { iflag = 1; goto out; }
+                LB_EVAL();
+            }
+            if (failed) { /* :906-935: restore, then either give up (empty memory) or refresh the memory and restart */
+                memcpy(x, t, sizeof(double) * n3); memcpy(g, r, sizeof(double) * n3); f = fold;
+                if (col == 0) { iter++; done = 1; break; }  /* ABNORMAL_TERMINATION_IN_LNSRCH */
+                col = 0; head = 0; theta = 1.0;
+                continue;
+            }
+        }
+        /* ---- NEW_X returned: one more call */
+        iter++;
+        calls++;
+        sbgnrm = 0.0; for (size_t o = 0; o < n3; o++) if (fabs(g[o]) > sbgnrm) sbgnrm = fabs(g[o]);
+        if (calls > mxnumsteps || calls + 1 > mxnumsteps) { iflag = 1; goto out; } /* the tests below belong to the NEXT call */
+        if (sbgnrm <= pgtol) break;
+        { const double dd = fmax(fabs(fold), fmax(fabs(f), 1.0)); if ((fold - f) <= tol * dd) break; }
+        /* ---- update :822-862 */
+        {
+            double rr, dr, ddum;
+            for (size_t o = 0; o < n3; o++) r[o] = g[o] - r[o];
+            rr = vdot(r, r, n3);
+            if (stp == 1.0) { dr = gd - gdold; ddum = -gdold; }
+            else { dr = (gd - gdold) * stp; for (size_t o = 0; o < n3; o++) d[o] = stp * d[o]; ddum = -gdold * stp; }
+            if (dr > epsmch * ddum) {
+                int slot;
+                if (col < msave) { slot = (head + col) % msave; col++; }
+                else { slot = head; head = (head + 1) % msave; }
+                memcpy(ws + (size_t)slot * n3, d, sizeof(double) * n3);
+                memcpy(wy + (size_t)slot * n3, r, sizeof(double) * n3);
+                rho[slot] = 1.0 / dr;
+                theta = rr / dr;
+            }
+        }
+    }
+out:
+    /* the last evaluated configuration stays on the device state; velocities are zeroed (:363-364) */
+    for (size_t o = 0; o < n3; o++) m->xp1[o] = 0.0;
+    if (nfg_out) *nfg_out = nfg;
+    if (niter_out) *niter_out = iter;
+#undef LB_EVAL
+    free(fre); free(x); free(g); free(d); free(t); free(r); free(ws); free(wy); free(rho); free(alpha);
+    return iflag;
+}

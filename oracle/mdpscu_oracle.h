@@ -181,6 +181,8 @@ int   orc_md_steepest0(orc_md *m, int mxnumsteps, double alpha0, double maxdis, 
 int   orc_md_cg(orc_md *m, int mxnumsteps, int lsearch, double maxdis, double mindis, double minepot, double *delepot_out);
 int   orc_md_steepest1(orc_md *m, int mxnumsteps, double maxdis, double mindis, double *delepot_out);
 /* Cal_GlobalT_DEV :1042-1064, VelScaling_DEV :1262-1446, CheckTimestep_DEV :1066-1258 (MD_DiffScheme_GPU.F90) */
+/* DO_LBFGSB_FORSTEPS_DEV (CommonGPU/MD_LBFGSScheme_GPU.F90:177-388) = SETULB without bounds; see the definition */
+int   orc_md_lbfgsb(orc_md *m, int mxnumsteps, int msave, double factr, double pgtol, int *nfg_out, int *niter_out);
 /* Thermalizing_MC_DEV :1608-1805 with Philox4x32-10 uniforms (see the definition) */
 void  orc_philox4x32_10(const unsigned ctr[4], const unsigned key[2], unsigned out[4]);
 void  orc_md_thermalize(orc_md *m, double ti, unsigned long long seed, unsigned draw);
