@@ -570,6 +570,7 @@ extern "C" int mdb_tables_set(mdb_ctx *c, int pot_type, int nkind, int ntab, dou
         }
     }
     c->h_potb.assign(potb, potb + (size_t)nkind * ntab);
+    c->h_potr.assign(potr, potr + (size_t)nkind * ntab);
     c->h_fpotr.assign(fpotr, fpotr + (size_t)nkind * ntab);
     c->h_fpotb.assign(fpotb, fpotb + (size_t)nkind * ntab);
     c->has_tables = true;

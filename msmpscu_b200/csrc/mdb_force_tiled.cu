@@ -372,6 +372,8 @@ struct TilePassArgs {
     const unsigned short *nbl; double *fp; int *counters; const TileDesc *desc;
     // tables: global packed {T[kk], T[kk+1]-T[kk]} (stride ntab+2 per kind) for the rare fall-backs
     const double2 *g_potb, *g_fpotr, *g_fpotb, *g_dfembd;
+    const double2 *g_potr, *g_fembd;   // PASS 3 (per-atom energy): pair term and embedding VALUE tables
+    double *epot;
     int ntab, nembd, pot_type;
     double csi, rhod;
     double r2eff;          // min(RU2, table support) for this pass
@@ -433,6 +435,22 @@ __device__ __noinline__ double pair_slow(double4 me, double4 pj, double csi, con
     const double fb0 = lerp_g(tb, stride, k0, kk, dk);
     const double fb1 = (k1 == k0) ? fb0 : lerp_g(tb, stride, k1, kk, dk);
     return y * fma(fr, y, fma(fb0, me.w, fb1 * pj.w));
+}
+
+// PASS 3 twin: (POTR/r, POTB) of one pair from the global tables, kind kt = KPAIR(ITYP_i, ITYP_j) for both (:1620-1623)
+__device__ __noinline__ double2 pair_slow_epot(double4 me, double4 pj, double csi, const double2 *__restrict__ tr,
+                                               const double2 *__restrict__ tb, int stride, int kt)
+{
+    const double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
+    const double r2 = fma(sz, sz, fma(sy, sy, sx * sx));
+    const double y = rsqrt_fast(r2);
+    const double r = r2 * y;
+    const double z = rsqrt_fast(r);
+    const double sk = (r * z) * csi;
+    const double tk = __dadd_rd(sk, 4503599627370496.0);
+    const int kk = __double2loint(tk);
+    const double dk = sk - (tk - 4503599627370496.0);
+    return make_double2(lerp_g(tr, stride, kt, kk, dk) * y, lerp_g(tb, stride, kt, kk, dk));
 }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers
@@ -516,8 +534,10 @@ k_tile_pass(TileParams P, TilePassArgs A)
             if (PASS == 1) {
                 const int k1 = min(kk + 1, stride - 1);
                 s_tab[r] = make_double2(A.g_potb[(size_t)A.kind0 * stride + kk].x, A.g_potb[(size_t)A.kind0 * stride + k1].x);
-            } else {
+            } else if (PASS == 2) {
                 s_tab[r] = make_double2(A.g_fpotr[(size_t)A.kind0 * stride + kk].x, A.g_fpotb[(size_t)A.kind0 * stride + kk].x);
+            } else { // PASS 3: {POTR[kk], POTB[kk]}, rows kk and kk+1 are read
+                s_tab[r] = make_double2(A.g_potr[(size_t)A.kind0 * stride + kk].x, A.g_potb[(size_t)A.kind0 * stride + kk].x);
             }
         }
         if (threadIdx.x == 0) {
@@ -694,6 +714,12 @@ k_tile_pass(TileParams P, TilePassArgs A)
                         const double2 t0 = s_tab[rs];
                         const double val = fma(dk, t0.y - t0.x, t0.x);
                         if (fast) acc0 += val;
+                    } else if (PASS == 3) {
+                        // ER0 += POTR/R ; DEN0 += POTB   (CALEPOT_KERNEL, MD_EAM_ForceTable_GPU.F90:1620-1623)
+                        const double2 t0 = s_tab[rs], t1 = s_tab[rs + 1];
+                        const double er = fma(dk, t1.x - t0.x, t0.x) * y;
+                        const double rb = fma(dk, t1.y - t0.y, t0.y);
+                        if (fast) { acc0 += er; acc1 += rb; }
                     } else {
                         const double2 t0 = s_tab[rs], t1 = s_tab[rs + 1];
                         const double fr = fma(dk, t1.x - t0.x, t0.x);
@@ -716,7 +742,12 @@ k_tile_pass(TileParams P, TilePassArgs A)
                     }
                     const int tj = MT ? (int)styp[s] : 0;
                     const int k0 = MT ? A.kpair[ti + P.ng * tj] : A.kind0, k1 = MT ? A.kpair[tj + P.ng * ti] : A.kind0;
-                    const double f = pair_slow<PASS>(me, pj, A.csi, PASS == 1 ? A.g_potb : A.g_fpotr, A.g_fpotb, A.ntab + 2, k0, k1);
+                    if (PASS == 3) {
+                        const double2 e = pair_slow_epot(me, pj, A.csi, A.g_potr, A.g_potb, A.ntab + 2, k0);
+                        acc0 += e.x; acc1 += e.y;
+                        return;
+                    }
+                    const double f = pair_slow<PASS == 3 ? 1 : PASS>(me, pj, A.csi, PASS == 1 ? A.g_potb : A.g_fpotr, A.g_fpotb, A.ntab + 2, k0, k1);
                     if (PASS == 1) acc0 += f;
                     else {
                         acc0 = fma(f, me.x - pj.x, acc0);
@@ -752,12 +783,23 @@ k_tile_pass(TileParams P, TilePassArgs A)
 #pragma unroll
                 for (int w = 1; w < G; w <<= 1) {
                     acc0 += __shfl_xor_sync(0xffffffffu, acc0, w);
-                    if (PASS == 2) {
-                        acc1 += __shfl_xor_sync(0xffffffffu, acc1, w);
-                        acc2 += __shfl_xor_sync(0xffffffffu, acc2, w);
-                    }
+                    if (PASS >= 2) acc1 += __shfl_xor_sync(0xffffffffu, acc1, w);
+                    if (PASS == 2) acc2 += __shfl_xor_sync(0xffffffffu, acc2, w);
                 }
-                if (PASS == 1) {
+                if (PASS == 3) {
+                    if (have && gl == 0) {
+                        double den0 = 0.0;
+                        if (active) { // :1625-1631; FS twin MD_FS_ForceTable_GPU.F90:1606
+                            if (A.pot_type == MDB_POT_FS) den0 = -sqrt(acc1);
+                            else {
+                                const double sk = acc1 / A.rhod + 1.0;
+                                const int kk = (int)(sk + 0.000001);
+                                den0 = lerp_g(A.g_fembd, A.nembd + 2, A.kembd[ti], kk, sk - (double)kk);
+                            }
+                        }
+                        A.epot[ia] = active ? acc0 + den0 : 0.0;
+                    }
+                } else if (PASS == 1) {
                     if (have && gl == 0) {
                         double den0 = acc0; // kv = 0 for inactive atoms: 0
                         if (A.pot_type == MDB_POT_FS) {
@@ -818,7 +860,8 @@ k_tile_pass(TileParams P, TilePassArgs A)
     if (blockIdx.x == 0 && A.zero_parked) {
         const int n_in = A.counters[CNT_INCELL];
         for (int i = n_in + threadIdx.x; i < P.n; i += NT) {
-            if (PASS == 1) reinterpret_cast<double *>(A.pos + i)[3] = 0.0;
+            if (PASS == 3) A.epot[i] = 0.0;
+            else if (PASS == 1) reinterpret_cast<double *>(A.pos + i)[3] = 0.0;
             else { A.fp[i] = 0.0; A.fp[i + (size_t)P.n] = 0.0; A.fp[i + 2 * (size_t)P.n] = 0.0; }
         }
     }
@@ -852,6 +895,10 @@ int mdb_tiled_plan(mdb_ctx *c)
     const int kz2 = std::max(last_nonzero_row(c->h_fpotr, t.nkind, t.ntab), last_nonzero_row(c->h_fpotb, t.nkind, t.ntab));
     S.r2eff[0] = std::min(t.ru2max, r2_of_row(kz1));
     S.r2eff[1] = std::min(t.ru2max, r2_of_row(kz2));
+    // per-atom energy pass: POTR and POTB; it may scan the class pass 2 scans when its tables end no later than pass 2's
+    const int kz3 = std::max(last_nonzero_row(c->h_potr, t.nkind, t.ntab), kz1);
+    S.r2eff_epot = std::min(t.ru2max, r2_of_row(kz3));
+    S.epot_in_class1 = S.r2eff_epot <= S.r2eff[1];
     const int kru = std::min(t.ntab + 1, (int)(std::sqrt(std::sqrt(t.ru2max)) * csi) + 1);
     S.khi[0] = std::min(kru, kz1 + 2);
     S.khi[1] = std::min(kru, kz2 + 2);
@@ -1019,12 +1066,14 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.pos = c->pos; A.ityp = c->ityp; A.statu = c->statu; A.kvois = c->kvois; A.ncls = S.ncls;
     A.nbl = S.nbl; A.fp = c->fp; A.counters = c->counters; A.desc = (const TileDesc *)S.desc;
     A.g_potb = t.potb; A.g_fpotr = t.fpotr; A.g_fpotb = t.fpotb; A.g_dfembd = t.dfembd;
+    A.g_potr = t.potr; A.g_fembd = t.fembd; A.epot = c->epot;
+    constexpr int PI = (PASS == 3) ? 1 : PASS - 1; // the energy pass shares the plan (window, classes, shared memory) of pass 2
     A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod;
-    A.r2eff = S.r2eff[PASS - 1]; A.kmin = S.kmin[PASS - 1]; A.ktab = S.ktab[PASS - 1];
+    A.r2eff = (PASS == 3) ? S.r2eff_epot : S.r2eff[PI]; A.kmin = S.kmin[PI]; A.ktab = S.ktab[PI];
     A.kind0 = t.kpair[0];
     if (PASS == 1) { A.safe_a = S.safe_d2[0]; A.row_a = 0; A.safe_b = S.safe_d2[2]; A.row_b = 1; }
     else { A.safe_a = S.safe_d2[1]; A.row_a = 1; A.safe_b = -1.0f; A.row_b = 1; }
-    if (!S.use_classes) { A.safe_a = -1.0f; A.safe_b = -1.0f; }
+    if (!S.use_classes || (PASS == 3 && !S.epot_in_class1)) { A.safe_a = -1.0f; A.safe_b = -1.0f; }
     A.fuse = fuse; A.hs2 = hs2; A.xp1 = c->xp1; A.epc = c->epc; A.mass = c->mass;
     A.tile_lo = c->dd_on ? c->dd_info[14] : 0;
     A.tile_hi = c->dd_on ? c->dd_info[15] : S.P.ntiles;
@@ -1035,9 +1084,9 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
     auto kern = k_tile_pass<PASS, G, MT, FUSE, NT>;
-    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_pass[PASS - 1]));
-    ProfScope ps(c, PASS == 1 ? MDB_K_PASS1 : MDB_K_PASS2);
-    kern<<<S.grid, NT, S.smem_pass[PASS - 1], c->stream>>>(S.P, A);
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_pass[PI]));
+    ProfScope ps(c, PASS == 1 ? MDB_K_PASS1 : (PASS == 2 ? MDB_K_PASS2 : MDB_K_EPOT));
+    kern<<<S.grid, NT, S.smem_pass[PI], c->stream>>>(S.P, A);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -1049,6 +1098,8 @@ static int launch_force(mdb_ctx *c, unsigned flags, int fuse, double hs2)
     if ((flags & (MDB_FORCE | MDB_DEN)) && !(flags & MDB_NOPASS1)) rc = launch_pass<1, G, MT, false, NT>(c, 0, 0.0);
     if (rc < 0) return rc;
     if (flags & MDB_FORCE) rc = fuse ? launch_pass<2, G, MT, true, NT>(c, fuse, hs2) : launch_pass<2, G, MT, false, NT>(c, 0, 0.0);
+    if (rc < 0) return rc;
+    if (flags & MDB_EPOT) rc = launch_pass<3, G, MT, false, NT>(c, 0, 0.0);
     return rc;
 }
 

@@ -74,6 +74,7 @@ struct TiledState {
     int ntx = 0, hcap = 0, ocap = 0, wmax = 0, lcap = 0, threads = 0, threads_opt = 768, grid = 0, nbuf = 2, stages_opt = 2;
     int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0};
     double r2eff[2] = {0.0, 0.0};
+    double r2eff_epot = 0.0; bool epot_in_class1 = false; // per-atom energy pass (PASS 3 of the tiled kernel)
     size_t smem_pass[2] = {0, 0}, smem_list = 0;
     double margin = 0.0, margin0 = 0.0; // class margins (length): a class holds while every atom moved < margin/2
     float rc2f[2] = {0.f, 0.f}, safe_d2[3] = {0.f, 0.f, 0.f};
@@ -139,7 +140,7 @@ struct mdb_ctx {
     EpcParams epc;
 
     // ---- host copies of the pair tables (Fortran layout) for planning the tiled path
-    std::vector<double> h_potb, h_fpotr, h_fpotb;
+    std::vector<double> h_potb, h_fpotr, h_fpotb, h_potr;
 
     // ---- tiled fast path
     TiledState tiled;

@@ -44,9 +44,10 @@ __device__ __forceinline__ double blk_max(double v, double *sh)
     if (threadIdx.x == 0) for (int w = 0; w < LT / 32; w++) r = fmax(r, sh[w]);
     return r;
 }
-__device__ __forceinline__ bool lb_last(LbScal *S)
+__device__ __forceinline__ bool lb_last(LbScal *S) // block-uniform: the last block to arrive finishes the reduction in parallel
 {
     __shared__ int is_last;
+    __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const int t = atomicAdd(&S->ticket, 1);
@@ -54,7 +55,19 @@ __device__ __forceinline__ bool lb_last(LbScal *S)
         if (is_last) { S->ticket = 0; __threadfence(); }
     }
     __syncthreads();
-    return is_last != 0 && threadIdx.x == 0;
+    return is_last != 0;
+}
+__device__ __forceinline__ double fin_sum(const double *part, int stride, int off, double *sh)
+{
+    double v = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += LT) v += __ldcg(part + (size_t)k * stride + off);
+    return blk_sum(v, sh);
+}
+__device__ __forceinline__ double fin_max(const double *part, int stride, int off, double *sh)
+{
+    double v = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += LT) v = fmax(v, __ldcg(part + (size_t)k * stride + off));
+    return blk_max(v, sh);
 }
 
 // free components (:213-243) and the unwrapped variable vector X = XP
@@ -120,11 +133,8 @@ __global__ void __launch_bounds__(LT) k_lb_grad(int n, const double *__restrict_
     f = blk_sum(f, sh); gd = blk_sum(gd, sh); gm = blk_max(gm, sh);
     if (threadIdx.x == 0) { part[3 * blockIdx.x] = f; part[3 * blockIdx.x + 1] = gd; part[3 * blockIdx.x + 2] = gm; }
     if (lb_last(S)) {
-        double a = 0.0, b = 0.0, c = 0.0;
-        for (int k = 0; k < (int)gridDim.x; k++) {
-            a += ((volatile double *)part)[3 * k]; b += ((volatile double *)part)[3 * k + 1]; c = fmax(c, ((volatile double *)part)[3 * k + 2]);
-        }
-        S->f = a; S->gd = b; S->gmax = c;
+        const double a = fin_sum(part, 3, 0, sh), b = fin_sum(part, 3, 1, sh), c = fin_max(part, 3, 2, sh);
+        if (threadIdx.x == 0) { S->f = a; S->gd = b; S->gmax = c; }
     }
 }
 // up to 3*col inner products of v with stored vectors: dots[j] = A_j.v, dots[M+j] = B_j.v, dots[2M+j] = C_j.v (null = skip)
@@ -155,9 +165,8 @@ __global__ void __launch_bounds__(LT) k_lb_dots(size_t n3, int col, LbCoef K, co
     if (lb_last(S)) {
         for (int q = 0; q < nacc; q++)
             for (int j = 0; j < col; j++) {
-                double a = 0.0;
-                for (int k = 0; k < (int)gridDim.x; k++) a += ((volatile double *)part)[(size_t)k * 3 * LB_MAXM + q * LB_MAXM + j];
-                S->dots[q * LB_MAXM + j] = a;
+                const double a = fin_sum(part, 3 * LB_MAXM, q * LB_MAXM + j, sh);
+                if (threadIdx.x == 0) S->dots[q * LB_MAXM + j] = a;
             }
     }
 }
@@ -179,9 +188,8 @@ __global__ void __launch_bounds__(LT) k_lb_dir(size_t n3, LbCoef K, const double
     dtd = blk_sum(dtd, sh); gd = blk_sum(gd, sh);
     if (threadIdx.x == 0) { part[2 * blockIdx.x] = dtd; part[2 * blockIdx.x + 1] = gd; }
     if (lb_last(S)) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < (int)gridDim.x; k++) { a += ((volatile double *)part)[2 * k]; b += ((volatile double *)part)[2 * k + 1]; }
-        S->dtd = a; S->gd = b;
+        const double a = fin_sum(part, 2, 0, sh), b = fin_sum(part, 2, 1, sh);
+        if (threadIdx.x == 0) { S->dtd = a; S->gd = b; }
     }
 }
 // new pair (mainlb :822-836): Y = G - R into wy[slot], S = STP*D into ws[slot]; Y.Y
@@ -200,9 +208,8 @@ __global__ void __launch_bounds__(LT) k_lb_pair(size_t n3, double stp, const dou
     rr = blk_sum(rr, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = rr;
     if (lb_last(S)) {
-        double a = 0.0;
-        for (int k = 0; k < (int)gridDim.x; k++) a += ((volatile double *)part)[k];
-        S->rr = a;
+        const double a = fin_sum(part, 1, 0, sh);
+        if (threadIdx.x == 0) S->rr = a;
     }
 }
 __global__ void k_lb_restore(size_t n3, const double *__restrict__ t, const double *__restrict__ r, double *__restrict__ xl, double *__restrict__ g)

@@ -41,10 +41,11 @@ __device__ __forceinline__ double block_max(double v, double *sh)
     __syncthreads();
     return r;
 }
-// true on thread 0 of the last block to arrive
+// true on EVERY thread of the last block to arrive (block-uniform): that block finishes the reduction in parallel
 __device__ __forceinline__ bool last_block(QuenchScal *S)
 {
     __shared__ int is_last;
+    __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const int t = atomicAdd(&S->ticket, 1);
@@ -52,7 +53,22 @@ __device__ __forceinline__ bool last_block(QuenchScal *S)
         if (is_last) { S->ticket = 0; __threadfence(); }
     }
     __syncthreads();
-    return is_last != 0 && threadIdx.x == 0;
+    return is_last != 0;
+}
+// second stage of a reduction, by all threads of one block: partial k of slot `off` sits at part[k*stride + off].
+// Fixed order (thread t takes k = t, t+QT, ...; then the block tree), so results are reproducible run to run.
+// (A single thread walking the partials pays one L2 round trip per partial: ~0.5 ms for 1024 blocks.)
+__device__ __forceinline__ double final_sum(const double *part, int stride, int off, double *sh)
+{
+    double v = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) v += __ldcg(part + (size_t)k * stride + off);
+    return block_sum(v, sh);
+}
+__device__ __forceinline__ double final_max(const double *part, int stride, int off, double *sh)
+{
+    double v = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) v = fmax(v, __ldcg(part + (size_t)k * stride + off));
+    return block_max(v, sh);
 }
 __device__ __forceinline__ void set_scale(QuenchScal *S, double maxmove, double maxdis)
 {
@@ -77,11 +93,12 @@ __global__ void __launch_bounds__(QT) k_sd_first(size_t n3, double alpha0, doubl
     m = block_max(m, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = m;
     if (last_block(S)) {
-        double mm = 0.0;
-        for (int b = 0; b < (int)gridDim.x; b++) mm = fmax(mm, ((volatile double *)part)[b]);
-        set_scale(S, mm, maxdis);
-        S->alpha = alpha0; S->pending = 0; S->iter = 0;
-        if (!(mm > maxdis) && mm <= mindis) { S->done = 1; S->iflag = -1; } // converged at the first step :76-86
+        const double mm = final_max(part, 1, 0, sh);
+        if (threadIdx.x == 0) {
+            set_scale(S, mm, maxdis);
+            S->alpha = alpha0; S->pending = 0; S->iter = 0;
+            if (!(mm > maxdis) && mm <= mindis) { S->done = 1; S->iflag = -1; } // converged at the first step :76-86
+        }
     }
 }
 
@@ -142,12 +159,13 @@ __global__ void __launch_bounds__(QT) k_sd_dots(size_t n3, double alpha0, const 
     b = block_sum(b, sh);
     if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
     if (last_block(S)) {
-        double sa = 0.0, sb = 0.0;
-        for (int k = 0; k < (int)gridDim.x; k++) { sa += ((volatile double *)part)[2 * k]; sb += ((volatile double *)part)[2 * k + 1]; }
-        S->dotdxdf = sa; S->dotdf = sb;
-        double alpha = sa / sb;
-        if (alpha < 0.0) alpha = alpha0;
-        S->alpha = alpha;
+        const double sa = final_sum(part, 2, 0, sh), sb = final_sum(part, 2, 1, sh);
+        if (threadIdx.x == 0) {
+            S->dotdxdf = sa; S->dotdf = sb;
+            double alpha = sa / sb;
+            if (alpha < 0.0) alpha = alpha0;
+            S->alpha = alpha;
+        }
     }
 }
 
@@ -167,10 +185,11 @@ __global__ void __launch_bounds__(QT) k_sd_step(size_t n3, double maxdis, double
     m = block_max(m, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = m;
     if (last_block(S)) {
-        double mm = 0.0;
-        for (int b = 0; b < (int)gridDim.x; b++) mm = fmax(mm, ((volatile double *)part)[b]);
-        set_scale(S, mm, maxdis);
-        S->pending = (mm <= mindis) ? 1 : 0;
+        const double mm = final_max(part, 1, 0, sh);
+        if (threadIdx.x == 0) {
+            set_scale(S, mm, maxdis);
+            S->pending = (mm <= mindis) ? 1 : 0;
+        }
     }
 }
 
@@ -185,10 +204,11 @@ __global__ void __launch_bounds__(QT) k_sd_echeck(int n, double minepot, const d
     m = block_max(m, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = m;
     if (last_block(S)) {
-        double mm = 0.0;
-        for (int b = 0; b < (int)gridDim.x; b++) mm = fmax(mm, ((volatile double *)part)[b]);
-        S->delepot = mm;
-        if (mm <= minepot) { S->done = 1; S->iflag = it; }
+        const double mm = final_max(part, 1, 0, sh);
+        if (threadIdx.x == 0) {
+            S->delepot = mm;
+            if (mm <= minepot) { S->done = 1; S->iflag = it; }
+        }
     }
 }
 
@@ -300,8 +320,8 @@ __global__ void __launch_bounds__(QT) k_q_dot(size_t n3, const double *__restric
     v = block_sum(v, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = v;
     if (last_block(S)) {
-        double sum = 0.0;
-        for (int k = 0; k < (int)gridDim.x; k++) sum += ((volatile double *)part)[k];
+        const double sum = final_sum(part, 1, 0, sh);
+        if (threadIdx.x != 0) return;
         if (mode == QD_MF1) S->mf1 = sum;
         else if (mode == QD_NORM) S->f0norm = sum;
         else {
@@ -370,12 +390,13 @@ __global__ void __launch_bounds__(QT) k_q_cgdir(size_t n3, int first, const doub
     b = block_sum(b, sh);
     if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
     if (last_block(S)) {
-        double sa = 0.0, sb = 0.0;
-        for (int k = 0; k < (int)gridDim.x; k++) { sa += ((volatile double *)part)[2 * k]; sb += ((volatile double *)part)[2 * k + 1]; }
-        S->f0norm = sa; S->pf0 = sb;
-        S->step = maxdis / sqrt(sa);
-        S->coef = S->step;
-        if (sa <= eps) { S->done = 1; S->iflag = it; } // :46-54 (it = -1), :103-105
+        const double sa = final_sum(part, 2, 0, sh), sb = final_sum(part, 2, 1, sh);
+        if (threadIdx.x == 0) {
+            S->f0norm = sa; S->pf0 = sb;
+            S->step = maxdis / sqrt(sa);
+            S->coef = S->step;
+            if (sa <= eps) { S->done = 1; S->iflag = it; } // :46-54 (it = -1), :103-105
+        }
     }
 }
 
@@ -394,9 +415,8 @@ __global__ void __launch_bounds__(QT) k_q_sd1dir(size_t n3, const double *__rest
     b = block_sum(b, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = b;
     if (last_block(S)) {
-        double sb = 0.0;
-        for (int k = 0; k < (int)gridDim.x; k++) sb += ((volatile double *)part)[k];
-        S->pf0 = sb; S->step = maxdis; S->coef = maxdis;
+        const double sb = final_sum(part, 1, 0, sh);
+        if (threadIdx.x == 0) { S->pf0 = sb; S->step = maxdis; S->coef = maxdis; }
     }
 }
 

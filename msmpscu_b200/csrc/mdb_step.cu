@@ -427,20 +427,20 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     CUDA_TRY(c, cudaSetDevice(c->dev));
     if (c->dd_on && !c->tiled.active)
         return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: slab decomposition needs the tiled path");
-    if (c->dd_on && (flags & (MDB_VIRIAL | MDB_EPOT)))
-        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: virial / per-atom energy are not available in slab-decomposed runs yet");
+    if (c->dd_on && (flags & MDB_VIRIAL))
+        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: the virial is not available in slab-decomposed runs yet");
     if (c->tiled.active && !c->list_reordered) {
-        // density + force passes on the tiled path; virial / per-atom energy (output steps only)
-        // run on the generic kernels over the reference-format list the tiled build also emits
-        unsigned fast = flags & (MDB_FORCE | MDB_DEN | MDB_NOPASS1);
-        if (flags & MDB_VIRIAL) fast = 0;
+        // density, force and per-atom energy passes on the tiled path; the virial (output steps only) runs on the generic
+        // kernels over the reference-format list, which is materialised on demand
+        unsigned fast = flags & (MDB_FORCE | MDB_DEN | MDB_NOPASS1 | MDB_EPOT);
+        if (flags & MDB_VIRIAL) fast &= MDB_EPOT;
         if (fast) {
             int rc = mdb_force_tiled(c, fast);
             if (rc < 0) return rc;
         }
         const unsigned rest = flags & ~fast;
-        if (rest & (MDB_VIRIAL | MDB_EPOT)) {
-            int rc = mdb_indi_ensure(c); // the generic kernels walk the reference-format list
+        if (rest & MDB_VIRIAL) {
+            int rc = mdb_indi_ensure(c);
             if (rc < 0) return rc;
             return mdb_force_generic(c, rest & ~MDB_DEN, vtensor);
         }

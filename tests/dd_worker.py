@@ -56,6 +56,10 @@ def main():
         x, y = full.download(f, capi.ORDER_CELL)[a0:a1], ctx.download(f, capi.ORDER_CELL)[a0:a1]
         worst[name] = util.relerr(y, x)
         ok &= worst[name] < tol
+    # per-atom energies of the owned atoms (the tiled energy pass works on owned tiles + current ghost positions)
+    full.force(capi.EPOT); ctx.force(capi.EPOT)
+    worst["epot"] = util.relerr(ctx.download(capi.F_EPOT, capi.ORDER_CELL)[a0:a1], full.download(capi.F_EPOT, capi.ORDER_CELL)[a0:a1])
+    ok &= worst["epot"] < 1e-12
     kf, _ = full.nlist_copyout(capi.ORDER_CELL)
     kd, _ = ctx.nlist_copyout(capi.ORDER_CELL)
     ok &= bool(np.array_equal(kf[a0:a1], kd[a0:a1]))

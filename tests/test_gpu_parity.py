@@ -26,6 +26,7 @@ CASES = {
     "multibox3": lambda: util.bcc_case((7, 7, 7), nbox=3, seed=99),
     "neb_WH": lambda: util.neb_case("react"),
     "bcc_fs_ackland": lambda: util.bcc_fs_case((7, 8, 9)),   # FS_TYPE kernels (MD_FS_ForceTable_GPU.F90), a real FS potential
+    "parrep_replicas": lambda: util.parrep_case(3),          # configs[3] shape: W+H replicas, 1.6 x RU lists, MAXNB 400
     "fcc_cu_setfl": lambda: util.fcc_cu_case((6, 7, 8)),   # imported NIST setfl tables (EAM_NIST library), 134-entry lists
 }
 

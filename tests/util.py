@@ -97,6 +97,22 @@ def fcc_cu_case(ncell=(8, 8, 8), seed=4242, nbox=1, ntab=10000):
     return c
 
 
+def parrep_case(nbox=3, seed=2024):
+    """BASELINE configs[3] shape (examples/PARREP_Test/CtrlFile300K.dat): replicas of the 2000 W + 1 H box (Bonny EAM1) as
+    MULTIBOX, list cutoff 1.6 x RU (about 258 neighbours), MAXNB 400.  Replicas differ by small seeded displacements."""
+    c = neb_case("react")
+    rng = np.random.default_rng(seed)
+    xs = [c.xp + rng.uniform(-0.01, 0.01, size=c.xp.shape) * c.rr for _ in range(nbox)]
+    c.xp = np.concatenate(xs)
+    c.xp1 = np.zeros_like(c.xp)
+    c.ityp = np.tile(c.ityp, nbox)
+    c.statu = np.tile(c.statu, nbox)
+    c.nbox = nbox
+    c.nb_rm = np.full((2, 2), 1.6 * c.ru)
+    c.mxkvois = 400
+    return c
+
+
 def product_tables(c):
     if getattr(c, "setfl", None):
         return forcetable.NIST_Register_Interaction_Table(c.setfl, c.ntab, c.nembd, c.ptype, rmax=c.rmax)
