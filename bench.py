@@ -276,11 +276,12 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     per_launch_bytes = (BYTES_PASS1 if dom == "pass1" else BYTES_PASS2) * n
     achieved = per_launch_bytes / (tms / nl * 1e-3) / 1e9 if nl else 0.0
-    traffic = None
+    traffic, pipes = None, None
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same workload only)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if int(tj.get("atoms", -1)) == n and args.path != "generic":
             traffic = tj.get(dom)
+            pipes = tj.get("pipes", {}).get(dom)
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -291,6 +292,12 @@ def run_ours(args):
             "whole_step": {"achieved": value / world * BYTES_STEP / 1e9, "frac": value / world * BYTES_STEP / 1e9 / peak,
                            "bytes_per_atom_step": BYTES_STEP},
             "per_class_ms_per_md_step": {k: v[1] / (3 * MD_PER_STEP) for k, v in prof.items() if v[0]}}
+    if traffic and nl:
+        # the kernel's OWN stream (16-bit class-limited slot list, positions from L2) and the pipe that actually bounds it
+        roof["own_stream"] = {"dram_bytes_per_atom": traffic / n, "achieved_GBs": traffic / (tms / nl * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": traffic / (tms / nl * 1e-3) / 1e9 / peak}
+    if pipes:
+        roof["limiting_pipe"] = dict(pipes, source="ncu --set full capture committed under profiles/ (not measured in this run)")
 
     line = base_line(args, n)
     line.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "gpu_launches": int(launches),
