@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--nbox", type=int, default=1, help="independent boxes per GPU, concatenated as MULTIBOX (configs[2] family)")
     ap.add_argument("--dd", action="store_true", help="configs[4] family: ONE box of --cells^3 bcc cells cut into z-slabs over the "
                     "ranks (ghost-layer exchange over NCCL), strong scaling; not the default bench line")
+    ap.add_argument("--potential", default="w_marinica", choices=["w_marinica", "cu_setfl"],
+                    help="cu_setfl: fcc Cu with the NIST setfl potential Cu1 imported through mdb_host_setfl_ftable (configs[2] family "
+                         "with a real external EAM table; --cells = fcc cells per edge)")
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "tiled"])
     ap.add_argument("--cpu-cells", type=int, default=32, help="edge of the CPU sample box (32 -> 65 536 atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -59,9 +62,11 @@ def parse():
     return ap.parse_args()
 
 
-def make_case(cells, seed, nbox=1):
+def make_case(cells, seed, nbox=1, potential="w_marinica"):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util
+    if potential == "cu_setfl":
+        return util.fcc_cu_case((cells, cells, cells), seed=seed, nbox=nbox)
     return util.bcc_case((cells, cells, cells), a0=A0, seed=seed, ru_lu=RU_LU, nb_fac=NB_FAC, mxkvois=MXKVOIS,
                          ntab=NTAB, temp=600.0, disp=0.02, nbox=nbox)
 
@@ -176,7 +181,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    c = make_case(args.cells, 12346 + rank, args.nbox)
+    c = make_case(args.cells, 12346 + rank, args.nbox, args.potential)
     n = c.xp.shape[0]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util
@@ -300,6 +305,12 @@ def run_ours(args):
         roof["limiting_pipe"] = dict(pipes, source="ncu --set full capture committed under profiles/ (not measured in this run)")
 
     line = base_line(args, n)
+    if args.potential == "cu_setfl":
+        line["config"]["workload"] = ("configs[2] family with an imported NIST setfl table: %d independent boxes x %d atoms of fcc Cu "
+                                      "(%d^3 cells, Cu1.eam.fs.setfl, force cutoff 6 A, list cutoff 7.2 A), NVT via EPC, per GPU"
+                                      % (args.nbox, n // args.nbox, args.cells))
+        line["config"].update({"cutoff_a0": 6.0 / 3.639087, "list_cutoff_a0": 7.2 / 3.639087})
+        line["roofline_note"] = "canonical byte counts assume K_list = 112 (bcc W); this workload lists 134 neighbours"
     line.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "gpu_launches": int(launches),
                  "e2e": {"value": e2e_val, "unit": "atom-steps/s", "h2d_bytes_per_step": 2 * 24 * n,
                          "d2h_bytes_per_step": 3 * 24 * n, "ms_per_step": ms_e2e / max(3, args.steps // 4)},

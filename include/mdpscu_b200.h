@@ -344,6 +344,13 @@ int mdb_host_setfl_info(const char *path, int *nelem, int *nrho, int *nr, double
 int mdb_host_setfl_ftable(const char *path, int ntab, int nembd, double rmax, int *nkind,
                           double *potr, double *fpotr, double *potb, double *fpotb, double *fembd, double *dfembd,
                           double *csi, double *rhod, double *rmax_out);
+/* the ".lspt" twin (Register_ForceTableProc_SPT, Potentials/EAM_NIST/Filedatas_Func_Lspt.F90:79-541): an index file naming one
+ * two-column (x, f) file per function -- F(rho), rho(r) per element ("NA" = none), V(r) per pair.  Restated as written,
+ * including the reader's use of the FIRST file name of a VR line for every pair of that line (:225). */
+int mdb_host_lspt_info(const char *path, int *nelem, double *cutoff_cm, double *rhomx, char *names, int names_stride);
+int mdb_host_lspt_ftable(const char *path, int ntab, int nembd, double rmax, int *nkind,
+                         double *potr, double *fpotr, double *potb, double *fpotb, double *fembd, double *dfembd,
+                         double *csi, double *rhod, double *rmax_out);
 int mdb_host_ftable_export(const char *fname, int pot_type, int nkind, const int *ids, int ntab, double csi,
                            const double *potr, const double *fpotr, const double *potb, const double *fpotb,
                            int nkind1, const int *ids1, int nembd, double rhod, const double *fembd, const double *dfembd);

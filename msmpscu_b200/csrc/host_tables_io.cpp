@@ -1,4 +1,4 @@
-// host_tables_io.cpp -- external force tables (no CUDA): the NIST "setfl" importer and the
+// host_tables_io.cpp -- external force tables (no CUDA): the NIST "setfl" and "lspt" importers and the
 // MDPSCU .pair/.embd table files.
 //
 // Reference behaviour restated here (paths relative to MDLIB/sor):
@@ -115,6 +115,7 @@ struct SetflElement {
     int z = 0;
     double mass = 0.0, alat = 0.0;
     bool frho_zero = false; // m_FRHO_ZERO, Filedatas_Func_Setfl.F90:209
+    bool rho_na = false;    // lspt: RHO_R file "NA" -> no density from this element
     Spline frho, rhor;
     std::vector<Spline> vr; // V_r(J), J <= I
 };
@@ -122,6 +123,8 @@ struct SetflElement {
 struct Setfl {
     int ne = 0, nrho = 0, nr = 0;
     double drho = 0.0, dr = 0.0, cutoff = 0.0; // Angstrom
+    double rhomx = 0.0;                        // FTable%RHOMX the importer sets
+    bool v_is_rv = true;                       // setfl files hold r*V(r); lspt files hold V(r)
     std::vector<SetflElement> el;
 };
 
@@ -163,6 +166,7 @@ int load_setfl(const char *path, Setfl &s)
     }
     if (!(in >> s.nrho >> s.drho >> s.nr >> s.dr >> s.cutoff)) return MDB_ERR_ARG;
     if (s.nrho < 4 || s.nr < 4 || !(s.cutoff > 0.0)) return MDB_ERR_ARG;
+    s.rhomx = (double)s.nrho * s.drho; // :178
     std::vector<double> rho(s.nrho), r(s.nr);
     for (int i = 0; i < s.nrho; ++i) rho[i] = (double)i * s.drho; // :181-183
     const double minr = s.cutoff / (double)s.nr;                    // :184-187 (cutoff/Nr, not the file's dr)
@@ -192,6 +196,126 @@ int load_setfl(const char *path, Setfl &s)
     return MDB_OK;
 }
 
+void trim(std::string &s)
+{
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    s = (a == std::string::npos) ? std::string() : s.substr(a, b - a + 1);
+}
+
+// ---- "lspt": an index file naming one two-column (x, f) file per function.  Potentials/EAM_NIST/Filedatas_Func_Lspt.F90:79-300.
+std::vector<std::string> quoted(const std::string &line)
+{
+    std::vector<std::string> out;
+    size_t i = 0;
+    while ((i = line.find('"', i)) != std::string::npos) {
+        const size_t j = line.find('"', i + 1);
+        if (j == std::string::npos) break;
+        std::string t = line.substr(i + 1, j - i - 1);
+        trim(t);
+        out.push_back(t);
+        i = j + 1;
+    }
+    return out;
+}
+bool next_line(std::istream &in, std::string &line, char comment)
+{
+    while (std::getline(in, line)) {
+        std::string t = line;
+        trim(t);
+        if (t.empty() || t[0] == comment) continue;
+        line = t;
+        return true;
+    }
+    return false;
+}
+bool is_na(std::string s)
+{
+    for (char &ch : s) ch = (char)std::toupper((unsigned char)ch);
+    return s == "NA";
+}
+bool read_spt(const std::string &path, Spline &sp)
+{
+    std::ifstream in(path);
+    if (!in) return false;
+    std::string line;
+    sp.x.clear(); sp.y.clear();
+    while (std::getline(in, line)) {
+        std::string t = line;
+        trim(t);
+        if (t.empty() || t[0] == '#') continue;
+        std::istringstream ls(t);
+        double a, b;
+        if (!(ls >> a >> b)) return false;
+        sp.x.push_back(a); sp.y.push_back(b);
+    }
+    if (sp.x.size() < 4) return false;
+    sp.fit(true);
+    return true;
+}
+int load_lspt(const char *path, Setfl &s)
+{
+    std::ifstream in(path);
+    if (!in) return MDB_ERR_ARG;
+    std::string dir(path);
+    const size_t slash = dir.find_last_of("/\\");
+    dir = (slash == std::string::npos) ? std::string() : dir.substr(0, slash + 1);
+    std::string line;
+    if (!next_line(in, line, '!')) return MDB_ERR_ARG;
+    {
+        std::string kw = line.substr(0, 5);
+        for (char &ch : kw) ch = (char)std::toupper((unsigned char)ch);
+        if (kw != "&LSPT") return MDB_ERR_ARG; // :105-107
+    }
+    if (!next_line(in, line, '!')) return MDB_ERR_ARG;
+    {
+        size_t i = line.find_first_of("0123456789");
+        if (i == std::string::npos) return MDB_ERR_ARG;
+        s.ne = std::atoi(line.c_str() + i);
+        if (s.ne < 1 || s.ne > MDB_MXGROUP) return MDB_ERR_ARG;
+    }
+    if (!next_line(in, line, '!')) return MDB_ERR_ARG;
+    const std::vector<std::string> names = quoted(line);
+    if ((int)names.size() != s.ne) return MDB_ERR_ARG; // :119-123
+    s.el.resize(s.ne);
+    s.v_is_rv = false;
+    double rhomax = 0.0, rmax = 0.0;
+    for (int i = 0; i < s.ne; ++i) {
+        SetflElement &e = s.el[i];
+        e.name = names[i];
+        if (!next_line(in, line, '!')) return MDB_ERR_ARG;
+        std::vector<std::string> q = quoted(line);
+        if (q.empty()) return MDB_ERR_ARG;
+        if (is_na(q[0])) e.frho_zero = true; // :135-137
+        else {
+            if (!read_spt(dir + q[0], e.frho)) return MDB_ERR_ARG;
+            double hi = e.frho.x[0];
+            for (double v : e.frho.x) hi = v > hi ? v : hi;
+            rhomax = hi > rhomax ? hi : rhomax; // :160
+        }
+        if (!next_line(in, line, '!')) return MDB_ERR_ARG;
+        q = quoted(line);
+        if (q.empty()) return MDB_ERR_ARG;
+        if (is_na(q[0])) e.rho_na = true;
+        else if (!read_spt(dir + q[0], e.rhor)) return MDB_ERR_ARG;
+    }
+    for (int i = 0; i < s.ne; ++i) {
+        if (!next_line(in, line, '!')) return MDB_ERR_ARG;
+        const std::vector<std::string> q = quoted(line);
+        if ((int)q.size() != i + 1) return MDB_ERR_ARG;
+        s.el[i].vr.resize(i + 1);
+        for (int j = 0; j <= i; ++j) {
+            // the reference opens SUBSTR(1) for every J (:225): all V(I,J) of a line come from its FIRST file
+            if (!read_spt(dir + q[0], s.el[i].vr[j])) return MDB_ERR_ARG;
+            double hi = s.el[i].vr[j].x[0];
+            for (double v : s.el[i].vr[j].x) hi = v > hi ? v : hi;
+            rmax = hi > rmax ? hi : rmax; // :243
+        }
+    }
+    s.rhomx = rhomax;   // :250
+    s.cutoff = rmax;    // FTable%RMAX = RMAX*CP_A2CM :251
+    return MDB_OK;
+}
+
 // value and derivative with the reference's range rule: inside [x0, xn] the spline; below x0 the end value with
 // zero slope; above xn zero -- or, for the embedding function, the end value (Filedatas_Func_Setfl.F90:334-352, :418-440)
 void ranged(const Spline &sp, double t, bool hold_above, double &f, double &df)
@@ -204,11 +328,6 @@ void ranged(const Spline &sp, double t, bool hold_above, double &f, double &df)
     f = 0.0; df = 0.0;
 }
 
-void trim(std::string &s)
-{
-    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
-    s = (a == std::string::npos) ? std::string() : s.substr(a, b - a + 1);
-}
 
 struct TableFile {
     std::string pottype;
@@ -285,7 +404,7 @@ extern "C" int mdb_host_setfl_info(const char *path, int *nelem, int *nrho, int 
     if (nrho) *nrho = s.nrho;
     if (nr) *nr = s.nr;
     if (cutoff_cm) *cutoff_cm = s.cutoff * kA2Cm;      // FTable%RMAX  :179
-    if (rhomx) *rhomx = (double)s.nrho * s.drho;       // FTable%RHOMX :178
+    if (rhomx) *rhomx = s.rhomx;                       // FTable%RHOMX :178
     for (int i = 0; i < s.ne; ++i) {
         if (names && names_stride > 1) {
             std::strncpy(names + (size_t)i * names_stride, s.el[i].name.c_str(), names_stride - 1);
@@ -298,31 +417,33 @@ extern "C" int mdb_host_setfl_info(const char *path, int *nelem, int *nrho, int 
     return MDB_OK;
 }
 
-extern "C" int mdb_host_setfl_ftable(const char *path, int ntab, int nembd, double rmax, int *nkind_out, double *potr, double *fpotr,
-                                     double *potb, double *fpotb, double *fembd, double *dfembd, double *csi_out, double *rhod_out,
-                                     double *rmax_out)
+namespace {
+// Generate_NIST_ForceTalbe (NIST_ForceTable.F90:332-398) over the spline callbacks of either importer
+int nist_tables(const Setfl &s, int ntab, int nembd, double rmax, int *nkind_out, double *potr, double *fpotr, double *potb,
+                double *fpotb, double *fembd, double *dfembd, double *csi_out, double *rhod_out, double *rmax_out)
 {
-    if (!path || ntab < 2 || nembd < 2 || !potr || !fpotr || !potb || !fpotb || !fembd || !dfembd) return MDB_ERR_ARG;
-    Setfl s;
-    const int rc = load_setfl(path, s);
-    if (rc != MDB_OK) return rc;
     const int ne = s.ne, nkind = ne * ne;
-    if (!(rmax > 0.0)) rmax = s.cutoff * kA2Cm; // the importer overrides the run's range with the file's cutoff
-    const double csi = (double)ntab / std::sqrt(rmax), csiv = 1.0 / csi; // NIST_ForceTable.F90:352-354
-    const double rhod = ((double)s.nrho * s.drho) / (double)nembd;       // :339, restored at :381-384
+    if (!(rmax > 0.0)) rmax = s.cutoff * kA2Cm; // the importer overrides the run's range with the file's
+    const double csi = (double)ntab / std::sqrt(rmax), csiv = 1.0 / csi; // :352-354
+    const double rhod = s.rhomx / (double)nembd;                         // :339, restored at :381-384
     for (int it = 1; it <= nkind; ++it) {
         int i = (it - 1) / ne + 1, j = it - (i - 1) * ne; // table id it = "I <- J"
         const int iv = (j > i) ? j : i, jv = (j > i) ? i : j;
         const Spline &v = s.el[iv - 1].vr[jv - 1];
-        const Spline &q = s.el[j - 1].rhor; // density contributed by the neighbour element J (:369-392)
-        const bool rho_off = s.el[i - 1].frho_zero;
+        const Spline &q = s.el[j - 1].rhor; // density contributed by the neighbour element J
+        const bool rho_off = s.el[i - 1].frho_zero || s.el[j - 1].rho_na;
         const int k = it - 1; // FPAIR(IFORCE) = IFORCE (:369-372): kind index = id
         for (int n = 1; n <= ntab; ++n) {
             const double t = (double)n * csiv, r = t * t, ra = r * kCm2A;
-            double f, df;
+            double f, df, pot, fpot;
             ranged(v, ra, false, f, df);
-            double pot = f / ra;           // NN_Spline :443-452 (the file holds r*V)
-            double fpot = (df - pot) / ra;
+            if (s.v_is_rv) { // setfl NN_Spline (Filedatas_Func_Setfl.F90:443-452): the file holds r*V
+                pot = f / ra;
+                fpot = (df - pot) / ra;
+            } else {         // lspt NN_Spline (Filedatas_Func_Lspt.F90:488-496): the file holds V
+                pot = f;
+                fpot = df;
+            }
             pot = 0.5 * pot * kEvErg;
             fpot = -1.0 * fpot * kEvErg * kCm2A;
             const size_t o = (size_t)(n - 1) * nkind + k;
@@ -330,16 +451,16 @@ extern "C" int mdb_host_setfl_ftable(const char *path, int ntab, int nembd, doub
             fpotr[o] = fpot * r;
             if (rho_off) {
                 potb[o] = 0.0;
-                fpotb[o] = -1.0 * 0.0 * kCm2A;
+                fpotb[o] = 0.0;
             } else {
                 ranged(q, ra, false, f, df);
                 potb[o] = f;
-                fpotb[o] = -1.0 * df * kCm2A; // RHO_Spline :454-462
+                fpotb[o] = -1.0 * df * kCm2A; // RHO_Spline
             }
         }
         for (int n = 1; n <= nembd; ++n) { // Create_EMBDFUNTable :1043-1047 through Frho_Spline / EMBED_Spline
             const size_t o = (size_t)(n - 1) * nkind + k;
-            if (i == j) {
+            if (i == j && !s.el[i - 1].frho.x.empty()) { // lspt "NA": no embedding function (Frho_Spline returns 0)
                 double f = 0.0, df = 0.0;
                 ranged(s.el[i - 1].frho, (double)(n - 1) * rhod, true, f, df);
                 fembd[o] = f * kEvErg;
@@ -355,6 +476,45 @@ extern "C" int mdb_host_setfl_ftable(const char *path, int ntab, int nembd, doub
     if (rhod_out) *rhod_out = (rhod <= 1.0e-64) ? 1.0 : rhod;
     if (rmax_out) *rmax_out = rmax;
     return MDB_OK;
+}
+} // namespace
+
+extern "C" int mdb_host_setfl_ftable(const char *path, int ntab, int nembd, double rmax, int *nkind_out, double *potr, double *fpotr,
+                                     double *potb, double *fpotb, double *fembd, double *dfembd, double *csi_out, double *rhod_out,
+                                     double *rmax_out)
+{
+    if (!path || ntab < 2 || nembd < 2 || !potr || !fpotr || !potb || !fpotb || !fembd || !dfembd) return MDB_ERR_ARG;
+    Setfl s;
+    const int rc = load_setfl(path, s);
+    if (rc != MDB_OK) return rc;
+    return nist_tables(s, ntab, nembd, rmax, nkind_out, potr, fpotr, potb, fpotb, fembd, dfembd, csi_out, rhod_out, rmax_out);
+}
+
+// Register_ForceTableProc_SPT + Generate_NIST_ForceTalbe for a ".lspt" library (Filedatas_Func_Lspt.F90:79-300, 488-541)
+extern "C" int mdb_host_lspt_info(const char *path, int *nelem, double *cutoff_cm, double *rhomx, char *names, int names_stride)
+{
+    if (!path) return MDB_ERR_ARG;
+    Setfl s;
+    const int rc = load_lspt(path, s);
+    if (rc != MDB_OK) return rc;
+    if (nelem) *nelem = s.ne;
+    if (cutoff_cm) *cutoff_cm = s.cutoff * kA2Cm;
+    if (rhomx) *rhomx = s.rhomx;
+    for (int i = 0; i < s.ne && names && names_stride > 1; ++i) {
+        std::strncpy(names + (size_t)i * names_stride, s.el[i].name.c_str(), names_stride - 1);
+        names[(size_t)i * names_stride + names_stride - 1] = '\0';
+    }
+    return MDB_OK;
+}
+extern "C" int mdb_host_lspt_ftable(const char *path, int ntab, int nembd, double rmax, int *nkind_out, double *potr, double *fpotr,
+                                    double *potb, double *fpotb, double *fembd, double *dfembd, double *csi_out, double *rhod_out,
+                                    double *rmax_out)
+{
+    if (!path || ntab < 2 || nembd < 2 || !potr || !fpotr || !potb || !fpotb || !fembd || !dfembd) return MDB_ERR_ARG;
+    Setfl s;
+    const int rc = load_lspt(path, s);
+    if (rc != MDB_OK) return rc;
+    return nist_tables(s, ntab, nembd, rmax, nkind_out, potr, fpotr, potb, fpotb, fembd, dfembd, csi_out, rhod_out, rmax_out);
 }
 
 // Export_ForceTable, Common/MD_TypeDef_ForceTable.F90:1315-1459.  ids[k] = FPAIR(k) of table row k (written in increasing

@@ -91,19 +91,32 @@ def setfl_info(path):
                 cutoff=cut.value, rhomx=rhomx.value)
 
 
+def lspt_info(path):
+    lib = capi.load()
+    ne, cut, rhomx = C.c_int(), C.c_double(), C.c_double()
+    names = C.create_string_buffer(16 * capi.MXGROUP)
+    rc = lib.mdb_host_lspt_info(os.fsencode(path), C.byref(ne), C.byref(cut), C.byref(rhomx), names, 16)
+    if rc != 0:
+        raise capi.MDBError(rc, "mdb_host_lspt_info: cannot read %r" % (path,))
+    el = [names.raw[16 * i:16 * i + 16].split(b"\0")[0].decode() for i in range(ne.value)]
+    return dict(elements=el, cutoff=cut.value, rhomx=rhomx.value)
+
+
 def NIST_Register_Interaction_Table(path, ntab, nembd, ptype=None, rmax=0.0):
-    """NIST_Register_Interaction_Table0 for a ".setfl" library (Potentials/EAM_NIST/NIST_ForceTable.F90:100-137,
+    """NIST_Register_Interaction_Table0 for a ".setfl" or ".lspt" library (Potentials/EAM_NIST/NIST_ForceTable.F90:100-137,
     332-398): tables for all NE*NE ids "I <- J" (id = (I-1)*NE + J, kind index = id), range and RHOMX from the
     file.  ptype defaults to the natural one, PTYPE(I,J) = (I-1)*NE + J."""
     lib = capi.load()
-    info = setfl_info(path)
+    is_lspt = str(path).lower().endswith(".lspt")   # Get_FileExtent dispatch, NIST_ForceTable.F90:111-125
+    info = lspt_info(path) if is_lspt else setfl_info(path)
     ne = len(info["elements"])
     nk = ne * ne
     t = MDForceTable("EAM_TYPE")
     t.potr, t.fpotr, t.potb, t.fpotb = (np.zeros(nk * ntab) for _ in range(4))
     t.fembd, t.dfembd = np.zeros(nk * nembd), np.zeros(nk * nembd)
     nkind, csi, rhod, rmax_out = C.c_int(), C.c_double(), C.c_double(), C.c_double()
-    rc = lib.mdb_host_setfl_ftable(os.fsencode(path), int(ntab), int(nembd), float(rmax), C.byref(nkind),
+    fn = lib.mdb_host_lspt_ftable if is_lspt else lib.mdb_host_setfl_ftable
+    rc = fn(os.fsencode(path), int(ntab), int(nembd), float(rmax), C.byref(nkind),
                                    capi.dp(t.potr), capi.dp(t.fpotr), capi.dp(t.potb), capi.dp(t.fpotb),
                                    capi.dp(t.fembd), capi.dp(t.dfembd), C.byref(csi), C.byref(rhod), C.byref(rmax_out))
     if rc != 0:

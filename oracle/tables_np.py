@@ -103,3 +103,27 @@ def export_columns(t, fs=False):
     pair = np.stack([t["potr"] * 2.0 * ergev * CM2A, t["fpotr"] * ergev, t["potb"] * rhounit, t["fpotb"] * rhounit * A2CM], axis=-1)
     embd = np.stack([t["fembd"] * ergev, t["dfembd"]], axis=-1)
     return pair, embd
+
+
+def lspt_tables_W(dirpath, ntab, nembd):
+    """The one-element lspt library of the fixture (F_W, rhoW, pWW): Filedatas_Func_Lspt.F90:79-300 (reader), :488-541
+    (NN_Spline: the files hold V, not r*V), NIST_ForceTable.F90:332-398.  RHOMX = max rho of F_W, Rmax = max r of pWW."""
+    import os
+    ld = lambda fn: np.loadtxt(os.path.join(dirpath, fn))
+    fw, rw, vw = ld("WHHe-EAM1-F_W.spt"), ld("WHHe-EAM1-rhoW.spt"), ld("WHHe-EAM1-pWW.spt")
+    rmax = vw[:, 0].max() * A2CM
+    rhomx = fw[:, 0].max()
+    csi = ntab / np.sqrt(rmax)
+    r = (np.arange(1, ntab + 1) / csi) ** 2
+    ra = r * CM2A
+    spv = CubicSpline(vw[:, 0], vw[:, 1], bc_type="natural")
+    f, df = _ranged(spv, vw[0, 0], vw[-1, 0], ra, False)
+    out = dict(potr=(0.5 * f * EVERG * r)[None], fpotr=(-1.0 * df * EVERG * CM2A * r)[None])
+    spq = CubicSpline(rw[:, 0], rw[:, 1], bc_type="natural")
+    f, df = _ranged(spq, rw[0, 0], rw[-1, 0], ra, False)
+    out.update(potb=f[None], fpotb=(-1.0 * df * CM2A)[None])
+    rhod = rhomx / nembd
+    spf = CubicSpline(fw[:, 0], fw[:, 1], bc_type="natural")
+    f, df = _ranged(spf, fw[0, 0], fw[-1, 0], np.arange(nembd) * rhod, True)
+    out.update(fembd=(f * EVERG)[None], dfembd=(df * EVERG)[None], csi=csi, rhod=rhod, rmax=rmax)
+    return out

@@ -18,6 +18,9 @@ Outputs (small, committed):
   wangjun_fs_ww_pair_rows.npz
       sampled rows of examples/use_ForceTableGen/EM_TB_WANGJUN_W-HE_2010.pair (FS_TYPE export, Rmax = 10 A): the four
       columns of table id 1 = W-W (Ackland, Thetford): r*V, -r dV/dr, RHO [eV^2], -dRHO/dr.
+  whhe_eam1_lspt_W.tar.xz, whhe_eam1_lspt_embd_rows.npz
+      the tungsten functions of examples/NIST_Potentials/WHHe_EAM1_LSPT (F_W, rhoW, pWW .spt data files, verbatim, with a
+      one-element index file) and sampled rows (RHO, F1, dF1/dRHO) of the reference's export WHHe_EAM1.lspt.embd.
   Cu1.eam.fs.setfl.xz
       examples/NIST_Potentials/Cu_EAM/Cu1.eam.fs.setfl (public NIST potential data file, an input), xz-compressed.
   cu1_setfl_table_rows.npz
@@ -112,6 +115,28 @@ def main():
     sel = np.unique(np.concatenate([np.arange(0, 32), np.arange(32, 10000, 19), np.arange(5200, 5260), np.arange(6600, 6660)]))
     np.savez_compressed(os.path.join(HERE, "wangjun_fs_ww_pair_rows.npz"), index=pr[sel, 0].astype(np.int32), r=pr[sel, 1],
                         pair=pr[sel, 2:6])
+    # lspt library: the W part of examples/NIST_Potentials/WHHe_EAM1_LSPT (index reduced to one element, the three data
+    # files it names verbatim) and sampled rows of the reference's exported embedding table for the full library
+    import io
+    import tarfile
+    ls = os.path.join(REF, "examples", "NIST_Potentials", "WHHe_EAM1_LSPT")
+    index = ('!  W part of WHHe_EAM1.lspt (examples/NIST_Potentials/WHHe_EAM1_LSPT), same keywords\n'
+             '&LSPT ----------------------------\n'
+             '   NGROUP  the number of groups =  1\n'
+             '   ATOMSYMBOL  group#1 = "W"\n'
+             '   F_RHO #1 filename =     "WHHe-EAM1-F_W.spt"\n'
+             '   RHO_R #1 filename =     "WHHe-EAM1-rhoW.spt"\n'
+             '   VR  (1,1)  filename  =  "WHHe-EAM1-pWW.spt"\n')
+    with tarfile.open(os.path.join(HERE, "whhe_eam1_lspt_W.tar.xz"), "w:xz", preset=9) as tf:
+        ti = tarfile.TarInfo("W_EAM1.lspt"); data = index.encode(); ti.size = len(data)
+        tf.addfile(ti, io.BytesIO(data))
+        for fn in ("WHHe-EAM1-F_W.spt", "WHHe-EAM1-rhoW.spt", "WHHe-EAM1-pWW.spt"):
+            tf.add(os.path.join(ls, fn), arcname=fn)
+    em = rows_of(os.path.join(ls, "WHHe_EAM1.lspt.embd"), 20)
+    assert em.shape[0] == 10000
+    sel = np.unique(np.concatenate([np.arange(0, 64), np.arange(64, 10000, 23), np.arange(9950, 10000)]))
+    np.savez_compressed(os.path.join(HERE, "whhe_eam1_lspt_embd_rows.npz"), index=em[sel, 0].astype(np.int32), rho=em[sel, 1],
+                        f=em[sel, 2], df=em[sel, 3])
     print("fixtures written to", HERE)
 
 

@@ -138,3 +138,34 @@ def test_fs_ackland_tables_match_reference_export(oracle):
             assert np.all(np.abs(cols[sel, c] - g["pair"][:, c]) <= PRINT_PAIR * np.abs(g["pair"][:, c]) + 1e-30), c
     assert np.max(np.abs(tp.potr - to.potr)) <= 1e-13 * np.max(np.abs(to.potr))
     assert np.max(np.abs(tp.fpotb - to.fpotb)) <= 1e-13 * np.max(np.abs(to.fpotb))
+
+
+@pytest.fixture(scope="module")
+def lspt_dir(tmp_path_factory):
+    import tarfile
+    d = tmp_path_factory.mktemp("lspt")
+    with tarfile.open(os.path.join(util.GOLD, "whhe_eam1_lspt_W.tar.xz"), "r:xz") as tf:
+        tf.extractall(d, filter="data")
+    return str(d)
+
+
+def test_lspt_import_matches_reference_embd_and_oracle(lspt_dir):
+    """The ".lspt" importer (Filedatas_Func_Lspt.F90) on the tungsten functions of examples/NIST_Potentials/WHHe_EAM1_LSPT:
+    the embedding table equals the reference's exported WHHe_EAM1.lspt.embd (id 1, 9 digits) for the product and the
+    NumPy/SciPy restatement, and all six tables of the two implementations agree far below print precision."""
+    g = np.load(os.path.join(util.GOLD, "whhe_eam1_lspt_embd_rows.npz"))
+    path = os.path.join(lspt_dir, "W_EAM1.lspt")
+    info = forcetable.lspt_info(path)
+    assert info["elements"] == ["W"] and abs(info["rhomx"] - 10.0) < 1e-12 and abs(info["cutoff"] - 5.4604375e-8) < 1e-20
+    t = forcetable.NIST_Register_Interaction_Table(path, 10000, 10000)
+    o = tables_np.lspt_tables_W(lspt_dir, 10000, 10000)
+    ergev = 1.0 / 1.60219e-12
+    sel = g["index"] - 1
+    for fe, dfe, rhod in ((t.fembd, t.dfembd, t.rhod), (o["fembd"][0], o["dfembd"][0], o["rhod"])):
+        assert np.allclose(np.arange(10000)[sel] * rhod, g["rho"], rtol=PRINT_EMBD, atol=1e-300)
+        assert np.all(np.abs(fe[sel] * ergev - g["f"]) <= PRINT_EMBD * np.abs(g["f"]) + 1e-40)
+        assert np.all(np.abs(dfe[sel] - g["df"]) <= PRINT_EMBD * np.abs(g["df"]) + 1e-40)
+    for name in ("potr", "fpotr", "potb", "fpotb", "fembd", "dfembd"):
+        a, b = getattr(t, name), o[name][0]
+        assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b)), name
+    assert t.csi == o["csi"] and t.rhod == o["rhod"]
