@@ -23,17 +23,3 @@ def test_slab_run_matches_single_gpu(world):
     print(out.stdout[-3000:], out.stderr[-3000:])
     assert out.returncode == 0
     assert "DD_RESULT PASS" in out.stdout
-
-
-def test_slab_layers_cover_the_box():
-    from msmpscu_b200.domain import slab_layers
-    for ncz in (3, 7, 35, 87):
-        for world in (1, 2, 3, 4, 8):
-            if world > ncz:
-                continue
-            got = []
-            for r in range(world):
-                z0, z1 = slab_layers(ncz, world, r)
-                assert z1 > z0
-                got += list(range(z0, z1))
-            assert got == list(range(ncz))

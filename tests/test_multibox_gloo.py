@@ -64,3 +64,18 @@ def test_two_ranks_gather_per_box_scalars():
         assert tot == nbox
         assert mx == 4  # rank 1 starts at box ceil(7/2) = 4
     assert sorted((r[4], r[5]) for r in res) == [(0, 4), (4, 3)]
+
+
+def test_slab_layers_cover_the_box():
+    """host-side plan of the slab decomposition (msmpscu_b200/domain.py): every z-layer of cells has exactly one owner"""
+    from msmpscu_b200.domain import slab_layers
+    for ncz in (3, 7, 35, 87):
+        for world in (1, 2, 3, 4, 8):
+            if world > ncz:
+                continue
+            got = []
+            for r in range(world):
+                z0, z1 = slab_layers(ncz, world, r)
+                assert z1 > z0
+                got += list(range(z0, z1))
+            assert got == list(range(ncz))
