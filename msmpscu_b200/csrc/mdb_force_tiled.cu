@@ -180,6 +180,23 @@ __device__ __forceinline__ unsigned long long f2_sq(unsigned long long a)
 }
 __device__ __forceinline__ float f2_lo(unsigned long long a) { return __uint_as_float((unsigned)a); }
 __device__ __forceinline__ float f2_hi(unsigned long long a) { return __uint_as_float((unsigned)(a >> 32)); }
+// Push of slot + 2-bit distance class onto a shared-memory column, with the membership test (r2 <= rm, and for the centre
+// row: slot != own slot) and the class tests evaluated INSIDE the asm: the predicates never take a round trip through
+// general registers (the C++ form costs a SEL and a second SETP per candidate).
+__device__ __forceinline__ void push_if_in(unsigned &addr, unsigned slot, float r2, float rm, float rc0, float rc1)
+{
+    asm volatile("{\n.reg .pred q, a, b;\n.reg .b32 e;\nsetp.le.f32 q, %2, %3;\nsetp.gt.f32 a, %2, %4;\nsetp.gt.f32 b, %2, %5;\n"
+                 "mov.b32 e, %1;\n@a add.u32 e, e, 0x4000;\n@b add.u32 e, e, 0x4000;\n"
+                 "@q st.shared.u16 [%0], e;\n@q add.u32 %0, %0, 64;\n}\n"
+                 : "+r"(addr) : "r"(slot), "f"(r2), "f"(rm), "f"(rc0), "f"(rc1) : "memory");
+}
+__device__ __forceinline__ void push_if_in_notself(unsigned &addr, unsigned slot, float r2, float rm, float rc0, float rc1, unsigned self)
+{
+    asm volatile("{\n.reg .pred q, a, b;\n.reg .b32 e;\nsetp.le.f32 q, %2, %3;\nsetp.ne.and.u32 q, %1, %6, q;\nsetp.gt.f32 a, %2, %4;\n"
+                 "setp.gt.f32 b, %2, %5;\nmov.b32 e, %1;\n@a add.u32 e, e, 0x4000;\n@b add.u32 e, e, 0x4000;\n"
+                 "@q st.shared.u16 [%0], e;\n@q add.u32 %0, %0, 64;\n}\n"
+                 : "+r"(addr) : "r"(slot), "f"(r2), "f"(rm), "f"(rc0), "f"(rc1), "r"(self) : "memory");
+}
 // predicated push of a 16-bit entry onto a shared-memory column (32-bit shared address, row stride 64 bytes)
 __device__ __forceinline__ void sts16_push(unsigned &addr, unsigned val, bool p)
 {
@@ -253,6 +270,11 @@ k_tile_nlist(TileParams P, TileListArgs A)
         // CAP: the list may fill up inside this range
         auto accept = [&](auto self_tag, auto cap_tag, const int s, const float r2, const float rm) {
             constexpr bool SELF = decltype(self_tag)::value, CAP = decltype(cap_tag)::value;
+            if (!CAP) {                                                     // the common case: room for the whole range
+                if (SELF) push_if_in_notself(pa, (unsigned)s, r2, rm, rc0, rc1, (unsigned)myslot);
+                else push_if_in(pa, (unsigned)s, r2, rm, rc0, rc1);
+                return;
+            }
             bool hit = r2 <= rm;                                            // :1123
             if (SELF) hit = hit && (s != myslot);
             const unsigned e = (unsigned)s + ((r2 > rc0) ? 0x4000u : 0u) + ((r2 > rc1) ? 0x4000u : 0u);
