@@ -351,6 +351,11 @@ int mdb_host_lspt_info(const char *path, int *nelem, double *cutoff_cm, double *
 int mdb_host_lspt_ftable(const char *path, int ntab, int nembd, double rmax, int *nkind,
                          double *potr, double *fpotr, double *potb, double *fpotb, double *fembd, double *dfembd,
                          double *csi, double *rhod, double *rmax_out);
+/* the ".moldy" twin (Register_ForceTableProc_Moldy, Potentials/EAM_NIST/Filedatas_Func_Moldy.F90:21-153): one element, cubic-knot
+ * V and rho with the lattice constant as the unit of the knots, F = -sqrt(rho); tables generated like a built-in library. */
+int mdb_host_moldy_ftable(const char *path, int ntab, int nembd, double rhoscal, double rmax,
+                          double *potr, double *fpotr, double *potb, double *fpotb, double *fembd, double *dfembd,
+                          double *csi, double *rhod);
 int mdb_host_ftable_export(const char *fname, int pot_type, int nkind, const int *ids, int ntab, double csi,
                            const double *potr, const double *fpotr, const double *potb, const double *fpotb,
                            int nkind1, const int *ids1, int nembd, double rhod, const double *fembd, const double *dfembd);

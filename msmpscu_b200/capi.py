@@ -92,6 +92,8 @@ SYMBOLS = {
     "mdb_host_lspt_info": (C.c_int, [C.c_char_p, c_ip, c_dp, c_dp, C.c_char_p, C.c_int]),
     "mdb_host_lspt_ftable": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_double, c_ip, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                        c_dp, c_dp, c_dp]),
+    "mdb_host_moldy_ftable": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                        c_dp, c_dp]),
     "mdb_host_ftable_export": (C.c_int, [C.c_char_p, C.c_int, C.c_int, c_ip, C.c_int, C.c_double, c_dp, c_dp, c_dp, c_dp,
                                          C.c_int, c_ip, C.c_int, C.c_double, c_dp, c_dp]),
     "mdb_host_ftable_file_info": (C.c_int, [C.c_char_p, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_ip, c_dp, c_dp]),

@@ -212,13 +212,11 @@ std::vector<int> unique_in_order(const std::vector<int> &ids)
 
 } // namespace
 
-extern "C" int mdb_host_ftable_create(int lib, int ng, const int *ptype, int ntab, int nembd, double rhoscal, double rmax,
-                                      int *nkind_out, int *nkind1_out, int *kpair, int *kembd, double *potr, double *fpotr,
-                                      double *potb, double *fpotb, double *fembd, double *dfembd, double *csi_out,
-                                      double *rhod_out)
+static int build_tables(const Registry &reg, int ng, const int *ptype, int ntab, int nembd, double rhoscal, double rmax,
+                        int *nkind_out, int *nkind1_out, int *kpair, int *kembd, double *potr, double *fpotr,
+                        double *potb, double *fpotb, double *fembd, double *dfembd, double *csi_out, double *rhod_out)
 {
     if (ng < 1 || ng > MDB_MXGROUP || !ptype || ntab < 2 || nembd < 2 || !(rmax > 0.0)) return MDB_ERR_ARG;
-    const Registry reg = make_registry(lib);
     if (reg.empty()) return MDB_ERR_ARG;
 
     std::vector<int> all, diag;
@@ -277,4 +275,64 @@ extern "C" int mdb_host_ftable_create(int lib, int ng, const int *ptype, int nta
     }
     *nkind_out = nkind; *nkind1_out = nkind1; *csi_out = csi; *rhod_out = rhod;
     return MDB_OK;
+}
+
+extern "C" int mdb_host_ftable_create(int lib, int ng, const int *ptype, int ntab, int nembd, double rhoscal, double rmax,
+                                      int *nkind_out, int *nkind1_out, int *kpair, int *kembd, double *potr, double *fpotr,
+                                      double *potb, double *fpotb, double *fembd, double *dfembd, double *csi_out,
+                                      double *rhod_out)
+{
+    return build_tables(make_registry(lib), ng, ptype, ntab, nembd, rhoscal, rmax, nkind_out, nkind1_out, kpair, kembd, potr, fpotr,
+                        potb, fpotb, fembd, dfembd, csi_out, rhod_out);
+}
+
+// ".moldy" library: Register_ForceTableProc_Moldy, Potentials/EAM_NIST/Filedatas_Func_Moldy.F90:21-153.  Six lines: symbol;
+// a_k of V; r_k of V; A_k of rho; R_k of rho; constants (the first is the lattice constant, which scales the knots and the
+// coefficients, :74-77).  One table id (1): V and rho cubic-knot sums, F = -sqrt(rho) (EMBED_FS_PLOY_Func with A = (-1)).
+// After registration the tables are generated like any built-in library (RHOMX = max rho * RHOSCAL).
+#include <fstream>
+#include <sstream>
+#include <string>
+extern "C" int mdb_host_moldy_ftable(const char *path, int ntab, int nembd, double rhoscal, double rmax, double *potr, double *fpotr,
+                                     double *potb, double *fpotb, double *fembd, double *dfembd, double *csi_out, double *rhod_out)
+{
+    if (!path) return MDB_ERR_ARG;
+    std::ifstream in(path);
+    if (!in) return MDB_ERR_ARG;
+    std::string line;
+    if (!std::getline(in, line)) return MDB_ERR_ARG; // symbol
+    std::vector<double> v[5];
+    for (int k = 0; k < 5; ++k) {
+        if (!std::getline(in, line)) return MDB_ERR_ARG;
+        for (char &ch : line)
+            if (ch == ',' || ch == ';') ch = ' ';
+        std::istringstream ls(line);
+        std::string tok;
+        while (ls >> tok) { // Extract_Numb: the numbers of the line; Fortran D exponents accepted
+            for (char &ch : tok)
+                if (ch == 'D' || ch == 'd') ch = 'E';
+            char *end = nullptr;
+            const double x = std::strtod(tok.c_str(), &end);
+            if (end && end != tok.c_str() && *end == '\0') v[k].push_back(x);
+        }
+    }
+    if (v[0].empty() || v[0].size() != v[1].size() || v[2].empty() || v[2].size() != v[3].size() || v[4].empty()) return MDB_ERR_ARG;
+    const double a0 = v[4][0];
+    KnotPoly pv, pr;
+    for (size_t i = 0; i < v[0].size(); ++i) { pv.a.push_back(v[0][i] / std::pow(a0, 3.0)); pv.rk.push_back(v[1][i] * a0); }
+    for (size_t i = 0; i < v[2].size(); ++i) { pr.a.push_back(v[2][i] / std::pow(a0, 6.0)); pr.rk.push_back(v[3][i] * a0); }
+    Registry reg;
+    Entry e;
+    e.pair = make_pair_poly3(pv);
+    e.rho = [pr](double r) { // RHO_FuncPoly3, Common/MD_Pot_EAM_Utilities.F90:259-290 (no inner clamp)
+        double s3, s2;
+        pr.eval(r * kCm2A, s3, s2);
+        return Val{s3, 3.0 * s2 / kA2Cm};
+    };
+    e.embed = make_embed_fs_poly({-1.0});
+    reg[1] = e;
+    const int ptype = 1;
+    int nkind = 0, nkind1 = 0, kpair = 0, kembd = 0;
+    return build_tables(reg, 1, &ptype, ntab, nembd, rhoscal, rmax, &nkind, &nkind1, &kpair, &kembd, potr, fpotr, potb, fpotb, fembd,
+                        dfembd, csi_out, rhod_out);
 }

@@ -134,6 +134,24 @@ def NIST_Register_Interaction_Table(path, ntab, nembd, ptype=None, rmax=0.0):
     return t
 
 
+def Moldy_Register_Interaction_Table(path, ntab, nembd, rmax, rhoscal=20.0):
+    """Register_ForceTableProc_Moldy + Generate_NIST_ForceTalbe for a ".moldy" file (Filedatas_Func_Moldy.F90:21-153)."""
+    lib = capi.load()
+    t = MDForceTable("EAM_TYPE")
+    t.potr, t.fpotr, t.potb, t.fpotb = (np.zeros(ntab) for _ in range(4))
+    t.fembd, t.dfembd = np.zeros(nembd), np.zeros(nembd)
+    csi, rhod = C.c_double(), C.c_double()
+    rc = lib.mdb_host_moldy_ftable(os.fsencode(path), int(ntab), int(nembd), float(rhoscal), float(rmax), capi.dp(t.potr),
+                                   capi.dp(t.fpotr), capi.dp(t.potb), capi.dp(t.fpotb), capi.dp(t.fembd), capi.dp(t.dfembd),
+                                   C.byref(csi), C.byref(rhod))
+    if rc != 0:
+        raise capi.MDBError(rc, "mdb_host_moldy_ftable: cannot import %r" % (path,))
+    t.ng, t.ntab, t.nembd, t.nkind, t.nkind1 = 1, int(ntab), int(nembd), 1, 1
+    t.kpair, t.kembd = np.array([1], dtype=np.int32), np.array([1], dtype=np.int32)
+    t.csi, t.rhod, t.Rmax = csi.value, rhod.value, float(rmax)
+    return t
+
+
 def Export_ForceTable(fname, t):
     """Common/MD_TypeDef_ForceTable.F90:1315-1459: writes fname.pair and fname.embd."""
     lib = capi.load()

@@ -169,3 +169,31 @@ def test_lspt_import_matches_reference_embd_and_oracle(lspt_dir):
         a, b = getattr(t, name), o[name][0]
         assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b)), name
     assert t.csi == o["csi"] and t.rhod == o["rhod"]
+
+
+def test_moldy_import_against_the_formulas(tmp_path):
+    """".moldy" files (Filedatas_Func_Moldy.F90): no example ships with the reference, so the importer is checked against
+    a direct NumPy evaluation of the documented functions (cubic-knot sums scaled by the lattice constant, F = -sqrt(rho))
+    on the reference's table grid -- "parity unpinned" for this format."""
+    a0 = 3.1652
+    ak, rk = [0.96, -0.29, 0.41], [1.30, 1.20, 0.90]
+    Ak, Rk = [0.70, 0.05], [1.35, 1.00]
+    p = tmp_path / "W_test.moldy"
+    p.write_text("W\n%s\n%s\n%s\n%s\n%.4f 183.84\n" % (" ".join("%.6f" % v for v in ak), " ".join("%.6f" % v for v in rk),
+                                                          " ".join("%.6fD0" % v for v in Ak), " ".join("%.6f" % v for v in Rk), a0))
+    ntab, nembd, rmax = 2000, 1500, 1.4 * a0 * 1e-8
+    t = forcetable.Moldy_Register_Interaction_Table(str(p), ntab, nembd, rmax)
+    ev, r = 1.60219e-12, (np.arange(1, ntab + 1) / t.csi) ** 2
+    ra = r * 1e8
+    H = lambda x: (x >= 0).astype(float)
+    V = sum(a / a0 ** 3 * (k * a0 - ra) ** 3 * H(k * a0 - ra) for a, k in zip(ak, rk))
+    dV = sum(a / a0 ** 3 * (k * a0 - ra) ** 2 * H(k * a0 - ra) for a, k in zip(ak, rk))
+    rho = sum(a / a0 ** 6 * (k * a0 - ra) ** 3 * H(k * a0 - ra) for a, k in zip(Ak, Rk))
+    drho = sum(a / a0 ** 6 * (k * a0 - ra) ** 2 * H(k * a0 - ra) for a, k in zip(Ak, Rk))
+    close = lambda a, b: np.max(np.abs(a - b)) <= 1e-14 * np.max(np.abs(b))   # (the knot sums cancel near their zero crossings)
+    assert close(t.potr, 0.5 * V * ev * r) and close(t.fpotr, 3.0 * dV * ev / 1e-8 * r)
+    assert close(t.potb, rho) and close(t.fpotb, 3.0 * drho / 1e-8)
+    assert abs(t.rhod - rho.max() * 20.0 / nembd) < 1e-15 * t.rhod
+    g = np.arange(nembd) * t.rhod
+    assert np.allclose(t.fembd[1:], -np.sqrt(g[1:]) * ev, rtol=1e-13) and t.fembd[0] == 0.0
+    assert np.allclose(t.dfembd[1:], -0.5 / np.sqrt(g[1:]) * ev, rtol=1e-13)
