@@ -153,6 +153,9 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
     if (c->h_dd) cudaFreeHost(c->h_dd);
     if (c->hstage) cudaFreeHost(c->hstage);
     if (c->avp) cudaFree(c->avp);
+    if (c->lb_buf) cudaFree(c->lb_buf);
+    if (c->lb_mask) cudaFree(c->lb_mask);
+    if (c->lb_host) cudaFreeHost(c->lb_host);
     if (c->q_buf) cudaFree(c->q_buf);
     if (c->q_host) cudaFreeHost(c->q_host);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);

@@ -159,6 +159,7 @@ struct mdb_ctx {
     //      kernels of already-converged iterations into no-ops
     double *q_buf = nullptr; int q_n = 0; void *q_host = nullptr;
     const int *skip_flag = nullptr;
+    double *lb_buf = nullptr; size_t lb_doubles = 0; unsigned char *lb_mask = nullptr; size_t lb_mask_n = 0; void *lb_host = nullptr; // L-BFGS workspace
     double *avp = nullptr; int avp_n = 0;                      // atomic stress scratch (mdb_atomic_stress_host)
 
     // ---- virial partials

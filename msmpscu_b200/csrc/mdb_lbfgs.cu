@@ -334,16 +334,27 @@ extern "C" int mdb_lbfgs(mdb_ctx *c, int mxnumsteps, int msave, double factr, do
     cudaStream_t st = c->stream;
     // ---- workspace: xl, g, d, t, r, ws[m], wy[m], partials, scalars, mask
     const size_t nd = (5 + 2 * (size_t)msave) * n3 + (size_t)nblk * 3 * LB_MAXM + 64;
-    double *buf = nullptr;
-    unsigned char *fre = nullptr;
-    LbScal *H = nullptr;
-    if (cudaMalloc(&buf, sizeof(double) * nd) != cudaSuccess) { cudaGetLastError(); return mdb_fail(c, MDB_ERR_NOMEM, "mdb_lbfgs: workspace"); }
-    if (cudaMalloc(&fre, n3) != cudaSuccess) { cudaFree(buf); cudaGetLastError(); return mdb_fail(c, MDB_ERR_NOMEM, "mdb_lbfgs: workspace"); }
-    if (cudaMallocHost(&H, sizeof(LbScal)) != cudaSuccess) { cudaFree(buf); cudaFree(fre); cudaGetLastError(); return mdb_fail(c, MDB_ERR_NOMEM, "mdb_lbfgs: workspace"); }
+    // the workspace stays with the context: allocation (pinned host memory in particular) costs far more than a quench
+    if (c->lb_doubles < nd) {
+        if (c->lb_buf) cudaFree(c->lb_buf);
+        c->lb_buf = nullptr; c->lb_doubles = 0;
+        if (cudaMalloc(&c->lb_buf, sizeof(double) * nd) != cudaSuccess) { cudaGetLastError(); return mdb_fail(c, MDB_ERR_NOMEM, "mdb_lbfgs: workspace"); }
+        c->lb_doubles = nd;
+    }
+    if (c->lb_mask_n < n3) {
+        if (c->lb_mask) cudaFree(c->lb_mask);
+        c->lb_mask = nullptr; c->lb_mask_n = 0;
+        if (cudaMalloc(&c->lb_mask, n3) != cudaSuccess) { cudaGetLastError(); return mdb_fail(c, MDB_ERR_NOMEM, "mdb_lbfgs: workspace"); }
+        c->lb_mask_n = n3;
+    }
+    if (!c->lb_host && cudaMallocHost(&c->lb_host, sizeof(LbScal)) != cudaSuccess) { cudaGetLastError(); return mdb_fail(c, MDB_ERR_NOMEM, "mdb_lbfgs: workspace"); }
+    double *buf = c->lb_buf;
+    unsigned char *fre = c->lb_mask;
+    LbScal *H = reinterpret_cast<LbScal *>(c->lb_host);
     double *xl = buf, *g = xl + n3, *d = g + n3, *t = d + n3, *r = t + n3, *ws = r + n3, *wy = ws + (size_t)msave * n3;
     double *part = wy + (size_t)msave * n3;
     LbScal *S = reinterpret_cast<LbScal *>(part + (size_t)nblk * 3 * LB_MAXM);
-    auto cleanup = [&](int code) { cudaStreamSynchronize(st); cudaFree(buf); cudaFree(fre); cudaFreeHost(H); return code; };
+    auto cleanup = [&](int code) { cudaStreamSynchronize(st); return code; };
     auto peek = [&]() -> int {
         if (cudaGetLastError() != cudaSuccess) return MDB_ERR_CUDA;
         if (cudaMemcpyAsync(H, S, sizeof(LbScal), cudaMemcpyDeviceToHost, st) != cudaSuccess) return MDB_ERR_CUDA;

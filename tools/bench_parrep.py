@@ -25,7 +25,12 @@ def main():
     out = {"workload": "configs[3] shape: %d replicas x 2001 atoms (2000 W + 1 H, Bonny EAM1), list cutoff 1.6 RU, MAXNB 400" % nrep,
            "atoms": n}
     for path, name in ((capi.FORCE_PATH_AUTO, "auto"),):
-        ctx = util.make_ctx(c, force_path=path)
+        ctx = util.make_ctx(c, build=False, force_path=path)
+        if os.environ.get("MDB_LANES"):
+            ctx.set_option(capi.OPT_TILED_LANES, int(os.environ["MDB_LANES"]))
+        if os.environ.get("MDB_THREADS"):
+            ctx.set_option(capi.OPT_TILED_THREADS, int(os.environ["MDB_THREADS"]))
+        ctx.nlist_build()
         out["active_path"] = "tiled" if ctx.get_option(capi.OPT_ACTIVE_PATH) == capi.FORCE_PATH_TILED else "generic"
         ctx.force(capi.FORCE)
         ctx.thermalize(600.0, 20240101, 0)
@@ -35,8 +40,13 @@ def main():
         ctx.thermalize(600.0, 20240101, 1)
         ctx.sync()
         out["thermalize_ms"] = (time.perf_counter() - t0) * 1e3
+        ctx.prof_reset(); ctx.prof_enable(True)
+        ctx.run(20, 50, 1, 10, 0.5e-15)
+        out["md_device_ms_per_step_by_class"] = {k: round(v[1] / 50, 4) for k, v in ctx.prof_get().items() if v[0]}
+        ctx.prof_enable(False)
+        ctx.sync()
         t0 = time.perf_counter()
-        ctx.run(20, 500, 1, 10, 0.5e-15)
+        ctx.run(70, 500, 1, 10, 0.5e-15)
         ctx.sync()
         dt = time.perf_counter() - t0
         out["md_500_steps_ms"] = dt * 1e3
