@@ -691,3 +691,39 @@ def test_lbfgs_quench_tracks_oracle(oracle, path):
         else:
             assert fl == 1 and np.abs(fp).max() < 0.5 * f0
         ctx.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_disordered_configurations_tiled_vs_oracle(oracle, seed):
+    """Strongly disordered boxes (random displacements up to 0.18 a0, a few vacancies, random box shape): the scan counts of
+    the distance classes differ from atom to atom inside a warp, which is what the warp-uniform padding skip of the pass
+    kernels and the class partition of the list builder must handle.  Forced TILED path against the oracle (forces, DEN,
+    energies) and against the generic path on the device, at the build positions and after the atoms have moved enough to
+    leave the class shortcut (displacement guard)."""
+    rng = np.random.default_rng(1000 + seed)
+    ncell = tuple(int(v) for v in rng.integers(7, 11, size=3))
+    c = util.bcc_case(ncell, seed=50 + seed, disp=0.18, temp=2000.0)
+    keep = np.ones(c.xp.shape[0], bool)
+    keep[rng.choice(c.xp.shape[0], size=9, replace=False)] = False
+    c.statu = c.statu.copy()
+    c.statu[~keep] = 0                                   # inactive atoms: skipped as i, still listed as j (reference behaviour)
+    ref = _oracle_list(oracle, c)
+    gid = ref["gid"] - 1
+    tabs = util.oracle_tables(oracle, c)
+    fp, den, _, ep = oracle.force(c.xp[gid], c.ityp[gid], ref["statu"][gid], ref["kvois"], ref["indi"], c.zl, c.ifpd, tabs, epot=True)
+    assert ref["kvois"].max() - ref["kvois"][ref["kvois"] > 0].min() >= 8
+    ctx = util.make_ctx(c, force_path=capi.FORCE_PATH_TILED)
+    assert ctx.get_option(capi.OPT_ACTIVE_PATH) == capi.FORCE_PATH_TILED and ctx.nlist_overflow() == 0
+    ctx.force(capi.FORCE | capi.EPOT)
+    assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < FORCE_RTOL
+    assert util.relerr(ctx.download(capi.F_DEN, capi.ORDER_CELL), den) < FORCE_RTOL
+    assert util.relerr(ctx.download(capi.F_EPOT, capi.ORDER_CELL), ep) < FORCE_RTOL
+    # 6 steps at 2000 K without a rebuild (NB_UPTAB = 100): the same list serves moved atoms; generic path is the witness
+    gen = util.make_ctx(c, force_path=capi.FORCE_PATH_GENERIC)
+    gen.force(capi.FORCE)
+    for k in range(3):
+        ctx.run(1 + 2 * k, 2, 0, 100, 1.0e-15)
+        gen.run(1 + 2 * k, 2, 0, 100, 1.0e-15)
+        assert util.relerr(ctx.download(capi.F_XP), gen.download(capi.F_XP)) < 1e-12
+        assert util.relerr(ctx.download(capi.F_FP), gen.download(capi.F_FP)) < 1e-9
+    ctx.close(); gen.close()
