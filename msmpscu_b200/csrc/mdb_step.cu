@@ -72,7 +72,7 @@ __device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict_
     return d2;
 }
 
-__global__ void k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, double *__restrict__ fp,
+__global__ void __launch_bounds__(256, 4) k_predict(int n, double4 *__restrict__ pos, double *__restrict__ xp1, double *__restrict__ fp,
                           double *__restrict__ dis, int *__restrict__ statu, const int *__restrict__ ityp,
                           MassParams M, BoxParams box, double th, double h2s2, double hs2,
                           float *__restrict__ dsr, int *__restrict__ counters, int a0, int a1, int pre, EpcParams E,
