@@ -665,8 +665,8 @@ extern "C" int mdb_nlist_build(mdb_ctx *c)
         // atom has more than mxKVOIS neighbours (the reference truncates in ITS scan order, which only the generic
         // kernel reproduces)
         if (c->opt_force_path == MDB_FORCE_PATH_TILED)
-            return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path: %d tiles / cells exceed the halo, list or mxKVOIS capacity",
-                            c->h_counters[CNT_TILE_OVERFLOW]);
+            return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path: %d tiles / cells exceed the halo, list or mxKVOIS capacity (longest list %d)",
+                            c->h_counters[CNT_TILE_OVERFLOW], c->h_counters[CNT_NNMAX]);
         c->tiled.ok = false; // AUTO: fall back to the generic path and rebuild
         rc = mdb_list_rebuild(c);
         if (rc < 0) return rc;

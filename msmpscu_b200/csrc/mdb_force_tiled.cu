@@ -183,19 +183,21 @@ __device__ __forceinline__ float f2_hi(unsigned long long a) { return __uint_as_
 // Push of slot + 2-bit distance class onto a shared-memory column, with the membership test (r2 <= rm, and for the centre
 // row: slot != own slot) and the class tests evaluated INSIDE the asm: the predicates never take a round trip through
 // general registers (the C++ form costs a SEL and a second SETP per candidate).
-__device__ __forceinline__ void push_if_in(unsigned &addr, unsigned slot, float r2, float rm, float rc0, float rc1)
+// (step = +64 or -64 bytes: the two warps of a cell fill the same column from its two ends)
+__device__ __forceinline__ void push_if_in(unsigned &addr, unsigned slot, float r2, float rm, float rc0, float rc1, int step)
 {
     asm volatile("{\n.reg .pred q, a, b;\n.reg .b32 e;\nsetp.le.f32 q, %2, %3;\nsetp.gt.f32 a, %2, %4;\nsetp.gt.f32 b, %2, %5;\n"
                  "mov.b32 e, %1;\n@a add.u32 e, e, 0x4000;\n@b add.u32 e, e, 0x4000;\n"
-                 "@q st.shared.u16 [%0], e;\n@q add.u32 %0, %0, 64;\n}\n"
-                 : "+r"(addr) : "r"(slot), "f"(r2), "f"(rm), "f"(rc0), "f"(rc1) : "memory");
+                 "@q st.shared.u16 [%0], e;\n@q add.s32 %0, %0, %6;\n}\n"
+                 : "+r"(addr) : "r"(slot), "f"(r2), "f"(rm), "f"(rc0), "f"(rc1), "r"(step) : "memory");
 }
-__device__ __forceinline__ void push_if_in_notself(unsigned &addr, unsigned slot, float r2, float rm, float rc0, float rc1, unsigned self)
+__device__ __forceinline__ void push_if_in_notself(unsigned &addr, unsigned slot, float r2, float rm, float rc0, float rc1, unsigned self,
+                                                   int step)
 {
     asm volatile("{\n.reg .pred q, a, b;\n.reg .b32 e;\nsetp.le.f32 q, %2, %3;\nsetp.ne.and.u32 q, %1, %6, q;\nsetp.gt.f32 a, %2, %4;\n"
                  "setp.gt.f32 b, %2, %5;\nmov.b32 e, %1;\n@a add.u32 e, e, 0x4000;\n@b add.u32 e, e, 0x4000;\n"
-                 "@q st.shared.u16 [%0], e;\n@q add.u32 %0, %0, 64;\n}\n"
-                 : "+r"(addr) : "r"(slot), "f"(r2), "f"(rm), "f"(rc0), "f"(rc1), "r"(self) : "memory");
+                 "@q st.shared.u16 [%0], e;\n@q add.s32 %0, %0, %7;\n}\n"
+                 : "+r"(addr) : "r"(slot), "f"(r2), "f"(rm), "f"(rc0), "f"(rc1), "r"(self), "r"(step) : "memory");
 }
 // predicated push of a 16-bit entry onto a shared-memory column (32-bit shared address, row stride 64 bytes)
 __device__ __forceinline__ void sts16_push(unsigned &addr, unsigned val, bool p)
@@ -204,12 +206,21 @@ __device__ __forceinline__ void sts16_push(unsigned &addr, unsigned val, bool p)
                  : "+r"(addr) : "h"((unsigned short)val), "r"((unsigned)p) : "memory");
 }
 
+__device__ __forceinline__ void pair_barrier(int cell) // the two warps of one owned cell
+{
+    __syncwarp();
+    asm volatile("bar.sync %0, 64;" ::"r"(cell + 1) : "memory");
+}
+
 template <int G, bool MT>
-__global__ void __launch_bounds__(32 * TILE_MAX_W)
+__global__ void __launch_bounds__(64 * TILE_MAX_W)
 k_tile_nlist(TileParams P, TileListArgs A)
 {
     extern __shared__ __align__(16) unsigned char nl_smem[];
     __shared__ TileDesc H;
+    // per lane: entries (10 bits) and overflow count (6 bits, saturating) of the second warp.  16-bit on purpose: two CTAs of
+    // this kernel share an SM only while 2 x (dynamic + static + 1 KB) stays under 228 KB, and the margin is ~1 KB.
+    __shared__ unsigned short s_half1[TILE_MAX_W][32];
     // halo as PAIRS of candidates: hxy[p] = {x(2p), x(2p+1), y(2p), y(2p+1)}, hzt[p] = {z, z, type, type}
     const int npair = (P.hcap + 2) / 2;
     float4 *hxy = reinterpret_cast<float4 *>(nl_smem);
@@ -242,17 +253,27 @@ k_tile_nlist(TileParams P, TileListArgs A)
         }
     }
     __syncthreads();
+    // TWO warps per owned cell (lanes = its atoms): warp 0 scans halo rows 0-3, warp 1 rows 4-8 (with the atom's own row).
+    // Both fill the SAME shared-memory column of an atom, warp 0 from row 0 upwards, warp 1 from the last row downwards, so
+    // the split of an atom's neighbours between the two row sets (anything from 25 % to 75 %, by where the atom sits in its
+    // cell) needs no capacity of its own; only the sum can overflow, and that is checked after both are done.  Warp 0 then
+    // moves warp 1's block down next to its own and does the class partition and the write-out.
+    // (One warp per cell left 14 warps per SM: 63 % of the issue slots used.)
     const int wt = nhx - 2;
-    if (warp >= wt) return;
-    const int myhc = 4 * nhx + warp + 1;           // centre row (hy = hz = 1), cell hx = warp + 1
+    const int cw = warp >> 1, half = warp & 1;
+    if (cw >= wt) return;
+    const int myhc = 4 * nhx + cw + 1;             // centre row (hy = hz = 1), cell hx = cw + 1
     const int ccnt = H.cnt[myhc];
     if (ccnt <= 0) return;                         // :1018
     if (A.naac[H.cid[myhc]] <= 0) return;          // cells without ACTIVE atoms are skipped (:981-982)
     const int cgst = H.gst[myhc], csl = H.slot[myhc];
     const float rm1 = A.rm2[0], rc0 = A.rc2[0], rc1 = A.rc2[1];
-    unsigned short *col = lists + (size_t)warp * A.lcap * 32 + lane;   // entry k of this lane at col[k * 32]
-    const unsigned col_a = (unsigned)__cvta_generic_to_shared(col);
+    unsigned short *col0 = lists + (size_t)cw * A.lcap * 32 + lane;    // entry k of this lane at col0[k * 32]
+    unsigned short *col = col0;
     const int lcap = A.lcap;
+    const unsigned col_a = (unsigned)__cvta_generic_to_shared(col0) + (half ? (unsigned)(lcap - 1) * 64u : 0u); // first entry of this warp
+    const int step = half ? -64 : 64;
+    const int r_lo = half ? 4 : 0, r_hi = half ? 9 : 4;
 
     for (int ab = 0; ab < ccnt; ab += 32) {
         const bool valid = ab + lane < ccnt;
@@ -263,7 +284,7 @@ k_tile_nlist(TileParams P, TileListArgs A)
         const int ity = MT ? __float_as_int(fzt[mo + 2]) : 1;
         const unsigned long long mx2 = f2_pack(mx, mx), my2 = f2_pack(my, my), mz2 = f2_pack(mz, mz);
         unsigned pa = col_a;                           // shared address of the next free entry of this lane
-        const unsigned pa_end = col_a + (valid ? (unsigned)lcap * 64u : 0u); // invalid lanes accept nothing
+        const int room = valid ? lcap : 0;             // invalid lanes accept nothing (capacity-checked path)
         int nover = 0;                                 // accepted beyond the capacity
 
         // one candidate / one aligned pair of candidates; SELF: the range holds the lane's own atom (:1124);
@@ -271,16 +292,20 @@ k_tile_nlist(TileParams P, TileListArgs A)
         auto accept = [&](auto self_tag, auto cap_tag, const int s, const float r2, const float rm) {
             constexpr bool SELF = decltype(self_tag)::value, CAP = decltype(cap_tag)::value;
             if (!CAP) {                                                     // the common case: room for the whole range
-                if (SELF) push_if_in_notself(pa, (unsigned)s, r2, rm, rc0, rc1, (unsigned)myslot);
-                else push_if_in(pa, (unsigned)s, r2, rm, rc0, rc1);
+                if (SELF) push_if_in_notself(pa, (unsigned)s, r2, rm, rc0, rc1, (unsigned)myslot, step);
+                else push_if_in(pa, (unsigned)s, r2, rm, rc0, rc1, step);
                 return;
             }
             bool hit = r2 <= rm;                                            // :1123
             if (SELF) hit = hit && (s != myslot);
             const unsigned e = (unsigned)s + ((r2 > rc0) ? 0x4000u : 0u) + ((r2 > rc1) ? 0x4000u : 0u);
-            bool st = hit;
-            if (CAP) { st = hit && (pa < pa_end); nover += (hit && !st) ? 1 : 0; }
-            sts16_push(pa, e, st);
+            const int have = half ? (int)((col_a - pa) >> 6) : (int)((pa - col_a) >> 6);
+            const bool st = hit && (have < room);
+            nover += (hit && !st) ? 1 : 0;
+            if (st) {
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(pa), "h"((unsigned short)e) : "memory");
+                pa = (unsigned)((int)pa + step);
+            }
         };
         auto one = [&](auto self_tag, auto cap_tag, const int s) {
             const int o = (s >> 1) * 4 + (s & 1);
@@ -308,11 +333,11 @@ k_tile_nlist(TileParams P, TileListArgs A)
             if (s < s_hi) one(self_tag, cap_tag, s);
         };
 #pragma unroll 1
-        for (int r = 0; r < 9; r++) {
-            const int hc0 = r * nhx + warp;            // cells hx = warp, warp+1, warp+2 of halo row r: contiguous slots
+        for (int r = r_lo; r < r_hi; r++) {
+            const int hc0 = r * nhx + cw;              // cells hx = cw, cw+1, cw+2 of halo row r: contiguous slots
             const int s_lo = H.slot[hc0], s_hi = H.slot[hc0 + 3];
             // warp-uniform choice: can any lane run out of list rows inside this range?
-            const int used = (int)((pa - col_a) >> 6);
+            const int used = half ? (int)((col_a - pa) >> 6) : (int)((pa - col_a) >> 6);
             const bool tight = __any_sync(0xffffffffu, used + (s_hi - s_lo) > lcap);
             if (r == 4) {
                 if (tight) range(std::true_type(), std::true_type(), s_lo, s_hi);
@@ -322,8 +347,20 @@ k_tile_nlist(TileParams P, TileListArgs A)
                 else range(std::false_type(), std::false_type(), s_lo, s_hi);
             }
         }
-        int nn = (int)((pa - col_a) >> 6);
+        int nn = half ? (int)((col_a - pa) >> 6) : (int)((pa - col_a) >> 6);
         if (!valid) { nn = 0; nover = 0; }
+        if (half) s_half1[cw][lane] = (unsigned short)(min(nn, 1023) | (min(nover, 63) << 10));
+        pair_barrier(cw);                              // warp 1's entries and counts are visible to warp 0
+        if (half) { pair_barrier(cw); continue; }      // ... and warp 1 waits until warp 0 is done with the columns
+        {
+            const int h1 = s_half1[cw][lane];
+            int n1 = h1 & 1023;
+            nover += h1 >> 10;
+            if (nn + n1 > lcap) { nover += nn + n1 - lcap; n1 = lcap - nn; }   // the two ends met: the build is discarded
+            // warp 1's block [lcap - n1, lcap) moves down to [nn, nn + n1): ascending copy to lower rows, overlap-safe
+            for (int k = 0; k < n1; k++) col0[(nn + k) * 32] = col0[(lcap - n1 + k) * 32];
+            nn += n1;
+        }
         const int nall = nn + nover;
         if (__any_sync(0xffffffffu, nover > 0 || nall > P.mxkvois)) {
             if (lane == 0) atomicAdd(&A.counters[CNT_TILE_OVERFLOW], 1);
@@ -333,7 +370,7 @@ k_tile_nlist(TileParams P, TileListArgs A)
             for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
             if (lane == 0) atomicMax(&A.counters[CNT_NNMAX], m);
         }
-        if (!valid) continue;
+        if (valid) { // (no early exit of single lanes: the pair barrier below needs the whole warp)
         A.kvois[ia] = min(nn, P.mxkvois);
         // ---- three-way partition of the column by class tag (order inside a class is free)
         int lo = 0, mid = 0, hi = nn - 1;
@@ -370,6 +407,8 @@ k_tile_nlist(TileParams P, TileListArgs A)
                 dst[v] = w;
             }
         }
+        }
+        pair_barrier(cw);
     }
 }
 
@@ -1021,6 +1060,17 @@ int mdb_tiled_plan(mdb_ctx *c)
             S.smem_list = sizeof(float4) * 2 * (size_t)((S.hcap + 2) / 2) + sizeof(unsigned short) * 32 * (size_t)S.lcap * S.wmax;
         }
         if (S.smem_list > (size_t)SMEM_BUDGET - 4096) return MDB_OK;
+        // two CTAs of the list kernel share an SM when 2 x (dynamic + ~3.7 KB static + 1 KB reserved) <= 228 KB; when a
+        // slightly shorter column (never below expected + 25 % + 16) gets there, take it: it doubles the resident warps
+        const size_t two_cta = (233472 / 2) - 1024 - 3712 - 512;
+        const size_t halo_b = sizeof(float4) * 2 * (size_t)((S.hcap + 2) / 2);
+        if (S.smem_list > two_cta && halo_b < two_cta) {
+            const int fit = (int)((two_cta - halo_b) / (sizeof(unsigned short) * 32 * (size_t)S.wmax)) & ~7;
+            if (fit >= (((int)(1.25 * expect) + 16 + 7) & ~7)) {
+                S.lcap = std::min(S.lcap, fit);
+                S.smem_list = halo_b + sizeof(unsigned short) * 32 * (size_t)S.lcap * S.wmax;
+            }
+        }
     }
     for (int p = 0; p < 2; p++) S.smem_pass[p] = TP_HDR_BYTES + tp_tab_bytes(S.ktab[p]) + S.nbuf * tp_buf_bytes(S.hcap, S.ocap, G, mt);
     S.ok = true;
@@ -1060,7 +1110,7 @@ static int launch_list(mdb_ctx *c)
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
     ProfScope ps(c, MDB_K_NLIST, 2);
     k_tile_desc<<<S.P.ntiles, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters);
-    if (tile_hi > tile_lo) kern<<<tile_hi - tile_lo, 32 * S.wmax, S.smem_list, c->stream>>>(S.P, A);
+    if (tile_hi > tile_lo) kern<<<tile_hi - tile_lo, 64 * S.wmax, S.smem_list, c->stream>>>(S.P, A);
     CUDA_TRY(c, cudaGetLastError());
     // the reference-format KVOIS/INDI pair is rebuilt on demand from the positions of this moment
     CUDA_TRY(c, cudaMemcpyAsync(c->pos_snap, c->pos, sizeof(double4) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
