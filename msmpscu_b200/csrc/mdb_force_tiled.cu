@@ -435,6 +435,7 @@ struct TilePassArgs {
     const double2 *g_potb, *g_fpotr, *g_fpotb, *g_dfembd;
     const double2 *g_potr, *g_fembd;   // PASS 3 (per-atom energy): pair term and embedding VALUE tables
     double *epot;
+    int den_too;           // PASS 3 also stores dF/drho (what pass 1 produces): its density sum is the same sum
     int ntab, nembd, pot_type;
     double csi, rhod;
     double r2eff;          // min(RU2, table support) for this pass
@@ -859,6 +860,17 @@ k_tile_pass(TileParams P, TilePassArgs A)
                             }
                         }
                         A.epot[ia] = active ? acc0 + den0 : 0.0;
+                        if (A.den_too) { // the epilogue of pass 1 on the same density sum (rows past the support add exactly 0)
+                            double dd = acc1;
+                            if (A.pot_type == MDB_POT_FS) {
+                                if (dd > 0.0) dd = -0.5 / sqrt(dd);
+                            } else if (dd > 0.0) {
+                                const double sk = dd / A.rhod + 1.0;
+                                const int kk = (int)(sk + 0.000001);
+                                dd = lerp_g(A.g_dfembd, A.nembd + 2, A.kembd[ti], kk, sk - (double)kk);
+                            }
+                            reinterpret_cast<double *>(A.pos + ia)[3] = active ? dd : 0.0;
+                        }
                     }
                 } else if (PASS == 1) {
                     if (have && gl == 0) {
@@ -921,7 +933,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
     if (blockIdx.x == 0 && A.zero_parked) {
         const int n_in = A.counters[CNT_INCELL];
         for (int i = n_in + threadIdx.x; i < P.n; i += NT) {
-            if (PASS == 3) A.epot[i] = 0.0;
+            if (PASS == 3) { A.epot[i] = 0.0; if (A.den_too) reinterpret_cast<double *>(A.pos + i)[3] = 0.0; }
             else if (PASS == 1) reinterpret_cast<double *>(A.pos + i)[3] = 0.0;
             else { A.fp[i] = 0.0; A.fp[i + (size_t)P.n] = 0.0; A.fp[i + 2 * (size_t)P.n] = 0.0; }
         }
@@ -1139,6 +1151,7 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.nbl = S.nbl; A.fp = c->fp; A.counters = c->counters; A.desc = (const TileDesc *)S.desc;
     A.g_potb = t.potb; A.g_fpotr = t.fpotr; A.g_fpotb = t.fpotb; A.g_dfembd = t.dfembd;
     A.g_potr = t.potr; A.g_fembd = t.fembd; A.epot = c->epot;
+    A.den_too = (PASS == 3 && fuse == -1) ? 1 : 0;
     constexpr int PI = (PASS == 3) ? 1 : PASS - 1; // the energy pass shares the plan (window, classes, shared memory) of pass 2
     A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod;
     A.r2eff = (PASS == 3) ? S.r2eff_epot : S.r2eff[PI]; A.kmin = S.kmin[PI]; A.ktab = S.ktab[PI];
@@ -1152,6 +1165,7 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.zero_parked = c->dd_on ? 0 : 1;
     A.nbuf = S.nbuf;
     A.skip = c->skip_flag;
+    if (PASS == 3) A.fuse = 0;
     if (!c->epc.on) A.fuse &= ~1;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
@@ -1167,11 +1181,17 @@ template <int G, bool MT, int NT>
 static int launch_force(mdb_ctx *c, unsigned flags, int fuse, double hs2)
 {
     int rc = MDB_OK;
-    if ((flags & (MDB_FORCE | MDB_DEN)) && !(flags & MDB_NOPASS1)) rc = launch_pass<1, G, MT, false, NT>(c, 0, 0.0);
+    const bool need_den = (flags & (MDB_FORCE | MDB_DEN)) && !(flags & MDB_NOPASS1);
+    // energies and forces together (every quench iteration): the energy pass forms the same density sum as pass 1, so it
+    // also stores dF/drho and pass 1 is not launched
+    const bool den_in_epot = need_den && (flags & MDB_EPOT);
+    if (need_den && !den_in_epot) rc = launch_pass<1, G, MT, false, NT>(c, 0, 0.0);
+    if (rc < 0) return rc;
+    if (den_in_epot) rc = launch_pass<3, G, MT, false, NT>(c, -1, 0.0);
     if (rc < 0) return rc;
     if (flags & MDB_FORCE) rc = fuse ? launch_pass<2, G, MT, true, NT>(c, fuse, hs2) : launch_pass<2, G, MT, false, NT>(c, 0, 0.0);
     if (rc < 0) return rc;
-    if (flags & MDB_EPOT) rc = launch_pass<3, G, MT, false, NT>(c, 0, 0.0);
+    if ((flags & MDB_EPOT) && !den_in_epot) rc = launch_pass<3, G, MT, false, NT>(c, 0, 0.0);
     return rc;
 }
 
