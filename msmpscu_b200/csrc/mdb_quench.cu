@@ -251,16 +251,18 @@ extern "C" int mdb_steepest(mdb_ctx *c, int mxnumsteps, int meth, double alpha, 
     cudaStream_t st = c->stream;
     CUDA_TRY(c, cudaMemsetAsync(S, 0, sizeof(QuenchScal), st));
     int rc;
-    // ---- first step :70-90
-    if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
+    // ---- first step :70-90.  The energies of a configuration and the forces the NEXT iteration starts from belong to the
+    // same positions, so they are evaluated together (MDB_FORCE | MDB_EPOT: the energy pass also delivers dF/drho and no
+    // separate density pass runs); PreFP is saved before that evaluation overwrites FP.
+    if ((rc = mdb_force(c, MDB_FORCE | MDB_EPOT, nullptr)) < 0) return rc;
     c->launches_total += 1;
     k_sd_first<<<nblk, QT, 0, st>>>(n3, alpha, maxdis, mindis, c->fp, prefp, dxp, part, S);
     c->skip_flag = &S->done;
     auto finish = [&](int code) { c->skip_flag = nullptr; return code; };
-    if ((rc = mdb_force(c, MDB_EPOT, nullptr)) < 0) return finish(rc);
     c->launches_total += 2;
     k_sd_save<<<nblk, QT, 0, st>>>(0, n, c->fp, prefp, c->epot, epot0, S);
     k_sd_apply<<<cdiv(n, QT), QT, 0, st>>>(n, dxp, c->pos, c->box, c->dsr, c->counters, S);
+    if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return finish(rc);          // forces of iteration 1
     // ---- iterations :93-133, the host looks at the flag once per batch
     const int batch = 8;
     int it = 1;
@@ -268,16 +270,15 @@ extern "C" int mdb_steepest(mdb_ctx *c, int mxnumsteps, int meth, double alpha, 
     CUDA_TRY(c, cudaStreamSynchronize(st));
     while (!H->done && it <= mxnumsteps) {
         for (int b = 0; b < batch && it <= mxnumsteps; b++, it++) {
-            if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return finish(rc);
-            c->launches_total += 4;
+            c->launches_total += 7;
             k_sd_dots<<<nblk, QT, 0, st>>>(n3, alpha, prefp, c->fp, dxp, part, S);
             k_sd_step<<<nblk, QT, 0, st>>>(n3, maxdis, mindis, c->fp, dxp, part, S);
+            k_sd_save<<<nblk, QT, 0, st>>>(n3, 0, c->fp, prefp, c->epot, epot0, S);    // PreFP = FP :131
             k_sd_apply<<<cdiv(n, QT), QT, 0, st>>>(n, dxp, c->pos, c->box, c->dsr, c->counters, S);
             k_sd_mark<<<1, 1, 0, st>>>(S, it);
-            if ((rc = mdb_force(c, MDB_EPOT, nullptr)) < 0) return finish(rc);
-            c->launches_total += 2;
+            if ((rc = mdb_force(c, MDB_FORCE | MDB_EPOT, nullptr)) < 0) return finish(rc); // EPOT :122 and the next FP :95
             k_sd_echeck<<<nblk, QT, 0, st>>>(n, minepot, c->epot, epot0, part, S, it);
-            k_sd_save<<<nblk, QT, 0, st>>>(n3, n, c->fp, prefp, c->epot, epot0, S);
+            k_sd_save<<<nblk, QT, 0, st>>>(0, n, c->fp, prefp, c->epot, epot0, S);     // EPOT0 = EPOT :129
         }
         CUDA_TRY(c, cudaGetLastError());
         CUDA_TRY(c, cudaMemcpyAsync(H, S, sizeof(QuenchScal), cudaMemcpyDeviceToHost, st));
