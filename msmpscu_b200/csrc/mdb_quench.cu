@@ -485,11 +485,11 @@ extern "C" int mdb_cg(mdb_ctx *c, int mxnumsteps, int meth, double maxdis, doubl
     // the tail of an iteration, :80-105 / :235-260: energy criterion, then the new direction
     auto tail = [&](int it) -> int {
         int r;
-        if ((r = mdb_force(c, MDB_EPOT, nullptr)) < 0) return r;
+        // the energies (:80) and the forces of the new direction (:88) belong to the same positions: one fused evaluation
+        if ((r = mdb_force(c, MDB_FORCE | MDB_EPOT, nullptr)) < 0) return r;
         k_sd_echeck<<<w.nblk, QT, 0, st>>>(n, minepot, c->epot, w.epot0, w.part, S, it);
         k_sd_save<<<w.nblk, QT, 0, st>>>(0, n, c->fp, w.f0, c->epot, w.epot0, S);
         c->launches_total += 2;
-        if ((r = mdb_force(c, MDB_FORCE, nullptr)) < 0) return r;
         dot(c->fp, w.f0, QD_MF1);
         k_q_cgdir<<<w.nblk, QT, 0, st>>>(w.n3, 0, c->fp, w.f0, w.dir, w.part, S, maxdis, eps, it);
         c->launches_total += 1;
