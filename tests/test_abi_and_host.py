@@ -98,3 +98,26 @@ def test_philox_known_answers():
     assert lib.mdb_thermalize_bits(0x1234ABCD5678, 3, 42, bits) == 0
     assert list(bits[:4]) == pyorc.philox4x32_10((42, 3, 0, 0), (0xABCD5678, 0x1234))
     assert list(bits[4:]) == pyorc.philox4x32_10((42, 3, 1, 0), (0xABCD5678, 0x1234))
+
+
+def test_bench_reference_arm_and_no_gpu_behaviour():
+    """bench.py --impl reference prints one JSON line with the contract's keys (CPU restatement on the host cores); the
+    product arm refuses to run without a CUDA device instead of falling back to anything."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-cells", "8"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+                "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True,
+                             text=True, timeout=300)
+        assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
