@@ -133,6 +133,40 @@ def read_ctrl_file(path, box):
             c.NB_MXNBS = int(_numbers(s[6:])[0])
         elif k == "UPDATEFRE":
             c.NB_UPTAB = int(_numbers(s[10:])[0])
+        elif k == "RANDSEED":                                   # MD_TypeDef_SimCtrlParam.F90:1694
+            c.SEED = [int(v) for v in _numbers(s[9:])] or c.SEED
+        elif k in ("QUENCHSTEP", "QUICKDAMP", "QUICKDUMP", "QUENCH"):   # :2018-2060, MD_SimCtrlParam_GMD.F90:59
+            v = _numbers(s[len(k) + 1:])
+            if v:
+                c.Quench_Steps = int(v[0])
+            st = [t.upper() for t in _strings(s)]
+            if st:
+                m = st[0]
+                c.Quench_LSearch = m.endswith("-LS")
+                m = m[:-3] if c.Quench_LSearch else m
+                c.Quench_Meth = {"LBFGS": "LBFGS", "CG": "CG", "ST": "ST", "DYN": "DYN", "DYNAMICS": "DYN"}.get(m, c.Quench_Meth)
+        elif k in ("STEPBOUND", "STEPCOND"):                    # :1890-1903
+            v = _numbers(s[len(k) + 1:])
+            if len(v) == 1:
+                c.STEEPEST_MxStep = v[0]
+            elif len(v) >= 2:
+                c.STEEPEST_MiStep, c.STEEPEST_MxStep = min(v[0], v[1]), max(v[0], v[1])
+        elif k in ("DELTAPOT", "POTCOND"):                      # :1905-1912
+            v = _numbers(s[len(k) + 1:])
+            if v:
+                c.STEEPEST_MiDelE = v[0]
+        elif k == "ALPHA":                                      # :1876-1888
+            v = _numbers(s[6:])
+            if v:
+                c.STEEPEST_Alpha = v[0]
+        elif k == "PGTOL":                                      # :1747
+            c.LBFGS_PGtol = (_numbers(s[6:]) or [0.0])[0]
+        elif k == "FACTR":                                      # :1761
+            c.LBFGS_Factr = (_numbers(s[6:]) or [10.0])[0]
+        elif k == "MSAVE":                                      # :1775
+            c.LBFGS_MSave = int((_numbers(s[6:]) or [7])[0])
+        elif k == "DRTOL":                                      # :2000
+            c.STRCUT_DRTol = (_numbers(s[6:]) or [0.0])[0]
     c.RU = ru_lu * box.RR
     c.NB_RM = nb_fac * c.RU
     c.LT_CTRL = [TiCtrlParam(TI=temp, METH_EPC=1 if epc else 0) for _ in range(ng)]

@@ -76,6 +76,9 @@ def main():
     for fn in ("W_2000_He1_EAM1_box.dat", "CtrlFile300K.dat", "W_2000_Tetra.cfg"):
         shutil.copyfile(os.path.join(gmd, fn), os.path.join(HERE, "gmd_" + fn))
 
+    # the PARREP example's control file (BASELINE configs[3]): input only
+    shutil.copyfile(os.path.join(REF, "examples", "PARREP_Test", "CtrlFile300K.dat"), os.path.join(HERE, "parrep_CtrlFile300K.dat"))
+
     # exported embedding table (10 significant digits)
     path = os.path.join(REF, "examples", "use_ForceTableGen", "EAM_WHeH_Bonny_JPCM26_2014.embd")
     rows = []

@@ -121,3 +121,21 @@ def test_bench_reference_arm_and_no_gpu_behaviour():
         out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True,
                              text=True, timeout=300)
         assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_control_files_of_the_reference_examples_are_read():
+    """The reference's own control files for BASELINE configs[0] (GMD_Test), the NEB_Test quench run and configs[3]
+    (PARREP_Test) through msmpscu_b200.inputs: cut-offs, list control, time step and the quench / event-detection
+    keywords (Common/MD_TypeDef_SimCtrlParam.F90:1694-2060) land in the SimMDCtrl fields mdlib.Do_Damp reads."""
+    from msmpscu_b200 import inputs
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    box = inputs.read_box_file(os.path.join(g, "W_2000_H1_EAM1_box.dat"))
+    neb = inputs.read_ctrl_file(os.path.join(g, "CtrlFile0K.dat"), box)
+    assert neb.Quench_Steps == 1000 and neb.Quench_Meth == "ST" and not neb.Quench_LSearch
+    assert neb.NB_MXNBS == 256 and neb.NB_UPTAB == 10 and abs(neb.NB_RM[0, 0] / neb.RU[0, 0] - 1.2) < 1e-12
+    assert neb.SEED == [123456] and abs(neb.H - 0.5e-15) < 1e-30
+    par = inputs.read_ctrl_file(os.path.join(g, "parrep_CtrlFile300K.dat"), box)
+    assert par.NB_MXNBS == 400 and abs(par.NB_RM[0, 0] / par.RU[0, 0] - 1.6) < 1e-12
+    assert par.Quench_Steps == 1000 and par.Quench_Meth == "ST"
+    assert par.STEEPEST_MiStep == 1.0e-5 and par.STEEPEST_MxStep == 0.1 and par.STEEPEST_MiDelE == 1.0e-5
+    assert par.STRCUT_DRTol == 0.02 and par.LBFGS_MSave == 7
