@@ -727,3 +727,54 @@ def test_disordered_configurations_tiled_vs_oracle(oracle, seed):
         assert util.relerr(ctx.download(capi.F_XP), gen.download(capi.F_XP)) < 1e-12
         assert util.relerr(ctx.download(capi.F_FP), gen.download(capi.F_FP)) < 1e-9
     ctx.close(); gen.close()
+
+
+def test_parrep_cycle_through_the_mdlib_interface():
+    """One parallel-replica cycle of examples/PARREP_Test driven by its own control file through the reference's procedure
+    names (Appshell/MD_Method_ParRep_GPU.F90: thermalise -> MD block -> Do_Damp -> compare with the quenched start, Do_Compare /
+    &DRTOL): two replicas of the 2000 W + 1 H box as MULTIBOX, 1.6 x RU lists, MAXNB 400, "ST" quench with the file's
+    &STEPBOUND / &DELTAPOT.  40 fs at 300 K leave both replicas in the basin they started from: the quench returns every atom
+    to within DRTOL (0.02 LU) of the quenched start, lowers the energy, and no event is flagged."""
+    from msmpscu_b200 import inputs, mdlib
+    g = util.GOLD
+    box = inputs.read_box_file(os.path.join(g, "W_2000_H1_EAM1_box.dat"))
+    ctl = inputs.read_ctrl_file(os.path.join(g, "parrep_CtrlFile300K.dat"), box)
+    neb = np.load(os.path.join(g, "neb_gmd_react.npz"))
+    boxes = []
+    for r in range(2):
+        b = inputs.read_box_file(os.path.join(g, "W_2000_H1_EAM1_box.dat"))
+        b.ITYP = neb["ityp"].astype(np.int32)
+        b.XP = neb["pos"] * b.RR
+        b.allocate()
+        boxes.append(b)
+    dev = mdlib.DeviceState(0)
+    fc = mdlib.Register_ForceClass(box.PotType)
+    mdlib.Initialize_Globle_Variables_DEV(dev, boxes, ctl)
+    mdlib.Init_Forcetable_Dev(dev, boxes, ctl, fc)
+    mdlib.Initialize_NeighboreList_DEV(dev, boxes, ctl)
+    assert mdlib.Cal_NeighBoreList_DEV(dev, boxes, ctl) == 0
+    mdlib.CalForce_ForceClass(dev, boxes, ctl, fc)
+    # the quenched start (SimBox0K of Do_ChangeDetect)
+    assert mdlib.Do_Damp(dev, boxes, ctl, fc)[0] != 0
+    x0 = dev.ctx.download(capi.F_XP)
+    e0 = dev.ctx.download(capi.F_EPOT).sum()
+    # thermalise both replicas (different numbers per replica: the key is the ORIGINAL atom id) and run 80 steps
+    mdlib.Thermalizing_MC_DEV(dev, boxes, ctl, 600.0)
+    v = dev.ctx.download(capi.F_XP1)
+    assert not np.allclose(v[:2001], v[2001:])
+    mdlib.For_Steps(dev, 0, 80, boxes, ctl)
+    mdlib.CalEpot_ForceClass(dev, boxes, ctl, fc)
+    e_hot = dev.ctx.download(capi.F_EPOT).sum()
+    assert e_hot > e0
+    mdlib.Cal_NeighBoreList_DEV(dev, boxes, ctl)
+    fl = mdlib.Do_Damp(dev, boxes, ctl, fc)
+    assert fl[0] != 0
+    mdlib.ResetXP1(dev, boxes)
+    x1 = dev.ctx.download(capi.F_XP)
+    e1 = dev.ctx.download(capi.F_EPOT).sum()
+    d = x1 - x0
+    d -= np.round(d / box.ZL) * box.ZL
+    dmax = np.sqrt((d ** 2).sum(axis=1)).max() / box.RR
+    assert dmax < ctl.STRCUT_DRTol, dmax          # Do_Compare: no atom moved by more than DRTOL -> no event
+    assert abs(e1 - e0) < 0.02 * 1.60219e-12      # back in the same minimum (the quench stops at 1e-5 eV per atom per step)
+    dev.ctx.close()
