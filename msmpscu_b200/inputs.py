@@ -27,7 +27,9 @@ def _numbers(s):
     s = re.sub(r'"[^"]*"', " ", s)
     # numbers that are part of a word (e.g. "A-B=") are fine; identifiers with digits (#1) are stripped
     s = re.sub(r"#\s*\d+", " ", s)
-    return [float(t.replace("d", "e").replace("D", "e")) for t in _NUM.findall(re.sub(r"[A-Za-z_][A-Za-z_0-9]*", " ", s))]
+    # words are dropped, but not the exponent letter of a number (1.0e-5, 1.D-5): a word starts after a non-digit
+    s = re.sub(r"(?<![\d.])[A-Za-z_][A-Za-z_0-9]*", " ", s)
+    return [float(t.replace("d", "e").replace("D", "e")) for t in _NUM.findall(s)]
 
 
 def _strings(s):
