@@ -197,3 +197,28 @@ def test_moldy_import_against_the_formulas(tmp_path):
     g = np.arange(nembd) * t.rhod
     assert np.allclose(t.fembd[1:], -np.sqrt(g[1:]) * ev, rtol=1e-13) and t.fembd[0] == 0.0
     assert np.allclose(t.dfembd[1:], -0.5 / np.sqrt(g[1:]) * ev, rtol=1e-13)
+
+
+REF_FS = "/root/reference/examples/use_ForceTableGen/EM_TB_WANGJUN_W-HE_2010"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FS + ".pair"), reason="reads the reference tree (build container only)")
+def test_import_of_a_reference_written_table_file():
+    """Format compatibility of Import_ForceTable / Register_Imported_ForceTable with files the REFERENCE wrote: the 5-id
+    FS_TYPE export examples/use_ForceTableGen/EM_TB_WANGJUN_W-HE_2010.pair/.embd (4 + 2 MB, read in place, not copied) is
+    imported for PTYPE = 1 onto its own grid and must give back the Ackland-Thetford W tables this package generates, to the
+    file's print precision; the FS embedding columns hold -sqrt(rho)."""
+    ntab, rmax = 10000, 10.0e-8
+    info_t = forcetable.Register_Imported_ForceTable(REF_FS, [[1]], ntab, 10000, rmax)
+    assert info_t.PotType == "FS_TYPE" and info_t.nkind == 1 and list(info_t.kpair) == [1]
+    gen = forcetable.Create_Interaction_ForceTable(capi.LIB_ACKLAND_FS_W, [[1]], ntab, 10000, rmax, pot_type="FS_TYPE")
+    for name in ("potr", "fpotr", "potb", "fpotb"):
+        a, b = getattr(info_t, name), getattr(gen, name)
+        scale = np.max(np.abs(b))
+        assert np.max(np.abs(a - b)) <= 2e-9 * scale, (name, np.max(np.abs(a - b)) / scale)
+    # a two-group box that uses ids 1 (W-W), 4 (W<-He) , 3 (He<-W), 2 (He-He): kinds numbered in first-appearance order
+    t2 = forcetable.Register_Imported_ForceTable(REF_FS, [[1, 4], [3, 2]], 2000, 2000, rmax)
+    assert t2.nkind == 4 and list(t2.kpair) == [1, 3, 2, 4] and list(t2.kembd) == [1, 2]
+    rho = np.arange(2000) * t2.rhod
+    fe = t2.fembd.reshape(-1, t2.nkind1).T[0]
+    assert np.allclose(fe[5:], -np.sqrt(rho[5:]), rtol=2e-5)      # FS export: F = -sqrt(RHO) (erg, RHO in erg^2), re-gridded
