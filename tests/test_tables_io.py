@@ -222,3 +222,22 @@ def test_import_of_a_reference_written_table_file():
     rho = np.arange(2000) * t2.rhod
     fe = t2.fembd.reshape(-1, t2.nkind1).T[0]
     assert np.allclose(fe[5:], -np.sqrt(rho[5:]), rtol=2e-5)      # FS export: F = -sqrt(RHO) (erg, RHO in erg^2), re-gridded
+
+
+REF_CU = "/root/reference/examples/NIST_Potentials/Cu_EAM/Cu1.eam.fs.setfl"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CU + ".pair"), reason="reads the reference tree (build container only)")
+def test_import_of_the_reference_written_cu_tables(setfl):
+    """The reference's own export of its setfl import (Cu1.eam.fs.setfl.pair/.embd, read in place) re-imported on the same
+    grid equals this package's direct setfl import, to the file's print precision (away from the file's 1e12 -> O(10) step)."""
+    t = forcetable.NIST_Register_Interaction_Table(setfl, 10000, 10000)
+    back = forcetable.Register_Imported_ForceTable(REF_CU, [[1]], 10000, 10000, t.Rmax)
+    assert back.PotType == "EAM_TYPE"
+    r = (np.arange(1, 10001) / t.csi) ** 2 * 1e8
+    far = r > 0.2
+    for name in ("potr", "fpotr", "potb", "fpotb"):
+        a, b = getattr(back, name)[far], getattr(t, name)[far]
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-12 * np.max(np.abs(b)))) < 3e-9, name
+    assert abs(back.rhod - t.rhod) < 1e-8 * t.rhod
+    assert np.max(np.abs(back.fembd - t.fembd)) < 1e-8 * np.max(np.abs(t.fembd))
