@@ -269,6 +269,21 @@ k_avstress_generic(ForceParams P, const double4 *__restrict__ pos, const int *__
     for (int q = 0; q < 9; q++) ap[i + (size_t)q * P.n] = p[q];
 }
 
+// final sum of nblk per-block virial partials (c->vpart) -> vt[9], divided by the number of boxes (:1462-1463)
+int mdb_virial_finish(mdb_ctx *c, int nblk, double *vt)
+{
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        k_virial_reduce<<<1, 256, 0, c->stream>>>(nblk, c->vpart, c->vpart + (size_t)nblk * 9, 1.0 / (double)c->nbox);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    if (vt) {
+        CUDA_TRY(c, cudaMemcpyAsync(vt, c->vpart + (size_t)nblk * 9, sizeof(double) * 9, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return MDB_OK;
+}
+
 static void fill_params(mdb_ctx *c, ForceParams &P);
 int mdb_avstress_generic(mdb_ctx *c, double *d_ap)
 {

@@ -435,6 +435,7 @@ struct TilePassArgs {
     const double2 *g_potb, *g_fpotr, *g_fpotb, *g_dfembd;
     const double2 *g_potr, *g_fembd;   // PASS 3 (per-atom energy): pair term and embedding VALUE tables
     double *epot;
+    double *vpart;         // VIR: per-warp partial virial tensors (9 doubles each), summed by mdb_virial_finish
     int den_too;           // PASS 3 also stores dF/drho (what pass 1 produces): its density sum is the same sum
     int ntab, nembd, pot_type;
     double csi, rhod;
@@ -564,7 +565,7 @@ __host__ __device__ __forceinline__ size_t tp_buf_bytes(int hcap, int ocap, int 
 __host__ __device__ __forceinline__ size_t tp_tab_bytes(int ktab) { return al128(sizeof(double2) * (size_t)(ktab + 2)); }
 
 // PASS 1: rho -> DEN.  PASS 2: forces.  G lanes per atom.  MT: more than one atom type.  FUSE: EPC + corrector epilogue.
-template <int PASS, int G, bool MT, bool FUSE, int NT>
+template <int PASS, int G, bool MT, bool FUSE, int NT, bool VIR = false>
 __global__ void __launch_bounds__(NT, 1)
 k_tile_pass(TileParams P, TilePassArgs A)
 {
@@ -585,6 +586,9 @@ k_tile_pass(TileParams P, TilePassArgs A)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % G;      // lane within the atom's group
+    // VIR (CALPTENSOR_KERNEL, MD_EAM_ForceTable_GPU.F90:1222-1232): per-lane partial sums of 1/2 FORTOT s_a s_b over every pair
+    // this lane evaluates in the whole launch (xx, xy, xz, yy, yz, zz: the tensor is symmetric); reduced once at the end
+    double vxx = 0.0, vxy = 0.0, vxz = 0.0, vyy = 0.0, vyz = 0.0, vzz = 0.0;
 
     // ---- tables for kind0, rows kmin..kmin+ktab : staged once per (persistent) CTA
     //      pass 1: {POTB[kk], POTB[kk+1]}         (one 16-byte read per pair)
@@ -792,6 +796,11 @@ k_tile_pass(TileParams P, TilePassArgs A)
                         acc0 = fma(ft, sx, acc0);
                         acc1 = fma(ft, sy, acc1);
                         acc2 = fma(ft, sz, acc2);
+                        if (VIR) {
+                            const double hx = 0.5 * ft * sx, hy = 0.5 * ft * sy, hz = 0.5 * ft * sz;
+                            vxx = fma(hx, sx, vxx); vxy = fma(hx, sy, vxy); vxz = fma(hx, sz, vxz);
+                            vyy = fma(hy, sy, vyy); vyz = fma(hy, sz, vyz); vzz = fma(hz, sz, vzz);
+                        }
                     }
                     return in && !fast;
                 };
@@ -812,9 +821,15 @@ k_tile_pass(TileParams P, TilePassArgs A)
                     const double f = pair_slow<PASS == 3 ? 1 : PASS>(me, pj, A.csi, PASS == 1 ? A.g_potb : A.g_fpotr, A.g_fpotb, A.ntab + 2, k0, k1);
                     if (PASS == 1) acc0 += f;
                     else {
-                        acc0 = fma(f, me.x - pj.x, acc0);
-                        acc1 = fma(f, me.y - pj.y, acc1);
-                        acc2 = fma(f, me.z - pj.z, acc2);
+                        const double sx = me.x - pj.x, sy = me.y - pj.y, sz = me.z - pj.z;
+                        acc0 = fma(f, sx, acc0);
+                        acc1 = fma(f, sy, acc1);
+                        acc2 = fma(f, sz, acc2);
+                        if (VIR) {
+                            const double hx = 0.5 * f * sx, hy = 0.5 * f * sy, hz = 0.5 * f * sz;
+                            vxx = fma(hx, sx, vxx); vxy = fma(hx, sy, vxy); vxz = fma(hx, sz, vxz);
+                            vyy = fma(hy, sy, vyy); vyz = fma(hy, sz, vyz); vzz = fma(hz, sz, vzz);
+                        }
                     }
                 };
 
@@ -927,6 +942,19 @@ k_tile_pass(TileParams P, TilePassArgs A)
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[b]);
             if (++b == nbuf) { b = 0; u++; }
+        }
+    }
+    if (VIR) { // one partial tensor per warp -> vpart[blockIdx.x * NW + warp][9] (column-major 3x3), summed by k_virial_reduce
+               // (no shared memory: the dynamic window already takes the whole per-CTA budget)
+        double v6[6] = {vxx, vxy, vxz, vyy, vyz, vzz};
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            for (int off = 16; off > 0; off >>= 1) v6[q] += __shfl_xor_sync(0xffffffffu, v6[q], off);
+        if (lane == 0) {
+            double *o = A.vpart + ((size_t)blockIdx.x * NW + warp) * 9;
+            o[0] = v6[0]; o[1] = v6[1]; o[2] = v6[2];
+            o[3] = v6[1]; o[4] = v6[3]; o[5] = v6[4];
+            o[6] = v6[2]; o[7] = v6[4]; o[8] = v6[5];
         }
     }
     // atoms parked outside the cells (out of box, inactive): zero outputs, as the generic path does
@@ -1141,7 +1169,7 @@ int mdb_tiled_nlist(mdb_ctx *c)
     return mdb_fail(c, MDB_ERR_ARG, "tiled path: unsupported lane-group size %d", c->tiled.G);
 }
 
-template <int PASS, int G, bool MT, bool FUSE, int NT>
+template <int PASS, int G, bool MT, bool FUSE, int NT, bool VIR = false>
 static int launch_pass(mdb_ctx *c, int fuse, double hs2)
 {
     TiledState &S = c->tiled;
@@ -1151,6 +1179,17 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.nbl = S.nbl; A.fp = c->fp; A.counters = c->counters; A.desc = (const TileDesc *)S.desc;
     A.g_potb = t.potb; A.g_fpotr = t.fpotr; A.g_fpotb = t.fpotb; A.g_dfembd = t.dfembd;
     A.g_potr = t.potr; A.g_fembd = t.fembd; A.epot = c->epot;
+    A.vpart = nullptr;
+    if (VIR) {
+        const int npart = S.grid * (NT / 32) + 2; // one partial per warp, + the reduced tensor
+        if (c->vpart_n < npart) {
+            if (c->vpart) cudaFree(c->vpart);
+            c->vpart = nullptr;
+            CUDA_TRY(c, cudaMalloc(&c->vpart, sizeof(double) * 9 * (size_t)npart));
+            c->vpart_n = npart;
+        }
+        A.vpart = c->vpart;
+    }
     A.den_too = (PASS == 3 && fuse == -1) ? 1 : 0;
     constexpr int PI = (PASS == 3) ? 1 : PASS - 1; // the energy pass shares the plan (window, classes, shared memory) of pass 2
     A.ntab = t.ntab; A.nembd = t.nembd; A.pot_type = t.pot_type; A.csi = t.csi; A.rhod = t.rhod;
@@ -1169,7 +1208,7 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     if (!c->epc.on) A.fuse &= ~1;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) A.kembd[i] = t.kembd[i];
-    auto kern = k_tile_pass<PASS, G, MT, FUSE, NT>;
+    auto kern = k_tile_pass<PASS, G, MT, FUSE, NT, VIR>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_pass[PI]));
     ProfScope ps(c, PASS == 1 ? MDB_K_PASS1 : (PASS == 2 ? MDB_K_PASS2 : MDB_K_EPOT));
     kern<<<S.grid, NT, S.smem_pass[PI], c->stream>>>(S.P, A);
@@ -1181,7 +1220,7 @@ template <int G, bool MT, int NT>
 static int launch_force(mdb_ctx *c, unsigned flags, int fuse, double hs2)
 {
     int rc = MDB_OK;
-    const bool need_den = (flags & (MDB_FORCE | MDB_DEN)) && !(flags & MDB_NOPASS1);
+    const bool need_den = (flags & (MDB_FORCE | MDB_DEN | MDB_VIRIAL)) && !(flags & MDB_NOPASS1);
     // energies and forces together (every quench iteration): the energy pass forms the same density sum as pass 1, so it
     // also stores dF/drho and pass 1 is not launched
     const bool den_in_epot = need_den && (flags & MDB_EPOT);
@@ -1189,7 +1228,8 @@ static int launch_force(mdb_ctx *c, unsigned flags, int fuse, double hs2)
     if (rc < 0) return rc;
     if (den_in_epot) rc = launch_pass<3, G, MT, false, NT>(c, -1, 0.0);
     if (rc < 0) return rc;
-    if (flags & MDB_FORCE) rc = fuse ? launch_pass<2, G, MT, true, NT>(c, fuse, hs2) : launch_pass<2, G, MT, false, NT>(c, 0, 0.0);
+    if (flags & MDB_VIRIAL) rc = launch_pass<2, G, MT, false, NT, true>(c, 0, 0.0);   // forces + virial (CALPTENSOR)
+    else if (flags & MDB_FORCE) rc = fuse ? launch_pass<2, G, MT, true, NT>(c, fuse, hs2) : launch_pass<2, G, MT, false, NT>(c, 0, 0.0);
     if (rc < 0) return rc;
     if ((flags & MDB_EPOT) && !den_in_epot) rc = launch_pass<3, G, MT, false, NT>(c, 0, 0.0);
     return rc;

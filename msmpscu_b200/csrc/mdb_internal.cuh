@@ -202,6 +202,7 @@ int mdb_nlist_nearest(mdb_ctx *c, int nearest); // mdb_nlist.cu
 int mdb_indi_ensure(mdb_ctx *c);             // mdb_api.cu : materialise INDI after a tiled rebuild
 int mdb_force_generic(mdb_ctx *c, unsigned flags, double *vt); // mdb_force.cu
 int mdb_avstress_generic(mdb_ctx *c, double *d_ap);            // mdb_force.cu
+int mdb_virial_finish(mdb_ctx *c, int nblk, double *vt);       // mdb_force.cu
 int mdb_tiled_plan(mdb_ctx *c);               // mdb_force_tiled.cu
 int mdb_tiled_nlist(mdb_ctx *c);
 void mdb_tiled_free(mdb_ctx *c);

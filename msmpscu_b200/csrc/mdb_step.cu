@@ -430,20 +430,11 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     if (c->dd_on && (flags & MDB_VIRIAL))
         return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: the virial is not available in slab-decomposed runs yet");
     if (c->tiled.active && !c->list_reordered) {
-        // density, force and per-atom energy passes on the tiled path; the virial (output steps only) runs on the generic
-        // kernels over the reference-format list, which is materialised on demand
-        unsigned fast = flags & (MDB_FORCE | MDB_DEN | MDB_NOPASS1 | MDB_EPOT);
-        if (flags & MDB_VIRIAL) fast &= MDB_EPOT;
-        if (fast) {
-            int rc = mdb_force_tiled(c, fast);
-            if (rc < 0) return rc;
-        }
-        const unsigned rest = flags & ~fast;
-        if (rest & MDB_VIRIAL) {
-            int rc = mdb_indi_ensure(c);
-            if (rc < 0) return rc;
-            return mdb_force_generic(c, rest & ~MDB_DEN, vtensor);
-        }
+        // density, force (+ virial) and per-atom energy passes all run on the tiled path
+        unsigned fast = flags & (MDB_FORCE | MDB_DEN | MDB_NOPASS1 | MDB_EPOT | MDB_VIRIAL);
+        int rc = mdb_force_tiled(c, fast);
+        if (rc < 0) return rc;
+        if (flags & MDB_VIRIAL) return mdb_virial_finish(c, c->tiled.grid * (c->tiled.threads / 32), vtensor); // one partial tensor per warp
         return MDB_OK;
     }
     return mdb_force_generic(c, flags, vtensor);
