@@ -144,7 +144,8 @@ int mdb_nlist_clear(mdb_ctx *ctx);
 /* ------------------------------------------------------------------------------------
  * force class slots (type MDForceClassGPU, CommonGPU/MD_ForceClass_Register_GPU.F90:248-259)
  * vtensor (3,3) column-major, already divided by the number of boxes (COPYOUT_VIRIALTENSOR :1462);
- * may be NULL unless MDB_VIRIAL is set.
+ * may be NULL unless MDB_VIRIAL is set.  In a slab-decomposed run (mdb_dd_*) it is the partial sum over the pairs whose
+ * first atom this rank owns: the sum over ranks is the tensor of the box.
  * ---------------------------------------------------------------------------------- */
 int mdb_force(mdb_ctx *ctx, unsigned flags, double vtensor[9]);
 

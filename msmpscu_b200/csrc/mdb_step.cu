@@ -427,8 +427,8 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     CUDA_TRY(c, cudaSetDevice(c->dev));
     if (c->dd_on && !c->tiled.active)
         return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: slab decomposition needs the tiled path");
-    if (c->dd_on && (flags & MDB_VIRIAL))
-        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: the virial is not available in slab-decomposed runs yet");
+    // slab-decomposed runs: vtensor is this rank's PARTIAL sum (every directed pair whose first atom it owns, each halved
+    // as in CALPTENSOR_KERNEL :1222); the caller adds the partial tensors of all ranks (SlabDomain.force_virial)
     if (c->tiled.active && !c->list_reordered) {
         // density, force (+ virial) and per-atom energy passes all run on the tiled path
         unsigned fast = flags & (MDB_FORCE | MDB_DEN | MDB_NOPASS1 | MDB_EPOT | MDB_VIRIAL);

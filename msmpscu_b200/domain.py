@@ -153,6 +153,23 @@ class SlabDomain:
             c.epc_correct(h)
             mark("correct")
 
+    def force_virial(self):
+        """pCalPTensor on the decomposed box (CALPTENSOR_EAM_Force_Table2A_DEV, MD_EAM_ForceTable_GPU.F90:1366): density pass,
+        DEN ghost exchange, force pass with the virial epilogue over the owned tiles, then ONE 72-byte all-reduce of the
+        per-rank partial tensors (the reference sums its per-device partial tensors on the host, :1434-1466).
+        Returns VTENSOR (3,3), identical on every rank."""
+        c = self.ctx
+        with self.torch.cuda.stream(self.stream):
+            c.force(capi.DEN)
+            if self.world > 1:
+                self._exchange()
+            vt = c.force(capi.FORCE | capi.VIRIAL | capi.NOPASS1)
+            if self.world > 1:
+                t = self.torch.as_tensor(np.ascontiguousarray(vt), device=self.device)
+                self.dist.all_reduce(t, group=self.group)
+                vt = t.cpu().numpy()
+        return vt
+
     def _mark(self, name):
         if self.phase_ms is None:
             return

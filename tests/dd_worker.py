@@ -60,6 +60,11 @@ def main():
     full.force(capi.EPOT); ctx.force(capi.EPOT)
     worst["epot"] = util.relerr(ctx.download(capi.F_EPOT, capi.ORDER_CELL)[a0:a1], full.download(capi.F_EPOT, capi.ORDER_CELL)[a0:a1])
     ok &= worst["epot"] < 1e-12
+    # virial: per-rank partial tensors of the owned tiles, summed over the ranks, against the single-GPU tensor
+    vt_full = full.force(capi.FORCE | capi.VIRIAL)
+    vt_dd = dom.force_virial()
+    worst["virial"] = util.relerr(vt_dd, vt_full)
+    ok &= worst["virial"] < 1e-10
     kf, _ = full.nlist_copyout(capi.ORDER_CELL)
     kd, _ = ctx.nlist_copyout(capi.ORDER_CELL)
     ok &= bool(np.array_equal(kf[a0:a1], kd[a0:a1]))
