@@ -186,7 +186,10 @@ def run_ours(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util
     ctx = capi.Context(local)
-    stream = torch.cuda.current_stream()
+    # an explicit torch stream (a non-null handle): the library launches on it and the timing events are recorded on it.
+    # (the null handle of torch's default stream would make the context fall back to its own stream, mdb_ctx_set_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
     ctx.set_option(capi.OPT_FORCE_PATH, {"auto": 0, "generic": 1, "tiled": 2}[args.path])

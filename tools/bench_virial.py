@@ -31,7 +31,8 @@ def main():
     vts = {}
     for name, path in (("generic", 1), ("tiled", 2)):
         ctx = util.make_ctx(c, build=False, force_path=path)
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.Stream()          # non-null handle: the library launches on it, the events are recorded on it
+        torch.cuda.set_stream(stream)
         ctx.set_stream(stream.cuda_stream)
         ctx.nlist_build()
         for _ in range(3):
