@@ -27,6 +27,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line: NCCL_DEBUG=VERSION makes NCCL itself print "NCCL version ..." there (INFO / WARN are left alone)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 MD_PER_STEP = 10      # NB_UPTAB: MD steps per neighbour-list period
 H = 0.5e-15           # s
