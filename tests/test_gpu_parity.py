@@ -778,3 +778,32 @@ def test_parrep_cycle_through_the_mdlib_interface():
     assert dmax < ctl.STRCUT_DRTol, dmax          # Do_Compare: no atom moved by more than DRTOL -> no event
     assert abs(e1 - e0) < 0.02 * 1.60219e-12      # back in the same minimum (the quench stops at 1e-5 eV per atom per step)
     dev.ctx.close()
+
+
+def test_slab_domain_single_rank_step_and_virial():
+    """SlabDomain with one rank (no process group): its step is the same GMD step as mdb_run (For_One_Step,
+    Appshell/MD_Method_GenericMD_GPU.F90:596-627) and force_virial returns the tensor of pCalPTensor
+    (MD_EAM_ForceTable_GPU.F90:1366) -- the N = 1 end of the slab-decomposed path that tests/test_gpu_dd.py runs on 2 and 4 GPUs."""
+    from msmpscu_b200.domain import SlabDomain
+    c = util.bcc_case((8, 8, 12), seed=77, temp=600.0)
+    h, it0, nup, nsteps = 0.5e-15, 1, 5, 12
+    epc = ([1], [300.0], [1.0e-12], [0.1], [100.0 * util.CP_EVERG])
+    full = util.make_ctx(c, force_path=capi.FORCE_PATH_TILED)
+    full.epc_set(*epc)
+    full.force(capi.FORCE)
+    full.run(0, nsteps, it0, nup, h)
+    ctx = util.make_ctx(c, build=False, force_path=capi.FORCE_PATH_TILED)
+    ctx.epc_set(*epc)
+    dom = SlabDomain(ctx, 0)
+    assert dom.world == 1
+    dom.rebuild()
+    ctx.force(capi.FORCE)
+    for it in range(nsteps):
+        dom.step(it, it0, nup, h)
+    assert dom.owned() == (0, ctx.n)
+    for f, tol in ((capi.F_XP, 1e-13), (capi.F_XP1, 1e-10), (capi.F_FP, 1e-10)):
+        assert util.relerr(ctx.download(f, capi.ORDER_CELL), full.download(f, capi.ORDER_CELL)) < tol
+    vt = dom.force_virial()
+    vt_full = full.force(capi.FORCE | capi.VIRIAL)
+    assert np.abs(vt_full).max() > 0.0 and util.relerr(vt, vt_full) < 1e-10
+    full.close(); ctx.close()
