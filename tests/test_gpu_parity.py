@@ -807,3 +807,40 @@ def test_slab_domain_single_rank_step_and_virial():
     vt_full = full.force(capi.FORCE | capi.VIRIAL)
     assert np.abs(vt_full).max() > 0.0 and util.relerr(vt, vt_full) < 1e-10
     full.close(); ctx.close()
+
+
+@pytest.mark.parametrize("name", ["bcc_7x9x11", "neb_WH", "fcc_cu_setfl"])
+def test_tiled_launch_variants_parity(oracle, name):
+    """Every selectable shape of the tiled kernels -- 2 / 4 / 8 lanes per atom, 512- / 768-thread pass CTAs, 2 / 3 pipeline
+    stages, with and without the distance classes -- against the CPU oracle (CalForceTest.F90:113-147 restated): forces, DEN,
+    EPOT and the virial of the force pass's virial epilogue; the neighbour counts stay the reference's bit for bit."""
+    c = CASES[name]()
+    ref = _oracle_list(oracle, c)
+    gid = ref["gid"] - 1
+    T = util.oracle_tables(oracle, c)
+    fp, den, vt, ep = oracle.force(c.xp[gid], c.ityp[gid], ref["statu"][gid], ref["kvois"], ref["indi"], c.zl, c.ifpd,
+                                   T, virial=True, epot=True)
+    ran = 0
+    for lanes in (2, 4, 8):
+        for threads in (512, 768):
+            for stages, classes in ((2, 1), (3, 1), (2, 0)):
+                ctx = util.make_ctx(c, build=False, force_path=capi.FORCE_PATH_TILED)
+                ctx.set_option(capi.OPT_TILED_LANES, lanes)
+                ctx.set_option(capi.OPT_TILED_THREADS, threads)
+                ctx.set_option(capi.OPT_TILED_STAGES, stages)
+                ctx.set_option(capi.OPT_TILED_CLASSES, classes)
+                ctx.nlist_build()
+                tag = "lanes %d threads %d stages %d classes %d" % (lanes, threads, stages, classes)
+                assert ctx.get_option(capi.OPT_ACTIVE_PATH) == capi.FORCE_PATH_TILED, tag
+                vt_gpu = ctx.force(capi.FORCE | capi.VIRIAL | capi.EPOT)
+                assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < FORCE_RTOL, tag
+                assert util.relerr(ctx.download(capi.F_DEN, capi.ORDER_CELL), den) < FORCE_RTOL, tag
+                assert util.relerr(ctx.download(capi.F_EPOT, capi.ORDER_CELL), ep) < FORCE_RTOL, tag
+                assert util.relerr(vt_gpu, vt / c.nbox) < FORCE_RTOL, tag
+                ctx.force(capi.FORCE)          # the force-only kernels (pass 1 + pass 2 without the epilogue)
+                assert util.relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < FORCE_RTOL, tag
+                kv, _ = ctx.nlist_copyout(capi.ORDER_CELL)
+                assert np.array_equal(kv, ref["kvois"]), tag
+                ctx.close()
+                ran += 1
+    assert ran == 18
