@@ -20,6 +20,7 @@ what makes the exchange two plain range copies per neighbour.
 import numpy as np
 
 from . import capi
+from .constants import CP_KB
 
 
 class _DevArray:
@@ -169,6 +170,22 @@ class SlabDomain:
                 self.dist.all_reduce(t, group=self.group)
                 vt = t.cpu().numpy()
         return vt
+
+    def global_t(self):
+        """Cal_GlobalT_DEV (CommonGPU/MD_DiffScheme_GPU.F90:1042-1064) on the decomposed box: the EKIN kernel over the arrays of
+        this rank, sum and count of EKIN >= 0 over its OWNED atoms (velocities of the other atoms are stale here), one
+        all-reduce of the two numbers, CURT = 2*sum/count/(3*CP_KB) (:1062).  Identical on every rank."""
+        c, t = self.ctx, self.torch
+        with t.cuda.stream(self.stream):
+            c.ekin()
+            a0, a1 = self.owned()
+            ek = t.as_tensor(_DevArray(c.devptr(capi.F_EKIN), (c.n,), "<f8"), device=self.device)[a0:a1]
+            ok = ek >= 0.0
+            acc = t.stack((t.where(ok, ek, t.zeros_like(ek)).sum(), ok.sum().to(t.float64)))
+            if self.world > 1:
+                self.dist.all_reduce(acc, group=self.group)
+            s, n = (float(v) for v in acc.tolist())
+        return 2.0 * s / n / (3.0 * CP_KB)
 
     def _mark(self, name):
         if self.phase_ms is None:

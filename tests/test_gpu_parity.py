@@ -806,6 +806,9 @@ def test_slab_domain_single_rank_step_and_virial():
     vt = dom.force_virial()
     vt_full = full.force(capi.FORCE | capi.VIRIAL)
     assert np.abs(vt_full).max() > 0.0 and util.relerr(vt, vt_full) < 1e-10
+    # Cal_GlobalT_DEV over the owned atoms (MD_DiffScheme_GPU.F90:1042-1064)
+    t_full = full.global_t()
+    assert 100.0 < t_full < 2000.0 and abs(dom.global_t() - t_full) < 1e-10 * t_full
     full.close(); ctx.close()
 
 
