@@ -65,6 +65,10 @@ def main():
     vt_dd = dom.force_virial()
     worst["virial"] = util.relerr(vt_dd, vt_full)
     ok &= worst["virial"] < 1e-10
+    # temperature: Cal_GlobalT over the owned atoms of every rank, one all-reduce
+    t_full = full.global_t()
+    worst["global_t"] = abs(dom.global_t() - t_full) / t_full
+    ok &= worst["global_t"] < 1e-10
     kf, _ = full.nlist_copyout(capi.ORDER_CELL)
     kd, _ = ctx.nlist_copyout(capi.ORDER_CELL)
     ok &= bool(np.array_equal(kf[a0:a1], kd[a0:a1]))
