@@ -22,7 +22,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import capi, forcetable
-from .constants import (CP_A2CM, CP_AU2G, CP_EVERG, CP_FS2S, CP_KB, CP_PS2S, CP_STATU_ACTIVE)
+from .constants import (CP_A2CM, CP_AU2G, CP_CGS2KBAR, CP_ERGEV, CP_EVERG, CP_FS2S, CP_KB, CP_PS2S, CP_STATU_ACTIVE, CP_STATU_FIXPOS,
+                        CP_STATU_FIXPOSX, CP_STATU_FIXPOSY, CP_STATU_FIXPOSZ)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -51,6 +52,7 @@ class SimMDBox:
     EKIN: np.ndarray = None
     STATU: np.ndarray = None
     VTENSOR: np.ndarray = field(default_factory=lambda: np.zeros((3, 3)))
+    PROP: np.ndarray = None              # (NGROUP) per-group status bits (CP_STATU_FIXPOS...); None = none set
 
     def allocate(self):
         n = self.NPRT
@@ -398,9 +400,54 @@ def For_Steps(dev, ITIME0, nsteps, SimBox, CtrlParam):
 
 
 def Cal_thermal_quantities(SimBox):
-    """T, cohesive energy, Hamiltonian per atom (Common/MD_TypeDef_SimBox.F90:5048-5170)."""
+    """Cal_thermal_quantities_SimMDBox (Common/MD_TypeDef_SimBox.F90:5048-5170), the host routine the reference runs on output
+    steps over the arrays copied out of the device: mass-weighted drift velocity of the active atoms of the groups whose
+    PROP carries no FIXPOS bit (:5063-5090), kinetic tensor of the drift-free velocities (:5092-5123), VOLUME, PTENSOR =
+    (KTENSOR + VTENSOR) / VOLUME (:5125-5131), TEMPERATURE from the trace of KTENSOR (:5133), SPRESS0/1 in kbar (:5150-5152),
+    AVEPOT in eV over the active atoms (:5155-5156) and HARMIL in erg (:5159-5163).  Groups are addressed through ITYP (the
+    reference's IPA ranges hold the atoms of one type).  As in the reference, row d of BOXSHAPE is applied to XP1(I,1:3) minus
+    the d-th drift component (:5096-5101), and a fixed component contributes nothing (the reference leaves it unset).
+    Also stores the results on SimBox, as the reference does."""
+    n, ng = SimBox.NPRT, SimBox.NGROUP
     act = (SimBox.STATU & CP_STATU_ACTIVE) == CP_STATU_ACTIVE
-    ek = SimBox.EKIN[act & (SimBox.EKIN > -1e31)]
-    n = int(act.sum())
-    return dict(TEMP=2.0 * ek.sum() / (3.0 * CP_KB * max(len(ek), 1)), AVEPOT=SimBox.EPOT[act].sum() / max(n, 1),
-                HARMIL=(SimBox.EPOT[act].sum() + ek.sum()) / max(n, 1))
+    prop = np.asarray(getattr(SimBox, "PROP", None) if getattr(SimBox, "PROP", None) is not None else np.zeros(ng, dtype=np.int64))
+    cm = np.asarray(SimBox.CM, dtype=np.float64)
+    shape = np.asarray(SimBox.BOXSHAPE, dtype=np.float64)
+    free_group = [(int(prop[k]) & CP_STATU_FIXPOS) == 0 for k in range(ng)]
+    vv0, tcm, anprt = np.zeros(3), 0.0, 0
+    for k in range(ng):
+        if not free_group[k]:
+            continue
+        m = act & (SimBox.ITYP == k + 1)
+        cnt = int(m.sum())
+        vv0 += SimBox.XP1[m].sum(axis=0) * cm[k]
+        tcm += cm[k] * cnt
+        anprt += cnt
+    vv0 = vv0 / tcm
+    cxp1 = np.zeros((n, 3))
+    for d, bit in enumerate((CP_STATU_FIXPOSX, CP_STATU_FIXPOSY, CP_STATU_FIXPOSZ)):
+        m = act & ((SimBox.STATU & bit) == 0)
+        cxp1[m, d] = ((SimBox.XP1[m] - vv0[d]) * shape[d]).sum(axis=1)
+    ket = np.zeros((3, 3))
+    for k in range(ng):
+        if not free_group[k]:
+            continue
+        m = act & (SimBox.ITYP == k + 1)
+        ket += cm[k] * (cxp1[m].T @ cxp1[m])
+    b = shape
+    vol = (b[0, 0] * (b[1, 1] * b[2, 2] - b[1, 2] * b[2, 1]) - b[1, 0] * (b[0, 1] * b[2, 2] - b[2, 1] * b[0, 2])
+           + b[2, 0] * (b[0, 1] * b[1, 2] - b[1, 1] * b[0, 2]))
+    volume = vol * SimBox.ZL[0] * SimBox.ZL[1] * SimBox.ZL[2]
+    vt = np.asarray(SimBox.VTENSOR, dtype=np.float64)
+    temp = (ket[0, 0] + ket[1, 1] + ket[2, 2]) / (3.0 * anprt * CP_KB)
+    spress0 = (n * CP_KB * temp / volume) * CP_CGS2KBAR
+    spress1 = ((vt[0, 0] + vt[1, 1] + vt[2, 2]) * (1.0 / 3.0) / volume) * CP_CGS2KBAR
+    avepot = CP_ERGEV * SimBox.EPOT[act].sum() / int(act.sum())
+    free = act & ((SimBox.STATU & CP_STATU_FIXPOS) == 0)
+    harmil = avepot * CP_EVERG + SimBox.EKIN[free].sum() / anprt
+    out = dict(TEMPERATURE=temp, TEMP=temp, KTENSOR=ket, VOLUME=volume, PTENSOR=(ket + vt) / volume, SPRESS0=spress0,
+               SPRESS1=spress1, SPRESS=spress0 + spress1, AVEPOT=avepot, HARMIL=harmil)
+    for key, val in out.items():
+        if key != "TEMP":
+            setattr(SimBox, key, val)
+    return out

@@ -139,3 +139,83 @@ def test_control_files_of_the_reference_examples_are_read():
     assert par.Quench_Steps == 1000 and par.Quench_Meth == "ST"
     assert par.STEEPEST_MiStep == 1.0e-5 and par.STEEPEST_MxStep == 0.1 and par.STEEPEST_MiDelE == 1.0e-5
     assert par.STRCUT_DRTol == 0.02 and par.LBFGS_MSave == 7
+
+
+def _thermal_loop_restatement(XP1, STATU, ITYP, CM, PROP, BOXSHAPE, ZL, VTENSOR, EPOT, EKIN):
+    """Cal_thermal_quantities_SimMDBox (Common/MD_TypeDef_SimBox.F90:5048-5170) as plain loops, statement by statement:
+    the checker of the vectorised host mirror in msmpscu_b200/mdlib.py."""
+    from msmpscu_b200.constants import CP_KB, CP_EVERG
+    n, ng = len(STATU), len(CM)
+    fixbits = (2, 4, 8)
+    vv0, tcm, anprt = [0.0, 0.0, 0.0], 0.0, 0
+    for k in range(ng):
+        if any((PROP[k] & b) == b for b in fixbits):
+            continue
+        vs = [0.0, 0.0, 0.0]
+        for j in range(n):
+            if ITYP[j] == k + 1 and (STATU[j] & 1) == 1:
+                for d in range(3):
+                    vs[d] += XP1[j, d]
+                tcm += CM[k]
+                anprt += 1
+        for d in range(3):
+            vv0[d] += vs[d] * CM[k]
+    vv0 = [v / tcm for v in vv0]
+    cxp1 = np.zeros((n, 3))
+    for i in range(n):
+        if (STATU[i] & 1) == 1:
+            for d in range(3):
+                if (STATU[i] & fixbits[d]) == 0:
+                    cxp1[i, d] = sum(BOXSHAPE[d, j] * (XP1[i, j] - vv0[d]) for j in range(3))
+    ket = np.zeros((3, 3))
+    for k in range(ng):
+        if any((PROP[k] & b) == b for b in fixbits):
+            continue
+        for j in range(n):
+            if ITYP[j] == k + 1 and (STATU[j] & 1) == 1:
+                for k1 in range(3):
+                    for k2 in range(3):
+                        ket[k1, k2] += cxp1[j, k1] * cxp1[j, k2] * CM[k]
+    volume = float(np.linalg.det(BOXSHAPE)) * ZL[0] * ZL[1] * ZL[2]
+    temp = (ket[0, 0] + ket[1, 1] + ket[2, 2]) / (3.0 * anprt * CP_KB)
+    sp0 = n * CP_KB * temp / volume * 1.0e-9
+    sp1 = (VTENSOR[0, 0] + VTENSOR[1, 1] + VTENSOR[2, 2]) / 3.0 / volume * 1.0e-9
+    act = [(STATU[i] & 1) == 1 for i in range(n)]
+    avepot = sum(EPOT[i] for i in range(n) if act[i]) / CP_EVERG / sum(act)
+    harmil = avepot * CP_EVERG + sum(EKIN[i] for i in range(n) if act[i] and (STATU[i] & 14) == 0) / anprt
+    return dict(KTENSOR=ket, VOLUME=volume, TEMPERATURE=temp, SPRESS0=sp0, SPRESS1=sp1, SPRESS=sp0 + sp1,
+                PTENSOR=(ket + VTENSOR) / volume, AVEPOT=avepot, HARMIL=harmil)
+
+
+@pytest.mark.parametrize("sheared", [False, True])
+def test_thermal_quantities_mirror(sheared):
+    """The output-step host routine behind the path (temperature from the drift-free kinetic tensor, pressure from
+    KTENSOR + VTENSOR, cohesive energy, Hamiltonian): three groups, one of them with a FIXPOS property (left out of the
+    drift and of the tensor), atoms with single fixed components, inactive atoms, and a non-identity BOXSHAPE."""
+    from msmpscu_b200 import mdlib
+    from msmpscu_b200.constants import CP_AU2G
+    rng = np.random.default_rng(11)
+    n = 600
+    ityp = np.repeat(np.array([1, 2, 3], dtype=np.int32), n // 3)
+    statu = np.full(n, 1, dtype=np.int32)
+    statu[rng.choice(n, 40, replace=False)] |= 2
+    statu[rng.choice(n, 30, replace=False)] |= 8
+    statu[rng.choice(n, 25, replace=False)] = 0            # inactive
+    cm = np.array([183.84, 1.008, 4.0026]) * CP_AU2G
+    prop = np.array([1, 1, 1 | 4], dtype=np.int32)          # the third group carries FIXPOSY
+    shape = np.eye(3)
+    if sheared:
+        shape = np.array([[1.0, 0.08, -0.03], [0.0, 0.97, 0.05], [0.02, 0.0, 1.04]])
+    box = mdlib.SimMDBox(NPRT=n, NGROUP=3, RR=3.1652e-8, ZL=np.array([6.0, 7.0, 8.0]) * 3.1652e-8, CM=cm, ITYP=ityp, STATU=statu,
+                         BOXSHAPE=shape, PROP=prop)
+    box.allocate()
+    box.XP1 = rng.normal(size=(n, 3)) * 3.0e4 + np.array([1.0e3, -2.0e3, 5.0e2])      # cm/s, with a drift
+    box.EPOT = -8.9 * 1.60219e-12 + rng.normal(size=n) * 1.0e-13
+    box.EKIN = 0.5 * cm[ityp - 1] * (box.XP1 ** 2).sum(axis=1)
+    box.VTENSOR = rng.normal(size=(3, 3)) * 1.0e-9
+    got = mdlib.Cal_thermal_quantities(box)
+    ref = _thermal_loop_restatement(box.XP1, statu, ityp, cm, prop, shape, box.ZL, box.VTENSOR, box.EPOT, box.EKIN)
+    for key, val in ref.items():
+        assert np.allclose(got[key], val, rtol=1e-12, atol=0.0), key
+        assert np.allclose(getattr(box, key), val, rtol=1e-12, atol=0.0), key
+    assert 200.0 < got["TEMPERATURE"] < 2.0e4 and got["SPRESS0"] > 0.0

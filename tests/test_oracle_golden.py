@@ -42,6 +42,32 @@ def test_known_answer_forces_and_energies(oracle, tag):
     assert np.max(np.abs(POT / c.gold_pot - 1.0)) < 1.5e-9
     # thermP0000_0001: C.E. = -8.89488 eV
     assert abs(-POT.mean() - (-8.89488)) < 5e-6
+    if tag == "react":
+        _thermal_line_of_the_reference(c, e)
+
+
+def _thermal_line_of_the_reference(c, epot):
+    """examples/NEB_Test/GMD/thermP0000_0001, the reference's own Putout_Instance_Thermal_Quantities lines: step 0 prints
+    C.E. -8.89488E+00 eV, HARMILT -1.42513E-11 erg, VOLUME 1.00000E+03 LU^3; step 1000 prints TEMP 9.50596E-06 K with
+    PRESS0 8.48210E-08 kbar.  The host mirror of Cal_thermal_quantities_SimMDBox (msmpscu_b200/mdlib.py) on the oracle's
+    energies reproduces the first line, and its PRESS0 at the printed temperature reproduces the second."""
+    from msmpscu_b200 import mdlib
+    n = c.xp.shape[0]
+    box = mdlib.SimMDBox(NPRT=n, NGROUP=2, RR=c.rr, ZL=c.zl, BOXLOW=c.boxlow, CM=c.mass, ITYP=c.ityp.copy(), EPOT=epot.copy(),
+                         STATU=c.statu.copy())
+    box.allocate()
+    th = mdlib.Cal_thermal_quantities(box)
+    assert abs(th["AVEPOT"] - (-8.89488)) < 5e-6
+    assert abs(th["HARMIL"] / (-1.42513e-11) - 1.0) < 5e-6
+    assert abs(th["VOLUME"] / c.rr ** 3 - 1.0e3) < 1e-9 * 1.0e3
+    assert th["TEMPERATURE"] == 0.0 and th["SPRESS"] == 0.0
+    rng = np.random.default_rng(5)
+    box.XP1 = rng.normal(size=(n, 3))
+    t0 = mdlib.Cal_thermal_quantities(box)["TEMPERATURE"]
+    box.XP1 *= np.sqrt(9.50596e-06 / t0)
+    th = mdlib.Cal_thermal_quantities(box)
+    assert abs(th["TEMPERATURE"] / 9.50596e-06 - 1.0) < 1e-12
+    assert abs(th["SPRESS0"] / 8.48210e-08 - 1.0) < 5e-6 and th["SPRESS1"] == 0.0
 
 
 def test_shipped_source_table_range_differs_measurably(oracle):
