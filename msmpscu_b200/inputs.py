@@ -6,10 +6,11 @@ Unit conversion follows Check_Globle_Variables, MDLIB/sor/Common/MD_Gvar.F90:918
   RR = a0[A]*1e-8, ZL = LATT*RR, BOXLOW = -ZL/2 unless &LOWB, CM = amu*1.66053e-24,
   H = fs*1e-15, RU = RU[LU]*RR, NB_RM = factor*RU."""
 import re
+from dataclasses import dataclass
 
 import numpy as np
 
-from .constants import CP_A2CM, CP_AU2G, CP_FS2S, CP_STATU_ACTIVE
+from .constants import CP_A2CM, CP_AU2G, CP_CM2A, CP_ERGEV, CP_EVERG, CP_FS2S, CP_S2PS, CP_STATU_ACTIVE
 from .mdlib import SimMDBox, SimMDCtrl, TiCtrlParam
 
 _NUM = re.compile(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eEdD][-+]?\d+)?")
@@ -177,10 +178,14 @@ def read_ctrl_file(path, box):
 
 
 def read_config(path, box):
-    """Rows 'type x y z [vx vy vz ...]' in lattice units (positions) -> fills box.ITYP / XP (/XP1 = 0)."""
+    """Rows 'type x y z [vx vy vz ...]' in lattice units (positions) -> fills box.ITYP / XP (/XP1 = 0).
+    A &BOXCFG18 file (the reference's own output, Putout_Instance_Config_SimMDBox) is read through its column directives:
+    velocities come back in cm/s (XP1*RR*CP_S2PS, Common/MD_SimBoxArray.F90:564-569), STATU, and -- for comparisons --
+    FP (dyn), EPOT / EKIN (erg) and DIS (cm) with the inverse of the writer's conversions."""
     rows = []
     started = False
     header = False
+    cols = {}
     with open(path) as f:
         for raw in f:
             s = raw.split("!")[0].strip()
@@ -188,14 +193,18 @@ def read_config(path, box):
                 continue
             if s.startswith("&"):
                 header = True
-                if s.upper().startswith("&TYPE"):
+                key = s.split()[0].upper()
+                if key == "&TYPE":
                     started = True
+                elif key.endswith("COL") and not started:
+                    p = s.split()
+                    cols[key[1:-3]] = (int(p[1]) - 1, int(p[2]))
                 continue
             if header and not started:
                 continue
             p = s.split()
             try:
-                rows.append([float(x.replace("D", "e").replace("d", "e")) for x in p[:4]])
+                rows.append([float(x.replace("D", "e").replace("d", "e")) for x in (p if cols else p[:4])])
             except ValueError:
                 continue
     a = np.array(rows)
@@ -204,4 +213,94 @@ def read_config(path, box):
     box.ITYP = a[:, 0].astype(np.int32)
     box.XP = a[:, 1:4] * box.RR
     box.allocate()
+    get = lambda k: a[:, cols[k][0]:cols[k][0] + cols[k][1]] if k in cols and a.shape[1] >= cols[k][0] + cols[k][1] else None
+    if get("VEL") is not None:
+        box.XP1 = get("VEL") * box.RR * CP_S2PS
+    if get("STAT") is not None:
+        box.STATU = get("STAT")[:, 0].astype(np.int32)
+    if get("FP") is not None:
+        box.FP = get("FP") * CP_EVERG / box.RR
+    if get("EPOT") is not None:
+        box.EPOT = -get("EPOT")[:, 0] * CP_EVERG
+    if get("EKIN") is not None:
+        box.EKIN = get("EKIN")[:, 0] * CP_EVERG
+    if get("DIS") is not None:
+        box.DIS = get("DIS") * box.RR
     return box
+
+
+@dataclass
+class MDRecordStamp:
+    """type(MDRecordStamp), Common/MD_TypeDef_RecordStamp.F90:12-31, with its defaults."""
+    AppType: str = ""
+    ITest: int = -1
+    IBox: tuple = (-1, -1)
+    ITime: int = -1
+    ISect: int = -1
+    Time: float = -1.0
+    ScalTime: float = -1.0
+    InstantTemp: float = -1.0
+    ICfg: tuple = (-1, -1)
+    IRec: tuple = (-1, -1)
+
+
+def _e(x, w, d):
+    """Fortran 1PEw.d"""
+    return "%*.*E" % (w, d, x)
+
+
+def write_config(fhead, box, stamp=None, date=None):
+    """Putout_Instance_Config_SimMDBox (Common/MD_TypeDef_SimBox.F90:2388-2630) without extra data pads: the &BOXCFG18 file
+    of one box -- record stamp (Putout_RecordStamp, MD_TypeDef_RecordStamp.F90:89-115), column directives, box lines and one
+    row per atom `(I8,3X,3(1PE17.8,1X),3(1PE17.8,1X),I6,2X,3(1PE17.8,1X),1PE17.8,1X,1PE17.8,1X,3(1PE17.8,1X))` holding
+    XP/RR, XP1/RR/CP_S2PS, STATU, FP*CP_ERGEV*RR, -EPOT*CP_ERGEV, EKIN*CP_ERGEV, DIS/RR (:2594-2600).  The file name is
+    Fhead.NNNN when Stamp%ICfg(1) >= 0 (:2424-2428).  Returns the name."""
+    import time as _time
+    st = stamp if stamp is not None else MDRecordStamp()
+    fname = "%s.%04d" % (fhead, st.ICfg[0]) if st.ICfg[0] >= 0 else fhead
+    date = date if date is not None else _time.strftime("%Y-%m-%d,%Hh%Mm%Ss")
+    rr = box.RR
+    out = ["&BOXCFG18",
+           '&APPTYPE        "%s" ' % st.AppType,
+           "&DATE            " + date,
+           "&TESTID          %12d" % st.ITest,
+           "&BOXID           %12d, %6d" % tuple(st.IBox),
+           "&CFGID           %12d, %6d" % tuple(st.ICfg),
+           "&RECID           %12d, %6d" % tuple(st.IRec),
+           "&TIMESTEPS       %12d" % st.ITime,
+           "&TIMESECT #      %12d" % st.ISect,
+           "&TIME (ps)       " + _e(st.Time, 12, 5),
+           "&SCALTIME (ps)   " + _e(st.ScalTime, 12, 5),
+           "&TEMPSET (K)     " + _e(st.InstantTemp, 12, 5),
+           " ",
+           "!--- Table colume information:"]
+    ncol = 1
+    for tag, width, kind in (("&TYPECOL", 1, "I"), ("&XYZCOL", 3, "D"), ("&VELCOL", 3, "D"), ("&STATCOL", 1, "I"),
+                             ("&FPCOL", 3, "D"), ("&EPOTCOL", 1, "D"), ("&EKINCOL", 1, "D"), ("&DISCOL", 3, "D")):
+        out.append("%-12s %4d %3d \"%s\"" % (tag, ncol, width, kind))
+        ncol += width
+    na = [int((box.ITYP == k + 1).sum()) for k in range(box.NGROUP)]
+    e3 = lambda v: " ".join(_e(x, 12, 5) for x in v)      # a trailing 1X writes nothing at the end of a Fortran record
+    out += ["",
+            "&LATT     lattice length (in A):       " + e3([rr * CP_CM2A]),
+            "&BOXLOW   low boundary of box (in LU): " + e3(np.asarray(box.BOXLOW) / rr),
+            "&BOXSIZE  boxsize (in LU):             " + e3(np.asarray(box.ZL) / rr),
+            "&NATOM    total number of atoms:       %8d" % box.NPRT,
+            "&NGROUP   number of group of atoms:    %8d" % box.NGROUP,
+            "    &NA   number of atoms in groups:   " + " ".join("%8d" % v for v in na),
+            "&TEMPCAL instant temperature(K):      " + e3([float(getattr(box, "TEMPERATURE", 0.0))]),
+            "!--- Configure:",
+            ("&TYPE         " "POS(LU)  (x)             (y)              (z)         "
+             "VEL(LU/ps)(vx)           (vy)             (vz)        " "STATU   "
+             "FOR(ev/LU)(fx)           (fy)             (fz)        " "POT(ev).          " "K.E.(ev)          "
+             "DISPLACE(dx )            (dy)               (dz)       ").rstrip()]
+    e17 = lambda v: "".join(_e(x, 17, 8) + " " for x in v)
+    xp, v = box.XP / rr, box.XP1 / rr / CP_S2PS
+    f, dis = box.FP * CP_ERGEV * rr, box.DIS / rr
+    pot, ke = -box.EPOT * CP_ERGEV, box.EKIN * CP_ERGEV
+    for k in range(box.NPRT):
+        out.append("%8d   " % box.ITYP[k] + e17(xp[k]) + e17(v[k]) + "%6d  " % box.STATU[k] + e17(f[k]) + e17([pot[k]])
+                   + e17([ke[k]]) + e17(dis[k]))
+    with open(fname, "w") as fh:
+        fh.write("\n".join(out) + "\n")
+    return fname

@@ -70,6 +70,9 @@ def main():
         shutil.copyfile(os.path.join(neb, fn), os.path.join(HERE, fn))
     with open(os.path.join(neb, "GMD", "thermP0000_0001")) as f:
         open(os.path.join(HERE, "neb_gmd_therm.txt"), "w").write(f.read())
+    # header + first 10 rows of the reference-written &BOXCFG18 file, as text: pins the layout of inputs.write_config
+    with open(os.path.join(neb, "GMD", "ReactP0000_0001.0000")) as f:
+        open(os.path.join(HERE, "neb_ReactP0000_0001_head.txt"), "w").write("".join(f.readlines()[:42]))
 
     # the reference's own CPU-runnable example (BASELINE.json configs[0]): inputs only
     gmd = os.path.join(REF, "examples", "GMD_Test")

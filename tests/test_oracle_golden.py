@@ -186,3 +186,50 @@ def test_oracle_steepest_quench_relaxes_and_stops_on_the_reference_criteria():
     md2 = util.oracle_md(O, c)
     md2.rebuild()
     assert md2.steepest0(5, 0.1, 0.1 * c.rr, 1.0e-12 * c.rr, 1.0e-16 * util.CP_EVERG)[0] == 0
+
+
+def test_config_file_written_like_the_reference(oracle, tmp_path):
+    """inputs.write_config (Putout_Instance_Config_SimMDBox, Common/MD_TypeDef_SimBox.F90:2388-2630) against the file the
+    reference GPU build wrote for the same state (examples/NEB_Test/GMD/ReactP0000_0001.0000; header and first ten rows kept
+    in tests/golden): record stamp, column directives, box lines and row layout are the reference's character for character
+    where the 2019 build and the shipped source agree; forces and POT columns agree to the printed 9 digits.  Read back,
+    the file restores the state (velocity / force / energy unit conversions of MD_SimBoxArray.F90:564-569 inverted)."""
+    from msmpscu_b200 import inputs, mdlib
+    c = util.neb_case("react", rmax_mode="NB_RM")
+    f, e, _ = _forces_from_oracle(oracle, c)
+    n = c.xp.shape[0]
+    box = mdlib.SimMDBox(NPRT=n, NGROUP=2, RR=c.rr, ZL=c.zl, BOXLOW=c.boxlow, CM=c.mass, ITYP=c.ityp.copy(), XP=c.xp.copy(),
+                         FP=f, EPOT=e, STATU=c.statu.copy())
+    box.allocate()
+    stamp = inputs.MDRecordStamp(AppType="GMD", ITest=1, IBox=(1, 1), ICfg=(0, 0), IRec=(0, 0), ITime=0, ISect=0, Time=0.0,
+                                 ScalTime=0.0, InstantTemp=-1.0)
+    name = inputs.write_config(str(tmp_path / "ReactP0000_0001"), box, stamp, date="2019-01-03,09h55m05s")
+    assert name.endswith("ReactP0000_0001.0000")
+    ours = open(name).read().split("\n")
+    gold = open(os.path.join(GOLD, "neb_ReactP0000_0001_head.txt")).read().split("\n")
+    # header: every '&' line of the golden file appears verbatim, in order (the 2019 build printed two comment lines and a
+    # shorter title that the shipped source words differently)
+    ours_kw = [l for l in ours if l.startswith("&") or l.startswith("    &NA")]
+    gold_kw = [l for l in gold if l.startswith("&") or l.startswith("    &NA")]
+    assert len(gold_kw) == 28 and len(ours_kw) == len(gold_kw)
+    for a, b in zip(ours_kw, gold_kw):
+        if b.startswith("&TYPE  "):
+            assert a.startswith(b.rstrip())                 # same title up to the K.E. column; the source adds DISPLACE
+        elif b.startswith("&TEMPCAL"):
+            assert a.split()[-1] == b.split()[-1]           # "&TEMPCAL  instant" (2019) vs "&TEMPCAL instant" (shipped source)
+        else:
+            assert a == b
+    rows_o = [l for l in ours if l[:8].strip().isdigit()]
+    rows_g = [l for l in gold if l[:8].strip().isdigit()]
+    assert len(rows_o) == n and len(rows_g) == 10
+    for a, b in zip(rows_o, rows_g):
+        assert a[:119] == b[:119]                           # type, position, velocity, STATU: identical text
+        assert len(a.rstrip()) >= len(b.rstrip())
+        va, vb = np.array(a.split(), dtype=float), np.array(b.split(), dtype=float)
+        assert np.max(np.abs(va[8:11] - vb[8:11])) < 1e-9 and abs(va[11] / vb[11] - 1.0) < 1.5e-9 and va[12] == vb[12]
+    back = mdlib.SimMDBox(NPRT=n, NGROUP=2, RR=c.rr, ZL=c.zl, BOXLOW=c.boxlow, CM=c.mass)
+    inputs.read_config(name, back)
+    assert np.array_equal(back.ITYP, box.ITYP) and np.array_equal(back.STATU, box.STATU)
+    assert np.allclose(back.XP, box.XP, rtol=0, atol=1e-8 * c.rr) and np.all(back.XP1 == 0.0)
+    assert np.allclose(back.FP, box.FP, rtol=0, atol=1e-8 * np.abs(box.FP).max())
+    assert np.allclose(back.EPOT, box.EPOT, rtol=1e-8, atol=0)
