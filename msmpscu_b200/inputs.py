@@ -304,3 +304,20 @@ def write_config(fhead, box, stamp=None, date=None):
     with open(fname, "w") as fh:
         fh.write("\n".join(out) + "\n")
     return fname
+
+
+_THERMAL_TITLES = ("  TIMESECTION   ", "    TIME(PS)    ", "    TEMP.(K)    ", "  VOULUME(LU)   ", "   PRESS0(kb)   ", "   PRESS1(kb)   ",
+                   "   PRESST(kb)   ", "    C.E.(ev)    ", "  HARMILT.(cgs) ")
+
+
+def write_thermal_quantities(fname, itime, time_ps, isect, box):
+    """Putout_Instance_Thermal_Quantities_SimMDBox (Common/MD_TypeDef_SimBox.F90:5172-5260): ITIME = 0 starts the file with
+    the title line `(20x,10(A16))`, later calls append; one line `(1x,I8,4x,I4,8x,11(1pE14.5,2x))` per call with TIME,
+    TEMPERATURE, VOLUME/RR**3, SPRESS0, SPRESS1, SPRESS, AVEPOT, HARMIL as Cal_thermal_quantities left them on the box."""
+    vals = (time_ps, box.TEMPERATURE, box.VOLUME / box.RR ** 3, box.SPRESS0, box.SPRESS1, box.SPRESS, box.AVEPOT, box.HARMIL)
+    line = " %8d    %4d        " % (itime, isect) + "  ".join(_e(float(v), 14, 5) for v in vals)
+    with open(fname, "w" if itime == 0 else "a") as fh:
+        if itime == 0:
+            fh.write((" " * 20 + "".join(_THERMAL_TITLES)).rstrip() + "\n")
+        fh.write(line + "\n")
+    return line

@@ -451,3 +451,15 @@ def Cal_thermal_quantities(SimBox):
         if key != "TEMP":
             setattr(SimBox, key, val)
     return out
+
+
+def Putout_Instance_Config_SimMDBox(Fhead, SimBox, Stamp=None):
+    """Common/MD_TypeDef_SimBox.F90:2388-2630 -> inputs.write_config (the &BOXCFG18 file of one box)."""
+    from . import inputs
+    return inputs.write_config(Fhead, SimBox, Stamp)
+
+
+def Putout_Instance_Thermal_Quantities_SimMDBox(ITIME, TIME, ISECT, FNAME, SimBox):
+    """Common/MD_TypeDef_SimBox.F90:5172-5260 -> inputs.write_thermal_quantities (one line per call; ITIME = 0 starts the file)."""
+    from . import inputs
+    return inputs.write_thermal_quantities(FNAME, ITIME, TIME, ISECT, SimBox)

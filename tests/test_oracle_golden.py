@@ -68,6 +68,26 @@ def _thermal_line_of_the_reference(c, epot):
     th = mdlib.Cal_thermal_quantities(box)
     assert abs(th["TEMPERATURE"] / 9.50596e-06 - 1.0) < 1e-12
     assert abs(th["SPRESS0"] / 8.48210e-08 - 1.0) < 5e-6 and th["SPRESS1"] == 0.0
+    # the lines themselves (Putout_Instance_Thermal_Quantities_SimMDBox): step 0 from the oracle's energies is the reference's
+    # line character for character; step 1000 with the printed temperature reproduces its TEMP / VOLUME / PRESS columns
+    import tempfile
+    from msmpscu_b200 import inputs
+    gold = open(os.path.join(GOLD, "neb_gmd_therm.txt")).read().split("\n")
+    box.XP1[:] = 0.0
+    mdlib.Cal_thermal_quantities(box)
+    with tempfile.TemporaryDirectory() as d:
+        name = os.path.join(d, "thermP0000_0001")
+        l0 = inputs.write_thermal_quantities(name, 0, 0.0, 0, box)
+        box.XP1 = rng.normal(size=(n, 3))
+        box.XP1 *= np.sqrt(9.50596e-06 / mdlib.Cal_thermal_quantities(box)["TEMPERATURE"])
+        mdlib.Cal_thermal_quantities(box)
+        l1 = inputs.write_thermal_quantities(name, 1000, 1.0e-3, 1, box)
+        written = open(name).read().split("\n")
+    assert l0 == gold[1].rstrip()
+    upto_volume = "     1000       1           1.00000E-03     9.50596E-06     1.00000E+03"
+    assert l1.startswith(upto_volume) and gold[2].startswith(upto_volume)     # PRESS0 itself: 5e-6 above (T is printed rounded)
+    assert len(l1) == len(gold[2].rstrip())
+    assert written[0].split() == gold[0].split() and written[1] == l0 and written[2] == l1
 
 
 def test_shipped_source_table_range_differs_measurably(oracle):
