@@ -463,3 +463,32 @@ def Putout_Instance_Thermal_Quantities_SimMDBox(ITIME, TIME, ISECT, FNAME, SimBo
     """Common/MD_TypeDef_SimBox.F90:5172-5260 -> inputs.write_thermal_quantities (one line per call; ITIME = 0 starts the file)."""
     from . import inputs
     return inputs.write_thermal_quantities(FNAME, ITIME, TIME, ISECT, SimBox)
+
+
+def Do_Compare(SimBoxIni, SimBox, CtrlParam, MASK=None):
+    """Do_Compare (Appshell/MD_Method_ParRep_GPU.F90:1241-1297), the default structure comparison of the event detection
+    (Do_ChangeDetect :1094-1167 calls it on the quenched replicas): Flag(IP) = 1 where atom I of replica IB sits further than
+    &DRTOL from its place in SimBoxIni -- minimum image along the periodic axes, strict `>` on the squared distance, atoms
+    with MASK <= 0 skipped.  STRCUT_DRTol is kept in LU on this side (inputs.read_ctrl_file), hence the RR.
+    Returns Flag (NB*NPRT), replica-major; a replica with any flag set is a transition (NCB / IBT of Do_ChangeDetect)."""
+    boxes = SimBox if isinstance(SimBox, (list, tuple)) else [SimBox]
+    nprt = SimBoxIni.NPRT
+    rc2 = (CtrlParam.STRCUT_DRTol * SimBoxIni.RR) ** 2
+    box, hbox = np.asarray(SimBoxIni.ZL, dtype=np.float64), 0.5 * np.asarray(SimBoxIni.ZL, dtype=np.float64)
+    per = np.asarray(CtrlParam.IFPD) > 0
+    mask = np.ones(nprt, dtype=bool) if MASK is None else np.asarray(MASK) > 0
+    flag = np.zeros(len(boxes) * nprt, dtype=np.int32)
+    for ib, b in enumerate(boxes):
+        sep = SimBoxIni.XP - b.XP
+        wrap = per[None, :] & (np.abs(sep) > hbox[None, :])
+        sep = np.where(wrap, sep - np.copysign(box[None, :], sep), sep)
+        flag[ib * nprt:(ib + 1) * nprt] = ((sep * sep).sum(axis=1) > rc2) & mask
+    return flag
+
+
+def Transition_Replicas(Flag, NPRT):
+    """The tail of Do_ChangeDetect (:1146-1156): NCB = number of replicas with any flagged atom, IBT = the last of them
+    (1-based, 0 when none)."""
+    nb = len(Flag) // NPRT
+    hit = [ib + 1 for ib in range(nb) if np.any(Flag[ib * NPRT:(ib + 1) * NPRT] > 0)]
+    return (hit[-1] if hit else 0), len(hit)

@@ -219,3 +219,44 @@ def test_thermal_quantities_mirror(sheared):
         assert np.allclose(got[key], val, rtol=1e-12, atol=0.0), key
         assert np.allclose(getattr(box, key), val, rtol=1e-12, atol=0.0), key
     assert 200.0 < got["TEMPERATURE"] < 2.0e4 and got["SPRESS0"] > 0.0
+
+
+def test_event_detection_compare():
+    """Do_Compare / the replica bookkeeping of Do_ChangeDetect (Appshell/MD_Method_ParRep_GPU.F90:1241-1297, 1146-1156) against
+    a per-atom loop: an atom that hopped by less than DRTOL is not an event, one that crossed a periodic face by a small step
+    is not an event either (minimum image), a 0.5 LU hop is, a masked atom never is, and along a non-periodic axis the raw
+    separation counts."""
+    from msmpscu_b200 import mdlib
+    rng = np.random.default_rng(3)
+    n, rr = 200, 3.14e-8
+    zl = np.array([10.0, 10.0, 10.0]) * rr
+    ini = mdlib.SimMDBox(NPRT=n, NGROUP=1, RR=rr, ZL=zl, BOXLOW=-0.5 * zl)
+    ini.XP = (rng.random((n, 3)) - 0.5) * zl
+    ini.XP[0] = [4.995 * rr, 0.0, 0.0]
+    ini.XP[4] = [0.0, 0.0, 4.995 * rr]
+    ctl = mdlib.SimMDCtrl(IFPD=np.array([1, 1, 0], dtype=np.int32), STRCUT_DRTol=0.02)
+    reps = []
+    for r in range(3):
+        b = mdlib.SimMDBox(NPRT=n, NGROUP=1, RR=rr, ZL=zl, BOXLOW=-0.5 * zl)
+        b.XP = ini.XP + rng.normal(size=(n, 3)) * 0.004 * rr
+        reps.append(b)
+    reps[0].XP[0] = [-4.998 * rr, 0.0, 0.0]          # wrapped through the periodic x face: 0.007 LU away
+    reps[1].XP[7] += [0.5 * rr, 0.0, 0.0]            # a hop
+    reps[1].XP[9] += [0.0, 0.5 * rr, 0.0]            # a hop of a masked atom
+    reps[2].XP[4] = [0.0, 0.0, -4.998 * rr]          # z is not periodic: 9.993 LU away
+    mask = np.ones(n, dtype=np.int32); mask[9] = 0
+    flag = mdlib.Do_Compare(ini, reps, ctl, mask)
+    ref = np.zeros(3 * n, dtype=np.int32)
+    for ib, b in enumerate(reps):
+        for i in range(n):
+            if mask[i] <= 0:
+                continue
+            sep = ini.XP[i] - b.XP[i]
+            for d in range(3):
+                if ctl.IFPD[d] > 0 and abs(sep[d]) > 0.5 * zl[d]:
+                    sep[d] -= np.copysign(zl[d], sep[d])
+            ref[ib * n + i] = 1 if (sep * sep).sum() > (0.02 * rr) ** 2 else 0
+    assert np.array_equal(flag, ref)
+    assert flag[0] == 0 and flag[n + 7] == 1 and flag[n + 9] == 0 and flag[2 * n + 4] == 1 and flag.sum() == 2
+    assert mdlib.Transition_Replicas(flag, n) == (3, 2)
+    assert mdlib.Transition_Replicas(mdlib.Do_Compare(ini, reps[:1], ctl), n) == (0, 0)
