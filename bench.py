@@ -1,20 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the MDPSCU tabulated EAM hot path on B200.
 
-Metric (BASELINE.json): atom-steps/s, bcc W, Marinica EAM2 table force, 1 024 000 atoms (80^3 bcc
-cells), NVT via the electron-phonon thermostat (MDLocalTempCtrl/EPC, T_e = 300 K), h = 0.5 fs,
-neighbour list (1.2 x 1.9 a0, MAXNB 256) rebuilt every 10 MD steps.
+Metric (BASELINE.json): atom-steps/s, bcc W, Marinica EAM2 table force, 1 024 000 atoms (80^3 bcc cells), NVT via the
+electron-phonon thermostat (MDLocalTempCtrl/EPC, T_e = 300 K), h = 0.5 fs, neighbour list (1.2 x 1.9 a0, MAXNB 256)
+rebuilt every 10 MD steps.
 
-One bench "step" = one neighbour-list period of the GMD loop = 10 MD steps (For_One_Step x 10:
-predictor -> [rebuild on the first] -> density pass -> force pass -> EPC -> corrector), i.e. one
-mdb_run(ctx, itime0, 10, ...) call; value counts MD steps: atoms x 10 x K / time.
+One bench "step" = one OUTPUT INTERVAL of the GMD loop = 100 MD steps = 10 neighbour-list periods (For_One_Step x 100:
+predictor -> [rebuild on the first step of a period] -> density pass -> force pass -> EPC -> corrector), i.e. one
+mdb_run(ctx, itime0, 100, ...) call.  value counts MD steps: atoms x 100 x K / time.  (Round 1 used one list period per
+step; 20 of those are a 0.13 s timed region, too short to be trusted, so the step now is the reference's output interval.)
+
+  value      the box stays resident in HBM; CUDA events on the launching stream around the K steps
+  e2e        the same K steps through the C ABI with HOST buffers: every step uploads XP, XP1 from page-locked memory
+             (CopyIn_SimBox_DEV), runs its 100 MD steps and downloads XP, XP1, FP (CopyOut_SimBox_DEV).  Consecutive
+             steps are independent jobs (the multi-box statistics pattern: box after box through one GPU) and alternate
+             between two device contexts on two streams, so the copies of one job overlap the steps of the other; one
+             host synchronisation per job.  "e2e_diagnostics" adds the same pipeline with a transfer every 10 MD steps
+             (round 1's e2e unit) and the serial single-context form.
+  roofline   dominant kernel: canonical algorithmic bytes per launch / its mean launch time (CUDA events, this run)
+  parity_check  after the timed region, on the state just timed: tiled forces vs the generic path (all atoms) and vs
+             the CPU oracle (10 000-atom range), per-atom relative error
+  cpu_baseline  the reference's CPU routines (C restatement, oracle/) on all host cores, full 1 024 000-atom box
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells 80]
 
-N > 1 (torchrun, one rank per GPU): every rank runs its own independent box (MDPSCU's natural
-multi-GPU grain: independent boxes, no data-path collective) -> weak scaling; time = max over ranks.
---impl reference times the reference's CPU implementation of the same path (the C restatement in
-oracle/, since the PGI CUDA-Fortran reference cannot be built here) on the host cores, rank 0 only.
+N > 1 (torchrun, one rank per GPU): every rank runs its own independent box (MDPSCU's natural multi-GPU grain: independent
+boxes, no data-path collective) -> weak scaling; time = max over ranks.  --impl reference times the reference's CPU path
+(Cal_NeighboreList2C + two-pass table force + Swope steps; the C restatement in oracle/, built -O3 -march=native, since
+the PGI CUDA-Fortran reference cannot be built here) with all host threads, rank 0 only.
 """
 import argparse
 import json
@@ -27,11 +40,14 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 # stdout carries ONE JSON line: NCCL_DEBUG=VERSION makes NCCL itself print "NCCL version ..." there (INFO / WARN are left alone)
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
 
-MD_PER_STEP = 10      # NB_UPTAB: MD steps per neighbour-list period
+MD_PER_PERIOD = 10    # NB_UPTAB: MD steps per neighbour-list period
+PERIODS_PER_STEP = 10
+MD_PER_STEP = MD_PER_PERIOD * PERIODS_PER_STEP   # one output interval
 H = 0.5e-15           # s
 A0 = 3.1652           # Angstrom
 RU_LU, NB_FAC, MXKVOIS, NTAB = 1.9, 1.2, 256, 10000
@@ -39,7 +55,8 @@ K_LIST = 112          # stored neighbours per atom for this lattice / cutoff (SU
 # canonical algorithmic bytes per atom (SURVEY.md 8d / BASELINE.md 4): int32 full list, fp64 SoA
 BYTES_PASS1 = 4 * K_LIST + 44
 BYTES_PASS2 = 4 * K_LIST + 68
-BYTES_STEP = 8 * K_LIST + 356 + (36 + 4 * K_LIST) / MD_PER_STEP  # = 1300.4
+BYTES_STEP = 8 * K_LIST + 356 + (36 + 4 * K_LIST) / MD_PER_PERIOD  # = 1300.4
+PARITY_TOL = 1e-10    # BASELINE.json north_star: forces, energies, virial within 1e-10 relative in fp64
 
 
 def parse():
@@ -56,22 +73,24 @@ def parse():
                     help="cu_setfl: fcc Cu with the NIST setfl potential Cu1 imported through mdb_host_setfl_ftable (configs[2] family "
                          "with a real external EAM table; --cells = fcc cells per edge)")
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "tiled"])
-    ap.add_argument("--cpu-cells", type=int, default=32, help="edge of the CPU sample box (32 -> 65 536 atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity_check after the timed region")
+    ap.add_argument("--no-c1", action="store_true", help="skip the configs[0] (8192 atoms, NVE, 1000 steps) sub-record")
     ap.add_argument("--lanes", type=int, default=0, help="tiled path: lanes per atom (2/4/8), 0 = default")
     ap.add_argument("--classes", type=int, default=1, help="tiled path: distance-classified lists on/off")
     ap.add_argument("--threads", type=int, default=0, help="tiled path: threads of the pass CTA (512/768), 0 = default")
+    ap.add_argument("--bankorder", type=int, default=-1, help="tiled path: bank-aware order of the scanned list classes (0/1), -1 = default")
     ap.add_argument("--stages", type=int, default=0, help="tiled path: pipeline stages of the pass kernel (2/3), 0 = default")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the timed CPU loop")
     return ap.parse_args()
 
 
-def make_case(cells, seed, nbox=1, potential="w_marinica"):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def make_case(cells, seed, nbox=1, potential="w_marinica", temp=600.0):
     import util
     if potential == "cu_setfl":
         return util.fcc_cu_case((cells, cells, cells), seed=seed, nbox=nbox)
     return util.bcc_case((cells, cells, cells), a0=A0, seed=seed, ru_lu=RU_LU, nb_fac=NB_FAC, mxkvois=MXKVOIS,
-                         ntab=NTAB, temp=600.0, disp=0.02, nbox=nbox)
+                         ntab=NTAB, temp=temp, disp=0.02, nbox=nbox)
 
 
 EPC = dict(enable=[1], te=[300.0], alpha=[1.0e-12], cut=[0.1], he=[100.0 * 1.60219e-12])
@@ -112,31 +131,78 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_arm(cells, steps, warmup, threads=None):
-    """The reference's CPU implementation of the path (C restatement, oracle/) on the host cores."""
-    from oracle import pyorc as O
-    nthr = threads or os.cpu_count() or 1
-    O.lib().orc_set_threads(nthr)
-    c = make_case(cells, 4242)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def bind_to_gpu_numa(index):
+    """Run this rank (and first-touch its page-locked buffers) on the CPUs of the GPU's NUMA node: with 8 ranks copying
+    ~120 MB per job each, buffers on the wrong socket were the e2e limiter at N = 8.  Best effort."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bus).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path (oracle/, fast build), loop in C
+# ------------------------------------------------------------------------------------------------
+def cpu_md(c, half=False, threads=None, epc=True):
     import util
-    md = util.oracle_md(O, c)
-    md.set_epc(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
+    from oracle import pyorc as O
+    md = util.oracle_cpu_md(O, c, half=half, fast=True)
+    md.set_threads(threads or os.cpu_count() or 1)
+    if epc:
+        md.set_epc(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
     md.rebuild()
     md.force()
-    n = c.xp.shape[0]
-    it = 0
-    for _ in range(warmup):
-        for _ in range(MD_PER_STEP):
-            md.step(it, 1, MD_PER_STEP, H)
-            it += 1
+    return md
+
+
+def cpu_time_periods(md, periods, it0=0):
+    """periods x (10 MD steps incl. one rebuild); returns (seconds, next itime)"""
     t0 = time.perf_counter()
-    for _ in range(steps):
-        for _ in range(MD_PER_STEP):
-            md.step(it, 1, MD_PER_STEP, H)
-            it += 1
-    dt = time.perf_counter() - t0
-    return n * MD_PER_STEP * steps / dt, dt, n, nthr
+    md.run(it0, periods * MD_PER_PERIOD, 1, MD_PER_PERIOD, H)
+    return time.perf_counter() - t0, it0 + periods * MD_PER_PERIOD
+
+
+def cpu_variants(cells=32):
+    """serial 1-core runs of the two CPU formulations on a bounded sample: the full list with every
+    directed pair (CALFORCE_FS_Force_Table2) and the half list with Newton's third law (CALFORCE_FS_Force_Table)"""
+    c = make_case(cells, 4242)
+    n = c.xp.shape[0]
+    out = {"sample": "bcc W %d atoms (%d^3 cells), 10 MD steps incl. one rebuild, 1 thread" % (n, cells)}
+    for name, half in (("serial_full_list", False), ("serial_newton3_half_list", True)):
+        md = cpu_md(c, half=half, threads=1)
+        dt, _ = cpu_time_periods(md, 1)
+        out[name] = n * MD_PER_PERIOD / dt
+    return out
+
+
+def c1_case():
+    return make_case(16, 12345)
+
+
+def cpu_c1(threads):
+    """configs[0]: 8192 W atoms, NVE, 1000 steps on the CPU path; HARMIL drift"""
+    c = c1_case()
+    md = cpu_md(c, threads=threads, epc=False)
+    h0 = md.harmil()
+    dt, _ = cpu_time_periods(md, 100)
+    h1 = md.harmil()
+    return {"atoms": int(c.xp.shape[0]), "md_steps": 1000, "value": c.xp.shape[0] * 1000 / dt, "unit": "atom-steps/s",
+            "harmil_erg": [h0, h1], "harmil_drift_rel": (h1 - h0) / abs(h0), "threads": threads}
 
 
 def base_line(args, n_atoms):
@@ -149,25 +215,162 @@ def base_line(args, n_atoms):
                                ("configs[2] family: %d independent boxes x %d atoms (%d^3 bcc cells, W Marinica EAM2 tables), "
                                 "NVT via EPC, per GPU" % (args.nbox, n_atoms // args.nbox, args.cells)),
                    "atoms_per_gpu": n_atoms, "md_steps_per_step": MD_PER_STEP, "h_fs": 0.5, "cutoff_a0": RU_LU,
-                   "list_cutoff_a0": RU_LU * NB_FAC, "rebuild_every": MD_PER_STEP, "ntab": NTAB,
-                   "l2_policy": "inputs larger than L2 (neighbour list + state ~0.6 GB per step, L2 126 MB)",
+                   "list_cutoff_a0": RU_LU * NB_FAC, "rebuild_every": MD_PER_PERIOD, "ntab": NTAB,
+                   "l2_policy": "inputs larger than L2 (neighbour list + state ~0.6 GB per MD step, L2 126 MB)",
                    "parallelism": "independent box per GPU, no data-path collective"},
     }
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores: FULL box of the benchmark, all threads.
+    One reference step = ONE list period (10 MD steps incl. its rebuild) of the 10 in a bench step -- a bounded sample in
+    time, not in size -- so that K + W steps end within minutes; the metric is a rate, so the unit is the same."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, dt, n, nthr = cpu_arm(args.cpu_cells, args.steps, args.warmup)
-    line = base_line(args, args.cells ** 3 * 2)
-    sample = "bcc W %d atoms (%d^3 cells), same potential/cutoffs/EPC, %d MD steps per step incl. 1 rebuild" % (
-        n, args.cpu_cells, MD_PER_STEP)
-    line.update({"impl": "reference", "value": val, "ms_per_step": dt / args.steps * 1e3,
-                 "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": nthr, "kind": "port", "sample": sample},
+    nthr = os.cpu_count() or 1
+    c = make_case(args.cells, 12346, args.nbox, args.potential)
+    n = c.xp.shape[0]
+    t_setup = time.perf_counter()
+    md = cpu_md(c, threads=nthr)
+    t_setup = time.perf_counter() - t_setup
+    it = 0
+    wdt = 0.0
+    for _ in range(max(args.warmup, 1)):
+        d, it = cpu_time_periods(md, 1, it)
+        wdt += d
+    per = wdt / max(args.warmup, 1)
+    steps = args.steps
+    if per * steps > args.cpu_budget_s:          # never silently: the line says how many steps were really timed
+        steps = max(2, int(args.cpu_budget_s / per))
+    dt, it = cpu_time_periods(md, steps, it)
+    val = n * MD_PER_PERIOD * steps / dt
+    line = base_line(args, n)
+    line["config"]["atoms_total"] = n
+    line["config"]["md_steps_per_step"] = MD_PER_PERIOD
+    line["config"]["parallelism"] = "host CPU, OpenMP over atoms, %d threads" % nthr
+    sample = ("full box of %d atoms; one reference step = 1 list period = %d MD steps incl. one Cal_NeighboreList2C rebuild "
+              "(a bench step of the GPU arm is %d such periods); %d steps timed after %d warm-up, loop inside C (orc_cpu_run), "
+              "gcc -O3 -march=native" % (n, MD_PER_PERIOD, PERIODS_PER_STEP, steps, max(args.warmup, 1)))
+    line.update({"impl": "reference", "value": val, "steps": steps, "ms_per_step": dt / steps * 1e3,
+                 "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": nthr, "kind": "port", "sample": sample,
+                                  "host_cores_nproc": os.cpu_count(), "setup_list_and_force_s": t_setup},
                  "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0, "n_gpus": args.gpus})
+    if steps != args.steps:
+        line["steps_requested"] = args.steps
+    if not os.environ.get("BENCH_CPU_QUICK"):   # (the GPU arm's cpu_baseline leg asks for the headline number only)
+        try:
+            line["cpu_baseline"]["variants_1core"] = cpu_variants()
+            line["cpu_baseline"]["configs0_c1"] = cpu_c1(nthr)
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"]["variants_error"] = repr(e)
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def new_ctx(c, local, args, stream):
+    import util
+    from msmpscu_b200 import capi
+    ctx = capi.Context(local)
+    # an explicit torch stream (a non-null handle): the library launches on it and the timing events are recorded on it.
+    ctx.set_stream(stream.cuda_stream)
+    ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
+    ctx.set_option(capi.OPT_FORCE_PATH, {"auto": 0, "generic": 1, "tiled": 2}[args.path])
+    ctx.tables_set(util.product_tables(c), c.ru * c.ru)
+    ctx.nlist_init(c.nb_rm, c.mxkvois)
+    if args.lanes:
+        ctx.set_option(capi.OPT_TILED_LANES, args.lanes)
+    if args.threads:
+        ctx.set_option(capi.OPT_TILED_THREADS, args.threads)
+    if args.stages:
+        ctx.set_option(capi.OPT_TILED_STAGES, args.stages)
+    if args.bankorder >= 0:
+        ctx.set_option(capi.OPT_TILED_BANKORDER, args.bankorder)
+    ctx.set_option(capi.OPT_TILED_CLASSES, args.classes)
+    ctx.epc_set(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
+    return ctx
+
+
+def parity_check(ctx, c, n):
+    """On the state the timed region left behind: (1) forces / dF/drho of the tiled path against the generic path for
+    every atom; (2) both against the CPU oracle on a 10 000-atom range (lists of the generic GPU path, themselves
+    bit-checked against the oracle in tests/).  Per-atom relative errors with a floor of 1e-3 x the largest magnitude."""
+    import util
+    from msmpscu_b200 import capi
+    from oracle import pyorc as O
+    out = {"tolerance": PARITY_TOL, "metric": "max_i |a_i - b_i| / max(|b_i|, 1e-3 max|b|)", "atoms": n}
+    active = ctx.get_option(capi.OPT_ACTIVE_PATH)
+    ctx.force(capi.FORCE)
+    f_t = ctx.download(capi.F_FP, capi.ORDER_ORIGINAL)
+    d_t = ctx.download(capi.F_DEN, capi.ORDER_ORIGINAL)
+    prev = ctx.get_option(capi.OPT_FORCE_PATH)
+    ctx.set_option(capi.OPT_FORCE_PATH, capi.FORCE_PATH_GENERIC)
+    ctx.nlist_build()
+    ctx.force(capi.FORCE)
+    f_g = ctx.download(capi.F_FP, capi.ORDER_ORIGINAL)
+    d_g = ctx.download(capi.F_DEN, capi.ORDER_ORIGINAL)
+    out["timed_path"] = "tiled" if active == capi.FORCE_PATH_TILED else "generic"
+    out["tiled_vs_generic_force"] = util.atom_relerr(f_t, f_g)
+    out["tiled_vs_generic_den"] = util.atom_relerr(d_t, d_g)
+    # oracle on a range in the middle of the cell-sorted array (no z wrap inside the range's neighbourhood)
+    gid = ctx.download(capi.F_GID, capi.ORDER_CELL) - 1
+    xp = ctx.download(capi.F_XP, capi.ORDER_CELL)
+    ityp = ctx.download(capi.F_ITYP, capi.ORDER_CELL)
+    statu = ctx.download(capi.F_STATU, capi.ORDER_CELL)
+    kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
+    npart = min(10000, n)
+    ia0 = max(0, n // 2 - npart // 2)
+    f_o, d_o = O.force_range(xp, ityp, statu, kv, ind, c.zl, c.ifpd, util.oracle_tables(O, c), ia0, npart)
+    sel = gid[ia0:ia0 + npart]
+    out["oracle_sample_atoms"] = npart
+    out["generic_vs_oracle_force"] = util.atom_relerr(f_g[sel], f_o)
+    out["tiled_vs_oracle_force"] = util.atom_relerr(f_t[sel], f_o)
+    out["tiled_vs_oracle_den"] = util.atom_relerr(d_t[sel], d_o)
+    out["ok"] = bool(max(out["tiled_vs_generic_force"], out["tiled_vs_generic_den"], out["generic_vs_oracle_force"],
+                         out["tiled_vs_oracle_force"], out["tiled_vs_oracle_den"]) <= PARITY_TOL)
+    ctx.set_option(capi.OPT_FORCE_PATH, prev)
+    ctx.nlist_build()
+    return out
+
+
+def gpu_c1(local, args):
+    """configs[0]: 8192 W atoms (16^3 bcc cells), NVE, 1000 steps, rebuild every 10; HARMIL drift"""
+    import torch
+    import util
+    from msmpscu_b200 import capi
+    c = c1_case()
+    n = c.xp.shape[0]
+    stream = torch.cuda.current_stream()
+    ctx = capi.Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
+    ctx.tables_set(util.product_tables(c), c.ru * c.ru)
+    ctx.nlist_init(c.nb_rm, c.mxkvois)
+    for f, a in ((capi.F_XP, c.xp), (capi.F_XP1, c.xp1), (capi.F_ITYP, c.ityp), (capi.F_STATU, c.statu)):
+        ctx.upload(f, a)
+    ctx.nlist_build()
+
+    def harmil():
+        ctx.force(capi.FORCE | capi.EPOT)
+        ctx.ekin()
+        ek = ctx.download(capi.F_EKIN)
+        return float((ctx.download(capi.F_EPOT).sum() + ek[ek >= 0.0].sum()) / n)
+
+    h0 = harmil()
+    ctx.run(0, 100, 1, MD_PER_PERIOD, H)       # warm-up, part of the 1000 steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    ctx.run(100, 900, 1, MD_PER_PERIOD, H)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    h1 = harmil()
+    ctx.close()
+    return {"atoms": n, "md_steps": 1000, "value": n * 900 / (e0.elapsed_time(e1) * 1e-3), "unit": "atom-steps/s",
+            "harmil_erg": [h0, h1], "harmil_drift_rel": (h1 - h0) / abs(h0)}
 
 
 def run_ours(args):
@@ -181,75 +384,98 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     c = make_case(args.cells, 12346 + rank, args.nbox, args.potential)
     n = c.xp.shape[0]
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import util
-    ctx = capi.Context(local)
-    # an explicit torch stream (a non-null handle): the library launches on it and the timing events are recorded on it.
-    # (the null handle of torch's default stream would make the context fall back to its own stream, mdb_ctx_set_stream)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
-    ctx.set_option(capi.OPT_FORCE_PATH, {"auto": 0, "generic": 1, "tiled": 2}[args.path])
-    ctx.tables_set(util.product_tables(c), c.ru * c.ru)
-    ctx.nlist_init(c.nb_rm, c.mxkvois)
-    if args.lanes:
-        ctx.set_option(capi.OPT_TILED_LANES, args.lanes)
-    if args.threads:
-        ctx.set_option(capi.OPT_TILED_THREADS, args.threads)
-    if args.stages:
-        ctx.set_option(capi.OPT_TILED_STAGES, args.stages)
-    ctx.set_option(capi.OPT_TILED_CLASSES, args.classes)
-    ctx.epc_set(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
-
-    # host buffers in pinned memory, reference layout XP(N,3) column-major
-    hx = torch.from_numpy(capi.colmajor(c.xp)).pin_memory()
-    hv = torch.from_numpy(capi.colmajor(c.xp1)).pin_memory()
-    hf = torch.empty(3 * n, dtype=torch.float64).pin_memory()
-    ctx.upload_raw(capi.F_XP, hx.data_ptr())
-    ctx.upload_raw(capi.F_XP1, hv.data_ptr())
-    ctx.upload(capi.F_ITYP, c.ityp)
-    ctx.upload(capi.F_STATU, c.statu)
-    ctx.nlist_build()
-    ctx.force(capi.FORCE)
+    # two device contexts on two streams: A carries the resident measurement, A and B alternate in the e2e pipeline
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.set_stream(streams[0])
+    ctxs = [new_ctx(c, local, args, s) for s in streams]
+    # host buffers in page-locked memory, reference layout XP(N,3) column-major; one set per context
+    host = []
+    for ctx in ctxs:
+        hx = torch.from_numpy(capi.colmajor(c.xp)).pin_memory()
+        hv = torch.from_numpy(capi.colmajor(c.xp1)).pin_memory()
+        hf = torch.empty(3 * n, dtype=torch.float64).pin_memory()
+        host.append((hx, hv, hf))
+        ctx.upload_raw(capi.F_XP, hx.data_ptr())
+        ctx.upload_raw(capi.F_XP1, hv.data_ptr())
+        ctx.upload(capi.F_ITYP, c.ityp)
+        ctx.upload(capi.F_STATU, c.statu)
+        ctx.nlist_build()
+        ctx.force(capi.FORCE)
+    ctx = ctxs[0]
+    stream = streams[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(stream)
-        for i in range(k):
-            fn(i)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def reduce_max(ms):
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
-    itime = [0]
+    def timed(fn, k, finish=None):
+        """K calls of fn between two events on stream A; `finish` drains the pipeline (and joins stream B) before the end event"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(k):
+            fn(i)
+        if finish:
+            finish()
+        e1.record(stream)
+        barrier()
+        return reduce_max(e0.elapsed_time(e1))
+
+    itime = [0, 0]
 
     def step_resident(_):
-        ctx.run(itime[0], MD_PER_STEP, 1, MD_PER_STEP, H)
+        ctx.run(itime[0], MD_PER_STEP, 1, MD_PER_PERIOD, H)
         itime[0] += MD_PER_STEP
 
-    def step_e2e(_):
-        # the reference-facing call with HOST buffers: CopyIn (XP, XP1) -> 10 x For_One_Step -> CopyOut (XP, XP1, FP)
+    pending = [False, False]
+
+    def make_job(md_steps):
+        def job(i):
+            # one independent job through the reference-facing calls with HOST buffers:
+            # CopyIn (XP, XP1) -> md_steps x For_One_Step -> CopyOut (XP, XP1, FP); ONE host synchronisation per job
+            k = i & 1
+            cx, (hx, hv, hf) = ctxs[k], host[k]
+            if pending[k]:
+                cx.sync()                      # the previous job of this context has landed in its host buffers
+            cx.upload_raw(capi.F_XP, hx.data_ptr())
+            cx.upload_raw(capi.F_XP1, hv.data_ptr())
+            cx.run_async(itime[k], md_steps, 1, MD_PER_PERIOD, H)
+            itime[k] += md_steps
+            cx.download_raw_async(capi.F_XP, hx.data_ptr())
+            cx.download_raw_async(capi.F_XP1, hv.data_ptr())
+            cx.download_raw_async(capi.F_FP, hf.data_ptr())
+            pending[k] = True
+        return job
+
+    def drain():
+        for k in (0, 1):
+            if pending[k]:
+                ctxs[k].sync()
+                pending[k] = False
+        ev = torch.cuda.Event()
+        ev.record(streams[1])
+        streams[0].wait_event(ev)
+
+    def job_serial(_):
+        hx, hv, hf = host[0]
         ctx.upload_raw(capi.F_XP, hx.data_ptr())
         ctx.upload_raw(capi.F_XP1, hv.data_ptr())
-        ctx.run(itime[0], MD_PER_STEP, 1, MD_PER_STEP, H)
-        itime[0] += MD_PER_STEP
+        ctx.run(itime[0], MD_PER_PERIOD, 1, MD_PER_PERIOD, H)
+        itime[0] += MD_PER_PERIOD
         ctx.download_raw(capi.F_XP, hx.data_ptr())
         ctx.download_raw(capi.F_XP1, hv.data_ptr())
         ctx.download_raw(capi.F_FP, hf.data_ptr())
@@ -264,16 +490,28 @@ def run_ours(args):
     clocks = sampler.result()
     value = world * n * MD_PER_STEP * args.steps / (ms * 1e-3)
 
-    # end to end through host buffers
-    step_e2e(0)
-    ms_e2e = timed(step_e2e, max(3, args.steps // 4))
-    e2e_val = world * n * MD_PER_STEP * max(3, args.steps // 4) / (ms_e2e * 1e-3)
+    # end to end through host buffers (pipelined over the two contexts)
+    job = make_job(MD_PER_STEP)
+    job(0); job(1); drain()
+    torch.cuda.synchronize()
+    ms_e2e = timed(job, args.steps, drain)
+    e2e_val = world * n * MD_PER_STEP * args.steps / (ms_e2e * 1e-3)
+    # diagnostics: a transfer every list period (10 MD steps, round 1's e2e unit), pipelined and serial
+    job10 = make_job(MD_PER_PERIOD)
+    job10(0); job10(1); drain()
+    k10 = max(10, args.steps)
+    ms_e2e10 = timed(job10, k10, drain)
+    job_serial(0)
+    ms_ser10 = timed(job_serial, k10)
+    e2e_diag = {"transfer_every_md_steps": MD_PER_PERIOD,
+                "pipelined_two_contexts": world * n * MD_PER_PERIOD * k10 / (ms_e2e10 * 1e-3),
+                "serial_one_context": world * n * MD_PER_PERIOD * k10 / (ms_ser10 * 1e-3),
+                "ms_per_job_pipelined": ms_e2e10 / k10, "ms_per_job_serial": ms_ser10 / k10, "numa_cpulist": numa}
 
     # per-kernel device times (CUDA events on the launching stream) for the roofline
     ctx.prof_reset()
     ctx.prof_enable(True)
-    for i in range(3):
-        step_resident(i)
+    step_resident(0)
     prof = ctx.prof_get()
     ctx.prof_enable(False)
     tot = sum(v[1] for v in prof.values())
@@ -296,13 +534,15 @@ def run_ours(args):
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
+            "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload, committed; "
+                                                  "not re-measured by this run)" if traffic else None,
+            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
             "algorithmic_bytes_per_atom": BYTES_PASS1 if dom == "pass1" else BYTES_PASS2,
             "avg_launch_ms": tms / nl if nl else None,
             "kernel_share_of_step": tms / tot if tot else None,
             "whole_step": {"achieved": value / world * BYTES_STEP / 1e9, "frac": value / world * BYTES_STEP / 1e9 / peak,
                            "bytes_per_atom_step": BYTES_STEP},
-            "per_class_ms_per_md_step": {k: v[1] / (3 * MD_PER_STEP) for k, v in prof.items() if v[0]}}
+            "per_class_ms_per_md_step": {k: v[1] / MD_PER_STEP for k, v in prof.items() if v[0]}}
     if traffic and nl:
         # the kernel's OWN stream (16-bit class-limited slot list, positions from L2) and the pipe that actually bounds it
         roof["own_stream"] = {"dram_bytes_per_atom": traffic / n, "achieved_GBs": traffic / (tms / nl * 1e-3) / 1e9,
@@ -319,18 +559,38 @@ def run_ours(args):
         line["roofline_note"] = "canonical byte counts assume K_list = 112 (bcc W); this workload lists 134 neighbours"
     line.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "gpu_launches": int(launches),
                  "e2e": {"value": e2e_val, "unit": "atom-steps/s", "h2d_bytes_per_step": 2 * 24 * n,
-                         "d2h_bytes_per_step": 3 * 24 * n, "ms_per_step": ms_e2e / max(3, args.steps // 4)},
-                 "roofline": roof, "force_path": args.path})
+                         "d2h_bytes_per_step": 3 * 24 * n, "ms_per_step": ms_e2e / args.steps,
+                         "how": "independent jobs alternate between two device contexts / streams; per job: CopyIn XP, XP1 from "
+                                "page-locked host memory, %d MD steps, CopyOut XP, XP1, FP; one host synchronisation per job" % MD_PER_STEP},
+                 "e2e_diagnostics": e2e_diag,
+                 "roofline": roof, "force_path": args.path, "timed_region_s": ms * 1e-3})
     line["config"]["atoms_total"] = n * world
 
+    if rank == 0 and not args.no_parity:
+        try:
+            line["parity_check"] = parity_check(ctx, c, n)
+        except Exception as e:  # a parity failure must be visible in the line, not kill the measurement
+            line["parity_check"] = {"ok": False, "error": repr(e)}
+    if rank == 0 and world == 1 and not args.no_c1:
+        try:
+            line["configs0_c1"] = gpu_c1(local, args)
+        except Exception as e:  # pragma: no cover
+            line["configs0_c1"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, dt, ncpu, nthr = cpu_arm(args.cpu_cells, 2, 1)
-        line["cpu_baseline"] = {"value": val, "unit": "atom-steps/s", "cores": nthr, "kind": "port",
-                                "sample": "bcc W %d atoms (%d^3 cells), same potential/cutoffs/EPC, 2 x %d MD steps "
-                                          "incl. rebuilds, OpenMP over atoms" % (ncpu, args.cpu_cells, MD_PER_STEP)}
+        # in a fresh process (no CUDA context, no second OpenMP runtime beside it): the same code path as --impl reference
+        import subprocess
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cells", str(args.cells),
+                                  "--nbox", str(args.nbox), "--potential", args.potential, "--steps", "2", "--warmup", "1"],
+                                 capture_output=True, text=True, timeout=900, env=dict(os.environ, BENCH_CPU_QUICK="1"))
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": "atom-steps/s", "cores": os.cpu_count(), "kind": "port", "error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
-    ctx.close()
+    for cx in ctxs:
+        cx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -340,6 +600,7 @@ def run_dd(args):
     seed); value = atoms of the box x MD steps / max-over-ranks device time."""
     import torch
     import torch.distributed as dist
+    import util
     from msmpscu_b200 import capi
     from msmpscu_b200.domain import SlabDomain
 
@@ -351,8 +612,6 @@ def run_dd(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = make_case(args.cells, 777)
     n = c.xp.shape[0]
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import util
     ctx = capi.Context(local)
     ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
     ctx.set_option(capi.OPT_FORCE_PATH, capi.FORCE_PATH_TILED)
@@ -368,8 +627,8 @@ def run_dd(args):
     itime = [0]
 
     def block(_):
-        for _i in range(MD_PER_STEP):
-            dom.step(itime[0], 1, MD_PER_STEP, H)
+        for _i in range(MD_PER_PERIOD):
+            dom.step(itime[0], 1, MD_PER_PERIOD, H)
             itime[0] += 1
 
     def barrier():
@@ -409,10 +668,10 @@ def run_dd(args):
     line["scaling"] = "strong"
     line["config"].update({"workload": "configs[4] family: ONE bcc W box of %d atoms (%d^3 cells) cut into %d z-slabs, ghost-layer "
                                        "exchange of {x,y,z,den} records over NCCL twice per step, list rebuilt every %d steps "
-                                       "(owned ranges broadcast, identical device sort on every rank)" % (n, args.cells, world, MD_PER_STEP),
-                           "atoms_per_gpu": a1 - a0, "atoms_total": n,
+                                       "(owned ranges broadcast, identical device sort on every rank)" % (n, args.cells, world, MD_PER_PERIOD),
+                           "atoms_per_gpu": a1 - a0, "atoms_total": n, "md_steps_per_step": MD_PER_PERIOD,
                            "parallelism": "z-slab domain decomposition, 1 ghost cell layer per side"})
-    line.update({"value": n * MD_PER_STEP * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "clocks": clocks,
+    line.update({"value": n * MD_PER_PERIOD * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "clocks": clocks,
                  "gpu_launches": int(launches), "force_path": "tiled", "mode": "dd",
                  "phase_ms_per_block_by_rank": phases})
     if rank == 0:

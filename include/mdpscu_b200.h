@@ -87,7 +87,9 @@ const char *mdb_version(void);
 /* run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = the context's own */
 int         mdb_ctx_set_stream(mdb_ctx *ctx, void *cuda_stream);
 void       *mdb_ctx_stream(mdb_ctx *ctx);
-int         mdb_sync(mdb_ctx *ctx); /* SynchronizeDevices */
+/* SynchronizeDevices.  Also completes what mdb_run_async / mdb_state_download_async enqueued: returns the out-of-box
+ * count of a pending mdb_run_async block (>= 0), else 0 */
+int         mdb_sync(mdb_ctx *ctx);
 
 /* ------------------------------------------------------------------------------------
  * device box: Initialize_Globle_Variables_DEV / Allocate_Working_Variables
@@ -103,6 +105,10 @@ int mdb_natom(const mdb_ctx *ctx);
  * host buffers have the reference shape of the field. */
 int mdb_state_upload(mdb_ctx *ctx, int field, const void *host, int order);
 int mdb_state_download(mdb_ctx *ctx, int field, void *host, int order);
+/* the same CopyOut enqueued on the context's stream without waiting (the reference's CopyOut blocks the host thread,
+ * MD_SimBoxArray_GPU.F90:225-318): `host` should be page-locked and holds the field after the next mdb_sync.  Uploads
+ * never wait.  With two contexts on two streams, the transfers of one box overlap the steps of the other. */
+int mdb_state_download_async(mdb_ctx *ctx, int field, void *host, int order);
 /* device pointer with the reference shape (CELL order), for CUDA(-Fortran) code that reads
  * dm_WorkSpace / dm_Neighbors arrays directly (Analysis/, BoostMeths/ ...).  XP, DEN and INDI are
  * materialised from the packed internal layout on request and stay valid until the next
@@ -177,6 +183,9 @@ int mdb_epc_correct(mdb_ctx *ctx, double h);
  * ---------------------------------------------------------------------------------- */
 int mdb_step(mdb_ctx *ctx, int itime, int it0, int nb_uptab, double h);
 int mdb_run(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double h);
+/* mdb_run without the final synchronisation: returns MDB_OK once the block is enqueued (the host only waits inside a
+ * list rebuild, for its capacity check); mdb_sync returns the block's out-of-box count */
+int mdb_run_async(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double h);
 
 /* ------------------------------------------------------------------------------------
  * single huge box over several GPUs: slab decomposition along z (whole z-layers of cells per rank).
@@ -284,6 +293,8 @@ int mdb_cg(mdb_ctx *ctx, int mxnumsteps, int meth, double maxdis, double mindis,
 #define MDB_OPT_FUSE_EPILOGUE 5  /* mdb_run on the tiled path: EPC friction + corrector inside the force-pass   */
                                  /* epilogue (1) or as one separate element-wise kernel (0, default: faster)    */
 #define MDB_OPT_TILED_STAGES  6  /* shared-memory pipeline stages of the pass kernel: 2 (default) or 3           */
+#define MDB_OPT_TILED_BANKORDER 7 /* 1: the list builder orders each scanned class so that the record             */
+                                 /* gathers of a half-warp spread over the shared-memory bank groups; 0 (default): scan order */
 #define MDB_FORCE_PATH_AUTO    0
 #define MDB_FORCE_PATH_GENERIC 1
 #define MDB_FORCE_PATH_TILED   2

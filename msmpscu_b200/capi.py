@@ -61,6 +61,8 @@ SYMBOLS = {
     "mdb_epc_apply": (C.c_int, [C.c_void_p]),
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_run_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_state_download_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "mdb_global_t": (C.c_int, [C.c_void_p, c_dp]),
     "mdb_vel_scaling": (C.c_int, [C.c_void_p, C.c_double]),
     "mdb_check_timestep": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, c_ip]),
@@ -102,6 +104,7 @@ SYMBOLS = {
 }
 
 OPT_FORCE_PATH, OPT_TILED_LANES, OPT_TILED_CLASSES, OPT_ACTIVE_PATH, OPT_TILED_THREADS, OPT_FUSE_EPILOGUE, OPT_TILED_STAGES = 0, 1, 2, 3, 4, 5, 6
+OPT_TILED_BANKORDER = 7
 FORCE_PATH_AUTO, FORCE_PATH_GENERIC, FORCE_PATH_TILED = 0, 1, 2
 QUENCH_LSEARCH = 65536  # CP_DAMPSCHEME_LSEARCH
 
@@ -213,6 +216,10 @@ class Context:
     def download_raw(self, field, ptr, order=ORDER_ORIGINAL):
         self._chk(self.lib.mdb_state_download(self.h, field, C.c_void_p(ptr), order))
 
+    def download_raw_async(self, field, ptr, order=ORDER_ORIGINAL):
+        """enqueue the CopyOut of one field into page-locked host memory; complete after sync()"""
+        self._chk(self.lib.mdb_state_download_async(self.h, field, C.c_void_p(ptr), order))
+
     def download(self, field, order=ORDER_ORIGINAL):
         n = self.n
         if field in (F_XP, F_XP1, F_FP, F_DIS):
@@ -295,6 +302,10 @@ class Context:
     def run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
 
+    def run_async(self, itime0, nsteps, it0, nb_uptab, h):
+        """enqueue nsteps steps; sync() returns the block's out-of-box count"""
+        return self._chk(self.lib.mdb_run_async(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
     def global_t(self):
         t = C.c_double(0.0)
         self._chk(self.lib.mdb_global_t(self.h, C.byref(t)))
@@ -363,7 +374,7 @@ class Context:
         return dict(zip(keys, list(out)))
 
     def sync(self):
-        self._chk(self.lib.mdb_sync(self.h))
+        return self._chk(self.lib.mdb_sync(self.h))
 
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.lib.mdb_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

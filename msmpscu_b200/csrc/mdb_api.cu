@@ -185,6 +185,10 @@ extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
         c->tiled.use_classes = value != 0;
         return MDB_OK;
     }
+    if (option == MDB_OPT_TILED_BANKORDER && (value == 0 || value == 1)) {
+        c->tiled.bank_order = value != 0; c->list_valid = false;
+        return MDB_OK;
+    }
     if (option == MDB_OPT_FORCE_PATH && value >= MDB_FORCE_PATH_AUTO && value <= MDB_FORCE_PATH_TILED) {
         c->opt_force_path = value;
         c->list_valid = false; // the two paths keep different list formats
@@ -202,6 +206,7 @@ extern "C" int mdb_get_option(const mdb_ctx *c, int option)
     if (option == MDB_OPT_TILED_STAGES) return c->tiled.stages_opt;
     if (option == MDB_OPT_FUSE_EPILOGUE) return c->opt_fuse_epilogue;
     if (option == MDB_OPT_TILED_CLASSES) return c->tiled.use_classes ? 1 : 0;
+    if (option == MDB_OPT_TILED_BANKORDER) return c->tiled.bank_order ? 1 : 0;
     if (option == MDB_OPT_ACTIVE_PATH) return c->tiled.active ? MDB_FORCE_PATH_TILED : MDB_FORCE_PATH_GENERIC;
     return MDB_ERR_ARG;
 }
@@ -219,7 +224,13 @@ extern "C" void *mdb_ctx_stream(mdb_ctx *c) { return c ? (void *)c->stream : nul
 extern "C" int mdb_sync(mdb_ctx *c)
 {
     if (!c) return MDB_ERR_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->dev));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stage_off = 0; // every staged transfer has landed
+    if (c->run_pending) { // mdb_run_async: the counters were copied at the end of the block
+        c->run_pending = false;
+        return c->h_counters[CNT_OOB_TOTAL];
+    }
     return MDB_OK;
 }
 
@@ -355,11 +366,33 @@ __global__ void k_down_pos(int n, int which, const double4 *__restrict__ pos, do
     else dst[o] = p.w;
 }
 
-static int ensure_stage(mdb_ctx *c, size_t bytes)
+// Device staging for field transfers: a bump-allocated pool, so that several asynchronous transfers can be in flight on
+// the stream at once (mdb_state_download_async).  A slot stays valid until the next mdb_sync / synchronous transfer,
+// which rewinds the pool.  Growing the pool synchronises the stream first (outstanding copies finish), once.
+static int stage_slot(mdb_ctx *c, size_t bytes, void **out)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (c->stage_off + bytes > c->stage_bytes) {
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        c->stage_off = 0;
+        if (bytes > c->stage_bytes) {
+            if (c->stage) cudaFree(c->stage);
+            c->stage = nullptr; c->stage_bytes = 0;
+            CUDA_TRY(c, cudaMalloc(&c->stage, bytes));
+            c->stage_bytes = bytes;
+        }
+    }
+    *out = (char *)c->stage + c->stage_off;
+    c->stage_off += bytes;
+    return MDB_OK;
+}
+// room for `count` more slots of `bytes` each without a later regrow (one synchronisation now instead of one per call)
+static int stage_reserve(mdb_ctx *c, size_t bytes)
 {
     if (c->stage_bytes >= bytes) return MDB_OK;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (c->stage) cudaFree(c->stage);
-    c->stage = nullptr; c->stage_bytes = 0;
+    c->stage = nullptr; c->stage_bytes = 0; c->stage_off = 0;
     CUDA_TRY(c, cudaMalloc(&c->stage, bytes));
     c->stage_bytes = bytes;
     return MDB_OK;
@@ -407,23 +440,26 @@ extern "C" int mdb_state_upload(mdb_ctx *c, int field, const void *host, int ord
     CUDA_TRY(c, cudaSetDevice(c->dev));
     int n = c->n;
     size_t bytes = (size_t)n * fi.ncol * (fi.is_int ? sizeof(int) : sizeof(double));
-    int rc = ensure_stage(c, bytes);
+    // room for a whole CopyIn/CopyOut set (XP, XP1, FP, DIS + integers) without regrowing between the calls
+    int rc = stage_reserve(c, (size_t)n * 128);
     if (rc) return rc;
-    CUDA_TRY(c, cudaMemcpyAsync(c->stage, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    void *stg = nullptr;
+    if ((rc = stage_slot(c, bytes, &stg))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(stg, host, bytes, cudaMemcpyHostToDevice, c->stream));
     const int *map = (order == MDB_ORDER_ORIGINAL) ? c->gidinv : nullptr;
     int nb = cdiv(n, 256);
     ProfScope ps(c, MDB_K_OTHER);
-    if (field == MDB_F_XP) k_up_pos<<<nb, 256, 0, c->stream>>>(n, 0, (const double *)c->stage, c->pos, map);
-    else if (field == MDB_F_DEN) k_up_pos<<<nb, 256, 0, c->stream>>>(n, 1, (const double *)c->stage, c->pos, map);
-    else if (fi.is_int) k_up_i<<<nb, 256, 0, c->stream>>>(n, (const int *)c->stage, dptr_i(c, field), map);
-    else k_up_d<<<nb, 256, 0, c->stream>>>(n, fi.ncol, (const double *)c->stage, dptr_d(c, field), map);
+    if (field == MDB_F_XP) k_up_pos<<<nb, 256, 0, c->stream>>>(n, 0, (const double *)stg, c->pos, map);
+    else if (field == MDB_F_DEN) k_up_pos<<<nb, 256, 0, c->stream>>>(n, 1, (const double *)stg, c->pos, map);
+    else if (fi.is_int) k_up_i<<<nb, 256, 0, c->stream>>>(n, (const int *)stg, dptr_i(c, field), map);
+    else k_up_d<<<nb, 256, 0, c->stream>>>(n, fi.ncol, (const double *)stg, dptr_d(c, field), map);
     CUDA_TRY(c, cudaGetLastError());
     if (field == MDB_F_XP) mdb_mark_positions_dirty(c);
     if (field == MDB_F_ITYP) c->list_valid = false;
     return MDB_OK;
 }
 
-extern "C" int mdb_state_download(mdb_ctx *c, int field, void *host, int order)
+static int state_download(mdb_ctx *c, int field, void *host, int order, bool sync)
 {
     if (!c || !host) return mdb_fail(c, MDB_ERR_ARG, "mdb_state_download: null argument");
     if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_download: mdb_box_set first");
@@ -433,28 +469,44 @@ extern "C" int mdb_state_download(mdb_ctx *c, int field, void *host, int order)
     if (fi.per_cell) {
         if (!c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_download: no cell data yet");
         CUDA_TRY(c, cudaMemcpyAsync(host, dptr_i(c, field), sizeof(int) * (size_t)c->nc, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (sync) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         return MDB_OK;
     }
     if (field == MDB_F_KVOIS && !c->kvois) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_download: no list yet");
     int n = c->n;
     size_t bytes = (size_t)n * fi.ncol * (fi.is_int ? sizeof(int) : sizeof(double));
-    int rc = ensure_stage(c, bytes);
+    int rc = stage_reserve(c, (size_t)n * 128);
     if (rc) return rc;
+    void *stg = nullptr;
+    if ((rc = stage_slot(c, bytes, &stg))) return rc;
     bool id_only = (field == MDB_F_GID || field == MDB_F_GIDINV);
     const int *map = (order == MDB_ORDER_ORIGINAL && !id_only) ? c->gidinv : nullptr;
     int nb = cdiv(n, 256);
     {
         ProfScope ps(c, MDB_K_OTHER);
-        if (field == MDB_F_XP) k_down_pos<<<nb, 256, 0, c->stream>>>(n, 0, c->pos, (double *)c->stage, map);
-        else if (field == MDB_F_DEN) k_down_pos<<<nb, 256, 0, c->stream>>>(n, 1, c->pos, (double *)c->stage, map);
-        else if (fi.is_int) k_down_i<<<nb, 256, 0, c->stream>>>(n, dptr_i(c, field), (int *)c->stage, map);
-        else k_down_d<<<nb, 256, 0, c->stream>>>(n, fi.ncol, dptr_d(c, field), (double *)c->stage, map);
+        if (field == MDB_F_XP) k_down_pos<<<nb, 256, 0, c->stream>>>(n, 0, c->pos, (double *)stg, map);
+        else if (field == MDB_F_DEN) k_down_pos<<<nb, 256, 0, c->stream>>>(n, 1, c->pos, (double *)stg, map);
+        else if (fi.is_int) k_down_i<<<nb, 256, 0, c->stream>>>(n, dptr_i(c, field), (int *)stg, map);
+        else k_down_d<<<nb, 256, 0, c->stream>>>(n, fi.ncol, dptr_d(c, field), (double *)stg, map);
     }
     CUDA_TRY(c, cudaGetLastError());
-    CUDA_TRY(c, cudaMemcpyAsync(host, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(host, stg, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (sync) {
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        c->stage_off = 0;
+    }
     return MDB_OK;
+}
+
+extern "C" int mdb_state_download(mdb_ctx *c, int field, void *host, int order)
+{
+    return state_download(c, field, host, order, true);
+}
+// CopyOut without the host synchronisation: the permutation kernel and the device-to-host copy are enqueued on the
+// context's stream; `host` (page-locked memory for a truly asynchronous copy) holds the field after the next mdb_sync.
+extern "C" int mdb_state_download_async(mdb_ctx *c, int field, void *host, int order)
+{
+    return state_download(c, field, host, order, false);
 }
 
 // host-side convenience over mdb_atomic_stress: AP(N,9) column-major in the requested order
@@ -473,14 +525,16 @@ extern "C" int mdb_atomic_stress_host(mdb_ctx *c, double *h_avp, int order)
     int rc = mdb_atomic_stress(c, c->avp);
     if (rc < 0) return rc;
     const size_t bytes = sizeof(double) * 9 * (size_t)n;
-    if ((rc = ensure_stage(c, bytes))) return rc;
+    void *stg = nullptr;
+    if ((rc = stage_slot(c, bytes, &stg))) return rc;
     {
         ProfScope ps(c, MDB_K_OTHER);
-        k_down_d<<<cdiv(n, 256), 256, 0, c->stream>>>(n, 9, c->avp, (double *)c->stage, order == MDB_ORDER_ORIGINAL ? c->gidinv : nullptr);
+        k_down_d<<<cdiv(n, 256), 256, 0, c->stream>>>(n, 9, c->avp, (double *)stg, order == MDB_ORDER_ORIGINAL ? c->gidinv : nullptr);
     }
     CUDA_TRY(c, cudaGetLastError());
-    CUDA_TRY(c, cudaMemcpyAsync(h_avp, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(h_avp, stg, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stage_off = 0;
     return MDB_OK;
 }
 
@@ -651,11 +705,11 @@ extern "C" int mdb_nlist_cellinfo(const mdb_ctx *c, int ncell[3], int *nc_total,
     return MDB_OK;
 }
 
-extern "C" int mdb_nlist_build(mdb_ctx *c)
+// Rebuild + capacity check (one small device-to-host copy and a stream synchronisation): when a tile's halo, an atom's
+// list or mxKVOIS overflowed on the tiled path, the same positions are rebuilt at once on the generic path (AUTO), so no
+// step ever runs on an incomplete list.  Used by mdb_nlist_build and at every rebuild inside mdb_run.
+int mdb_list_rebuild_checked(mdb_ctx *c)
 {
-    if (!c) return MDB_ERR_ARG;
-    if (!c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_nlist_build: mdb_nlist_init first");
-    CUDA_TRY(c, cudaSetDevice(c->dev));
     int rc = mdb_list_rebuild(c);
     if (rc < 0) return rc;
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
@@ -672,8 +726,19 @@ extern "C" int mdb_nlist_build(mdb_ctx *c)
         if (rc < 0) return rc;
         CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        c->fallbacks++;
     }
     c->mxnac = c->h_counters[CNT_MXNAC];
+    return MDB_OK;
+}
+
+extern "C" int mdb_nlist_build(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_nlist_build: mdb_nlist_init first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    int rc = mdb_list_rebuild_checked(c);
+    if (rc < 0) return rc;
     if (c->dd_on) {
         if (!c->tiled.active) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "slab decomposition needs the tiled path");
         if ((rc = mdb_dd_update(c)) < 0) return rc;
@@ -819,16 +884,18 @@ extern "C" int mdb_nlist_copyout(mdb_ctx *c, int *kvois, int *indi, int order)
         if (order == MDB_ORDER_CELL) {
             CUDA_TRY(c, cudaMemcpyAsync(indi, c->indi, bytes, cudaMemcpyDeviceToHost, c->stream));
         } else {
-            int rc = ensure_stage(c, bytes);
+            void *stg = nullptr;
+            int rc = stage_slot(c, bytes, &stg);
             if (rc) return rc;
             {
                 ProfScope ps(c, MDB_K_OTHER);
-                k_indi_to_original<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->mxkvois, c->indi, c->kvois, c->gid, (int *)c->stage);
+                k_indi_to_original<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->mxkvois, c->indi, c->kvois, c->gid, (int *)stg);
             }
             CUDA_TRY(c, cudaGetLastError());
-            CUDA_TRY(c, cudaMemcpyAsync(indi, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(indi, stg, bytes, cudaMemcpyDeviceToHost, c->stream));
         }
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        c->stage_off = 0;
     }
     return MDB_OK;
 }

@@ -127,6 +127,7 @@ struct TileListArgs {
     int *kvois; unsigned short *nbl; unsigned short *ncls; int *counters; const TileDesc *desc;
     int tile_lo;          // first tile of this rank (slab decomposition), 0 otherwise
     int lcap;             // rows of the per-atom shared-memory list
+    int bank_order;       // order the scanned classes for conflict-free record reads (see the write-out)
     float rm2[MDB_MXGROUP * MDB_MXGROUP];
     float rc2[2]; // class radii^2 (build-time, fp32): class 0 <= rc2[0] < class 1 <= rc2[1] < class 2
 };
@@ -212,8 +213,57 @@ __device__ __forceinline__ void pair_barrier(int cell) // the two warps of one o
     asm volatile("bar.sync %0, 64;" ::"r"(cell + 1) : "memory");
 }
 
+// ---- bank-aware order of a list class (see the write-out of k_tile_nlist).
+// residue (slot mod 4) that lane lam0 + e % G of a half-warp wants at list entry e (row e / G)
+template <int G>
+__device__ __forceinline__ unsigned list_wanted(int lam0, int e) { return (unsigned)((((lam0 + e % G) >> 1) + e / G) & 3); }
+// Entries [a, b) of one column (stride 32 shorts, b - a <= 255): counting pass, in-place American-flag sort by slot residue
+// driven by four 8-bit cursors packed in one register, then the deal: entry position e takes the next entry of the residue it
+// wants, or of a residue in surplus when none is left; the dealt order is staged in the free rows [scr, scr + b - a) of the
+// column and copied back.  Loop bodies are branch-free: the lanes of the warp work on different atoms.
+template <int G>
+__device__ __noinline__ void seg_deal(unsigned short *col, int a, int b, int lam0, int scr)
+{
+    unsigned cnt = 0u, want = 0u;
+    for (int k = a; k < b; k++) { cnt += 1u << (8 * (col[k * 32] & 3u)); want += 1u << (8 * list_wanted<G>(lam0, k)); }
+    const unsigned c0 = cnt & 255u, c1 = (cnt >> 8) & 255u, c2 = (cnt >> 16) & 255u;
+    const unsigned start = (c0 << 8) | ((c0 + c1) << 16) | ((c0 + c1 + c2) << 24);
+    unsigned cur = start;
+    const unsigned end = start + cnt;
+#pragma unroll 1
+    for (unsigned bkt = 0; bkt < 3; bkt++) { // the last bucket is in place once the first three are
+        int i = (int)((cur >> (8 * bkt)) & 255u);
+        const int e = (int)((end >> (8 * bkt)) & 255u);
+        while (i < e) {
+            const unsigned v = col[(a + i) * 32], r = v & 3u;
+            const bool same = r == bkt;
+            const int j = same ? i : (int)((cur >> (8 * r)) & 255u);
+            const unsigned w = col[(a + j) * 32];
+            col[(a + j) * 32] = (unsigned short)v;
+            col[(a + i) * 32] = (unsigned short)w;
+            cur += same ? 0u : (1u << (8 * r));
+            i += same ? 1 : 0;
+        }
+    }
+    cur = start;
+    unsigned have = cnt;
+#pragma unroll 1
+    for (int e = a; e < b; e++) {
+        const unsigned t = list_wanted<G>(lam0, e);
+        unsigned r = t;
+        if (((have >> (8 * t)) & 255u) == 0u) {
+#pragma unroll
+            for (unsigned x = 0; x < 4; x++)
+                if (((have >> (8 * x)) & 255u) > ((want >> (8 * x)) & 255u)) r = x;
+        }
+        col[(scr + e - a) * 32] = col[(a + (int)((cur >> (8 * r)) & 255u)) * 32];
+        cur += 1u << (8 * r); have -= 1u << (8 * r); want -= 1u << (8 * t);
+    }
+    for (int e = a; e < b; e++) col[e * 32] = col[(scr + e - a) * 32];
+}
+
 template <int G, bool MT>
-__global__ void __launch_bounds__(64 * TILE_MAX_W)
+__global__ void __launch_bounds__(64 * TILE_MAX_W, 2)
 k_tile_nlist(TileParams P, TileListArgs A)
 {
     extern __shared__ __align__(16) unsigned char nl_smem[];
@@ -387,14 +437,27 @@ k_tile_nlist(TileParams P, TileListArgs A)
         }
         A.ncls[ia] = (unsigned short)lo;               // class 0
         A.ncls[ia + P.npad] = (unsigned short)mid;     // classes 0+1
+        // ---- bank-aware order inside the two classes the passes scan.  A pass reads the staged 32-byte record of a slot as two
+        // LDS.128 (even lanes {x,y} first, odd lanes {z,den} first); the hardware serves an LDS.128 per HALF-warp and takes
+        // max(2, lanes per 16-byte bank group) cycles for it (tools/micro/lds128_patterns.cu), so a row of the list is
+        // conflict-free when the 8 even and the 8 odd lanes of a half-warp each hold every slot residue (mod 4) exactly twice.
+        // Lane lam of the half-warp therefore WANTS residue ((lam >> 1) + row) & 3 at list row `row`; every class segment is
+        // sorted by residue in place and dealt out to the positions that want it, leftovers fill the remaining positions.
+        const int lam0 = ((ia - H.own_start) % (16 / G)) * G; // first lane of this atom inside its half-warp
+        // the free rows of the column [nn, lcap) are the scratch space of the deal
+        if (A.bank_order && mid <= 255 && lcap - nn >= max(lo, mid - lo)) {
+            seg_deal<G>(col, 0, lo, lam0, nn);
+            seg_deal<G>(col, lo, mid, lam0, nn);
+        }
         // ---- write out: 4G consecutive entries form one contiguous 8G-byte block [gl][m%4] of the layout
-        const unsigned pad = (unsigned)P.hcap;
+        const unsigned pad = (unsigned)P.hcap;         // four dummy records hcap .. hcap+3: a pad takes the wanted residue too
         for (int q = 0; q * 4 * G < nn; q++) {
             unsigned short blk[4 * G];
 #pragma unroll
             for (int j = 0; j < 4 * G; j++) {
                 const int k = q * 4 * G + j;
-                blk[(j % G) * 4 + j / G] = (k < nn) ? (unsigned short)(col[k * 32] & 0x3fffu) : (unsigned short)pad;
+                blk[(j % G) * 4 + j / G] = (k < nn) ? (unsigned short)(col[k * 32] & 0x3fffu)
+                                                    : (unsigned short)(pad + (A.bank_order ? list_wanted<G>(lam0, k) : 0u));
             }
             uint4 *dst = reinterpret_cast<uint4 *>(A.nbl + ((((size_t)q * P.npad + (size_t)ia) * G) << 2));
 #pragma unroll
@@ -553,14 +616,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #define TP_MAXBUF 3
 #define TP_HDR_BYTES 256 // mbarriers [full, ready, empty] x stages, stage info, chunk counters
 __host__ __device__ __forceinline__ size_t al128(size_t x) { return (x + 127) & ~(size_t)127; }
-__host__ __device__ __forceinline__ size_t tp_pos_bytes(int hcap) { return al128(sizeof(double4) * (size_t)(hcap + 1)); } // +1: dummy record
+__host__ __device__ __forceinline__ size_t tp_pos_bytes(int hcap) { return al128(sizeof(double4) * (size_t)(hcap + 4)); } // +4: dummy records (one per slot residue)
 __host__ __device__ __forceinline__ size_t tp_idx_bytes(int ocap, int G) { return al128(sizeof(uint2) * (size_t)ocap * G); }
 // 16-byte aligned windows of STATU / KVOIS (int32) and of the class counts (uint16) around the owned range
 __host__ __device__ __forceinline__ size_t tp_i32_bytes(int ocap) { return al128(sizeof(int) * (size_t)(ocap + 8)); }
 __host__ __device__ __forceinline__ size_t tp_u16_bytes(int ocap) { return al128(sizeof(unsigned short) * (size_t)(ocap + 16)); }
 __host__ __device__ __forceinline__ size_t tp_buf_bytes(int hcap, int ocap, int G, bool mt)
 {
-    return tp_pos_bytes(hcap) + tp_idx_bytes(ocap, G) + 2 * tp_i32_bytes(ocap) + tp_u16_bytes(ocap) + (mt ? al128((size_t)hcap + 1) : 0);
+    return tp_pos_bytes(hcap) + tp_idx_bytes(ocap, G) + 2 * tp_i32_bytes(ocap) + tp_u16_bytes(ocap) + (mt ? al128((size_t)hcap + 4) : 0);
 }
 __host__ __device__ __forceinline__ size_t tp_tab_bytes(int ktab) { return al128(sizeof(double2) * (size_t)(ktab + 2)); }
 
@@ -612,8 +675,10 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 mbar_init(&bar_ready[b], 32);
                 mbar_init(&bar_empty[b], NCW);
                 // the dummy record list tails point at: far from everything, finite
-                reinterpret_cast<double4 *>(buf0 + b * bufb)[P.hcap] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
-                if (MT) (buf0 + b * bufb + o_typ)[P.hcap] = 0;
+                for (int q = 0; q < 4; q++) { // hcap is a multiple of 4: dummy q has slot residue q (bank-aware list padding)
+                    reinterpret_cast<double4 *>(buf0 + b * bufb)[P.hcap + q] = make_double4(1.0e30, 1.0e30, 1.0e30, 0.0);
+                    if (MT) (buf0 + b * bufb + o_typ)[P.hcap + q] = 0;
+                }
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -1026,7 +1091,7 @@ int mdb_tiled_plan(mdb_ctx *c)
     for (int ntx = 1; ntx <= c->ncell[0] && !best_w; ntx++) {
         const int wt = (c->ncell[0] + ntx - 1) / ntx;
         if (wt > TILE_MAX_W) continue;
-        const int hcap = (int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64;
+        const int hcap = ((int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64 + 3) & ~3; // multiple of 4: see the dummy records of the passes
         const int ocap = (((int)(wt * rho_cell * 1.25) + 32) + 7) & ~7;
         if (hcap >= 16000) continue; // slots carry a 2-bit class tag while the list is built
         const size_t fixed = TP_HDR_BYTES + nbuf * tp_buf_bytes(hcap, ocap, G, mt);
@@ -1139,6 +1204,7 @@ static int launch_list(mdb_ctx *c)
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
     A.rc2[0] = S.rc2f[0]; A.rc2[1] = S.rc2f[1];
     A.lcap = S.lcap;
+    A.bank_order = S.bank_order ? 1 : 0;
     int tile_lo = 0, tile_hi = S.P.ntiles;
     if (c->dd_on) { // owned z-layers of cells: the descriptors are cheap and built for every tile
         const int tiles_per_layer = c->ncell[1] * S.ntx;

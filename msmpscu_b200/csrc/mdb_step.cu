@@ -461,7 +461,9 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h, b
     const bool fused_epilogue = c->opt_fuse_epilogue && c->tiled.active && c->has_tables && c->shape_identity;
     if ((rc = predict_launch(c, h, (first || fused_epilogue) ? 0 : 3)) < 0) return rc;
     if (nb_uptab > 0 && (itime - it0) % nb_uptab == 0) { // MOD(ITIME-IT0,NB_UPTAB)==0, GenericMD:599-601
-        if ((rc = mdb_list_rebuild(c)) < 0) return rc;
+        // the capacity counters are read back at once (a 48-byte copy and a synchronisation per list period): an overflow of
+        // the tiled path is redone on the generic path before any force is evaluated on the new list
+        if ((rc = mdb_list_rebuild_checked(c)) < 0) return rc;
     }
     if (fused_epilogue && c->list_valid && !c->list_reordered) {
         // EPC friction and the corrector are fused into the epilogue of the force pass
@@ -476,11 +478,14 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h, b
     return MDB_OK;
 }
 
-extern "C" int mdb_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab, double h)
+// nsteps x For_One_Step, enqueued on the context's stream.  The host only waits inside a list rebuild (capacity check);
+// the out-of-box count of the block is read by mdb_sync.
+extern "C" int mdb_run_async(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab, double h)
 {
     if (!c) return MDB_ERR_ARG;
     if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_run: a slab-decomposed step needs the ghost exchanges between its "
-                                                           "kernels; drive it with mdb_predict / mdb_force / mdb_correct (msmpscu_b200/domain.py)");
+                                                           "kernels; use mdb_dd_run (one process per GPU, NCCL) or drive it with "
+                                                           "mdb_predict / mdb_force / mdb_correct (msmpscu_b200/domain.py)");
     if (!c->has_box || !c->has_tables || !c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_run: box, tables and list must be set");
     CUDA_TRY(c, cudaSetDevice(c->dev));
     CUDA_TRY(c, cudaMemsetAsync(c->counters + CNT_OOB_TOTAL, 0, sizeof(int), c->stream));
@@ -489,14 +494,15 @@ extern "C" int mdb_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab
         if (rc < 0) return rc;
     }
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (c->tiled.active && c->h_counters[CNT_TILE_OVERFLOW] > 0) {
-        c->tiled.ok = false; // later rebuilds use the generic path
-        c->list_valid = false;
-        return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path: a tile exceeded its halo capacity during mdb_run; state is unreliable, "
-                                                 "re-upload and rerun (the generic path is now selected)");
-    }
-    return c->h_counters[CNT_OOB_TOTAL];
+    c->run_pending = true;
+    return MDB_OK;
+}
+
+extern "C" int mdb_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab, double h)
+{
+    int rc = mdb_run_async(c, itime0, nsteps, it0, nb_uptab, h);
+    if (rc < 0) return rc;
+    return mdb_sync(c);
 }
 
 extern "C" int mdb_step(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)

@@ -489,12 +489,16 @@ int orc_nlist_build_dev(int nbox, int napb, const double *xp, const int *ityp, i
     return numout;
 }
 
-int orc_nlist_build_cpu(int n, const double *xp, const int *ityp, const int *statu,
-                        const double boxlow[3], const double zl[3], const int ifpd[3],
-                        const double boxshape[9], int ng, const double *nb_rm, int mxkvois,
-                        int *kvois, int *indi)
+/* half = 0: Cal_NeighboreList2C (every directed pair), Common/MD_NeighborsList.F90:396-633
+ * half = 1: Cal_NeighboreListC (Newton's third law: neighbour cells 2..14 of the NIX/NIY/NIZ table and J = I+1..N inside
+ *           the gathered sub-box, so every pair is stored once), :152-391 */
+static int nlist_build_cpu(int half, int n, const double *xp, const int *ityp, const int *statu,
+                           const double boxlow[3], const double zl[3], const int ifpd[3],
+                           const double boxshape[9], int ng, const double *nb_rm, int mxkvois,
+                           int *kvois, int *indi)
 {
     /* Common/MD_NeighborsList.F90:432-633 */
+    const int kcell_hi = half ? 14 : 27;
     double rmmax = 0.0, rcut2[ORC_MXGROUP * ORC_MXGROUP];
     for (int i = 0; i < ng * ng; i++) {
         if (nb_rm[i] > rmmax) rmmax = nb_rm[i];
@@ -554,7 +558,7 @@ int orc_nlist_build_cpu(int n, const double *xp, const int *ityp, const int *sta
     } while (0)
             for (int id = head[ic0]; id > 0; id = link[id]) PUSH(id, 0.0, 0.0, 0.0);
             n0 = nloc;
-            for (int k = 1; k < 27; k++) { /* :555-588 */
+            for (int k = 1; k < kcell_hi; k++) { /* :555-588 (2C) / :317-349 (C: IC = 2,14) */
                 int j[3] = {ix + NIX[k], iy + NIY[k], iz + NIZ[k]};
                 double cx[3] = {0.0, 0.0, 0.0};
                 int out = 0;
@@ -572,7 +576,7 @@ int orc_nlist_build_cpu(int n, const double *xp, const int *ityp, const int *sta
 #undef PUSH
             for (int i = 0; i < n0; i++) { /* :594-621 */
                 int id = ident[i], itp = typ[i], nn = 0;
-                for (int jj = 0; jj < nloc; jj++) {
+                for (int jj = half ? i + 1 : 0; jj < nloc; jj++) { /* 2C: J = 1..N, J /= I (:597-598); C: J = I+1..N (:356) */
                     if (jj == i) continue;
                     double c1 = xpt[3 * i] - xpt[3 * jj], c2 = xpt[3 * i + 1] - xpt[3 * jj + 1],
                            c3 = xpt[3 * i + 2] - xpt[3 * jj + 2];
@@ -596,6 +600,21 @@ int orc_nlist_build_cpu(int n, const double *xp, const int *ityp, const int *sta
     free(head);
     free(link);
     return err;
+}
+
+int orc_nlist_build_cpu(int n, const double *xp, const int *ityp, const int *statu,
+                        const double boxlow[3], const double zl[3], const int ifpd[3],
+                        const double boxshape[9], int ng, const double *nb_rm, int mxkvois,
+                        int *kvois, int *indi)
+{
+    return nlist_build_cpu(0, n, xp, ityp, statu, boxlow, zl, ifpd, boxshape, ng, nb_rm, mxkvois, kvois, indi);
+}
+int orc_nlist_build_cpu_half(int n, const double *xp, const int *ityp, const int *statu,
+                             const double boxlow[3], const double zl[3], const int ifpd[3],
+                             const double boxshape[9], int ng, const double *nb_rm, int mxkvois,
+                             int *kvois, int *indi)
+{
+    return nlist_build_cpu(1, n, xp, ityp, statu, boxlow, zl, ifpd, boxshape, ng, nb_rm, mxkvois, kvois, indi);
 }
 
 /* =====================================================================================
@@ -1775,3 +1794,232 @@ out:
     free(fre); free(x); free(g); free(d); free(t); free(r); free(ws); free(wy); free(rho); free(alpha);
     return iflag;
 }
+
+
+/* =====================================================================================
+ * The reference's CPU path -- what bench.py times as the CPU baseline.
+ *   lists   Cal_NeighboreList2C (every directed pair)        Common/MD_NeighborsList.F90:396-633  orc_nlist_build_cpu
+ *           Cal_NeighboreListC  (Newton's third law)          :152-391                             orc_nlist_build_cpu_half
+ *   forces  CALFORCE_FS_Force_Table2 (preCALFOR2 / CALFOR2)   Common/MD_FS_ForceTable.F90:400-640  orc_force_pass1/2
+ *           CALFORCE_FS_Force_Table  (preCALFOR / CALFOR)     :150-395                             orc_force_newton3
+ *   step    Predictor / Correction (Swope form of velocity Verlet)  Common/MD_SwopeScheme.F90:22-283: the arithmetic of
+ *           the device scheme (h*v + h^2/2*F/m, wrap, half kicks), restated once as orc_predictor / orc_corrector
+ * The reference has no CPU EAM force (Common/MD_ForceClass_Register.F90:155-160 refuses EAM_TYPE on the CPU): as SURVEY.md
+ * 8(d) prescribes, the FS code path is generalised with the embedding lookup of the device kernels (the FS form -1/2/sqrt(rho)
+ * is kept for ORC_POT_FS).  The CPU path never sorts atoms: state stays in the ORIGINAL order.  The in-range test uses
+ * maxval(RU^2) as the device kernels do (the CPU twin tests m_RCUT2 per pair of types: identical for one atom type).
+ * ===================================================================================== */
+static double embed_df(const orc_tables *t, int ti, double rho)
+{
+    if (t->pot_type == ORC_POT_FS) return rho > 0.0 ? -0.5 / sqrt(rho) : 0.0;
+    if (!(rho > 0.0)) return 0.0;
+    int ktab = t->kembd[ti - 1];
+    double sk = rho / t->rhod + 1.0;
+    int kk = (int)(sk + 0.000001);
+    double a = tab(t->dfembd, t->nkind1, t->nembd, ktab, kk);
+    return a + (sk - (double)kk) * (tab(t->dfembd, t->nkind1, t->nembd, ktab, kk + 1) - a);
+}
+static double embed_f(const orc_tables *t, int ti, double rho)
+{
+    if (t->pot_type == ORC_POT_FS) return rho > 0.0 ? -sqrt(rho) : 0.0; /* EPOT = m_ER - DSQRT(m_DEN) :180 */
+    if (!(rho > 0.0)) return 0.0;
+    int ktab = t->kembd[ti - 1];
+    double sk = rho / t->rhod + 1.0;
+    int kk = (int)(sk + 0.000001);
+    double a = tab(t->fembd, t->nkind1, t->nembd, ktab, kk);
+    return a + (sk - (double)kk) * (tab(t->fembd, t->nkind1, t->nembd, ktab, kk + 1) - a);
+}
+
+/* preCALFOR + CALFOR on a HALF list (Common/MD_FS_ForceTable.F90:188-395): every stored pair adds to both atoms.
+ * Serial, as the reference runs it.  den: work array (rho, then dF/drho); er: pair energies; epot may be NULL.
+ * vtensor (9, column-major) gets sum over pairs of FORTOT*d_a*d_b (:384-388). */
+void orc_force_newton3(int n, const double *xp, const int *ityp, const int *kvois, const int *indi, int ldindi,
+                       const double zl[3], const int ifpd[3], const double bs[9], const orc_tables *t,
+                       double *den, double *er, double *fp, double *epot, double *vtensor)
+{
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; i++) { den[i] = 0.0; er[i] = 0.0; }
+    for (int i = 0; i < n; i++) { /* preCALFOR :219-266 */
+        int ti = ityp[i], iiw = kvois[i];
+        for (int iw = 0; iw < iiw; iw++) {
+            int j = indi[i + (size_t)iw * ldindi] - 1;
+            double s[3] = {xp[i] - xp[j], xp[i + n] - xp[j + n], xp[i + 2 * n] - xp[j + 2 * n]};
+            min_image(s, zl, ifpd);
+            double dx = bs[0] * s[0] + bs[3] * s[1] + bs[6] * s[2];
+            double dy = bs[1] * s[0] + bs[4] * s[1] + bs[7] * s[2];
+            double dz = bs[2] * s[0] + bs[5] * s[1] + bs[8] * s[2];
+            double r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 <= t->ru2max) {
+                int tj = ityp[j];
+                int k0 = t->kpair[(ti - 1) + t->ng * (tj - 1)], k1 = t->kpair[(tj - 1) + t->ng * (ti - 1)];
+                double r = sqrt(r2);
+                double sk = sqrt(r) * t->csi;
+                int kk = (int)sk;
+                double dk = sk - (double)kk;
+                double a = tab(t->potr, t->nkind, t->ntab, k0, kk);
+                double exp1 = (a + dk * (tab(t->potr, t->nkind, t->ntab, k0, kk + 1) - a)) / r; /* :256 */
+                er[i] = er[i] + exp1;
+                er[j] = er[j] + exp1;
+                double b = tab(t->potb, t->nkind, t->ntab, k0, kk), c = tab(t->potb, t->nkind, t->ntab, k1, kk);
+                den[i] = den[i] + (b + dk * (tab(t->potb, t->nkind, t->ntab, k0, kk + 1) - b)); /* :260 */
+                den[j] = den[j] + (c + dk * (tab(t->potb, t->nkind, t->ntab, k1, kk + 1) - c)); /* :261 */
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) { /* :269-271 */
+        if (epot) epot[i] = er[i] + embed_f(t, ityp[i], den[i]);
+        den[i] = embed_df(t, ityp[i], den[i]);
+    }
+    if (n > 0) memset(fp, 0, sizeof(double) * 3 * (size_t)n); /* FP = C_ZERO :303 */
+    for (int i = 0; i < n; i++) { /* CALFOR :305-391 */
+        int ti = ityp[i], iiw = kvois[i];
+        double denki = den[i];
+        for (int iw = 0; iw < iiw; iw++) {
+            int j = indi[i + (size_t)iw * ldindi] - 1;
+            double s[3] = {xp[i] - xp[j], xp[i + n] - xp[j + n], xp[i + 2 * n] - xp[j + 2 * n]};
+            min_image(s, zl, ifpd);
+            double dx = bs[0] * s[0] + bs[3] * s[1] + bs[6] * s[2];
+            double dy = bs[1] * s[0] + bs[4] * s[1] + bs[7] * s[2];
+            double dz = bs[2] * s[0] + bs[5] * s[1] + bs[8] * s[2];
+            double r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 <= t->ru2max) {
+                int tj = ityp[j];
+                int k0 = t->kpair[(ti - 1) + t->ng * (tj - 1)], k1 = t->kpair[(tj - 1) + t->ng * (ti - 1)];
+                double r = sqrt(r2);
+                double sk = sqrt(r) * t->csi;
+                int kk = (int)sk;
+                double dk = sk - (double)kk;
+                double a = tab(t->fpotr, t->nkind, t->ntab, k0, kk);
+                double b = tab(t->fpotb, t->nkind, t->ntab, k0, kk);
+                double c = tab(t->fpotb, t->nkind, t->ntab, k1, kk);
+                /* :364-367 */
+                double fortot = (a + dk * (tab(t->fpotr, t->nkind, t->ntab, k0, kk + 1) - a)) / r2 +
+                                ((c + dk * (tab(t->fpotb, t->nkind, t->ntab, k1, kk + 1) - c)) * den[j] +
+                                 (b + dk * (tab(t->fpotb, t->nkind, t->ntab, k0, kk + 1) - b)) * denki) / r;
+                for (int k = 0; k < 3; k++) { /* :369-373 */
+                    double f = fortot * s[k];
+                    fp[i + (size_t)k * n] = fp[i + (size_t)k * n] + f;
+                    fp[j + (size_t)k * n] = fp[j + (size_t)k * n] - f;
+                }
+                if (vtensor) {
+                    double d[3] = {dx, dy, dz};
+                    for (int k = 0; k < 3; k++)
+                        for (int k1_ = 0; k1_ < 3; k1_++) v[k + 3 * k1_] = v[k + 3 * k1_] + d[k1_] * d[k] * fortot;
+                }
+            }
+        }
+    }
+    if (vtensor) memcpy(vtensor, v, sizeof(v));
+}
+
+struct orc_cpu {
+    int n, ng, mxkvois, half, epc_on;
+    double boxlow[3], boxup[3], zl[3], bs[9], cm[ORC_MXGROUP], nb_rm[ORC_MXGROUP * ORC_MXGROUP];
+    int ifpd[3];
+    orc_tables t;
+    double *xp, *xp1, *fp, *dis, *den, *er, *epot, *ekin;
+    int *ityp, *statu, *kvois, *indi;
+    int epc_enable[ORC_MXGROUP];
+    double epc_te[ORC_MXGROUP], epc_alpha[ORC_MXGROUP], epc_cut[ORC_MXGROUP], epc_he[ORC_MXGROUP];
+};
+
+orc_cpu *orc_cpu_create(int n, const double *xp, const double *xp1, const int *ityp, const int *statu, int ng,
+                        const double *cm, const double boxlow[3], const double zl[3], const int ifpd[3],
+                        const double *nb_rm, int mxkvois, const orc_tables *t, int half)
+{
+    orc_cpu *m = (orc_cpu *)calloc(1, sizeof(orc_cpu));
+    size_t n3 = (size_t)n * 3;
+    m->n = n; m->ng = ng; m->mxkvois = mxkvois; m->half = half;
+    for (int d = 0; d < 3; d++) {
+        m->boxlow[d] = boxlow[d]; m->zl[d] = zl[d]; m->boxup[d] = boxlow[d] + zl[d]; m->ifpd[d] = ifpd[d];
+    }
+    m->bs[0] = m->bs[4] = m->bs[8] = 1.0;
+    memcpy(m->cm, cm, sizeof(double) * ng);
+    memcpy(m->nb_rm, nb_rm, sizeof(double) * ng * ng);
+    m->t = *t;
+    m->xp = (double *)malloc(sizeof(double) * n3); m->xp1 = (double *)malloc(sizeof(double) * n3);
+    m->fp = (double *)calloc(n3, sizeof(double)); m->dis = (double *)calloc(n3, sizeof(double));
+    m->den = (double *)calloc(n, sizeof(double)); m->er = (double *)calloc(n, sizeof(double));
+    m->epot = (double *)calloc(n, sizeof(double)); m->ekin = (double *)calloc(n, sizeof(double));
+    m->ityp = (int *)malloc(sizeof(int) * n); m->statu = (int *)malloc(sizeof(int) * n);
+    m->kvois = (int *)calloc(n, sizeof(int)); m->indi = (int *)malloc(sizeof(int) * (size_t)n * mxkvois);
+    memcpy(m->xp, xp, sizeof(double) * n3); memcpy(m->xp1, xp1, sizeof(double) * n3);
+    memcpy(m->ityp, ityp, sizeof(int) * n); memcpy(m->statu, statu, sizeof(int) * n);
+    return m;
+}
+void orc_cpu_destroy(orc_cpu *m)
+{
+    if (!m) return;
+    free(m->xp); free(m->xp1); free(m->fp); free(m->dis); free(m->den); free(m->er); free(m->epot); free(m->ekin);
+    free(m->ityp); free(m->statu); free(m->kvois); free(m->indi);
+    free(m);
+}
+void orc_cpu_set_epc(orc_cpu *m, const int *enable, const double *te, const double *alpha, const double *cut, const double *he)
+{
+    m->epc_on = 0;
+    for (int g = 0; g < m->ng; g++) {
+        m->epc_enable[g] = enable[g]; m->epc_te[g] = te[g]; m->epc_alpha[g] = alpha[g]; m->epc_cut[g] = cut[g];
+        m->epc_he[g] = he[g];
+        if (enable[g] > 0) m->epc_on = 1;
+    }
+}
+int orc_cpu_rebuild(orc_cpu *m)
+{
+    return nlist_build_cpu(m->half, m->n, m->xp, m->ityp, m->statu, m->boxlow, m->zl, m->ifpd, m->bs, m->ng, m->nb_rm,
+                           m->mxkvois, m->kvois, m->indi);
+}
+void orc_cpu_force(orc_cpu *m, int with_epot)
+{
+    int n = m->n;
+    if (m->half) {
+        orc_force_newton3(n, m->xp, m->ityp, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->den, m->er, m->fp,
+                          with_epot ? m->epot : NULL, NULL);
+        return;
+    }
+    orc_force_pass1(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->den);
+    orc_force_pass2(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->den, m->fp, n, NULL);
+    if (with_epot)
+        orc_force_epot(n, 0, n, m->xp, m->ityp, m->statu, m->kvois, m->indi, n, m->zl, m->ifpd, m->bs, &m->t, m->epot);
+}
+/* nsteps x For_One_Step on the CPU path; the loop is here, not in the caller.  Returns the number of rebuilds, <0 on a
+ * list error (more than mxKVOIS neighbours / atom outside the cells: the reference stops). */
+int orc_cpu_run(orc_cpu *m, int itime0, int nsteps, int it0, int nb_uptab, double h)
+{
+    int n = m->n, nreb = 0;
+    for (int s = 0; s < nsteps; s++) {
+        int itime = itime0 + s;
+        orc_predictor(n, m->xp, m->xp1, m->fp, m->dis, m->statu, m->ityp, m->cm, h, m->boxlow, m->boxup, m->zl, m->ifpd);
+        if (nb_uptab > 0 && (itime - it0) % nb_uptab == 0) {
+            int rc = orc_cpu_rebuild(m);
+            if (rc < 0) return rc;
+            nreb++;
+        }
+        orc_cpu_force(m, 0);
+        if (m->epc_on)
+            orc_epc(n, m->xp1, m->fp, m->statu, m->ityp, m->ng, m->epc_enable, m->cm, m->epc_te, m->epc_alpha, m->epc_cut,
+                    m->epc_he);
+        orc_corrector(n, m->xp1, m->fp, m->statu, m->ityp, m->cm, h);
+    }
+    return nreb;
+}
+/* HARMIL = (sum EPOT + sum EKIN) / N over active atoms, Common/MD_TypeDef_SimBox.F90:5155-5163 (energies recomputed here) */
+double orc_cpu_harmil(orc_cpu *m)
+{
+    int n = m->n;
+    orc_cpu_force(m, 1);
+    orc_ekin(n, m->xp1, m->statu, m->ityp, m->cm, m->ekin);
+    double se = 0.0, sk = 0.0;
+    int na = 0;
+    for (int i = 0; i < n; i++)
+        if ((m->statu[i] & ORC_STATU_ACTIVE) == ORC_STATU_ACTIVE) { se += m->epot[i]; if (m->ekin[i] >= 0.0) sk += m->ekin[i]; na++; }
+    return na ? (se + sk) / (double)na : 0.0;
+}
+void orc_cpu_get(orc_cpu *m, double *xp, double *xp1, double *fp, double *epot)
+{
+    size_t n3 = (size_t)m->n * 3;
+    if (xp) memcpy(xp, m->xp, sizeof(double) * n3);
+    if (xp1) memcpy(xp1, m->xp1, sizeof(double) * n3);
+    if (fp) memcpy(fp, m->fp, sizeof(double) * n3);
+    if (epot) memcpy(epot, m->epot, sizeof(double) * m->n);
+}
+const int *orc_cpu_kvois(orc_cpu *m) { return m->kvois; }

@@ -194,6 +194,28 @@ const int *orc_md_kvois(orc_md *m);
 const int *orc_md_indi(orc_md *m);
 void  orc_md_ncell(orc_md *m, int ncell[3]);
 
+
+/* ---- the reference's CPU path (see the definitions): CPU lists, Newton-3 force, step loop in C */
+int   orc_nlist_build_cpu_half(int n, const double *xp, const int *ityp, const int *statu,
+                               const double boxlow[3], const double zl[3], const int ifpd[3],
+                               const double boxshape[9], int ng, const double *nb_rm, int mxkvois,
+                               int *kvois, int *indi);
+void  orc_force_newton3(int n, const double *xp, const int *ityp, const int *kvois, const int *indi, int ldindi,
+                        const double zl[3], const int ifpd[3], const double bs[9], const orc_tables *t,
+                        double *den, double *er, double *fp, double *epot, double *vtensor);
+typedef struct orc_cpu orc_cpu;
+orc_cpu *orc_cpu_create(int n, const double *xp, const double *xp1, const int *ityp, const int *statu, int ng,
+                        const double *cm, const double boxlow[3], const double zl[3], const int ifpd[3],
+                        const double *nb_rm, int mxkvois, const orc_tables *t, int half);
+void  orc_cpu_destroy(orc_cpu *m);
+void  orc_cpu_set_epc(orc_cpu *m, const int *enable, const double *te, const double *alpha, const double *cut, const double *he);
+int   orc_cpu_rebuild(orc_cpu *m);
+void  orc_cpu_force(orc_cpu *m, int with_epot);
+int   orc_cpu_run(orc_cpu *m, int itime0, int nsteps, int it0, int nb_uptab, double h);
+double orc_cpu_harmil(orc_cpu *m);
+void  orc_cpu_get(orc_cpu *m, double *xp, double *xp1, double *fp, double *epot);
+const int *orc_cpu_kvois(orc_cpu *m);
+
 #ifdef __cplusplus
 }
 #endif

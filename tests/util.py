@@ -153,6 +153,25 @@ def oracle_md(O, c):
                 np.ascontiguousarray(c.nb_rm.T).ravel(), c.mxkvois, oracle_tables(O, c))
 
 
+def oracle_cpu_md(O, c, half=False, fast=False):
+    """the reference's CPU path (original order, CPU list rule) on a case"""
+    return O.CpuMD(c.xp, c.xp1, c.ityp, c.statu, c.mass, c.boxlow, c.zl, c.ifpd, np.ascontiguousarray(c.nb_rm.T).ravel(),
+                   c.mxkvois, oracle_tables(O, c), half=half, fast=fast)
+
+
+def atom_relerr(a, b, floor_frac=1e-3):
+    """PER-ATOM relative error max_i |a_i - b_i| / max(|b_i|, floor), floor = floor_frac x the largest |b_i|.
+    a, b: (N,) or (N,3) (vector norm per atom).  Stricter than relerr(): an atom with a small force / energy is
+    measured against its own magnitude (down to the floor), not against the largest one in the box."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.ndim == 1:
+        d, m = np.abs(a - b), np.abs(b)
+    else:
+        d, m = np.linalg.norm(a - b, axis=1), np.linalg.norm(b, axis=1)
+    floor = floor_frac * max(float(np.max(m)), 1e-300)
+    return float(np.max(d / np.maximum(m, floor)))
+
+
 def relerr(a, b):
     """max |a-b| / max |b| : the parity metric for per-atom vectors"""
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
