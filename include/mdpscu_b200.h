@@ -127,6 +127,11 @@ int mdb_tables_set(mdb_ctx *ctx, int pot_type, int nkind, int ntab, double csi,
                    int nkind1, int nembd, double rhod, const double *fembd, const double *dfembd,
                    const int *kpair, const int *kembd, double ru2max);
 int mdb_tables_clear(mdb_ctx *ctx); /* pClrForcetable -> Clear_EAM_Force_Table_DEV :343 */
+/* Density-pass evaluations since the last call whose rho exceeded the embedding table (RHOMX = max(POTB)*RHOSCAL,
+ * Common/MD_TypeDef_ForceTable.F90:1043-1048).  The reference reads past DFEMBD there (:535-541 has no bound test); this
+ * library clamps to the zero pad (dF/drho = 0 for that atom) and counts the event, e.g. for close collisions in cascades:
+ * raise RHOSCAL when it is not 0. */
+int mdb_embed_overruns(mdb_ctx *ctx);
 
 /* ------------------------------------------------------------------------------------
  * neighbour list: Initialize_NeighboreList_DEV / Cal_NeighBoreList_DEV / Copyout_NeighboreList_DEV /

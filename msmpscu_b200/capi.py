@@ -61,6 +61,7 @@ SYMBOLS = {
     "mdb_epc_apply": (C.c_int, [C.c_void_p]),
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_embed_overruns": (C.c_int, [C.c_void_p]),
     "mdb_run_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_state_download_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "mdb_global_t": (C.c_int, [C.c_void_p, c_dp]),
@@ -301,6 +302,10 @@ class Context:
 
     def run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    def embed_overruns(self):
+        """rho > RHOMX events of the density pass since the last call"""
+        return self._chk(self.lib.mdb_embed_overruns(self.h))
 
     def run_async(self, itime0, nsteps, it0, nb_uptab, h):
         """enqueue nsteps steps; sync() returns the block's out-of-box count"""

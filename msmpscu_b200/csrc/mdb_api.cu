@@ -848,6 +848,18 @@ extern "C" int mdb_dd_info(const mdb_ctx *c, int out[16])
     return MDB_OK;
 }
 
+// rho > RHOMX events since the last call (the embedding table ends at RHOMX = max(POTB)*RHOSCAL; the reference reads past
+// DFEMBD there, here the row is clamped to the zero pad, i.e. dF/drho = 0 for that atom)
+extern "C" int mdb_embed_overruns(mdb_ctx *c)
+{
+    if (!c || !c->counters) return MDB_ERR_STATE;
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + CNT_RHO_OVER, c->counters + CNT_RHO_OVER, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->counters + CNT_RHO_OVER, 0, sizeof(int), c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return c->h_counters[CNT_RHO_OVER];
+}
+
 extern "C" int mdb_nlist_overflow(mdb_ctx *c)
 {
     if (!c || !c->has_nlist) return MDB_ERR_STATE;

@@ -21,6 +21,7 @@ struct ForceParams {
     double csi, rhod, ru2max;
     const double2 *potr, *fpotr, *potb, *fpotb, *fembd, *dfembd;
     const int *skip; // device flag: the kernel returns at once when it is set (converged quench iterations)
+    int *counters;
     int kpair[MDB_MXGROUP * MDB_MXGROUP];
     int kembd[MDB_MXGROUP];
 };
@@ -46,10 +47,14 @@ __device__ __forceinline__ double lerp_tab(const double2 *__restrict__ t, int st
     return e.x + dk * e.y; // T(KK) + DK*(T(KK+1)-T(KK))
 }
 
-__device__ __forceinline__ double embed_lookup(const double2 *__restrict__ t, int stride, int k, double rho, double rhod)
+// rho beyond the table (KK > NEMBD: close collisions) reads past the arrays in the reference; here the row is clamped to the
+// zero pad and the event is counted (mdb_embed_overruns) so that the caller can see it
+__device__ __forceinline__ double embed_lookup(const double2 *__restrict__ t, int stride, int k, double rho, double rhod,
+                                               int *__restrict__ counters)
 {
     const double sk = rho / rhod + 1.0;  // :538
     const int kk = (int)(sk + 0.000001); // :539
+    if (kk > stride - 2 && counters) atomicAdd(&counters[CNT_RHO_OVER], 1);
     return lerp_tab(t, stride, k, kk, sk - (double)kk);
 }
 
@@ -84,7 +89,7 @@ k_pass1_generic(ForceParams P, double4 *__restrict__ pos, const int *__restrict_
         if (P.pot_type == MDB_POT_FS) {
             if (den0 > 0.0) den0 = -0.5 / sqrt(den0); // MD_FS_ForceTable_GPU.F90:497-507
         } else if (den0 > 0.0) {                      // :535-541
-            den0 = embed_lookup(P.dfembd, P.nembd + 2, P.kembd[ti], den0, P.rhod);
+            den0 = embed_lookup(P.dfembd, P.nembd + 2, P.kembd[ti], den0, P.rhod, P.counters);
         }
     }
     reinterpret_cast<double *>(pos + i)[3] = den0; // DEN(IC+IA0) = DEN0 :544
@@ -217,7 +222,7 @@ k_epot_generic(ForceParams P, const double4 *__restrict__ pos, const int *__rest
             }
         }
         if (P.pot_type == MDB_POT_FS) den0 = -sqrt(den0); // MD_FS_ForceTable_GPU.F90:1606
-        else den0 = embed_lookup(P.fembd, P.nembd + 2, P.kembd[ti], den0, P.rhod); // :1628-1631 (no rho>0 guard)
+        else den0 = embed_lookup(P.fembd, P.nembd + 2, P.kembd[ti], den0, P.rhod, nullptr); // :1628-1631 (no rho>0 guard)
     }
     epot[i] = er0 + den0; // :1633
 }
@@ -303,6 +308,7 @@ static void fill_params(mdb_ctx *c, ForceParams &P)
     P.pot_type = t.pot_type; P.ng = c->ng; P.ntab = t.ntab; P.nembd = t.nembd;
     P.csi = t.csi; P.rhod = t.rhod; P.ru2max = t.ru2max;
     P.skip = c->skip_flag;
+    P.counters = c->counters;
     P.potr = t.potr; P.fpotr = t.fpotr; P.potb = t.potb; P.fpotb = t.fpotb; P.fembd = t.fembd; P.dfembd = t.dfembd;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) P.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) P.kembd[i] = t.kembd[i];

@@ -960,6 +960,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
                         } else if (den0 > 0.0) {
                             const double sk = den0 / A.rhod + 1.0;
                             const int kk = (int)(sk + 0.000001);
+                            if (kk > A.nembd) atomicAdd(&A.counters[CNT_RHO_OVER], 1); // rho beyond RHOMX (mdb_embed_overruns)
                             den0 = lerp_g(A.g_dfembd, A.nembd + 2, A.kembd[ti], kk, sk - (double)kk);
                         }
                         reinterpret_cast<double *>(A.pos + ia)[3] = den0;

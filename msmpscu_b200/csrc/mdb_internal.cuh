@@ -26,7 +26,9 @@
 // the first CNT_PERBUILD_N are reset at every rebuild
 enum { CNT_OOB = 0, CNT_OVERFLOW, CNT_NNMAX, CNT_MXNAC, CNT_INCELL, CNT_TILE_OVERFLOW,
        CNT_D2MAX,       // float bits: max |displacement since the rebuild|^2 over all atoms (predictor)
-       CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N, CNT_SCRATCH, CNT__N = 12 };
+       CNT_PERBUILD_N, CNT_OOB_TOTAL = CNT_PERBUILD_N, CNT_SCRATCH,
+       CNT_RHO_OVER,    // density-pass evaluations whose rho lay beyond the embedding table (RHOMX): sticky, read by mdb_embed_overruns
+       CNT__N = 12 };
 
 struct BoxParams { // passed by value to kernels
     double lo[3], up[3], size[3], half[3];

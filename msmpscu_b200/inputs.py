@@ -98,16 +98,24 @@ def read_box_file(path):
     return box
 
 
-def read_ctrl_file(path, box):
-    """First time section of a &CTLF:GMD file -> SimMDCtrl (CGS)."""
+def read_ctrl_file(path, box, section=1):
+    """The common blocks plus ONE time section (&SECTSUBCTL #section, 1-based; default the first) of a &CTLF:GMD file
+    -> SimMDCtrl (CGS).  The reference keeps one SimMDCtrl per section in a linked list (sectCtrlParam); later sections
+    never overwrite the values of the one asked for.  read_ctrl_sections returns them all."""
     c = SimMDCtrl()
     ng = box.NGROUP
     ru_lu = np.full((ng, ng), 0.0)
     nb_fac = 1.2
     temp = 0.0
     epc = False
+    sect = 0
     for s in _lines(path):
         k = _kw(s)
+        if k == "SECTSUBCTL":
+            sect += 1
+            continue
+        if sect not in (0, section):
+            continue
         if k == "BOXS":
             c.MULTIBOX = int(_numbers(s[5:])[0])
         elif k == "CUTOFF" and "NEIGH" not in s.upper() and not np.any(ru_lu):
@@ -168,13 +176,21 @@ def read_ctrl_file(path, box):
             c.LBFGS_Factr = (_numbers(s[6:]) or [10.0])[0]
         elif k == "MSAVE":                                      # :1775
             c.LBFGS_MSave = int((_numbers(s[6:]) or [7])[0])
-        elif k == "DRTOL":                                      # :2000
-            c.STRCUT_DRTol = (_numbers(s[6:]) or [0.0])[0]
+        elif k == "DRTOL":                                      # :2000 (a bare &DRTOL keeps the default)
+            v = _numbers(s[6:])
+            if v:
+                c.STRCUT_DRTol = v[0]
     c.RU = ru_lu * box.RR
     c.NB_RM = nb_fac * c.RU
     c.LT_CTRL = [TiCtrlParam(TI=temp, METH_EPC=1 if epc else 0) for _ in range(ng)]
     c.TEMP = temp
     return c
+
+
+def read_ctrl_sections(path, box):
+    """one SimMDCtrl per &SECTSUBCTL of the file, in file order"""
+    nsect = sum(1 for s in _lines(path) if _kw(s) == "SECTSUBCTL")
+    return [read_ctrl_file(path, box, section=k) for k in range(1, max(nsect, 1) + 1)]
 
 
 def read_config(path, box):

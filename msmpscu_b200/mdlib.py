@@ -95,7 +95,7 @@ class SimMDCtrl:
     LT_CTRL: list = field(default_factory=list)
     # quench / event detection (Common/MD_TypeDef_SimCtrlParam.F90:205-217; parsed at :1694-2060)
     SEED: list = field(default_factory=lambda: [43434])
-    Quench_Steps: int = 0
+    Quench_Steps: int = 1000             # MD_TypeDef_SimCtrlParam.F90:204,997
     Quench_Meth: str = "ST"              # "LBFGS" | "CG" | "ST" | "DYN"  (the low word of CtrlParam%Quench_Meth)
     Quench_LSearch: bool = False         # CP_DAMPSCHEME_LSEARCH ("CG-LS", "ST-LS")
     STEEPEST_Alpha: float = 0.1
@@ -105,7 +105,7 @@ class SimMDCtrl:
     LBFGS_PGtol: float = 0.0
     LBFGS_Factr: float = 0.0
     LBFGS_MSave: int = 7
-    STRCUT_DRTol: float = 0.0            # &DRTOL: displacement that counts as an event (LU)
+    STRCUT_DRTol: float = 0.03           # &DRTOL: displacement that counts as an event (LU); default :202,996
     DAMPTIME0: int = 0
     DAMPTIME1: int = 0
 

@@ -107,14 +107,18 @@ def test_bench_reference_arm_and_no_gpu_behaviour():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          "--cpu-cells", "8"], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--cells", "8"], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, BENCH_CPU_QUICK="1"))
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
                 "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    # the line says what was really run: atoms of the timed box, threads, MD steps per reference step
+    assert line["config"]["atoms_total"] == 2 * 8 ** 3 and "%d atoms" % (2 * 8 ** 3) in line["config"]["workload"]
+    assert line["cpu_baseline"]["cores"] == os.cpu_count() and line["config"]["md_steps_per_step"] == 10
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     import torch
     if not torch.cuda.is_available():
@@ -260,3 +264,23 @@ def test_event_detection_compare():
     assert flag[0] == 0 and flag[n + 7] == 1 and flag[n + 9] == 0 and flag[2 * n + 4] == 1 and flag.sum() == 2
     assert mdlib.Transition_Replicas(flag, n) == (3, 2)
     assert mdlib.Transition_Replicas(mdlib.Do_Compare(ini, reps[:1], ctl), n) == (0, 0)
+
+
+def test_ctrl_defaults_and_sections_follow_the_reference():
+    """MD_TypeDef_SimCtrlParam.F90:202-204,996-997: STRCUT_DRTol = 0.03 LU, Quench_Steps = 1000 when the file is silent;
+    a control file with several &SECTSUBCTL blocks yields one SimMDCtrl per section (sectCtrlParam list)"""
+    from msmpscu_b200 import inputs, mdlib
+    d = mdlib.SimMDCtrl()
+    assert d.STRCUT_DRTol == 0.03 and d.Quench_Steps == 1000
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    box = inputs.read_box_file(os.path.join(g, "gmd_W_8192_EAM_box.dat")) if os.path.exists(os.path.join(g, "gmd_W_8192_EAM_box.dat")) else None
+    if box is None:
+        import glob
+        box = inputs.read_box_file(sorted(glob.glob(os.path.join(g, "gmd_*box*.dat")))[0])
+    secs = inputs.read_ctrl_sections(os.path.join(g, "gmd_CtrlFile300K.dat"), box)
+    assert len(secs) == 3
+    assert secs[0].TEMP == 0.0 and secs[0].Quench_Steps == 1000 and secs[0].Quench_Meth == "ST"
+    assert secs[1].TEMP == 300.0
+    one = inputs.read_ctrl_file(os.path.join(g, "gmd_CtrlFile300K.dat"), box)
+    assert one.TEMP == secs[0].TEMP and one.NB_MXNBS == 256 and one.NB_UPTAB == 10
+    assert one.STRCUT_DRTol == 0.03          # the file has no &DRTOL
