@@ -208,6 +208,27 @@ int mdb_run_async(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, d
  * ---------------------------------------------------------------------------------- */
 int mdb_dd_set(mdb_ctx *ctx, int rank, int nranks);
 int mdb_dd_info(const mdb_ctx *ctx, int info[16]);
+/* The decomposed run driven from inside the library (mdb_dd.cu): one process per GPU, exchanges as ncclSend / ncclRecv
+ * enqueued on the context's stream.  Replaces Synchroniz_XP_on_Devices (MD_Globle_Variables_GPU.F90:2026-2040) and
+ * Synchroniz_DEN_on_Devices (MD_EAM_ForceTable_GPU.F90:617-642), and the all-atoms host sort of every device
+ * (MD_NeighborsList_GPU.F90:1421-1695): a rank re-sorts only its slab.
+ *   mdb_dd_nccl_id    rank 0 obtains the 128-byte NCCL unique id; the caller distributes it (MPI, torch.distributed, a file ...)
+ *   mdb_dd_nccl_init  after mdb_dd_set: creates the communicator of the nranks processes
+ *   mdb_dd_local_attach  backend for single-GPU tests: the contexts of ALL ranks in one process on one device; a call of
+ *                     the entry points below on any of them then drives every rank in lock step
+ *   mdb_dd_build      collective.  First call: every rank holds the whole initial state (uploaded as usual), sorts it and
+ *                     builds the lists of its own tiles.  Later calls: the local rebuild.
+ *   mdb_dd_force      collective pCalForce / pCalPTensor (flags as mdb_force; the virial is summed over the ranks)
+ *   mdb_dd_run        collective nsteps x For_One_Step (rebuild cadence as mdb_run)
+ *   mdb_dd_global_t   Cal_GlobalT_DEV over the owned atoms of all ranks
+ * State is read back per rank with mdb_state_download(..., MDB_ORDER_CELL): the slice [info[0], info[1]) is this rank's. */
+int mdb_dd_nccl_id(void *id128);
+int mdb_dd_nccl_init(mdb_ctx *ctx, const void *id128);
+int mdb_dd_local_attach(mdb_ctx **ctxs, int nranks);
+int mdb_dd_build(mdb_ctx *ctx);
+int mdb_dd_force(mdb_ctx *ctx, unsigned flags, double vtensor[9]);
+int mdb_dd_run(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double h);
+int mdb_dd_global_t(mdb_ctx *ctx, double *curt);
 
 /* ------------------------------------------------------------------------------------
  * The other integrator-module procedures the step loops call (CommonGPU/MD_DiffScheme_GPU.F90):
@@ -318,7 +339,8 @@ int mdb_get_option(const mdb_ctx *ctx, int option);
 #define MDB_K_PREDICT  5
 #define MDB_K_CORRECT  6
 #define MDB_K_OTHER    7
-#define MDB_K__COUNT   8
+#define MDB_K_EXCHANGE 8  /* ghost-layer exchanges of a slab-decomposed run (time between enqueue and completion on the stream) */
+#define MDB_K__COUNT   9
 int mdb_prof_enable(mdb_ctx *ctx, int on);
 int mdb_prof_reset(mdb_ctx *ctx);
 /* launches[k] = kernel launches recorded for class k, ms[k] = summed device time */

@@ -22,8 +22,8 @@ ORDER_ORIGINAL, ORDER_CELL = 0, 1
 POT_EAM, POT_FS = 0, 1
 FORCE, VIRIAL, EPOT, DEN, NOPASS1 = 1, 2, 4, 8, 16
 F_POS4, F_D2MAX = 17, 18
-K_NAMES = ("cellsort", "nlist", "pass1", "pass2", "epot", "predict", "correct", "other")
-K_COUNT = 8
+K_NAMES = ("cellsort", "nlist", "pass1", "pass2", "epot", "predict", "correct", "other", "exchange")
+K_COUNT = 9
 LIB_MARINICA_EAM2, LIB_BONNY_EAM1, LIB_ACKLAND_FS_W = 1, 2, 3
 
 c_dp = C.POINTER(C.c_double)
@@ -62,6 +62,13 @@ SYMBOLS = {
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_embed_overruns": (C.c_int, [C.c_void_p]),
+    "mdb_dd_nccl_id": (C.c_int, [C.c_void_p]),
+    "mdb_dd_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mdb_dd_local_attach": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "mdb_dd_build": (C.c_int, [C.c_void_p]),
+    "mdb_dd_force": (C.c_int, [C.c_void_p, C.c_uint, c_dp]),
+    "mdb_dd_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "mdb_dd_global_t": (C.c_int, [C.c_void_p, c_dp]),
     "mdb_run_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_state_download_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "mdb_global_t": (C.c_int, [C.c_void_p, c_dp]),
@@ -150,6 +157,23 @@ def f64(a):
 
 def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def dd_nccl_id():
+    """rank 0: the 128-byte NCCL unique id to hand to every rank's Context.dd_nccl_init"""
+    buf = C.create_string_buffer(128)
+    rc = load().mdb_dd_nccl_id(buf)
+    if rc < 0:
+        raise MDBError(rc, "mdb_dd_nccl_id failed (libnccl.so.2 not found?)")
+    return buf.raw
+
+
+def dd_local_attach(ctxs):
+    """in-process backend of the decomposed run: all ranks' contexts in this process on one device (single-GPU tests)"""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = load().mdb_dd_local_attach(arr, len(ctxs))
+    if rc < 0:
+        raise MDBError(rc, ctxs[0].lib.mdb_last_error(ctxs[0].h).decode())
 
 
 def colmajor(a):
@@ -377,6 +401,27 @@ class Context:
         keys = ("a0", "a1", "gb0", "gb1", "ga0", "ga1", "sb0", "sb1", "st0", "st1", "below", "above", "cell_lo", "cell_hi",
                 "tile_lo", "tile_hi")
         return dict(zip(keys, list(out)))
+
+    # ---- slab decomposition driven from the library (mdb_dd.cu)
+    def dd_nccl_init(self, id128: bytes):
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._chk(self.lib.mdb_dd_nccl_init(self.h, buf))
+
+    def dd_build(self):
+        return self._chk(self.lib.mdb_dd_build(self.h))
+
+    def dd_force(self, flags=FORCE):
+        vt = np.zeros(9)
+        self._chk(self.lib.mdb_dd_force(self.h, flags, dp(vt)))
+        return vt.reshape(3, 3).T if (flags & VIRIAL) else None
+
+    def dd_run(self, itime0, nsteps, it0, nb_uptab, h):
+        return self._chk(self.lib.mdb_dd_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    def dd_global_t(self):
+        t = C.c_double(0.0)
+        self._chk(self.lib.mdb_dd_global_t(self.h, C.byref(t)))
+        return t.value
 
     def sync(self):
         return self._chk(self.lib.mdb_sync(self.h))

@@ -145,6 +145,7 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->dev);
     cudaStreamSynchronize(c->stream);
+    mdb_dd_free(c);
     mdb_prof_collect(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     free_state(c); free_nlist(c); free_tables(c);
@@ -837,6 +838,7 @@ extern "C" int mdb_dd_set(mdb_ctx *c, int rank, int nranks)
     if (nranks > 1 && c->nbox != 1) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_dd_set: slab decomposition is for a single box");
     c->dd_on = nranks > 1;
     c->dd_rank = rank; c->dd_n = nranks;
+    c->dd_built = false;
     c->list_valid = false;
     return MDB_OK;
 }

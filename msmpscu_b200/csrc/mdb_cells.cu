@@ -185,3 +185,199 @@ int mdb_cells_build(mdb_ctx *c)
     swp(c->ityp, c->ityp_alt); swp(c->statu, c->statu_alt); swp(c->ic, c->ic_alt); swp(c->gid, c->gid_alt);
     return MDB_OK;
 }
+
+// =====================================================================================
+// Slab-decomposed rebuild (mdb_dd.cu): a rank re-sorts only the atoms that end up in ITS z-layers of cells.
+// Candidates are the atoms of its old owned range and of its two old ghost layers (an atom moves far less than a cell
+// between two rebuilds); the result is written at the GLOBAL slots of the common cell-sorted order -- cells ascending,
+// atoms of a cell by descending original id -- so owned slices stay bit-identical to the single-GPU order.
+// =====================================================================================
+struct DDRanges { int r0[3], r1[3]; }; // old-slot ranges [r0, r1): ghost below, owned, ghost above
+
+__device__ __forceinline__ int dd_slot_of(const DDRanges &R, int t)
+{
+    int s = -1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int len = R.r1[k] - R.r0[k];
+        if (s < 0 && t < len) s = R.r0[k] + t;
+        t -= (s < 0) ? len : 0;
+    }
+    return s;
+}
+
+__global__ void k_dd_cell_assign(DDRanges R, int total, const double4 *__restrict__ pos, int *__restrict__ statu, BoxParams box,
+                                 int ncx, int ncy, int ncz, int zl0, int zl1, int *__restrict__ ic, int *__restrict__ nac,
+                                 int *__restrict__ naac, int *__restrict__ slot, int *__restrict__ counters)
+{
+    const double eps = (double)0.0001f;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int cell = 0, active = 0, s = -1;
+    if (t < total) {
+        s = dd_slot_of(R, t);
+        const int st = statu[s];
+        if ((st & ST_OUTOFBOX) != ST_OUTOFBOX) {
+            const double4 p = pos[s];
+            const int ix = cell_coord(p.x, box.lo[0], box.size[0], ncx, eps);
+            const int iy = cell_coord(p.y, box.lo[1], box.size[1], ncy, eps);
+            const int iz = cell_coord(p.z, box.lo[2], box.size[2], ncz, eps);
+            if (ix < 0 || ix >= ncx || iy < 0 || iy >= ncy || iz < 0 || iz >= ncz) cell = -2;
+            else if (iz >= zl0 && iz < zl1) cell = 1 + (ix + ncx * (iy + ncy * iz));
+        } else cell = -1;
+        if (cell < 0) { atomicAdd(&counters[CNT_OOB], 1); cell = 0; } // a decomposed box must be periodic / closed: reported as an error
+        ic[s] = cell;
+        active = (st & ST_ACTIVE) == ST_ACTIVE;
+    }
+    const int key = (cell > 0) ? cell : -(lane + 1);
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const unsigned act = __ballot_sync(0xffffffffu, active && cell > 0);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (cell > 0 && lane == leader) {
+        base = atomicAdd(&nac[cell - 1], __popc(grp));
+        const int na = __popc(grp & act);
+        if (na) atomicAdd(&naac[cell - 1], na);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (cell > 0) slot[s] = base + __popc(grp & ((1u << lane) - 1u));
+}
+
+// exclusive prefix over the cells [c0, c1): ia1th[c] = first + prefix + 1.  out (optional): {atoms in [c0,c1), atoms of the first
+// `cl` cells (bottom layer), atoms of the last `cl` cells (top layer), max count}
+__global__ void k_dd_scan(int c0, int c1, int cl, int first, const int *__restrict__ nac, int *__restrict__ ia1th, int *__restrict__ out)
+{
+    __shared__ int part[1024];
+    __shared__ int pmax[1024];
+    const int t = threadIdx.x, nt = blockDim.x, nc = c1 - c0;
+    const int chunk = (nc + nt - 1) / nt;
+    const int b = c0 + t * chunk, e = min(b + chunk, c1);
+    int sum = 0, mx = 0;
+    for (int i = b; i < e; i++) { const int v = nac[i]; sum += v; mx = max(mx, v); }
+    part[t] = sum; pmax[t] = mx;
+    __syncthreads();
+    for (int off = 1; off < nt; off <<= 1) {
+        const int v = (t >= off) ? part[t - off] : 0, m = (t >= off) ? pmax[t - off] : 0;
+        __syncthreads();
+        part[t] += v; pmax[t] = max(pmax[t], m);
+        __syncthreads();
+    }
+    int run = part[t] - sum;
+    for (int i = b; i < e; i++) { ia1th[i] = first + run + 1; run += nac[i]; }
+    __syncthreads();
+    if (out && t == nt - 1) { out[0] = part[t]; out[3] = pmax[t]; }
+    if (out && t == 0) { // layer sums from the finished prefixes (cells are x-fastest, z-slowest: a layer is `cl` consecutive cells)
+        const int lastc = c1 - 1;
+        const int total = ia1th[lastc] - 1 - first + nac[lastc];
+        out[1] = (nc > cl) ? ia1th[c0 + cl] - 1 - first : total;
+        out[2] = (nc > cl) ? total - (ia1th[c1 - cl] - 1 - first) : total;
+    }
+}
+
+__global__ void k_dd_add_base(int c0, int c1, int base, int *__restrict__ ia1th)
+{
+    const int i = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c1) ia1th[i] += base;
+}
+
+__global__ void k_dd_scatter(DDRanges R, int total, const int *__restrict__ ic, const int *__restrict__ slot,
+                             const int *__restrict__ ia1th, const int *__restrict__ gid, int *__restrict__ tmp_orig)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int s = dd_slot_of(R, t), cell = ic[s];
+    if (cell > 0) tmp_orig[ia1th[cell - 1] - 1 + slot[s]] = gid[s];
+}
+
+__global__ void k_dd_rank(DDRanges R, int total, const int *__restrict__ ic, const int *__restrict__ ia1th, const int *__restrict__ nac,
+                          const int *__restrict__ gid, const int *__restrict__ tmp_orig, int *__restrict__ gid_new, int *__restrict__ srcof)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int s = dd_slot_of(R, t), cell = ic[s];
+    if (cell <= 0) return;
+    const int base = ia1th[cell - 1] - 1, cnt = nac[cell - 1], me = gid[s];
+    int rank = 0;
+    for (int k = 0; k < cnt; k++) rank += (tmp_orig[base + k] > me);
+    gid_new[base + rank] = me;
+    srcof[base + rank] = s;
+}
+
+__global__ void k_dd_permute(int n, int a0, int a1, const int *__restrict__ srcof, const int *__restrict__ gid_new,
+                             const double4 *__restrict__ pos, double4 *__restrict__ pos_o,
+                             const double *__restrict__ xp1, double *__restrict__ xp1_o,
+                             const double *__restrict__ fp, double *__restrict__ fp_o,
+                             const double *__restrict__ dis, double *__restrict__ dis_o,
+                             const int *__restrict__ ityp, int *__restrict__ ityp_o,
+                             const int *__restrict__ statu, int *__restrict__ statu_o,
+                             const int *__restrict__ ic, int *__restrict__ ic_o, int *__restrict__ gidinv)
+{
+    const int d = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= a1) return;
+    const int s = srcof[d];
+    pos_o[d] = pos[s];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        xp1_o[d + (size_t)k * n] = xp1[s + (size_t)k * n];
+        fp_o[d + (size_t)k * n] = fp[s + (size_t)k * n];
+        dis_o[d + (size_t)k * n] = dis[s + (size_t)k * n];
+    }
+    ityp_o[d] = ityp[s];
+    statu_o[d] = statu[s];
+    ic_o[d] = ic[s];
+    gidinv[gid_new[d] - 1] = d + 1;
+}
+
+// phase 1: bin the candidates into this rank's cells and scan; d_out4 = {owned atoms, bottom layer, top layer, max per cell}
+int mdb_cells_dd_count(mdb_ctx *c, const int cand[6], int zl0, int zl1, int *d_out4)
+{
+    const int cl = c->ncell[0] * c->ncell[1], c0 = zl0 * cl, c1 = zl1 * cl;
+    cudaStream_t st = c->stream;
+    DDRanges R;
+    int total = 0;
+    for (int k = 0; k < 3; k++) { R.r0[k] = cand[2 * k]; R.r1[k] = cand[2 * k + 1]; total += R.r1[k] - R.r0[k]; }
+    ProfScope ps(c, MDB_K_CELLSORT, 2);
+    CUDA_TRY(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * CNT_PERBUILD_N, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->nac + c0, 0, sizeof(int) * (size_t)(c1 - c0), st));
+    CUDA_TRY(c, cudaMemsetAsync(c->naac + c0, 0, sizeof(int) * (size_t)(c1 - c0), st));
+    k_dd_cell_assign<<<cdiv(total, 256), 256, 0, st>>>(R, total, c->pos, c->statu, c->box, c->ncell[0], c->ncell[1], c->ncell[2], zl0, zl1,
+                                                       c->ic, c->nac, c->naac, c->slot, c->counters);
+    k_dd_scan<<<1, 1024, 0, st>>>(c0, c1, cl, 0, c->nac, c->ia1th, d_out4);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+// phase 2: with the global slot `base` of this rank's first atom known, place and permute the owned range [base, base + nown)
+int mdb_cells_dd_place(mdb_ctx *c, const int cand[6], int zl0, int zl1, int base, int nown)
+{
+    const int cl = c->ncell[0] * c->ncell[1], c0 = zl0 * cl, c1 = zl1 * cl, n = c->n;
+    cudaStream_t st = c->stream;
+    DDRanges R;
+    int total = 0;
+    for (int k = 0; k < 3; k++) { R.r0[k] = cand[2 * k]; R.r1[k] = cand[2 * k + 1]; total += R.r1[k] - R.r0[k]; }
+    ProfScope ps(c, MDB_K_CELLSORT, 4);
+    k_dd_add_base<<<cdiv(c1 - c0, 256), 256, 0, st>>>(c0, c1, base, c->ia1th);
+    k_dd_scatter<<<cdiv(total, 256), 256, 0, st>>>(R, total, c->ic, c->slot, c->ia1th, c->gid, c->tmp_orig);
+    k_dd_rank<<<cdiv(total, 256), 256, 0, st>>>(R, total, c->ic, c->ia1th, c->nac, c->gid, c->tmp_orig, c->gid_alt, c->srcof);
+    if (nown > 0)
+        k_dd_permute<<<cdiv(nown, 256), 256, 0, st>>>(n, base, base + nown, c->srcof, c->gid_alt, c->pos, c->pos_alt, c->xp1, c->xp1_alt,
+                                                      c->fp, c->fp_alt, c->dis, c->dis_alt, c->ityp, c->ityp_alt, c->statu, c->statu_alt,
+                                                      c->ic, c->ic_alt, c->gidinv);
+    CUDA_TRY(c, cudaGetLastError());
+    if (c->dsr && nown > 0) {
+        for (int k = 0; k < 3; k++) CUDA_TRY(c, cudaMemsetAsync(c->dsr + base + (size_t)k * n, 0, sizeof(float) * (size_t)nown, st));
+    }
+    swp(c->pos, c->pos_alt); swp(c->xp1, c->xp1_alt); swp(c->fp, c->fp_alt); swp(c->dis, c->dis_alt);
+    swp(c->ityp, c->ityp_alt); swp(c->statu, c->statu_alt); swp(c->ic, c->ic_alt); swp(c->gid, c->gid_alt);
+    return MDB_OK;
+}
+
+// IA1th of one ghost layer of cells [c0, c0 + cl) from the counts received from the neighbour; its first atom sits at `first`
+int mdb_cells_dd_ghost_layer(mdb_ctx *c, int c0, int first)
+{
+    const int cl = c->ncell[0] * c->ncell[1];
+    ProfScope ps(c, MDB_K_CELLSORT, 1);
+    k_dd_scan<<<1, 1024, 0, c->stream>>>(c0, c0 + cl, cl, first, c->nac, c->ia1th, nullptr);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}

@@ -137,10 +137,10 @@ struct TileListArgs {
 // tile descriptors: one small CTA per tile
 __global__ void __launch_bounds__(NL_THREADS)
 k_tile_desc(TileParams P, const int *__restrict__ nac, const int *__restrict__ ia1th, TileDesc *__restrict__ desc,
-            int *__restrict__ counters)
+            int *__restrict__ counters, int tile_lo)
 {
     __shared__ TileDesc H;
-    const int tile = blockIdx.x;
+    const int tile = tile_lo + blockIdx.x;
     const TileGeom g = tile_geom(P, tile);
     build_halo_table(P, g, nac, ia1th, H);
     const int *src = reinterpret_cast<const int *>(&H);
@@ -1216,11 +1216,15 @@ static int launch_list(mdb_ctx *c)
     auto kern = k_tile_nlist<G, MT>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
     ProfScope ps(c, MDB_K_NLIST, 2);
-    k_tile_desc<<<S.P.ntiles, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters);
-    if (tile_hi > tile_lo) kern<<<tile_hi - tile_lo, 64 * S.wmax, S.smem_list, c->stream>>>(S.P, A);
+    // descriptors: of this rank's tiles only in a decomposed run (cell counts of other slabs are not kept current there)
+    if (tile_hi > tile_lo) {
+        k_tile_desc<<<tile_hi - tile_lo, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters, tile_lo);
+        kern<<<tile_hi - tile_lo, 64 * S.wmax, S.smem_list, c->stream>>>(S.P, A);
+    }
     CUDA_TRY(c, cudaGetLastError());
     // the reference-format KVOIS/INDI pair is rebuilt on demand from the positions of this moment
-    CUDA_TRY(c, cudaMemcpyAsync(c->pos_snap, c->pos, sizeof(double4) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    if (!c->dd_built)
+        CUDA_TRY(c, cudaMemcpyAsync(c->pos_snap, c->pos, sizeof(double4) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
     c->indi_stale = true;
     return MDB_OK;
 }

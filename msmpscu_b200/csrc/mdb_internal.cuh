@@ -155,6 +155,13 @@ struct mdb_ctx {
     int dd_rank = 0, dd_n = 1;
     int dd_info[16] = {0}; // a0,a1, gb0,gb1, ga0,ga1, sb0,sb1, st0,st1, below,above, cell_lo,cell_hi, tile_lo,tile_hi
     int *h_dd = nullptr;   // pinned scratch
+    // backend of the library-level decomposed run (mdb_dd.cu): NCCL communicator (one process per GPU) or, for single-GPU
+    // tests, the contexts of all ranks in this process (same device, same stream: exchanges are device-to-device copies)
+    void *dd_comm = nullptr;
+    std::vector<mdb_ctx *> dd_peers;
+    int *dd_dev = nullptr;      // device: per rank {owned atoms, bottom-layer atoms, top-layer atoms, max atoms per cell}, then scratch
+    bool dd_built = false;      // the initial replicated build is done: later rebuilds sort owned + ghost atoms only
+    std::vector<int> dd_tab;    // host copy of the per-rank table of the last rebuild
 
     // ---- options
     int opt_force_path = MDB_FORCE_PATH_AUTO;
@@ -216,5 +223,11 @@ int mdb_force_tiled(mdb_ctx *c, unsigned flags, int fuse = 0, double hs2 = 0.0);
 int mdb_list_rebuild(mdb_ctx *c);
 int mdb_list_rebuild_checked(mdb_ctx *c);    // mdb_api.cu : + capacity check and generic fallback (syncs)
 int mdb_dd_update(mdb_ctx *c);                // mdb_api.cu : owned / ghost ranges after a rebuild (syncs)
+int mdb_cells_dd_count(mdb_ctx *c, const int cand[6], int zl0, int zl1, int *d_out4);      // mdb_cells.cu
+int mdb_cells_dd_place(mdb_ctx *c, const int cand[6], int zl0, int zl1, int base, int nown);
+int mdb_cells_dd_ghost_layer(mdb_ctx *c, int c0, int first);
+int mdb_predict_launch(mdb_ctx *c, double h, int pre);    // mdb_step.cu
+int mdb_epc_correct_launch(mdb_ctx *c, double h);
+void mdb_dd_free(mdb_ctx *c);                 // mdb_dd.cu
 static inline int own_a0(const mdb_ctx *c) { return c->dd_on ? c->dd_info[0] : 0; }
 static inline int own_a1(const mdb_ctx *c) { return c->dd_on ? c->dd_info[1] : c->n; }             // mdb_api.cu : cells + list kernel of the active path (no sync)
