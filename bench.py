@@ -81,6 +81,8 @@ def parse():
     ap.add_argument("--threads", type=int, default=0, help="tiled path: threads of the pass CTA (512/768), 0 = default")
     ap.add_argument("--bankorder", type=int, default=-1, help="tiled path: bank-aware order of the scanned list classes (0/1), -1 = default")
     ap.add_argument("--stages", type=int, default=0, help="tiled path: pipeline stages of the pass kernel (2/3), 0 = default")
+    ap.add_argument("--dd-cells", type=int, default=200, help="edge (bcc cells) of the single box of the dd_strong sub-record "
+                    "(200 -> 16 M atoms; 0 = skip)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the timed CPU loop")
     return ap.parse_args()
 
@@ -587,17 +589,27 @@ def run_ours(args):
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": "atom-steps/s", "cores": os.cpu_count(), "kind": "port", "error": repr(e)}
-    if rank == 0:
-        print(json.dumps(line))
     for cx in ctxs:
         cx.close()
+    del ctxs, host
+    torch.cuda.empty_cache()
+    if args.dd_cells > 0:
+        # configs[4] family on the same N GPUs: one 16 M-atom box, strong scaling (collective: every rank takes part)
+        try:
+            line["dd_strong"] = dd_measure(args, args.dd_cells, 5, 2)
+        except Exception as e:  # pragma: no cover
+            line["dd_strong"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_dd(args):
-    """One box over all ranks (slab decomposition, msmpscu_b200/domain.py): the box is the same on every rank (same
-    seed); value = atoms of the box x MD steps / max-over-ranks device time."""
+def dd_measure(args, cells, blocks, warm):
+    """ONE box over all ranks (slab decomposition inside the library, csrc/mdb_dd.cu): the box is the same on every rank
+    (same seed) for the initial build; afterwards a rank touches only its slab and its ghost layers.  Strong scaling:
+    value = atoms of the box x MD steps / max-over-ranks device time.  One block = one list period (10 MD steps, one
+    local rebuild).  Requires torch.cuda.set_device / the process group to be set up by the caller."""
     import torch
     import torch.distributed as dist
     import util
@@ -605,12 +617,8 @@ def run_dd(args):
     from msmpscu_b200.domain import SlabDomain
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    c = make_case(args.cells, 777)
+    c = make_case(cells, 777)
     n = c.xp.shape[0]
     ctx = capi.Context(local)
     ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
@@ -620,32 +628,32 @@ def run_dd(args):
     ctx.epc_set(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
     ctx.upload(capi.F_XP, c.xp); ctx.upload(capi.F_XP1, c.xp1)
     ctx.upload(capi.F_ITYP, c.ityp); ctx.upload(capi.F_STATU, c.statu)
+    del c.xp1
     dom = SlabDomain(ctx, local)
     dom.rebuild()
-    ctx.force(capi.DEN); dom.exchange(); ctx.force(capi.FORCE | capi.NOPASS1)
+    dom.force(capi.FORCE)
     stream = dom.stream
     itime = [0]
 
-    def block(_):
-        for _i in range(MD_PER_PERIOD):
-            dom.step(itime[0], 1, MD_PER_PERIOD, H)
-            itime[0] += 1
+    def block():
+        dom.run(itime[0], MD_PER_PERIOD, 1, MD_PER_PERIOD, H)
+        itime[0] += MD_PER_PERIOD
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        block(i)
+    for _ in range(max(warm, 1)):
+        block()
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ctx.launch_count()
     barrier()
     e0.record(stream)
-    for i in range(args.steps):
-        block(i)
+    for _ in range(blocks):
+        block()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -655,33 +663,63 @@ def run_dd(args):
         ms = float(t.item())
     launches = ctx.launch_count() - l0
     clocks = sampler.result()
-    dom.phase_ms = {}
-    block(0)
-    phases = dom.phase_report()   # one extra block of 10 steps with per-phase CUDA events (not part of the timed region)
-    dom.phase_ms = None
+    # per-phase device times of one more block (CUDA events of the library's profiling classes, not part of the timed region)
+    ctx.prof_reset(); ctx.prof_enable(True)
+    block()
+    prof = {k: round(v[1], 3) for k, v in ctx.prof_get().items() if v[0]}
+    ctx.prof_enable(False)
     if world > 1:
         allp = [None] * world
-        dist.all_gather_object(allp, phases)
-        phases = {k: [round(p.get(k, 0.0), 3) for p in allp] for k in phases}
+        dist.all_gather_object(allp, prof)
+        prof = {k: [p.get(k, 0.0) for p in allp] for k in prof}
     a0, a1 = dom.owned()
-    line = base_line(args, n)
+    rec = {"value": n * MD_PER_PERIOD * blocks / (ms * 1e-3), "unit": "atom-steps/s", "scaling": "strong", "atoms_total": n,
+           "atoms_owned_rank0": a1 - a0, "n_gpus": world, "blocks": blocks, "md_steps_per_block": MD_PER_PERIOD,
+           "ms_per_block": ms / blocks, "gpu_launches": int(launches), "clocks": clocks,
+           "phase_ms_per_block_by_rank": prof,
+           "workload": "configs[4] family: ONE bcc W box of %d atoms (%d^3 cells) cut into %d z-slabs; per step two ghost-layer "
+                       "exchanges of {x,y,z,den} records (ncclSend/ncclRecv enqueued by the library), per %d steps a local rebuild "
+                       "of the rank's slab (no broadcast, no all-atom sort)" % (n, cells, world, MD_PER_PERIOD)}
+    ctx.close()
+    return rec
+
+
+def run_dd(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rec = dd_measure(args, args.cells, args.steps, max(args.warmup, 3))
+    line = base_line(args, rec["atoms_total"])
     line["scaling"] = "strong"
-    line["config"].update({"workload": "configs[4] family: ONE bcc W box of %d atoms (%d^3 cells) cut into %d z-slabs, ghost-layer "
-                                       "exchange of {x,y,z,den} records over NCCL twice per step, list rebuilt every %d steps "
-                                       "(owned ranges broadcast, identical device sort on every rank)" % (n, args.cells, world, MD_PER_PERIOD),
-                           "atoms_per_gpu": a1 - a0, "atoms_total": n, "md_steps_per_step": MD_PER_PERIOD,
-                           "parallelism": "z-slab domain decomposition, 1 ghost cell layer per side"})
-    line.update({"value": n * MD_PER_PERIOD * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "clocks": clocks,
-                 "gpu_launches": int(launches), "force_path": "tiled", "mode": "dd",
-                 "phase_ms_per_block_by_rank": phases})
+    line["config"].update({"workload": rec["workload"], "atoms_per_gpu": rec["atoms_owned_rank0"], "atoms_total": rec["atoms_total"],
+                           "md_steps_per_step": MD_PER_PERIOD, "parallelism": "z-slab domain decomposition, 1 ghost cell layer per side"})
+    line.update({"value": rec["value"], "ms_per_step": rec["ms_per_block"], "clocks": rec["clocks"], "gpu_launches": rec["gpu_launches"],
+                 "force_path": "tiled", "mode": "dd", "phase_ms_per_block_by_rank": rec["phase_ms_per_block_by_rank"]})
     if rank == 0:
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line, the JSON record: libraries that print there (NCCL's version banner, ...) are sent to
+    # stderr for the duration of the run
+    _real_stdout = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001  (module-level print of the record goes to the real stdout)
+        if kw.get("file") is None:
+            os.write(_real_stdout, (" ".join(str(x) for x in args) + "\n").encode())
+        else:
+            _print(*args, **kw)
+
     a = parse()
     if a.impl == "reference":
         run_reference(a)

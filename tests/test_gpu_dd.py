@@ -18,7 +18,7 @@ def test_slab_run_matches_single_gpu(world):
     if capi.load().mdb_device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29533 + world), os.path.join(ROOT, "tests", "dd_worker.py"), "25"]
+           "--master-port", str(29533 + world), os.path.join(ROOT, "tests", "dd_worker.py"), "35"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(out.stdout[-3000:], out.stderr[-3000:])
     assert out.returncode == 0
