@@ -232,3 +232,282 @@ contains
       end if
   end subroutine
 end module MD_LBFGSScheme_GPU
+
+module MD_FS_Force_Table_GPU             ! replaces MDLIB/sor/CommonGPU/MD_FS_ForceTable_GPU.F90 (the FS_TYPE slots of Register_ForceClass)
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MD_TYPEDEF_ForceTable
+  use MDB_C_BINDING
+  implicit none
+contains
+  subroutine INITIALIZE_FS_Force_Table_DEV(SimBox, CtrlParam, FTable, RelaseTable, MULTIBOX)    ! :178-310
+    type(SimMDBox),     intent(inout)::SimBox
+    type(SimMDCtrl),    intent(in)   ::CtrlParam
+    type(MDForceTable), intent(in)   ::FTable
+    integer,            optional     ::RelaseTable, MULTIBOX
+      ! FS_TYPE: same tables, embedding -sqrt(rho) evaluated in the kernels (FEMBD / DFEMBD are not read)
+      if(mdb_tables_set(m_CTX, MDB_POT_FS, size(FTable%POTR,1), size(FTable%POTR,2), FTable%CSI,                &
+                        FTable%POTR, FTable%FPOTR, FTable%POTB, FTable%FPOTB,                                    &
+                        size(FTable%FEMBD,1), size(FTable%FEMBD,2), FTable%RHOD, FTable%FEMBD, FTable%DFEMBD,    &
+                        FTable%KPAIR, FTable%KEMBD, maxval(CtrlParam%RU*CtrlParam%RU)) .lt. 0)                   &
+         stop "MDPSCU Error: mdb_tables_set failed"
+  end subroutine
+  subroutine CALFORCE_FS_Force_Table2A_DEV(SimBox, CtrlParam)                                    ! :934-1000
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+    real(c_double)::VT(9)
+      if(mdb_force(m_CTX, MDB_FORCE, VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+  end subroutine
+  subroutine CALPTENSOR_FS_Force_Table2A_DEV(SimBox, CtrlParam)                                  ! :1348-1412
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+    real(c_double)::VT(9)
+      if(mdb_force(m_CTX, ior(MDB_FORCE, MDB_VIRIAL), VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+      SimBox%VTENSOR = reshape(VT, (/3,3/))
+  end subroutine
+  subroutine UpdateEPOT_FS_Force_Table2A_DEV(SimBox, CtrlParam)                                  ! :1679-1716
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+    real(c_double)::VT(9)
+      if(mdb_force(m_CTX, MDB_EPOT, VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+  end subroutine
+  subroutine CALEPOT_FS_Force_Table2A_DEV(SimBox, CtrlParam)                                     ! :1720-1760: + copy to hm_EPOT
+    use MD_Globle_Variables_GPU, only: hm_EPOT
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+    real(c_double)::VT(9)
+      if(mdb_force(m_CTX, MDB_EPOT, VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+      if(mdb_state_download(m_CTX, MDB_F_EPOT, c_loc(hm_EPOT), MDB_ORDER_CELL) .lt. 0) stop "MDPSCU Error: mdb_state_download failed"
+  end subroutine
+  subroutine CALDEN_FS_Force_Table2A_DEV(SimBox, CtrlParam)                                      ! :875-930
+    type(SimMDBox),  intent(inout)::SimBox
+    type(SimMDCtrl), intent(in)   ::CtrlParam
+    real(c_double)::VT(9)
+      if(mdb_force(m_CTX, MDB_DEN, VT) .lt. 0) stop "MDPSCU Error: mdb_force failed"
+  end subroutine
+  subroutine Cal_FS_AtomicStressTensor_DEV(IDEV, dAVP)                                           ! :2044-2061 (pCalAVStress)
+    integer, intent(in)::IDEV
+    real(KINDDF), device, dimension(:,:), intent(out)::dAVP
+      if(mdb_atomic_stress(m_CTX, c_devloc(dAVP)) .lt. 0) stop "MDPSCU Error: mdb_atomic_stress failed"
+  end subroutine
+  subroutine Clear_FS_Force_Table_DEV()                                                          ! :314-337
+    integer(c_int)::ERR
+      ERR = mdb_tables_clear(m_CTX)
+  end subroutine
+end module MD_FS_Force_Table_GPU
+
+module MSM_MultiGPU_Basic_B200           ! the device bookkeeping of MSMLIB/sor/CommonGPU/MSM_MultiGPU_Basic.F90 the hot path uses
+  use MDB_C_BINDING
+  implicit none
+  integer, parameter :: m_MXDEVICE = 8   ! one box of 8 B200 (the reference allows 6, :22); ONE device per host process here
+  integer            :: m_NDEVICE = 0, m_DEVICES(m_MXDEVICE) = -1
+contains
+  subroutine Initialize_DEVICES(FIRSTDEV, NDEV)                                                  ! :571-599
+    integer::FIRSTDEV, NDEV
+      if(NDEV .gt. m_MXDEVICE) then
+         write(*,*) "MDPSCU Error: the number of devices larger than permitted value ", m_MXDEVICE
+         stop
+      end if
+      if(NDEV .gt. 1) then
+         ! several devices of one process is the reference's scheme; here a process drives ONE device and several
+         ! processes share a box through mdb_dd_* (slab decomposition over NCCL) or own independent boxes
+         write(*,*) "MDPSCU Warning: libmdpscu_b200 drives one device per process; using device ", FIRSTDEV
+      end if
+      if(mdb_device_count() .le. FIRSTDEV) stop "MDPSCU Error: no such CUDA device"
+      if(c_associated(m_CTX)) call mdb_ctx_destroy(m_CTX)
+      if(mdb_ctx_create(FIRSTDEV, m_CTX) .lt. 0) stop "MDPSCU Error: mdb_ctx_create failed"
+      m_NDEVICE = 1
+      m_DEVICES(1) = FIRSTDEV
+  end subroutine
+  subroutine End_DEVICES()                                                                       ! :640-657
+      if(c_associated(m_CTX)) call mdb_ctx_destroy(m_CTX)
+      m_CTX = c_null_ptr
+      m_NDEVICE = 0
+  end subroutine
+end module MSM_MultiGPU_Basic_B200
+
+module MD_Globle_Variables_GPU           ! replaces MDLIB/sor/CommonGPU/MD_Globle_Variables_GPU.F90 (:196-510 public names)
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MDB_C_BINDING
+  implicit none
+  ! host mirrors the application shell reads (reference :113-139); filled by the Copy...From_Devices_to_Host family
+  integer                                       :: m_NAPDEV = 0, dm_NPRT = 0
+  integer,      dimension(:),   allocatable, target :: hm_ITYP, hm_STATU, hm_GID, hm_GIDINV
+  real(KINDDF), dimension(:,:), allocatable, target :: hm_XP, hm_XP1, hm_FP, hm_DIS
+  real(KINDDF), dimension(:),   allocatable, target :: hm_EPOT, hm_EKIN
+  interface Initialize_Globle_Variables_DEV
+     module procedure Initialize_GB_A_DEV
+     module procedure Initialize_GB_B_DEV
+  end interface
+contains
+  subroutine Initialize_GB_A_DEV(SimBox, CtrlParam)                                              ! :585-655: SimBox(:) = MULTIBOX
+    type(SimMDBox), dimension(:)::SimBox
+    type(SimMDCtrl)             ::CtrlParam
+    integer::NB, NPRT, I, IS
+      NB = size(SimBox); NPRT = SimBox(1)%NPRT
+      call Clear_Globle_Variables_DEV()
+      if(mdb_box_set(m_CTX, NB, NPRT, SimBox(1)%BOXLOW, SimBox(1)%ZL, reshape(SimBox(1)%BOXSHAPE, (/9/)), CtrlParam%IFPD, &
+                     SimBox(1)%NGROUP, SimBox(1)%CM) .lt. 0) stop "MDPSCU Error: mdb_box_set failed"
+      dm_NPRT = NB*NPRT; m_NAPDEV = dm_NPRT
+      allocate(hm_ITYP(dm_NPRT), hm_STATU(dm_NPRT), hm_GID(dm_NPRT), hm_GIDINV(dm_NPRT), hm_XP(dm_NPRT,3), hm_XP1(dm_NPRT,3), &
+               hm_FP(dm_NPRT,3), hm_DIS(dm_NPRT,3), hm_EPOT(dm_NPRT), hm_EKIN(dm_NPRT))
+      IS = 0
+      do I=1, NB                                                                                 ! :628-640
+         hm_ITYP(IS+1:IS+NPRT) = SimBox(I)%ITYP;      hm_STATU(IS+1:IS+NPRT) = SimBox(I)%STATU
+         hm_XP(IS+1:IS+NPRT,:) = SimBox(I)%XP;        hm_XP1(IS+1:IS+NPRT,:) = SimBox(I)%XP1
+         hm_DIS(IS+1:IS+NPRT,:)= SimBox(I)%DIS;       hm_FP(IS+1:IS+NPRT,:)  = SimBox(I)%FP
+         IS = IS + NPRT
+      end do
+      call CopyAllFrom_Host_to_Devices()
+  end subroutine
+  subroutine Initialize_GB_B_DEV(SimBox, CtrlParam)                                              ! one box
+    type(SimMDBox) ::SimBox
+    type(SimMDCtrl)::CtrlParam
+    type(SimMDBox), dimension(1)::SB
+      SB(1) = SimBox
+      call Initialize_GB_A_DEV(SB, CtrlParam)
+  end subroutine
+  subroutine Clear_Globle_Variables_DEV()                                                        ! :658-714
+      if(allocated(hm_ITYP)) deallocate(hm_ITYP, hm_STATU, hm_GID, hm_GIDINV, hm_XP, hm_XP1, hm_FP, hm_DIS, hm_EPOT, hm_EKIN)
+      dm_NPRT = 0; m_NAPDEV = 0
+  end subroutine
+  subroutine CopyAllFrom_Host_to_Devices()                                                       ! :1076-1122
+      if(mdb_state_upload(m_CTX, MDB_F_XP,    c_loc(hm_XP),    MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: upload XP"
+      if(mdb_state_upload(m_CTX, MDB_F_XP1,   c_loc(hm_XP1),   MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: upload XP1"
+      if(mdb_state_upload(m_CTX, MDB_F_DIS,   c_loc(hm_DIS),   MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: upload DIS"
+      if(mdb_state_upload(m_CTX, MDB_F_FP,    c_loc(hm_FP),    MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: upload FP"
+      if(mdb_state_upload(m_CTX, MDB_F_ITYP,  c_loc(hm_ITYP),  MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: upload ITYP"
+      if(mdb_state_upload(m_CTX, MDB_F_STATU, c_loc(hm_STATU), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: upload STATU"
+  end subroutine
+  subroutine CopyAllFrom_Devices_to_Host()                                                       ! :1023-1072 (original order restored)
+      call CopyXPFrom_Devices_to_Host();   call CopyXP1From_Devices_to_Host();  call CopyFPFrom_Devices_to_Host()
+      call CopyDISFrom_Devices_to_Host();  call CopyEPOTFrom_Devices_to_Host(); call CopyEKINFrom_Devices_to_Host()
+      call CopyStatuFrom_Devices_to_Host()
+  end subroutine
+  subroutine CopyXPFrom_Devices_to_Host()
+      if(mdb_state_download(m_CTX, MDB_F_XP, c_loc(hm_XP), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: download XP"
+  end subroutine
+  subroutine CopyXP1From_Devices_to_Host()
+      if(mdb_state_download(m_CTX, MDB_F_XP1, c_loc(hm_XP1), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: download XP1"
+  end subroutine
+  subroutine CopyFPFrom_Devices_to_Host()
+      if(mdb_state_download(m_CTX, MDB_F_FP, c_loc(hm_FP), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: download FP"
+  end subroutine
+  subroutine CopyDISFrom_Devices_to_Host()
+      if(mdb_state_download(m_CTX, MDB_F_DIS, c_loc(hm_DIS), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: download DIS"
+  end subroutine
+  subroutine CopyEPOTFrom_Devices_to_Host()
+      if(mdb_state_download(m_CTX, MDB_F_EPOT, c_loc(hm_EPOT), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: download EPOT"
+  end subroutine
+  subroutine CopyEKINFrom_Devices_to_Host()
+      if(mdb_ekin(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_ekin failed"
+      if(mdb_state_download(m_CTX, MDB_F_EKIN, c_loc(hm_EKIN), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: download EKIN"
+  end subroutine
+  subroutine CopyStatuFrom_Devices_to_Host()
+      if(mdb_state_download(m_CTX, MDB_F_STATU, c_loc(hm_STATU), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: download STATU"
+      if(mdb_state_download(m_CTX, MDB_F_GID, c_loc(hm_GID), MDB_ORDER_CELL) .lt. 0) stop "MDPSCU Error: download GID"
+      if(mdb_state_download(m_CTX, MDB_F_GIDINV, c_loc(hm_GIDINV), MDB_ORDER_CELL) .lt. 0) stop "MDPSCU Error: download GIDINV"
+  end subroutine
+  subroutine CopyXPFrom_Devices_to_Host1(hXP)                                                    ! :2133-2147
+    real(KINDDF), dimension(:,:), target::hXP
+      if(mdb_state_download(m_CTX, MDB_F_XP, c_loc(hXP), MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: download XP"
+  end subroutine
+  subroutine Synchroniz_XP_on_Devices()                                                          ! :2026-2040
+      ! one device per process: nothing to gather (the decomposed run exchanges ghost layers inside mdb_dd_run)
+  end subroutine
+  subroutine SynchronizeDevices()
+      if(mdb_sync(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_sync failed"
+  end subroutine
+end module MD_Globle_Variables_GPU
+
+module MD_SimBoxArray_GPU                ! replaces MDLIB/sor/CommonGPU/MD_SimBoxArray_GPU.F90 (:24-88 generic names)
+  use MD_TYPEDEF_SimMDBox
+  use MD_Globle_Variables_GPU
+  use MDB_C_BINDING
+  implicit none
+  interface CopyIn_SimBox_DEV
+     module procedure CopyIn_SimBoxA
+  end interface
+  interface CopyOut_SimBox_DEV
+     module procedure CopyOut_SimBoxA
+  end interface
+contains
+  subroutine CopyIn_SimBoxA(SimBox)                                                              ! :91-155
+    type(SimMDBox), dimension(:)::SimBox
+    integer::I, IS, NPRT
+      NPRT = SimBox(1)%NPRT; IS = 0
+      do I=1, size(SimBox)
+         hm_XP(IS+1:IS+NPRT,:) = SimBox(I)%XP;   hm_XP1(IS+1:IS+NPRT,:) = SimBox(I)%XP1
+         hm_DIS(IS+1:IS+NPRT,:)= SimBox(I)%DIS;  hm_FP(IS+1:IS+NPRT,:)  = SimBox(I)%FP
+         hm_STATU(IS+1:IS+NPRT)= SimBox(I)%STATU; hm_ITYP(IS+1:IS+NPRT) = SimBox(I)%ITYP
+         IS = IS + NPRT
+      end do
+      call CopyAllFrom_Host_to_Devices()
+  end subroutine
+  subroutine CopyOut_SimBoxA(SimBox)                                                             ! :202-240
+    type(SimMDBox), dimension(:)::SimBox
+    integer::I, IS, NPRT
+      call CopyAllFrom_Devices_to_Host()
+      NPRT = SimBox(1)%NPRT; IS = 0
+      do I=1, size(SimBox)
+         SimBox(I)%XP  = hm_XP(IS+1:IS+NPRT,:);   SimBox(I)%XP1  = hm_XP1(IS+1:IS+NPRT,:)
+         SimBox(I)%DIS = hm_DIS(IS+1:IS+NPRT,:);  SimBox(I)%FP   = hm_FP(IS+1:IS+NPRT,:)
+         SimBox(I)%EPOT= hm_EPOT(IS+1:IS+NPRT);   SimBox(I)%EKIN = hm_EKIN(IS+1:IS+NPRT)
+         SimBox(I)%STATU = hm_STATU(IS+1:IS+NPRT)
+         IS = IS + NPRT
+      end do
+  end subroutine
+end module MD_SimBoxArray_GPU
+
+module MD_NeighborsList_GPU_More         ! the remaining public entry points of MD_NeighborsList_GPU.F90 (:116-202)
+  use MD_NeighborsList
+  use MDB_C_BINDING
+  implicit none
+contains
+  subroutine Copyout_NeighboreList_A2(List)                                                      ! :584-600: cell-sorted order
+    type(NEIGHBOR_LIST), target::List
+      if(mdb_nlist_copyout(m_CTX, List%KVOIS, List%INDI, MDB_ORDER_CELL) .lt. 0) stop "MDPSCU Error: mdb_nlist_copyout failed"
+  end subroutine
+  subroutine Copyout_NeighboreList_ORIG(List)                                                    ! :465-560 with GID: original order
+    type(NEIGHBOR_LIST), target::List
+      if(mdb_nlist_copyout(m_CTX, List%KVOIS, List%INDI, MDB_ORDER_ORIGINAL) .lt. 0) stop "MDPSCU Error: mdb_nlist_copyout failed"
+  end subroutine
+  subroutine GetCellInform(TNC, NCELL, MXNAC)                                                    ! :2391-2399
+    integer::TNC, NCELL(3), MXNAC
+      if(mdb_nlist_cellinfo(m_CTX, NCELL, TNC, MXNAC) .lt. 0) stop "MDPSCU Error: mdb_nlist_cellinfo failed"
+  end subroutine
+  subroutine Clear_NeighboreList_DEV()                                                           ! :139-152
+    integer(c_int)::ERR
+      ERR = mdb_nlist_clear(m_CTX)
+  end subroutine
+end module MD_NeighborsList_GPU_More
+
+module MD_LocalTempMethod_GPU            ! replaces MDLIB/sor/LocalTempCtrlMeths/MD_LocalTempMethod_GPU.F90 (:95-138) for the EPC part
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MDB_C_BINDING
+  implicit none
+contains
+  subroutine Do_ResetParam_DEV(SimBox, CtrlParam)                                                ! -> Reset_EPCMOD_DEV, EPC/MD_EP_Coupling_GPU.F90:370-417
+    type(SimMDBox),  intent(in)::SimBox
+    type(SimMDCtrl), intent(in)::CtrlParam
+    integer(c_int)::ENABLE(MDB_MXGROUP)
+    real(c_double)::TE(MDB_MXGROUP), ALPHA(MDB_MXGROUP), CUT(MDB_MXGROUP), HE(MDB_MXGROUP)
+    integer::I
+      ENABLE = 0; TE = 0; ALPHA = 1; CUT = 0; HE = 0
+      do I=1, SimBox%NGROUP                                                                      ! :384-391: V2TI, EPA, EPACUT, EPUPPER are formed inside mdb_epc_set
+         ENABLE(I) = iand(CtrlParam%LT_CTRL(I)%METH, CP_TICTRL_METH_EPC)
+         TE(I)     = CtrlParam%LT_CTRL(I)%TI
+         ALPHA(I)  = CtrlParam%LT_CTRL(I)%EPC_Alpha
+         CUT(I)    = CtrlParam%LT_CTRL(I)%EPC_CUT
+         HE(I)     = CtrlParam%LT_CTRL(I)%EPC_HE
+      end do
+      if(mdb_epc_set(m_CTX, ENABLE, TE, ALPHA, CUT, HE) .lt. 0) stop "MDPSCU Error: mdb_epc_set failed"
+  end subroutine
+  subroutine Do_EPCForce_DEV(SimBox, CtrlParam)                                                  ! :119-138 -> Do_EPCMOD_DEV :421-493
+    type(SimMDBox), dimension(:)::SimBox
+    type(SimMDCtrl)             ::CtrlParam
+      if(mdb_epc_apply(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_epc_apply failed"
+  end subroutine
+end module MD_LocalTempMethod_GPU

@@ -284,3 +284,42 @@ def test_ctrl_defaults_and_sections_follow_the_reference():
     one = inputs.read_ctrl_file(os.path.join(g, "gmd_CtrlFile300K.dat"), box)
     assert one.TEMP == secs[0].TEMP and one.NB_MXNBS == 256 and one.NB_UPTAB == 10
     assert one.STRCUT_DRTol == 0.03          # the file has no &DRTOL
+
+
+def test_fortran_binding_covers_the_whole_header():
+    """fortran/mdb_c_binding.F90 is generated from include/mdpscu_b200.h (tools/gen_fortran_binding.py): every entry point of
+    the header has a bind(C) interface with the same name and the same number of arguments, and the committed file is fresh.
+    fortran/mdb_shims.F90 only calls bound entry points and defines the procedures INTEGRATION.md's table names."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_fortran_binding", os.path.join(root, "tools", "gen_fortran_binding.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    decls = gen.declarations()
+    from msmpscu_b200 import capi
+    assert {d[1] for d in decls} == set(capi.SYMBOLS), "header and capi.SYMBOLS disagree"
+    text = open(os.path.join(root, "fortran", "mdb_c_binding.F90")).read()
+    assert text == gen.generate(), "fortran/mdb_c_binding.F90 is stale: run python tools/gen_fortran_binding.py"
+    flat = re.sub(r"&\s*\n\s*", " ", text)
+    for ret, name, args in decls:
+        m = re.search(r"(?:function|subroutine)\s+%s\(([^)]*)\)\s+bind\(C, name=\"%s\"\)" % (name, name), flat)
+        assert m, name
+        got = [a for a in m.group(1).split(",") if a.strip()]
+        assert len(got) == len(args), (name, got, args)
+    shims = open(os.path.join(root, "fortran", "mdb_shims.F90")).read()
+    bound = {d[1] for d in decls}
+    for called in set(re.findall(r"\b(mdb_[a-z0-9_]+)\s*\(", shims)):
+        assert called in bound, "shim calls %s, which the header does not declare" % called
+    for proc in ("INITIALIZE_EAM_Force_Table_DEV", "CALFORCE_EAM_Force_Table2A_DEV", "CALPTENSOR_EAM_Force_Table2A_DEV",
+                 "UpdateEPOT_EAM_Force_Table2A_DEV", "CALDEN_EAM_Force_Table2A_DEV", "Cal_EAM_AtomicStressTensor_DEV",
+                 "Clear_EAM_Force_Table_DEV", "INITIALIZE_FS_Force_Table_DEV", "CALFORCE_FS_Force_Table2A_DEV",
+                 "CALPTENSOR_FS_Force_Table2A_DEV", "UpdateEPOT_FS_Force_Table2A_DEV", "CALDEN_FS_Force_Table2A_DEV",
+                 "Cal_FS_AtomicStressTensor_DEV", "Clear_FS_Force_Table_DEV", "Initialize_NeighboreList_DEV", "Cal_NeighBoreList_DEV",
+                 "Copyout_NeighboreList_A2", "GetCellInform", "Clear_NeighboreList_DEV", "Reorder_NeighBoreList_Nearest_Dev",
+                 "Predictor_DEV", "Correction_DEV", "CalEKin_DEV", "Cal_GlobalT_DEV", "VelScaling_DEV", "Thermalizing_MC_DEV",
+                 "CheckTimestep_DEV", "Do_EPCForce_DEV", "Do_ResetParam_DEV", "Initialize_GB_A_DEV", "Clear_Globle_Variables_DEV",
+                 "CopyAllFrom_Devices_to_Host", "CopyAllFrom_Host_to_Devices", "Synchroniz_XP_on_Devices", "CopyIn_SimBoxA",
+                 "CopyOut_SimBoxA", "Initialize_DEVICES", "Do_Steepest_Forsteps_DEV", "Do_CG_Forsteps_DEV", "DO_LBFGSB_FORSTEPS_DEV",
+                 "Do_DynDamp_Forsteps_DEV"):
+        assert re.search(r"subroutine\s+%s\b" % proc, shims), "shim %s missing" % proc

@@ -145,3 +145,55 @@ def test_bank_ordered_lists_give_the_same_sums(oracle, name, lanes):
     kv, _ = ctx.nlist_copyout(capi.ORDER_CELL)
     assert np.array_equal(kv, ref["kvois"])
     ctx.close()
+
+
+def test_cpp_host_replays_the_fortran_shim_call_sequence(tmp_path):
+    """tests/cpp/replay_shims.cpp: a compiled C++ host that makes the calls of fortran/mdb_shims.F90 in the order the unchanged
+    MDPSCU shell makes them (device init, box, force-class slots, list, kernel-by-kernel For_One_Step, copy-out, clear).  Its
+    results must be those of the same sequence through Python/ctypes: the boundary is language-neutral."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "replay_shims")
+    libdir = os.path.join(root, "msmpscu_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "cpp", "replay_shims.cpp"),
+                           "-L" + libdir, "-lmdpscu_b200", "-Wl,-rpath," + libdir])
+    c = util.bcc_case((9, 9, 9), seed=2025)
+    n = c.xp.shape[0]
+    nsteps = 23
+    cfg, out = str(tmp_path / "cfg.bin"), str(tmp_path / "out.bin")
+    with open(cfg, "wb") as f:
+        np.array([n], np.int32).tofile(f)
+        np.array(list(c.boxlow) + list(c.zl) + [c.mass[0], c.ru, float(c.nb_rm[0, 0] / c.ru)]).tofile(f)
+        capi.colmajor(c.xp).tofile(f)
+        capi.colmajor(c.xp1).tofile(f)
+    r = subprocess.run([exe, cfg, out, str(nsteps)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    raw = np.fromfile(out)
+    scal, vt, rest = raw[:4], raw[4:13].reshape(3, 3).T, raw[13:]
+    xp, xp1, fp = (capi.from_colmajor(rest[k * 3 * n:(k + 1) * 3 * n], n, 3) for k in range(3))
+    epot = rest[9 * n:10 * n]
+    # the same sequence through the Python binding
+    ctx = util.make_ctx(c)
+    ctx.epc_set([1], [300.0], [1.0e-12], [0.1], [100.0 * util.CP_EVERG])
+    ctx.force(capi.FORCE)
+    h = 0.5e-15
+    for it in range(nsteps):
+        ctx.predict(h)
+        if (it - 1) % 10 == 0:
+            ctx.nlist_build()
+        ctx.force(capi.FORCE)
+        ctx.epc_apply()
+        ctx.correct(h)
+    ctx.ekin()
+    t = ctx.global_t()
+    vt_py = ctx.force(capi.FORCE | capi.EPOT | capi.VIRIAL)
+    assert np.array_equal(xp, ctx.download(capi.F_XP)) and np.array_equal(xp1, ctx.download(capi.F_XP1))
+    assert np.array_equal(fp, ctx.download(capi.F_FP)) and np.array_equal(epot, ctx.download(capi.F_EPOT))
+    assert scal[0] == t
+    assert util.relerr(vt, vt_py) < 1e-13      # per-warp partial tensors: the summation order follows the chunk scheduling
+    kv, _ = ctx.nlist_copyout(capi.ORDER_ORIGINAL)
+    assert int(scal[1]) == int(kv.sum())
+    assert ctx.embed_overruns() == 0          # a thermal crystal never leaves the embedding table
+    ctx.close()
