@@ -180,6 +180,32 @@ int mdb_epc_apply(mdb_ctx *ctx);
 int mdb_epc_correct(mdb_ctx *ctx, double h);
 
 /* ------------------------------------------------------------------------------------
+ * cascade physics around the path (BASELINE configs[4]; csrc/mdb_cascade.cu)
+ *   mdb_active_region  ActivateRegion_DEV -> ActiveByCells1 (CommonGPU/MD_ActiveRegion_GPU.F90:1165-1353): seeds by atom type
+ *                      (method bit 0, centpart[ngroup] > 0) and / or kinetic energy >= ekin_erg (bit 1); bit 2 = CP_KEEP_AR
+ *                      (earlier activations are kept); the seeds' cells grown `extend` times over the 27-cell
+ *                      neighbourhood; atoms of marked cells become active.  Needs the cell ids of a built list.  Inactive
+ *                      atoms get no force and do not move; cells without active atoms are skipped by the next list build
+ *                      (NAAC, MD_NeighborsList_GPU.F90:981-982).  Returns the number of active atoms.
+ *   mdb_active_all     Active_All_ActiveRegion_DEV (on != 0) / DeActive_All_ActiveRegion_DEV (on == 0), :242-425
+ *   mdb_stopping_set   Initialize_STMOD_DEV + Reset_STMOD_DEV (LocalTempCtrlMeths/Stopping/MD_ST_Coupling_GPU.F90:334-427):
+ *                      stopping tables ETAB(NE) [erg], STAB(NE,NK) [erg cm^2] as the stopping libraries (Stop_Srim, Stop_Z85,
+ *                      Stop_Z95, Stop_B) fill them, KPAIR(NG,NG) column-major 1-based (moving type, medium type), the
+ *                      per-type switch (LT_CTRL%METH and CP_TICTRL_METH_ST) and the number densities MDEN [1/cm^3] of the
+ *                      medium types (global-density model, ST_MOD_GDEN_KERNEL :431-536).  ne < 2 switches it off.
+ *   mdb_stopping_apply Do_STMOD_Force_DEV (:787-831): FP -= sum_g MDEN_g S_kg(E) v/|v|.  mdb_run applies it every step between
+ *                      the EPC friction and the corrector once tables are set.
+ *   mdb_pka_insert     a primary knock-on atom (Deposition/MD_TypeDef_Projectile.F90, CP_DEP_STYPE_PKA, mono-energetic): the
+ *                      velocity of the atom with ORIGINAL id orig_id becomes sqrt(2 EK / m) along dir
+ * ---------------------------------------------------------------------------------- */
+int mdb_active_region(mdb_ctx *ctx, int method, const int *centpart, double ekin_erg, int extend);
+int mdb_active_all(mdb_ctx *ctx, int on);
+int mdb_stopping_set(mdb_ctx *ctx, int ne, int nk, const double *etab, const double *stab, const int *kpair, const int *enable,
+                     const double *mden);
+int mdb_stopping_apply(mdb_ctx *ctx);
+int mdb_pka_insert(mdb_ctx *ctx, int orig_id, double ekin_erg, const double dir[3]);
+
+/* ------------------------------------------------------------------------------------
  * one whole MD step, For_One_Step (Appshell/MD_Method_GenericMD_GPU.F90:496-659):
  * predictor -> [rebuild if MOD(itime-it0,nb_uptab)==0] -> force -> EPC -> corrector,
  * with the element-wise stages fused into the force passes where no rebuild intervenes.

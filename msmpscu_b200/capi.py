@@ -62,6 +62,11 @@ SYMBOLS = {
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_embed_overruns": (C.c_int, [C.c_void_p]),
+    "mdb_active_region": (C.c_int, [C.c_void_p, C.c_int, c_ip, C.c_double, C.c_int]),
+    "mdb_active_all": (C.c_int, [C.c_void_p, C.c_int]),
+    "mdb_stopping_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_ip, c_dp]),
+    "mdb_stopping_apply": (C.c_int, [C.c_void_p]),
+    "mdb_pka_insert": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp]),
     "mdb_dd_nccl_id": (C.c_int, [C.c_void_p]),
     "mdb_dd_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mdb_dd_local_attach": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
@@ -326,6 +331,33 @@ class Context:
 
     def run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    # ---- cascade physics (csrc/mdb_cascade.cu)
+    def active_region(self, centpart=None, ekin_erg=None, extend=1, keep=False):
+        """ActivateRegion_DEV by cells; returns the number of active atoms"""
+        method = (1 if centpart is not None else 0) | (2 if ekin_erg is not None else 0) | (4 if keep else 0)
+        cp = i32(centpart) if centpart is not None else None
+        return self._chk(self.lib.mdb_active_region(self.h, method, ip(cp) if cp is not None else None,
+                                                    float(ekin_erg or 0.0), int(extend)))
+
+    def active_all(self, on=True):
+        self._chk(self.lib.mdb_active_all(self.h, 1 if on else 0))
+
+    def stopping_set(self, etab, stab, kpair, enable, mden):
+        """etab (NE,), stab (NE, NK) [columns = tables], kpair (NG, NG) 1-based, enable (NG,), mden (NG,)"""
+        e = f64(etab)
+        st = np.ascontiguousarray(np.asarray(stab, dtype=np.float64).reshape(len(e), -1).T).ravel()   # column-major STAB(NE,NK)
+        kp = np.ascontiguousarray(np.asarray(kpair, dtype=np.int32).T).ravel()
+        self._stop_keep = (e, st, kp, i32(enable), f64(mden))
+        self._chk(self.lib.mdb_stopping_set(self.h, len(e), st.size // len(e), dp(e), dp(st), ip(kp), ip(self._stop_keep[3]),
+                                            dp(self._stop_keep[4])))
+
+    def stopping_apply(self):
+        self._chk(self.lib.mdb_stopping_apply(self.h))
+
+    def pka_insert(self, orig_id, ekin_erg, direction):
+        d = f64(direction)
+        self._chk(self.lib.mdb_pka_insert(self.h, int(orig_id), float(ekin_erg), dp(d)))
 
     def embed_overruns(self):
         """rho > RHOMX events of the density pass since the last call"""

@@ -146,6 +146,7 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
     cudaSetDevice(c->dev);
     cudaStreamSynchronize(c->stream);
     mdb_dd_free(c);
+    mdb_stopping_free(c);
     mdb_prof_collect(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     free_state(c); free_nlist(c); free_tables(c);

@@ -1,0 +1,259 @@
+// mdb_cascade.cu -- the cascade-physics neighbours of the hot path (BASELINE configs[4]):
+//   * active region by cells   CommonGPU/MD_ActiveRegion_GPU.F90:193-1353  (ActivateRegion_DEV -> ActiveByCells1 -> ActiveByCells0)
+//   * electronic stopping      LocalTempCtrlMeths/Stopping/MD_ST_Coupling_GPU.F90:361-600,787-831  (global-density model)
+//   * primary knock-on atom    Deposition/MD_TypeDef_Projectile.F90 (CP_DEP_STYPE_PKA, CP_EK_STYLE_MONO, lattice / given direction)
+// The force, list and integrator kernels already honour the result: inactive atoms get no force and do not move, and
+// cells without an active atom are skipped by the list builders (NAAC, MD_NeighborsList_GPU.F90:981-982) at the next rebuild.
+//
+// Active region: the reference marks the seed cells on the device, copies the marks to the host, grows them there
+// AR_Extend times over the 27-cell neighbourhood (periodic wrap as the list uses it) and copies them back
+// (:1221-1287).  Here the growth runs on the device (one kernel per extension step over the cells), same marks.
+#include <cstring>
+#include <vector>
+#include "mdb_internal.cuh"
+
+__global__ void k_ar_deactive_all(int n, int *__restrict__ statu) // DeActive_All_Kernel :242-279
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) statu[i] &= ~ST_ACTIVE;
+}
+__global__ void k_ar_active_all(int n, int *__restrict__ statu)   // Active_All_Kernel :334-373
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (statu[i] & ST_OUTOFBOX) != ST_OUTOFBOX) statu[i] |= ST_ACTIVE;
+}
+// CreateSeedByType_Kernel :513-560 and CreateSeedByEkin_Kernel :646-700 in one pass; marks the seed's cell at once
+// (MarkSeedCell_Kernel0 :1001-1045).  cent[t] > 0: atoms of type t+1 are seeds; e0 < 0: no energy criterion.
+__global__ void k_ar_seed_cells(int n, const int *__restrict__ ityp, const int *__restrict__ statu, const double *__restrict__ xp1,
+                                const int *__restrict__ ic, MassParams M, int use_type, const int *__restrict__ cent, int use_ekin,
+                                double e0, int *__restrict__ mark)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((statu[i] & ST_OUTOFBOX) == ST_OUTOFBOX) return;
+    const int t = ityp[i] - 1;
+    bool seed = use_type && cent[t] > 0;
+    if (use_ekin) {
+        const double vx = xp1[i], vy = xp1[i + (size_t)n], vz = xp1[i + 2 * (size_t)n];
+        const double ek = 0.5 * M.cm[t] * (vx * vx + vy * vy + vz * vz); // C_HALF*CM*(...) :688
+        seed = seed || ek >= e0;
+    }
+    const int c = ic[i];
+    if (seed && c > 0) mark[c - 1] = 1;
+}
+// one growth step: a marked cell marks its 27-cell neighbourhood (:1238-1284); src -> dst
+__global__ void k_ar_grow(int nc0, int nbox, int ncx, int ncy, int ncz, int pdx, int pdy, int pdz, const int *__restrict__ src,
+                          int *__restrict__ dst)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc0 * nbox) return;
+    if (src[c] <= 0) return;
+    const int ib = c / nc0, r = c - ib * nc0;
+    const int iz = r / (ncx * ncy), iy = (r - iz * ncx * ncy) / ncx, ix = r - iz * ncx * ncy - iy * ncx;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                int x = ix + dx, y = iy + dy, z = iz + dz;
+                if (x >= ncx) { if (pdx > 0) x = 0; } else if (x < 0) { if (pdx > 0) x = ncx - 1; }
+                if (y >= ncy) { if (pdy > 0) y = 0; } else if (y < 0) { if (pdy > 0) y = ncy - 1; }
+                if (z >= ncz) { if (pdz > 0) z = 0; } else if (z < 0) { if (pdz > 0) z = ncz - 1; }
+                if (x < 0 || x >= ncx || y < 0 || y >= ncy || z < 0 || z >= ncz) continue;
+                dst[ib * nc0 + (z * ncy + y) * ncx + x] = 1;
+            }
+}
+// Active_InCells_Kernel :1085-1127
+__global__ void k_ar_activate(int n, const int *__restrict__ ic, const int *__restrict__ mark, int *__restrict__ statu, int *__restrict__ nact)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int a = 0;
+    if (i < n) {
+        const int c = ic[i];
+        int st = statu[i];
+        if (c > 0 && mark[c - 1] > 0) { st |= ST_ACTIVE; statu[i] = st; }
+        a = (st & ST_ACTIVE) == ST_ACTIVE;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, a);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(nact, __popc(b));
+}
+
+// ActivateRegion_DEV(SimBox, CtrlParam) for the cell method.  method: bit 0 = seeds by atom type (AR_CENTPART), bit 1 = seeds
+// by kinetic energy >= ekin_erg (AR_EKIN, already in erg), bit 2 = KEEP (do not clear the active bits first; CP_KEEP_AR).
+// Uses the cell ids of the last rebuild (INC).  Returns the number of active atoms (>= 0) or < 0.
+extern "C" int mdb_active_region(mdb_ctx *c, int method, const int *centpart, double ekin_erg, int extend)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box || !c->has_nlist || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_active_region: needs a built neighbour list (cell ids)");
+    if ((method & 1) && !centpart) return mdb_fail(c, MDB_ERR_ARG, "mdb_active_region: seeds by type need centpart[ngroup]");
+    if (extend < 0) return mdb_fail(c, MDB_ERR_ARG, "mdb_active_region: negative extension");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_active_region: not available in slab-decomposed runs yet");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    const int n = c->n, nc = c->nc, nb = cdiv(n, 256);
+    cudaStream_t st = c->stream;
+    int *work = nullptr;
+    CUDA_TRY(c, cudaMallocAsync(&work, sizeof(int) * (2 * (size_t)nc + MDB_MXGROUP + 1), st));
+    int *m0 = work, *m1 = work + nc, *cent = work + 2 * (size_t)nc, *nact = cent + MDB_MXGROUP;
+    CUDA_TRY(c, cudaMemsetAsync(work, 0, sizeof(int) * (2 * (size_t)nc + MDB_MXGROUP + 1), st));
+    if (method & 1) CUDA_TRY(c, cudaMemcpyAsync(cent, centpart, sizeof(int) * c->ng, cudaMemcpyHostToDevice, st));
+    ProfScope ps(c, MDB_K_OTHER, 3 + extend);
+    if (!(method & 4)) k_ar_deactive_all<<<nb, 256, 0, st>>>(n, c->statu);       // ActiveByCells1 :1313-1319
+    if (method & 3) {                                                            // no intrinsic seed method: nothing is activated (:1207-1209)
+        k_ar_seed_cells<<<nb, 256, 0, st>>>(n, c->ityp, c->statu, c->xp1, c->ic, c->mass, method & 1, cent, (method & 2) ? 1 : 0, ekin_erg, m0);
+        for (int l = 0; l < extend; l++) {
+            CUDA_TRY(c, cudaMemsetAsync(m1, 0, sizeof(int) * (size_t)nc, st));
+            k_ar_grow<<<cdiv(nc, 256), 256, 0, st>>>(c->nc0, c->nbox, c->ncell[0], c->ncell[1], c->ncell[2], c->box.pd[0], c->box.pd[1],
+                                                    c->box.pd[2], m0, m1);
+            int *t = m0; m0 = m1; m1 = t;
+        }
+    }
+    k_ar_activate<<<nb, 256, 0, st>>>(n, c->ic, m0, c->statu, nact);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + CNT_SCRATCH, nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaFreeAsync(work, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return c->h_counters[CNT_SCRATCH];
+}
+
+extern "C" int mdb_active_all(mdb_ctx *c, int on)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_active_all: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    ProfScope ps(c, MDB_K_OTHER);
+    if (on) k_ar_active_all<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->statu);
+    else k_ar_deactive_all<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->statu);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// electronic stopping, global-density model: ST_MOD_GDEN_KERNEL :431-536
+// ------------------------------------------------------------------------------------
+struct StopParams {
+    int on, ne, nk, ng;
+    int enable[MDB_MXGROUP];
+    double mden[MDB_MXGROUP], cm2[MDB_MXGROUP];
+    int kpair[MDB_MXGROUP * MDB_MXGROUP]; // 1-based table index for (moving type, medium type) at i + ng*j
+};
+
+__global__ void k_stopping(int n, StopParams S, const double *__restrict__ etab, const double *__restrict__ stab,
+                           const int *__restrict__ ityp, const int *__restrict__ statu, const double *__restrict__ xp1,
+                           double *__restrict__ fp, int a0, int a1)
+{
+    const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a1) return;
+    const int kk = ityp[i] - 1;
+    if ((statu[i] & ST_ACTIVE) != ST_ACTIVE || S.enable[kk] <= 0) return;
+    const double vx = xp1[i], vy = xp1[i + (size_t)n], vz = xp1[i + 2 * (size_t)n];
+    double vv = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+    const double ek = __dmul_rn(S.cm2[kk], vv);                                           // EK = CM2(KK)*VV :509
+    const double emin = etab[0], emax = etab[S.ne - 1];
+    if (!(ek >= emin && ek <= emax)) return;                                              // :511
+    const double deinv = __ddiv_rn(1.0, __dsub_rn(etab[1], etab[0]));                      // DEINV :482
+    const int ik = (int)__dmul_rn(__dsub_rn(ek, emin), deinv);                             // 0-based IK-1 :512
+    double ff = 0.0;
+    for (int ig = 0; ig < S.ng; ig++) {                                                   // :516-520
+        const int kp = S.kpair[kk + S.ng * ig] - 1;
+        const double sk = __ddiv_rn(S.mden[ig], __dsub_rn(etab[1], etab[0]));              // SK(IG) = MDEN/(ETAB(2)-ETAB(1)) :487
+        const double s0 = stab[ik + (size_t)S.ne * kp], s1 = stab[ik + 1 + (size_t)S.ne * kp];
+        const double lin = __dadd_rn(__dmul_rn(__dsub_rn(ek, etab[ik]), s1), __dmul_rn(__dsub_rn(etab[ik + 1], ek), s0));
+        ff = __dadd_rn(ff, __dmul_rn(sk, lin));
+    }
+    vv = sqrt(vv);
+    fp[i] = __dsub_rn(fp[i], __ddiv_rn(__dmul_rn(ff, vx), vv));                            // FP = FP - FF*V/|V| :523-525
+    fp[i + (size_t)n] = __dsub_rn(fp[i + (size_t)n], __ddiv_rn(__dmul_rn(ff, vy), vv));
+    fp[i + 2 * (size_t)n] = __dsub_rn(fp[i + 2 * (size_t)n], __ddiv_rn(__dmul_rn(ff, vz), vv));
+}
+
+struct StopState { StopParams P; double *etab = nullptr, *stab = nullptr; };
+static StopState *stop_of(mdb_ctx *c) { return reinterpret_cast<StopState *>(c->stop_state); }
+
+// Initialize_STMOD_DEV + Reset_STMOD_DEV (:334-427): the E-S tables of the stopping library (ETAB(NE) in erg, STAB(NE,NK) in
+// erg*cm^2, as Stop_Srim / Stop_Z85 / Stop_Z95 / Stop_B fill them), KPAIR(NG,NG) column-major 1-based, per-type switch and the
+// number density of every medium type (MDEN, atoms per cm^3; <= 0: atoms of the box / box volume * NA/NPRT as :379-383)
+extern "C" int mdb_stopping_set(mdb_ctx *c, int ne, int nk, const double *etab, const double *stab, const int *kpair, const int *enable,
+                                const double *mden)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_stopping_set: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    StopState *S = stop_of(c);
+    if (S) { cudaFree(S->etab); cudaFree(S->stab); delete S; c->stop_state = nullptr; }
+    if (ne < 2 || nk < 1 || !etab || !stab || !kpair || !enable) return MDB_OK; // switched off
+    S = new StopState();
+    memset(&S->P, 0, sizeof(S->P));
+    S->P.ne = ne; S->P.nk = nk; S->P.ng = c->ng;
+    for (int g = 0; g < c->ng; g++) {
+        S->P.enable[g] = enable[g];
+        S->P.cm2[g] = 0.5 * c->mass.cm[g];
+        S->P.mden[g] = mden ? mden[g] : 0.0;
+        if (enable[g] > 0) S->P.on = 1;
+        for (int h = 0; h < c->ng; h++) {
+            const int k = kpair[g + c->ng * h];
+            if (k < 1 || k > nk) { delete S; return mdb_fail(c, MDB_ERR_ARG, "mdb_stopping_set: KPAIR(%d,%d) = %d outside 1..%d", g + 1, h + 1, k, nk); }
+            S->P.kpair[g + c->ng * h] = k;
+        }
+    }
+    CUDA_TRY(c, cudaMalloc(&S->etab, sizeof(double) * ne));
+    CUDA_TRY(c, cudaMalloc(&S->stab, sizeof(double) * (size_t)ne * nk));
+    CUDA_TRY(c, cudaMemcpyAsync(S->etab, etab, sizeof(double) * ne, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(S->stab, stab, sizeof(double) * (size_t)ne * nk, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stop_state = S;
+    return MDB_OK;
+}
+
+// Do_STMOD_Force_DEV (:787-831): to be called after the force and the EPC friction (Do_EPCForce_DEV :135-136)
+int mdb_stopping_launch(mdb_ctx *c)
+{
+    StopState *S = stop_of(c);
+    if (!S || !S->P.on) return MDB_OK; // hm_NEEDDO = .false.
+    ProfScope ps(c, MDB_K_CORRECT);
+    k_stopping<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, S->P, S->etab, S->stab, c->ityp, c->statu, c->xp1, c->fp,
+                                                                      own_a0(c), own_a1(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+bool mdb_stopping_on(const mdb_ctx *c)
+{
+    const StopState *S = reinterpret_cast<const StopState *>(c->stop_state);
+    return S && S->P.on;
+}
+void mdb_stopping_free(mdb_ctx *c)
+{
+    StopState *S = stop_of(c);
+    if (S) { cudaFree(S->etab); cudaFree(S->stab); delete S; }
+    c->stop_state = nullptr;
+}
+extern "C" int mdb_stopping_apply(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_stopping_apply: mdb_box_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    return mdb_stopping_launch(c);
+}
+
+// ------------------------------------------------------------------------------------
+// primary knock-on atom: the velocity of ONE atom is replaced by sqrt(2 EK / m) along a direction
+// (internal deposition of MD_TypeDef_Projectile.F90: DEPSTYLE = CP_DEP_STYPE_PKA, EKSTYPE = CP_EK_STYLE_MONO)
+// ------------------------------------------------------------------------------------
+__global__ void k_pka(int n, int orig, const int *__restrict__ gidinv, const int *__restrict__ ityp, MassParams M, double ek,
+                      double dx, double dy, double dz, double *__restrict__ xp1, int *__restrict__ statu)
+{
+    const int s = gidinv[orig - 1] - 1;
+    const double v = sqrt(2.0 * ek / M.cm[ityp[s] - 1]);
+    xp1[s] = v * dx; xp1[s + (size_t)n] = v * dy; xp1[s + 2 * (size_t)n] = v * dz;
+    statu[s] |= ST_ACTIVE;
+}
+extern "C" int mdb_pka_insert(mdb_ctx *c, int orig_id, double ekin_erg, const double dir[3])
+{
+    if (!c || !dir) return mdb_fail(c, MDB_ERR_ARG, "mdb_pka_insert: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_pka_insert: mdb_box_set first");
+    if (orig_id < 1 || orig_id > c->n || !(ekin_erg >= 0.0)) return mdb_fail(c, MDB_ERR_ARG, "mdb_pka_insert: bad atom id / energy");
+    const double d = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    if (!(d > 0.0)) return mdb_fail(c, MDB_ERR_ARG, "mdb_pka_insert: zero direction");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    ProfScope ps(c, MDB_K_OTHER);
+    k_pka<<<1, 1, 0, c->stream>>>(c->n, orig_id, c->gidinv, c->ityp, c->mass, ekin_erg, dir[0] / d, dir[1] / d, dir[2] / d, c->xp1, c->statu);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}

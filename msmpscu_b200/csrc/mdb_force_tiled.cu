@@ -315,8 +315,12 @@ k_tile_nlist(TileParams P, TileListArgs A)
     const int myhc = 4 * nhx + cw + 1;             // centre row (hy = hz = 1), cell hx = cw + 1
     const int ccnt = H.cnt[myhc];
     if (ccnt <= 0) return;                         // :1018
-    if (A.naac[H.cid[myhc]] <= 0) return;          // cells without ACTIVE atoms are skipped (:981-982)
     const int cgst = H.gst[myhc], csl = H.slot[myhc];
+    if (A.naac[H.cid[myhc]] <= 0) {                // cells without ACTIVE atoms are skipped (:981-982): empty lists
+        if (!half)
+            for (int a = lane; a < ccnt; a += 32) { A.kvois[cgst + a] = 0; A.ncls[cgst + a] = 0; A.ncls[cgst + a + P.npad] = 0; }
+        return;
+    }
     const float rm1 = A.rm2[0], rc0 = A.rc2[0], rc1 = A.rc2[1];
     unsigned short *col0 = lists + (size_t)cw * A.lcap * 32 + lane;    // entry k of this lane at col0[k * 32]
     unsigned short *col = col0;

@@ -143,6 +143,7 @@ struct mdb_ctx {
 
     // ---- epc
     EpcParams epc;
+    void *stop_state = nullptr; // electronic stopping tables and switches (mdb_cascade.cu)
 
     // ---- host copies of the pair tables (Fortran layout) for planning the tiled path
     std::vector<double> h_potb, h_fpotr, h_fpotb, h_potr;
@@ -229,5 +230,8 @@ int mdb_cells_dd_ghost_layer(mdb_ctx *c, int c0, int first);
 int mdb_predict_launch(mdb_ctx *c, double h, int pre);    // mdb_step.cu
 int mdb_epc_correct_launch(mdb_ctx *c, double h);
 void mdb_dd_free(mdb_ctx *c);                 // mdb_dd.cu
+int mdb_stopping_launch(mdb_ctx *c);          // mdb_cascade.cu : electronic stopping on FP (no-op when switched off)
+bool mdb_stopping_on(const mdb_ctx *c);
+void mdb_stopping_free(mdb_ctx *c);
 static inline int own_a0(const mdb_ctx *c) { return c->dd_on ? c->dd_info[0] : 0; }
 static inline int own_a1(const mdb_ctx *c) { return c->dd_on ? c->dd_info[1] : c->n; }             // mdb_api.cu : cells + list kernel of the active path (no sync)

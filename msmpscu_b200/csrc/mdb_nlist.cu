@@ -37,9 +37,13 @@ k_nlist_cellwarp(NlistParams P, const double4 *__restrict__ pos, const int *__re
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int ic0 = blockIdx.x * NL_WARPS + wib;
     if (ic0 >= P.nc) return;
-    if (naac[ic0] <= 0) return; // cells without ACTIVE atoms are skipped :981-982
     const int na = nac[ic0];
     if (na <= 0) return;        // :1018
+    if (naac[ic0] <= 0) {       // cells without ACTIVE atoms are skipped :981-982 (their atoms keep no list: KVOIS = 0 here, where the
+                                // reference leaves the counts of an earlier build behind; such atoms never read their list)
+        for (int a = lane; a < na; a += 32) kvois[ia1th[ic0] - 1 + a] = 0;
+        return;
+    }
     const int is0 = ic0 / P.nc0, icl = ic0 - is0 * P.nc0;
     const int ncxy = P.ncx * P.ncy;
     const int iz0 = icl / ncxy, iy0 = (icl - iz0 * ncxy) / P.ncx, ix0 = icl - iz0 * ncxy - iy0 * P.ncx;

@@ -468,8 +468,11 @@ extern "C" int mdb_atomic_stress(mdb_ctx *c, double *d_avp)
 static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h, bool first, bool last)
 {
     int rc;
-    const bool fused_epilogue = c->opt_fuse_epilogue && c->tiled.active && c->has_tables && c->shape_identity;
-    if ((rc = predict_launch(c, h, (first || fused_epilogue) ? 0 : 3)) < 0) return rc;
+    // electronic stopping (Do_STMOD_DEV) acts on FP between the EPC friction and the corrector (Do_EPCForce_DEV,
+    // MD_LocalTempMethod_GPU.F90:135-136): with it the three stages run unfused at the end of every step
+    const bool stopping = mdb_stopping_on(c);
+    const bool fused_epilogue = !stopping && c->opt_fuse_epilogue && c->tiled.active && c->has_tables && c->shape_identity;
+    if ((rc = predict_launch(c, h, (first || fused_epilogue || stopping) ? 0 : 3)) < 0) return rc;
     if (nb_uptab > 0 && (itime - it0) % nb_uptab == 0) { // MOD(ITIME-IT0,NB_UPTAB)==0, GenericMD:599-601
         // the capacity counters are read back at once (a 48-byte copy and a synchronisation per list period): an overflow of
         // the tiled path is redone on the generic path before any force is evaluated on the new list
@@ -480,6 +483,18 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h, b
         return mdb_force_tiled(c, MDB_FORCE, 3, h * 0.5);
     }
     if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
+    if (stopping) {
+        {
+            ProfScope ps(c, MDB_K_CORRECT);
+            if (c->epc.on)
+                k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, 0.0, 1, 0, 0, c->n);
+        }
+        if ((rc = mdb_stopping_launch(c)) < 0) return rc;
+        ProfScope ps(c, MDB_K_CORRECT);
+        k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, h * 0.5, 0, 1, 0, c->n);
+        CUDA_TRY(c, cudaGetLastError());
+        return MDB_OK;
+    }
     if (!last) return MDB_OK; // applied by the next step's predictor kernel
     ProfScope ps(c, MDB_K_CORRECT);
     k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
