@@ -22,6 +22,8 @@ struct ForceParams {
     const double2 *potr, *fpotr, *potb, *fpotb, *fembd, *dfembd;
     const int *skip; // device flag: the kernel returns at once when it is set (converged quench iterations)
     int *counters;
+    int identity;   // BOXSHAPE is the unit matrix
+    double bs[9];   // BOXSHAPE, column-major
     int kpair[MDB_MXGROUP * MDB_MXGROUP];
     int kembd[MDB_MXGROUP];
 };
@@ -38,6 +40,17 @@ __device__ __forceinline__ void min_image(double &s, double size, double half, i
 {
     // if(IFPD.GT.0 .AND. DABS(SEP).GT.HB) SEP = SEP - DSIGN(B,SEP)   :500-510
     if (pd > 0 && fabs(s) > half) s = s - copysign(size, s);
+}
+
+// DXYZ = BOXSHAPE * SEP (MD_EAM_ForceTable_GPU.F90:515-517); column-major bs
+__device__ __forceinline__ void box_shape(const ForceParams &P, double sx, double sy, double sz, double &dx, double &dy, double &dz)
+{
+    dx = sx; dy = sy; dz = sz;
+    if (!P.identity) {
+        dx = P.bs[0] * sx + P.bs[3] * sy + P.bs[6] * sz;
+        dy = P.bs[1] * sx + P.bs[4] * sy + P.bs[7] * sz;
+        dz = P.bs[2] * sx + P.bs[5] * sy + P.bs[8] * sz;
+    }
 }
 
 __device__ __forceinline__ double lerp_tab(const double2 *__restrict__ t, int stride, int k, int kk, double dk)
@@ -77,7 +90,9 @@ k_pass1_generic(ForceParams P, double4 *__restrict__ pos, const int *__restrict_
             min_image(sx, P.box.size[0], P.box.half[0], P.box.pd[0]);
             min_image(sy, P.box.size[1], P.box.half[1], P.box.pd[1]);
             min_image(sz, P.box.size[2], P.box.half[2], P.box.pd[2]);
-            const double r2 = sx * sx + sy * sy + sz * sz;
+            double dx, dy, dz;
+            box_shape(P, sx, sy, sz, dx, dy, dz);
+            const double r2 = dx * dx + dy * dy + dz * dz;
             if (r2 <= P.ru2max) { // :522
                 const int kt = (P.ng == 1) ? P.kpair[0] : P.kpair[ti + P.ng * (ityp[j] - 1)];
                 const double r = sqrt(r2);
@@ -121,7 +136,10 @@ k_pass2_generic(ForceParams P, const double4 *__restrict__ pos, const int *__res
             min_image(sx, P.box.size[0], P.box.half[0], P.box.pd[0]);
             min_image(sy, P.box.size[1], P.box.half[1], P.box.pd[1]);
             min_image(sz, P.box.size[2], P.box.half[2], P.box.pd[2]);
-            const double r2 = sx * sx + sy * sy + sz * sz;
+            // the force-only kernel ignores BOXSHAPE (:775); the virial variant applies it (:1171-1174)
+            double dx = sx, dy = sy, dz = sz;
+            if (VIR) box_shape(P, sx, sy, sz, dx, dy, dz);
+            const double r2 = dx * dx + dy * dy + dz * dz;
             if (r2 <= P.ru2max) {
                 int k0 = P.kpair[0], k1 = k0;
                 if (P.ng > 1) {
@@ -141,11 +159,11 @@ k_pass2_generic(ForceParams P, const double4 *__restrict__ pos, const int *__res
                 fx = fx + fortot * sx;
                 fy = fy + fortot * sy;
                 fz = fz + fortot * sz;
-                if (VIR) { // :1222-1232 (identity BOXSHAPE: DXYZ = SEP)
+                if (VIR) { // :1222-1232
                     fortot = fortot * 0.5;
-                    v[0] += sx * sx * fortot; v[3] += sx * sy * fortot; v[6] += sx * sz * fortot;
-                    v[1] += sy * sx * fortot; v[4] += sy * sy * fortot; v[7] += sy * sz * fortot;
-                    v[2] += sz * sx * fortot; v[5] += sz * sy * fortot; v[8] += sz * sz * fortot;
+                    v[0] += dx * dx * fortot; v[3] += dx * dy * fortot; v[6] += dx * dz * fortot;
+                    v[1] += dy * dx * fortot; v[4] += dy * dy * fortot; v[7] += dy * dz * fortot;
+                    v[2] += dz * dx * fortot; v[5] += dz * dy * fortot; v[8] += dz * dz * fortot;
                 }
             }
         }
@@ -210,7 +228,9 @@ k_epot_generic(ForceParams P, const double4 *__restrict__ pos, const int *__rest
             min_image(sx, P.box.size[0], P.box.half[0], P.box.pd[0]);
             min_image(sy, P.box.size[1], P.box.half[1], P.box.pd[1]);
             min_image(sz, P.box.size[2], P.box.half[2], P.box.pd[2]);
-            const double r2 = sx * sx + sy * sy + sz * sz;
+            double dx, dy, dz;
+            box_shape(P, sx, sy, sz, dx, dy, dz);
+            const double r2 = dx * dx + dy * dy + dz * dz;
             if (r2 <= P.ru2max) {
                 const int kt = (P.ng == 1) ? P.kpair[0] : P.kpair[ti + P.ng * (ityp[j] - 1)];
                 const double r = sqrt(r2);
@@ -249,7 +269,9 @@ k_avstress_generic(ForceParams P, const double4 *__restrict__ pos, const int *__
             min_image(sx, P.box.size[0], P.box.half[0], P.box.pd[0]);
             min_image(sy, P.box.size[1], P.box.half[1], P.box.pd[1]);
             min_image(sz, P.box.size[2], P.box.half[2], P.box.pd[2]);
-            const double r2 = sx * sx + sy * sy + sz * sz; // identity BOXSHAPE: DXYZ = SEP
+            double dx, dy, dz;
+            box_shape(P, sx, sy, sz, dx, dy, dz); // :1861-1864
+            const double r2 = dx * dx + dy * dy + dz * dz;
             if (r2 <= P.ru2max) {
                 int k0 = P.kpair[0], k1 = k0;
                 if (P.ng > 1) {
@@ -264,9 +286,9 @@ k_avstress_generic(ForceParams P, const double4 *__restrict__ pos, const int *__
                 const double fortot = lerp_tab(P.fpotr, P.ntab + 2, k0, kk, dk) / r2 +
                                       (lerp_tab(P.fpotb, P.ntab + 2, k0, kk, dk) * denki +
                                        lerp_tab(P.fpotb, P.ntab + 2, k1, kk, dk) * pj.w) / r; // :1877-1880
-                p[0] = p[0] + sx * sx * fortot; p[1] = p[1] + sx * sy * fortot; p[2] = p[2] + sx * sz * fortot;
-                p[3] = p[3] + sy * sx * fortot; p[4] = p[4] + sy * sy * fortot; p[5] = p[5] + sy * sz * fortot;
-                p[6] = p[6] + sz * sx * fortot; p[7] = p[7] + sz * sy * fortot; p[8] = p[8] + sz * sz * fortot;
+                p[0] = p[0] + dx * dx * fortot; p[1] = p[1] + dx * dy * fortot; p[2] = p[2] + dx * dz * fortot;
+                p[3] = p[3] + dy * dx * fortot; p[4] = p[4] + dy * dy * fortot; p[5] = p[5] + dy * dz * fortot;
+                p[6] = p[6] + dz * dx * fortot; p[7] = p[7] + dz * dy * fortot; p[8] = p[8] + dz * dz * fortot;
             }
         }
     }
@@ -309,6 +331,8 @@ static void fill_params(mdb_ctx *c, ForceParams &P)
     P.csi = t.csi; P.rhod = t.rhod; P.ru2max = t.ru2max;
     P.skip = c->skip_flag;
     P.counters = c->counters;
+    P.identity = c->shape_identity ? 1 : 0;
+    for (int i = 0; i < 9; i++) P.bs[i] = c->boxshape[i];
     P.potr = t.potr; P.fpotr = t.fpotr; P.potb = t.potb; P.fpotb = t.fpotb; P.fembd = t.fembd; P.dfembd = t.dfembd;
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) P.kpair[i] = t.kpair[i];
     for (int i = 0; i < MDB_MXGROUP; i++) P.kembd[i] = t.kembd[i];

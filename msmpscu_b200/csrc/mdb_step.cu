@@ -432,7 +432,6 @@ extern "C" int mdb_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     if (!c) return MDB_ERR_ARG;
     if (!c->has_box || !c->has_tables) return mdb_fail(c, MDB_ERR_STATE, "mdb_force: box and tables must be set");
     if (!c->has_nlist || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_force: no valid neighbour list (mdb_nlist_build)");
-    if (!c->shape_identity) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_force: non-identity BOXSHAPE is not supported yet");
     if ((flags & MDB_VIRIAL) && !vtensor) return mdb_fail(c, MDB_ERR_ARG, "mdb_force: MDB_VIRIAL needs vtensor");
     CUDA_TRY(c, cudaSetDevice(c->dev));
     if (c->dd_on && !c->tiled.active)

@@ -197,3 +197,45 @@ def test_cpp_host_replays_the_fortran_shim_call_sequence(tmp_path):
     assert int(scal[1]) == int(kv.sum())
     assert ctx.embed_overruns() == 0          # a thermal crystal never leaves the embedding table
     ctx.close()
+
+
+def test_non_identity_boxshape_on_the_generic_path(oracle):
+    """A sheared / strained BOXSHAPE (pressure-coupled boxes): the list kernel (fp32, :1117-1119), the density pass, the
+    virial kernel and the energy kernel apply it, the force-only kernel does not (MD_EAM_ForceTable_GPU.F90:515-518,775,
+    1171-1174) -- the tiled path declines such boxes and AUTO runs the generic kernels; forcing TILED is refused."""
+    c = util.bcc_case((7, 8, 9), seed=21)
+    bs = np.array([[1.0, 0.02, 0.0], [0.0, 1.0, 0.01], [0.0, 0.0, 0.99]])
+    ctx = capi.Context(0)
+    ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass, boxshape=bs)
+    for f, a in ((capi.F_XP, c.xp), (capi.F_XP1, c.xp1), (capi.F_ITYP, c.ityp), (capi.F_STATU, c.statu)):
+        ctx.upload(f, a)
+    ctx.tables_set(util.product_tables(c), c.ru * c.ru)
+    ctx.nlist_init(c.nb_rm, c.mxkvois)
+    ctx.nlist_build()
+    assert ctx.get_option(capi.OPT_ACTIVE_PATH) == capi.FORCE_PATH_GENERIC
+    nbr = np.ascontiguousarray(c.nb_rm.T).ravel()
+    ref = oracle.nlist_build_dev(c.nbox, c.napb, c.xp, c.ityp, c.statu, c.boxlow, c.zl, c.ifpd, nbr, c.mxkvois, boxshape=bs)
+    ident = oracle.nlist_build_dev(c.nbox, c.napb, c.xp, c.ityp, c.statu, c.boxlow, c.zl, c.ifpd, nbr, c.mxkvois)
+    assert not np.array_equal(ref["kvois"], ident["kvois"])          # the shape does change the lists of this case
+    kv, ind = ctx.nlist_copyout(capi.ORDER_CELL)
+    assert np.array_equal(kv, ref["kvois"])
+    for w in range(int(kv.max())):
+        assert np.array_equal(ind[w][kv > w], ref["indi"][w][kv > w])
+    gid = ref["gid"] - 1
+    T = util.oracle_tables(oracle, c)
+    args = (c.xp[gid], c.ityp[gid], ref["statu"][gid], ref["kvois"], ref["indi"], c.zl, c.ifpd, T)
+    fp, den, _, ep = oracle.force(*args, epot=True, boxshape=bs)
+    fpv, _, vt, _ = oracle.force(*args, virial=True, boxshape=bs)
+    ctx.force(capi.FORCE | capi.EPOT)
+    assert util.atom_relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fp) < TOL
+    assert util.atom_relerr(ctx.download(capi.F_DEN, capi.ORDER_CELL), den) < TOL
+    assert util.atom_relerr(ctx.download(capi.F_EPOT, capi.ORDER_CELL), ep) < TOL
+    v = ctx.force(capi.FORCE | capi.VIRIAL)
+    assert util.relerr(v, vt) < TOL
+    assert util.atom_relerr(ctx.download(capi.F_FP, capi.ORDER_CELL), fpv) < TOL   # CALPTENSOR's forces (r2 through the shape)
+    ctx.run(0, 12, 1, 10, 0.5e-15)                                    # steps run on such a box
+    ctx.set_option(capi.OPT_FORCE_PATH, capi.FORCE_PATH_TILED)
+    with pytest.raises(capi.MDBError) as e:
+        ctx.nlist_build()
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    ctx.close()
