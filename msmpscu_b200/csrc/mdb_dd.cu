@@ -25,6 +25,7 @@
 // of all ranks living in one process on one stream.  The host waits twice per rebuild (sizes of the exchanged ranges).
 #include <dlfcn.h>
 #include <nccl.h>
+#include <cstdlib>
 #include <cstring>
 #include "mdb_internal.cuh"
 
@@ -115,8 +116,10 @@ extern "C" int mdb_dd_local_attach(mdb_ctx **ctxs, int nranks)
     return MDB_OK;
 }
 
+static void p2p_free(mdb_ctx *c);
 void mdb_dd_free(mdb_ctx *c)
 {
+    p2p_free(c);
     if (c->dd_comm && nccl().CommDestroy) nccl().CommDestroy((ncclComm_t)c->dd_comm);
     c->dd_comm = nullptr;
     if (c->dd_dev) cudaFree(c->dd_dev);
@@ -242,6 +245,153 @@ static int dd_publish_d2max(mdb_ctx *c)
     return MDB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------
+// Peer-to-peer ghost exchange of the step loop (NCCL backend, same node): the boundary layers are written straight into
+// the neighbours' position arrays over NVLink (CUDA IPC mappings, copy engines), ordered by flags in device memory.
+// An ncclSend/ncclRecv group costs ~0.12 ms per exchange here (launch + rendezvous latency, 20 exchanges per list period);
+// the direct form is two copies and two one-thread handshake kernels.  Protocol of exchange number e (all ranks issue the
+// same sequence of exchanges):
+//   handshake 1  tell both neighbours "everything I read from you up to exchange e-1 is consumed" (all earlier kernels of
+//                this stream have finished), wait for the same word from both      -> their ghost ranges may be overwritten
+//   push         cudaMemcpyAsync of my bottom / top layer into the neighbour's array (same global slots there)
+//   handshake 2  publish "exchange e has landed" (+ my max displacement since the rebuild) in both neighbours' flags, wait
+//                for theirs, merge their displacement bound into mine
+// Flags are monotonic counters, written with system-scope fences; a wait gives up after ~seconds and raises an error
+// counter instead of hanging the device.  The rebuild's own exchanges (sizes known to the host only then) stay on NCCL.
+// MDB_DD_P2P=0 in the environment keeps everything on NCCL.
+// ------------------------------------------------------------------------------------
+struct P2PState {
+    bool on = false;
+    int epoch = 0, buf = 0;            // buf: which of the two position buffers is the current one (toggles at a local rebuild)
+    double4 *my_pos[2] = {nullptr, nullptr};
+    double4 *peer_pos[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; // [0 = rank below, 1 = rank above][buffer]
+    int *peer_flags[2] = {nullptr, nullptr};
+    int *flags = nullptr;              // mine: [0,1] arrive from below / above, [2,3] ack from below / above, [4,5] d2max of below / above, [6] errors
+    void *opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+static P2PState *p2p_of(mdb_ctx *c) { return reinterpret_cast<P2PState *>(c->dd_p2p); }
+
+#define P2P_SPIN_LIMIT 20000000LL
+// word `slot` of both neighbours := val (and optionally my displacement bound next to it), then wait until both of MY
+// words `mine0`, `mine1` have reached val
+__global__ void k_p2p_handshake(int *peer_lo, int *peer_hi, int slot_lo, int slot_hi, int val, volatile int *flags, int mine0, int mine1,
+                                int *counters, int with_d2)
+{
+    if (with_d2) { peer_lo[5] = counters[CNT_D2MAX]; peer_hi[4] = counters[CNT_D2MAX]; } // I am "above" the rank below me, "below" the rank above
+    __threadfence_system();
+    *(volatile int *)(peer_lo + slot_lo) = val;
+    *(volatile int *)(peer_hi + slot_hi) = val;
+    long long spins = 0;
+    while ((flags[mine0] < val || flags[mine1] < val) && ++spins < P2P_SPIN_LIMIT) { }
+    if (spins >= P2P_SPIN_LIMIT) atomicAdd((int *)flags + 6, 1);
+    __threadfence_system();
+    if (with_d2) atomicMax(&counters[CNT_D2MAX], max(flags[4], flags[5]));
+}
+
+static void p2p_free(mdb_ctx *c)
+{
+    P2PState *S = p2p_of(c);
+    if (!S) return;
+    for (void *p : S->opened) if (p) cudaIpcCloseMemHandle(p);
+    if (S->flags) cudaFree(S->flags);
+    delete S;
+    c->dd_p2p = nullptr;
+}
+
+// after the first build: export my two position buffers and my flags, import the neighbours'
+static int p2p_init(mdb_ctx *c)
+{
+    p2p_free(c);
+    const char *env = getenv("MDB_DD_P2P");
+    if (env && atoi(env) == 0) return MDB_OK;
+    if (!c->dd_comm) return MDB_OK;
+    P2PState *S = new P2PState();
+    c->dd_p2p = S;
+    auto give_up = [&](const char *why) { (void)why; p2p_free(c); cudaGetLastError(); return (int)MDB_OK; };
+    if (cudaMalloc(&S->flags, 64 * sizeof(int)) != cudaSuccess) return give_up("flags");
+    cudaMemsetAsync(S->flags, 0, 64 * sizeof(int), c->stream);
+    S->my_pos[0] = c->pos; S->my_pos[1] = c->pos_alt;
+    cudaIpcMemHandle_t mine[3], theirs[2][3];
+    int ok = 1;
+    if (cudaIpcGetMemHandle(&mine[0], c->pos) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], c->pos_alt) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine[2], S->flags) != cudaSuccess) { ok = 0; cudaGetLastError(); memset(mine, 0, sizeof(mine)); }
+    // handles travel over the communicator that already exists (device staging: NCCL moves device memory)
+    char *d = nullptr;
+    const size_t hb = sizeof(mine);
+    if (cudaMalloc(&d, 3 * hb + 16) != cudaSuccess) return give_up("staging");
+    int *dok = reinterpret_cast<int *>(d + 3 * hb);
+    cudaMemcpyAsync(d, mine, hb, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream);
+    NcclApi &N = nccl();
+    ncclComm_t comm = (ncclComm_t)c->dd_comm;
+    const int below = c->dd_info[10], above = c->dd_info[11];
+    NCCL_TRY(c, N.GroupStart());
+    NCCL_TRY(c, N.Send(d, hb, ncclChar, below, comm, c->stream));
+    NCCL_TRY(c, N.Send(d, hb, ncclChar, above, comm, c->stream));
+    NCCL_TRY(c, N.Recv(d + 2 * hb, hb, ncclChar, above, comm, c->stream));   // (first receive = from above: see dd_exchange)
+    NCCL_TRY(c, N.Recv(d + hb, hb, ncclChar, below, comm, c->stream));
+    NCCL_TRY(c, N.GroupEnd());
+    // every rank must take the same decision: all-reduce (min) of "my exports worked"
+    NCCL_TRY(c, N.AllReduce(dok, dok, 1, ncclInt, ncclMin, comm, c->stream));
+    cudaMemcpyAsync(theirs[0], d + hb, hb, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(theirs[1], d + 2 * hb, hb, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (!ok) return give_up("export");
+    int opened_ok = 1;
+    for (int dir = 0; dir < 2 && opened_ok; dir++) {
+        if (dir == 1 && below == above) { // two ranks: both neighbours are the same process, a handle may be opened once only
+            S->peer_pos[1][0] = S->peer_pos[0][0]; S->peer_pos[1][1] = S->peer_pos[0][1]; S->peer_flags[1] = S->peer_flags[0];
+            break;
+        }
+        void *p[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3; k++) {
+            if (cudaIpcOpenMemHandle(&p[k], theirs[dir][k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened_ok = 0; cudaGetLastError(); break; }
+            S->opened[3 * dir + k] = p[k];
+        }
+        S->peer_pos[dir][0] = (double4 *)p[0]; S->peer_pos[dir][1] = (double4 *)p[1]; S->peer_flags[dir] = (int *)p[2];
+    }
+    // again a common decision
+    int *d2 = nullptr;
+    if (cudaMalloc(&d2, sizeof(int)) != cudaSuccess) return give_up("staging");
+    cudaMemcpyAsync(d2, &opened_ok, sizeof(int), cudaMemcpyHostToDevice, c->stream);
+    NCCL_TRY(c, N.AllReduce(d2, d2, 1, ncclInt, ncclMin, comm, c->stream));
+    cudaMemcpyAsync(&opened_ok, d2, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d2);
+    if (!opened_ok) return give_up("open");
+    S->on = true; S->epoch = 0; S->buf = 0;
+    return MDB_OK;
+}
+
+static int p2p_exchange(mdb_ctx *c, bool with_d2max)
+{
+    P2PState *S = p2p_of(c);
+    const XRanges R = atom_ranges(c);
+    const int e = ++S->epoch;
+    ProfScope ps(c, MDB_K_EXCHANGE, 2);
+    // handshake 1: acks of exchange e-1 (word 3 of the rank below = "the rank above me consumed", word 2 of the rank above)
+    k_p2p_handshake<<<1, 1, 0, c->stream>>>(S->peer_flags[0], S->peer_flags[1], 3, 2, e - 1, S->flags, 2, 3, c->counters, 0);
+    double4 *lo = S->peer_pos[0][S->buf], *hi = S->peer_pos[1][S->buf];
+    if (R.sb1 > R.sb0) CUDA_TRY(c, cudaMemcpyAsync(lo + R.sb0, c->pos + R.sb0, sizeof(double4) * (size_t)(R.sb1 - R.sb0), cudaMemcpyDefault, c->stream));
+    if (R.st1 > R.st0) CUDA_TRY(c, cudaMemcpyAsync(hi + R.st0, c->pos + R.st0, sizeof(double4) * (size_t)(R.st1 - R.st0), cudaMemcpyDefault, c->stream));
+    // handshake 2: arrival of exchange e (word 1 of the rank below = "from above", word 0 of the rank above = "from below")
+    k_p2p_handshake<<<1, 1, 0, c->stream>>>(S->peer_flags[0], S->peer_flags[1], 1, 0, e, S->flags, 0, 1, c->counters, with_d2max ? 1 : 0);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+static int p2p_check(mdb_ctx *c)
+{
+    P2PState *S = p2p_of(c);
+    if (!S || !S->on) return MDB_OK;
+    int err = 0;
+    CUDA_TRY(c, cudaMemcpy(&err, S->flags + 6, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) return mdb_fail(c, MDB_ERR_STATE, "slab decomposition: a neighbour rank did not answer a ghost exchange (%d time-outs)", err);
+    return MDB_OK;
+}
+
 // runs one phase on this rank (NCCL backend) or on every rank of the process (in-process backend)
 template <class F>
 static int all_ranks(mdb_ctx *c, F f)
@@ -258,6 +408,7 @@ static int x_pos(mdb_ctx *c, bool with_d2max)
 {
     const int f[1] = {DF_POS};
     int rc = MDB_OK;
+    if (P2PState *S = p2p_of(c); S && S->on) return p2p_exchange(c, with_d2max);
     if (with_d2max && (rc = all_ranks(c, [](mdb_ctx *p) { return dd_publish_d2max(p); })) < 0) return rc;
     return all_ranks(c, [&](mdb_ctx *p) { return dd_exchange(p, f, 1, atom_ranges(p), with_d2max); });
 }
@@ -343,6 +494,7 @@ static int dd_local_rebuild(mdb_ctx *c)
             const int r = p->dd_rank, below = (r - 1 + R) % R, above = (r + 1) % R;
             int rc2 = mdb_cells_dd_place(p, cand, p->dd_info[12] / cl, p->dd_info[13] / cl, base[r], t[4 * r]);
             if (rc2 < 0) return rc2;
+            if (P2PState *S = p2p_of(p)) S->buf ^= 1; // the position buffers were swapped
             int *d = p->dd_info;
             d[0] = base[r]; d[1] = base[r + 1];
             d[2] = base[below + 1] - t[4 * below + 2]; d[3] = base[below + 1];   // top layer of the rank below
@@ -391,7 +543,11 @@ extern "C" int mdb_dd_build(mdb_ctx *c)
     if (!c->dd_on) return mdb_fail(c, MDB_ERR_STATE, "mdb_dd_build: mdb_dd_set first");
     if (!c->has_nlist || !c->has_tables) return mdb_fail(c, MDB_ERR_STATE, "mdb_dd_build: tables and list must be set");
     CUDA_TRY(c, cudaSetDevice(c->dev));
-    if (!c->dd_built || !c->list_valid) return all_ranks(c, [](mdb_ctx *p) { return dd_first_build(p); });
+    if (!c->dd_built || !c->list_valid) {
+        int rc = all_ranks(c, [](mdb_ctx *p) { return dd_first_build(p); });
+        if (rc < 0) return rc;
+        return p2p_init(c); // (NCCL backend only; falls back to NCCL exchanges when IPC mappings are not available)
+    }
     return dd_local_rebuild(c);
 }
 
@@ -457,7 +613,7 @@ extern "C" int mdb_dd_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_up
     }
     if (nsteps > 0 && (rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_epc_correct_launch(p, h); })) < 0) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    return MDB_OK;
+    return p2p_check(c);
 }
 
 // Cal_GlobalT_DEV (CommonGPU/MD_DiffScheme_GPU.F90:1042-1064) on the decomposed box: EKIN of the owned atoms of every rank

@@ -159,6 +159,7 @@ struct mdb_ctx {
     // backend of the library-level decomposed run (mdb_dd.cu): NCCL communicator (one process per GPU) or, for single-GPU
     // tests, the contexts of all ranks in this process (same device, same stream: exchanges are device-to-device copies)
     void *dd_comm = nullptr;
+    void *dd_p2p = nullptr;     // peer-to-peer ghost exchange state (CUDA IPC mappings of the neighbours' arrays)
     std::vector<mdb_ctx *> dd_peers;
     int *dd_dev = nullptr;      // device: per rank {owned atoms, bottom-layer atoms, top-layer atoms, max atoms per cell}, then scratch
     bool dd_built = false;      // the initial replicated build is done: later rebuilds sort owned + ghost atoms only
