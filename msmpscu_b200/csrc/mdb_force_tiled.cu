@@ -832,9 +832,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
                     const double r2 = fma(sz, sz, fma(sy, sy, sx * sx));
                     const bool in = r2 <= A.r2eff;                // rows beyond the table support interpolate to exactly 0
                     const double y = rsqrt_fast(r2);              // 1/r
-                    const double r = r2 * y;
-                    const double z = rsqrt_fast(r);               // 1/sqrt(r)
-                    const double sk = (r * z) * A.csi;            // SK = sqrt(r)*CSI
+                    const double sk = rsqrt_fast(y) * A.csi;      // SK = sqrt(r)*CSI, sqrt(r) = (1/r)^(-1/2)
                     const double tk = __dadd_rd(sk, 4503599627370496.0);
                     const int kk = __double2loint(tk);            // KK = int(SK)
                     const double dk = sk - (tk - 4503599627370496.0);
@@ -860,12 +858,13 @@ k_tile_pass(TileParams P, TilePassArgs A)
                         const double fr = fma(dk, t1.x - t0.x, t0.x);
                         const double fb = fma(dk, t1.y - t0.y, t0.y);
                         // FORTOT = FPOTR/R2 + (FPOTB_ij*DEN_i + FPOTB_ji*DEN_j)/R     (:811-813)
-                        double ft = y * fma(fr, y, fma(fb, me.w, fb * pzw.y));
-                        ft = fast ? ft : 0.0;
-                        acc0 = fma(ft, sx, acc0);
-                        acc1 = fma(ft, sy, acc1);
-                        acc2 = fma(ft, sz, acc2);
-                        if (VIR) {
+                        const double ft = y * fma(fr, y, fma(fb, me.w, fb * pzw.y));
+                        if (fast) { // predicated accumulation (no select of the 64-bit factor)
+                            acc0 = fma(ft, sx, acc0);
+                            acc1 = fma(ft, sy, acc1);
+                            acc2 = fma(ft, sz, acc2);
+                        }
+                        if (VIR && fast) {
                             const double hx = 0.5 * ft * sx, hy = 0.5 * ft * sy, hz = 0.5 * ft * sz;
                             vxx = fma(hx, sx, vxx); vxy = fma(hx, sy, vxy); vxz = fma(hx, sz, vxz);
                             vyy = fma(hy, sy, vyy); vyz = fma(hy, sz, vyz); vzz = fma(hz, sz, vzz);
