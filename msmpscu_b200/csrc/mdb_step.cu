@@ -29,9 +29,14 @@ __device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict_
     double x[3] = {p.x, p.y, p.z};
     const int fixp[3] = {ST_FIXPOSX, ST_FIXPOSY, ST_FIXPOSZ};
     const int fixv[3] = {ST_FIXVELX, ST_FIXVELY, ST_FIXVELZ};
-    double v[3], f[3];
+    // every load of the atom is issued before the first dependent instruction (the kernel is latency-bound on HBM)
+    double v[3], f[3], ds[3];
+    float dr[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int d = 0; d < 3; d++) { v[d] = xp1[i + (size_t)d * n]; f[d] = fp[i + (size_t)d * n]; }
+    for (int d = 0; d < 3; d++) {
+        v[d] = xp1[i + (size_t)d * n]; f[d] = fp[i + (size_t)d * n]; ds[d] = dis[i + (size_t)d * n];
+        if (dsr) dr[d] = dsr[i + (size_t)d * n];
+    }
     if ((pre & 1) && E.enable[kk] > 0) { // EPC_MOD_KERNEL, MD_EP_Coupling_GPU.F90:473-490
         const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])), __dmul_rn(v[2], v[2]));
         if (v2 <= E.eup[kk]) {
@@ -57,9 +62,9 @@ __device__ __forceinline__ float predict_atom(int i, int n, double4 *__restrict_
         }
         x[d] = xx;
         if (freev) xp1[o] = __dadd_rn(v[d], __dmul_rn(hs2, a));                 // :353-361
-        dis[o] = __dadd_rn(dis[o], dd);                                          // :371-373
+        dis[o] = __dadd_rn(ds[d], dd);                                           // :371-373
         if (dsr) { // un-wrapped displacement accumulated since the last neighbour rebuild (fp32 is ample)
-            const float t = dsr[o] + (float)dd;
+            const float t = dr[d] + (float)dd;
             dsr[o] = t;
             d2 += t * t;
         }
