@@ -1,32 +1,32 @@
-// mdb_force_tiled.cu -- the TILED fast path: neighbour-list build, density pass and force pass
-// over shared-memory staged halo tiles (geometry in mdb_tiled.cuh).
+// mdb_force_tiled.cu -- the TILED fast path: neighbour-list build, density pass, force pass (+ virial epilogue) and
+// per-atom energy pass over shared-memory staged halo tiles (geometry in mdb_tiled.cuh).
 //
-// Why: with one thread per atom over a global-id list (the reference design, kept as the generic
-// path) every (atom, neighbour) visit is a 32-byte random gather that costs a full L1 wavefront
-// per lane and an un-fused sqrt/sqrt/div/div chain on the fp64 pipe; on B200 that runs at ~5 % of
-// the HBM roofline (profiles/r01_generic_path_summary.md).  Here, per tile:
-//   stage   the <=27 contiguous halo runs are brought into shared memory by TMA bulk copies
-//           (cp.async.bulk + mbarrier) as fp64 {x,y,z,den} records; cells on a periodic face are
-//           moved into the tile frame; a byte-modular packed copy (8 bits per axis) is derived for
-//           filtering;
-//   phase A each lane streams its share of the 16-bit slot list (8-byte coalesced loads, next load
-//           in flight), filters with one SIMD byte subtract + one dp4a per entry (conservative:
-//           it can pass a far pair, never drop an in-range one) and pushes survivors into the
-//           atom's queue (shared by the G lanes of the atom);
-//   phase B the queue is drained in lock-step: fp64 separation from the staged records, the exact
-//           r2 test, one rsqrt-based evaluation of r, 1/r, sqrt(r), table rows from shared memory.
-// The CTA is split into two halves that each own a tile: while one half waits for its TMA copies
-// or sits at a tile barrier the other computes (two tiles in flight per SM, one shared table copy).
+// Why: with one thread per atom over a global-id list (the reference design, kept as the generic path) every (atom,
+// neighbour) visit is a 32-byte random gather that costs a full L1 wavefront per lane and an un-fused sqrt/sqrt/div/div
+// chain on the fp64 pipe; on B200 that runs at ~5 % of the HBM roofline (profiles/r01_generic_path_summary.md).
 //
+// Structure:
+//   tile        a run of cells along x in one cell row: owned atoms contiguous, halo = (Wt+2) x 3 x 3 cells = at most 27
+//               contiguous RUNS of the {x,y,z,den} record array.  k_tile_desc writes one descriptor per tile per rebuild.
+//   k_tile_nlist  one CTA per tile, two warps per owned cell (lanes = atoms); the halo is staged once as pairs of fp32
+//               candidates, membership is the reference's fp32 expression (Cal_NeighboreList_Kernel2C,
+//               CommonGPU/MD_NeighborsList_GPU.F90:1097-1131), accepted 14-bit halo SLOTS + a 2-bit build-distance class go to
+//               a per-atom shared-memory column, which is partitioned by class (optionally dealt out by slot residue for
+//               conflict-free record reads, MDB_OPT_TILED_BANKORDER) and written as a lane-interleaved 16-bit list.
+//   k_tile_pass   one persistent CTA per SM, warp-specialised: a PRODUCER warp brings each tile's runs, first index group,
+//               STATU and scan counts into a 2-stage shared-memory pipeline with TMA bulk copies (cp.async.bulk + mbarrier);
+//               CONSUMER warps grab chunks of 32/G owned atoms from a shared counter and evaluate every listed entry
+//               branch-free: fp64 separation from the staged records, exact r2 <= r_eff^2, MUFU.RSQ64H + Halley for 1/r and
+//               sqrt(r), table rows from a shared-memory window, masked accumulation, G-lane shuffle reduce.  No CTA-wide
+//               barrier anywhere.  PASS 1 density -> dF/drho, PASS 2 forces (VIR: + per-warp partial virial tensors),
+//               PASS 3 per-atom energies.
 // Exact work reductions (results identical to evaluating every listed pair):
-//   * rows beyond the last non-zero table row interpolate to exactly 0, so the in-range test uses
-//     min(RU, table support);
-//   * the slot list is stored in three classes by BUILD-time distance (<= r_eff(pass1)+m,
-//     <= r_eff(pass2)+m, rest).  A pass scans only its classes while every atom has moved less
-//     than m/2 since the rebuild (tracked by the predictor); otherwise it scans the whole list.
-// The list itself (members, order, truncation) is the reference's: the build kernel evaluates the
-// same fp32 expression as Cal_NeighboreList_Kernel2C (CommonGPU/MD_NeighborsList_GPU.F90:1097-1131)
-// and emits the reference-format KVOIS/INDI next to the slot list.
+//   * rows beyond the last non-zero table row interpolate to exactly 0, so the in-range test uses min(RU, table support);
+//   * the slot list is stored in three classes by BUILD-time distance (<= r_eff(pass1)+m0, <= r_eff(pass2)+m, rest).  A pass
+//     scans only its classes while every atom has moved less than half the margin since the rebuild (tracked by the
+//     predictor); otherwise it scans the whole list.
+// The list's members are the reference's; its ORDER is free on this path (the passes only sum over it): the reference-ordered
+// KVOIS/INDI pair is produced on demand by the generic kernel from the positions saved at the rebuild (mdb_indi_ensure).
 #include <algorithm>
 #include <cmath>
 #include <cstring>
