@@ -267,6 +267,8 @@ int mdb_dd_global_t(mdb_ctx *ctx, double *curt);
  *                       active atom would move more than sqrt(DMX2) in the next predictor step
  * ---------------------------------------------------------------------------------- */
 int mdb_global_t(mdb_ctx *ctx, double *curt);
+/* the same per box of a MULTIBOX context (t_box[nbox]): the per-box scalars a multi-box run gathers at output intervals */
+int mdb_box_temperatures(mdb_ctx *ctx, double *t_box);
 int mdb_vel_scaling(mdb_ctx *ctx, double dt);
 int mdb_check_timestep(mdb_ctx *ctx, double th, double h2s2, double dmx2, int *iflag);
 

@@ -62,6 +62,7 @@ SYMBOLS = {
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_embed_overruns": (C.c_int, [C.c_void_p]),
+    "mdb_box_temperatures": (C.c_int, [C.c_void_p, c_dp]),
     "mdb_active_region": (C.c_int, [C.c_void_p, C.c_int, c_ip, C.c_double, C.c_int]),
     "mdb_active_all": (C.c_int, [C.c_void_p, C.c_int]),
     "mdb_stopping_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_ip, c_dp]),
@@ -358,6 +359,11 @@ class Context:
     def pka_insert(self, orig_id, ekin_erg, direction):
         d = f64(direction)
         self._chk(self.lib.mdb_pka_insert(self.h, int(orig_id), float(ekin_erg), dp(d)))
+
+    def box_temperatures(self, nbox):
+        t = np.zeros(int(nbox))
+        self._chk(self.lib.mdb_box_temperatures(self.h, dp(t)))
+        return t
 
     def embed_overruns(self):
         """rho > RHOMX events of the density pass since the last call"""

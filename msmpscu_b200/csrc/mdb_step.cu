@@ -387,6 +387,21 @@ extern "C" int mdb_global_t(mdb_ctx *c, double *curt)
     return MDB_OK;
 }
 
+// per-box temperatures of a MULTIBOX run (the per-box sums VelScaling_DEV forms, :1405-1432, as temperatures): what the
+// multi-box dispatcher gathers over the ranks at an output interval
+extern "C" int mdb_box_temperatures(mdb_ctx *c, double *t_box)
+{
+    if (!c || !t_box) return mdb_fail(c, MDB_ERR_ARG, "mdb_box_temperatures: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_box_temperatures: mdb_box_set first");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_box_temperatures: not available in slab-decomposed runs");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    std::vector<double> sum; std::vector<int> cnt;
+    int nb = box_ekin_host(c, sum, cnt);
+    if (nb < 0) return nb;
+    for (int b = 0; b < nb; b++) t_box[b] = cnt[b] > 0 ? 2.0 * sum[b] / (double)cnt[b] / (3.0 * KB_CGS) : 0.0;
+    return MDB_OK;
+}
+
 extern "C" int mdb_vel_scaling(mdb_ctx *c, double dt)
 {
     if (!c) return MDB_ERR_ARG;
