@@ -10,6 +10,11 @@ Reference scheme replaced: replicated positions with host-staged all-gathers of 
 from . import capi
 
 
+def slab_layers(ncz, world, rank):
+    """z-layers [z0, z1) of cells owned by `rank` (same formula as mdb_dd_update in the library)."""
+    return (rank * ncz) // world, ((rank + 1) * ncz) // world
+
+
 class SlabDomain:
     def __init__(self, ctx: capi.Context, device, group=None):
         import torch
