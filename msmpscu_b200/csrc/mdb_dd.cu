@@ -120,6 +120,8 @@ static void p2p_free(mdb_ctx *c);
 void mdb_dd_free(mdb_ctx *c)
 {
     p2p_free(c);
+    if (c->dd_xs) { cudaStreamSynchronize(c->dd_xs); cudaStreamDestroy(c->dd_xs); c->dd_xs = nullptr; }
+    for (int k = 0; k < 4; k++) if (c->dd_ev[k]) { cudaEventDestroy(c->dd_ev[k]); c->dd_ev[k] = nullptr; }
     if (c->dd_comm && nccl().CommDestroy) nccl().CommDestroy((ncclComm_t)c->dd_comm);
     c->dd_comm = nullptr;
     if (c->dd_dev) cudaFree(c->dd_dev);
@@ -366,8 +368,11 @@ static int p2p_init(mdb_ctx *c)
     return MDB_OK;
 }
 
-static int p2p_exchange(mdb_ctx *c, bool with_d2max)
+static int p2p_exchange(mdb_ctx *c, bool with_d2max, cudaStream_t xs = nullptr)
 {
+    cudaStream_t keep = c->stream;
+    if (xs) c->stream = xs; // (ProfScope and the launches below follow c->stream)
+    struct Restore { mdb_ctx *c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{c, keep};
     P2PState *S = p2p_of(c);
     const XRanges R = atom_ranges(c);
     const int e = ++S->epoch;
@@ -600,11 +605,48 @@ extern "C" int mdb_dd_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_up
     if (!c->dd_on || !c->dd_built || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_dd_run: mdb_dd_build first");
     CUDA_TRY(c, cudaSetDevice(c->dev));
     int rc;
+    // Overlap (peer-to-peer backend, >= 3 layers per rank): the exchange runs on a side stream while the INTERIOR tiles --
+    // whose halos hold owned atoms only -- are computed; the two boundary layers follow once the ghost layers have landed.
+    P2PState *PS = p2p_of(c);
+    const int cl = c->ncell[0] * c->ncell[1];
+    const int nlay = (c->dd_info[13] - c->dd_info[12]) / cl, tpl = c->ncell[1] * c->tiled.ntx;
+    const char *env = getenv("MDB_DD_OVERLAP");
+    const bool overlap = PS && PS->on && nlay >= 3 && !(env && atoi(env) == 0);
+    if (overlap && !c->dd_xs) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->dd_xs, cudaStreamNonBlocking));
+        for (int k = 0; k < 4; k++) CUDA_TRY(c, cudaEventCreateWithFlags(&c->dd_ev[k], cudaEventDisableTiming));
+    }
+    const int t0 = c->dd_info[14], t1 = c->dd_info[15];
+    auto select = [&](int a, int b, int a2, int b2) { c->tile_sel[0] = a; c->tile_sel[1] = b; c->tile_sel[2] = a2; c->tile_sel[3] = b2; };
+    auto pass_split = [&](unsigned flags, cudaEvent_t landed) -> int { // interior, wait for the ghosts, the two boundary layers
+        select(t0 + tpl, t1 - tpl, 0, 0);
+        int r = mdb_force_tiled(c, flags);
+        if (r >= 0) {
+            if (cudaStreamWaitEvent(c->stream, landed, 0) != cudaSuccess) r = mdb_fail(c, MDB_ERR_CUDA, "cudaStreamWaitEvent failed");
+            select(t0, t0 + tpl, t1 - tpl, t1);
+            if (r >= 0) r = mdb_force_tiled(c, flags);
+        }
+        c->tile_sel[0] = -1;
+        return r;
+    };
     for (int s = 0; s < nsteps; s++) {
         const int itime = itime0 + s;
         const int pre = (s == 0) ? 0 : 3; // EPC friction + corrector of the previous step ride in front of this predictor
         if ((rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_predict_launch(p, h, pre); })) < 0) return rc;
         const bool rebuild = nb_uptab > 0 && (itime - it0) % nb_uptab == 0;
+        if (overlap && !rebuild) {
+            CUDA_TRY(c, cudaEventRecord(c->dd_ev[0], c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->dd_xs, c->dd_ev[0], 0));
+            if ((rc = p2p_exchange(c, true, c->dd_xs)) < 0) return rc;
+            CUDA_TRY(c, cudaEventRecord(c->dd_ev[1], c->dd_xs));
+            if ((rc = pass_split(MDB_DEN, c->dd_ev[1])) < 0) return rc;
+            CUDA_TRY(c, cudaEventRecord(c->dd_ev[2], c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->dd_xs, c->dd_ev[2], 0));
+            if ((rc = p2p_exchange(c, false, c->dd_xs)) < 0) return rc;
+            CUDA_TRY(c, cudaEventRecord(c->dd_ev[3], c->dd_xs));
+            if ((rc = pass_split(MDB_FORCE | MDB_NOPASS1, c->dd_ev[3])) < 0) return rc;
+            continue;
+        }
         if ((rc = x_pos(c, !rebuild)) < 0) return rc;
         if (rebuild && (rc = dd_local_rebuild(c)) < 0) return rc;
         if ((rc = all_ranks(c, [](mdb_ctx *p) { return mdb_force_tiled(p, MDB_DEN); })) < 0) return rc;

@@ -515,6 +515,7 @@ struct TilePassArgs {
     int row_a, row_b;
     int fuse;              // fused epilogue of pass 2 (mdb_run): bit 0 EPC friction, bit 1 corrector half-kick
     int tile_lo, tile_hi;  // tiles of this rank (slab decomposition), [0, ntiles) otherwise
+    int tile_lo2, tile_hi2; // an optional second range (boundary layers of a slab: first and last layer in one launch)
     int zero_parked;       // block 0 zeroes the outputs of atoms parked outside the cells
     int nbuf;              // pipeline stages (2 or 3)
     const int *skip;       // device flag: return at once when set (converged quench iterations)
@@ -696,16 +697,18 @@ k_tile_pass(TileParams P, TilePassArgs A)
     // flat index of the class count of owned atom 0 (uint16 array [2][npad]) = ncl_base + own_start
     const size_t ncl_base = (size_t)cls_row * P.npad;
 
+    const int nt1 = A.tile_hi - A.tile_lo, nvt = nt1 + (A.tile_hi2 - A.tile_lo2); // tiles of this launch: range 1, then range 2
     if (warp == NCW) {
         // =========================== producer warp ===========================
         // Everything a stage needs arrives by TMA: halo runs, the first index group, and 16-byte aligned windows of
         // STATU and of the scan counts around the owned range.  The descriptor of the NEXT tile is loaded one tile
         // ahead and only used in the next iteration, so no global-memory round trip sits on the per-tile path.
         struct Pre { int htot, nrun, edge_any, own_start, own_slot0, own_count, rs0, rs1, rgst; };
-        auto prefetch = [&](int tile) {
+        auto prefetch = [&](int v) {
             Pre q;
             q.htot = 0; q.nrun = 0; q.edge_any = 0; q.own_start = 0; q.own_slot0 = 0; q.own_count = 0; q.rs0 = 0; q.rs1 = 0; q.rgst = 0;
-            if (tile < A.tile_hi) {
+            if (v < nvt) {
+                const int tile = v < nt1 ? A.tile_lo + v : A.tile_lo2 + (v - nt1);
                 const TileDesc &D = A.desc[tile];
                 q.htot = D.htot; q.nrun = D.nrun; q.edge_any = D.edge_any;
                 q.own_start = D.own_start; q.own_slot0 = D.own_slot0; q.own_count = D.own_count;
@@ -715,8 +718,9 @@ k_tile_pass(TileParams P, TilePassArgs A)
         };
         int b = 0;
         unsigned u = 0;
-        Pre nx = prefetch(A.tile_lo + blockIdx.x);
-        for (int tile = A.tile_lo + blockIdx.x; tile < A.tile_hi; tile += gridDim.x) {
+        Pre nx = prefetch(blockIdx.x);
+        for (int v = blockIdx.x; v < nvt; v += gridDim.x) {
+            const int tile = v < nt1 ? A.tile_lo + v : A.tile_lo2 + (v - nt1);
             const Pre cur = nx;
             int own_count = cur.own_count;
             const bool fits = cur.htot <= P.hcap && own_count <= P.ocap && cur.nrun <= TILE_MAX_RUN;
@@ -747,7 +751,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 }
             }
             // next tile's descriptor: in flight while this tile's copies land, first used in the next iteration
-            nx = prefetch(tile + gridDim.x);
+            nx = prefetch(v + gridDim.x);
             if (fits) {
                 if (MT) { // lane per halo cell: copy the types of its atoms
                     const TileDesc &D = A.desc[tile];
@@ -776,7 +780,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
         // =========================== consumer warps ===========================
         int b = 0;
         unsigned u = 0;
-        for (int tile = A.tile_lo + blockIdx.x; tile < A.tile_hi; tile += gridDim.x) {
+        for (int v = blockIdx.x; v < nvt; v += gridDim.x) {
             mbar_wait(&bar_ready[b], u & 1u);
             mbar_wait(&bar_full[b], u & 1u);
             const int own_start = s_info[4 * b + 0], own_slot0 = s_info[4 * b + 1], own_count = s_info[4 * b + 2];
@@ -1275,6 +1279,10 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     A.fuse = fuse; A.hs2 = hs2; A.xp1 = c->xp1; A.epc = c->epc; A.mass = c->mass;
     A.tile_lo = c->dd_on ? c->dd_info[14] : 0;
     A.tile_hi = c->dd_on ? c->dd_info[15] : S.P.ntiles;
+    A.tile_lo2 = A.tile_hi2 = 0;
+    if (c->tile_sel[0] >= 0) { // a sub-range launch of a decomposed step (interior tiles / the two boundary layers)
+        A.tile_lo = c->tile_sel[0]; A.tile_hi = c->tile_sel[1]; A.tile_lo2 = c->tile_sel[2]; A.tile_hi2 = c->tile_sel[3];
+    }
     A.zero_parked = c->dd_on ? 0 : 1;
     A.nbuf = S.nbuf;
     A.skip = c->skip_flag;
@@ -1285,7 +1293,9 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     auto kern = k_tile_pass<PASS, G, MT, FUSE, NT, VIR>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_pass[PI]));
     ProfScope ps(c, PASS == 1 ? MDB_K_PASS1 : (PASS == 2 ? MDB_K_PASS2 : MDB_K_EPOT));
-    kern<<<S.grid, NT, S.smem_pass[PI], c->stream>>>(S.P, A);
+    const int ntl = (A.tile_hi - A.tile_lo) + (A.tile_hi2 - A.tile_lo2);
+    if (ntl <= 0) return MDB_OK;
+    kern<<<std::min(S.grid, ntl), NT, S.smem_pass[PI], c->stream>>>(S.P, A);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }

@@ -159,6 +159,9 @@ struct mdb_ctx {
     // backend of the library-level decomposed run (mdb_dd.cu): NCCL communicator (one process per GPU) or, for single-GPU
     // tests, the contexts of all ranks in this process (same device, same stream: exchanges are device-to-device copies)
     void *dd_comm = nullptr;
+    int tile_sel[4] = {-1, -1, 0, 0}; // tile ranges of the next tiled pass launches when >= 0 (mdb_dd.cu: interior / boundary split)
+    cudaStream_t dd_xs = nullptr;     // side stream of the overlapped ghost exchange
+    cudaEvent_t dd_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     void *dd_p2p = nullptr;     // peer-to-peer ghost exchange state (CUDA IPC mappings of the neighbours' arrays)
     std::vector<mdb_ctx *> dd_peers;
     int *dd_dev = nullptr;      // device: per rank {owned atoms, bottom-layer atoms, top-layer atoms, max atoms per cell}, then scratch
