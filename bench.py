@@ -82,6 +82,8 @@ def parse():
     ap.add_argument("--bankorder", type=int, default=-1, help="tiled path: bank-aware order of the scanned list classes (0/1), -1 = default")
     ap.add_argument("--stages", type=int, default=0, help="tiled path: pipeline stages of the pass kernel (2/3), 0 = default")
     ap.add_argument("--c3-boxes", type=int, default=512, help="boxes of the configs[2] sub-record (512 x 16 000 atoms; 0 = skip)")
+    ap.add_argument("--c4-replicas", type=int, default=96, help="replicas of the configs[3] sub-record (PARREP_Test asks for 100; 96 "
+                    "divides over 1/2/4/8 GPUs; 0 = skip)")
     ap.add_argument("--dd-cells", type=int, default=200, help="edge (bcc cells) of the single box of the dd_strong sub-record "
                     "(200 -> 16 M atoms; 0 = skip)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the timed CPU loop")
@@ -600,6 +602,12 @@ def run_ours(args):
             line["multibox_c3"] = c3_measure(args, args.c3_boxes, 20, 5, 2)
         except Exception as e:  # pragma: no cover
             line["multibox_c3"] = {"error": repr(e)}
+    if args.c4_replicas > 0:
+        # configs[3] on the same N GPUs: PARREP replicas sharded per GPU, event detection on the device
+        try:
+            line["parrep_c4"] = c4_measure(args, args.c4_replicas, 2, 500)
+        except Exception as e:  # pragma: no cover
+            line["parrep_c4"] = {"error": repr(e)}
     if args.dd_cells > 0:
         # configs[4] family on the same N GPUs: one 16 M-atom box, strong scaling (collective: every rank takes part)
         try:
@@ -756,6 +764,68 @@ def c3_measure(args, nbox_total, cells, blocks, warm):
             "workload": "configs[2]: %d independent boxes x %d atoms (%d^3 bcc cells) sharded over %d GPU(s) as contiguous blocks of "
                         "boxes (MULTIBOX inside a rank), NVT via EPC, no inter-GPU traffic per step; W Marinica EAM2 tables stand in "
                         "for the Fe EAM_NIST file the reference does not ship" % (nbox_total, c.napb, cells, world)}
+
+
+def c4_measure(args, nrep_total, cycles, md_steps):
+    """configs[3]: PARREP replicas (2000 W + 1 H, Bonny EAM1, examples/PARREP_Test control values: list cutoff 1.6 RU, MAXNB 400,
+    rebuild every 10, quench ST 1000 steps, DRTOL 0.03 LU) sharded over the ranks by the multi-box dispatcher; per cycle every
+    rank runs `md_steps` MD steps on its replicas, then the event detection ON THE DEVICE (save, steepest-descent quench,
+    compare with the starting configuration, restore + rebuild), and the per-replica event flags are gathered over the ranks --
+    the only collective.  value = replica atoms x MD steps / max-over-ranks wall time, detection included."""
+    import torch
+    import torch.distributed as dist
+    import util
+    from msmpscu_b200 import capi
+    from msmpscu_b200.multibox import MultiBoxDispatcher
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    disp = MultiBoxDispatcher(nrep_total)
+    c = util.parrep_case(disp.count, seed=3000 + disp.first)
+    xini = util.neb_case("react").xp
+    ctx = util.make_ctx(c)
+    ctx.epc_set([1, 1], [300.0, 300.0], [1.0e-12] * 2, [0.1] * 2, [100.0 * 1.60219e-12] * 2)
+    ctx.force(capi.FORCE)
+    ctx.thermalize(600.0, 20240101 + disp.first, 0)
+    ctx.run(0, 20, 1, MD_PER_PERIOD, H)
+    it = 20
+    events = 0
+    t_md = t_det = 0.0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(cycles):
+        a = time.perf_counter()
+        ctx.run(it, md_steps, 1, MD_PER_PERIOD, H)
+        it += md_steps
+        b = time.perf_counter()
+        ctx.state_save()
+        ctx.steepest(1000, 0.1, 0.1 * c.rr, 1.0e-5 * c.rr, 1.0e-5 * 1.60219e-12)
+        fb, ibt, ncb = ctx.compare(xini, 0.03 * c.rr, nbox=disp.count)
+        ctx.state_restore()
+        flags = disp.gather_box_scalars(fb.reshape(-1, 1).astype(np.float64))      # every rank sees every replica's flag
+        events += int(flags.sum())
+        d = time.perf_counter()
+        t_md += b - a
+        t_det += d - b
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt, t_md, t_det], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, t_md, t_det = (float(v) for v in t.tolist())
+    path = ctx.get_option(capi.OPT_ACTIVE_PATH)
+    ctx.close()
+    ntot = nrep_total * c.napb
+    return {"value": ntot * md_steps * cycles / dt, "unit": "atom-steps/s", "scaling": "strong", "n_gpus": world,
+            "replicas_total": nrep_total, "replicas_this_rank": disp.count, "atoms_per_replica": int(c.napb), "cycles": cycles,
+            "md_steps_per_cycle": md_steps, "wall_s": dt, "md_s": t_md, "event_detection_s": t_det, "events_flagged": events,
+            "md_only_atom_steps_per_s": ntot * md_steps * cycles / t_md,
+            "force_path": "tiled" if path == capi.FORCE_PATH_TILED else "generic",
+            "workload": "configs[3]: %d PARREP replicas x %d atoms (2000 W + 1 H, Bonny EAM1), %d cycles of %d MD steps + event detection "
+                        "(device-side save / ST quench / compare / restore), replicas sharded over %d GPU(s), event flags gathered over the ranks"
+                        % (nrep_total, c.napb, cycles, md_steps, world)}
 
 
 def run_dd(args):

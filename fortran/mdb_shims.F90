@@ -511,3 +511,31 @@ contains
       if(mdb_epc_apply(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_epc_apply failed"
   end subroutine
 end module MD_LocalTempMethod_GPU
+
+module MD_Method_ParRep_GPU_EventDetect  ! the device pieces of Do_ChangeDetect, Appshell/MD_Method_ParRep_GPU.F90:1094-1167
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MDB_C_BINDING
+  implicit none
+contains
+  ! the body of Do_ChangeDetect between "allocate(SwapBox ...)" and "deallocate": no host copies of the replicas
+  subroutine Do_ChangeDetect_DEV(SimBoxIni, NB, CtrlParam, Mask, IBT, NCB, FlagBox)
+    type(SimMDBox),  intent(in) ::SimBoxIni
+    integer,         intent(in) ::NB
+    type(SimMDCtrl), intent(in) ::CtrlParam
+    integer, dimension(:), intent(in) ::Mask
+    integer, intent(out)::IBT, NCB
+    integer, dimension(:)::FlagBox
+    integer(c_int)::IFLAG
+    real(c_double)::MAXMOVE, DELEPOT
+    integer(c_int), target::DUMMY(1)
+      if(mdb_state_save(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_state_save failed"
+      ! Do_Damp(SwapBox, m_CtrlParamDamp, gm_ForceClass): the "ST" scheme; the other schemes call mdb_cg / mdb_lbfgs / mdb_dyndamp
+      if(mdb_steepest(m_CTX, CtrlParam%Quench_Steps, 0, CtrlParam%STEEPEST_Alpha, CtrlParam%STEEPEST_MxStep*SimBoxIni%RR,  &
+                      CtrlParam%STEEPEST_MiStep*SimBoxIni%RR, CtrlParam%STEEPEST_MiDelE*CP_EVERG, IFLAG, MAXMOVE, DELEPOT) .lt. 0) &
+         stop "MDPSCU Error: mdb_steepest failed"
+      if(mdb_compare(m_CTX, SimBoxIni%XP, Mask, CtrlParam%STRCUT_DRTol, FlagBox, DUMMY, IBT, NCB) .lt. 0) &
+         stop "MDPSCU Error: mdb_compare failed"
+      if(mdb_state_restore(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_state_restore failed"
+  end subroutine
+end module MD_Method_ParRep_GPU_EventDetect

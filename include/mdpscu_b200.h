@@ -206,6 +206,18 @@ int mdb_stopping_apply(mdb_ctx *ctx);
 int mdb_pka_insert(mdb_ctx *ctx, int orig_id, double ekin_erg, const double dir[3]);
 
 /* ------------------------------------------------------------------------------------
+ * PARREP event detection on the device: Do_ChangeDetect (Appshell/MD_Method_ParRep_GPU.F90:1094-1167) =
+ *   mdb_state_save    Copy_SimMDBox(SimBox(IB), SwapBox(IB)) for all replicas, kept in device memory (ORIGINAL order)
+ *   (quench)          Do_Damp -> mdb_steepest / mdb_cg / mdb_lbfgs / mdb_dyndamp
+ *   mdb_compare       Do_Compare (:1241-1297): replicas against SimBoxIni%XP(NPRT,3) (host, column-major), optional MASK(NPRT),
+ *                     drtol = STRCUT_DRTol in cm; flag_box[nbox] (host), optional per-atom Flag(nbox*NPRT); IBT / NCB as :1146-1156
+ *   mdb_state_restore CopyIn_SimBox_DEV + Cal_NeighBoreList_DEV (:1158-1159): the saved replicas and their list come back
+ * ---------------------------------------------------------------------------------- */
+int mdb_state_save(mdb_ctx *ctx);
+int mdb_state_restore(mdb_ctx *ctx);
+int mdb_compare(mdb_ctx *ctx, const double *xp_ini, const int *mask, double drtol, int *flag_box, int *flag_atom, int *ibt, int *ncb);
+
+/* ------------------------------------------------------------------------------------
  * one whole MD step, For_One_Step (Appshell/MD_Method_GenericMD_GPU.F90:496-659):
  * predictor -> [rebuild if MOD(itime-it0,nb_uptab)==0] -> force -> EPC -> corrector,
  * with the element-wise stages fused into the force passes where no rebuild intervenes.

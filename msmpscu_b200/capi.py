@@ -62,6 +62,9 @@ SYMBOLS = {
     "mdb_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_embed_overruns": (C.c_int, [C.c_void_p]),
+    "mdb_state_save": (C.c_int, [C.c_void_p]),
+    "mdb_state_restore": (C.c_int, [C.c_void_p]),
+    "mdb_compare": (C.c_int, [C.c_void_p, c_dp, c_ip, C.c_double, c_ip, c_ip, c_ip, c_ip]),
     "mdb_box_temperatures": (C.c_int, [C.c_void_p, c_dp]),
     "mdb_active_region": (C.c_int, [C.c_void_p, C.c_int, c_ip, C.c_double, C.c_int]),
     "mdb_active_all": (C.c_int, [C.c_void_p, C.c_int]),
@@ -364,6 +367,24 @@ class Context:
         t = np.zeros(int(nbox))
         self._chk(self.lib.mdb_box_temperatures(self.h, dp(t)))
         return t
+
+    # ---- PARREP event detection (Do_ChangeDetect pieces)
+    def state_save(self):
+        self._chk(self.lib.mdb_state_save(self.h))
+
+    def state_restore(self):
+        return self._chk(self.lib.mdb_state_restore(self.h))
+
+    def compare(self, xp_ini, drtol, mask=None, per_atom=False, nbox=1):
+        """Do_Compare: returns (flag_box, IBT, NCB[, Flag per atom])"""
+        x = colmajor(xp_ini)
+        fb = np.zeros(int(nbox), np.int32)
+        fa = np.zeros(self.n, np.int32) if per_atom else None
+        m = i32(mask) if mask is not None else None
+        ibt, ncb = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.mdb_compare(self.h, dp(x), ip(m) if m is not None else None, float(drtol), ip(fb),
+                                       ip(fa) if fa is not None else None, C.byref(ibt), C.byref(ncb)))
+        return (fb, ibt.value, ncb.value, fa) if per_atom else (fb, ibt.value, ncb.value)
 
     def embed_overruns(self):
         """rho > RHOMX events of the density pass since the last call"""

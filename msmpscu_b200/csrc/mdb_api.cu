@@ -147,6 +147,7 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
     cudaStreamSynchronize(c->stream);
     mdb_dd_free(c);
     mdb_stopping_free(c);
+    mdb_save_free(c);
     mdb_prof_collect(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     free_state(c); free_nlist(c); free_tables(c);

@@ -257,3 +257,148 @@ extern "C" int mdb_pka_insert(mdb_ctx *c, int orig_id, double ekin_erg, const do
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// PARREP event detection on the device: Do_ChangeDetect, Appshell/MD_Method_ParRep_GPU.F90:1094-1167 =
+//   copy the replicas aside -> Do_Damp (quench) -> Do_Compare (:1241-1297) -> restore the replicas and their list.
+// The reference copies every replica to host SwapBoxes and compares on the host; here the state is saved in device memory
+// (ORIGINAL order, so it survives the re-sorts of the quench), the comparison is one kernel, and only NB flags come back.
+// ------------------------------------------------------------------------------------
+struct SaveState { double *xp = nullptr, *xp1 = nullptr, *dis = nullptr, *fp = nullptr; int *statu = nullptr; int n = 0; };
+static SaveState *save_of(mdb_ctx *c) { return reinterpret_cast<SaveState *>(c->save_state); }
+void mdb_save_free(mdb_ctx *c)
+{
+    SaveState *S = save_of(c);
+    if (!S) return;
+    cudaFree(S->xp); cudaFree(S->xp1); cudaFree(S->dis); cudaFree(S->fp); cudaFree(S->statu);
+    delete S;
+    c->save_state = nullptr;
+}
+__global__ void k_save(int n, const int *__restrict__ gid, const double4 *__restrict__ pos, const double *__restrict__ xp1,
+                       const double *__restrict__ dis, const double *__restrict__ fp, const int *__restrict__ statu,
+                       double *__restrict__ sx, double *__restrict__ sv, double *__restrict__ sd, double *__restrict__ sf, int *__restrict__ ss)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int o = gid[s] - 1;
+    const double4 p = pos[s];
+    sx[o] = p.x; sx[o + (size_t)n] = p.y; sx[o + 2 * (size_t)n] = p.z;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        sv[o + (size_t)d * n] = xp1[s + (size_t)d * n];
+        sd[o + (size_t)d * n] = dis[s + (size_t)d * n];
+        sf[o + (size_t)d * n] = fp[s + (size_t)d * n];
+    }
+    ss[o] = statu[s];
+}
+__global__ void k_restore(int n, const int *__restrict__ gid, double4 *__restrict__ pos, double *__restrict__ xp1, double *__restrict__ dis,
+                          double *__restrict__ fp, int *__restrict__ statu, const double *__restrict__ sx, const double *__restrict__ sv,
+                          const double *__restrict__ sd, const double *__restrict__ sf, const int *__restrict__ ss)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int o = gid[s] - 1;
+    double4 p = pos[s];
+    p.x = sx[o]; p.y = sx[o + (size_t)n]; p.z = sx[o + 2 * (size_t)n];
+    pos[s] = p;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        xp1[s + (size_t)d * n] = sv[o + (size_t)d * n];
+        dis[s + (size_t)d * n] = sd[o + (size_t)d * n];
+        fp[s + (size_t)d * n] = sf[o + (size_t)d * n];
+    }
+    statu[s] = ss[o];
+}
+// Copy_SimMDBox(SimBox(IB), SwapBox(IB)) for all replicas (:1131-1133), on the device
+extern "C" int mdb_state_save(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_save: mdb_box_set first");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_state_save: not available in slab-decomposed runs");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    SaveState *S = save_of(c);
+    const int n = c->n;
+    if (S && S->n != n) { mdb_save_free(c); S = nullptr; }
+    if (!S) {
+        S = new SaveState();
+        S->n = n;
+        c->save_state = S;
+        CUDA_TRY(c, cudaMalloc(&S->xp, sizeof(double) * 3 * (size_t)n)); CUDA_TRY(c, cudaMalloc(&S->xp1, sizeof(double) * 3 * (size_t)n));
+        CUDA_TRY(c, cudaMalloc(&S->dis, sizeof(double) * 3 * (size_t)n)); CUDA_TRY(c, cudaMalloc(&S->fp, sizeof(double) * 3 * (size_t)n));
+        CUDA_TRY(c, cudaMalloc(&S->statu, sizeof(int) * (size_t)n));
+    }
+    ProfScope ps(c, MDB_K_OTHER);
+    k_save<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->gid, c->pos, c->xp1, c->dis, c->fp, c->statu, S->xp, S->xp1, S->dis, S->fp, S->statu);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+// CopyIn_SimBox_DEV(SimBox) + Cal_NeighBoreList_DEV (:1158-1159): the saved replicas come back and the list is rebuilt
+extern "C" int mdb_state_restore(mdb_ctx *c)
+{
+    if (!c) return MDB_ERR_ARG;
+    SaveState *S = save_of(c);
+    if (!S || S->n != c->n) return mdb_fail(c, MDB_ERR_STATE, "mdb_state_restore: nothing saved (mdb_state_save)");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        k_restore<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->gid, c->pos, c->xp1, c->dis, c->fp, c->statu, S->xp, S->xp1, S->dis, S->fp, S->statu);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    mdb_mark_positions_dirty(c);
+    c->list_valid = false;
+    return c->has_nlist ? mdb_nlist_build(c) : (int)MDB_OK;
+}
+
+// Do_Compare (:1241-1297): Flag = 1 where atom I of replica IB sits further than DRTOL from its place in SimBoxIni (minimum image
+// on periodic axes, strict '>' on the squared distance, MASK(I) <= 0 skipped); a replica with any flag is a transition.
+__global__ void k_compare(int n, int napb, const int *__restrict__ gid, const double4 *__restrict__ pos, const double *__restrict__ xini,
+                          const int *__restrict__ mask, BoxParams box, double rc2, int *__restrict__ flag_atom, int *__restrict__ flag_box)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int o = gid[s] - 1, ib = o / napb, i = o - ib * napb;
+    int f = 0;
+    if (!mask || mask[i] > 0) {
+        const double4 p = pos[s];
+        double sep[3] = {__dsub_rn(xini[i], p.x), __dsub_rn(xini[i + (size_t)napb], p.y), __dsub_rn(xini[i + 2 * (size_t)napb], p.z)};
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            if (box.pd[d] > 0 && fabs(sep[d]) > box.half[d]) sep[d] = __dsub_rn(sep[d], copysign(box.size[d], sep[d]));
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(sep[0], sep[0]), __dmul_rn(sep[1], sep[1])), __dmul_rn(sep[2], sep[2]));
+        f = r2 > rc2 ? 1 : 0;
+    }
+    if (flag_atom) flag_atom[o] = f;
+    if (f) flag_box[ib] = 1;
+}
+// xp_ini: SimBoxIni%XP(NPRT,3) column-major (host); mask: NPRT ints or NULL; drtol in cm; flag_box[nbox] (host out);
+// flag_atom: nbox*NPRT ints, replica-major, or NULL.  IBT = last replica with a flag (1-based, 0 = none), NCB = how many.
+extern "C" int mdb_compare(mdb_ctx *c, const double *xp_ini, const int *mask, double drtol, int *flag_box, int *flag_atom, int *ibt, int *ncb)
+{
+    if (!c || !xp_ini || !flag_box) return mdb_fail(c, MDB_ERR_ARG, "mdb_compare: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_compare: mdb_box_set first");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_compare: not available in slab-decomposed runs");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    const int n = c->n, napb = c->napb, nb = c->nbox;
+    cudaStream_t st = c->stream;
+    char *w = nullptr;
+    const size_t bx = sizeof(double) * 3 * (size_t)napb, bm = sizeof(int) * (size_t)napb, bf = sizeof(int) * (size_t)nb, ba = sizeof(int) * (size_t)n;
+    CUDA_TRY(c, cudaMallocAsync(&w, bx + bm + bf + ba + 64, st));
+    double *dx = (double *)w; int *dm = (int *)(w + bx), *dfb = dm + napb, *dfa = dfb + nb;
+    CUDA_TRY(c, cudaMemcpyAsync(dx, xp_ini, bx, cudaMemcpyHostToDevice, st));
+    if (mask) CUDA_TRY(c, cudaMemcpyAsync(dm, mask, bm, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemsetAsync(dfb, 0, bf, st));
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        k_compare<<<cdiv(n, 256), 256, 0, st>>>(n, napb, c->gid, c->pos, dx, mask ? dm : nullptr, c->box, drtol * drtol, flag_atom ? dfa : nullptr, dfb);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(flag_box, dfb, bf, cudaMemcpyDeviceToHost, st));
+    if (flag_atom) CUDA_TRY(c, cudaMemcpyAsync(flag_atom, dfa, ba, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaFreeAsync(w, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    int last = 0, cnt = 0;
+    for (int b = 0; b < nb; b++) if (flag_box[b] > 0) { last = b + 1; cnt++; } // :1146-1156
+    if (ibt) *ibt = last;
+    if (ncb) *ncb = cnt;
+    return MDB_OK;
+}

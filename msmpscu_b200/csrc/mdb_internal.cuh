@@ -143,6 +143,7 @@ struct mdb_ctx {
 
     // ---- epc
     EpcParams epc;
+    void *save_state = nullptr; // device copy of the replicas taken by mdb_state_save (PARREP event detection)
     void *stop_state = nullptr; // electronic stopping tables and switches (mdb_cascade.cu)
 
     // ---- host copies of the pair tables (Fortran layout) for planning the tiled path
@@ -237,5 +238,6 @@ void mdb_dd_free(mdb_ctx *c);                 // mdb_dd.cu
 int mdb_stopping_launch(mdb_ctx *c);          // mdb_cascade.cu : electronic stopping on FP (no-op when switched off)
 bool mdb_stopping_on(const mdb_ctx *c);
 void mdb_stopping_free(mdb_ctx *c);
+void mdb_save_free(mdb_ctx *c);
 static inline int own_a0(const mdb_ctx *c) { return c->dd_on ? c->dd_info[0] : 0; }
 static inline int own_a1(const mdb_ctx *c) { return c->dd_on ? c->dd_info[1] : c->n; }             // mdb_api.cu : cells + list kernel of the active path (no sync)

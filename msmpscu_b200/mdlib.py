@@ -486,6 +486,19 @@ def Do_Compare(SimBoxIni, SimBox, CtrlParam, MASK=None):
     return flag
 
 
+def Do_ChangeDetect(dev, SimBoxIni, SimBox, CtrlParam, CtrlParamDamp=None, MASK=None, ForceClass=gm_ForceClass):
+    """Do_ChangeDetect (Appshell/MD_Method_ParRep_GPU.F90:1094-1167) on the device: the replicas are saved in device memory
+    (mdb_state_save) instead of host SwapBoxes, quenched (Do_Damp), compared with SimBoxIni by one kernel (mdb_compare =
+    Do_Compare :1241-1297) and restored together with their list (mdb_state_restore = CopyIn_SimBox_DEV + Cal_NeighBoreList_DEV).
+    Returns (IBT, NCB, flag per replica)."""
+    nb = len(SimBox) if isinstance(SimBox, (list, tuple)) else int(getattr(dev.ctx, "nbox", 1))
+    dev.ctx.state_save()
+    Do_Damp(dev, SimBox, CtrlParamDamp or CtrlParam, ForceClass)
+    fb, ibt, ncb = dev.ctx.compare(SimBoxIni.XP, CtrlParam.STRCUT_DRTol * SimBoxIni.RR, mask=MASK, nbox=nb)
+    dev.ctx.state_restore()
+    return ibt, ncb, fb
+
+
 def Transition_Replicas(Flag, NPRT):
     """The tail of Do_ChangeDetect (:1146-1156): NCB = number of replicas with any flagged atom, IBT = the last of them
     (1-based, 0 when none)."""

@@ -146,3 +146,55 @@ def test_electronic_stopping_matches_restatement_and_rides_in_mdb_run():
     assert ke(a) < ke(d)
     for x in (ctx, a, b, d):
         x.close()
+
+
+def test_parrep_event_detection_on_the_device():
+    """Do_ChangeDetect (Appshell/MD_Method_ParRep_GPU.F90:1094-1167) from its device pieces: save the replicas, quench, compare with
+    SimBoxIni (Do_Compare :1241-1297, host mirror msmpscu_b200.mdlib.Do_Compare as the checker), restore replicas and list."""
+    from types import SimpleNamespace
+    from msmpscu_b200 import mdlib
+    nrep = 4
+    c = util.parrep_case(nrep)
+    napb = c.napb
+    xini = util.neb_case("react").xp                      # SimBoxIni: the configuration the replicas were started from
+    ctx = util.make_ctx(c)
+    ctx.force(capi.FORCE)
+    ctx.thermalize(600.0, 777, 0)
+    ctx.run(0, 40, 1, 10, 0.5e-15)
+    before = {f: ctx.download(f) for f in (capi.F_XP, capi.F_XP1, capi.F_DIS, capi.F_STATU)}
+    ctx.nlist_build()                                      # (the restore rebuilds the list from the restored positions, as :1158-1159)
+    kv0 = ctx.download(capi.F_KVOIS, capi.ORDER_ORIGINAL)
+    ctx.state_save()
+    fl, mm, de = ctx.steepest(300, 0.1, 0.1 * c.rr, 1.0e-5 * c.rr, 1.0e-5 * EV)
+    xq = ctx.download(capi.F_XP)
+    drtol = 0.03 * c.rr                                    # STRCUT_DRTol default, MD_TypeDef_SimCtrlParam.F90:202
+    ini = SimpleNamespace(NPRT=napb, RR=c.rr, ZL=np.asarray(c.zl), XP=xini)
+    ctrl = SimpleNamespace(STRCUT_DRTol=0.03, IFPD=c.ifpd)
+    boxes = [SimpleNamespace(XP=xq[b * napb:(b + 1) * napb]) for b in range(nrep)]
+    want = mdlib.Do_Compare(ini, boxes, ctrl)
+    fb, ibt, ncb, fa = ctx.compare(xini, drtol, per_atom=True, nbox=nrep)
+    assert np.array_equal(fa, want)
+    assert (ibt, ncb) == mdlib.Transition_Replicas(want, napb)
+    # a forced event in ONE replica: the reference state with two atoms displaced by 0.1 a0 is what replica 3 is compared to ...
+    x2 = xq.copy()
+    x2[2 * napb + 7, 0] += 0.1 * c.rr
+    x2[2 * napb + 100, 2] -= 0.05 * c.rr
+    ctx.upload(capi.F_XP, x2)
+    fb2, ibt2, ncb2, fa2 = ctx.compare(xini, drtol, per_atom=True, nbox=nrep)
+    boxes = [SimpleNamespace(XP=x2[b * napb:(b + 1) * napb]) for b in range(nrep)]
+    want2 = mdlib.Do_Compare(ini, boxes, ctrl)
+    assert np.array_equal(fa2, want2) and fa2[2 * napb + 7] == 1 and fa2[2 * napb + 100] == 1
+    assert fb2[2] == 1 and ibt2 >= 3 and ncb2 >= 1
+    # ... and the mask takes them out again (m_pCfgCompMask)
+    mask = np.ones(napb, np.int32)
+    mask[[7, 100]] = 0
+    fb3, _, _, fa3 = ctx.compare(xini, drtol, mask=mask, per_atom=True, nbox=nrep)
+    assert fa3[2 * napb + 7] == 0 and fa3[2 * napb + 100] == 0
+    assert np.array_equal(fa3, mdlib.Do_Compare(ini, boxes, ctrl, MASK=mask))
+    # restore: replicas and list exactly as before the detection
+    ctx.state_restore()
+    for f, a in before.items():
+        assert np.array_equal(ctx.download(f), a)
+    assert np.array_equal(ctx.download(capi.F_KVOIS, capi.ORDER_ORIGINAL), kv0)
+    ctx.run(40, 10, 1, 10, 0.5e-15)                       # and the run goes on
+    ctx.close()
