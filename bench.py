@@ -391,7 +391,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # (a rank that dies must not leave the others waiting ten minutes in a collective)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
 
     c = make_case(args.cells, 12346 + rank, args.nbox, args.potential)
     n = c.xp.shape[0]
@@ -783,7 +785,13 @@ def c4_measure(args, nrep_total, cycles, md_steps):
     disp = MultiBoxDispatcher(nrep_total)
     c = util.parrep_case(disp.count, seed=3000 + disp.first)
     xini = util.neb_case("react").xp
-    ctx = util.make_ctx(c)
+    ctx = capi.Context(local)
+    ctx.box_set(c.nbox, c.napb, c.boxlow, c.zl, c.ifpd, c.mass)
+    for f, a in ((capi.F_XP, c.xp), (capi.F_XP1, c.xp1), (capi.F_ITYP, c.ityp), (capi.F_STATU, c.statu)):
+        ctx.upload(f, a)
+    ctx.tables_set(util.product_tables(c), c.ru * c.ru)
+    ctx.nlist_init(c.nb_rm, c.mxkvois)
+    ctx.nlist_build()
     ctx.epc_set([1, 1], [300.0, 300.0], [1.0e-12] * 2, [0.1] * 2, [100.0 * 1.60219e-12] * 2)
     ctx.force(capi.FORCE)
     ctx.thermalize(600.0, 20240101 + disp.first, 0)

@@ -32,6 +32,14 @@ class MultiBoxDispatcher:
         self.first, self.count = partition_boxes(self.nbox_total, self.world, self.rank)
         self.counts = [partition_boxes(self.nbox_total, self.world, r)[1] for r in range(self.world)]
 
+    def _device(self):
+        """the rank's own GPU (LOCAL_RANK), not "whatever device is current": the library's calls select their context's device"""
+        import os
+        import torch
+        if self.dist.get_backend(self.group) != "nccl":
+            return "cpu"
+        return torch.device("cuda", int(os.environ.get("LOCAL_RANK", torch.cuda.current_device())))
+
     def local_boxes(self):
         return range(self.first, self.first + self.count)
 
@@ -42,7 +50,7 @@ class MultiBoxDispatcher:
         k = local.shape[1]
         if self.world == 1:
             return local.copy()
-        dev = device or ("cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu")
+        dev = device or self._device()
         mx = max(self.counts)
         buf = torch.zeros((mx, k), dtype=torch.float64, device=dev)
         if self.count:
@@ -56,7 +64,7 @@ class MultiBoxDispatcher:
         x = np.asarray(x, dtype=np.float64)
         if self.world == 1:
             return x.copy()
-        dev = device or ("cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu")
+        dev = device or self._device()
         t = torch.from_numpy(x.copy()).to(dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
@@ -66,7 +74,7 @@ class MultiBoxDispatcher:
         x = np.asarray(x, dtype=np.float64)
         if self.world == 1:
             return x.copy()
-        dev = device or ("cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu")
+        dev = device or self._device()
         t = torch.from_numpy(x.copy()).to(dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t.cpu().numpy()
