@@ -230,6 +230,25 @@ int mdb_run(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double 
  * list rebuild, for its capacity check); mdb_sync returns the block's out-of-box count */
 int mdb_run_async(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double h);
 
+/* The time loop of the GMD method with its schedules, nsteps x { step size, list period, For_One_Step, TIME += H }:
+ *   scheme I  (IHDUP > 0)  H = min(HMX, HMI*(int((ITIME-IT0+1)/IHDUP)+1))            Appshell/MD_Method_GenericMD_GPU.F90:353-356
+ *   scheme II (IHDUP < 0)  every |IHDUP| steps (MOD(ITIME-IT0+1,|IHDUP|) == 0) Predictor_DEV starts from TH = HMX and halves it
+ *                          until CheckTimestep_DEV finds no active atom that would move more than DMX in the predictor step;
+ *                          that TH becomes CtrlParam%H                                 CommonGPU/MD_DiffScheme_GPU.F90:633-655
+ *   IHDUP = 0              fixed H (the value passed in *h)
+ *   list period            NB_UPTAB = min(NB_UPTABMX, NB_UPTABMI*(int((ITIME-IT0+1)/NB_DBITAB)+1))                  :358-360
+ * The halving loop runs as ONE kernel that tests all trial steps HMX 2^-k at once and one 4-byte read-back per check.  Electronic
+ * stopping, when switched on (mdb_stopping_set), acts between the EPC friction and the corrector of every step.  With stopping or
+ * scheme II the tiled passes decide the distance-class shortcut PER TILE (MDB_OPT_TILE_GUARD): one fast atom sends only the tiles
+ * around it to the full list.  hmi / hmx in s, dmx in cm (the control file gives fs and lattice units).
+ * In/out: *h = CtrlParam%H, *time_s (may be NULL) += the sum of the steps taken [s].  Returns like mdb_run. */
+typedef struct mdb_sched {
+    int ihdup;
+    double hmi, hmx, dmx;
+    int nb_uptabmi, nb_uptabmx, nb_dbitab;
+} mdb_sched;
+int mdb_run_sched(mdb_ctx *ctx, int itime0, int nsteps, int it0, const mdb_sched *sched, double *h, double *time_s);
+
 /* ------------------------------------------------------------------------------------
  * single huge box over several GPUs: slab decomposition along z (whole z-layers of cells per rank).
  * Upgrades the reference's scheme -- contiguous cell ranges per device with REPLICATED positions and
@@ -267,6 +286,9 @@ int mdb_dd_build(mdb_ctx *ctx);
 int mdb_dd_force(mdb_ctx *ctx, unsigned flags, double vtensor[9]);
 int mdb_dd_run(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, double h);
 int mdb_dd_global_t(mdb_ctx *ctx, double *curt);
+/* mdb_run_sched on the decomposed box: the time-step masks of the ranks are OR-ed (4 bytes per rank all-gathered), electronic
+ * stopping acts on the owned atoms, EPC friction and the corrector close every step. */
+int mdb_dd_run_sched(mdb_ctx *ctx, int itime0, int nsteps, int it0, const mdb_sched *sched, double *h, double *time_s);
 
 /* ------------------------------------------------------------------------------------
  * The other integrator-module procedures the step loops call (CommonGPU/MD_DiffScheme_GPU.F90):
@@ -361,6 +383,8 @@ int mdb_cg(mdb_ctx *ctx, int mxnumsteps, int meth, double maxdis, double mindis,
 #define MDB_OPT_TILED_STAGES  6  /* shared-memory pipeline stages of the pass kernel: 2 (default) or 3           */
 #define MDB_OPT_TILED_BANKORDER 7 /* 1: the list builder orders each scanned class so that the record             */
                                  /* gathers of a half-warp spread over the shared-memory bank groups; 0 (default): scan order */
+#define MDB_OPT_TILE_GUARD    8  /* distance-class shortcut decided per tile from per-block displacement maxima: 1 on, 0 off,  */
+                                 /* -1 (default) on with electronic stopping or the displacement-limited time step            */
 #define MDB_FORCE_PATH_AUTO    0
 #define MDB_FORCE_PATH_GENERIC 1
 #define MDB_FORCE_PATH_TILED   2

@@ -78,6 +78,8 @@ SYMBOLS = {
     "mdb_dd_force": (C.c_int, [C.c_void_p, C.c_uint, c_dp]),
     "mdb_dd_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_dd_global_t": (C.c_int, [C.c_void_p, c_dp]),
+    "mdb_run_sched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, c_dp]),
+    "mdb_dd_run_sched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, c_dp]),
     "mdb_run_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_state_download_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "mdb_global_t": (C.c_int, [C.c_void_p, c_dp]),
@@ -122,6 +124,13 @@ SYMBOLS = {
 
 OPT_FORCE_PATH, OPT_TILED_LANES, OPT_TILED_CLASSES, OPT_ACTIVE_PATH, OPT_TILED_THREADS, OPT_FUSE_EPILOGUE, OPT_TILED_STAGES = 0, 1, 2, 3, 4, 5, 6
 OPT_TILED_BANKORDER = 7
+OPT_TILE_GUARD = 8
+
+
+class Sched(C.Structure):
+    """mdb_sched: CtrlParam%IHDUP / HMI / HMX / DMX and NB_UPTABMI / NB_UPTABMX / NB_DBITAB (seconds, cm)"""
+    _fields_ = [("ihdup", C.c_int), ("hmi", C.c_double), ("hmx", C.c_double), ("dmx", C.c_double),
+                ("nb_uptabmi", C.c_int), ("nb_uptabmx", C.c_int), ("nb_dbitab", C.c_int)]
 FORCE_PATH_AUTO, FORCE_PATH_GENERIC, FORCE_PATH_TILED = 0, 1, 2
 QUENCH_LSEARCH = 65536  # CP_DAMPSCHEME_LSEARCH
 
@@ -336,6 +345,12 @@ class Context:
     def run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
 
+    def run_sched(self, itime0, nsteps, it0, sched, h, time_s=0.0):
+        """the GMD time loop with its step-size / list-period schedules -> (out-of-box count, H after the block, TIME [s])"""
+        hh, tt = C.c_double(float(h)), C.c_double(float(time_s))
+        rc = self._chk(self.lib.mdb_run_sched(self.h, itime0, nsteps, it0, C.byref(sched), C.byref(hh), C.byref(tt)))
+        return rc, hh.value, tt.value
+
     # ---- cascade physics (csrc/mdb_cascade.cu)
     def active_region(self, centpart=None, ekin_erg=None, extend=1, keep=False):
         """ActivateRegion_DEV by cells; returns the number of active atoms"""
@@ -476,6 +491,11 @@ class Context:
 
     def dd_run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_dd_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    def dd_run_sched(self, itime0, nsteps, it0, sched, h, time_s=0.0):
+        hh, tt = C.c_double(float(h)), C.c_double(float(time_s))
+        rc = self._chk(self.lib.mdb_dd_run_sched(self.h, itime0, nsteps, it0, C.byref(sched), C.byref(hh), C.byref(tt)))
+        return rc, hh.value, tt.value
 
     def dd_global_t(self):
         t = C.c_double(0.0)

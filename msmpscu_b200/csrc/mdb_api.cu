@@ -123,6 +123,8 @@ static void free_state(mdb_ctx *c)
     dfree(c->ic); dfree(c->ic_alt); dfree(c->xp_view); dfree(c->den_view);
     dfree(c->slot); dfree(c->srcof); dfree(c->tmp_orig); dfree(c->oob); dfree(c->vpart);
     dfree(c->dsr); c->dsr_bytes = 0;
+    dfree(c->dmax_blk); c->dmax_blk_bytes = 0;
+    dfree(c->tile_d2); c->tile_d2_bytes = 0; c->tile_guard_fresh = false;
     dfree(c->pos_snap); c->pos_snap_bytes = 0;
     if (c->stage) { cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
     c->has_box = false;
@@ -192,6 +194,10 @@ extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
         c->tiled.bank_order = value != 0; c->list_valid = false;
         return MDB_OK;
     }
+    if (option == MDB_OPT_TILE_GUARD && value >= -1 && value <= 1) {
+        c->opt_tile_guard = value;
+        return MDB_OK;
+    }
     if (option == MDB_OPT_FORCE_PATH && value >= MDB_FORCE_PATH_AUTO && value <= MDB_FORCE_PATH_TILED) {
         c->opt_force_path = value;
         c->list_valid = false; // the two paths keep different list formats
@@ -210,6 +216,7 @@ extern "C" int mdb_get_option(const mdb_ctx *c, int option)
     if (option == MDB_OPT_FUSE_EPILOGUE) return c->opt_fuse_epilogue;
     if (option == MDB_OPT_TILED_CLASSES) return c->tiled.use_classes ? 1 : 0;
     if (option == MDB_OPT_TILED_BANKORDER) return c->tiled.bank_order ? 1 : 0;
+    if (option == MDB_OPT_TILE_GUARD) return c->opt_tile_guard;
     if (option == MDB_OPT_ACTIVE_PATH) return c->tiled.active ? MDB_FORCE_PATH_TILED : MDB_FORCE_PATH_GENERIC;
     return MDB_ERR_ARG;
 }

@@ -163,8 +163,8 @@ static char *dd_field(mdb_ctx *c, int f, size_t &elem)
 static int dd_scratch(mdb_ctx *c)
 {
     if (c->dd_dev) return MDB_OK;
-    CUDA_TRY(c, cudaMalloc(&c->dd_dev, sizeof(int) * (4 * (size_t)c->dd_n + 64)));
-    CUDA_TRY(c, cudaMemsetAsync(c->dd_dev, 0, sizeof(int) * (4 * (size_t)c->dd_n + 64), c->stream));
+    CUDA_TRY(c, cudaMalloc(&c->dd_dev, sizeof(int) * (5 * (size_t)c->dd_n + 64)));   // [4 R] table, [64] scratch, [R] time-step masks
+    CUDA_TRY(c, cudaMemsetAsync(c->dd_dev, 0, sizeof(int) * (5 * (size_t)c->dd_n + 64), c->stream));
     return MDB_OK;
 }
 
@@ -597,13 +597,32 @@ extern "C" int mdb_dd_force(mdb_ctx *c, unsigned flags, double vtensor[9])
     return MDB_OK;
 }
 
-// nsteps x For_One_Step on the decomposed box, enqueued from here (no host round trip between the kernels and the exchanges
-// of a step; the host waits only inside a rebuild)
-extern "C" int mdb_dd_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab, double h)
+// Predictor_DEV's halving loop on the decomposed box: every rank's mask of objecting trial steps, OR-ed over the ranks
+static int dd_timestep(mdb_ctx *c, const mdb_sched *s, double *h)
 {
-    if (!c) return MDB_ERR_ARG;
-    if (!c->dd_on || !c->dd_built || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_dd_run: mdb_dd_build first");
-    CUDA_TRY(c, cudaSetDevice(c->dev));
+    int rc;
+    const int R = c->dd_n;
+    if ((rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_timestep_mask_launch(p, s->hmx, s->dmx * s->dmx); })) < 0) return rc;
+    unsigned mask = 0u;
+    if (!c->dd_peers.empty()) {
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        for (mdb_ctx *p : c->dd_peers) mask |= (unsigned)p->h_counters[CNT_SCRATCH];
+    } else {
+        int *all = c->dd_dev + 4 * R + 64;
+        NCCL_TRY(c, nccl().AllGather(c->counters + CNT_SCRATCH, all, 1, ncclInt, (ncclComm_t)c->dd_comm, c->stream));
+        std::vector<int> tab(R);
+        CUDA_TRY(c, cudaMemcpyAsync(tab.data(), all, sizeof(int) * R, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < R; r++) mask |= (unsigned)tab[r];
+    }
+    return mdb_timestep_from_mask(c, mask, s->hmx, h);
+}
+
+// nsteps x For_One_Step on the decomposed box, enqueued from here (no host round trip between the kernels and the exchanges
+// of a step; the host waits only inside a rebuild and at a time-step check).  sch == NULL: fixed step and list period.
+static int dd_run_impl(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_fixed, double h_fixed, const mdb_sched *sch, double *h_io,
+                       double *time_io)
+{
     int rc;
     // Overlap (peer-to-peer backend, >= 3 layers per rank): the exchange runs on a side stream while the INTERIOR tiles --
     // whose halos hold owned atoms only -- are computed; the two boundary layers follow once the ghost layers have landed.
@@ -616,22 +635,41 @@ extern "C" int mdb_dd_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_up
         CUDA_TRY(c, cudaStreamCreateWithFlags(&c->dd_xs, cudaStreamNonBlocking));
         for (int k = 0; k < 4; k++) CUDA_TRY(c, cudaEventCreateWithFlags(&c->dd_ev[k], cudaEventDisableTiming));
     }
+    // steps that close themselves (EPC friction, electronic stopping, corrector at their end): whenever the step size may
+    // change from one step to the next or stopping acts between friction and corrector; else the two ride in front of the
+    // next predictor
+    const bool closed = sch != nullptr || mdb_stopping_on(c);
+    all_ranks(c, [&](mdb_ctx *p) { p->var_step = sch && sch->ihdup < 0; return (int)MDB_OK; });
+    const bool guard = mdb_tile_guard_wanted(c);
+    struct Leave { mdb_ctx *c; ~Leave() { all_ranks(c, [](mdb_ctx *p) { p->var_step = false; p->tile_guard_fresh = false; return (int)MDB_OK; }); } } leave{c};
     const int t0 = c->dd_info[14], t1 = c->dd_info[15];
     auto select = [&](int a, int b, int a2, int b2) { c->tile_sel[0] = a; c->tile_sel[1] = b; c->tile_sel[2] = a2; c->tile_sel[3] = b2; };
-    auto pass_split = [&](unsigned flags, cudaEvent_t landed) -> int { // interior, wait for the ghosts, the two boundary layers
+    auto pass_split = [&](unsigned flags, cudaEvent_t landed, bool bounds) -> int { // interior, wait for the ghosts, the two boundary layers
+        int r = MDB_OK;
+        if (bounds) r = mdb_tile_guard_launch(c, t0 + tpl, t1 - tpl);
         select(t0 + tpl, t1 - tpl, 0, 0);
-        int r = mdb_force_tiled(c, flags);
+        if (r >= 0) r = mdb_force_tiled(c, flags);
         if (r >= 0) {
             if (cudaStreamWaitEvent(c->stream, landed, 0) != cudaSuccess) r = mdb_fail(c, MDB_ERR_CUDA, "cudaStreamWaitEvent failed");
+            // (the neighbours' displacement bounds are merged by now: the boundary tiles read them)
+            if (r >= 0 && bounds) r = mdb_tile_guard_launch(c, t0, t0 + tpl);
+            if (r >= 0 && bounds) r = mdb_tile_guard_launch(c, t1 - tpl, t1);
             select(t0, t0 + tpl, t1 - tpl, t1);
             if (r >= 0) r = mdb_force_tiled(c, flags);
         }
         c->tile_sel[0] = -1;
         return r;
     };
+    double h = h_io ? *h_io : h_fixed, t = time_io ? *time_io : 0.0;
     for (int s = 0; s < nsteps; s++) {
         const int itime = itime0 + s;
-        const int pre = (s == 0) ? 0 : 3; // EPC friction + corrector of the previous step ride in front of this predictor
+        int nb_uptab = nb_fixed;
+        if (sch) {
+            h = mdb_sched_h1(sch, itime, it0, h);
+            if (mdb_sched_check_due(sch, itime, it0) && (rc = dd_timestep(c, sch, &h)) < 0) return rc;
+            nb_uptab = mdb_sched_nb_uptab(sch, itime, it0);
+        }
+        const int pre = (s == 0 || closed) ? 0 : 3; // EPC friction + corrector of the previous step ride in front of this predictor
         if ((rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_predict_launch(p, h, pre); })) < 0) return rc;
         const bool rebuild = nb_uptab > 0 && (itime - it0) % nb_uptab == 0;
         if (overlap && !rebuild) {
@@ -639,23 +677,46 @@ extern "C" int mdb_dd_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_up
             CUDA_TRY(c, cudaStreamWaitEvent(c->dd_xs, c->dd_ev[0], 0));
             if ((rc = p2p_exchange(c, true, c->dd_xs)) < 0) return rc;
             CUDA_TRY(c, cudaEventRecord(c->dd_ev[1], c->dd_xs));
-            if ((rc = pass_split(MDB_DEN, c->dd_ev[1])) < 0) return rc;
+            if ((rc = pass_split(MDB_DEN, c->dd_ev[1], guard)) < 0) return rc;
             CUDA_TRY(c, cudaEventRecord(c->dd_ev[2], c->stream));
             CUDA_TRY(c, cudaStreamWaitEvent(c->dd_xs, c->dd_ev[2], 0));
             if ((rc = p2p_exchange(c, false, c->dd_xs)) < 0) return rc;
             CUDA_TRY(c, cudaEventRecord(c->dd_ev[3], c->dd_xs));
-            if ((rc = pass_split(MDB_FORCE | MDB_NOPASS1, c->dd_ev[3])) < 0) return rc;
-            continue;
+            if ((rc = pass_split(MDB_FORCE | MDB_NOPASS1, c->dd_ev[3], false)) < 0) return rc;
+        } else {
+            if ((rc = x_pos(c, !rebuild)) < 0) return rc;
+            if (rebuild && (rc = dd_local_rebuild(c)) < 0) return rc;
+            if (guard && !rebuild && (rc = all_ranks(c, [](mdb_ctx *p) { return mdb_tile_guard_launch(p, p->dd_info[14], p->dd_info[15]); })) < 0) return rc;
+            if ((rc = all_ranks(c, [](mdb_ctx *p) { return mdb_force_tiled(p, MDB_DEN); })) < 0) return rc;
+            if ((rc = x_pos(c, false)) < 0) return rc;
+            if ((rc = all_ranks(c, [](mdb_ctx *p) { return mdb_force_tiled(p, MDB_FORCE | MDB_NOPASS1); })) < 0) return rc;
         }
-        if ((rc = x_pos(c, !rebuild)) < 0) return rc;
-        if (rebuild && (rc = dd_local_rebuild(c)) < 0) return rc;
-        if ((rc = all_ranks(c, [](mdb_ctx *p) { return mdb_force_tiled(p, MDB_DEN); })) < 0) return rc;
-        if ((rc = x_pos(c, false)) < 0) return rc;
-        if ((rc = all_ranks(c, [](mdb_ctx *p) { return mdb_force_tiled(p, MDB_FORCE | MDB_NOPASS1); })) < 0) return rc;
+        all_ranks(c, [](mdb_ctx *p) { p->tile_guard_fresh = false; return (int)MDB_OK; }); // the bounds were this step's
+        if (closed && (rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_step_close_launch(p, h); })) < 0) return rc;
+        t += h;
     }
-    if (nsteps > 0 && (rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_epc_correct_launch(p, h); })) < 0) return rc;
+    if (!closed && nsteps > 0 && (rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_epc_correct_launch(p, h); })) < 0) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (h_io) *h_io = h;
+    if (time_io) *time_io = t;
     return p2p_check(c);
+}
+
+extern "C" int mdb_dd_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab, double h)
+{
+    if (!c) return MDB_ERR_ARG;
+    if (!c->dd_on || !c->dd_built || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_dd_run: mdb_dd_build first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    return dd_run_impl(c, itime0, nsteps, it0, nb_uptab, h, nullptr, nullptr, nullptr);
+}
+
+extern "C" int mdb_dd_run_sched(mdb_ctx *c, int itime0, int nsteps, int it0, const mdb_sched *s, double *h, double *time_s)
+{
+    if (!c || !s || !h) return mdb_fail(c, MDB_ERR_ARG, "mdb_dd_run_sched: null argument");
+    if (!c->dd_on || !c->dd_built || !c->list_valid) return mdb_fail(c, MDB_ERR_STATE, "mdb_dd_run_sched: mdb_dd_build first");
+    if (s->nb_uptabmi < 1 || (s->ihdup != 0 && !(s->hmx > 0.0))) return mdb_fail(c, MDB_ERR_ARG, "mdb_dd_run_sched: bad schedule");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    return dd_run_impl(c, itime0, nsteps, it0, 0, *h, s, h, time_s);
 }
 
 // Cal_GlobalT_DEV (CommonGPU/MD_DiffScheme_GPU.F90:1042-1064) on the decomposed box: EKIN of the owned atoms of every rank

@@ -150,6 +150,34 @@ k_tile_desc(TileParams P, const int *__restrict__ nac, const int *__restrict__ i
     if (threadIdx.x == 0 && (H.htot > P.hcap || H.own_count > P.ocap || H.nrun > TILE_MAX_RUN)) atomicAdd(&counters[CNT_TILE_OVERFLOW], 1);
 }
 
+// Per-tile displacement bound of cascade runs: one warp per tile takes the maximum of the predictor's per-block maxima
+// (blocks of 256 atoms of the owned range [a0, a1)) over the tile's halo runs.  A run that reaches into ghost layers
+// (slab decomposition) or any atom outside the predictor's range takes the global maximum, which the ghost exchange has
+// merged with the neighbours' by then.  One fast atom then sends only the tiles around it to the full list.
+__global__ void __launch_bounds__(256)
+k_tile_d2(const TileDesc *__restrict__ desc, int tile_lo, int ntl, const float *__restrict__ dmax_blk, int a0, int a1,
+          const int *__restrict__ counters, float *__restrict__ tile_d2)
+{
+    const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= ntl) return;
+    const TileDesc &D = desc[tile_lo + w];
+    const int nrun = D.nrun;
+    float m = 0.f;
+    bool outside = nrun > TILE_MAX_RUN;
+    if (lane < min(nrun, TILE_MAX_RUN)) {
+        const int g0 = D.rgst[lane], g1 = g0 + D.rslot[lane + 1] - D.rslot[lane];
+        if (g1 > g0) {
+            outside = outside || g0 < a0 || g1 > a1;
+            const int lo = max(g0, a0), hi = min(g1, a1);
+            if (hi > lo)
+                for (int b = (lo - a0) >> 8; b <= (hi - 1 - a0) >> 8; b++) m = fmaxf(m, dmax_blk[b]);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (__any_sync(0xffffffffu, outside)) m = fmaxf(m, __int_as_float(counters[CNT_D2MAX]));
+    if (lane == 0) tile_d2[tile_lo + w] = m;
+}
+
 // One CTA per tile, one warp per owned cell (lanes = atoms of the cell).  The tile's halo is staged once in shared
 // memory as the reference's fp32 candidate SPOS = (float)(XP + (double)(float)shift) (:1100-1103) with the type in
 // .w; every lane then walks the 27 neighbour cells as 9 contiguous slot ranges (broadcast reads), decides
@@ -513,6 +541,8 @@ struct TilePassArgs {
     // row_a while d2 <= safe_a, else row row_b while d2 <= safe_b, else the full list (KVOIS)
     float safe_a, safe_b;
     int row_a, row_b;
+    // per-tile displacement bound (k_tile_d2, cascade runs): when set, a tile decides on ITS halo's maximum instead of the global one
+    const float *tile_d2;
     int fuse;              // fused epilogue of pass 2 (mdb_run): bit 0 EPC friction, bit 1 corrector half-kick
     int tile_lo, tile_hi;  // tiles of this rank (slab decomposition), [0, ntiles) otherwise
     int tile_lo2, tile_hi2; // an optional second range (boundary layers of a slab: first and last layer in one launch)
@@ -643,7 +673,7 @@ k_tile_pass(TileParams P, TilePassArgs A)
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // TMA bytes landed
     unsigned long long *bar_ready = bar_full + TP_MAXBUF;                        // producer finished the stage
     unsigned long long *bar_empty = bar_ready + TP_MAXBUF;                       // every consumer warp left the stage
-    int *s_info = reinterpret_cast<int *>(smem + 96);                             // [stage][own_start, own_slot0, own_count, edge]
+    int *s_info = reinterpret_cast<int *>(smem + 96);                             // [stage][own_start, own_slot0, own_count, edge, scan mode]
     int *s_ctr = reinterpret_cast<int *>(smem + 160);                             // [stage] next owned atom to hand out
     double2 *s_tab = reinterpret_cast<double2 *>(smem + TP_HDR_BYTES);
     unsigned char *buf0 = smem + TP_HDR_BYTES + tp_tab_bytes(A.ktab);
@@ -689,13 +719,11 @@ k_tile_pass(TileParams P, TilePassArgs A)
         }
     }
     __syncthreads();
-    // distance classes are usable while no atom has moved more than half the class margin since the rebuild
-    const float d2max = __int_as_float(A.counters[CNT_D2MAX]);
-    const bool safe = d2max <= A.safe_a || d2max <= A.safe_b;
-    const int cls_row = d2max <= A.safe_a ? A.row_a : A.row_b;
+    // distance classes are usable while no atom (of the tile's halo, when the per-tile bounds are given) has moved more than half
+    // the class margin since the rebuild.  mode: class-count row 0 / 1, or 2 = the full list (KVOIS)
+    const float d2glob = __int_as_float(A.counters[CNT_D2MAX]);
+    auto mode_of = [&](const float d2) -> int { return d2 <= A.safe_a ? A.row_a : (d2 <= A.safe_b ? A.row_b : 2); };
     const uint2 *nbl2 = reinterpret_cast<const uint2 *>(A.nbl);
-    // flat index of the class count of owned atom 0 (uint16 array [2][npad]) = ncl_base + own_start
-    const size_t ncl_base = (size_t)cls_row * P.npad;
 
     const int nt1 = A.tile_hi - A.tile_lo, nvt = nt1 + (A.tile_hi2 - A.tile_lo2); // tiles of this launch: range 1, then range 2
     if (warp == NCW) {
@@ -703,13 +731,15 @@ k_tile_pass(TileParams P, TilePassArgs A)
         // Everything a stage needs arrives by TMA: halo runs, the first index group, and 16-byte aligned windows of
         // STATU and of the scan counts around the owned range.  The descriptor of the NEXT tile is loaded one tile
         // ahead and only used in the next iteration, so no global-memory round trip sits on the per-tile path.
-        struct Pre { int htot, nrun, edge_any, own_start, own_slot0, own_count, rs0, rs1, rgst; };
+        struct Pre { int htot, nrun, edge_any, own_start, own_slot0, own_count, rs0, rs1, rgst; float d2; };
         auto prefetch = [&](int v) {
             Pre q;
             q.htot = 0; q.nrun = 0; q.edge_any = 0; q.own_start = 0; q.own_slot0 = 0; q.own_count = 0; q.rs0 = 0; q.rs1 = 0; q.rgst = 0;
+            q.d2 = d2glob;
             if (v < nvt) {
                 const int tile = v < nt1 ? A.tile_lo + v : A.tile_lo2 + (v - nt1);
                 const TileDesc &D = A.desc[tile];
+                if (A.tile_d2) q.d2 = A.tile_d2[tile];
                 q.htot = D.htot; q.nrun = D.nrun; q.edge_any = D.edge_any;
                 q.own_start = D.own_start; q.own_slot0 = D.own_slot0; q.own_count = D.own_count;
                 q.rs0 = D.rslot[lane]; q.rs1 = D.rslot[lane + 1]; q.rgst = D.rgst[lane]; // lane r: run r (entries past nrun unused)
@@ -724,6 +754,9 @@ k_tile_pass(TileParams P, TilePassArgs A)
             const Pre cur = nx;
             int own_count = cur.own_count;
             const bool fits = cur.htot <= P.hcap && own_count <= P.ocap && cur.nrun <= TILE_MAX_RUN;
+            const int mode = mode_of(cur.d2);
+            const bool safe = mode < 2;
+            const size_t ncl_base = (size_t)(mode & 1) * P.npad; // flat index of the class count of owned atom 0 (uint16 [2][npad]) = ncl_base + own_start
             mbar_wait(&bar_empty[b], (u & 1u) ^ 1u);
             unsigned char *bp = buf0 + b * bufb;
             double4 *sp = reinterpret_cast<double4 *>(bp);
@@ -769,8 +802,8 @@ k_tile_pass(TileParams P, TilePassArgs A)
                 if (lane == 0) mbar_arrive(&bar_full[b]);
             }
             if (lane == 0) {
-                s_info[4 * b + 0] = cur.own_start; s_info[4 * b + 1] = cur.own_slot0; s_info[4 * b + 2] = own_count;
-                s_info[4 * b + 3] = cur.edge_any;
+                s_info[5 * b + 0] = cur.own_start; s_info[5 * b + 1] = cur.own_slot0; s_info[5 * b + 2] = own_count;
+                s_info[5 * b + 3] = cur.edge_any; s_info[5 * b + 4] = mode;
                 s_ctr[b] = 0;
             }
             mbar_arrive(&bar_ready[b]); // all 32 lanes: their writes to the stage are released to the consumers
@@ -783,8 +816,11 @@ k_tile_pass(TileParams P, TilePassArgs A)
         for (int v = blockIdx.x; v < nvt; v += gridDim.x) {
             mbar_wait(&bar_ready[b], u & 1u);
             mbar_wait(&bar_full[b], u & 1u);
-            const int own_start = s_info[4 * b + 0], own_slot0 = s_info[4 * b + 1], own_count = s_info[4 * b + 2];
-            const bool edge_tile = s_info[4 * b + 3] != 0;
+            const int own_start = s_info[5 * b + 0], own_slot0 = s_info[5 * b + 1], own_count = s_info[5 * b + 2];
+            const bool edge_tile = s_info[5 * b + 3] != 0;
+            const int mode = s_info[5 * b + 4];
+            const bool safe = mode < 2;
+            const size_t ncl_base = (size_t)(mode & 1) * P.npad;
             const unsigned char *bp = buf0 + b * bufb;
             const double4 *sp = reinterpret_cast<const double4 *>(bp);
             const uint2 *sidx = reinterpret_cast<const uint2 *>(bp + o_idx);
@@ -1156,6 +1192,10 @@ int mdb_tiled_plan(mdb_ctx *c)
     if (!ensure((void **)&S.desc, S.desc_bytes, (size_t)P.ntiles * sizeof(TileDesc))) return MDB_OK;
     if (!ensure((void **)&c->dsr, c->dsr_bytes, 3 * (size_t)c->n * sizeof(float))) return MDB_OK;
     cudaMemsetAsync(c->dsr, 0, 3 * (size_t)c->n * sizeof(float), c->stream);
+    if (!ensure((void **)&c->dmax_blk, c->dmax_blk_bytes, sizeof(float) * ((size_t)c->n / 256 + 2))) return MDB_OK;
+    if (!ensure((void **)&c->tile_d2, c->tile_d2_bytes, sizeof(float) * (size_t)P.ntiles)) return MDB_OK;
+    cudaMemsetAsync(c->dmax_blk, 0, c->dmax_blk_bytes, c->stream);
+    c->tile_guard_fresh = false;
 
     // ---- launch configuration: one persistent CTA per SM
     int nsm = 148;
@@ -1247,6 +1287,19 @@ int mdb_tiled_nlist(mdb_ctx *c)
     return mdb_fail(c, MDB_ERR_ARG, "tiled path: unsupported lane-group size %d", c->tiled.G);
 }
 
+// per-tile displacement bounds for the tiles [lo, hi) (the passes of this step use them until mdb_tile_guard_clear)
+int mdb_tile_guard_launch(mdb_ctx *c, int lo, int hi)
+{
+    TiledState &S = c->tiled;
+    if (!S.active || !c->dmax_blk || !c->tile_d2 || hi <= lo) return MDB_OK;
+    ProfScope ps(c, MDB_K_OTHER);
+    k_tile_d2<<<cdiv(hi - lo, 8), 256, 0, c->stream>>>((const TileDesc *)S.desc, lo, hi - lo, c->dmax_blk, own_a0(c), own_a1(c), c->counters,
+                                                     c->tile_d2);
+    CUDA_TRY(c, cudaGetLastError());
+    c->tile_guard_fresh = true;
+    return MDB_OK;
+}
+
 template <int PASS, int G, bool MT, bool FUSE, int NT, bool VIR = false>
 static int launch_pass(mdb_ctx *c, int fuse, double hs2)
 {
@@ -1276,6 +1329,7 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     if (PASS == 1) { A.safe_a = S.safe_d2[0]; A.row_a = 0; A.safe_b = S.safe_d2[2]; A.row_b = 1; }
     else { A.safe_a = S.safe_d2[1]; A.row_a = 1; A.safe_b = -1.0f; A.row_b = 1; }
     if (!S.use_classes || (PASS == 3 && !S.epot_in_class1)) { A.safe_a = -1.0f; A.safe_b = -1.0f; }
+    A.tile_d2 = c->tile_guard_fresh ? c->tile_d2 : nullptr;
     A.fuse = fuse; A.hs2 = hs2; A.xp1 = c->xp1; A.epc = c->epc; A.mass = c->mass;
     A.tile_lo = c->dd_on ? c->dd_info[14] : 0;
     A.tile_hi = c->dd_on ? c->dd_info[15] : S.P.ntiles;

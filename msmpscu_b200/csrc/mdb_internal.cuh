@@ -111,6 +111,13 @@ struct mdb_ctx {
     int *gid = nullptr, *gid_alt = nullptr, *gidinv = nullptr;
     int *ic = nullptr, *ic_alt = nullptr;
     float *dsr = nullptr; size_t dsr_bytes = 0; // displacement since the last rebuild, (N,3) fp32
+    // cascade runs: per-block (256 atoms of the predictor's range) maxima of |dsr|^2 and the per-tile bounds derived from them;
+    // the passes read tile_d2 only between mdb_tile_guard_launch and the end of the same step (tile_guard_fresh)
+    float *dmax_blk = nullptr; size_t dmax_blk_bytes = 0;
+    float *tile_d2 = nullptr; size_t tile_d2_bytes = 0;
+    bool tile_guard_fresh = false;
+    bool var_step = false;     // inside a run with the displacement-limited time step (mdb_run_sched, IHDUP < 0)
+    int opt_tile_guard = -1;   // -1 auto (on with electronic stopping or a displacement-limited time step), 0 off, 1 on
     // materialised reference-shaped views
     double *xp_view = nullptr, *den_view = nullptr;
     // staging for up/download
@@ -234,6 +241,14 @@ int mdb_cells_dd_place(mdb_ctx *c, const int cand[6], int zl0, int zl1, int base
 int mdb_cells_dd_ghost_layer(mdb_ctx *c, int c0, int first);
 int mdb_predict_launch(mdb_ctx *c, double h, int pre);    // mdb_step.cu
 int mdb_epc_correct_launch(mdb_ctx *c, double h);
+int mdb_step_close_launch(mdb_ctx *c, double h);          // EPC friction [, stopping], corrector on the owned range
+int mdb_timestep_mask_launch(mdb_ctx *c, double hmx, double dmx2);                 // mdb_step.cu : variable time step (scheme II)
+int mdb_timestep_from_mask(mdb_ctx *c, unsigned mask, double hmx, double *h);
+int mdb_sched_nb_uptab(const mdb_sched *s, int itime, int it0);
+bool mdb_sched_check_due(const mdb_sched *s, int itime, int it0);
+double mdb_sched_h1(const mdb_sched *s, int itime, int it0, double h);
+bool mdb_tile_guard_wanted(const mdb_ctx *c);
+int mdb_tile_guard_launch(mdb_ctx *c, int lo, int hi);    // mdb_force_tiled.cu : per-tile displacement bounds for this step's passes
 void mdb_dd_free(mdb_ctx *c);                 // mdb_dd.cu
 int mdb_stopping_launch(mdb_ctx *c);          // mdb_cascade.cu : electronic stopping on FP (no-op when switched off)
 bool mdb_stopping_on(const mdb_ctx *c);

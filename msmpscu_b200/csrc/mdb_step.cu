@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, 4) k_predict(int n, double4 *__restrict__
                           double *__restrict__ dis, int *__restrict__ statu, const int *__restrict__ ityp,
                           MassParams M, BoxParams box, double th, double h2s2, double hs2,
                           float *__restrict__ dsr, int *__restrict__ counters, int a0, int a1, int pre, EpcParams E,
-                          const int *__restrict__ skip)
+                          const int *__restrict__ skip, float *__restrict__ dmax_blk)
 {
     if (skip && *skip) return; // converged quench iteration (mdb_dyndamp)
     const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256, 4) k_predict(int n, double4 *__restrict__
             float m = smax[0];
             for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, smax[w]);
             if (m > 0.f) atomicMax(&counters[CNT_D2MAX], __float_as_int(m)); // non-negative floats order like ints
+            if (dmax_blk) dmax_blk[blockIdx.x] = m; // per-block bound for the per-tile decision of cascade runs (k_tile_d2)
         }
     }
 }
@@ -161,7 +162,8 @@ static int predict_launch(mdb_ctx *c, double h, int pre)
     ProfScope ps(c, MDB_K_PREDICT);
     k_predict<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp,
                                                                      c->mass, c->box, th, h2s2, hs2, c->dsr, c->counters,
-                                                                     own_a0(c), own_a1(c), pre, c->epc, c->skip_flag);
+                                                                     own_a0(c), own_a1(c), pre, c->epc, c->skip_flag,
+                                                                     c->dsr ? c->dmax_blk : nullptr);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -196,6 +198,24 @@ extern "C" int mdb_damping(mdb_ctx *c)
 }
 
 int mdb_predict_launch(mdb_ctx *c, double h, int pre) { return predict_launch(c, h, pre); }
+// the end of a step that is not fused into the next one: Do_EPCForce_DEV = EPC friction, then electronic stopping
+// (MD_LocalTempMethod_GPU.F90:135-136), then Correction_DEV; one kernel when stopping is off
+int mdb_step_close_launch(mdb_ctx *c, double h)
+{
+    const int a0 = own_a0(c), a1 = own_a1(c);
+    if (!mdb_stopping_on(c)) return mdb_epc_correct_launch(c, h);
+    {
+        ProfScope ps(c, MDB_K_CORRECT);
+        if (c->epc.on)
+            k_epc_correct<<<cdiv(a1 - a0, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, 0.0, 1, 0, a0, a1);
+    }
+    int rc = mdb_stopping_launch(c);
+    if (rc < 0) return rc;
+    ProfScope ps(c, MDB_K_CORRECT);
+    k_epc_correct<<<cdiv(a1 - a0, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, h * 0.5, 0, 1, a0, a1);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
 int mdb_epc_correct_launch(mdb_ctx *c, double h)
 {
     ProfScope ps(c, MDB_K_CORRECT);
@@ -344,6 +364,71 @@ __global__ void k_check_timestep(int n, const double *__restrict__ xp1, const do
         d2 = __dadd_rn(d2, __dmul_rn(dd, dd));
     }
     if (d2 > mxd2) *flag = 1;
+}
+
+// The halving loop of Predictor_DEV (:633-655) in one pass: bit k of *mask is set when CheckTimestep_KERNEL would raise its
+// flag for the trial step TH_k = HMX 2^-k (H2S2_k = TH_k TH_k / 2, both exact scalings of the reference's sequence).  The
+// reference halves until no atom objects: its result is TH_k for the lowest clear bit.
+#define TS_MAXHALVE 31
+__global__ void k_timestep_mask(int n, const double *__restrict__ xp1, const double *__restrict__ fp, const int *__restrict__ statu,
+                                const int *__restrict__ ityp, MassParams M, double hmx, double mxd2, unsigned *__restrict__ mask,
+                                int a0, int a1)
+{
+    const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned m = 0u;
+    if (i < a1) {
+        const int st = statu[i];
+        if ((st & ST_ACTIVE) == ST_ACTIVE) {
+            const double cm0 = M.cm[ityp[i] - 1];
+            double v[3], a[3];
+            bool fr[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                fr[d] = (st & (ST_FIXPOSX << d)) == 0;
+                v[d] = xp1[i + (size_t)d * n];
+                a[d] = __ddiv_rn(fp[i + (size_t)d * n], cm0);
+            }
+            double th = hmx;
+            for (int k = 0; k < TS_MAXHALVE; k++) {
+                const double h2s2 = __dmul_rn(__dmul_rn(th, th), 0.5);
+                double d2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double dd = fr[d] ? __dadd_rn(__dmul_rn(th, v[d]), __dmul_rn(h2s2, a[d])) : 0.0;
+                    d2 = __dadd_rn(d2, __dmul_rn(dd, dd));
+                }
+                if (d2 > mxd2) m |= 1u << k;
+                th = __dmul_rn(th, 0.5);
+            }
+        }
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(mask, m);
+}
+// enqueues the mask of this rank's atoms and its copy to h_counters[CNT_SCRATCH] (the caller synchronises)
+int mdb_timestep_mask_launch(mdb_ctx *c, double hmx, double dmx2)
+{
+    unsigned *mask = reinterpret_cast<unsigned *>(c->counters + CNT_SCRATCH);
+    CUDA_TRY(c, cudaMemsetAsync(mask, 0, sizeof(int), c->stream));
+    {
+        ProfScope ps(c, MDB_K_OTHER);
+        k_timestep_mask<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, hmx, dmx2,
+                                                                                mask, own_a0(c), own_a1(c));
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + CNT_SCRATCH, mask, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return MDB_OK;
+}
+// TH for the OR of the ranks' masks; < 0 when even HMX 2^-30 moves an atom further than DMX
+int mdb_timestep_from_mask(mdb_ctx *c, unsigned mask, double hmx, double *h)
+{
+    int k = 0;
+    while (k < TS_MAXHALVE && (mask >> k & 1u)) k++;
+    if (k >= TS_MAXHALVE) return mdb_fail(c, MDB_ERR_STATE, "variable time step: an atom moves more than DMX even with HMX/2^%d", TS_MAXHALVE - 1);
+    double th = hmx;
+    for (int j = 0; j < k; j++) th = th * 0.5; // m_TH = m_TH*C_HALF :648
+    *h = th;
+    return MDB_OK;
 }
 
 // fills per-box sums on the host (pinned staging); returns nbox or <0
@@ -496,24 +581,17 @@ static int step_nosync(mdb_ctx *c, int itime, int it0, int nb_uptab, double h, b
         // the capacity counters are read back at once (a 48-byte copy and a synchronisation per list period): an overflow of
         // the tiled path is redone on the generic path before any force is evaluated on the new list
         if ((rc = mdb_list_rebuild_checked(c)) < 0) return rc;
+    } else if (mdb_tile_guard_wanted(c) && c->list_valid && !c->list_reordered) {
+        // cascade runs: one fast atom must not send every tile to the full list -- per-tile displacement bounds for this step
+        if ((rc = mdb_tile_guard_launch(c, 0, c->tiled.P.ntiles)) < 0) return rc;
     }
+    struct GuardOff { mdb_ctx *c; ~GuardOff() { c->tile_guard_fresh = false; } } guard_off{c}; // the bounds are this step's only
     if (fused_epilogue && c->list_valid && !c->list_reordered) {
         // EPC friction and the corrector are fused into the epilogue of the force pass
         return mdb_force_tiled(c, MDB_FORCE, 3, h * 0.5);
     }
     if ((rc = mdb_force(c, MDB_FORCE, nullptr)) < 0) return rc;
-    if (stopping) {
-        {
-            ProfScope ps(c, MDB_K_CORRECT);
-            if (c->epc.on)
-                k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, 0.0, 1, 0, 0, c->n);
-        }
-        if ((rc = mdb_stopping_launch(c)) < 0) return rc;
-        ProfScope ps(c, MDB_K_CORRECT);
-        k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, h * 0.5, 0, 1, 0, c->n);
-        CUDA_TRY(c, cudaGetLastError());
-        return MDB_OK;
-    }
+    if (stopping) return mdb_step_close_launch(c, h);
     if (!last) return MDB_OK; // applied by the next step's predictor kernel
     ProfScope ps(c, MDB_K_CORRECT);
     k_epc_correct<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
@@ -552,4 +630,64 @@ extern "C" int mdb_run(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_uptab
 extern "C" int mdb_step(mdb_ctx *c, int itime, int it0, int nb_uptab, double h)
 {
     return mdb_run(c, itime, 1, it0, nb_uptab, h);
+}
+
+// ------------------------------------------------------------------------------------
+// The time loop of the GMD method with its step-size and list-period schedules (Appshell/MD_Method_GenericMD_GPU.F90:351-361)
+// and the displacement-limited step of Predictor_DEV (CommonGPU/MD_DiffScheme_GPU.F90:633-655).
+// ------------------------------------------------------------------------------------
+bool mdb_tile_guard_wanted(const mdb_ctx *c)
+{
+    if (!c->tiled.active || !c->tiled.use_classes || !c->dsr) return false;
+    if (c->opt_tile_guard >= 0) return c->opt_tile_guard == 1;
+    return mdb_stopping_on(c) || c->var_step;
+}
+int mdb_sched_nb_uptab(const mdb_sched *s, int itime, int it0)
+{
+    if (s->nb_dbitab <= 0) return s->nb_uptabmi;
+    const int v = s->nb_uptabmi * ((itime - it0 + 1) / s->nb_dbitab + 1); // NB_UPTABMI*(int((ITIME-IT0+1)/NB_DBITAB)+1) :359
+    return v > s->nb_uptabmx ? s->nb_uptabmx : v;
+}
+bool mdb_sched_check_due(const mdb_sched *s, int itime, int it0)
+{
+    return s->ihdup < 0 && (itime - it0 + 1) % (-s->ihdup) == 0; // MOD(ITIME-IT0+1,IABS(IHDUP)) == 0 :637
+}
+double mdb_sched_h1(const mdb_sched *s, int itime, int it0, double h)
+{
+    if (s->ihdup <= 0) return h;
+    const double v = s->hmi * (double)((itime - it0 + 1) / s->ihdup + 1);  // HMI*(int((ITIME-IT0+1)/IHDUP)+1) :354
+    return v > s->hmx ? s->hmx : v;
+}
+
+extern "C" int mdb_run_sched(mdb_ctx *c, int itime0, int nsteps, int it0, const mdb_sched *s, double *h, double *time_s)
+{
+    if (!c || !s || !h) return mdb_fail(c, MDB_ERR_ARG, "mdb_run_sched: null argument");
+    if (c->dd_on) return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_run_sched: use mdb_dd_run_sched in slab-decomposed runs");
+    if (!c->has_box || !c->has_tables || !c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_run_sched: box, tables and list must be set");
+    if (s->nb_uptabmi < 1 || (s->ihdup != 0 && !(s->hmx > 0.0))) return mdb_fail(c, MDB_ERR_ARG, "mdb_run_sched: bad schedule");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    CUDA_TRY(c, cudaMemsetAsync(c->counters + CNT_OOB_TOTAL, 0, sizeof(int), c->stream));
+    c->var_step = s->ihdup < 0;
+    double hh = *h, t = time_s ? *time_s : 0.0;
+    int rc = MDB_OK;
+    for (int k = 0; k < nsteps && rc >= 0; k++) {
+        const int itime = itime0 + k;
+        hh = mdb_sched_h1(s, itime, it0, hh);
+        if (mdb_sched_check_due(s, itime, it0)) {
+            if ((rc = mdb_timestep_mask_launch(c, s->hmx, s->dmx * s->dmx)) < 0) break;
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = mdb_fail(c, MDB_ERR_CUDA, "mdb_run_sched: synchronisation failed"); break; }
+            if ((rc = mdb_timestep_from_mask(c, (unsigned)c->h_counters[CNT_SCRATCH], s->hmx, &hh)) < 0) break;
+        }
+        // the step may differ from its neighbours': EPC friction and the corrector close every step (nothing rides in front of
+        // the next predictor), and CheckTimestep sees the corrected velocities as in the reference
+        rc = step_nosync(c, itime, it0, mdb_sched_nb_uptab(s, itime, it0), hh, true, true);
+        t += hh; // TIME = TIME + H :367 (here in seconds)
+    }
+    c->var_step = false;
+    if (rc < 0) return rc;
+    *h = hh;
+    if (time_s) *time_s = t;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(int) * CNT__N, cudaMemcpyDeviceToHost, c->stream));
+    c->run_pending = true;
+    return mdb_sync(c);
 }
