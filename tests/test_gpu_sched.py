@@ -78,7 +78,7 @@ def test_run_sched_matches_the_oracle_loop(oracle, ihdup):
 def test_per_tile_displacement_bounds_change_nothing_but_the_work():
     """the class shortcut is exact, so per-tile bounds (on), the global bound (off) and the full list (classes off) must give
     bit-identical trajectories; with the PKA in the box the global bound trips, the per-tile one only around the PKA"""
-    c, ipka = _pka_case((12, 12, 12), ekev=3.0)
+    c, ipka = _pka_case((48, 48, 48), ekev=3.0)      # 221 184 atoms: large enough for the pass times to show the work
     ng = len(c.mass)
     epc = ([1] * ng, [300.0] * ng, [1.0e-12] * ng, [0.1] * ng, [100.0 * EV] * ng)
     s = _sched(c, -1)
@@ -101,7 +101,7 @@ def test_per_tile_displacement_bounds_change_nothing_but_the_work():
     # the work: per-tile bounds must keep the passes clearly below the full-list cost the global bound falls back to
     ms = lambda p: p["pass1"][1] + p["pass2"][1]
     print("pass ms: per-tile %.3f  global %.3f  auto %.3f  full list %.3f" % tuple(ms(o[5]) for o in out))
-    assert ms(out[0][5]) < 0.9 * ms(out[1][5])
+    assert ms(out[0][5]) < 0.8 * ms(out[1][5])
     assert abs(ms(out[2][5]) - ms(out[0][5])) < 0.25 * ms(out[0][5])     # auto = on in a displacement-limited run
 
 
