@@ -49,6 +49,7 @@ MD_PER_PERIOD = 10    # NB_UPTAB: MD steps per neighbour-list period
 PERIODS_PER_STEP = 10
 MD_PER_STEP = MD_PER_PERIOD * PERIODS_PER_STEP   # one output interval
 H = 0.5e-15           # s
+CP_EVERG = 1.60219e-12  # MSMLIB/sor/Common/MSM_Const.F90:74
 A0 = 3.1652           # Angstrom
 RU_LU, NB_FAC, MXKVOIS, NTAB = 1.9, 1.2, 256, 10000
 K_LIST = 112          # stored neighbours per atom for this lattice / cutoff
@@ -84,6 +85,7 @@ def parse():
     ap.add_argument("--c3-boxes", type=int, default=512, help="boxes of the configs[2] sub-record (512 x 16 000 atoms; 0 = skip)")
     ap.add_argument("--c4-replicas", type=int, default=96, help="replicas of the configs[3] sub-record (PARREP_Test asks for 100; 96 "
                     "divides over 1/2/4/8 GPUs; 0 = skip)")
+    ap.add_argument("--dd-pka-kev", type=float, default=10.0, help="energy of the PKA of the cascade phase of the one-box run (0: skip)")
     ap.add_argument("--dd-cells", type=int, default=200, help="edge (bcc cells) of the single box of the dd_strong sub-record "
                     "(200 -> 16 M atoms; 0 = skip)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the timed CPU loop")
@@ -690,6 +692,7 @@ def dd_measure(args, cells, blocks, warm):
         dist.all_gather_object(allp, prof)
         prof = {k: [p.get(k, 0.0) for p in allp] for k in prof}
     a0, a1 = dom.owned()
+    cascade = dd_cascade(args, c, ctx, dom, stream, itime, blocks, barrier, world) if args.dd_pka_kev > 0 else None
     rec = {"value": n * MD_PER_PERIOD * blocks / (ms * 1e-3), "unit": "atom-steps/s", "scaling": "strong", "atoms_total": n,
            "atoms_owned_rank0": a1 - a0, "n_gpus": world, "blocks": blocks, "md_steps_per_block": MD_PER_PERIOD,
            "ms_per_block": ms / blocks, "gpu_launches": int(launches), "clocks": clocks,
@@ -697,8 +700,64 @@ def dd_measure(args, cells, blocks, warm):
            "workload": "configs[4] family: ONE bcc W box of %d atoms (%d^3 cells) cut into %d z-slabs; per step two ghost-layer "
                        "exchanges of {x,y,z,den} records (ncclSend/ncclRecv enqueued by the library), per %d steps a local rebuild "
                        "of the rank's slab (no broadcast, no all-atom sort)" % (n, cells, world, MD_PER_PERIOD)}
+    if cascade:
+        rec["cascade"] = cascade
     ctx.close()
     return rec
+
+
+def dd_cascade(args, c, ctx, dom, stream, itime, blocks, barrier, world):
+    """configs[4] as SURVEY.md 8(d) specifies it: the same box with ONE primary knock-on atom at the centre (velocity along <135>),
+    run the way the reference runs cascades (examples/Cascade_Test/CtrlFile300K_LOC_T.dat): displacement-limited time step
+    (&STEPSIZE flag -1, hmx 0.5 fs, dmx 0.05 LU), EPC + electronic stopping on the atoms, list rebuilt every 10 steps.  The
+    stopping table is of the Lindhard-Scharff form S(E) = k sqrt(E) with k for W in W (the reference builds its LS_Z85 table
+    from the same law; the global-density model is the one the library has)."""
+    import torch
+    import torch.distributed as dist
+    from msmpscu_b200 import capi
+
+    n = c.xp.shape[0]
+    centre = c.boxlow + 0.5 * c.zl
+    ipka = int(np.argmin(np.sum((c.xp - centre) ** 2, axis=1))) + 1                    # ORIGINAL id (1-based)
+    ekev = float(args.dd_pka_kev)
+    ctx.pka_insert(ipka, ekev * 1000.0 * CP_EVERG, [1.0, 3.0, 5.0])
+    etab = np.linspace(20.0, 2.0e5, 20001) * CP_EVERG                                 # uniform grid as the reference's tables; &EMIN 20 eV
+    k_ls = 69.3e-15 * CP_EVERG                                                       # erg cm^2 per sqrt(eV): 1.212 Z^(7/6) Z / ((2 Z^(2/3))^(3/4) sqrt(M)) x 1e-15 eV cm^2
+    stab = (k_ls * np.sqrt(etab / CP_EVERG)).reshape(-1, 1)
+    mden = n / float(np.prod(c.zl))
+    ctx.stopping_set(etab, stab, np.array([[1]]), [1], [mden])
+    sched = capi.Sched(-1, H, H, 0.05 * c.rr, MD_PER_PERIOD, MD_PER_PERIOD, 100)
+    st = {"h": H, "t": 0.0}
+
+    def block():
+        _, st["h"], st["t"] = dom.run_sched(itime[0], MD_PER_PERIOD, 1, sched, st["h"], st["t"])
+        itime[0] += MD_PER_PERIOD
+
+    block()                                                                          # warm-up: the first steps of the PKA
+    h_first = st["h"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(blocks):
+        block()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))), dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ctx.prof_reset(); ctx.prof_enable(True)
+    block()
+    prof = {k: round(v[1], 3) for k, v in ctx.prof_get().items() if v[0]}
+    ctx.prof_enable(False)
+    return {"value": n * MD_PER_PERIOD * blocks / (ms * 1e-3), "unit": "atom-steps/s", "ms_per_block": ms / blocks, "blocks": blocks,
+            "pka_kev": ekev, "pka_original_id": ipka, "h_fs_after_first_block": h_first * 1e15, "h_fs_last": st["h"] * 1e15,
+            "simulated_fs": st["t"] * 1e15, "phase_ms_per_block_rank0": prof,
+            "workload": "the same box with one %.0f keV PKA at the centre along <135>: displacement-limited step (hmx 0.5 fs, dmx 0.05 a0, "
+                        "checked every step: one mask kernel + 4-byte read-back, OR-ed over the ranks), EPC + electronic stopping "
+                        "(Lindhard-Scharff form table, global-density model) between friction and corrector, per-tile displacement "
+                        "bounds for the distance-class shortcut" % ekev}
 
 
 def c3_measure(args, nbox_total, cells, blocks, warm):
@@ -844,7 +903,8 @@ def run_dd(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     rec = dd_measure(args, args.cells, args.steps, max(args.warmup, 3))
     line = base_line(args, rec["atoms_total"])
     line["scaling"] = "strong"
@@ -852,6 +912,8 @@ def run_dd(args):
                            "md_steps_per_step": MD_PER_PERIOD, "parallelism": "z-slab domain decomposition, 1 ghost cell layer per side"})
     line.update({"value": rec["value"], "ms_per_step": rec["ms_per_block"], "clocks": rec["clocks"], "gpu_launches": rec["gpu_launches"],
                  "force_path": "tiled", "mode": "dd", "phase_ms_per_block_by_rank": rec["phase_ms_per_block_by_rank"]})
+    if rec.get("cascade"):
+        line["cascade"] = rec["cascade"]
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -10,7 +10,7 @@
 // (:1221-1287).  Here the growth runs on the device (one kernel per extension step over the cells), same marks.
 #include <cstring>
 #include <vector>
-#include "mdb_internal.cuh"
+#include "mdb_stop.cuh"
 
 __global__ void k_ar_deactive_all(int n, int *__restrict__ statu) // DeActive_All_Kernel :242-279
 {
@@ -128,43 +128,19 @@ extern "C" int mdb_active_all(mdb_ctx *c, int on)
 // ------------------------------------------------------------------------------------
 // electronic stopping, global-density model: ST_MOD_GDEN_KERNEL :431-536
 // ------------------------------------------------------------------------------------
-struct StopParams {
-    int on, ne, nk, ng;
-    int enable[MDB_MXGROUP];
-    double mden[MDB_MXGROUP], cm2[MDB_MXGROUP];
-    int kpair[MDB_MXGROUP * MDB_MXGROUP]; // 1-based table index for (moving type, medium type) at i + ng*j
-};
-
 __global__ void k_stopping(int n, StopParams S, const double *__restrict__ etab, const double *__restrict__ stab,
                            const int *__restrict__ ityp, const int *__restrict__ statu, const double *__restrict__ xp1,
                            double *__restrict__ fp, int a0, int a1)
 {
     const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a1) return;
-    const int kk = ityp[i] - 1;
-    if ((statu[i] & ST_ACTIVE) != ST_ACTIVE || S.enable[kk] <= 0) return;
-    const double vx = xp1[i], vy = xp1[i + (size_t)n], vz = xp1[i + 2 * (size_t)n];
-    double vv = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
-    const double ek = __dmul_rn(S.cm2[kk], vv);                                           // EK = CM2(KK)*VV :509
-    const double emin = etab[0], emax = etab[S.ne - 1];
-    if (!(ek >= emin && ek <= emax)) return;                                              // :511
-    const double deinv = __ddiv_rn(1.0, __dsub_rn(etab[1], etab[0]));                      // DEINV :482
-    const int ik = (int)__dmul_rn(__dsub_rn(ek, emin), deinv);                             // 0-based IK-1 :512
-    double ff = 0.0;
-    for (int ig = 0; ig < S.ng; ig++) {                                                   // :516-520
-        const int kp = S.kpair[kk + S.ng * ig] - 1;
-        const double sk = __ddiv_rn(S.mden[ig], __dsub_rn(etab[1], etab[0]));              // SK(IG) = MDEN/(ETAB(2)-ETAB(1)) :487
-        const double s0 = stab[ik + (size_t)S.ne * kp], s1 = stab[ik + 1 + (size_t)S.ne * kp];
-        const double lin = __dadd_rn(__dmul_rn(__dsub_rn(ek, etab[ik]), s1), __dmul_rn(__dsub_rn(etab[ik + 1], ek), s0));
-        ff = __dadd_rn(ff, __dmul_rn(sk, lin));
+    if ((statu[i] & ST_ACTIVE) != ST_ACTIVE) return;
+    double fx = fp[i], fy = fp[i + (size_t)n], fz = fp[i + 2 * (size_t)n];
+    if (stop_force(S, etab, stab, ityp[i] - 1, xp1[i], xp1[i + (size_t)n], xp1[i + 2 * (size_t)n], fx, fy, fz)) {
+        fp[i] = fx; fp[i + (size_t)n] = fy; fp[i + 2 * (size_t)n] = fz;
     }
-    vv = sqrt(vv);
-    fp[i] = __dsub_rn(fp[i], __ddiv_rn(__dmul_rn(ff, vx), vv));                            // FP = FP - FF*V/|V| :523-525
-    fp[i + (size_t)n] = __dsub_rn(fp[i + (size_t)n], __ddiv_rn(__dmul_rn(ff, vy), vv));
-    fp[i + 2 * (size_t)n] = __dsub_rn(fp[i + 2 * (size_t)n], __ddiv_rn(__dmul_rn(ff, vz), vv));
 }
 
-struct StopState { StopParams P; double *etab = nullptr, *stab = nullptr; };
 static StopState *stop_of(mdb_ctx *c) { return reinterpret_cast<StopState *>(c->stop_state); }
 
 // Initialize_STMOD_DEV + Reset_STMOD_DEV (:334-427): the E-S tables of the stopping library (ETAB(NE) in erg, STAB(NE,NK) in
@@ -236,10 +212,14 @@ extern "C" int mdb_stopping_apply(mdb_ctx *c)
 // primary knock-on atom: the velocity of ONE atom is replaced by sqrt(2 EK / m) along a direction
 // (internal deposition of MD_TypeDef_Projectile.F90: DEPSTYLE = CP_DEP_STYPE_PKA, EKSTYPE = CP_EK_STYLE_MONO)
 // ------------------------------------------------------------------------------------
-__global__ void k_pka(int n, int orig, const int *__restrict__ gidinv, const int *__restrict__ ityp, MassParams M, double ek,
+__global__ void k_pka(int n, int orig, const int *__restrict__ gidinv, const int *__restrict__ gid, int a0, int a1,
+                      const int *__restrict__ ityp, MassParams M, double ek,
                       double dx, double dy, double dz, double *__restrict__ xp1, int *__restrict__ statu)
 {
     const int s = gidinv[orig - 1] - 1;
+    // slab-decomposed runs: only the rank that owns the atom acts (GIDINV is current for owned atoms only; the slot must
+    // hold this very atom)
+    if (s < a0 || s >= a1 || gid[s] != orig) return;
     const double v = sqrt(2.0 * ek / M.cm[ityp[s] - 1]);
     xp1[s] = v * dx; xp1[s + (size_t)n] = v * dy; xp1[s + 2 * (size_t)n] = v * dz;
     statu[s] |= ST_ACTIVE;
@@ -253,7 +233,7 @@ extern "C" int mdb_pka_insert(mdb_ctx *c, int orig_id, double ekin_erg, const do
     if (!(d > 0.0)) return mdb_fail(c, MDB_ERR_ARG, "mdb_pka_insert: zero direction");
     CUDA_TRY(c, cudaSetDevice(c->dev));
     ProfScope ps(c, MDB_K_OTHER);
-    k_pka<<<1, 1, 0, c->stream>>>(c->n, orig_id, c->gidinv, c->ityp, c->mass, ekin_erg, dir[0] / d, dir[1] / d, dir[2] / d, c->xp1, c->statu);
+    k_pka<<<1, 1, 0, c->stream>>>(c->n, orig_id, c->gidinv, c->gid, own_a0(c), own_a1(c), c->ityp, c->mass, ekin_erg, dir[0] / d, dir[1] / d, dir[2] / d, c->xp1, c->statu);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }

@@ -11,7 +11,7 @@
 // trajectories track the oracle as closely as the force sums allow.
 #include <cmath>
 #include <vector>
-#include "mdb_internal.cuh"
+#include "mdb_stop.cuh"
 
 // one atom of the predictor; returns |displacement since the last rebuild|^2 (0 when not tracked).
 // pre != 0: the EPC friction (bit 0) and the corrector half-kick (bit 1) of the PREVIOUS step are applied first, on
@@ -136,6 +136,40 @@ __global__ void k_epc_correct(int n, double *__restrict__ xp1, double *__restric
     }
 }
 
+// The end of a step with electronic stopping in ONE pass over XP1 / FP: EPC friction (EPC_MOD_KERNEL), stopping
+// (ST_MOD_GDEN_KERNEL) and the corrector half-kick, each with the arithmetic of its own kernel, on the values in registers.
+__global__ void k_step_close(int n, double *__restrict__ xp1, double *__restrict__ fp, const int *__restrict__ statu,
+                             const int *__restrict__ ityp, MassParams M, EpcParams E, int do_epc, StopParams S,
+                             const double *__restrict__ etab, const double *__restrict__ stab, double hs2, int a0, int a1)
+{
+    const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a1) return;
+    const int stat = statu[i];
+    if ((stat & ST_ACTIVE) != ST_ACTIVE) return;
+    const int kk = ityp[i] - 1;
+    const size_t n1 = n, n2 = 2 * (size_t)n;
+    const double vx = xp1[i], vy = xp1[i + n1], vz = xp1[i + n2];
+    double fx = fp[i], fy = fp[i + n1], fz = fp[i + n2];
+    bool wr = false;
+    if (do_epc && E.enable[kk] > 0) { // EPC_MOD_KERNEL :473-490
+        const double v2 = __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz));
+        if (v2 <= E.eup[kk]) {
+            const double tm = __dmul_rn(v2, E.v2ti[kk]);
+            const double mu = __ddiv_rn(__dmul_rn(E.epa[kk], __dsub_rn(tm, E.te[kk])), fmax(tm, E.tcut[kk]));
+            fx = __dsub_rn(fx, __dmul_rn(mu, vx));
+            fy = __dsub_rn(fy, __dmul_rn(mu, vy));
+            fz = __dsub_rn(fz, __dmul_rn(mu, vz));
+            wr = true;
+        }
+    }
+    wr = stop_force(S, etab, stab, kk, vx, vy, vz, fx, fy, fz) || wr;
+    if (wr) { fp[i] = fx; fp[i + n1] = fy; fp[i + n2] = fz; }
+    const double cm0 = M.cm[kk]; // Correction_KERNEL :735-753
+    if ((stat & ST_FIXVELX) == 0 && (stat & ST_FIXPOSX) == 0) xp1[i] = __dadd_rn(vx, __dmul_rn(hs2, __ddiv_rn(fx, cm0)));
+    if ((stat & ST_FIXVELY) == 0 && (stat & ST_FIXPOSY) == 0) xp1[i + n1] = __dadd_rn(vy, __dmul_rn(hs2, __ddiv_rn(fy, cm0)));
+    if ((stat & ST_FIXVELZ) == 0 && (stat & ST_FIXPOSZ) == 0) xp1[i + n2] = __dadd_rn(vz, __dmul_rn(hs2, __ddiv_rn(fz, cm0)));
+}
+
 __global__ void k_ekin(int n, const double *__restrict__ xp1, const int *__restrict__ statu, const int *__restrict__ ityp,
                        MassParams M, double *__restrict__ ekin)
 {
@@ -204,23 +238,10 @@ int mdb_step_close_launch(mdb_ctx *c, double h)
 {
     const int a0 = own_a0(c), a1 = own_a1(c);
     if (!mdb_stopping_on(c)) return mdb_epc_correct_launch(c, h);
-    {
-        ProfScope ps(c, MDB_K_CORRECT);
-        if (c->epc.on)
-            k_epc_correct<<<cdiv(a1 - a0, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, 0.0, 1, 0, a0, a1);
-    }
-    int rc = mdb_stopping_launch(c);
-    if (rc < 0) return rc;
+    const StopState *S = reinterpret_cast<const StopState *>(c->stop_state);
     ProfScope ps(c, MDB_K_CORRECT);
-    k_epc_correct<<<cdiv(a1 - a0, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, h * 0.5, 0, 1, a0, a1);
-    CUDA_TRY(c, cudaGetLastError());
-    return MDB_OK;
-}
-int mdb_epc_correct_launch(mdb_ctx *c, double h)
-{
-    ProfScope ps(c, MDB_K_CORRECT);
-    k_epc_correct<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
-                                                                         h * 0.5, c->epc.on, 1, own_a0(c), own_a1(c));
+    k_step_close<<<cdiv(a1 - a0, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, c->epc.on, S->P,
+                                                          S->etab, S->stab, h * 0.5, a0, a1);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -388,8 +409,12 @@ __global__ void k_timestep_mask(int n, const double *__restrict__ xp1, const dou
                 v[d] = xp1[i + (size_t)d * n];
                 a[d] = __ddiv_rn(fp[i + (size_t)d * n], cm0);
             }
+            // |TH v + H2S2 a| <= TH |v| + H2S2 |a|, which grows with TH: an atom that passes this bound at HMX (with a margin for
+            // the roundings) passes every trial step -- almost all atoms, which then skip the loop
+            const double vn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            const double ub = hmx * vn + 0.5 * hmx * hmx * an;
             double th = hmx;
-            for (int k = 0; k < TS_MAXHALVE; k++) {
+            for (int k = 0; k < ((ub * ub * 1.000001 <= mxd2) ? 0 : TS_MAXHALVE); k++) {
                 const double h2s2 = __dmul_rn(__dmul_rn(th, th), 0.5);
                 double d2 = 0.0;
 #pragma unroll

@@ -49,6 +49,12 @@ class SlabDomain:
             return self.ctx.dd_run(itime0, nsteps, it0, nb_uptab, h)
         return self.ctx.run(itime0, nsteps, it0, nb_uptab, h)
 
+    def run_sched(self, itime0, nsteps, it0, sched, h, time_s=0.0):
+        """the GMD loop with its step-size / list-period schedules (capi.Sched) -> (out-of-box count, H, TIME)"""
+        if self.world > 1:
+            return self.ctx.dd_run_sched(itime0, nsteps, it0, sched, h, time_s)
+        return self.ctx.run_sched(itime0, nsteps, it0, sched, h, time_s)
+
     def step(self, itime, it0, nb_uptab, h):
         return self.run(itime, 1, it0, nb_uptab, h)
 
