@@ -246,6 +246,15 @@ int mdb_step_close_launch(mdb_ctx *c, double h)
     return MDB_OK;
 }
 
+int mdb_epc_correct_launch(mdb_ctx *c, double h)
+{
+    ProfScope ps(c, MDB_K_CORRECT);
+    k_epc_correct<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc,
+                                                                         h * 0.5, c->epc.on, 1, own_a0(c), own_a1(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
+}
+
 extern "C" int mdb_predict(mdb_ctx *c, double h)
 {
     if (!c) return MDB_ERR_ARG;
