@@ -22,6 +22,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 25
+    cascade = len(sys.argv) > 2 and sys.argv[2] == "cascade"   # PKA + electronic stopping + displacement-limited time step
     c = util.bcc_case((8, 8, 20), seed=404, temp=900.0)
     # atoms near the faces of the 8 z-layers of cells are shot across them: every rebuild migrates atoms between ranks
     t = (c.xp[:, 2] - c.boxlow[2]) / c.zl[2] * 8
@@ -43,18 +44,38 @@ def main():
         ctx.epc_set(*epc)
         return ctx
 
+    ne = 200
+    etab = np.linspace(1.0, 2.0e4, ne) * util.CP_EVERG
+    stab = (1.0e-27 * np.sqrt(etab / util.CP_EVERG)).reshape(-1, 1)
+    sched = capi.Sched(-1, h, h, 0.05 * c.rr, nup, nup, 100)
+    ipka = int(np.argmin(np.sum((c.xp - (c.boxlow + 0.5 * c.zl)) ** 2, axis=1))) + 1
+
+    def arm(x):
+        if cascade:
+            x.pka_insert(ipka, 1000.0 * util.CP_EVERG, [1.0, 3.0, 5.0])
+            x.stopping_set(etab, stab, np.array([[1]]), [1], [6.3e22])
+
     full = make(local)             # the whole box on this GPU: the reference for this test
-    full.nlist_build(); full.force(capi.FORCE)
-    full.run(0, nsteps, it0, nup, h)
-    nsteps_chk = nsteps
+    full.nlist_build(); arm(full); full.force(capi.FORCE)
+    if cascade:
+        _, h_full, t_full = full.run_sched(0, nsteps, it0, sched, h)
+    else:
+        full.run(0, nsteps, it0, nup, h)
 
     ctx = make(local)
     dom = SlabDomain(ctx, local)
     dom.rebuild()
+    arm(ctx)
     dom.force(capi.FORCE)
-    dom.run(0, nsteps, it0, nup, h)        # step loop, NCCL exchanges and local rebuilds inside the library
+    # step loop, exchanges (peer memory / NCCL) and local rebuilds inside the library
+    if cascade:
+        _, h_dd, t_dd = dom.run_sched(0, nsteps, it0, sched, h)
+    else:
+        dom.run(0, nsteps, it0, nup, h)
     a0, a1 = dom.owned()
     ok = True
+    if cascade:
+        ok &= bool(h_dd == h_full and t_dd == t_full and t_full < nsteps * h)
     gid_f, gid_d = full.download(capi.F_GID, capi.ORDER_CELL), ctx.download(capi.F_GID, capi.ORDER_CELL)
     ok &= bool(np.array_equal(gid_f[a0:a1], gid_d[a0:a1]))
     worst = {}
