@@ -108,6 +108,11 @@ contains
       if(ITIME .ge. CtrlParam%DAMPTIME0 .and. ITIME .le. CtrlParam%DAMPTIME0 + CtrlParam%DAMPTIME1-1) then   ! :611-617
          if(mdb_damping(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_damping failed"
       end if
+      if(CtrlParam%IHDUP .lt. 0) then                     ! variable time step, scheme II (:633-655): the halving loop in one call
+         if(MOD(ITIME-CtrlParam%IT0+1, IABS(CtrlParam%IHDUP)) .eq. 0) then
+            if(mdb_timestep_limit(m_CTX, CtrlParam%HMX, CtrlParam%DMX, CtrlParam%H) .lt. 0) stop "MDPSCU Error: mdb_timestep_limit failed"
+         end if
+      end if
       if(mdb_predict(m_CTX, CtrlParam%H) .lt. 0) stop "MDPSCU Error: mdb_predict failed"
   end subroutine
   subroutine Correction_DEV(ITIME, SimBox, CtrlParam)

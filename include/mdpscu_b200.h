@@ -240,7 +240,7 @@ int mdb_run_async(mdb_ctx *ctx, int itime0, int nsteps, int it0, int nb_uptab, d
  * The halving loop runs as ONE kernel that tests all trial steps HMX 2^-k at once and one 4-byte read-back per check.  Electronic
  * stopping, when switched on (mdb_stopping_set), acts between the EPC friction and the corrector of every step.  With stopping or
  * scheme II the tiled passes decide the distance-class shortcut PER TILE (MDB_OPT_TILE_GUARD): one fast atom sends only the tiles
- * around it to the full list.  hmi / hmx in s, dmx in cm (the control file gives fs and lattice units).
+ * around it to the full list.  hmi / hmx in s, dmx in cm (the control file gives fs and Angstrom, Common/MD_Gvar.F90:944-947).
  * In/out: *h = CtrlParam%H, *time_s (may be NULL) += the sum of the steps taken [s].  Returns like mdb_run. */
 typedef struct mdb_sched {
     int ihdup;
@@ -305,6 +305,10 @@ int mdb_global_t(mdb_ctx *ctx, double *curt);
 int mdb_box_temperatures(mdb_ctx *ctx, double *t_box);
 int mdb_vel_scaling(mdb_ctx *ctx, double dt);
 int mdb_check_timestep(mdb_ctx *ctx, double th, double h2s2, double dmx2, int *iflag);
+/* The halving loop Predictor_DEV runs around CheckTimestep_DEV when IHDUP < 0 (:633-655), as one call: *h = the first
+ * TH = HMX, HMX/2, HMX/4, ... for which no active atom would move further than DMX [cm] in the predictor step (one kernel tests
+ * all trial steps, one 4-byte read-back).  Collective in slab-decomposed runs (the ranks' findings are combined). */
+int mdb_timestep_limit(mdb_ctx *ctx, double hmx, double dmx, double *h);
 
 /* ------------------------------------------------------------------------------------
  * Quench.  Do_Steepest_Forsteps_DEV(SimBox, CtrlParam, ForceClass, MXNUMSTEPS, METH),

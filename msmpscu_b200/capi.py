@@ -78,6 +78,7 @@ SYMBOLS = {
     "mdb_dd_force": (C.c_int, [C.c_void_p, C.c_uint, c_dp]),
     "mdb_dd_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "mdb_dd_global_t": (C.c_int, [C.c_void_p, c_dp]),
+    "mdb_timestep_limit": (C.c_int, [C.c_void_p, C.c_double, C.c_double, c_dp]),
     "mdb_run_sched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, c_dp]),
     "mdb_dd_run_sched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_dp, c_dp]),
     "mdb_run_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
@@ -344,6 +345,12 @@ class Context:
 
     def run(self, itime0, nsteps, it0, nb_uptab, h):
         return self._chk(self.lib.mdb_run(self.h, itime0, nsteps, it0, nb_uptab, float(h)))
+
+    def timestep_limit(self, hmx, dmx):
+        """Predictor_DEV's halving loop (IHDUP < 0): the largest HMX/2^k that moves no active atom further than DMX"""
+        hh = C.c_double(0.0)
+        self._chk(self.lib.mdb_timestep_limit(self.h, float(hmx), float(dmx), C.byref(hh)))
+        return hh.value
 
     def run_sched(self, itime0, nsteps, it0, sched, h, time_s=0.0):
         """the GMD time loop with its step-size / list-period schedules -> (out-of-box count, H after the block, TIME [s])"""

@@ -598,11 +598,12 @@ extern "C" int mdb_dd_force(mdb_ctx *c, unsigned flags, double vtensor[9])
 }
 
 // Predictor_DEV's halving loop on the decomposed box: every rank's mask of objecting trial steps, OR-ed over the ranks
-static int dd_timestep(mdb_ctx *c, const mdb_sched *s, double *h)
+int mdb_dd_timestep(mdb_ctx *c, double hmx, double dmx, double *h)
 {
     int rc;
     const int R = c->dd_n;
-    if ((rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_timestep_mask_launch(p, s->hmx, s->dmx * s->dmx); })) < 0) return rc;
+    if (!c->dd_built) return mdb_fail(c, MDB_ERR_STATE, "mdb_timestep_limit: mdb_dd_build first");
+    if ((rc = all_ranks(c, [&](mdb_ctx *p) { return mdb_timestep_mask_launch(p, hmx, dmx * dmx); })) < 0) return rc;
     unsigned mask = 0u;
     if (!c->dd_peers.empty()) {
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -615,7 +616,7 @@ static int dd_timestep(mdb_ctx *c, const mdb_sched *s, double *h)
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         for (int r = 0; r < R; r++) mask |= (unsigned)tab[r];
     }
-    return mdb_timestep_from_mask(c, mask, s->hmx, h);
+    return mdb_timestep_from_mask(c, mask, hmx, h);
 }
 
 // nsteps x For_One_Step on the decomposed box, enqueued from here (no host round trip between the kernels and the exchanges
@@ -666,7 +667,7 @@ static int dd_run_impl(mdb_ctx *c, int itime0, int nsteps, int it0, int nb_fixed
         int nb_uptab = nb_fixed;
         if (sch) {
             h = mdb_sched_h1(sch, itime, it0, h);
-            if (mdb_sched_check_due(sch, itime, it0) && (rc = dd_timestep(c, sch, &h)) < 0) return rc;
+            if (mdb_sched_check_due(sch, itime, it0) && (rc = mdb_dd_timestep(c, sch->hmx, sch->dmx, &h)) < 0) return rc;
             nb_uptab = mdb_sched_nb_uptab(sch, itime, it0);
         }
         const int pre = (s == 0 || closed) ? 0 : 3; // EPC friction + corrector of the previous step ride in front of this predictor

@@ -244,6 +244,7 @@ int mdb_epc_correct_launch(mdb_ctx *c, double h);
 int mdb_step_close_launch(mdb_ctx *c, double h);          // EPC friction [, stopping], corrector on the owned range
 int mdb_timestep_mask_launch(mdb_ctx *c, double hmx, double dmx2);                 // mdb_step.cu : variable time step (scheme II)
 int mdb_timestep_from_mask(mdb_ctx *c, unsigned mask, double hmx, double *h);
+int mdb_dd_timestep(mdb_ctx *c, double hmx, double dmx, double *h);                // mdb_dd.cu : the same over all ranks
 int mdb_sched_nb_uptab(const mdb_sched *s, int itime, int it0);
 bool mdb_sched_check_due(const mdb_sched *s, int itime, int it0);
 double mdb_sched_h1(const mdb_sched *s, int itime, int it0, double h);

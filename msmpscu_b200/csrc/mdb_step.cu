@@ -693,6 +693,21 @@ double mdb_sched_h1(const mdb_sched *s, int itime, int it0, double h)
     return v > s->hmx ? s->hmx : v;
 }
 
+// the halving loop of Predictor_DEV (:633-655) as one call: the largest TH = HMX 2^-k for which no active atom would move
+// further than DMX in the predictor step (collective in slab-decomposed runs)
+extern "C" int mdb_timestep_limit(mdb_ctx *c, double hmx, double dmx, double *h)
+{
+    if (!c || !h) return mdb_fail(c, MDB_ERR_ARG, "mdb_timestep_limit: null argument");
+    if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_timestep_limit: mdb_box_set first");
+    if (!(hmx > 0.0)) return mdb_fail(c, MDB_ERR_ARG, "mdb_timestep_limit: HMX must be positive");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    if (c->dd_on) return mdb_dd_timestep(c, hmx, dmx, h);
+    int rc = mdb_timestep_mask_launch(c, hmx, dmx * dmx);
+    if (rc < 0) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return mdb_timestep_from_mask(c, (unsigned)c->h_counters[CNT_SCRATCH], hmx, h);
+}
+
 extern "C" int mdb_run_sched(mdb_ctx *c, int itime0, int nsteps, int it0, const mdb_sched *s, double *h, double *time_s)
 {
     if (!c || !s || !h) return mdb_fail(c, MDB_ERR_ARG, "mdb_run_sched: null argument");
@@ -708,9 +723,7 @@ extern "C" int mdb_run_sched(mdb_ctx *c, int itime0, int nsteps, int it0, const 
         const int itime = itime0 + k;
         hh = mdb_sched_h1(s, itime, it0, hh);
         if (mdb_sched_check_due(s, itime, it0)) {
-            if ((rc = mdb_timestep_mask_launch(c, s->hmx, s->dmx * s->dmx)) < 0) break;
-            if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = mdb_fail(c, MDB_ERR_CUDA, "mdb_run_sched: synchronisation failed"); break; }
-            if ((rc = mdb_timestep_from_mask(c, (unsigned)c->h_counters[CNT_SCRATCH], s->hmx, &hh)) < 0) break;
+            if ((rc = mdb_timestep_limit(c, s->hmx, s->dmx, &hh)) < 0) break;
         }
         // the step may differ from its neighbours': EPC friction and the corrector close every step (nothing rides in front of
         // the next predictor), and CheckTimestep sees the corrected velocities as in the reference

@@ -136,14 +136,21 @@ def read_ctrl_file(path, box, section=1):
         elif k == "E_P_COUPLE":
             epc = True
         elif k == "STEPSIZE":
-            v = _numbers(s[9:])
-            c.H = v[1] * CP_FS2S  # flag, hmi, hmx, dmx
+            v = _numbers(s[9:])     # flag (IHDUP), hmi, hmx [fs], dmx [Angstrom]: MD_SimCtrlParam_GMD.F90:362-378, MD_Gvar.F90:944-947
+            c.IHDUP = int(v[0])
+            c.HMI, c.HMX = v[1] * CP_FS2S, (v[2] if len(v) > 2 else v[1]) * CP_FS2S
+            c.DMX = max(v[3] if len(v) > 3 else 0.1, 1.0e-6) * 1.0e-8
+            c.H = c.HMI               # "the time step starts from its minimum value"
         elif k == "PERIDIC":
             c.IFPD = np.array([int(x) for x in _numbers(s[8:])[:3]], dtype=np.int32)
         elif k == "MAXNB":
             c.NB_MXNBS = int(_numbers(s[6:])[0])
         elif k == "UPDATEFRE":
-            c.NB_UPTAB = int(_numbers(s[10:])[0])
+            v = [int(x) for x in _numbers(s[10:])]          # MD_TypeDef_SimCtrlParam.F90:1355-1372
+            c.NB_UPTABMI = v[0]
+            c.NB_UPTABMX = v[1] if len(v) > 1 else v[0]
+            c.NB_DBITAB = v[2] if len(v) > 2 else 100000
+            c.NB_UPTAB = c.NB_UPTABMI
         elif k == "RANDSEED":                                   # MD_TypeDef_SimCtrlParam.F90:1694
             c.SEED = [int(v) for v in _numbers(s[9:])] or c.SEED
         elif k in ("QUENCHSTEP", "QUICKDAMP", "QUICKDUMP", "QUENCH"):   # :2018-2060, MD_SimCtrlParam_GMD.F90:59

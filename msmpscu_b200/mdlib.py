@@ -89,6 +89,14 @@ class SimMDCtrl:
     NB_UPTAB: int = 10
     IT0: int = 1
     H: float = 0.5 * CP_FS2S
+    # step-size and list-period schedules (Common/MD_TypeDef_SimCtrlParam.F90:41-47,120-122; defaults :886-890,940-942)
+    IHDUP: int = 0                       # 0 fixed step; > 0 ramp HMI -> HMX every IHDUP steps; < 0 displacement-limited (DMX)
+    HMI: float = 1.0 * CP_FS2S
+    HMX: float = 1.0 * CP_FS2S
+    DMX: float = 0.1e-8                  # cm (the control file gives Angstrom)
+    NB_UPTABMI: int = 10
+    NB_UPTABMX: int = 10
+    NB_DBITAB: int = 100000
     NUMFTABR: int = 10000
     NUMFTABE: int = 10000
     RHOSCAL: float = 20.0
@@ -395,8 +403,17 @@ def ResetXP1(dev, SimBox):
 
 
 def For_Steps(dev, ITIME0, nsteps, SimBox, CtrlParam):
-    """The same sequence for nsteps steps inside the library (mdb_run): no host round trip per step."""
-    return dev.ctx.run(ITIME0, nsteps, CtrlParam.IT0, CtrlParam.NB_UPTAB, CtrlParam.H)
+    """The same sequence for nsteps steps inside the library: mdb_run for a fixed step and list period, else mdb_run_sched with
+    the schedules of the time loop (Appshell/MD_Method_GenericMD_GPU.F90:351-361: &STEPSIZE flag / hmi / hmx / dmx,
+    &UPDATEFRE min / max / doubling interval).  CtrlParam.H and CtrlParam.NB_UPTAB are left as the loop leaves them."""
+    c = CtrlParam
+    if c.IHDUP == 0 and c.NB_UPTABMI == c.NB_UPTABMX == c.NB_UPTAB:
+        return dev.ctx.run(ITIME0, nsteps, c.IT0, c.NB_UPTAB, c.H)
+    s = capi.Sched(c.IHDUP, c.HMI, c.HMX, c.DMX, c.NB_UPTABMI, c.NB_UPTABMX, c.NB_DBITAB)
+    rc, c.H, _ = dev.ctx.run_sched(ITIME0, nsteps, c.IT0, s, c.H)
+    last = ITIME0 + nsteps - 1
+    c.NB_UPTAB = min(c.NB_UPTABMX, c.NB_UPTABMI * ((last - c.IT0 + 1) // c.NB_DBITAB + 1))
+    return rc
 
 
 def Cal_thermal_quantities(SimBox):

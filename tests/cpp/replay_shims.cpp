@@ -83,9 +83,11 @@ int main(int argc, char **argv)
     const double te[1] = {300.0}, alpha[1] = {1.0e-12}, cut[1] = {0.1}, he[1] = {100.0 * 1.60219e-12};
     CHECK(mdb_epc_set(ctx, enable, te, alpha, cut, he));
     // ---- For_One_Step x nsteps, kernel by kernel as the shell calls them
-    const double h = 0.5e-15;
-    const int it0 = 1, nb_uptab = 10;
+    double h = 0.5e-15;
+    const double hmx = 0.5e-15, dmx = 0.05e-8;                                      // &STEPSIZE flag -1, hmx 0.5 fs, dmx 0.05 A
+    const int it0 = 1, nb_uptab = 10, ihdup = -2;
     for (int itime = 0; itime < nsteps; itime++) {
+        if ((itime - it0 + 1) % (-ihdup) == 0) CHECK(mdb_timestep_limit(ctx, hmx, dmx, &h)); // Predictor_DEV, IHDUP < 0 (:633-655)
         CHECK(mdb_predict(ctx, h));                                               // Predictor_DEV
         if ((itime - it0) % nb_uptab == 0) CHECK(mdb_nlist_build(ctx));           // Cal_NeighBoreList_DEV
         CHECK(mdb_force(ctx, MDB_FORCE, nullptr));                                // CalForce_ForceClass

@@ -145,6 +145,25 @@ def test_control_files_of_the_reference_examples_are_read():
     assert par.STRCUT_DRTol == 0.02 and par.LBFGS_MSave == 7
 
 
+def test_step_size_and_list_period_schedules_are_read(tmp_path):
+    """the two lines of the reference's cascade control file (examples/Cascade_Test/CtrlFile300K_LOC_T.dat) that steer the time
+    loop: &STEPSIZE flag / hmi / hmx [fs] / dmx [Angstrom, MD_Gvar.F90:947] and &UPDATEFRE min / max / doubling interval"""
+    from msmpscu_b200 import inputs
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    box = inputs.read_box_file(os.path.join(g, "W_2000_H1_EAM1_box.dat"))
+    p = tmp_path / "ctrl.dat"
+    p.write_text("&CTLF\n &POTENSUBCTL\n  &CUTOFF cutoff distances: A-A= 1.9\n &ENDSUBCTL\n &SECTSUBCTL #1\n  &TIMESUBCTL\n"
+                 "   &STEPSIZE   use fixd step flag= -1, hmi= 0.25, hmx = 0.5, dmx = 0.05\n  &ENDSUBCTL\n  &NEIGHBSUBCTL\n"
+                 "   &UPDATEFRE minimun frequcency= 5, max frequence= 10, frequecy of changing updating frequency 100\n"
+                 "   &CUTOFF    cutoff between neighbors = 1.6\n  &ENDSUBCTL\n &ENDSUBCTL\n&ENDCTLF\n")
+    c = inputs.read_ctrl_file(str(p), box)
+    assert c.IHDUP == -1 and abs(c.HMI - 0.25e-15) < 1e-30 and abs(c.HMX - 0.5e-15) < 1e-30 and abs(c.DMX - 0.05e-8) < 1e-24
+    assert abs(c.H - c.HMI) < 1e-30                       # "the time step starts from its minimum value"
+    assert (c.NB_UPTABMI, c.NB_UPTABMX, c.NB_DBITAB, c.NB_UPTAB) == (5, 10, 100, 5)
+    d = mdlib_defaults = __import__("msmpscu_b200.mdlib", fromlist=["SimMDCtrl"]).SimMDCtrl()
+    assert (d.IHDUP, d.NB_UPTABMI, d.NB_UPTABMX, d.NB_DBITAB) == (0, 10, 10, 100000) and d.DMX == 0.1e-8   # :886-890, :940-942
+
+
 def _thermal_loop_restatement(XP1, STATU, ITYP, CM, PROP, BOXSHAPE, ZL, VTENSOR, EPOT, EKIN):
     """Cal_thermal_quantities_SimMDBox (Common/MD_TypeDef_SimBox.F90:5048-5170) as plain loops, statement by statement:
     the checker of the vectorised host mirror in msmpscu_b200/mdlib.py."""

@@ -162,6 +162,9 @@ def test_cpp_host_replays_the_fortran_shim_call_sequence(tmp_path):
     c = util.bcc_case((9, 9, 9), seed=2025)
     n = c.xp.shape[0]
     nsteps = 23
+    c.xp1 = c.xp1.copy()
+    c.xp1[n // 2] = np.sqrt(2.0 * 800.0 * util.CP_EVERG / c.mass[0]) * np.array([1.0, 3.0, 5.0]) / np.sqrt(35.0)   # a fast atom: the
+    # displacement-limited step of Predictor_DEV (IHDUP = -2 in the replay) has to shorten the step
     cfg, out = str(tmp_path / "cfg.bin"), str(tmp_path / "out.bin")
     with open(cfg, "wb") as f:
         np.array([n], np.int32).tofile(f)
@@ -179,13 +182,18 @@ def test_cpp_host_replays_the_fortran_shim_call_sequence(tmp_path):
     ctx.epc_set([1], [300.0], [1.0e-12], [0.1], [100.0 * util.CP_EVERG])
     ctx.force(capi.FORCE)
     h = 0.5e-15
+    hs = []
     for it in range(nsteps):
+        if (it - 1 + 1) % 2 == 0:
+            h = ctx.timestep_limit(0.5e-15, 0.05e-8)
+        hs.append(h)
         ctx.predict(h)
         if (it - 1) % 10 == 0:
             ctx.nlist_build()
         ctx.force(capi.FORCE)
         ctx.epc_apply()
         ctx.correct(h)
+    assert min(hs) < 0.5e-15
     ctx.ekin()
     t = ctx.global_t()
     vt_py = ctx.force(capi.FORCE | capi.EPOT | capi.VIRIAL)
