@@ -127,7 +127,6 @@ struct TileListArgs {
     int *kvois; unsigned short *nbl; unsigned short *ncls; int *counters; const TileDesc *desc;
     int tile_lo;          // first tile of this rank (slab decomposition), 0 otherwise
     int lcap;             // rows of the per-atom shared-memory list
-    int bank_order;       // order the scanned classes for conflict-free record reads (see the write-out)
     float rm2[MDB_MXGROUP * MDB_MXGROUP];
     float rc2[2]; // class radii^2 (build-time, fp32): class 0 <= rc2[0] < class 1 <= rc2[1] < class 2
 };
@@ -245,51 +244,6 @@ __device__ __forceinline__ void pair_barrier(int cell) // the two warps of one o
 // residue (slot mod 4) that lane lam0 + e % G of a half-warp wants at list entry e (row e / G)
 template <int G>
 __device__ __forceinline__ unsigned list_wanted(int lam0, int e) { return (unsigned)((((lam0 + e % G) >> 1) + e / G) & 3); }
-// Entries [a, b) of one column (stride 32 shorts, b - a <= 255): counting pass, in-place American-flag sort by slot residue
-// driven by four 8-bit cursors packed in one register, then the deal: entry position e takes the next entry of the residue it
-// wants, or of a residue in surplus when none is left; the dealt order is staged in the free rows [scr, scr + b - a) of the
-// column and copied back.  Loop bodies are branch-free: the lanes of the warp work on different atoms.
-template <int G>
-__device__ __noinline__ void seg_deal(unsigned short *col, int a, int b, int lam0, int scr)
-{
-    unsigned cnt = 0u, want = 0u;
-    for (int k = a; k < b; k++) { cnt += 1u << (8 * (col[k * 32] & 3u)); want += 1u << (8 * list_wanted<G>(lam0, k)); }
-    const unsigned c0 = cnt & 255u, c1 = (cnt >> 8) & 255u, c2 = (cnt >> 16) & 255u;
-    const unsigned start = (c0 << 8) | ((c0 + c1) << 16) | ((c0 + c1 + c2) << 24);
-    unsigned cur = start;
-    const unsigned end = start + cnt;
-#pragma unroll 1
-    for (unsigned bkt = 0; bkt < 3; bkt++) { // the last bucket is in place once the first three are
-        int i = (int)((cur >> (8 * bkt)) & 255u);
-        const int e = (int)((end >> (8 * bkt)) & 255u);
-        while (i < e) {
-            const unsigned v = col[(a + i) * 32], r = v & 3u;
-            const bool same = r == bkt;
-            const int j = same ? i : (int)((cur >> (8 * r)) & 255u);
-            const unsigned w = col[(a + j) * 32];
-            col[(a + j) * 32] = (unsigned short)v;
-            col[(a + i) * 32] = (unsigned short)w;
-            cur += same ? 0u : (1u << (8 * r));
-            i += same ? 1 : 0;
-        }
-    }
-    cur = start;
-    unsigned have = cnt;
-#pragma unroll 1
-    for (int e = a; e < b; e++) {
-        const unsigned t = list_wanted<G>(lam0, e);
-        unsigned r = t;
-        if (((have >> (8 * t)) & 255u) == 0u) {
-#pragma unroll
-            for (unsigned x = 0; x < 4; x++)
-                if (((have >> (8 * x)) & 255u) > ((want >> (8 * x)) & 255u)) r = x;
-        }
-        col[(scr + e - a) * 32] = col[(a + (int)((cur >> (8 * r)) & 255u)) * 32];
-        cur += 1u << (8 * r); have -= 1u << (8 * r); want -= 1u << (8 * t);
-    }
-    for (int e = a; e < b; e++) col[e * 32] = col[(scr + e - a) * 32];
-}
-
 template <int G, bool MT>
 __global__ void __launch_bounds__(64 * TILE_MAX_W, 2)
 k_tile_nlist(TileParams P, TileListArgs A)
@@ -469,27 +423,14 @@ k_tile_nlist(TileParams P, TileListArgs A)
         }
         A.ncls[ia] = (unsigned short)lo;               // class 0
         A.ncls[ia + P.npad] = (unsigned short)mid;     // classes 0+1
-        // ---- bank-aware order inside the two classes the passes scan.  A pass reads the staged 32-byte record of a slot as two
-        // LDS.128 (even lanes {x,y} first, odd lanes {z,den} first); the hardware serves an LDS.128 per HALF-warp and takes
-        // max(2, lanes per 16-byte bank group) cycles for it (tools/micro/lds128_patterns.cu), so a row of the list is
-        // conflict-free when the 8 even and the 8 odd lanes of a half-warp each hold every slot residue (mod 4) exactly twice.
-        // Lane lam of the half-warp therefore WANTS residue ((lam >> 1) + row) & 3 at list row `row`; every class segment is
-        // sorted by residue in place and dealt out to the positions that want it, leftovers fill the remaining positions.
-        const int lam0 = ((ia - H.own_start) % (16 / G)) * G; // first lane of this atom inside its half-warp
-        // the free rows of the column [nn, lcap) are the scratch space of the deal
-        if (A.bank_order && mid <= 255 && lcap - nn >= max(lo, mid - lo)) {
-            seg_deal<G>(col, 0, lo, lam0, nn);
-            seg_deal<G>(col, lo, mid, lam0, nn);
-        }
         // ---- write out: 4G consecutive entries form one contiguous 8G-byte block [gl][m%4] of the layout
-        const unsigned pad = (unsigned)P.hcap;         // four dummy records hcap .. hcap+3: a pad takes the wanted residue too
+        const unsigned pad = (unsigned)P.hcap;         // list tails point at the dummy record (k_tile_deal re-aims them by residue)
         for (int q = 0; q * 4 * G < nn; q++) {
             unsigned short blk[4 * G];
 #pragma unroll
             for (int j = 0; j < 4 * G; j++) {
                 const int k = q * 4 * G + j;
-                blk[(j % G) * 4 + j / G] = (k < nn) ? (unsigned short)(col[k * 32] & 0x3fffu)
-                                                    : (unsigned short)(pad + (A.bank_order ? list_wanted<G>(lam0, k) : 0u));
+                blk[(j % G) * 4 + j / G] = (k < nn) ? (unsigned short)(col[k * 32] & 0x3fffu) : (unsigned short)pad;
             }
             uint4 *dst = reinterpret_cast<uint4 *>(A.nbl + ((((size_t)q * P.npad + (size_t)ia) * G) << 2));
 #pragma unroll
@@ -504,6 +445,121 @@ k_tile_nlist(TileParams P, TileListArgs A)
         }
         }
         pair_barrier(cw);
+    }
+}
+
+// ---- bank-aware order of the stored lists (MDB_OPT_TILED_BANKORDER), one thread per owned atom.
+// A pass reads the staged 32-byte record of a slot as two LDS.128 (even lanes {x,y} first, odd lanes {z,den} first); the
+// hardware serves an LDS.128 per HALF-warp and takes max(2, lanes per 16-byte bank group) cycles for it
+// (tools/micro/lds128_patterns.cu), so a list position is conflict-free when the 8 even and the 8 odd lanes of a half-warp
+// each hold every slot residue (mod 4) exactly twice.  Lane lam of the half-warp therefore WANTS residue ((lam >> 1) + row) & 3
+// at list row `row`.  Each of the two class segments a pass scans ([0, n0) and [n0, n1)) is counting-sorted by residue and dealt
+// back: entry position e takes the next entry of the residue it wants; positions that find none are filled with the leftovers
+// afterwards (so every residue serves as many of its positions as it can).  The order
+// inside a class is free, so nothing but the order changes.  (Round 2 first did this inside the list kernel, on one of the two
+// warps of a cell with strided 2-byte shared-memory accesses: +0.58 ms per rebuild.  Here every lane works, the lists are read
+// and written as whole 32-byte blocks, and an atom's entries sit in its own conflict-free shared-memory column.)
+// 8 * list_wanted<G>(lam0, e) as a shift count; for G = 4 the residue is (lam0/2 + ((e + 2) >> 2)) & 3
+template <int G>
+__device__ __forceinline__ unsigned wanted_sh(int lam0, int e)
+{
+    if (G == 4) return (unsigned)(((lam0 >> 1) + ((e + 2) >> 2)) & 3) << 3;
+    return list_wanted<G>(lam0, e) << 3;
+}
+#define DEAL_T 128     // threads per CTA
+#define DEAL_E 80      // entries per atom that can be ordered: an atom whose classes 0+1 hold more keeps the built order
+template <int G>
+__global__ void __launch_bounds__(DEAL_T)
+k_tile_deal(TileParams P, const TileDesc *__restrict__ desc, int a0, int a1, int tile_lo, int tile_hi, const int *__restrict__ ic,
+            unsigned short *__restrict__ nbl, const unsigned short *__restrict__ ncls, const int *__restrict__ kvois)
+{
+    __shared__ unsigned short sa[DEAL_E * DEAL_T], sb[DEAL_E * DEAL_T];
+    const int t = threadIdx.x;
+    unsigned short *A0 = sa + t, *B0 = sb + t;        // entry e of this thread at A0[e * DEAL_T]
+    {
+        const int ia = a0 + blockIdx.x * DEAL_T + t;
+        if (ia >= a1) return;
+        const int cell = ic[ia] - 1;                  // atoms parked outside the cells have no list
+        if (cell < 0) return;
+        const int n0 = ncls[ia], n1 = ncls[ia + P.npad], nn = min(kvois[ia], P.mxkvois);
+        if (n1 <= 0 || ((n1 + 4 * G - 1) / (4 * G)) * 4 * G > DEAL_E) return;   // whole blocks are staged
+        // the tile of the atom -> its index among the tile's owned atoms -> the lanes it gets in a pass
+        const int box = cell / P.nc0, rem = cell - box * P.nc0;
+        const int ix = rem % P.ncx, iyz = rem / P.ncx, iy = iyz % P.ncy, iz = iyz / P.ncy;
+        const int tx = ((ix + 1) * P.ntx - 1) / P.ncx;          // the largest tx with (tx * ncx) / ntx <= ix (tile_geom)
+        const int tile = ((box * P.ncz + iz) * P.ncy + iy) * P.ntx + tx;
+        if (tile < tile_lo || tile >= tile_hi) return;          // (slab decomposition: lists exist for this rank's tiles only)
+        const int o = ia - desc[tile].own_start;
+        const int nblk = (n1 + 4 * G - 1) / (4 * G);
+        const int lam0 = (o % (16 / G)) * G;          // first lane of this atom inside its half-warp (as the passes map atoms)
+        // ---- load the blocks that hold classes 0 + 1 (entry j of a block sits at [(j % G)][j / G])
+        for (int q = 0; q < nblk; q++) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(nbl + ((((size_t)q * P.npad + (size_t)ia) * G) << 2));
+#pragma unroll
+            for (int v = 0; v < (4 * G) / 8; v++) {
+                const uint4 w = src[v];
+                const unsigned u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int h = 0; h < 8; h++) {
+                    const int p = 8 * v + h, j = (p % 4) * G + p / 4;
+                    A0[(q * 4 * G + j) * DEAL_T] = (unsigned short)((u[h >> 1] >> (16 * (h & 1))) & 0xffffu);
+                }
+            }
+        }
+        // ---- the two class segments
+#pragma unroll 1
+        for (int seg = 0; seg < 2; seg++) {
+            const int a = seg ? n0 : 0, b = seg ? n1 : n0;
+            if (b - a < 2) continue;
+            unsigned cnt = 0u;                        // four 8-bit counters (b - a <= DEAL_E < 256)
+#pragma unroll 4
+            for (int e = a; e < b; e++) cnt += 1u << ((A0[e * DEAL_T] & 3u) << 3);
+            const unsigned c0 = cnt & 255u, c1 = (cnt >> 8) & 255u, c2 = (cnt >> 16) & 255u;
+            const unsigned start = (unsigned)a * 0x01010101u + ((c0 << 8) | ((c0 + c1) << 16) | ((c0 + c1 + c2) << 24));
+            unsigned cur = start;
+#pragma unroll 4
+            for (int e = a; e < b; e++) {             // counting sort by residue into B
+                const unsigned v = A0[e * DEAL_T], sh = (v & 3u) << 3;
+                B0[((cur >> sh) & 255u) * DEAL_T] = (unsigned short)v;
+                cur += 1u << sh;
+            }
+            cur = start;
+            unsigned have = cnt;
+            int holes = 0;
+#pragma unroll 2
+            for (int e = a; e < b; e++) {             // deal: every position takes the residue it wants while that lasts ...
+                const unsigned tw = wanted_sh<G>(lam0, e);
+                const bool got = ((have >> tw) & 255u) != 0u;
+                const unsigned v = B0[min((cur >> tw) & 255u, (unsigned)(DEAL_E - 1)) * DEAL_T]; // (an exhausted residue's cursor may sit at row b)
+                A0[e * DEAL_T] = got ? (unsigned short)v : (unsigned short)0xffffu;
+                cur += got ? 1u << tw : 0u;
+                have -= got ? 1u << tw : 0u;
+                holes += got ? 0 : 1;
+            }
+            for (int e = a; holes > 0 && e < b; e++) { // ... and the positions left empty take what is left over, lowest residue first
+                if (A0[e * DEAL_T] != 0xffffu) continue;
+                const unsigned r = (unsigned)(__ffs((int)have) - 1) & ~7u;
+                A0[e * DEAL_T] = B0[((cur >> r) & 255u) * DEAL_T];
+                cur += 1u << r; have -= 1u << r;
+                holes--;
+            }
+        }
+        // list tails inside these blocks: one dummy record per residue (hcap .. hcap + 3)
+        for (int e = nn; e < nblk * 4 * G; e++) A0[e * DEAL_T] = (unsigned short)(P.hcap + (int)list_wanted<G>(lam0, e));
+        // ---- store
+        for (int q = 0; q < nblk; q++) {
+            uint4 *dst = reinterpret_cast<uint4 *>(nbl + ((((size_t)q * P.npad + (size_t)ia) * G) << 2));
+#pragma unroll
+            for (int v = 0; v < (4 * G) / 8; v++) {
+                unsigned u[4];
+#pragma unroll
+                for (int h = 0; h < 8; h += 2) {
+                    const int p = 8 * v + h, j0 = (p % 4) * G + p / 4, p1 = p + 1, j1 = (p1 % 4) * G + p1 / 4;
+                    u[h >> 1] = (unsigned)A0[(q * 4 * G + j0) * DEAL_T] | ((unsigned)A0[(q * 4 * G + j1) * DEAL_T] << 16);
+                }
+                dst[v] = make_uint4(u[0], u[1], u[2], u[3]);
+            }
+        }
     }
 }
 
@@ -1252,7 +1308,6 @@ static int launch_list(mdb_ctx *c)
     for (int i = 0; i < MDB_MXGROUP * MDB_MXGROUP; i++) A.rm2[i] = (i < c->ng * c->ng) ? c->rm2f[i] : 0.f;
     A.rc2[0] = S.rc2f[0]; A.rc2[1] = S.rc2f[1];
     A.lcap = S.lcap;
-    A.bank_order = S.bank_order ? 1 : 0;
     int tile_lo = 0, tile_hi = S.P.ntiles;
     if (c->dd_on) { // owned z-layers of cells: the descriptors are cheap and built for every tile
         const int tiles_per_layer = c->ncell[1] * S.ntx;
@@ -1267,6 +1322,14 @@ static int launch_list(mdb_ctx *c)
     if (tile_hi > tile_lo) {
         k_tile_desc<<<tile_hi - tile_lo, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters, tile_lo);
         kern<<<tile_hi - tile_lo, 64 * S.wmax, S.smem_list, c->stream>>>(S.P, A);
+        if (S.bank_order) {
+            // the atoms of this rank's tiles: its owned range once the decomposition knows it, every atom (filtered by tile) before
+            const bool ranged = c->dd_on && c->dd_built;
+            const int a0 = ranged ? own_a0(c) : 0, a1 = ranged ? own_a1(c) : c->n;
+            if (a1 > a0)
+                k_tile_deal<G><<<cdiv(a1 - a0, DEAL_T), DEAL_T, 0, c->stream>>>(S.P, (const TileDesc *)S.desc, a0, a1, tile_lo, tile_hi, c->ic, S.nbl,
+                                                                               S.ncls, c->kvois);
+        }
     }
     CUDA_TRY(c, cudaGetLastError());
     // the reference-format KVOIS/INDI pair is rebuilt on demand from the positions of this moment
