@@ -385,8 +385,9 @@ int mdb_cg(mdb_ctx *ctx, int mxnumsteps, int meth, double maxdis, double mindis,
 #define MDB_OPT_FUSE_EPILOGUE 5  /* mdb_run on the tiled path: EPC friction + corrector inside the force-pass   */
                                  /* epilogue (1) or as one separate element-wise kernel (0, default: faster)    */
 #define MDB_OPT_TILED_STAGES  6  /* shared-memory pipeline stages of the pass kernel: 2 (default) or 3           */
-#define MDB_OPT_TILED_BANKORDER 7 /* 1: the list builder orders each scanned class so that the record             */
-                                 /* gathers of a half-warp spread over the shared-memory bank groups; 0 (default): scan order */
+#define MDB_OPT_TILED_BANKORDER 7 /* a kernel after the list build orders each scanned class of the stored lists so that the    */
+                                 /* record gathers of a half-warp spread over the shared-memory bank groups: 1 on, 0 off,     */
+                                 /* -1 (default) on for boxes of >= 12 cells per edge                                         */
 #define MDB_OPT_TILE_GUARD    8  /* distance-class shortcut decided per tile from per-block displacement maxima: 1 on, 0 off,  */
                                  /* -1 (default) on with electronic stopping or the displacement-limited time step            */
 #define MDB_FORCE_PATH_AUTO    0

@@ -190,8 +190,8 @@ extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
         c->tiled.use_classes = value != 0;
         return MDB_OK;
     }
-    if (option == MDB_OPT_TILED_BANKORDER && (value == 0 || value == 1)) {
-        c->tiled.bank_order = value != 0; c->list_valid = false;
+    if (option == MDB_OPT_TILED_BANKORDER && value >= -1 && value <= 1) {
+        c->tiled.bank_order_opt = value; c->tiled.dirty = true; c->list_valid = false;
         return MDB_OK;
     }
     if (option == MDB_OPT_TILE_GUARD && value >= -1 && value <= 1) {

@@ -1282,6 +1282,7 @@ int mdb_tiled_plan(mdb_ctx *c)
         }
     }
     for (int p = 0; p < 2; p++) S.smem_pass[p] = TP_HDR_BYTES + tp_tab_bytes(S.ktab[p]) + S.nbuf * tp_buf_bytes(S.hcap, S.ocap, G, mt);
+    S.bank_order = S.bank_order_opt == 1 || (S.bank_order_opt < 0 && std::min(c->ncell[0], std::min(c->ncell[1], c->ncell[2])) >= 12);
     S.ok = true;
     return MDB_OK;
 }

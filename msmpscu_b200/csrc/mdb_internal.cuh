@@ -81,7 +81,11 @@ struct TiledState {
     double margin = 0.0, margin0 = 0.0; // class margins (length): a class holds while every atom moved < margin/2
     float rc2f[2] = {0.f, 0.f}, safe_d2[3] = {0.f, 0.f, 0.f};
     bool use_classes = true;
-    bool bank_order = true;   // k_tile_deal orders the scanned classes of the stored lists for conflict-free record reads (passes -3..8 %, +0.17 ms per rebuild)
+    // k_tile_deal orders the scanned classes of the stored lists for conflict-free record reads: passes -3..8 %, +0.17 ms per rebuild
+    // and million atoms.  -1 = auto: on for boxes of at least 12 cells per edge (most tiles interior: the passes are bound by the
+    // shared-memory pipe), off for small boxes whose tiles all take the minimum-image variant (fp64-bound: measured -1 % there)
+    int bank_order_opt = -1;
+    bool bank_order = false;  // resolved by mdb_tiled_plan
     unsigned short *nbl = nullptr; size_t nbl_elems = 0;   // slot list (bytes in nbl_elems)
     unsigned short *ncls = nullptr; size_t ncls_bytes = 0; // per-atom class counts [2][npad]
     void *desc = nullptr; size_t desc_bytes = 0;           // TileDesc per tile

@@ -19,6 +19,7 @@ def _make(c):
     ctx.upload(capi.F_ITYP, c.ityp); ctx.upload(capi.F_STATU, c.statu)
     ctx.tables_set(util.product_tables(c), c.ru * c.ru)
     ctx.set_option(capi.OPT_FORCE_PATH, capi.FORCE_PATH_TILED)
+    ctx.set_option(capi.OPT_TILED_BANKORDER, 1)     # (auto would leave it off for a box this small: the big runs have it on)
     ctx.nlist_init(c.nb_rm, c.mxkvois)
     ctx.epc_set(*EPC)
     return ctx

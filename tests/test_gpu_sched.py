@@ -115,6 +115,7 @@ def _stop_tables(ng):
 
 def _make_tiled(c, epc, stop):
     ctx = util.make_ctx(c, build=False, force_path=capi.FORCE_PATH_TILED)
+    ctx.set_option(capi.OPT_TILED_BANKORDER, 1)     # (auto would leave it off for a box this small: the big runs have it on)
     ctx.epc_set(*epc)
     if stop:
         ctx.stopping_set(*stop)
