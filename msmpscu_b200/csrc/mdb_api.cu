@@ -133,6 +133,7 @@ static void free_nlist(mdb_ctx *c)
 {
     mdb_tiled_free(c);
     dfree(c->nac); dfree(c->naac); dfree(c->ia1th); dfree(c->kvois); dfree(c->indi);
+    dfree(c->scan_tmp); c->scan_n = 0;
     c->has_nlist = false; c->list_valid = false;
 }
 static void free_tables(mdb_ctx *c)

@@ -9,7 +9,7 @@
 //
 // Pipeline (all on ctx->stream, no host round trip):
 //   k_cell_assign   cell id per atom + per-cell counts by warp-aggregated atomics
-//   k_cell_scan     exclusive prefix -> IA1th, max count
+//   k_scan_local / k_scan_apply   exclusive prefix -> IA1th, max count (two kernels, one cell per thread)
 //   k_cell_scatter  provisional placement inside the cell segment (atomic order)
 //   k_cell_rank     deterministic in-cell order: rank by descending original id
 //   k_oob_place     out-of-box atoms to the tail
@@ -71,31 +71,109 @@ __global__ void k_cell_assign(int n, int napb, const double4 *__restrict__ pos, 
     if (cell > 0) slot[s] = base + __popc(grp & ((1u << lane) - 1u));
 }
 
-// single-block exclusive scan over the cells (run once per rebuild; nc <= ~1e6)
-__global__ void k_cell_scan(int nc, const int *__restrict__ nac, int *__restrict__ ia1th, int *__restrict__ counters)
+// Exclusive prefix over the cells [c0, c1) in two kernels (the reference scans on the host, :1542-1551; round 1 used one
+// 1024-thread block, 40 us at 42 875 cells): k_scan_local -- one cell per thread, block-wide scan, block total and maximum;
+// k_scan_apply -- every block adds the totals of the blocks before it (<= ~650 numbers even at 16 M atoms, summed by the block
+// itself: no third kernel, no look-back chain) and writes IA1th = first + prefix + 1 (1-based as hm_IA1th).
+#define SCAN_B 1024
+__device__ __forceinline__ int block_excl_scan(int v, int &total, int &vmax)
 {
-    __shared__ int part[1024];
-    __shared__ int pmax[1024];
-    int t = threadIdx.x, nt = blockDim.x;
-    int chunk = (nc + nt - 1) / nt;
-    int b = t * chunk, e = min(b + chunk, nc);
-    int sum = 0, mx = 0;
-    for (int i = b; i < e; i++) { int v = nac[i]; sum += v; mx = max(mx, v); }
-    part[t] = sum;
-    pmax[t] = mx;
-    __syncthreads();
-    // Hillis-Steele inclusive scan of the partials
-    for (int off = 1; off < nt; off <<= 1) {
-        int v = (t >= off) ? part[t - off] : 0;
-        int m = (t >= off) ? pmax[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        pmax[t] = max(pmax[t], m);
-        __syncthreads();
+    __shared__ int wsum[32], wmax[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v, mx = v;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += u;
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
     }
-    int run = part[t] - sum; // exclusive prefix of this chunk
-    for (int i = b; i < e; i++) { ia1th[i] = run + 1; run += nac[i]; } // hm_IA1th is 1-based :1542-1551
-    if (t == nt - 1) { counters[CNT_MXNAC] = pmax[t]; counters[CNT_INCELL] = part[t]; }
+    if (lane == 31) wsum[w] = inc;
+    if (lane == 0) wmax[w] = mx;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (int)(blockDim.x >> 5);
+        int x = lane < nw ? wsum[lane] : 0, m = lane < nw ? wmax[lane] : 0, xi = x;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, xi, off);
+            if (lane >= off) xi += u;
+            m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+        }
+        wsum[lane] = xi - x;                      // exclusive prefix of the warp sums
+        if (lane == 31) wmax[0] = m;
+        if (lane == 31) wmax[1] = xi;             // block total
+    }
+    __syncthreads();
+    total = wmax[1]; vmax = wmax[0];
+    return wsum[w] + inc - v;
+}
+__global__ void __launch_bounds__(SCAN_B) k_scan_local(int c0, int c1, const int *__restrict__ nac, int *__restrict__ ia1th,
+                                                       int *__restrict__ btot, int *__restrict__ bmax)
+{
+    const int i = c0 + blockIdx.x * SCAN_B + threadIdx.x;
+    const int v = i < c1 ? nac[i] : 0;
+    int total, vmax;
+    const int ex = block_excl_scan(v, total, vmax);
+    if (i < c1) ia1th[i] = ex;
+    if (threadIdx.x == 0) { btot[blockIdx.x] = total; bmax[blockIdx.x] = vmax; }
+}
+// cnt_incell / cnt_mxnac (optional): device counters that take the number of atoms in [c0, c1) and the largest cell.
+// out4 (optional, slab decomposition): {atoms in [c0, c1), atoms of the first `cl` cells, atoms of the last `cl` cells, max count}
+__global__ void __launch_bounds__(SCAN_B) k_scan_apply(int c0, int c1, int first, int cl, const int *__restrict__ btot,
+                                                       const int *__restrict__ bmax, int *__restrict__ ia1th, int *__restrict__ cnt_incell,
+                                                       int *__restrict__ cnt_mxnac, int *__restrict__ out4)
+{
+    __shared__ int red[3][32];
+    const int nb = gridDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    int before = 0, all = 0, mx = 0;
+    for (int b = t; b < nb; b += SCAN_B) {
+        const int v = btot[b];
+        all += v;
+        if (b < (int)blockIdx.x) before += v;
+        mx = max(mx, bmax[b]);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, off);
+        all += __shfl_xor_sync(0xffffffffu, all, off);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if (lane == 0) { red[0][w] = before; red[1][w] = all; red[2][w] = mx; }
+    __syncthreads();
+    before = 0; all = 0; mx = 0;
+    for (int k = 0; k < SCAN_B / 32; k++) { before += red[0][k]; all += red[1][k]; mx = max(mx, red[2][k]); }
+    const int i = c0 + blockIdx.x * SCAN_B + t;
+    if (i < c1) {
+        const int pre = before + ia1th[i];               // atoms in the cells [c0, i)
+        ia1th[i] = first + pre + 1;
+        if (out4) {
+            const int nc = c1 - c0;
+            if (nc > cl && i == c0 + cl) out4[1] = pre;
+            if (nc > cl && i == c1 - cl) out4[2] = all - pre;
+        }
+    }
+    if (blockIdx.x == 0 && t == 0) {
+        if (cnt_incell) *cnt_incell = all;
+        if (cnt_mxnac) *cnt_mxnac = mx;
+        if (out4) {
+            out4[0] = all; out4[3] = mx;
+            if (c1 - c0 <= cl) { out4[1] = all; out4[2] = all; }
+        }
+    }
+}
+// host: the two launches; scratch = 2 * cdiv(c1 - c0, SCAN_B) ints
+static int scan_cells(mdb_ctx *c, int c0, int c1, int first, int cl, int *cnt_incell, int *cnt_mxnac, int *out4)
+{
+    const int nb = cdiv(c1 - c0, SCAN_B);
+    if (nb <= 0) return MDB_OK;
+    if (c->scan_n < 2 * nb) {
+        if (c->scan_tmp) cudaFree(c->scan_tmp);
+        c->scan_tmp = nullptr; c->scan_n = 0;
+        CUDA_TRY(c, cudaMalloc(&c->scan_tmp, sizeof(int) * 2 * (size_t)(nb + 64)));
+        c->scan_n = 2 * (nb + 64);
+    }
+    int *btot = c->scan_tmp, *bmax = c->scan_tmp + c->scan_n / 2;
+    k_scan_local<<<nb, SCAN_B, 0, c->stream>>>(c0, c1, c->nac, c->ia1th, btot, bmax);
+    k_scan_apply<<<nb, SCAN_B, 0, c->stream>>>(c0, c1, first, cl, btot, bmax, c->ia1th, cnt_incell, cnt_mxnac, out4);
+    CUDA_TRY(c, cudaGetLastError());
+    return MDB_OK;
 }
 
 __global__ void k_cell_scatter(int n, const int *__restrict__ ic, const int *__restrict__ slot,
@@ -173,7 +251,10 @@ int mdb_cells_build(mdb_ctx *c)
     if (c->dsr) CUDA_TRY(c, cudaMemsetAsync(c->dsr, 0, 3 * (size_t)n * sizeof(float), st)); // displacement since THIS rebuild
     k_cell_assign<<<nb, 256, 0, st>>>(n, c->napb, c->pos, c->gid, c->statu, c->box, c->ncell[0], c->ncell[1],
                                       c->ncell[2], c->nc0, c->ic, c->nac, c->naac, c->slot, c->oob, c->counters);
-    k_cell_scan<<<1, 1024, 0, st>>>(c->nc, c->nac, c->ia1th, c->counters);
+    {
+        int rc = scan_cells(c, 0, c->nc, 0, c->nc, c->counters + CNT_INCELL, c->counters + CNT_MXNAC, nullptr);
+        if (rc < 0) return rc;
+    }
     k_cell_scatter<<<nb, 256, 0, st>>>(n, c->ic, c->slot, c->ia1th, c->gid, c->tmp_orig);
     k_cell_rank<<<nb, 256, 0, st>>>(n, c->ic, c->ia1th, c->nac, c->gid, c->tmp_orig, c->gid_alt, c->srcof);
     k_oob_place<<<64, 256, 0, st>>>(n, c->counters, c->oob, c->gidinv, c->gid_alt, c->srcof);
@@ -241,37 +322,6 @@ __global__ void k_dd_cell_assign(DDRanges R, int total, const double4 *__restric
     }
     base = __shfl_sync(0xffffffffu, base, leader);
     if (cell > 0) slot[s] = base + __popc(grp & ((1u << lane) - 1u));
-}
-
-// exclusive prefix over the cells [c0, c1): ia1th[c] = first + prefix + 1.  out (optional): {atoms in [c0,c1), atoms of the first
-// `cl` cells (bottom layer), atoms of the last `cl` cells (top layer), max count}
-__global__ void k_dd_scan(int c0, int c1, int cl, int first, const int *__restrict__ nac, int *__restrict__ ia1th, int *__restrict__ out)
-{
-    __shared__ int part[1024];
-    __shared__ int pmax[1024];
-    const int t = threadIdx.x, nt = blockDim.x, nc = c1 - c0;
-    const int chunk = (nc + nt - 1) / nt;
-    const int b = c0 + t * chunk, e = min(b + chunk, c1);
-    int sum = 0, mx = 0;
-    for (int i = b; i < e; i++) { const int v = nac[i]; sum += v; mx = max(mx, v); }
-    part[t] = sum; pmax[t] = mx;
-    __syncthreads();
-    for (int off = 1; off < nt; off <<= 1) {
-        const int v = (t >= off) ? part[t - off] : 0, m = (t >= off) ? pmax[t - off] : 0;
-        __syncthreads();
-        part[t] += v; pmax[t] = max(pmax[t], m);
-        __syncthreads();
-    }
-    int run = part[t] - sum;
-    for (int i = b; i < e; i++) { ia1th[i] = first + run + 1; run += nac[i]; }
-    __syncthreads();
-    if (out && t == nt - 1) { out[0] = part[t]; out[3] = pmax[t]; }
-    if (out && t == 0) { // layer sums from the finished prefixes (cells are x-fastest, z-slowest: a layer is `cl` consecutive cells)
-        const int lastc = c1 - 1;
-        const int total = ia1th[lastc] - 1 - first + nac[lastc];
-        out[1] = (nc > cl) ? ia1th[c0 + cl] - 1 - first : total;
-        out[2] = (nc > cl) ? total - (ia1th[c1 - cl] - 1 - first) : total;
-    }
 }
 
 __global__ void k_dd_add_base(int c0, int c1, int base, int *__restrict__ ia1th)
@@ -342,9 +392,7 @@ int mdb_cells_dd_count(mdb_ctx *c, const int cand[6], int zl0, int zl1, int *d_o
     CUDA_TRY(c, cudaMemsetAsync(c->naac + c0, 0, sizeof(int) * (size_t)(c1 - c0), st));
     k_dd_cell_assign<<<cdiv(total, 256), 256, 0, st>>>(R, total, c->pos, c->statu, c->box, c->ncell[0], c->ncell[1], c->ncell[2], zl0, zl1,
                                                        c->ic, c->nac, c->naac, c->slot, c->counters);
-    k_dd_scan<<<1, 1024, 0, st>>>(c0, c1, cl, 0, c->nac, c->ia1th, d_out4);
-    CUDA_TRY(c, cudaGetLastError());
-    return MDB_OK;
+    return scan_cells(c, c0, c1, 0, cl, nullptr, nullptr, d_out4);
 }
 
 // phase 2: with the global slot `base` of this rank's first atom known, place and permute the owned range [base, base + nown)
@@ -377,7 +425,5 @@ int mdb_cells_dd_ghost_layer(mdb_ctx *c, int c0, int first)
 {
     const int cl = c->ncell[0] * c->ncell[1];
     ProfScope ps(c, MDB_K_CELLSORT, 1);
-    k_dd_scan<<<1, 1024, 0, c->stream>>>(c0, c0 + cl, cl, first, c->nac, c->ia1th, nullptr);
-    CUDA_TRY(c, cudaGetLastError());
-    return MDB_OK;
+    return scan_cells(c, c0, c0 + cl, first, cl, nullptr, nullptr, nullptr);
 }

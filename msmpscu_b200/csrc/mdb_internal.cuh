@@ -136,6 +136,7 @@ struct mdb_ctx {
     int ncell[3] = {0, 0, 0}, nc0 = 0, nc = 0, mxnac = 0;
     int *nac = nullptr, *naac = nullptr, *ia1th = nullptr;
     int *slot = nullptr, *srcof = nullptr, *tmp_orig = nullptr, *oob = nullptr;
+    int *scan_tmp = nullptr; int scan_n = 0; // block totals / maxima of the cell prefix scan
     int *counters = nullptr; // CNT__N ints on device
     int *h_counters = nullptr; // pinned mirror
     int mxkvois = 0;
