@@ -857,6 +857,7 @@ def c4_measure(args, nrep_total, cycles, md_steps):
     ctx.run(0, 20, 1, MD_PER_PERIOD, H)
     it = 20
     events = 0
+    quench = []
     t_md = t_det = 0.0
     if world > 1:
         dist.barrier()
@@ -868,9 +869,17 @@ def c4_measure(args, nrep_total, cycles, md_steps):
         it += md_steps
         b = time.perf_counter()
         ctx.state_save()
-        ctx.steepest(1000, 0.1, 0.1 * c.rr, 1.0e-5 * c.rr, 1.0e-5 * 1.60219e-12)
+        ctx.sync()
+        t1 = time.perf_counter()
+        q_iflag, q_move, q_de = ctx.steepest(1000, 0.1, 0.1 * c.rr, 1.0e-5 * c.rr, 1.0e-5 * 1.60219e-12)
+        t2 = time.perf_counter()
         fb, ibt, ncb = ctx.compare(xini, 0.03 * c.rr, nbox=disp.count)
+        t3 = time.perf_counter()
         ctx.state_restore()
+        ctx.sync()
+        t4 = time.perf_counter()
+        quench.append({"iflag": int(q_iflag), "save_s": round(t1 - b, 4), "quench_s": round(t2 - t1, 4), "compare_s": round(t3 - t2, 4),
+                       "restore_s": round(t4 - t3, 4)})
         flags = disp.gather_box_scalars(fb.reshape(-1, 1).astype(np.float64))      # every rank sees every replica's flag
         events += int(flags.sum())
         d = time.perf_counter()
@@ -888,7 +897,7 @@ def c4_measure(args, nrep_total, cycles, md_steps):
     return {"value": ntot * md_steps * cycles / dt, "unit": "atom-steps/s", "scaling": "strong", "n_gpus": world,
             "replicas_total": nrep_total, "replicas_this_rank": disp.count, "atoms_per_replica": int(c.napb), "cycles": cycles,
             "md_steps_per_cycle": md_steps, "wall_s": dt, "md_s": t_md, "event_detection_s": t_det, "events_flagged": events,
-            "md_only_atom_steps_per_s": ntot * md_steps * cycles / t_md,
+            "md_only_atom_steps_per_s": ntot * md_steps * cycles / t_md, "quench_per_cycle_rank0": quench,
             "force_path": "tiled" if path == capi.FORCE_PATH_TILED else "generic",
             "workload": "configs[3]: %d PARREP replicas x %d atoms (2000 W + 1 H, Bonny EAM1), %d cycles of %d MD steps + event detection "
                         "(device-side save / ST quench / compare / restore), replicas sharded over %d GPU(s), event flags gathered over the ranks"

@@ -151,6 +151,7 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
     mdb_dd_free(c);
     mdb_stopping_free(c);
     mdb_save_free(c);
+    if (c->scratch) { cudaFree(c->scratch); c->scratch = nullptr; c->scratch_bytes = 0; }
     mdb_prof_collect(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     free_state(c); free_nlist(c); free_tables(c);
@@ -719,6 +720,16 @@ extern "C" int mdb_nlist_cellinfo(const mdb_ctx *c, int ncell[3], int *nc_total,
 // Rebuild + capacity check (one small device-to-host copy and a stream synchronisation): when a tile's halo, an atom's
 // list or mxKVOIS overflowed on the tiled path, the same positions are rebuilt at once on the generic path (AUTO), so no
 // step ever runs on an incomplete list.  Used by mdb_nlist_build and at every rebuild inside mdb_run.
+void *mdb_scratch(mdb_ctx *c, size_t bytes)
+{
+    if (c->scratch_bytes >= bytes) return c->scratch;
+    if (c->scratch) { cudaStreamSynchronize(c->stream); cudaFree(c->scratch); }
+    c->scratch = nullptr; c->scratch_bytes = 0;
+    if (cudaMalloc(&c->scratch, bytes + bytes / 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    c->scratch_bytes = bytes + bytes / 4;
+    return c->scratch;
+}
+
 int mdb_list_rebuild_checked(mdb_ctx *c)
 {
     int rc = mdb_list_rebuild(c);

@@ -89,8 +89,10 @@ extern "C" int mdb_active_region(mdb_ctx *c, int method, const int *centpart, do
     CUDA_TRY(c, cudaSetDevice(c->dev));
     const int n = c->n, nc = c->nc, nb = cdiv(n, 256);
     cudaStream_t st = c->stream;
-    int *work = nullptr;
-    CUDA_TRY(c, cudaMallocAsync(&work, sizeof(int) * (2 * (size_t)nc + MDB_MXGROUP + 1), st));
+    // (work space from the context's grow-only scratch buffer: stream-ordered pool allocations were seen to stall for up to
+    // seconds after another context of the process had released a few GB)
+    int *work = reinterpret_cast<int *>(mdb_scratch(c, sizeof(int) * (2 * (size_t)nc + MDB_MXGROUP + 1)));
+    if (!work) return mdb_fail(c, MDB_ERR_CUDA, "mdb_active_region: out of device memory");
     int *m0 = work, *m1 = work + nc, *cent = work + 2 * (size_t)nc, *nact = cent + MDB_MXGROUP;
     CUDA_TRY(c, cudaMemsetAsync(work, 0, sizeof(int) * (2 * (size_t)nc + MDB_MXGROUP + 1), st));
     if (method & 1) CUDA_TRY(c, cudaMemcpyAsync(cent, centpart, sizeof(int) * c->ng, cudaMemcpyHostToDevice, st));
@@ -108,7 +110,6 @@ extern "C" int mdb_active_region(mdb_ctx *c, int method, const int *centpart, do
     k_ar_activate<<<nb, 256, 0, st>>>(n, c->ic, m0, c->statu, nact);
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + CNT_SCRATCH, nact, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(c, cudaFreeAsync(work, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     return c->h_counters[CNT_SCRATCH];
 }
@@ -360,9 +361,9 @@ extern "C" int mdb_compare(mdb_ctx *c, const double *xp_ini, const int *mask, do
     CUDA_TRY(c, cudaSetDevice(c->dev));
     const int n = c->n, napb = c->napb, nb = c->nbox;
     cudaStream_t st = c->stream;
-    char *w = nullptr;
     const size_t bx = sizeof(double) * 3 * (size_t)napb, bm = sizeof(int) * (size_t)napb, bf = sizeof(int) * (size_t)nb, ba = sizeof(int) * (size_t)n;
-    CUDA_TRY(c, cudaMallocAsync(&w, bx + bm + bf + ba + 64, st));
+    char *w = reinterpret_cast<char *>(mdb_scratch(c, bx + bm + bf + ba + 64));
+    if (!w) return mdb_fail(c, MDB_ERR_CUDA, "mdb_compare: out of device memory");
     double *dx = (double *)w; int *dm = (int *)(w + bx), *dfb = dm + napb, *dfa = dfb + nb;
     CUDA_TRY(c, cudaMemcpyAsync(dx, xp_ini, bx, cudaMemcpyHostToDevice, st));
     if (mask) CUDA_TRY(c, cudaMemcpyAsync(dm, mask, bm, cudaMemcpyHostToDevice, st));
@@ -374,7 +375,6 @@ extern "C" int mdb_compare(mdb_ctx *c, const double *xp_ini, const int *mask, do
     CUDA_TRY(c, cudaGetLastError());
     CUDA_TRY(c, cudaMemcpyAsync(flag_box, dfb, bf, cudaMemcpyDeviceToHost, st));
     if (flag_atom) CUDA_TRY(c, cudaMemcpyAsync(flag_atom, dfa, ba, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(c, cudaFreeAsync(w, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     int last = 0, cnt = 0;
     for (int b = 0; b < nb; b++) if (flag_box[b] > 0) { last = b + 1; cnt++; } // :1146-1156

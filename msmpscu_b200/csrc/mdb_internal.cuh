@@ -137,6 +137,7 @@ struct mdb_ctx {
     int *nac = nullptr, *naac = nullptr, *ia1th = nullptr;
     int *slot = nullptr, *srcof = nullptr, *tmp_orig = nullptr, *oob = nullptr;
     int *scan_tmp = nullptr; int scan_n = 0; // block totals / maxima of the cell prefix scan
+    void *scratch = nullptr; size_t scratch_bytes = 0; // grow-only work space of the occasional calls (mdb_scratch)
     int *counters = nullptr; // CNT__N ints on device
     int *h_counters = nullptr; // pinned mirror
     int mxkvois = 0;
@@ -260,5 +261,6 @@ int mdb_stopping_launch(mdb_ctx *c);          // mdb_cascade.cu : electronic sto
 bool mdb_stopping_on(const mdb_ctx *c);
 void mdb_stopping_free(mdb_ctx *c);
 void mdb_save_free(mdb_ctx *c);
+void *mdb_scratch(mdb_ctx *c, size_t bytes);  // mdb_api.cu : grow-only device work space of the context (valid until the next call)
 static inline int own_a0(const mdb_ctx *c) { return c->dd_on ? c->dd_info[0] : 0; }
 static inline int own_a1(const mdb_ctx *c) { return c->dd_on ? c->dd_info[1] : c->n; }             // mdb_api.cu : cells + list kernel of the active path (no sync)
