@@ -244,7 +244,7 @@ int mdb_cells_build(mdb_ctx *c)
 {
     int n = c->n, nb = cdiv(n, 256);
     cudaStream_t st = c->stream;
-    ProfScope ps(c, MDB_K_CELLSORT, 6);
+    ProfScope ps(c, MDB_K_CELLSORT, 7);
     CUDA_TRY(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * CNT_PERBUILD_N, st)); // CNT_OOB_TOTAL accumulates
     CUDA_TRY(c, cudaMemsetAsync(c->nac, 0, sizeof(int) * (size_t)c->nc, st));  // hm_NAC = 0 :1431
     CUDA_TRY(c, cudaMemsetAsync(c->naac, 0, sizeof(int) * (size_t)c->nc, st));
@@ -386,7 +386,7 @@ int mdb_cells_dd_count(mdb_ctx *c, const int cand[6], int zl0, int zl1, int *d_o
     DDRanges R;
     int total = 0;
     for (int k = 0; k < 3; k++) { R.r0[k] = cand[2 * k]; R.r1[k] = cand[2 * k + 1]; total += R.r1[k] - R.r0[k]; }
-    ProfScope ps(c, MDB_K_CELLSORT, 2);
+    ProfScope ps(c, MDB_K_CELLSORT, 3);
     CUDA_TRY(c, cudaMemsetAsync(c->counters, 0, sizeof(int) * CNT_PERBUILD_N, st));
     CUDA_TRY(c, cudaMemsetAsync(c->nac + c0, 0, sizeof(int) * (size_t)(c1 - c0), st));
     CUDA_TRY(c, cudaMemsetAsync(c->naac + c0, 0, sizeof(int) * (size_t)(c1 - c0), st));
@@ -424,6 +424,6 @@ int mdb_cells_dd_place(mdb_ctx *c, const int cand[6], int zl0, int zl1, int base
 int mdb_cells_dd_ghost_layer(mdb_ctx *c, int c0, int first)
 {
     const int cl = c->ncell[0] * c->ncell[1];
-    ProfScope ps(c, MDB_K_CELLSORT, 1);
+    ProfScope ps(c, MDB_K_CELLSORT, 2);
     return scan_cells(c, c0, c0 + cl, first, cl, nullptr, nullptr, nullptr);
 }

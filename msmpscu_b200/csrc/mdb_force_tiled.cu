@@ -1318,7 +1318,7 @@ static int launch_list(mdb_ctx *c)
     A.tile_lo = tile_lo;
     auto kern = k_tile_nlist<G, MT>;
     CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.smem_list));
-    ProfScope ps(c, MDB_K_NLIST, 2);
+    ProfScope ps(c, MDB_K_NLIST, S.bank_order ? 3 : 2);
     // descriptors: of this rank's tiles only in a decomposed run (cell counts of other slabs are not kept current there)
     if (tile_hi > tile_lo) {
         k_tile_desc<<<tile_hi - tile_lo, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters, tile_lo);
