@@ -80,6 +80,7 @@ def parse():
     ap.add_argument("--lanes", type=int, default=0, help="tiled path: lanes per atom (2/4/8), 0 = default")
     ap.add_argument("--classes", type=int, default=1, help="tiled path: distance-classified lists on/off")
     ap.add_argument("--threads", type=int, default=0, help="tiled path: threads of the pass CTA (512/768), 0 = default")
+    ap.add_argument("--pdl", type=int, default=-1, help="programmatic dependent launch of the predictor / passes (0/1), -1 = default")
     ap.add_argument("--bankorder", type=int, default=-1, help="tiled path: bank-aware order of the scanned list classes (0/1), -1 = default")
     ap.add_argument("--stages", type=int, default=0, help="tiled path: pipeline stages of the pass kernel (2/3), 0 = default")
     ap.add_argument("--c3-boxes", type=int, default=512, help="boxes of the configs[2] sub-record (512 x 16 000 atoms; 0 = skip)")
@@ -296,6 +297,8 @@ def new_ctx(c, local, args, stream):
         ctx.set_option(capi.OPT_TILED_STAGES, args.stages)
     if args.bankorder >= 0:
         ctx.set_option(capi.OPT_TILED_BANKORDER, args.bankorder)
+    if args.pdl >= 0:
+        ctx.set_option(capi.OPT_PDL, args.pdl)
     ctx.set_option(capi.OPT_TILED_CLASSES, args.classes)
     ctx.epc_set(EPC["enable"], EPC["te"], EPC["alpha"], EPC["cut"], EPC["he"])
     return ctx

@@ -390,6 +390,7 @@ int mdb_cg(mdb_ctx *ctx, int mxnumsteps, int meth, double maxdis, double mindis,
                                  /* -1 (default) on for boxes of >= 12 cells per edge                                         */
 #define MDB_OPT_TILE_GUARD    8  /* distance-class shortcut decided per tile from per-block displacement maxima: 1 on, 0 off,  */
                                  /* -1 (default) on with electronic stopping or the displacement-limited time step            */
+#define MDB_OPT_PDL           9  /* programmatic dependent launch of the predictor and the tiled passes: 1 (default) / 0            */
 #define MDB_FORCE_PATH_AUTO    0
 #define MDB_FORCE_PATH_GENERIC 1
 #define MDB_FORCE_PATH_TILED   2

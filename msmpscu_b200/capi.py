@@ -126,6 +126,7 @@ SYMBOLS = {
 OPT_FORCE_PATH, OPT_TILED_LANES, OPT_TILED_CLASSES, OPT_ACTIVE_PATH, OPT_TILED_THREADS, OPT_FUSE_EPILOGUE, OPT_TILED_STAGES = 0, 1, 2, 3, 4, 5, 6
 OPT_TILED_BANKORDER = 7
 OPT_TILE_GUARD = 8
+OPT_PDL = 9
 
 
 class Sched(C.Structure):

@@ -196,6 +196,10 @@ extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
         c->tiled.bank_order_opt = value; c->tiled.dirty = true; c->list_valid = false;
         return MDB_OK;
     }
+    if (option == MDB_OPT_PDL && (value == 0 || value == 1)) {
+        c->opt_pdl = value;
+        return MDB_OK;
+    }
     if (option == MDB_OPT_TILE_GUARD && value >= -1 && value <= 1) {
         c->opt_tile_guard = value;
         return MDB_OK;
@@ -219,6 +223,7 @@ extern "C" int mdb_get_option(const mdb_ctx *c, int option)
     if (option == MDB_OPT_TILED_CLASSES) return c->tiled.use_classes ? 1 : 0;
     if (option == MDB_OPT_TILED_BANKORDER) return c->tiled.bank_order ? 1 : 0;
     if (option == MDB_OPT_TILE_GUARD) return c->opt_tile_guard;
+    if (option == MDB_OPT_PDL) return c->opt_pdl;
     if (option == MDB_OPT_ACTIVE_PATH) return c->tiled.active ? MDB_FORCE_PATH_TILED : MDB_FORCE_PATH_GENERIC;
     return MDB_ERR_ARG;
 }

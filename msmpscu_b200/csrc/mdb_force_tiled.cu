@@ -724,7 +724,10 @@ __global__ void __launch_bounds__(NT, 1)
 k_tile_pass(TileParams P, TilePassArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    if (A.skip && *A.skip) return;
+    // Programmatic dependent launch: the kernel that follows in the stream may start its prologue while this grid drains, and
+    // this grid's own prologue (table window, barriers: constant data only) runs under the tail of the kernel before it;
+    // nothing that a previous kernel produced is touched before cudaGridDependencySynchronize() below.
+    cudaTriggerProgrammaticLaunchCompletion();
     constexpr int NW = NT / 32, NCW = NW - 1, APW = 32 / G;
     unsigned long long *bar_full = reinterpret_cast<unsigned long long *>(smem);  // TMA bytes landed
     unsigned long long *bar_ready = bar_full + TP_MAXBUF;                        // producer finished the stage
@@ -774,7 +777,9 @@ k_tile_pass(TileParams P, TilePassArgs A)
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
+    cudaGridDependencySynchronize();
     __syncthreads();
+    if (A.skip && *A.skip) return;   // converged quench iteration (uniform over the grid)
     // distance classes are usable while no atom (of the tile's halo, when the per-tile bounds are given) has moved more than half
     // the class margin since the rebuild.  mode: class-count row 0 / 1, or 2 = the full list (KVOIS)
     const float d2glob = __int_as_float(A.counters[CNT_D2MAX]);
@@ -1413,7 +1418,15 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
     ProfScope ps(c, PASS == 1 ? MDB_K_PASS1 : (PASS == 2 ? MDB_K_PASS2 : MDB_K_EPOT));
     const int ntl = (A.tile_hi - A.tile_lo) + (A.tile_hi2 - A.tile_lo2);
     if (ntl <= 0) return MDB_OK;
-    kern<<<std::min(S.grid, ntl), NT, S.smem_pass[PI], c->stream>>>(S.P, A);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(std::min(S.grid, ntl)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = S.smem_pass[PI]; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = c->opt_pdl ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_TRY(c, cudaLaunchKernelEx(&cfg, kern, S.P, A));
+    }
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }

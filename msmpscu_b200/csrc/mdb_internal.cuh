@@ -184,6 +184,7 @@ struct mdb_ctx {
 
     // ---- options
     int opt_force_path = MDB_FORCE_PATH_AUTO;
+    int opt_pdl = 1;           // programmatic dependent launch of the predictor and the tiled passes (prologues under the previous kernel's tail)
     int opt_fuse_epilogue = 0; // measured slower than the separate 27 us kernel on B200 (profiles/r01_summary.md)
 
     // ---- quench (mdb_quench.cu): work arrays, pinned scalar mirror, and the device flag that turns the force

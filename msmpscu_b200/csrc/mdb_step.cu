@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256, 4) k_predict(int n, double4 *__restrict__
                           float *__restrict__ dsr, int *__restrict__ counters, int a0, int a1, int pre, EpcParams E,
                           const int *__restrict__ skip, float *__restrict__ dmax_blk)
 {
+    cudaTriggerProgrammaticLaunchCompletion();   // (programmatic dependent launch: see k_tile_pass)
+    cudaGridDependencySynchronize();
     if (skip && *skip) return; // converged quench iteration (mdb_dyndamp)
     const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     float d2 = 0.f;
@@ -194,10 +196,17 @@ static int predict_launch(mdb_ctx *c, double h, int pre)
     const double th = h, hs2 = th * 0.5, h2s2 = th * th * 0.5;
     if (!c->epc.on) pre &= ~1;
     ProfScope ps(c, MDB_K_PREDICT);
-    k_predict<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, c->ityp,
-                                                                     c->mass, c->box, th, h2s2, hs2, c->dsr, c->counters,
-                                                                     own_a0(c), own_a1(c), pre, c->epc, c->skip_flag,
-                                                                     c->dsr ? c->dmax_blk : nullptr);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cdiv(own_a1(c) - own_a0(c), 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = c->opt_pdl ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_TRY(c, cudaLaunchKernelEx(&cfg, k_predict, c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, (const int *)c->ityp, c->mass, c->box, th, h2s2,
+                                       hs2, c->dsr, c->counters, own_a0(c), own_a1(c), pre, c->epc, c->skip_flag,
+                                       c->dsr ? c->dmax_blk : (float *)nullptr));
+    }
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
