@@ -1423,7 +1423,7 @@ static int launch_pass(mdb_ctx *c, int fuse, double hs2)
         cfg.gridDim = dim3(std::min(S.grid, ntl)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = S.smem_pass[PI]; cfg.stream = c->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = c->opt_pdl ? 1 : 0;
+        at[0].val.programmaticStreamSerializationAllowed = (c->opt_pdl && !c->dd_on) ? 1 : 0; // (decomposed steps order their kernels with events)
         cfg.attrs = at; cfg.numAttrs = 1;
         CUDA_TRY(c, cudaLaunchKernelEx(&cfg, kern, S.P, A));
     }

@@ -201,7 +201,7 @@ static int predict_launch(mdb_ctx *c, double h, int pre)
         cfg.gridDim = dim3(cdiv(own_a1(c) - own_a0(c), 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = c->opt_pdl ? 1 : 0;
+        at[0].val.programmaticStreamSerializationAllowed = (c->opt_pdl && !c->dd_on) ? 1 : 0; // (decomposed steps order their kernels with events)
         cfg.attrs = at; cfg.numAttrs = 1;
         CUDA_TRY(c, cudaLaunchKernelEx(&cfg, k_predict, c->n, c->pos, c->xp1, c->fp, c->dis, c->statu, (const int *)c->ityp, c->mass, c->box, th, h2s2,
                                        hs2, c->dsr, c->counters, own_a0(c), own_a1(c), pre, c->epc, c->skip_flag,
