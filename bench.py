@@ -714,7 +714,7 @@ def dd_cascade(args, c, ctx, dom, stream, itime, blocks, barrier, world):
     run the way the reference runs cascades (examples/Cascade_Test/CtrlFile300K_LOC_T.dat): displacement-limited time step
     (&STEPSIZE flag -1, hmx 0.5 fs, dmx 0.05 A), EPC + electronic stopping on the atoms, list rebuilt every 10 steps.  The
     stopping table is of the Lindhard-Scharff form S(E) = k sqrt(E) with k for W in W (the reference builds its LS_Z85 table
-    from the same law; the global-density model is the one the library has)."""
+    from the same law); local-density model and per-atom energy-loss bookkeeping as in that file (&MDEN = -1, &SAVEELOSS)."""
     import torch
     import torch.distributed as dist
     from msmpscu_b200 import capi
@@ -729,6 +729,7 @@ def dd_cascade(args, c, ctx, dom, stream, itime, blocks, barrier, world):
     stab = (k_ls * np.sqrt(etab / CP_EVERG)).reshape(-1, 1)
     mden = n / float(np.prod(c.zl))
     ctx.stopping_set(etab, stab, np.array([[1]]), [1], [mden])
+    ctx.stopping_options(local_density=True, save_eloss=True)                        # &MDEN = -1, &SAVEELOSS = "YES" of the reference's cascade file
     sched = capi.Sched(-1, H, H, 0.05e-8, MD_PER_PERIOD, MD_PER_PERIOD, 100)          # dmx = 0.05 Angstrom (MD_Gvar.F90:947)
     st = {"h": H, "t": 0.0}
 
@@ -757,9 +758,10 @@ def dd_cascade(args, c, ctx, dom, stream, itime, blocks, barrier, world):
     return {"value": n * MD_PER_PERIOD * blocks / (ms * 1e-3), "unit": "atom-steps/s", "ms_per_block": ms / blocks, "blocks": blocks,
             "pka_kev": ekev, "pka_original_id": ipka, "h_fs_after_first_block": h_first * 1e15, "h_fs_last": st["h"] * 1e15,
             "simulated_fs": st["t"] * 1e15, "phase_ms_per_block_rank0": prof,
+            "inelastic_loss_ev_this_rank": float(ctx.stopping_eloss().sum() / CP_EVERG),
             "workload": "the same box with one %.0f keV PKA at the centre along <135>: displacement-limited step (hmx 0.5 fs, dmx 0.05 A, "
                         "checked every step: one mask kernel + 4-byte read-back, OR-ed over the ranks), EPC + electronic stopping "
-                        "(Lindhard-Scharff form table, global-density model) between friction and corrector, per-tile displacement "
+                        "(Lindhard-Scharff form table, local-density model, per-atom energy loss accumulated) between friction and corrector, per-tile displacement "
                         "bounds for the distance-class shortcut" % ekev}
 
 

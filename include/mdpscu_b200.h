@@ -193,8 +193,15 @@ int mdb_epc_correct(mdb_ctx *ctx, double h);
  *                      Stop_Z95, Stop_B) fill them, KPAIR(NG,NG) column-major 1-based (moving type, medium type), the
  *                      per-type switch (LT_CTRL%METH and CP_TICTRL_METH_ST) and the number densities MDEN [1/cm^3] of the
  *                      medium types (global-density model, ST_MOD_GDEN_KERNEL :431-536).  ne < 2 switches it off.
- *   mdb_stopping_apply Do_STMOD_Force_DEV (:787-831): FP -= sum_g MDEN_g S_kg(E) v/|v|.  mdb_run applies it every step between
- *                      the EPC friction and the corrector once tables are set.
+ *   mdb_stopping_options  the two switches Reset_STMOD_DEV derives from the control file (:361-427): local_density != 0 = the
+ *                      local-density model (ST_CTRL%MDEN < 0 -> mp_STMOD_L, ST_MOD_LDEN_KERNEL :604-717: the density of medium type
+ *                      g around an atom is its number of LIST neighbours of that type over LVOL = 4 pi/3 NB_RM(i,g)^3);
+ *                      save_eloss != 0 = per-atom inelastic energy loss FF |V| DT accumulated over the steps
+ *                      (ST_CTRL%SaveEloss, ST_MOD_ELOSS_*_KERNEL :835-1132, the "Eloss (ev)" data pad of Do_STMOD_DEV :1248-1262)
+ *   mdb_stopping_eloss the accumulators [erg], ORIGINAL order; reset != 0 clears them
+ *   mdb_stopping_apply Do_STMOD_Force_DEV / Do_STMOD_Force_Eloss_DEV (:787-831, :1206-1262): FP -= sum_g n_g S_kg(E) v/|v|; dt =
+ *                      CtrlParam%H (used by the energy-loss bookkeeping only).  mdb_run applies it every step between the EPC
+ *                      friction and the corrector once tables are set.
  *   mdb_pka_insert     a primary knock-on atom (Deposition/MD_TypeDef_Projectile.F90, CP_DEP_STYPE_PKA, mono-energetic): the
  *                      velocity of the atom with ORIGINAL id orig_id becomes sqrt(2 EK / m) along dir
  * ---------------------------------------------------------------------------------- */
@@ -202,7 +209,9 @@ int mdb_active_region(mdb_ctx *ctx, int method, const int *centpart, double ekin
 int mdb_active_all(mdb_ctx *ctx, int on);
 int mdb_stopping_set(mdb_ctx *ctx, int ne, int nk, const double *etab, const double *stab, const int *kpair, const int *enable,
                      const double *mden);
-int mdb_stopping_apply(mdb_ctx *ctx);
+int mdb_stopping_options(mdb_ctx *ctx, int local_density, int save_eloss);
+int mdb_stopping_eloss(mdb_ctx *ctx, double *eloss_host, int reset);
+int mdb_stopping_apply(mdb_ctx *ctx, double dt);
 int mdb_pka_insert(mdb_ctx *ctx, int orig_id, double ekin_erg, const double dir[3]);
 
 /* ------------------------------------------------------------------------------------

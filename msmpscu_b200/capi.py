@@ -69,7 +69,9 @@ SYMBOLS = {
     "mdb_active_region": (C.c_int, [C.c_void_p, C.c_int, c_ip, C.c_double, C.c_int]),
     "mdb_active_all": (C.c_int, [C.c_void_p, C.c_int]),
     "mdb_stopping_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_ip, c_ip, c_dp]),
-    "mdb_stopping_apply": (C.c_int, [C.c_void_p]),
+    "mdb_stopping_apply": (C.c_int, [C.c_void_p, C.c_double]),
+    "mdb_stopping_options": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mdb_stopping_eloss": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
     "mdb_pka_insert": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp]),
     "mdb_dd_nccl_id": (C.c_int, [C.c_void_p]),
     "mdb_dd_nccl_init": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -379,8 +381,18 @@ class Context:
         self._chk(self.lib.mdb_stopping_set(self.h, len(e), st.size // len(e), dp(e), dp(st), ip(kp), ip(self._stop_keep[3]),
                                             dp(self._stop_keep[4])))
 
-    def stopping_apply(self):
-        self._chk(self.lib.mdb_stopping_apply(self.h))
+    def stopping_apply(self, dt=0.0):
+        self._chk(self.lib.mdb_stopping_apply(self.h, float(dt)))
+
+    def stopping_options(self, local_density=False, save_eloss=False):
+        """Reset_STMOD_DEV's switches: local-density model (ST_CTRL%MDEN < 0), per-atom energy-loss accumulation"""
+        self._chk(self.lib.mdb_stopping_options(self.h, 1 if local_density else 0, 1 if save_eloss else 0))
+
+    def stopping_eloss(self, reset=False):
+        """accumulated inelastic energy loss per atom [erg], ORIGINAL order"""
+        e = np.zeros(self.n)
+        self._chk(self.lib.mdb_stopping_eloss(self.h, dp(e), 1 if reset else 0))
+        return e
 
     def pka_insert(self, orig_id, ekin_erg, direction):
         d = f64(direction)

@@ -817,6 +817,7 @@ int mdb_list_rebuild(mdb_ctx *c)
     if (c->opt_force_path == MDB_FORCE_PATH_TILED && !c->tiled.ok)
         return mdb_fail(c, MDB_ERR_UNSUPPORTED, "tiled path not available for this configuration (tables, BOXSHAPE or density)");
     c->tiled.active = c->tiled.ok && c->opt_force_path != MDB_FORCE_PATH_GENERIC;
+    c->list_gen++;
     int rc = mdb_cells_build(c);
     if (rc < 0) return rc;
     c->indi_stale = false;

@@ -131,15 +131,35 @@ extern "C" int mdb_active_all(mdb_ctx *c, int on)
 // ------------------------------------------------------------------------------------
 __global__ void k_stopping(int n, StopParams S, const double *__restrict__ etab, const double *__restrict__ stab,
                            const int *__restrict__ ityp, const int *__restrict__ statu, const double *__restrict__ xp1,
-                           double *__restrict__ fp, int a0, int a1)
+                           double *__restrict__ fp, int a0, int a1, const int *__restrict__ kvois, const int *__restrict__ nbc,
+                           double dt, double *__restrict__ eloss, const int *__restrict__ gid)
 {
     const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a1) return;
     if ((statu[i] & ST_ACTIVE) != ST_ACTIVE) return;
-    double fx = fp[i], fy = fp[i + (size_t)n], fz = fp[i + 2 * (size_t)n];
-    if (stop_force(S, etab, stab, ityp[i] - 1, xp1[i], xp1[i + (size_t)n], xp1[i + 2 * (size_t)n], fx, fy, fz)) {
+    double fx = fp[i], fy = fp[i + (size_t)n], fz = fp[i + 2 * (size_t)n], loss;
+    if (stop_force(S, etab, stab, ityp[i] - 1, xp1[i], xp1[i + (size_t)n], xp1[i + 2 * (size_t)n], fx, fy, fz, kvois, nbc, i, n, dt,
+                   eloss ? &loss : nullptr)) {
         fp[i] = fx; fp[i + (size_t)n] = fy; fp[i + 2 * (size_t)n] = fz;
+        if (eloss) eloss[gid[i] - 1] += loss;     // (one thread per atom: no race)
     }
+}
+// DEN(IG) of the local-density model for boxes with several types: list neighbours of every type (:690-694), from INDI
+__global__ void k_stop_nbcount(int n, int ng, const int *__restrict__ kvois, const int *__restrict__ indi, const int *__restrict__ ityp,
+                               int *__restrict__ nbc, int a0, int a1)
+{
+    const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a1) return;
+    int cnt[MDB_MXGROUP];
+#pragma unroll
+    for (int g = 0; g < MDB_MXGROUP; g++) cnt[g] = 0;
+    const int kv = kvois[i];
+    for (int w = 0; w < kv; w++) {
+        const int t = ityp[indi[i + (size_t)w * n] - 1] - 1;
+#pragma unroll
+        for (int g = 0; g < MDB_MXGROUP; g++) cnt[g] += (t == g) ? 1 : 0;
+    }
+    for (int g = 0; g < ng; g++) nbc[(size_t)g * n + i] = cnt[g];
 }
 
 static StopState *stop_of(mdb_ctx *c) { return reinterpret_cast<StopState *>(c->stop_state); }
@@ -154,7 +174,7 @@ extern "C" int mdb_stopping_set(mdb_ctx *c, int ne, int nk, const double *etab, 
     if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_stopping_set: mdb_box_set first");
     CUDA_TRY(c, cudaSetDevice(c->dev));
     StopState *S = stop_of(c);
-    if (S) { cudaFree(S->etab); cudaFree(S->stab); delete S; c->stop_state = nullptr; }
+    if (S) mdb_stopping_free(c);
     if (ne < 2 || nk < 1 || !etab || !stab || !kpair || !enable) return MDB_OK; // switched off
     S = new StopState();
     memset(&S->P, 0, sizeof(S->P));
@@ -179,14 +199,72 @@ extern "C" int mdb_stopping_set(mdb_ctx *c, int ne, int nk, const double *etab, 
     return MDB_OK;
 }
 
-// Do_STMOD_Force_DEV (:787-831): to be called after the force and the EPC friction (Do_EPCForce_DEV :135-136)
-int mdb_stopping_launch(mdb_ctx *c)
+// model and bookkeeping switches of Reset_STMOD_DEV (:361-427): ST_CTRL%MDEN < 0 selects the local-density model (hm_STMOD =
+// mp_STMOD_L, LVOL = 4 pi/3 NB_RM^3 from the list cut-offs), ST_CTRL%SaveEloss the per-atom energy-loss accumulation
+extern "C" int mdb_stopping_options(mdb_ctx *c, int local_density, int save_eloss)
+{
+    if (!c) return MDB_ERR_ARG;
+    StopState *S = stop_of(c);
+    if (!S) return mdb_fail(c, MDB_ERR_STATE, "mdb_stopping_options: mdb_stopping_set first");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    if (local_density) {
+        if (!c->has_nlist) return mdb_fail(c, MDB_ERR_STATE, "mdb_stopping_options: the local-density model needs the list cut-offs (mdb_nlist_init)");
+        if (c->dd_on && c->ng > 1)
+            return mdb_fail(c, MDB_ERR_UNSUPPORTED, "mdb_stopping_options: local-density model with several atom types is not available in slab-decomposed runs");
+        for (int i = 0; i < c->ng * c->ng; i++) {
+            const double r = c->nb_rm[i];
+            S->P.lv[i] = 4.0 * 3.14159265358979323846 / 3.0 * (r * r * r);   // CP_4PI3*(NB_RM**3)
+        }
+    }
+    S->P.local = local_density ? 1 : 0;
+    S->nbc_gen = -1;
+    S->save_eloss = save_eloss ? 1 : 0;
+    if (S->save_eloss && !S->eloss) {
+        CUDA_TRY(c, cudaMalloc(&S->eloss, sizeof(double) * (size_t)c->n));
+        CUDA_TRY(c, cudaMemsetAsync(S->eloss, 0, sizeof(double) * (size_t)c->n, c->stream));
+    }
+    return MDB_OK;
+}
+// accumulated inelastic energy loss per atom [erg], ORIGINAL order ("Eloss (ev)" data pad of the reference, :1248-1262, in erg);
+// reset != 0 clears the accumulators afterwards.  In a decomposed run every rank holds the losses of the atoms while it owned them.
+extern "C" int mdb_stopping_eloss(mdb_ctx *c, double *eloss_host, int reset)
+{
+    if (!c || !eloss_host) return mdb_fail(c, MDB_ERR_ARG, "mdb_stopping_eloss: null argument");
+    StopState *S = stop_of(c);
+    if (!S || !S->eloss) return mdb_fail(c, MDB_ERR_STATE, "mdb_stopping_eloss: energy-loss bookkeeping is not switched on (mdb_stopping_options)");
+    CUDA_TRY(c, cudaSetDevice(c->dev));
+    CUDA_TRY(c, cudaMemcpyAsync(eloss_host, S->eloss, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (reset) CUDA_TRY(c, cudaMemsetAsync(S->eloss, 0, sizeof(double) * (size_t)c->n, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MDB_OK;
+}
+// per-type neighbour counts of the local model (several types): refreshed when the list has been rebuilt since the last count
+int mdb_stopping_prepare(mdb_ctx *c)
+{
+    StopState *S = stop_of(c);
+    if (!S || !S->P.on || !S->P.local || c->ng == 1 || S->nbc_gen == c->list_gen) return MDB_OK;
+    int rc = mdb_indi_ensure(c);
+    if (rc < 0) return rc;
+    if (!S->nbc) CUDA_TRY(c, cudaMalloc(&S->nbc, sizeof(int) * (size_t)c->ng * c->n));
+    ProfScope ps(c, MDB_K_OTHER);
+    k_stop_nbcount<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, c->ng, c->kvois, c->indi, c->ityp, S->nbc, own_a0(c), own_a1(c));
+    CUDA_TRY(c, cudaGetLastError());
+    S->nbc_gen = c->list_gen;
+    return MDB_OK;
+}
+
+// Do_STMOD_Force_DEV / Do_STMOD_Force_Eloss_DEV (:787-831, :1206-1262): to be called after the force and the EPC friction
+// (Do_EPCForce_DEV :135-136); dt = CtrlParam%H of the step (energy-loss bookkeeping only)
+int mdb_stopping_launch(mdb_ctx *c, double dt)
 {
     StopState *S = stop_of(c);
     if (!S || !S->P.on) return MDB_OK; // hm_NEEDDO = .false.
+    int rc = mdb_stopping_prepare(c);
+    if (rc < 0) return rc;
     ProfScope ps(c, MDB_K_CORRECT);
     k_stopping<<<cdiv(own_a1(c) - own_a0(c), 256), 256, 0, c->stream>>>(c->n, S->P, S->etab, S->stab, c->ityp, c->statu, c->xp1, c->fp,
-                                                                      own_a0(c), own_a1(c));
+                                                                      own_a0(c), own_a1(c), c->kvois, S->nbc, dt,
+                                                                      S->save_eloss ? S->eloss : nullptr, c->gid);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }
@@ -198,15 +276,15 @@ bool mdb_stopping_on(const mdb_ctx *c)
 void mdb_stopping_free(mdb_ctx *c)
 {
     StopState *S = stop_of(c);
-    if (S) { cudaFree(S->etab); cudaFree(S->stab); delete S; }
+    if (S) { cudaFree(S->etab); cudaFree(S->stab); if (S->nbc) cudaFree(S->nbc); if (S->eloss) cudaFree(S->eloss); delete S; }
     c->stop_state = nullptr;
 }
-extern "C" int mdb_stopping_apply(mdb_ctx *c)
+extern "C" int mdb_stopping_apply(mdb_ctx *c, double dt)
 {
     if (!c) return MDB_ERR_ARG;
     if (!c->has_box) return mdb_fail(c, MDB_ERR_STATE, "mdb_stopping_apply: mdb_box_set first");
     CUDA_TRY(c, cudaSetDevice(c->dev));
-    return mdb_stopping_launch(c);
+    return mdb_stopping_launch(c, dt);
 }
 
 // ------------------------------------------------------------------------------------

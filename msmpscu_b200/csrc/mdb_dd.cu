@@ -526,7 +526,7 @@ static int dd_local_rebuild(mdb_ctx *c)
     }
     // (6) lists of my tiles; a capacity overflow cannot fall back to the generic path here
     if ((rc = all_ranks(c, [&](mdb_ctx *p) {
-            p->indi_stale = true; p->list_reordered = false;
+            p->indi_stale = true; p->list_reordered = false; p->list_gen++;
             int rc2 = mdb_tiled_nlist(p);
             if (rc2 < 0) return rc2;
             p->list_valid = true;

@@ -146,6 +146,7 @@ struct mdb_ctx {
     bool indi_stale = false;
     double4 *pos_snap = nullptr; size_t pos_snap_bytes = 0;
     int oob_total = 0;
+    long long list_gen = 0;    // counts the list rebuilds (caches derived from the list compare it)
     bool run_pending = false;  // mdb_run_async enqueued a block whose counters mdb_sync still has to read
     int fallbacks = 0;         // rebuilds that overflowed the tiled path and were redone on the generic one
 
@@ -258,7 +259,8 @@ double mdb_sched_h1(const mdb_sched *s, int itime, int it0, double h);
 bool mdb_tile_guard_wanted(const mdb_ctx *c);
 int mdb_tile_guard_launch(mdb_ctx *c, int lo, int hi);    // mdb_force_tiled.cu : per-tile displacement bounds for this step's passes
 void mdb_dd_free(mdb_ctx *c);                 // mdb_dd.cu
-int mdb_stopping_launch(mdb_ctx *c);          // mdb_cascade.cu : electronic stopping on FP (no-op when switched off)
+int mdb_stopping_launch(mdb_ctx *c, double dt); // mdb_cascade.cu : electronic stopping on FP (no-op when switched off)
+int mdb_stopping_prepare(mdb_ctx *c);          // per-type neighbour counts of the local-density model, after a rebuild
 bool mdb_stopping_on(const mdb_ctx *c);
 void mdb_stopping_free(mdb_ctx *c);
 void mdb_save_free(mdb_ctx *c);

@@ -142,7 +142,9 @@ __global__ void k_epc_correct(int n, double *__restrict__ xp1, double *__restric
 // (ST_MOD_GDEN_KERNEL) and the corrector half-kick, each with the arithmetic of its own kernel, on the values in registers.
 __global__ void k_step_close(int n, double *__restrict__ xp1, double *__restrict__ fp, const int *__restrict__ statu,
                              const int *__restrict__ ityp, MassParams M, EpcParams E, int do_epc, StopParams S,
-                             const double *__restrict__ etab, const double *__restrict__ stab, double hs2, int a0, int a1)
+                             const double *__restrict__ etab, const double *__restrict__ stab, double hs2, int a0, int a1,
+                             const int *__restrict__ kvois, const int *__restrict__ nbc, double *__restrict__ eloss,
+                             const int *__restrict__ gid)
 {
     const int i = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a1) return;
@@ -164,7 +166,10 @@ __global__ void k_step_close(int n, double *__restrict__ xp1, double *__restrict
             wr = true;
         }
     }
-    wr = stop_force(S, etab, stab, kk, vx, vy, vz, fx, fy, fz) || wr;
+    double loss;
+    const bool stopped = stop_force(S, etab, stab, kk, vx, vy, vz, fx, fy, fz, kvois, nbc, i, n, __dadd_rn(hs2, hs2), eloss ? &loss : nullptr);
+    if (stopped && eloss) eloss[gid[i] - 1] += loss;
+    wr = stopped || wr;
     if (wr) { fp[i] = fx; fp[i + n1] = fy; fp[i + n2] = fz; }
     const double cm0 = M.cm[kk]; // Correction_KERNEL :735-753
     if ((stat & ST_FIXVELX) == 0 && (stat & ST_FIXPOSX) == 0) xp1[i] = __dadd_rn(vx, __dmul_rn(hs2, __ddiv_rn(fx, cm0)));
@@ -248,9 +253,12 @@ int mdb_step_close_launch(mdb_ctx *c, double h)
     const int a0 = own_a0(c), a1 = own_a1(c);
     if (!mdb_stopping_on(c)) return mdb_epc_correct_launch(c, h);
     const StopState *S = reinterpret_cast<const StopState *>(c->stop_state);
+    int rc = mdb_stopping_prepare(c);
+    if (rc < 0) return rc;
     ProfScope ps(c, MDB_K_CORRECT);
     k_step_close<<<cdiv(a1 - a0, 256), 256, 0, c->stream>>>(c->n, c->xp1, c->fp, c->statu, c->ityp, c->mass, c->epc, c->epc.on, S->P,
-                                                          S->etab, S->stab, h * 0.5, a0, a1);
+                                                          S->etab, S->stab, h * 0.5, a0, a1, c->kvois, S->nbc,
+                                                          S->save_eloss ? S->eloss : nullptr, c->gid);
     CUDA_TRY(c, cudaGetLastError());
     return MDB_OK;
 }

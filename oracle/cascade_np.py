@@ -91,3 +91,44 @@ def stopping_force_gden(fp, xp1, ityp, statu, cm, etab, stab, kpair, enable, mde
         f[i, 1] -= ff * vy / v
         f[i, 2] -= ff * vz / v
     return f
+
+
+def stopping_force_lden(fp, xp1, ityp, statu, cm, etab, stab, kpair, enable, kvois, indi, nb_rm, dt=0.0):
+    """ST_MOD_LDEN_KERNEL / ST_MOD_ELOSS_LDEN_KERNEL, LocalTempCtrlMeths/Stopping/MD_ST_Coupling_GPU.F90:604-717,1015-1132: the local
+    density of medium type g around atom i is the number of its LIST neighbours of that type (:690-694) over LVOL(i,g) = 4 pi/3
+    NB_RM(i,g)^3 (Reset_STMOD_DEV :412).  All per-atom arrays in ONE order (the list's): fp, xp1 (N,3); kvois (N,), indi (N, mx)
+    1-based; nb_rm (NG,NG) in cm.  Returns (updated FP, ELOSS = FF |V| DT per atom).  (Per-atom Python loop: small cases only.)"""
+    f = np.array(fp, dtype=np.float64)
+    etab, stab = np.asarray(etab, dtype=np.float64), np.asarray(stab, dtype=np.float64)
+    nb_rm = np.asarray(nb_rm, dtype=np.float64)
+    ng = len(cm)
+    de = etab[1] - etab[0]
+    deinv = 1.0 / de
+    emin, emax = etab[0], etab[-1]
+    lv = 4.0 * np.pi / 3.0 * nb_rm ** 3
+    eloss = np.zeros(f.shape[0])
+    for i in range(f.shape[0]):
+        kk = int(ityp[i]) - 1
+        if (statu[i] & STATU_ACTIVE) != STATU_ACTIVE or enable[kk] <= 0:
+            continue
+        vx, vy, vz = xp1[i]
+        vv = vx * vx + vy * vy + vz * vz
+        ek = 0.5 * cm[kk] * vv
+        iiw = int(kvois[i])
+        if not (emin <= ek <= emax) or iiw <= 0:                        # :688
+            continue
+        den = np.zeros(ng)
+        for w in range(iiw):                                            # :690-694
+            den[int(ityp[int(indi[i, w]) - 1]) - 1] += 1.0
+        ik = int((ek - emin) * deinv)
+        ff = 0.0
+        for ig in range(ng):                                            # :701-705
+            kp = int(kpair[kk][ig]) - 1
+            ilv = 1.0 / lv[kk, ig] / de                                 # ILV :669
+            ff = ff + den[ig] * ilv * ((ek - etab[ik]) * stab[ik + 1, kp] + (etab[ik + 1] - ek) * stab[ik, kp])
+        v = np.sqrt(vv)
+        f[i, 0] -= ff * vx / v
+        f[i, 1] -= ff * vy / v
+        f[i, 2] -= ff * vz / v
+        eloss[i] = ff * v * dt                                          # :1130
+    return f, eloss

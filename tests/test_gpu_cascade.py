@@ -148,6 +148,63 @@ def test_electronic_stopping_matches_restatement_and_rides_in_mdb_run():
         x.close()
 
 
+def test_local_density_stopping_and_energy_loss_match_restatement():
+    """ST_MOD_LDEN_KERNEL + the ELOSS bookkeeping: W + H box (two types: per-type neighbour counts from INDI) and a one-type box
+    (counts = KVOIS), on both force paths; the loss accumulates over the steps of mdb_run with the step's own H"""
+    for case, pkas in ((util.neb_case("react"), ((17, 5000.0), (None, 300.0))), (util.bcc_case((9, 8, 8), seed=5, temp=300.0), ((40, 3000.0),))):
+        c = case
+        n = c.xp.shape[0]
+        ng = len(c.mass)
+        etab, stab, kpair = _stop_tables(ng)
+        enable = [1] * ng
+        for path in (capi.FORCE_PATH_GENERIC, capi.FORCE_PATH_TILED):
+            ctx = util.make_ctx(c, build=False, force_path=path)
+            ctx.nlist_build()
+            for orig, ev in pkas:
+                ctx.pka_insert(n if orig is None else orig, ev * EV, [1.0, 3.0, 5.0])
+            ctx.force(capi.FORCE)
+            ctx.stopping_set(etab, stab, kpair, enable, [0.0] * ng)
+            ctx.stopping_options(local_density=True, save_eloss=True)
+            f0 = ctx.download(capi.F_FP, capi.ORDER_CELL)
+            v = ctx.download(capi.F_XP1, capi.ORDER_CELL)
+            ityp_c, st_c = ctx.download(capi.F_ITYP, capi.ORDER_CELL), ctx.download(capi.F_STATU, capi.ORDER_CELL)
+            kv, indi = ctx.nlist_copyout(capi.ORDER_CELL)
+            h = 0.25e-15
+            ctx.stopping_apply(h)
+            f1 = ctx.download(capi.F_FP, capi.ORDER_CELL)
+            want, loss = CN.stopping_force_lden(f0, v, ityp_c, st_c, c.mass, etab, stab, kpair, enable, kv, indi.T, c.nb_rm, dt=h)
+            assert np.any(f1 != f0) and np.max(np.abs(f1 - want)) <= 1e-14 * np.max(np.abs(want))
+            gid = ctx.download(capi.F_GID, capi.ORDER_CELL)
+            el = ctx.stopping_eloss()
+            assert np.count_nonzero(loss) == len(pkas) and np.max(np.abs(el[gid - 1] - loss)) <= 1e-14 * loss.max()
+            # inside mdb_run: the fused end-of-step kernel == the kernel-by-kernel sequence, losses included
+            a, b = util.make_ctx(c, build=False, force_path=path), util.make_ctx(c, build=False, force_path=path)
+            epc = ([1] * ng, [300.0] * ng, [1.0e-12] * ng, [0.1] * ng, [100.0 * EV] * ng)
+            for x in (a, b):
+                x.nlist_build()
+                for orig, ev in pkas:
+                    x.pka_insert(n if orig is None else orig, ev * EV, [1.0, 3.0, 5.0])
+                x.epc_set(*epc)
+                x.stopping_set(etab, stab, kpair, enable, [0.0] * ng)
+                x.stopping_options(local_density=True, save_eloss=True)
+                x.force(capi.FORCE)
+            a.run(0, 12, 1, 10, h)
+            for it in range(12):
+                b.predict(h)
+                if (it - 1) % 10 == 0:
+                    b.nlist_build()
+                b.force(capi.FORCE)
+                b.epc_apply()
+                b.stopping_apply(h)
+                b.correct(h)
+            for fld in (capi.F_XP, capi.F_XP1, capi.F_FP):
+                assert np.array_equal(a.download(fld), b.download(fld))
+            ea, eb = a.stopping_eloss(), b.stopping_eloss(reset=True)
+            assert np.array_equal(ea, eb) and ea.max() > 0.0 and np.count_nonzero(b.stopping_eloss()) == 0
+            for x in (ctx, a, b):
+                x.close()
+
+
 def test_parrep_event_detection_on_the_device():
     """Do_ChangeDetect (Appshell/MD_Method_ParRep_GPU.F90:1094-1167) from its device pieces: save the replicas, quench, compare with
     SimBoxIni (Do_Compare :1241-1297, host mirror msmpscu_b200.mdlib.Do_Compare as the checker), restore replicas and list."""
