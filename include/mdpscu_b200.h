@@ -184,7 +184,9 @@ int mdb_epc_correct(mdb_ctx *ctx, double h);
  *   mdb_active_region  ActivateRegion_DEV -> ActiveByCells1 (CommonGPU/MD_ActiveRegion_GPU.F90:1165-1353): seeds by atom type
  *                      (method bit 0, centpart[ngroup] > 0) and / or kinetic energy >= ekin_erg (bit 1); bit 2 = CP_KEEP_AR
  *                      (earlier activations are kept); the seeds' cells grown `extend` times over the 27-cell
- *                      neighbourhood; atoms of marked cells become active.  Needs the cell ids of a built list.  Inactive
+ *                      neighbourhood; atoms of marked cells become active.  bit 3 = CP_BYNB_AR: ActiveByNeigbors1 (:887-997)
+ *                      instead -- a seed marks the atoms of its neighbour list, `extend` times, marked atoms become active.
+ *                      Needs the cell ids / the list of a built list.  Inactive
  *                      atoms get no force and do not move; cells without active atoms are skipped by the next list build
  *                      (NAAC, MD_NeighborsList_GPU.F90:981-982).  Returns the number of active atoms.
  *   mdb_active_all     Active_All_ActiveRegion_DEV (on != 0) / DeActive_All_ActiveRegion_DEV (on == 0), :242-425

@@ -362,9 +362,9 @@ class Context:
         return rc, hh.value, tt.value
 
     # ---- cascade physics (csrc/mdb_cascade.cu)
-    def active_region(self, centpart=None, ekin_erg=None, extend=1, keep=False):
-        """ActivateRegion_DEV by cells; returns the number of active atoms"""
-        method = (1 if centpart is not None else 0) | (2 if ekin_erg is not None else 0) | (4 if keep else 0)
+    def active_region(self, centpart=None, ekin_erg=None, extend=1, keep=False, by_neighbours=False):
+        """ActivateRegion_DEV by cells (or through the neighbour list, CP_BYNB_AR); returns the number of active atoms"""
+        method = (1 if centpart is not None else 0) | (2 if ekin_erg is not None else 0) | (4 if keep else 0) | (8 if by_neighbours else 0)
         cp = i32(centpart) if centpart is not None else None
         return self._chk(self.lib.mdb_active_region(self.h, method, ip(cp) if cp is not None else None,
                                                     float(ekin_erg or 0.0), int(extend)))

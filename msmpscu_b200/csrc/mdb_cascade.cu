@@ -76,9 +76,55 @@ __global__ void k_ar_activate(int n, const int *__restrict__ ic, const int *__re
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(nact, __popc(b));
 }
 
+// ---- activation through the neighbour list (ActiveByNeigbors0/1 :887-997, CP_BYNB_AR)
+// per-atom seeds: the two criteria of k_ar_seed_cells on atoms instead of cells (CreateSeedByType_Kernel / CreateSeedByEkin_Kernel)
+__global__ void k_ar_seed_atoms(int n, const int *__restrict__ ityp, const int *__restrict__ statu, const double *__restrict__ xp1,
+                                MassParams M, int use_type, const int *__restrict__ cent, int use_ekin, double e0, int *__restrict__ seed)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int sd = 0;
+    if ((statu[i] & ST_OUTOFBOX) != ST_OUTOFBOX) {
+        const int t = ityp[i] - 1;
+        bool s1 = use_type && cent[t] > 0;
+        if (use_ekin) {
+            const double vx = xp1[i], vy = xp1[i + (size_t)n], vz = xp1[i + 2 * (size_t)n];
+            s1 = s1 || 0.5 * M.cm[t] * (vx * vx + vy * vy + vz * vz) >= e0;
+        }
+        sd = s1 ? 1 : 0;
+    }
+    seed[i] = sd;
+}
+// MarkSeedNeighbore_Kernel :783-842 : a seed marks itself and the atoms of its list (the reference counts, MARK(J) = MARK(J) + 1,
+// unsynchronised; only MARK > 0 is ever read)
+__global__ void k_ar_mark_neighbours(int n, const int *__restrict__ seed, const int *__restrict__ kvois, const int *__restrict__ indi,
+                                     int *__restrict__ mark)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || seed[i] <= 0) return;
+    mark[i] = 1;
+    const int kv = kvois[i];
+    for (int w = 0; w < kv; w++) mark[indi[i + (size_t)w * n] - 1] = 1;
+}
+// Active_Marked_Kernel :428-471 (+ the count of active atoms)
+__global__ void k_ar_activate_marked(int n, const int *__restrict__ mark, int *__restrict__ statu, int *__restrict__ nact)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int a = 0;
+    if (i < n) {
+        int st = statu[i];
+        if (mark[i] > 0) { st |= ST_ACTIVE; statu[i] = st; }
+        a = (st & ST_ACTIVE) == ST_ACTIVE;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, a);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(nact, __popc(b));
+}
+
 // ActivateRegion_DEV(SimBox, CtrlParam) for the cell method.  method: bit 0 = seeds by atom type (AR_CENTPART), bit 1 = seeds
-// by kinetic energy >= ekin_erg (AR_EKIN, already in erg), bit 2 = KEEP (do not clear the active bits first; CP_KEEP_AR).
-// Uses the cell ids of the last rebuild (INC).  Returns the number of active atoms (>= 0) or < 0.
+// by kinetic energy >= ekin_erg (AR_EKIN, already in erg), bit 2 = KEEP (do not clear the active bits first; CP_KEEP_AR), bit 3 =
+// grow through the neighbour list instead of the cells (CP_BYNB_AR, ActiveByNeigbors0/1 :887-997: a seed marks the atoms of its
+// list, `extend` times; needs INDI, which the tiled path produces on demand).
+// Uses the cell ids / the list of the last rebuild.  Returns the number of active atoms (>= 0) or < 0.
 extern "C" int mdb_active_region(mdb_ctx *c, int method, const int *centpart, double ekin_erg, int extend)
 {
     if (!c) return MDB_ERR_ARG;
@@ -89,6 +135,33 @@ extern "C" int mdb_active_region(mdb_ctx *c, int method, const int *centpart, do
     CUDA_TRY(c, cudaSetDevice(c->dev));
     const int n = c->n, nc = c->nc, nb = cdiv(n, 256);
     cudaStream_t st = c->stream;
+    if (method & 8) {
+        int rc = mdb_indi_ensure(c);
+        if (rc < 0) return rc;
+        int *w = reinterpret_cast<int *>(mdb_scratch(c, sizeof(int) * (2 * (size_t)n + MDB_MXGROUP + 1)));
+        if (!w) return mdb_fail(c, MDB_ERR_CUDA, "mdb_active_region: out of device memory");
+        int *seed = w, *mark = w + n, *cent = w + 2 * (size_t)n, *nact = cent + MDB_MXGROUP;
+        CUDA_TRY(c, cudaMemsetAsync(cent, 0, sizeof(int) * (MDB_MXGROUP + 1), st));
+        if (method & 1) CUDA_TRY(c, cudaMemcpyAsync(cent, centpart, sizeof(int) * c->ng, cudaMemcpyHostToDevice, st));
+        ProfScope ps(c, MDB_K_OTHER, 3 + extend);
+        if (!(method & 4)) k_ar_deactive_all<<<nb, 256, 0, st>>>(n, c->statu);   // ActiveByNeigbors1 :984-990
+        if (method & 3) {
+            k_ar_seed_atoms<<<nb, 256, 0, st>>>(n, c->ityp, c->statu, c->xp1, c->mass, method & 1, cent, (method & 2) ? 1 : 0, ekin_erg, seed);
+            CUDA_TRY(c, cudaMemcpyAsync(mark, seed, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));   // DevMakeCopy :932
+            for (int l = 0; l < extend; l++) {                                    // :935-951
+                k_ar_mark_neighbours<<<nb, 256, 0, st>>>(n, seed, c->kvois, c->indi, mark);
+                CUDA_TRY(c, cudaMemcpyAsync(seed, mark, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+            }
+            k_ar_activate_marked<<<nb, 256, 0, st>>>(n, mark, c->statu, nact);
+        } else {
+            CUDA_TRY(c, cudaMemsetAsync(mark, 0, sizeof(int) * (size_t)n, st));
+            k_ar_activate_marked<<<nb, 256, 0, st>>>(n, mark, c->statu, nact);   // (counts what KEEP left active)
+        }
+        CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + CNT_SCRATCH, nact, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        return c->h_counters[CNT_SCRATCH];
+    }
     // (work space from the context's grow-only scratch buffer: stream-ordered pool allocations were seen to stall for up to
     // seconds after another context of the process had released a few GB)
     int *work = reinterpret_cast<int *>(mdb_scratch(c, sizeof(int) * (2 * (size_t)nc + MDB_MXGROUP + 1)));

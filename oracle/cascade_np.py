@@ -132,3 +132,31 @@ def stopping_force_lden(fp, xp1, ityp, statu, cm, etab, stab, kpair, enable, kvo
         f[i, 2] -= ff * vz / v
         eloss[i] = ff * v * dt                                          # :1130
     return f, eloss
+
+
+def activate_region_by_neighbours(statu, ityp, xp1, cm, kvois, indi, centpart=None, ekin_erg=None, extend=1, keep=False):
+    """ActivateRegion_DEV -> ActiveByNeigbors1 -> ActiveByNeigbors0 (CP_BYNB_AR), CommonGPU/MD_ActiveRegion_GPU.F90:887-997: the seeds
+    mark themselves and the atoms of their neighbour lists (MarkSeedNeighbore_Kernel :783-842), `extend` times with the marks as the
+    next seeds; marked atoms are activated (Active_Marked_Kernel :428-471).  All arrays in the list's atom order; indi (N, mx) 1-based."""
+    st = np.array(statu, dtype=np.int64)
+    n = st.size
+    if not keep:
+        st &= ~STATU_ACTIVE                                            # :984-990
+    if centpart is None and ekin_erg is None:                          # :909-910
+        return st.astype(np.int32)
+    inbox = (st & STATU_OUTOFBOX) != STATU_OUTOFBOX
+    seed = np.zeros(n, dtype=np.int64)
+    if centpart is not None:
+        seed += (inbox & (np.asarray(centpart)[np.asarray(ityp) - 1] > 0)).astype(np.int64)
+    if ekin_erg is not None:
+        ek = 0.5 * np.asarray(cm)[np.asarray(ityp) - 1] * np.sum(np.asarray(xp1) ** 2, axis=1)
+        seed += (inbox & (ek >= ekin_erg)).astype(np.int64)
+    mark = seed.copy()                                                 # DevMakeCopy :932
+    for _ in range(int(extend)):                                       # :935-951
+        for i in np.nonzero(seed > 0)[0]:
+            mark[i] = 1
+            for w in range(int(kvois[i])):
+                mark[int(indi[i, w]) - 1] += 1
+        seed = mark.copy()
+    st[mark > 0] |= STATU_ACTIVE
+    return st.astype(np.int32)

@@ -92,6 +92,31 @@ def test_active_region_by_type_and_keep(oracle):
     ctx.close()
 
 
+@pytest.mark.parametrize("path", [capi.FORCE_PATH_GENERIC, capi.FORCE_PATH_TILED])
+def test_active_region_through_the_neighbour_list(path):
+    """CP_BYNB_AR (ActiveByNeigbors0/1): seeds by kinetic energy and by type grown through the list, with KEEP"""
+    c = util.neb_case("react")
+    n = c.xp.shape[0]
+    ctx = util.make_ctx(c, build=False, force_path=path)
+    ctx.nlist_build()
+    ctx.pka_insert(137, 500.0 * EV, [1.0, 3.0, 5.0])
+    cell = lambda f: ctx.download(f, capi.ORDER_CELL)
+    kv, indi = ctx.nlist_copyout(capi.ORDER_CELL)
+    for extend in (0, 1, 2):
+        nact = ctx.active_region(ekin_erg=50.0 * EV, extend=extend, by_neighbours=True)
+        want = CN.activate_region_by_neighbours(np.ones(n, np.int32), cell(capi.F_ITYP), cell(capi.F_XP1), c.mass, kv, indi.T,
+                                                ekin_erg=50.0 * EV, extend=extend)
+        assert np.array_equal(cell(capi.F_STATU), want) and nact == int(np.count_nonzero(want & 1))
+        assert (nact == 1) if extend == 0 else (1 < nact < n)
+    # by type (the H atom), kept on top of the region of the fast atom
+    st0 = cell(capi.F_STATU)
+    cent = [0] * len(c.mass); cent[-1] = 1
+    nact2 = ctx.active_region(centpart=cent, extend=1, keep=True, by_neighbours=True)
+    want = CN.activate_region_by_neighbours(st0, cell(capi.F_ITYP), cell(capi.F_XP1), c.mass, kv, indi.T, centpart=cent, extend=1, keep=True)
+    assert np.array_equal(cell(capi.F_STATU), want) and nact2 == int(np.count_nonzero(want & 1)) and nact2 > nact
+    ctx.close()
+
+
 def _stop_tables(ng):
     """a smooth synthetic E-S table (erg, erg cm^2): the reference reads such tables from its stopping libraries"""
     ne = 200
