@@ -725,7 +725,7 @@ def dd_cascade(args, c, ctx, dom, stream, itime, blocks, barrier, world):
     ekev = float(args.dd_pka_kev)
     ctx.pka_insert(ipka, ekev * 1000.0 * CP_EVERG, [1.0, 3.0, 5.0])
     etab = np.linspace(20.0, 2.0e5, 20001) * CP_EVERG                                 # uniform grid as the reference's tables; &EMIN 20 eV
-    k_ls = 6.93e-16 * CP_EVERG                                                       # erg cm^2 per sqrt(eV): S_e(10 keV) = 6.9e-14 eV cm^2, ~45 eV/A in W (Lindhard-Scharff order of magnitude)
+    k_ls = 3.25e-16 * CP_EVERG                                                       # erg cm^2 per sqrt(eV): the W->W column of the reference's examples/Cascade_Test/Stopping_table.stp (LS_Z85) is 1.0278e-17 keV cm^2 x sqrt(E / keV)
     stab = (k_ls * np.sqrt(etab / CP_EVERG)).reshape(-1, 1)
     mden = n / float(np.prod(c.zl))
     ctx.stopping_set(etab, stab, np.array([[1]]), [1], [mden])

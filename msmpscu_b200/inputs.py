@@ -344,3 +344,62 @@ def write_thermal_quantities(fname, itime, time_ps, isect, box):
             fh.write((" " * 20 + "".join(_THERMAL_TITLES)).rstrip() + "\n")
         fh.write(line + "\n")
     return line
+
+
+def read_stopping_table(path):
+    """An external stopping-cross-section table in the reference's `&MDPSCU_STPTAB.stp` format (written by Export_STPTable /
+    Stop_Srim, read by Load_STPTable, Common/MD_TypeDef_StpRangTable.F90:662-825; e.g. examples/Cascade_Test/Stopping_table.stp):
+    `&NUMTABLE nt`, `&NUMPOINT ne`, one line `&A->B with COL# k Z1 M1 Z2 M2` per table, then rows `E S_2 ... S_{nt+1}` with the
+    energy in keV and the cross sections in keV cm^2.  Returns (E [erg], {"A->B": S [erg cm^2]}, {"A->B": (Z1, M1, Z2, M2)})."""
+    kev = 1000.0 * CP_EVERG
+    cols, ids = {}, {}
+    rows = []
+    with open(path) as f:
+        first = True
+        for raw in f:
+            t = raw.strip()
+            if not t or t.startswith("!"):
+                continue
+            if t.startswith("&"):
+                key = t.split()[0].upper()
+                if first:
+                    if key != "&MDPSCU_STPTAB.STP":
+                        raise ValueError("unknown format for external stop-table: the header keyword should be &MDPSCU_STPTAB.stp")
+                    first = False
+                    continue
+                if key in ("&NUMTABLE", "&NUMPOINT"):
+                    continue
+                v = [float(x.replace("D", "E").replace("d", "e")) for x in re.findall(r"[-+]?\d+\.?\d*(?:[eEdD][-+]?\d+)?", t[len(t.split()[0]):])]
+                if "->" in key and len(v) >= 5:                       # (Extract_Numb(STR, 5, ...): COL, Z1, M1, Z2, M2)
+                    cols[key[1:]] = int(v[0])
+                    ids[key[1:]] = tuple(v[1:5])
+                continue
+            first = False
+            rows.append([float(x) for x in t.split()])
+    a = np.asarray(rows, dtype=np.float64)
+    if a.ndim != 2 or not cols:
+        raise ValueError("no stopping tables in %s" % path)
+    return a[:, 0] * kev, {k: a[:, c - 1] * kev for k, c in cols.items()}, ids
+
+
+def stopping_tables_for(path, symbols, emin_ev, emax_ev, ntab):
+    """What Import_STPTable (Common/MD_TypeDef_StpRangTable.F90:830-907) hands to Initialize_STMOD_DEV for a box whose groups carry
+    the element `symbols`: ETAB(0:ntab) uniform between &EMIN and &EMAX, STAB(:, K) per pair table, KPAIR(NG, NG) 1-based -- the
+    arguments of mdb_stopping_set.  (The reference re-grids with its spline library; here linearly, the tables are smooth.)"""
+    e, tabs, _ = read_stopping_table(path)
+    ng = len(symbols)
+    emin, emax = emin_ev * CP_EVERG, emax_ev * CP_EVERG
+    if emax > e.max() or emin < e.min():
+        raise ValueError("&EMIN / &EMAX outside the energy range of the stopping data")
+    etab = np.linspace(emin, emax, ntab + 1)
+    keys, kpair = [], np.zeros((ng, ng), dtype=np.int32)
+    for i in range(ng):
+        for j in range(ng):
+            k = ("%s->%s" % (symbols[i], symbols[j])).upper()
+            if k not in tabs:
+                raise ValueError("cannot find stopping cross section for " + k)
+            if k not in keys:
+                keys.append(k)
+            kpair[i, j] = keys.index(k) + 1
+    stab = np.stack([np.interp(etab, e, tabs[k]) for k in keys], axis=1)
+    return etab, stab, kpair

@@ -164,6 +164,32 @@ def test_step_size_and_list_period_schedules_are_read(tmp_path):
     assert (d.IHDUP, d.NB_UPTABMI, d.NB_UPTABMX, d.NB_DBITAB) == (0, 10, 10, 100000) and d.DMX == 0.1e-8   # :886-890, :940-942
 
 
+def test_external_stopping_table_file_is_read(tmp_path):
+    """the `&MDPSCU_STPTAB.stp` format of the reference's stopping tables (Load_STPTable / Import_STPTable): units keV and keV cm^2,
+    column directives per pair, re-gridding to ETAB / STAB / KPAIR of mdb_stopping_set"""
+    from msmpscu_b200 import inputs
+    e = np.linspace(0.02, 200.0, 101)
+    k = {"W->W": 1.0278e-17, "W->HE": 1.7337e-18, "HE->W": 3.2238e-18, "HE->HE": 8.599e-19}   # keV cm^2 per sqrt(keV), as the shipped table
+    p = tmp_path / "tab.stp"
+    with open(p, "w") as f:
+        f.write("&MDPSCU_STPTAB.stp\n! energy in the unit of keV\n! stoping in the unit of keV*cm^2\n&NUMTABLE       4\n&NUMPOINT     101\n")
+        f.write("&W->W       with COL#    2     74.00    183.84     74.00    183.84\n&W->He      with COL#    3     74.00    183.84      2.00      4.00\n")
+        f.write("&He->W      with COL#    4      2.00      4.00     74.00    183.84\n&He->He     with COL#    5      2.00      4.00      2.00      4.00\n")
+        f.write("!--- ENERGY        W->W            W->He           He->W           He->He\n")
+        for x in e:
+            f.write("  %.8E" % x + "".join("  %.8E" % (k[q] * np.sqrt(x)) for q in ("W->W", "W->HE", "HE->W", "HE->HE")) + "\n")
+    ee, tabs, ids = inputs.read_stopping_table(str(p))
+    kev = 1000.0 * 1.60219e-12
+    assert set(tabs) == set(k) and ids["W->HE"] == (74.0, 183.84, 2.0, 4.0)
+    assert np.allclose(ee, e * kev, rtol=1e-8) and np.allclose(tabs["HE->W"], k["HE->W"] * np.sqrt(e) * kev, rtol=1e-8)
+    etab, stab, kpair = inputs.stopping_tables_for(str(p), ["W", "He"], 20.0, 200000.0, 2000)
+    assert etab.shape == (2001,) and stab.shape == (2001, 4) and np.array_equal(kpair, [[1, 2], [3, 4]])
+    assert abs(etab[0] - 20.0 * 1.60219e-12) < 1e-24 and abs(etab[-1] - 2.0e5 * 1.60219e-12) < 1e-18
+    assert np.allclose(stab[:, 0], k["W->W"] * np.sqrt(etab / kev) * kev, rtol=2e-3)     # (linear re-gridding of a sqrt law on 101 points)
+    with pytest.raises(ValueError):
+        inputs.stopping_tables_for(str(p), ["W", "H"], 20.0, 1000.0, 10)
+
+
 def _thermal_loop_restatement(XP1, STATU, ITYP, CM, PROP, BOXSHAPE, ZL, VTENSOR, EPOT, EKIN):
     """Cal_thermal_quantities_SimMDBox (Common/MD_TypeDef_SimBox.F90:5048-5170) as plain loops, statement by statement:
     the checker of the vectorised host mirror in msmpscu_b200/mdlib.py."""
