@@ -544,3 +544,96 @@ contains
       if(mdb_state_restore(m_CTX) .lt. 0) stop "MDPSCU Error: mdb_state_restore failed"
   end subroutine
 end module MD_Method_ParRep_GPU_EventDetect
+
+module MD_ST_Coupling_GPU                ! replaces MDLIB/sor/LocalTempCtrlMeths/Stopping/MD_ST_Coupling_GPU.F90 (:317-427, :1265-1291)
+  use MD_CONSTANTS
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MD_TYPEDEF_StopRange_Table
+  use MDB_C_BINDING
+  implicit none
+  type(MDSTPTable), pointer, private::m_pSTPTable => null()
+contains
+  subroutine Initialize_STMOD_DEV(SimBox, CtrlParam, STPTable)                                   ! :334-357
+    type(SimMDBox),  intent(in)::SimBox
+    type(SimMDCtrl), intent(in)::CtrlParam
+    type(MDSTPTable),intent(in), target::STPTable
+      m_pSTPTable => STPTable
+      call Reset_STMOD_DEV(SimBox, CtrlParam)
+  end subroutine
+  subroutine Reset_STMOD_DEV(SimBox, CtrlParam)                                                  ! :361-427
+    type(SimMDBox)  ::SimBox
+    type(SimMDCtrl) ::CtrlParam
+    integer(c_int)::ENABLE(MDB_MXGROUP), LOCAL
+    real(c_double)::MDEN(MDB_MXGROUP)
+    integer::I
+      ENABLE = 0; MDEN = 0; LOCAL = 0
+      do I=1, SimBox%NGROUP
+         ENABLE(I) = iand(CtrlParam%LT_CTRL(I)%METH, CP_TICTRL_METH_ST)
+      end do
+      if(CtrlParam%ST_CTRL%MDEN .gt. 0.000001D0) then                                            ! :377-379: the given density
+         MDEN(1:SimBox%NGROUP) = CtrlParam%ST_CTRL%MDEN*dble(SimBox%NA(1:SimBox%NGROUP))/dble(SimBox%NPRT)
+      else if(dabs(CtrlParam%ST_CTRL%MDEN) .le. 0.00001D0) then                                  ! :381-386: atoms of the box / box volume
+         MDEN(1:SimBox%NGROUP) = dble(SimBox%NA(1:SimBox%NGROUP))/(SimBox%ZL(1)*SimBox%ZL(2)*SimBox%ZL(3))
+      else                                                                                       ! :395-397: mp_STMOD_L
+         LOCAL = 1
+      end if
+      ! ETAB / STAB / KPAIR exactly as type(MDSTPTable) holds them (E(0:NTAB), STPWR(0:NTAB,NK), KPAIR(NG,NG))
+      if(mdb_stopping_set(m_CTX, size(m_pSTPTable%E), size(m_pSTPTable%STPWR, dim=2), m_pSTPTable%E, m_pSTPTable%STPWR, &
+                          m_pSTPTable%KPAIR, ENABLE, MDEN) .lt. 0) stop "MDPSCU Error: mdb_stopping_set failed"
+      if(mdb_stopping_options(m_CTX, LOCAL, CtrlParam%ST_CTRL%SaveEloss) .lt. 0) stop "MDPSCU Error: mdb_stopping_options failed"
+  end subroutine
+  subroutine Do_STMOD_DEV(SimBox, CtrlParam)                                                     ! :1265-1291
+    type(SimMDBox), dimension(:)::SimBox
+    type(SimMDCtrl)             ::CtrlParam
+      if(mdb_stopping_apply(m_CTX, CtrlParam%H) .lt. 0) stop "MDPSCU Error: mdb_stopping_apply failed"
+  end subroutine
+  subroutine CopyElossFrom_Devices_to_Host(hELOSS)                                               ! :1295-1312 (accumulated, original order, erg)
+    real(KINDDF), dimension(:)::hELOSS
+      if(mdb_stopping_eloss(m_CTX, hELOSS, 0) .lt. 0) stop "MDPSCU Error: mdb_stopping_eloss failed"
+  end subroutine
+  subroutine Clear_STMOD_DEV(SimBox)                                                             ! :317-330
+    type(SimMDBox), optional::SimBox
+    integer(c_int)::IDUM(1)
+    real(c_double)::DDUM(1)
+      if(mdb_stopping_set(m_CTX, 0, 0, DDUM, DDUM, IDUM, IDUM, DDUM) .lt. 0) stop "MDPSCU Error: mdb_stopping_set failed"
+  end subroutine
+end module MD_ST_Coupling_GPU
+
+module MD_ActiveRegion_GPU               ! replaces MDLIB/sor/CommonGPU/MD_ActiveRegion_GPU.F90 (:193-238, :283-424, :1329-1353)
+  use MD_CONSTANTS
+  use MD_TYPEDEF_SimMDBox
+  use MD_TYPEDEF_SimMDCtrl
+  use MDB_C_BINDING
+  implicit none
+contains
+  subroutine Initialize_ActiveRegion_DEV(SimBox, CtrlParam)                                      ! :193-215: nothing to allocate here
+    type(SimMDBox), dimension(:), intent(in) ::SimBox
+    type(SimMDCtrl),              intent(in) ::CtrlParam
+  end subroutine
+  subroutine ActivateRegion_DEV(SimBox, CtrlParam)                                               ! :1329-1353
+    type(SimMDBox), dimension(:) ::SimBox
+    type(SimMDCtrl)              ::CtrlParam
+    integer(c_int)::METHOD, NACT
+      if(iand(CtrlParam%AR_METHOD, CP_ENABLE_AR) .ne. CP_ENABLE_AR) return
+      METHOD = 0
+      if(iand(CtrlParam%AR_METHOD, CP_CENTPART_AR) .eq. CP_CENTPART_AR) METHOD = METHOD + 1
+      if(iand(CtrlParam%AR_METHOD, CP_EKIN_AR)     .eq. CP_EKIN_AR)     METHOD = METHOD + 2
+      if(iand(CtrlParam%AR_METHOD, CP_KEEP_AR)     .eq. CP_KEEP_AR)     METHOD = METHOD + 4
+      if(ibits(CtrlParam%AR_METHOD, CP_BYNBSETBIT_AR, 1) .gt. 0)        METHOD = METHOD + 8       ! ActiveByNeigbors1, else ActiveByCells1
+      NACT = mdb_active_region(m_CTX, METHOD, CtrlParam%AR_CENTPART, CtrlParam%AR_EKIN*CP_EVERG, CtrlParam%AR_Extend)
+      if(NACT .lt. 0) stop "MDPSCU Error: mdb_active_region failed"
+  end subroutine
+  subroutine Active_All_ActiveRegion_DEV(SimBox, CtrlParam)                                      ! :408-424
+    type(SimMDBox), dimension(:) ::SimBox
+    type(SimMDCtrl)              ::CtrlParam
+      if(mdb_active_all(m_CTX, 1) .lt. 0) stop "MDPSCU Error: mdb_active_all failed"
+  end subroutine
+  subroutine DeActive_All_ActiveRegion_DEV(SimBox, CtrlParam)                                    ! :314-330
+    type(SimMDBox), dimension(:) ::SimBox
+    type(SimMDCtrl)              ::CtrlParam
+      if(mdb_active_all(m_CTX, 0) .lt. 0) stop "MDPSCU Error: mdb_active_all failed"
+  end subroutine
+  subroutine Clear_ActiveRegion_DEV()                                                            ! :219-238
+  end subroutine
+end module MD_ActiveRegion_GPU

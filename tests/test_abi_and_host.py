@@ -366,5 +366,7 @@ def test_fortran_binding_covers_the_whole_header():
                  "CheckTimestep_DEV", "Do_EPCForce_DEV", "Do_ResetParam_DEV", "Initialize_GB_A_DEV", "Clear_Globle_Variables_DEV",
                  "CopyAllFrom_Devices_to_Host", "CopyAllFrom_Host_to_Devices", "Synchroniz_XP_on_Devices", "CopyIn_SimBoxA",
                  "CopyOut_SimBoxA", "Initialize_DEVICES", "Do_Steepest_Forsteps_DEV", "Do_CG_Forsteps_DEV", "DO_LBFGSB_FORSTEPS_DEV",
-                 "Do_DynDamp_Forsteps_DEV"):
+                 "Do_DynDamp_Forsteps_DEV", "Initialize_STMOD_DEV", "Reset_STMOD_DEV", "Do_STMOD_DEV", "Clear_STMOD_DEV",
+                 "Initialize_ActiveRegion_DEV", "ActivateRegion_DEV", "Active_All_ActiveRegion_DEV", "DeActive_All_ActiveRegion_DEV",
+                 "Do_ChangeDetect_DEV"):
         assert re.search(r"subroutine\s+%s\b" % proc, shims), "shim %s missing" % proc
