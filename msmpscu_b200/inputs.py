@@ -133,6 +133,17 @@ def read_ctrl_file(path, box, section=1):
                 c.RHOSCAL = v[2]
         elif k == "TEMPERATURE":
             temp = _numbers(s[12:])[0]
+        elif k in ("THERMALIZATION", "THERMAL"):                # MD_SimCtrlParam_GMD.F90:97-125 (PARREP reader :58-74 wants both numbers)
+            v = _numbers(s[len(k) + 1:])
+            if len(v) < 1:
+                raise ValueError("MDPSCU Error: the number of thermalization circle should be set")
+            c.IVTIME = int(v[0])
+            if c.IVTIME > 0 and len(v) < 2:
+                raise ValueError("MDPSCU Error: the timestep interval for thermalizing should be set")
+            if len(v) >= 2:
+                c.IVPAS = int(v[1])
+            if c.IVTIME > 0 and c.IVPAS == 0:
+                raise ValueError("MDPSCU Error: the interval for thermalizing cannot be zero")
         elif k == "E_P_COUPLE":
             epc = True
         elif k == "STEPSIZE":
@@ -190,7 +201,7 @@ def read_ctrl_file(path, box, section=1):
     c.RU = ru_lu * box.RR
     c.NB_RM = nb_fac * c.RU
     c.LT_CTRL = [TiCtrlParam(TI=temp, METH_EPC=1 if epc else 0) for _ in range(ng)]
-    c.TEMP = temp
+    c.TEMP = c.TI = temp
     return c
 
 

@@ -116,6 +116,11 @@ class SimMDCtrl:
     STRCUT_DRTol: float = 0.03           # &DRTOL: displacement that counts as an event (LU); default :202,996
     DAMPTIME0: int = 0
     DAMPTIME1: int = 0
+    # thermalisation schedule (Common/MD_TypeDef_SimCtrlParam.F90:89-91, defaults :918-920; &TEMPERATURE / &THERMALIZATION)
+    TI: float = 0.0                      # K
+    IVTIME0: int = 1
+    IVTIME: int = 0                      # number of thermalisations in one section
+    IVPAS: int = 50                      # steps between two thermalisations
 
 
 class MDPSCUError(RuntimeError):
@@ -514,6 +519,56 @@ def Do_ChangeDetect(dev, SimBoxIni, SimBox, CtrlParam, CtrlParamDamp=None, MASK=
     fb, ibt, ncb = dev.ctx.compare(SimBoxIni.XP, CtrlParam.STRCUT_DRTol * SimBoxIni.RR, mask=MASK, nbox=nb)
     dev.ctx.state_restore()
     return ibt, ncb, fb
+
+
+def Do_DePhase(dev, SimBoxIni, SimBox, CtrlParamDephase, CtrlParamDamp=None, MASK=None, ForceClass=gm_ForceClass, log=None):
+    """Do_DePhase (Appshell/MD_Method_ParRep_GPU.F90:959-1090): every replica starts from the quenched configuration SimBoxIni
+    (:996-998), the device box, tables and list are set up (:1001-1008), then (IVTIME+1)*IVPAS steps run with the velocities
+    redrawn at the first IVTIME multiples of IVPAS (Thermalizing_MC_DEV at TI, :1024-1042) -- predictor, list every NB_UPTAB
+    steps counted from ITIME = 1, force, corrector, no thermostat (:1045-1063).  The replicas are then quenched and compared
+    with SimBoxIni on the device (mdb_state_save / Do_Damp / mdb_compare / mdb_state_restore instead of the host SwapSimBox
+    copies, :1066-1076) and the ones that left the basin are dropped: the survivors are packed to the front of SimBox in
+    replica order (:1078-1086).  Returns (m_curReplicas, flag per replica); SimBox[0:m_curReplicas] hold the dephased states."""
+    c = CtrlParamDephase
+    boxes = SimBox if isinstance(SimBox, (list, tuple)) else [SimBox]
+    for b in boxes:                                     # Copy_SimMDBox(SimBoxIni, SimBox(IB))
+        b.ITYP = np.array(SimBoxIni.ITYP, dtype=np.int32)
+        b.XP = np.array(SimBoxIni.XP, dtype=np.float64)
+        b.XP1 = b.DIS = b.FP = b.EPOT = b.EKIN = b.STATU = None
+        b.allocate()
+        if getattr(SimBoxIni, "STATU", None) is not None:
+            b.STATU[:] = SimBoxIni.STATU
+    Initialize_Globle_Variables_DEV(dev, boxes, c)
+    Init_Forcetable_Dev(dev, boxes, c, ForceClass)
+    Initialize_NeighboreList_DEV(dev, boxes, c)
+    if Cal_NeighBoreList_DEV(dev, boxes, c) != 0:
+        raise MDPSCUError("Do_DePhase: neighbour list failed")
+    CalForce_ForceClass(dev, boxes, c, ForceClass)
+    ivnum = 0
+    for itime in range(1, (c.IVTIME + 1) * c.IVPAS + 1):
+        if (itime - 1) % c.IVPAS == 0:
+            if log is not None:                         # "temp. ... K at ... timsteps in DEPHAS" (:1030-1034)
+                log(itime, Cal_GlobalT_DEV(dev, boxes, c))
+            if ivnum < c.IVTIME:
+                Thermalizing_MC_DEV(dev, boxes, c, c.TI)
+                ivnum += 1
+        Predictor_DEV(dev, itime, boxes, c)
+        if itime % c.NB_UPTAB == 0:
+            Cal_NeighBoreList_DEV(dev, boxes, c)
+        CalForce_ForceClass(dev, boxes, c, ForceClass)
+        Correction_DEV(dev, itime, boxes, c)
+    _ibt, _ncb, fb = Do_ChangeDetect(dev, SimBoxIni, boxes, c, CtrlParamDamp or c, MASK, ForceClass)
+    fb = np.asarray(fb)
+    n = SimBoxIni.NPRT
+    fields = {name: dev.ctx.download(f, capi.ORDER_ORIGINAL) for name, f in
+              (("XP", capi.F_XP), ("XP1", capi.F_XP1), ("DIS", capi.F_DIS), ("FP", capi.F_FP))}
+    ibf0 = 0
+    for ib in range(len(boxes)):
+        if fb[ib] == 0:
+            for name, a in fields.items():
+                getattr(boxes[ibf0], name)[:] = a[ib * n:(ib + 1) * n]
+            ibf0 += 1
+    return ibf0, fb
 
 
 def Transition_Replicas(Flag, NPRT):

@@ -329,6 +329,11 @@ def test_ctrl_defaults_and_sections_follow_the_reference():
     one = inputs.read_ctrl_file(os.path.join(g, "gmd_CtrlFile300K.dat"), box)
     assert one.TEMP == secs[0].TEMP and one.NB_MXNBS == 256 and one.NB_UPTAB == 10
     assert one.STRCUT_DRTol == 0.03          # the file has no &DRTOL
+    # thermalisation schedule: defaults MD_TypeDef_SimCtrlParam.F90:918-920, &THERMALIZATION per MD_SimCtrlParam_GMD.F90:97-125
+    assert (d.IVTIME0, d.IVTIME, d.IVPAS) == (1, 0, 50)
+    assert [(s.IVTIME, s.IVPAS, s.TI) for s in secs] == [(0, 50, 0.0), (100, 100, 300.0), (0, 50, 0.0)]
+    par = inputs.read_ctrl_file(os.path.join(g, "parrep_CtrlFile300K.dat"), box)
+    assert (par.IVTIME, par.IVPAS, par.TI) == (10, 100, 300.0)
 
 
 def test_fortran_binding_covers_the_whole_header():

@@ -780,6 +780,87 @@ def test_parrep_cycle_through_the_mdlib_interface():
     dev.ctx.close()
 
 
+def test_parrep_dephase_through_the_mdlib_interface():
+    """Do_DePhase (Appshell/MD_Method_ParRep_GPU.F90:959-1090) through the reference's procedure names on the shipped PARREP_Test
+    inputs: three replicas start from the quenched configuration, are thermalised IVTIME times IVPAS steps apart and run
+    (IVTIME+1)*IVPAS steps, then quenched and compared with the start on the device; replicas that stayed in the basin are kept.
+    Checked: the schedule (a raw C-ABI replay of the same calls gives the same bits), the replicas decorrelate, none is dropped
+    at the file's &DRTOL, all are dropped when the tolerance is made smaller than the quench's own residual."""
+    from msmpscu_b200 import inputs, mdlib
+    g = util.GOLD
+    path = os.path.join(g, "W_2000_H1_EAM1_box.dat")
+    box = inputs.read_box_file(path)
+    ctl = inputs.read_ctrl_file(os.path.join(g, "parrep_CtrlFile300K.dat"), box)
+    assert (ctl.IVTIME, ctl.IVPAS, ctl.TI) == (10, 100, 300.0)       # &THERMALIZATION / &TEMPERATURE of the file
+    ctl.IVTIME, ctl.IVPAS = 2, 40                                     # a short schedule for the test
+    neb = np.load(os.path.join(g, "neb_gmd_react.npz"))
+    nrep = 3
+
+    def fresh():
+        b = inputs.read_box_file(path)
+        b.ITYP = neb["ityp"].astype(np.int32)
+        b.XP = neb["pos"] * b.RR
+        b.allocate()
+        return b
+    # SimBoxIni: the quenched start
+    dev = mdlib.DeviceState(0)
+    fc = mdlib.Register_ForceClass(box.PotType)
+    ini = fresh()
+    mdlib.Initialize_Globle_Variables_DEV(dev, [ini], ctl)
+    mdlib.Init_Forcetable_Dev(dev, [ini], ctl, fc)
+    mdlib.Initialize_NeighboreList_DEV(dev, [ini], ctl)
+    assert mdlib.Cal_NeighBoreList_DEV(dev, [ini], ctl) == 0
+    mdlib.CalForce_ForceClass(dev, [ini], ctl, fc)
+    assert mdlib.Do_Damp(dev, [ini], ctl, fc)[0] != 0
+    ini.XP = dev.ctx.download(capi.F_XP)
+    dev.ctx.close()
+
+    dev = mdlib.DeviceState(0)
+    boxes = [fresh() for _ in range(nrep)]
+    draw0 = mdlib._thermalize_draw[0]
+    temps = []
+    ncur, fb = mdlib.Do_DePhase(dev, ini, boxes, ctl, ForceClass=fc, log=lambda it, t: temps.append((it, t)))
+    assert [it for it, _ in temps] == [1, 41, 81]
+    assert temps[0][1] == 0.0 and 50.0 < temps[1][1] < 400.0 and 50.0 < temps[2][1] < 400.0   # TI redrawn, then equipartition
+    assert ncur == nrep and not np.any(fb)
+    assert not np.allclose(boxes[0].XP1, boxes[1].XP1) and np.abs(boxes[1].XP - boxes[2].XP).max() > 1.0e-3 * ini.RR
+    # the same calls through the raw C ABI
+    n = ini.NPRT
+    xp_dev = dev.ctx.download(capi.F_XP)
+    for ib in range(nrep):
+        assert np.array_equal(boxes[ib].XP, xp_dev[ib * n:(ib + 1) * n])
+    raw = mdlib.DeviceState(0)
+    rb = [fresh() for _ in range(nrep)]
+    for b in rb:
+        b.XP = ini.XP.copy()
+    mdlib.Initialize_Globle_Variables_DEV(raw, rb, ctl)
+    mdlib.Init_Forcetable_Dev(raw, rb, ctl, fc)
+    mdlib.Initialize_NeighboreList_DEV(raw, rb, ctl)
+    c = raw.ctx
+    assert c.nlist_build() == 0
+    c.force(capi.FORCE)
+    seed, k = int(ctl.SEED[0]), 0
+    for it in range(1, 121):
+        if (it - 1) % 40 == 0 and k < 2:
+            c.thermalize(300.0, seed, draw0 + k)
+            k += 1
+        c.predict(ctl.H)
+        if it % ctl.NB_UPTAB == 0:
+            c.nlist_build()
+        c.force(capi.FORCE)
+        c.correct(ctl.H)
+    assert np.array_equal(c.download(capi.F_XP), xp_dev)
+    assert np.array_equal(c.download(capi.F_XP1), dev.ctx.download(capi.F_XP1))
+    raw.ctx.close()
+    # a tolerance below what the quench leaves (it stops on an energy criterion): every replica counts as having left
+    ctl.STRCUT_DRTol = 1.0e-12
+    dev.ctx.close()
+    dev = mdlib.DeviceState(0)
+    ncur2, fb2 = mdlib.Do_DePhase(dev, ini, boxes, ctl, ForceClass=fc)
+    assert ncur2 == 0 and np.all(np.asarray(fb2) != 0)
+    dev.ctx.close()
+
+
 def test_slab_domain_single_rank_step_and_virial():
     """SlabDomain with one rank (no process group): its step is the same GMD step as mdb_run (For_One_Step,
     Appshell/MD_Method_GenericMD_GPU.F90:596-627) and force_virial returns the tensor of pCalPTensor
