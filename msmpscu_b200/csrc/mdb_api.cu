@@ -302,7 +302,7 @@ extern "C" int mdb_box_set(mdb_ctx *c, int nbox, int napb, const double boxlow[3
         ALLOC(fp, double, n3); ALLOC(fp_alt, double, n3);
         ALLOC(dis, double, n3); ALLOC(dis_alt, double, n3);
         ALLOC(epot, double, n); ALLOC(ekin, double, n);
-        ALLOC(ityp, int, n); ALLOC(ityp_alt, int, n);
+        ALLOC(ityp, int, n + 8); ALLOC(ityp_alt, int, n + 8); // +8: the tiled passes read ITYP in aligned int4 windows
         ALLOC(statu, int, n + 8); ALLOC(statu_alt, int, n + 8); // +8: 16-byte aligned TMA windows may overshoot
         ALLOC(gid, int, n); ALLOC(gid_alt, int, n); ALLOC(gidinv, int, n);
         ALLOC(ic, int, n); ALLOC(ic_alt, int, n);

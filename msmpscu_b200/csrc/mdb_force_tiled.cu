@@ -847,14 +847,57 @@ k_tile_pass(TileParams P, TilePassArgs A)
             // next tile's descriptor: in flight while this tile's copies land, first used in the next iteration
             nx = prefetch(v + gridDim.x);
             if (fits) {
-                if (MT) { // lane per halo cell: copy the types of its atoms
+                if (MT) {
+                    // Types of the halo atoms, one lane per halo cell: the cell's atoms are read as aligned int4 windows of ITYP
+                    // (a window may start up to 3 atoms before the cell and end up to 3 after it: ITYP is allocated with padding),
+                    // TYB windows in flight before the first value is stored.  A single warp under 23 busy consumer warps pays
+                    // about as much per instruction as per L2 round trip / 50, so both counts matter: walking the atoms one by one,
+                    // four loads in flight (the first version), took atoms-per-cell/4 round trips -- with the 74-atom cells of
+                    // the PARREP boxes the producer was the bottleneck of both passes (0.15 ms for 192 k atoms); a warp-wide
+                    // walk over the runs needs one round trip per tile but ~70 instructions per 128 atoms and was slower still.
+                    constexpr int TYB = 8;
                     const TileDesc &D = A.desc[tile];
                     unsigned char *styp = bp + o_typ;
                     const int nhc = D.nhc;
                     for (int hc = lane; hc < nhc; hc += 32) {
-                        const int cnt = D.cnt[hc], sl = D.slot[hc], gst = D.gst[hc];
-#pragma unroll 4
-                        for (int a = 0; a < cnt; a++) styp[sl + a] = (unsigned char)(A.ityp[gst + a] - 1);
+                        const int cnt = D.cnt[hc], gst = D.gst[hc];
+                        const int off = gst & 3, nw = cnt > 0 ? (off + cnt + 3) >> 2 : 0;
+                        const int4 *src = reinterpret_cast<const int4 *>(A.ityp) + (gst >> 2);
+                        unsigned char *dst = styp + (D.slot[hc] - off);   // element e of window w is atom 4w + e - off of the cell
+                        for (int w0 = 0; w0 < nw; w0 += TYB) {
+                            int4 ty[TYB];
+#pragma unroll
+                            for (int j = 0; j < TYB; j++) {
+                                ty[j] = make_int4(1, 1, 1, 1);
+                                if (w0 + j < nw)
+                                    asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];"
+                                                 : "=r"(ty[j].x), "=r"(ty[j].y), "=r"(ty[j].z), "=r"(ty[j].w) : "l"(src + w0 + j));
+                            }
+                            // every load of the batch is issued before the first value is used (the compiler otherwise converts
+                            // each value as soon as it arrives: one round trip per window)
+                            static_assert(TYB == 8, "the barriers below name 4 * TYB registers");
+#define TY4(j) "+r"(ty[j].x), "+r"(ty[j].y), "+r"(ty[j].z), "+r"(ty[j].w)
+                            asm volatile("" : TY4(0), TY4(1), TY4(2), TY4(3));
+                            asm volatile("" : TY4(4), TY4(5), TY4(6), TY4(7));
+#undef TY4
+                            const unsigned da = smem_u32(dst) + ((unsigned)w0 << 2);
+#pragma unroll
+                            for (int j = 0; j < TYB; j++) {
+                                const int rel = ((w0 + j) << 2) - off;   // first atom of the window; windows past the cell fail every test
+                                const int t0 = ty[j].x - 1, t1 = ty[j].y - 1, t2 = ty[j].z - 1, t3 = ty[j].w - 1;
+                                if (rel >= 0 && rel + 3 < cnt) {         // inside the cell: the common case
+                                    asm volatile("st.shared.u8 [%0], %1;\nst.shared.u8 [%0+1], %2;\nst.shared.u8 [%0+2], %3;\nst.shared.u8 [%0+3], %4;"
+                                                 :: "r"(da + 4u * j), "r"(t0), "r"(t1), "r"(t2), "r"(t3) : "memory");
+                                } else {                                 // first / last window of the cell: atom by atom
+                                    asm volatile("{\n.reg .pred q0, q1, q2, q3;\n.reg .u32 r1, r2, r3;\n"
+                                                 "add.u32 r1, %5, 1;\nadd.u32 r2, %5, 2;\nadd.u32 r3, %5, 3;\n"
+                                                 "setp.lt.u32 q0, %5, %6;\nsetp.lt.u32 q1, r1, %6;\nsetp.lt.u32 q2, r2, %6;\nsetp.lt.u32 q3, r3, %6;\n"
+                                                 "@q0 st.shared.u8 [%0], %1;\n@q1 st.shared.u8 [%0+1], %2;\n@q2 st.shared.u8 [%0+2], %3;\n"
+                                                 "@q3 st.shared.u8 [%0+3], %4;\n}\n"
+                                                 :: "r"(da + 4u * j), "r"(t0), "r"(t1), "r"(t2), "r"(t3), "r"((unsigned)rel), "r"((unsigned)cnt) : "memory");
+                                }
+                            }
+                        }
                     }
                 }
             } else {
