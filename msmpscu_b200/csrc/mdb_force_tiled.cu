@@ -291,27 +291,32 @@ k_tile_nlist(TileParams P, TileListArgs A)
     // cell) needs no capacity of its own; only the sum can overflow, and that is checked after both are done.  Warp 0 then
     // moves warp 1's block down next to its own and does the class partition and the write-out.
     // (One warp per cell left 14 warps per SM: 63 % of the issue slots used.)
+    // A CTA is launched with `nwarps / 2` warp pairs for tiles of up to wmax cells: where cells hold more than 32 atoms and the
+    // tile is narrow (3 x 3 x 3-cell PARREP boxes: one 74-atom cell per tile), `ppc` pairs share a cell and take its atoms in
+    // blocks of 32 in turn, each pair with a column block of its own.
     const int wt = nhx - 2;
-    const int cw = warp >> 1, half = warp & 1;
+    const int ppc = max((nwarps >> 1) / wt, 1);
+    const int pid = warp >> 1, half = warp & 1;
+    const int cw = pid / ppc, blk = pid - cw * ppc;
     if (cw >= wt) return;
     const int myhc = 4 * nhx + cw + 1;             // centre row (hy = hz = 1), cell hx = cw + 1
     const int ccnt = H.cnt[myhc];
     if (ccnt <= 0) return;                         // :1018
     const int cgst = H.gst[myhc], csl = H.slot[myhc];
     if (A.naac[H.cid[myhc]] <= 0) {                // cells without ACTIVE atoms are skipped (:981-982): empty lists
-        if (!half)
+        if (!half && blk == 0)
             for (int a = lane; a < ccnt; a += 32) { A.kvois[cgst + a] = 0; A.ncls[cgst + a] = 0; A.ncls[cgst + a + P.npad] = 0; }
         return;
     }
     const float rm1 = A.rm2[0], rc0 = A.rc2[0], rc1 = A.rc2[1];
-    unsigned short *col0 = lists + (size_t)cw * A.lcap * 32 + lane;    // entry k of this lane at col0[k * 32]
+    unsigned short *col0 = lists + (size_t)pid * A.lcap * 32 + lane;   // entry k of this lane at col0[k * 32]
     unsigned short *col = col0;
     const int lcap = A.lcap;
     const unsigned col_a = (unsigned)__cvta_generic_to_shared(col0) + (half ? (unsigned)(lcap - 1) * 64u : 0u); // first entry of this warp
     const int step = half ? -64 : 64;
     const int r_lo = half ? 4 : 0, r_hi = half ? 9 : 4;
 
-    for (int ab = 0; ab < ccnt; ab += 32) {
+    for (int ab = blk * 32; ab < ccnt; ab += 32 * ppc) {
         const bool valid = ab + lane < ccnt;
         const int ia = cgst + ab + (valid ? lane : 0);
         const int myslot = csl + ab + (valid ? lane : 0);
@@ -385,11 +390,11 @@ k_tile_nlist(TileParams P, TileListArgs A)
         }
         int nn = half ? (int)((col_a - pa) >> 6) : (int)((pa - col_a) >> 6);
         if (!valid) { nn = 0; nover = 0; }
-        if (half) s_half1[cw][lane] = (unsigned short)(min(nn, 1023) | (min(nover, 63) << 10));
-        pair_barrier(cw);                              // warp 1's entries and counts are visible to warp 0
-        if (half) { pair_barrier(cw); continue; }      // ... and warp 1 waits until warp 0 is done with the columns
+        if (half) s_half1[pid][lane] = (unsigned short)(min(nn, 1023) | (min(nover, 63) << 10));
+        pair_barrier(pid);                             // warp 1's entries and counts are visible to warp 0
+        if (half) { pair_barrier(pid); continue; }     // ... and warp 1 waits until warp 0 is done with the columns
         {
-            const int h1 = s_half1[cw][lane];
+            const int h1 = s_half1[pid][lane];
             int n1 = h1 & 1023;
             nover += h1 >> 10;
             if (nn + n1 > lcap) { nover += nn + n1 - lcap; n1 = lcap - nn; }   // the two ends met: the build is discarded
@@ -444,7 +449,7 @@ k_tile_nlist(TileParams P, TileListArgs A)
             }
         }
         }
-        pair_barrier(cw);
+        pair_barrier(pid);
     }
 }
 
@@ -1310,24 +1315,40 @@ int mdb_tiled_plan(mdb_ctx *c)
         const double dens = (double)c->n / ((double)c->nbox * c->box.size[0] * c->box.size[1] * c->box.size[2]);
         const int expect = (int)(4.18879 * rmmax * rmmax * rmmax * dens);
         S.wmax = best_w;
-        S.lcap = std::min(c->mxkvois, ((int)(1.45 * expect) + 24 + 7) & ~7);
-        S.smem_list = sizeof(float4) * 2 * (size_t)((S.hcap + 2) / 2) + sizeof(unsigned short) * 32 * (size_t)S.lcap * S.wmax;
-        while (S.smem_list > (size_t)SMEM_BUDGET - 4096 && S.lcap > 32) {
-            S.lcap -= 8;
-            S.smem_list = sizeof(float4) * 2 * (size_t)((S.hcap + 2) / 2) + sizeof(unsigned short) * 32 * (size_t)S.lcap * S.wmax;
-        }
-        if (S.smem_list > (size_t)SMEM_BUDGET - 4096) return MDB_OK;
         // two CTAs of the list kernel share an SM when 2 x (dynamic + ~3.7 KB static + 1 KB reserved) <= 228 KB; when a
         // slightly shorter column (never below expected + 25 % + 16) gets there, take it: it doubles the resident warps
         const size_t two_cta = (233472 / 2) - 1024 - 3712 - 512;
         const size_t halo_b = sizeof(float4) * 2 * (size_t)((S.hcap + 2) / 2);
-        if (S.smem_list > two_cta && halo_b < two_cta) {
-            const int fit = (int)((two_cta - halo_b) / (sizeof(unsigned short) * 32 * (size_t)S.wmax)) & ~7;
-            if (fit >= (((int)(1.25 * expect) + 16 + 7) & ~7)) {
-                S.lcap = std::min(S.lcap, fit);
-                S.smem_list = halo_b + sizeof(unsigned short) * 32 * (size_t)S.lcap * S.wmax;
+        auto size_for = [&](int pairs, int &lcap, size_t &bytes) -> bool { // false: does not fit at all
+            lcap = std::min(c->mxkvois, ((int)(1.45 * expect) + 24 + 7) & ~7);
+            bytes = halo_b + sizeof(unsigned short) * 32 * (size_t)lcap * pairs;
+            while (bytes > (size_t)SMEM_BUDGET - 4096 && lcap > 32) {
+                lcap -= 8;
+                bytes = halo_b + sizeof(unsigned short) * 32 * (size_t)lcap * pairs;
             }
+            if (bytes > (size_t)SMEM_BUDGET - 4096) return false;
+            if (bytes > two_cta && halo_b < two_cta) {
+                const int fit = (int)((two_cta - halo_b) / (sizeof(unsigned short) * 32 * (size_t)pairs)) & ~7;
+                if (fit >= (((int)(1.25 * expect) + 16 + 7) & ~7)) {
+                    lcap = std::min(lcap, fit);
+                    bytes = halo_b + sizeof(unsigned short) * 32 * (size_t)lcap * pairs;
+                }
+            }
+            return true;
+        };
+        // warp pairs of a list CTA: one per cell of the widest tile, times the 32-atom blocks of a cell when the tile is narrow
+        // (k_tile_nlist deals a cell's blocks to the pairs that share it).  A pair costs a column block of lcap rows: extra pairs
+        // are taken only while two CTAs still share an SM with columns of the full expected length + 45 %.
+        const int lcap_full = std::min(c->mxkvois, ((int)(1.45 * expect) + 24 + 7) & ~7);
+        int ppc = std::max(1, std::min(TILE_MAX_W / best_w, (int)(1.3 * rho_cell + 31.0) / 32));
+        for (;; ppc--) {
+            if (!size_for(best_w * ppc, S.lcap, S.smem_list)) {
+                if (ppc > 1) continue;
+                return MDB_OK;
+            }
+            if (ppc == 1 || (S.smem_list <= two_cta && S.lcap >= std::min(lcap_full, ((int)(1.25 * expect) + 16 + 7) & ~7))) break;
         }
+        S.lpairs = best_w * ppc;
     }
     for (int p = 0; p < 2; p++) S.smem_pass[p] = TP_HDR_BYTES + tp_tab_bytes(S.ktab[p]) + S.nbuf * tp_buf_bytes(S.hcap, S.ocap, G, mt);
     S.bank_order = S.bank_order_opt == 1 || (S.bank_order_opt < 0 && std::min(c->ncell[0], std::min(c->ncell[1], c->ncell[2])) >= 12);
@@ -1370,7 +1391,7 @@ static int launch_list(mdb_ctx *c)
     // descriptors: of this rank's tiles only in a decomposed run (cell counts of other slabs are not kept current there)
     if (tile_hi > tile_lo) {
         k_tile_desc<<<tile_hi - tile_lo, NL_THREADS, 0, c->stream>>>(S.P, c->nac, c->ia1th, (TileDesc *)S.desc, c->counters, tile_lo);
-        kern<<<tile_hi - tile_lo, 64 * S.wmax, S.smem_list, c->stream>>>(S.P, A);
+        kern<<<tile_hi - tile_lo, 64 * S.lpairs, S.smem_list, c->stream>>>(S.P, A);
         if (S.bank_order) {
             // the atoms of this rank's tiles: its owned range once the decomposition knows it, every atom (filtered by tile) before
             const bool ranged = c->dd_on && c->dd_built;

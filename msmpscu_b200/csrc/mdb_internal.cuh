@@ -73,7 +73,7 @@ struct TiledState {
     TileParams P;
     bool ok = false, dirty = true, active = false;
     int G = 4;                 // lanes per atom
-    int ntx = 0, hcap = 0, ocap = 0, wmax = 0, lcap = 0, threads = 0, threads_opt = 768, grid = 0, nbuf = 2, stages_opt = 2;
+    int ntx = 0, hcap = 0, ocap = 0, wmax = 0, lpairs = 0, lcap = 0, threads = 0, threads_opt = 768, grid = 0, nbuf = 2, stages_opt = 2;
     int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0};
     double r2eff[2] = {0.0, 0.0};
     double r2eff_epot = 0.0; bool epot_in_class1 = false; // per-atom energy pass (PASS 3 of the tiled kernel)
