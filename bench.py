@@ -860,6 +860,12 @@ def c4_measure(args, nrep_total, cycles, md_steps):
     ctx.force(capi.FORCE)
     ctx.thermalize(600.0, 20240101 + disp.first, 0)
     ctx.run(0, 20, 1, MD_PER_PERIOD, H)
+    # warm-up of the event check: its device buffers (saved replicas, comparison work space) are allocated at first use, and a
+    # cudaMalloc right after another context of this process released several GB has been seen to take 0.3 s
+    ctx.state_save()
+    ctx.compare(xini, 0.03 * c.rr, nbox=disp.count)
+    ctx.state_restore()
+    ctx.sync()
     it = 20
     events = 0
     quench = []
