@@ -172,8 +172,9 @@ extern "C" void mdb_ctx_destroy(mdb_ctx *c)
 extern "C" int mdb_set_option(mdb_ctx *c, int option, int value)
 {
     if (!c) return MDB_ERR_ARG;
-    if (option == MDB_OPT_TILED_LANES && (value == 2 || value == 4 || value == 8)) {
-        c->tiled.G = value; c->tiled.dirty = true; c->list_valid = false;
+    if (option == MDB_OPT_TILED_LANES && (value == 0 || value == 2 || value == 4 || value == 8)) {
+        c->tiled.G_opt = value; if (value) c->tiled.G = value;
+        c->tiled.dirty = true; c->list_valid = false;
         return MDB_OK;
     }
     if (option == MDB_OPT_TILED_THREADS && (value == 512 || value == 768)) {

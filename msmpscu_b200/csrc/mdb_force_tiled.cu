@@ -1234,29 +1234,48 @@ int mdb_tiled_plan(mdb_ctx *c)
     // ---- tile geometry: the widest tile (fewest halo atoms staged per owned atom) whose two pipeline stages
     //      leave room for a table window that reaches down to 0.6 of the support edge's row (r ~ 0.36 r_eff;
     //      closer pairs read the tables from global memory)
-    const int G = S.G;
     const double rho_cell = (double)c->n / (double)c->nc;
     const bool mt = c->ng > 1;
     const int need = std::max(S.khi[0], S.khi[1]) + 1;
     const int minrows = std::min(need, std::max(512, (int)(0.4 * need)));
-    int best_w = 0;
     const int nbuf = (S.stages_opt == 3) ? 3 : 2;
-    for (int ntx = 1; ntx <= c->ncell[0] && !best_w; ntx++) {
-        const int wt = (c->ncell[0] + ntx - 1) / ntx;
-        if (wt > TILE_MAX_W) continue;
-        const int hcap = ((int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64 + 3) & ~3; // multiple of 4: see the dummy records of the passes
-        const int ocap = (((int)(wt * rho_cell * 1.25) + 32) + 7) & ~7;
-        if (hcap >= 16000) continue; // slots carry a 2-bit class tag while the list is built
-        const size_t fixed = TP_HDR_BYTES + nbuf * tp_buf_bytes(hcap, ocap, G, mt);
-        if (fixed + tp_tab_bytes(minrows) + 1024 > (size_t)SMEM_BUDGET) continue;
-        const int maxrows = (int)((SMEM_BUDGET - fixed - 1024) / 16) - 2;
-        best_w = wt;
-        S.ntx = ntx; S.hcap = hcap; S.ocap = ocap; S.nbuf = nbuf;
-        for (int p = 0; p < 2; p++) {
-            S.ktab[p] = std::min(S.khi[p] + 1, maxrows);
-            S.kmin[p] = S.khi[p] + 1 - S.ktab[p];
+    auto fit_tiles = [&](const int G) -> int { // tile width for G lanes per atom, 0: nothing fits
+        for (int ntx = 1; ntx <= c->ncell[0]; ntx++) {
+            const int wt = (c->ncell[0] + ntx - 1) / ntx;
+            if (wt > TILE_MAX_W) continue;
+            int hcap = ((int)(9.0 * (wt + 2) * rho_cell * 1.15) + 64 + 3) & ~3; // multiple of 4: see the dummy records of the passes
+            {   // a halo lies in one box and holds a cell at most once per wrap: never more atoms than the box has (small periodic
+                // boxes: the 27 halo cells of a 3 x 3 x 3-cell box ARE the box, 2001 atoms instead of the 2362 of the density estimate)
+                const long long wraps = (long long)((wt + 2 + c->ncell[0] - 1) / c->ncell[0]) * ((3 + c->ncell[1] - 1) / c->ncell[1]) *
+                                        ((3 + c->ncell[2] - 1) / c->ncell[2]);
+                const long long bound = (((long long)c->napb * wraps) + 3) & ~3LL;
+                if (bound < hcap) hcap = (int)bound;
+            }
+            const int ocap = (((int)(wt * rho_cell * 1.25) + 32) + 7) & ~7;
+            if (hcap >= 16000) continue; // slots carry a 2-bit class tag while the list is built
+            const size_t fixed = TP_HDR_BYTES + nbuf * tp_buf_bytes(hcap, ocap, G, mt);
+            if (fixed + tp_tab_bytes(minrows) + 1024 > (size_t)SMEM_BUDGET) continue;
+            const int maxrows = (int)((SMEM_BUDGET - fixed - 1024) / 16) - 2;
+            S.ntx = ntx; S.hcap = hcap; S.ocap = ocap; S.nbuf = nbuf;
+            for (int p = 0; p < 2; p++) {
+                S.ktab[p] = std::min(S.khi[p] + 1, maxrows);
+                S.kmin[p] = S.khi[p] + 1 - S.ktab[p];
+            }
+            return wt;
         }
+        return 0;
+    };
+    // lanes per atom: the option, or 4 -- and 8 where a tile owns so few atoms that chunks of 8 atoms (4 lanes each) leave most
+    // of the CTA's consumer warps without work (PARREP boxes: one 74-atom cell per tile = 10 chunks for 23 warps; ncu: 44 % of
+    // the stall samples were warps waiting at the next stage's barrier; 8 lanes: passes 0.112 / 0.142 -> 0.094 / 0.120 ms)
+    int G = S.G_opt ? S.G_opt : 4;
+    int best_w = fit_tiles(G);
+    if (!S.G_opt && best_w && best_w * rho_cell < 128.0) {
+        const int w8 = fit_tiles(8);
+        if (w8) { G = 8; best_w = w8; }
+        else best_w = fit_tiles(4);
     }
+    S.G = G;
     if (!best_w) return MDB_OK;
     if (S.threads_opt != 512 && S.threads_opt != 768) S.threads_opt = 768;
     S.threads = S.threads_opt;

@@ -72,7 +72,8 @@ struct TileParams {
 struct TiledState {
     TileParams P;
     bool ok = false, dirty = true, active = false;
-    int G = 4;                 // lanes per atom
+    int G = 4;                 // lanes per atom (set by mdb_tiled_plan)
+    int G_opt = 0;             // MDB_OPT_TILED_LANES: 2 / 4 / 8, 0 = the plan decides (4, or 8 for narrow tiles)
     int ntx = 0, hcap = 0, ocap = 0, wmax = 0, lpairs = 0, lcap = 0, threads = 0, threads_opt = 768, grid = 0, nbuf = 2, stages_opt = 2;
     int ktab[2] = {0, 0}, kmin[2] = {0, 0}, khi[2] = {0, 0};
     double r2eff[2] = {0.0, 0.0};

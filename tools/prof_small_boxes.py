@@ -60,6 +60,11 @@ if __name__ == "__main__":
     measure(c, "parrep %d x 2001" % nrep, epc_groups=2)
     if len(sys.argv) > 3 and sys.argv[3] == "quick":
         sys.exit(0)
+    if len(sys.argv) > 3 and sys.argv[3] == "lanes":
+        measure(c, "parrep %d x 2001, lanes 8" % nrep, epc_groups=2, opts=((capi.OPT_TILED_LANES, 8),))
+        measure(c, "parrep %d x 2001, lanes 8, 512 threads" % nrep, epc_groups=2, opts=((capi.OPT_TILED_LANES, 8), (capi.OPT_TILED_THREADS, 512)))
+        measure(c, "parrep %d x 2001, 512 threads" % nrep, epc_groups=2, opts=((capi.OPT_TILED_THREADS, 512),))
+        sys.exit(0)
     measure(c, "parrep %d x 2001, lanes 8" % nrep, epc_groups=2, opts=((capi.OPT_TILED_LANES, 8),))
     measure(c, "parrep %d x 2001, bank order on" % nrep, epc_groups=2, opts=((capi.OPT_TILED_BANKORDER, 1),))
     measure(c, "parrep %d x 2001, 512 threads" % nrep, epc_groups=2, opts=((capi.OPT_TILED_THREADS, 512),))
