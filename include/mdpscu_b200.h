@@ -389,7 +389,7 @@ int mdb_cg(mdb_ctx *ctx, int mxnumsteps, int meth, double maxdis, double mindis,
  *   TILED   shared-memory staged halo tiles (TMA producer warp + consumer warps), 16-bit slot lists
  * ---------------------------------------------------------------------------------- */
 #define MDB_OPT_FORCE_PATH    0
-#define MDB_OPT_TILED_LANES   1  /* lanes sharing one atom in the tiled kernels: 2, 4 or 8; 0 (default): 4, or 8 where a tile owns fewer than 128 atoms */
+#define MDB_OPT_TILED_LANES   1  /* lanes sharing one atom in the tiled kernels: 2, 4 or 8; 0 (default): 4, or 8 where a tile owns fewer than 96 atoms */
 #define MDB_OPT_TILED_CLASSES 2  /* 1 (default): scan only the distance classes a pass needs while safe; 0: all */
 #define MDB_OPT_ACTIVE_PATH   3  /* read-only: the path the last list build selected                            */
 #define MDB_OPT_TILED_THREADS 4  /* threads of the persistent pass CTA (one producer warp + consumers): 512 or 768 (default) */
