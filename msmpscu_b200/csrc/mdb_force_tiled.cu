@@ -8,14 +8,16 @@
 // Structure:
 //   tile        a run of cells along x in one cell row: owned atoms contiguous, halo = (Wt+2) x 3 x 3 cells = at most 27
 //               contiguous RUNS of the {x,y,z,den} record array.  k_tile_desc writes one descriptor per tile per rebuild.
-//   k_tile_nlist  one CTA per tile, two warps per owned cell (lanes = atoms); the halo is staged once as pairs of fp32
+//   k_tile_nlist  one CTA per tile, two warps per owned cell (lanes = atoms; several warp pairs share a cell of more than 32
+//               atoms when the tile is narrow, each taking 32-atom blocks in turn); the halo is staged once as pairs of fp32
 //               candidates, membership is the reference's fp32 expression (Cal_NeighboreList_Kernel2C,
 //               CommonGPU/MD_NeighborsList_GPU.F90:1097-1131), accepted 14-bit halo SLOTS + a 2-bit build-distance class go to
 //               a per-atom shared-memory column, which is partitioned by class (optionally dealt out by slot residue for
 //               conflict-free record reads, MDB_OPT_TILED_BANKORDER) and written as a lane-interleaved 16-bit list.
 //   k_tile_pass   one persistent CTA per SM, warp-specialised: a PRODUCER warp brings each tile's runs, first index group,
 //               STATU and scan counts into a 2-stage shared-memory pipeline with TMA bulk copies (cp.async.bulk + mbarrier);
-//               CONSUMER warps grab chunks of 32/G owned atoms from a shared counter and evaluate every listed entry
+//               (multi-type boxes: its lanes also copy the halo atoms' types, aligned int4 windows of ITYP, 8 in flight);
+//               CONSUMER warps grab chunks of 32/G owned atoms (G = 4, or 8 where a tile owns < 96 atoms) from a shared counter and evaluate every listed entry
 //               branch-free: fp64 separation from the staged records, exact r2 <= r_eff^2, MUFU.RSQ64H + Halley for 1/r and
 //               sqrt(r), table rows from a shared-memory window, masked accumulation, G-lane shuffle reduce.  No CTA-wide
 //               barrier anywhere.  PASS 1 density -> dF/drho, PASS 2 forces (VIR: + per-warp partial virial tensors),
