@@ -375,3 +375,75 @@ def test_fortran_binding_covers_the_whole_header():
                  "Initialize_ActiveRegion_DEV", "ActivateRegion_DEV", "Active_All_ActiveRegion_DEV", "DeActive_All_ActiveRegion_DEV",
                  "Do_ChangeDetect_DEV"):
         assert re.search(r"subroutine\s+%s\b" % proc, shims), "shim %s missing" % proc
+
+
+def _fortran_logical_lines(path):
+    """free-form source with comments removed and continuation lines joined"""
+    import re
+    out, buf = [], ""
+    for line in open(path).read().splitlines():
+        s = re.sub(r"!.*$", "", line).strip()
+        if s.startswith("&"):
+            s = s[1:]
+        if s.endswith("&"):
+            buf += s[:-1] + " "
+            continue
+        out.append(buf + s)
+        buf = ""
+    return out
+
+
+def test_fortran_shims_are_balanced_and_call_the_binding_with_its_arity():
+    """No Fortran compiler exists in this image (Oracle), so the shim layer is checked structurally: every
+    module / subroutine / function / interface / type / do / if-then / select block of fortran/*.F90 closes in order, and
+    every call of an mdb_* entry point in fortran/mdb_shims.F90 passes exactly as many arguments as its bind(C) interface in
+    fortran/mdb_c_binding.F90 declares (which test_fortran_binding_covers_the_whole_header ties to the C header)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    openers = (("module", r"^module\s+(?!procedure\b)\w+"), ("subroutine", r"^(pure\s+|elemental\s+|recursive\s+)*subroutine\s+\w+"),
+               ("function", r"^((integer|real|logical|character|type|double)\S*\s+)*function\s+\w+"), ("interface", r"^(abstract\s+)?interface\b"),
+               ("type", r"^type\s*(,|::|\s+[a-z])"), ("do", r"^(\w+\s*:\s*)?do\b"), ("if", r"^(\w+\s*:\s*)?if\s*\(.*\)\s*then$"),
+               ("select", r"^select\s+case"))
+    for name in ("mdb_shims.F90", "mdb_c_binding.F90"):
+        stack = []
+        for n, raw in enumerate(_fortran_logical_lines(os.path.join(root, "fortran", name))):
+            line = raw.strip().lower()
+            if not line:
+                continue
+            m = re.match(r"^end\s*(module|subroutine|function|interface|type|do|if|select)\b", line)
+            if m:
+                assert stack and stack[-1][0] == m.group(1), "%s: '%s' (logical line %d) closes %s" % (name, line, n, stack[-1:] or "nothing")
+                stack.pop()
+                continue
+            for kind, pat in openers:
+                if re.match(pat, line):
+                    stack.append((kind, n))
+                    break
+        assert not stack, "%s: unclosed %s" % (name, stack)
+    binding = "\n".join(_fortran_logical_lines(os.path.join(root, "fortran", "mdb_c_binding.F90")))
+    arity = {}
+    for m in re.finditer(r"(?:function|subroutine)\s+(mdb_\w+)\s*\(([^)]*)\)", binding, re.I):
+        arity[m.group(1).lower()] = len([a for a in m.group(2).split(",") if a.strip()])
+    assert len(arity) >= 85
+    shims = "\n".join(_fortran_logical_lines(os.path.join(root, "fortran", "mdb_shims.F90")))
+    checked = 0
+    for m in re.finditer(r"\b(mdb_\w+)\s*\(", shims):
+        name = m.group(1).lower()
+        if name not in arity:
+            continue
+        i, depth, nargs, empty = m.end(), 1, 1, True
+        while depth > 0 and i < len(shims):
+            ch = shims[i]
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                nargs += 1
+            elif not ch.isspace():
+                empty = False
+            i += 1
+        nargs = 0 if empty else nargs
+        assert nargs == arity[name], "%s called with %d arguments, its interface has %d: %s" % (name, nargs, arity[name], shims[m.start():i][:160])
+        checked += 1
+    assert checked >= 60
