@@ -562,13 +562,20 @@ def Do_DePhase(dev, SimBoxIni, SimBox, CtrlParamDephase, CtrlParamDamp=None, MAS
     n = SimBoxIni.NPRT
     fields = {name: dev.ctx.download(f, capi.ORDER_ORIGINAL) for name, f in
               (("XP", capi.F_XP), ("XP1", capi.F_XP1), ("DIS", capi.F_DIS), ("FP", capi.F_FP))}
+    return Pack_Replicas(boxes, fields, fb, n), fb
+
+
+def Pack_Replicas(boxes, fields, flag_box, n):
+    """The tail of Do_DePhase (Appshell/MD_Method_ParRep_GPU.F90:1078-1086): replicas whose flag is 0 are copied, in replica
+    order, to the front of the box array (IBF0 runs over the survivors); returns m_curReplicas.  `fields` maps an array name
+    of SimMDBox to the replica-major device download (nbox * n rows)."""
     ibf0 = 0
     for ib in range(len(boxes)):
-        if fb[ib] == 0:
+        if flag_box[ib] == 0:
             for name, a in fields.items():
                 getattr(boxes[ibf0], name)[:] = a[ib * n:(ib + 1) * n]
             ibf0 += 1
-    return ibf0, fb
+    return ibf0
 
 
 def Transition_Replicas(Flag, NPRT):

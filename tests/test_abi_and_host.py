@@ -447,3 +447,19 @@ def test_fortran_shims_are_balanced_and_call_the_binding_with_its_arity():
         assert nargs == arity[name], "%s called with %d arguments, its interface has %d: %s" % (name, nargs, arity[name], shims[m.start():i][:160])
         checked += 1
     assert checked >= 60
+
+
+def test_dephase_packs_the_surviving_replicas_in_order():
+    """Pack_Replicas = the tail of Do_DePhase (Appshell/MD_Method_ParRep_GPU.F90:1078-1086): replicas 1 and 3 of four left the basin,
+    so replicas 0 and 2 end up in boxes 0 and 1 and m_curReplicas = 2; the boxes behind keep what they held."""
+    from types import SimpleNamespace
+    from msmpscu_b200 import mdlib
+    n, nb = 5, 4
+    boxes = [SimpleNamespace(XP=np.full((n, 3), -1.0 - b), XP1=np.full((n, 3), -10.0 - b)) for b in range(nb)]
+    xp = np.concatenate([np.full((n, 3), float(b)) for b in range(nb)])
+    fields = {"XP": xp, "XP1": 10.0 * xp}
+    assert mdlib.Pack_Replicas(boxes, fields, np.array([0, 1, 0, 1]), n) == 2
+    assert np.all(boxes[0].XP == 0.0) and np.all(boxes[1].XP == 2.0) and np.all(boxes[1].XP1 == 20.0)
+    assert np.all(boxes[2].XP == -3.0) and np.all(boxes[3].XP1 == -13.0)
+    assert mdlib.Pack_Replicas(boxes, fields, np.ones(nb, dtype=int), n) == 0
+    assert mdlib.Pack_Replicas(boxes, fields, np.zeros(nb, dtype=int), n) == nb and np.all(boxes[3].XP == 3.0)
